@@ -1,0 +1,340 @@
+// TEST INFRASTRUCTURE ONLY -- part of oracle/, never linked into the product.
+//
+// C-ABI driver around the UNMODIFIED reference sources (compiled from
+// /root/reference/src/triumvirate/src by oracle/Makefile into
+// oracle/_ref/libtrv_ref.so).  It lets the Python tests and bench.py's
+// cpu_baseline / --impl reference legs call the reference's own
+// implementation of the hot path:
+//   trv::compute_bispec / compute_3pcf / compute_bispec_in_gpp_box /
+//   compute_3pcf_in_gpp_box                 (S/threept.cpp:248,1014,1473,2190)
+//   trv::MeshField assignment / FFT / compensation (S/field.cpp:569-1785)
+//   trv::calc_bispec_normalisation_from_{particles,mesh} (S/threept.cpp:96,138)
+//   trv::maths calculators                  (S/maths.cpp:167-375)
+// Nothing here re-implements reference logic: it only marshals arrays.
+
+#include <chrono>
+#include <complex>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "dataobjs.hpp"
+#include "field.hpp"
+#include "maths.hpp"
+#include "monitor.hpp"
+#include "parameters.hpp"
+#include "particles.hpp"
+#include "threept.hpp"
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+thread_local std::string g_err;
+
+void load_catalogue(
+  trv::ParticleCatalogue& cat, int n,
+  const double* x, const double* y, const double* z,
+  const double* nz, const double* ws, const double* wc
+) {
+  std::vector<double> vx(x, x + n), vy(y, y + n), vz(z, z + n);
+  std::vector<double> vnz(n, 0.), vws(n, 1.), vwc(n, 1.);
+  if (nz) vnz.assign(nz, nz + n);
+  if (ws) vws.assign(ws, ws + n);
+  if (wc) vwc.assign(wc, wc + n);
+  cat.load_particle_data(vx, vy, vz, vnz, vws, vwc);
+}
+
+void fill_params(
+  trv::ParameterSet& params,
+  const char* catalogue_type, const char* statistic_type,
+  const double boxsize[3], const int ngrid[3], const char* assignment,
+  int ell1, int ell2, int ELL, const char* form, int idx_bin,
+  const char* binning, double bin_min, double bin_max, int num_bins,
+  int interlace_after_validate, int verbose
+) {
+  params.catalogue_type = catalogue_type;
+  params.statistic_type = statistic_type;
+  for (int i = 0; i < 3; i++) {
+    params.boxsize[i] = boxsize[i];
+    params.ngrid[i] = ngrid[i];
+  }
+  params.alignment = "centre";
+  params.padscale = "box";
+  params.assignment = assignment;
+  params.interlace = "false";
+  params.ell1 = ell1; params.ell2 = ell2; params.ELL = ELL;
+  params.form = form;
+  params.idx_bin = idx_bin;
+  params.norm_convention = "particle";
+  params.binning = binning;
+  params.bin_min = bin_min; params.bin_max = bin_max;
+  params.num_bins = num_bins;
+  params.fftw_scheme = "estimate";
+  params.use_fftw_wisdom = "false";
+  params.verbose = verbose;
+  params.progbar = "false";
+  params.validate(false);
+  // Interlacing is forced off by validate() for three-point statistics
+  // (S/parameters.cpp:1240-1249); the interlaced MeshField paths are only
+  // reachable by poking the public member afterwards.
+  if (interlace_after_validate) params.interlace = "true";
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* trvref_last_error() { return g_err.c_str(); }
+
+int trvref_num_threads() {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+void trvref_set_num_threads(int n) {
+#ifdef _OPENMP
+  omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
+// Three-point estimator.  `stat` = "bispec" | "3pcf"; `catalogue_type` =
+// "sim" (periodic box, global plane-parallel) | "survey" (data + randoms,
+// local plane-parallel; `los_*` are n x 3 row-major unit vectors).
+// Output arrays must hold at least dv_dim entries (raw/shot: 2 * dv_dim).
+int trvref_threept(
+  const char* stat, const char* catalogue_type,
+  int nd, const double* xd, const double* yd, const double* zd,
+  const double* nzd, const double* wsd, const double* wcd, const double* los_d,
+  int nr, const double* xr, const double* yr, const double* zr,
+  const double* nzr, const double* wsr, const double* wcr, const double* los_r,
+  const double* boxsize, const int* ngrid, const char* assignment,
+  int ell1, int ell2, int ELL, const char* form, int idx_bin,
+  const char* binning, double bin_min, double bin_max, int num_bins,
+  int interlace_after_validate, double norm_factor, int verbose,
+  int* dim, double* c1_bin, double* c2_bin, double* c1_eff, double* c2_eff,
+  int* n1, int* n2, double* raw, double* shot, double* elapsed_s
+) {
+  try {
+    trv::ParameterSet params;
+    fill_params(
+      params, catalogue_type, stat, boxsize, ngrid, assignment,
+      ell1, ell2, ELL, form, idx_bin, binning, bin_min, bin_max, num_bins,
+      interlace_after_validate, verbose
+    );
+    trv::Binning bins(params);
+    bins.set_bins();
+
+    trv::ParticleCatalogue data(verbose), rand(verbose);
+    load_catalogue(data, nd, xd, yd, zd, nzd, wsd, wcd);
+    const bool survey = std::string(catalogue_type) == "survey";
+    if (survey) load_catalogue(rand, nr, xr, yr, zr, nzr, wsr, wcr);
+
+    const bool is_bispec = std::string(stat) == "bispec";
+    auto t0 = std::chrono::steady_clock::now();
+    if (is_bispec) {
+      trv::BispecMeasurements out = survey
+        ? trv::compute_bispec(
+            data, rand, (trv::LineOfSight*)los_d, (trv::LineOfSight*)los_r,
+            params, bins, norm_factor)
+        : trv::compute_bispec_in_gpp_box(data, params, bins, norm_factor);
+      auto t1 = std::chrono::steady_clock::now();
+      if (elapsed_s) *elapsed_s = std::chrono::duration<double>(t1 - t0).count();
+      *dim = out.dim;
+      for (int i = 0; i < out.dim; i++) {
+        c1_bin[i] = out.k1_bin[i]; c2_bin[i] = out.k2_bin[i];
+        c1_eff[i] = out.k1_eff[i]; c2_eff[i] = out.k2_eff[i];
+        n1[i] = out.nmodes_1[i]; n2[i] = out.nmodes_2[i];
+        raw[2*i] = out.bk_raw[i].real(); raw[2*i+1] = out.bk_raw[i].imag();
+        shot[2*i] = out.bk_shot[i].real(); shot[2*i+1] = out.bk_shot[i].imag();
+      }
+    } else {
+      trv::ThreePCFMeasurements out = survey
+        ? trv::compute_3pcf(
+            data, rand, (trv::LineOfSight*)los_d, (trv::LineOfSight*)los_r,
+            params, bins, norm_factor)
+        : trv::compute_3pcf_in_gpp_box(data, params, bins, norm_factor);
+      auto t1 = std::chrono::steady_clock::now();
+      if (elapsed_s) *elapsed_s = std::chrono::duration<double>(t1 - t0).count();
+      *dim = out.dim;
+      for (int i = 0; i < out.dim; i++) {
+        c1_bin[i] = out.r1_bin[i]; c2_bin[i] = out.r2_bin[i];
+        c1_eff[i] = out.r1_eff[i]; c2_eff[i] = out.r2_eff[i];
+        n1[i] = out.npairs_1[i]; n2[i] = out.npairs_2[i];
+        raw[2*i] = out.zeta_raw[i].real(); raw[2*i+1] = out.zeta_raw[i].imag();
+        shot[2*i] = out.zeta_shot[i].real(); shot[2*i+1] = out.zeta_shot[i].imag();
+      }
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+
+// Normalisation factors (S/threept.cpp:96-149).
+int trvref_norm(
+  int from_mesh, int n, const double* x, const double* y, const double* z,
+  const double* nz, const double* ws, const double* wc, double alpha,
+  const double* boxsize, const int* ngrid, const char* assignment,
+  double* norm
+) {
+  try {
+    trv::ParticleCatalogue cat(60);
+    load_catalogue(cat, n, x, y, z, nz, ws, wc);
+    if (from_mesh) {
+      trv::ParameterSet params;
+      fill_params(params, "sim", "bispec", boxsize, ngrid, assignment,
+                  0, 0, 0, "diag", 0, "lin", 0.005, 0.105, 4, 0, 60);
+      *norm = trv::calc_bispec_normalisation_from_mesh(cat, params, alpha);
+    } else {
+      *norm = trv::calc_bispec_normalisation_from_particles(cat, alpha);
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+
+// Mesh pipeline for intermediate parity checks.  `stage`:
+//   0  assignment only (complex weights w_re/w_im; NULL -> unit weights)
+//   1  + fourier_transform()                       (S/field.cpp:1496)
+//   2  + apply_assignment_compensation()           (S/field.cpp:1764)
+//   3  + inv_fourier_transform()                   (S/field.cpp:1657)
+// `subtract_mean` applies compute_unweighted_field_fluctuations_insitu's
+// `field.re -= N/V` after assignment (S/field.cpp:1235-1243).
+// `field_out` receives 2*nmesh doubles (re, im interleaved).
+int trvref_mesh(
+  int stage, int subtract_mean, int interlace,
+  int n, const double* x, const double* y, const double* z,
+  const double* w_re, const double* w_im,
+  const double* boxsize, const int* ngrid, const char* assignment,
+  double* field_out, double* elapsed_assign_s
+) {
+  try {
+    trv::ParameterSet params;
+    fill_params(params, "sim", "bispec", boxsize, ngrid, assignment,
+                0, 0, 0, "diag", 0, "lin", 0.005, 0.105, 4, interlace, 60);
+    trv::ParticleCatalogue cat(60);
+    load_catalogue(cat, n, x, y, z, nullptr, nullptr, nullptr);
+    trv::MeshField mesh(params, true, "`oracle_mesh`");
+    fftw_complex* weights = fftw_alloc_complex(n);
+    for (int i = 0; i < n; i++) {
+      weights[i][0] = w_re ? w_re[i] : 1.;
+      weights[i][1] = w_im ? w_im[i] : 0.;
+    }
+    auto t0 = std::chrono::steady_clock::now();
+    mesh.assign_weighted_field_to_mesh(cat, weights);
+    auto t1 = std::chrono::steady_clock::now();
+    if (elapsed_assign_s)
+      *elapsed_assign_s = std::chrono::duration<double>(t1 - t0).count();
+    fftw_free(weights);
+    if (subtract_mean) {
+      double nbar = double(cat.ntotal) / mesh.vol;
+      for (long long g = 0; g < params.nmesh; g++) mesh.field[g][0] -= nbar;
+    }
+    if (stage >= 1) mesh.fourier_transform();
+    if (stage >= 2) mesh.apply_assignment_compensation();
+    if (stage >= 3) mesh.inv_fourier_transform();
+    std::memcpy(field_out, mesh.field, sizeof(fftw_complex) * params.nmesh);
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+
+// Calculators (S/maths.cpp).
+void trvref_ylm(int ell, int m, const double* pos, int n, double* out) {
+  for (int i = 0; i < n; i++) {
+    double p[3] = {pos[3*i], pos[3*i+1], pos[3*i+2]};
+    std::complex<double> y = trv::maths::SphericalHarmonicCalculator::
+      calc_reduced_spherical_harmonic(ell, m, p);
+    out[2*i] = y.real(); out[2*i+1] = y.imag();
+  }
+}
+
+void trvref_sjl(int ell, const double* x, int n, double* out) {
+  trv::maths::SphericalBesselCalculator sj(ell);
+  for (int i = 0; i < n; i++) out[i] = sj.eval(x[i]);
+}
+
+double trvref_w3j(int j1, int j2, int j3, int m1, int m2, int m3) {
+  return trv::maths::wigner_3j(j1, j2, j3, m1, m2, m3);
+}
+
+double trvref_coupling(int l1, int l2, int L, int m1, int m2, int M) {
+  return trv::calc_coupling_coeff_3pt(l1, l2, L, m1, m2, M);
+}
+
+// Binning (S/dataobjs.cpp:134-249): edges[nb+1], centres[nb], widths[nb].
+int trvref_binning(
+  const char* space, const char* scheme, double bmin, double bmax, int nb,
+  const double* boxsize, const int* ngrid,
+  double* edges, double* centres, double* widths
+) {
+  try {
+    trv::ParameterSet params;
+    for (int i = 0; i < 3; i++) {
+      params.boxsize[i] = boxsize[i]; params.ngrid[i] = ngrid[i];
+    }
+    params.space = space; params.binning = scheme;
+    params.bin_min = bmin; params.bin_max = bmax; params.num_bins = nb;
+    trv::Binning b(params);
+    b.set_bins();
+    for (int i = 0; i <= nb; i++) edges[i] = b.bin_edges[i];
+    for (int i = 0; i < nb; i++) {
+      centres[i] = b.bin_centres[i]; widths[i] = b.bin_widths[i];
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+
+// ParameterSet::validate derivations (S/parameters.cpp:466-1270).
+int trvref_validate(
+  const char* catalogue_type, const char* statistic_type,
+  const char* assignment, const char* interlace, const char* form,
+  int ell1, int ell2, int ELL, int num_bins, int idx_bin,
+  double bin_min, double bin_max,
+  char* shape_out, char* interlace_out, char* npoint_out, char* space_out,
+  int* assignment_order
+) {
+  try {
+    trv::ParameterSet params;
+    params.catalogue_type = catalogue_type;
+    params.statistic_type = statistic_type;
+    params.boxsize[0] = params.boxsize[1] = params.boxsize[2] = 1000.;
+    params.ngrid[0] = params.ngrid[1] = params.ngrid[2] = 64;
+    params.assignment = assignment;
+    params.interlace = interlace;
+    params.form = form;
+    params.ell1 = ell1; params.ell2 = ell2; params.ELL = ELL;
+    params.num_bins = num_bins; params.idx_bin = idx_bin;
+    params.bin_min = bin_min; params.bin_max = bin_max;
+    params.verbose = 60;
+    params.fftw_scheme = "estimate";
+    params.validate(false);
+    std::strcpy(shape_out, params.shape.c_str());
+    std::strcpy(interlace_out, params.interlace.c_str());
+    std::strcpy(npoint_out, params.npoint.c_str());
+    std::strcpy(space_out, params.space.c_str());
+    *assignment_order = params.assignment_order;
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+
+}  // extern "C"
