@@ -1,0 +1,225 @@
+/* trvb.h -- C-ABI device layer of triumvirate_b200 (libtrvb.so).
+ *
+ * The reference (MikeSWang/Triumvirate) has no C ABI: its bindings link the
+ * C++ headers directly.  This header is the layer the
+ * B200 build inserts UNDER the reference's C++ surface: every function takes
+ * plain pointers and sizes only, returns an int status (0 = ok) and records a
+ * message retrievable with trvb_last_error().  The host-side C++ classes in
+ * triumvirate_b200/include/trv/ (trv::MeshField, trv::FieldStats,
+ * trv::compute_bispec*, trv::compute_3pcf*) are thin callers of these.
+ *
+ * Each entry point cites the reference code it replaces (paths relative to
+ * /root/reference/src/triumvirate/, S/ = src/, I/ = include/).
+ *
+ * Conventions
+ *  - All arithmetic is IEEE fp64.  Complex values are interleaved (re, im).
+ *  - A "mesh" is row-major [n0][n1][n2], x slowest (S/field.cpp:533-538).
+ *  - trvb_mesh describes one device buffer:
+ *      TRVB_REAL     n0*n1*n2 doubles                 (configuration space)
+ *      TRVB_COMPLEX  n0*n1*n2 complex                 (either space)
+ *      TRVB_HALF     n0*n1*(n2/2+1) complex           (Fourier space of a
+ *                    real field; the missing half is implied by Hermitian
+ *                    symmetry and reconstructed on access)
+ *  - Device pointers are ordinary CUDA device addresses (cudaMalloc'ed by
+ *    trvb_malloc, or e.g. a torch tensor's data_ptr()).
+ *  - Work is enqueued on the context's stream; functions that return results
+ *    to host memory synchronise that stream before returning.
+ */
+#ifndef TRVB_H_INCLUDED_
+#define TRVB_H_INCLUDED_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct trvb_ctx trvb_ctx;   /* grid + box + plans + tables, one GPU */
+typedef struct trvb_cat trvb_cat;   /* device-resident particle catalogue   */
+
+enum { TRVB_REAL = 0, TRVB_COMPLEX = 1, TRVB_HALF = 2 };
+
+typedef struct {
+  void* data;   /* device pointer */
+  int layout;   /* TRVB_REAL | TRVB_COMPLEX | TRVB_HALF */
+} trvb_mesh;
+
+/* Particle weight kinds for assignment / catalogue sums. */
+enum {
+  TRVB_W_UNIT = 0,      /* 1               S/field.cpp:1208-1227            */
+  TRVB_W_W = 1,         /* w               S/field.cpp:2033-2036            */
+  TRVB_W_YLM_W = 2,     /* y_LM(los) w     S/field.cpp:1259-1269            */
+  TRVB_W_CYLM_W2 = 3,   /* conj(y_LM) w^2  S/field.cpp:1379-1391            */
+  TRVB_W_YLM_W3 = 4,    /* y_LM(los) w^3   S/threept.cpp:156-236 (sums only)*/
+  TRVB_W_CUSTOM = 5     /* caller-supplied complex weights
+                           (fftw_complex* weights, S/field.cpp:569-571)     */
+};
+
+/* ---- status ---------------------------------------------------------- */
+const char* trvb_last_error(void);
+const char* trvb_version(void);
+/* Number of visible CUDA devices (0 when none / no driver); replaces the
+ * probe of S/monitor.cpp:258-282. */
+int trvb_device_count(void);
+/* Number of kernel launches issued by this library since the last reset. */
+long long trvb_launch_count(void);
+void trvb_launch_count_reset(void);
+
+/* ---- context: replaces MeshField/FieldStats ctor state ----------------
+ * (S/field.cpp:45-365: dr, dk, vol, vol_cell, FFT plans; S/field.cpp:2076).
+ * assignment_order: 1 ngp, 2 cic, 3 tsc, 4 pcs (S/parameters.cpp:659-683). */
+int trvb_ctx_create(trvb_ctx** ctx, int device, const int ngrid[3],
+                    const double boxsize[3], int assignment_order);
+void trvb_ctx_destroy(trvb_ctx* ctx);
+int trvb_ctx_sync(trvb_ctx* ctx);
+void* trvb_ctx_stream(trvb_ctx* ctx);          /* cudaStream_t */
+long long trvb_ctx_nmesh(const trvb_ctx* ctx);
+/* Bytes of a mesh buffer in the given layout. */
+size_t trvb_mesh_bytes(const trvb_ctx* ctx, int layout);
+
+/* ---- memory (replaces S/arrayops.cpp:273-343 H2D/D2H helpers) ---------- */
+int trvb_mem_info(trvb_ctx* ctx, size_t* free_bytes, size_t* total_bytes);
+int trvb_malloc(trvb_ctx* ctx, void** dptr, size_t bytes);
+int trvb_free(trvb_ctx* ctx, void* dptr);
+int trvb_memset0(trvb_ctx* ctx, void* dptr, size_t bytes);
+int trvb_h2d(trvb_ctx* ctx, void* dptr, const void* hptr, size_t bytes);
+int trvb_d2h(trvb_ctx* ctx, void* hptr, const void* dptr, size_t bytes);
+int trvb_d2d(trvb_ctx* ctx, void* dst, const void* src, size_t bytes);
+
+/* ---- catalogue (replaces I/particles.hpp:63-90 on the device) ----------
+ * Host (or device, if src_on_device) arrays of length n; `w` may be NULL
+ * (unit weights), `los` is n x 3 row-major unit vectors or NULL
+ * (I/dataobjs.hpp:186-188).  Positions must already be aligned in the box. */
+int trvb_cat_create(trvb_ctx* ctx, trvb_cat** cat, long long n,
+                    const double* x, const double* y, const double* z,
+                    const double* w, const double* los, int src_on_device);
+/* Same from the reference's AoS layout: 7 doubles per particle
+ * {x, y, z, nz, ws, wc, w} (I/particles.hpp:63-69). */
+int trvb_cat_create_aos(trvb_ctx* ctx, trvb_cat** cat, long long n,
+                        const double* pdata, const double* los);
+/* Attach caller-supplied complex weights (n interleaved (re, im) pairs, host
+ * memory) for TRVB_W_CUSTOM. */
+int trvb_cat_set_custom_weights(trvb_ctx* ctx, trvb_cat* cat,
+                                const double* weights);
+void trvb_cat_destroy(trvb_cat* cat);
+long long trvb_cat_size(const trvb_cat* cat);
+/* sum_i weight(kind, L, M)_i, complex, e.g. Sbar_LM (S/threept.cpp:156-236). */
+int trvb_cat_sum(trvb_ctx* ctx, trvb_cat* cat, int kind, int L, int M,
+                 double out[2]);
+
+/* ---- mesh assignment (replaces S/field.cpp:569-1112) -------------------
+ * Scatter `scale * weight(kind, L, M)_i * Wx Wy Wz` (times 1/vol_cell when
+ * density_units != 0, exactly `inv_vol_cell*w*Wx*Wy*Wz` as S/field.cpp:1044)
+ * into `mesh` (TRVB_REAL allowed only for real-valued weight kinds, else
+ * TRVB_COMPLEX).  accumulate == 0 zero-fills first (reset_density_field).
+ * shifted != 0 assigns on the half-cell-shifted shadow mesh
+ * (S/field.cpp:1056-1111).  mode: 0 = throughput (cell-sorted, atomics),
+ * 1 = deterministic (per-cell ascending particle order, no FMA; bit-exact
+ * against the reference run single-threaded). */
+int trvb_assign(trvb_ctx* ctx, trvb_cat* cat, int kind, int L, int M,
+                double scale, int density_units, int accumulate, int shifted,
+                int mode, trvb_mesh mesh);
+
+/* mesh.re += c   (S/field.cpp:1235-1243 with c = -N/V). */
+int trvb_mesh_add_const(trvb_ctx* ctx, trvb_mesh mesh, double c);
+/* dst = a*dst + b*src, elementwise over same-layout meshes
+ * (S/field.cpp:1309-1312, 1433-1436, 1358-1361). */
+int trvb_mesh_axpby(trvb_ctx* ctx, trvb_mesh dst, double a, trvb_mesh src,
+                    double b);
+/* sum_x Re(mesh)^3 (S/field.cpp:2056-2058). */
+int trvb_mesh_sum_pow3(trvb_ctx* ctx, trvb_mesh mesh, double* out);
+
+/* ---- transforms (replace S/field.cpp:1496-1720) ------------------------
+ * Forward: dst(k) = FFT[prescale * src(x)] (sign -1, unnormalised).
+ *   src TRVB_REAL  -> dst TRVB_HALF (out of place)
+ *   src TRVB_COMPLEX -> dst TRVB_COMPLEX (in place when dst.data==src.data)
+ * Inverse: dst(x) = IFFT[src(k)] (sign +1, unnormalised), HALF -> REAL or
+ * COMPLEX -> COMPLEX.  The HALF source is overwritten by cuFFT's Z2D. */
+int trvb_fft_forward(trvb_ctx* ctx, trvb_mesh src, trvb_mesh dst,
+                     double prescale);
+int trvb_fft_inverse(trvb_ctx* ctx, trvb_mesh src, trvb_mesh dst);
+/* field(k) += add at the k = 0 mode (mean subtraction done in Fourier
+ * space: FFT of a constant only populates k = 0). */
+int trvb_kmesh_add_zero_mode(trvb_ctx* ctx, trvb_mesh kmesh, double add_re);
+/* f = (f + exp(+i pi (mx+my+mz)) f_s)/2  (S/field.cpp:1618-1653). */
+int trvb_interlace_combine(trvb_ctx* ctx, trvb_mesh kmesh, trvb_mesh kmesh_s);
+/* f /= W(k), W = prod_i sinc(pi m_i/n_i)^order (S/field.cpp:1114-1201,
+ * 1764-1785). */
+int trvb_compensate(trvb_ctx* ctx, trvb_mesh kmesh);
+
+/* ---- sub-grid ("shell grid") ------------------------------------------
+ * The shell fields F_b(x) and the band-limited part of G(x) that enter
+ * sum_x F_a F_b G (S/threept.cpp:1708-1717) only involve Fourier modes with
+ * |m_i| <= mcut; the sum over the n^3 mesh equals (n^3/ns^3) times the sum
+ * over an ns^3 mesh whenever ns > 4*mcut (no aliasing of the triple product),
+ * or ns = n.  A sub-grid context shares the parent's box and tables. */
+int trvb_subgrid_create(trvb_ctx* parent, trvb_ctx** sub, const int nsub[3]);
+
+/* Number of modes and sum of |k| per shell [edges[b], edges[b+1]), all bins
+ * in one pass (the k_eff / nmodes side of S/field.cpp:1815-1847).  `fine`
+ * != 0 applies the two-stage rule of S/field.cpp:2619,2674-2676 instead
+ * (mode -> fine bin int(|k|/1e-5); fine bin q in shell iff edge_lo <= q*1e-5
+ * < edge_hi). */
+int trvb_shell_stats(trvb_ctx* ctx, const double* edges, int nbins, int fine,
+                     long long* nmodes, double* ksum);
+
+/* dst(x) = IFFT on `sub`'s grid of
+ *   amp * 1{klo <= |k| < khi} * y_lm(khat) * src(k) / W(k)
+ * (S/field.cpp:1792-1906 with amp = 1/nmodes folded in; src lives on the
+ * parent grid `ctx`, dst is a TRVB_COMPLEX mesh of `sub`).  klo < 0 and
+ * khi < 0 disable the shell test (all modes representable on `sub`):
+ * with l = m = 0 and amp = 1/V this is G(x) (S/field.cpp:1764-1785,1657). */
+int trvb_shell_ifft(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh src, int ell,
+                    int m, double klo, double khi, double amp, trvb_mesh dst);
+
+/* dst(x) = IFFT[ amp * j_l(|k| r) * y_lm(khat) * src(k) / W(k) ]
+ * (S/field.cpp:1908-2010, amp = 1/V), spline table from trvb_sjl_table. */
+int trvb_sjl_ifft(trvb_ctx* ctx, trvb_mesh src, int ell, int m, double r,
+                  double amp, trvb_mesh dst);
+/* Upload the natural-cubic-spline table of j_ell (I/maths.hpp:305-306,
+ * S/maths.cpp:309-375): knots x_i = step*i, values y[i], coefficients c[i],
+ * i < nsample; beyond split = step*(nsample-1) j_ell is evaluated directly. */
+int trvb_sjl_table(trvb_ctx* ctx, int ell, const double* y, const double* c,
+                   int nsample, double step);
+
+/* ---- reductions -------------------------------------------------------
+ * out[p] = sum_x A[ia[p]](x) * B[ib[p]](x) * G(x), complex, for p < npairs
+ * (S/threept.cpp:1708-1717 and clones, all pairs in one pass over x).
+ * A, B: arrays of na / nb device pointers to TRVB_COMPLEX meshes of `ctx`. */
+int trvb_gram_reduce(trvb_ctx* ctx, const void* const* A, int na,
+                     const void* const* B, int nb, trvb_mesh G,
+                     const int* ia, const int* ib, int npairs, double* out);
+
+/* Binned pseudo-2pt statistics in Fourier space with the fine-bin rule
+ * (S/field.cpp:2511-2703): per bin nmodes, mean |k|, mean
+ * y_lm fa conj(fb)/C1 and mean y_lm S (C1/C1).  Empty bins follow
+ * S/field.cpp:2688-2692 (k = centre, pk = sn = 0). */
+int trvb_twopt_fourier(trvb_ctx* ctx, trvb_mesh fa, trvb_mesh fb,
+                       const double S[2], int ell, int m, const double* edges,
+                       const double* centres, int nbins, long long* nmodes,
+                       double* k, double* pk, double* sn);
+
+/* xi(x) = IFFT[ (fa conj(fb)/C1 - S C1/C1) / V ]  (S/field.cpp:3273-3345,
+ * 3018-3090); dst TRVB_COMPLEX on the same grid. */
+int trvb_shot_xi(trvb_ctx* ctx, trvb_mesh fa, trvb_mesh fb, const double S[2],
+                 trvb_mesh dst);
+
+/* out[p] = vol_cell * sum_x j_la(ka[p] |x|) j_lb(kb[p] |x|) y_la,ma(xhat)
+ * y_lb,mb(xhat) xi(x)   (S/field.cpp:3362-3393), all pairs in one pass. */
+int trvb_shot_bispec_reduce(trvb_ctx* ctx, trvb_mesh xi, int la, int ma,
+                            int lb, int mb, const double* ka, const double* kb,
+                            int npairs, double* out);
+
+/* Radially binned y_a y_b xi(x) with the fine-bin rule, dr_sample = 1
+ * (S/field.cpp:3092-3189): per bin npairs, mean |x| and the doubly
+ * normalised xi.  parity = (-1)^(l1+l2) (S/field.cpp:3181). */
+int trvb_shot_3pcf_bin(trvb_ctx* ctx, trvb_mesh xi, int la, int ma, int lb,
+                       int mb, const double* edges, const double* centres,
+                       int nbins, double parity, long long* npairs, double* r,
+                       double* xi_out);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif  /* TRVB_H_INCLUDED_ */

@@ -1,0 +1,780 @@
+// trvb_assign.cu -- device-resident catalogue, cell sort and particle-to-mesh
+// assignment (NGP/CIC/TSC/PCS, optional half-cell shift) for libtrvb.so.
+//
+// Replaces the OpenMP scatter loops of S/field.cpp:618-1112 and the weight
+// kernels of S/field.cpp:1259-1269,1379-1391.  Two modes:
+//   throughput     particles are counting-sorted by 4^3-cell tile so that a
+//                  warp's red.global.add.f64 traffic stays inside a few cache
+//                  lines of L2; one thread per particle, p^3 REDs each.
+//   deterministic  particles are counting-sorted by home cell with ascending
+//                  particle id inside a cell; one thread per OUTPUT cell
+//                  gathers its contributions and adds them in ascending
+//                  particle order with non-contracted IEEE operations, i.e.
+//                  the single-threaded reference order => bit-identical mesh.
+#include "trvb_common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------
+// Window functions: the exact operation sequence of S/field.cpp.
+// ---------------------------------------------------------------------
+
+// loc_grid = ngrid * pos / boxsize (+0.5 and wrap for the shadow mesh),
+// S/field.cpp:643-644, 689-694.
+__device__ __forceinline__ double grid_loc(double pos, int n, double L, int shifted) {
+  double loc = __ddiv_rn(__dmul_rn((double)n, pos), L);
+  if (shifted) {
+    loc = __dadd_rn(loc, 0.5);
+    if (loc > (double)n) loc = __dsub_rn(loc, (double)n);
+  }
+  return loc;
+}
+
+template <int ORDER>
+__device__ __forceinline__ void window_1d(double loc, int n, int* ijk, double* win);
+
+// NGP, S/field.cpp:646-655.
+template <>
+__device__ __forceinline__ void window_1d<1>(double loc, int n, int* ijk, double* win) {
+  int idx = __double2int_rz(loc);
+  if (__dsub_rn(loc, (double)idx) >= 0.5) idx = (idx == n - 1) ? 0 : idx + 1;
+  ijk[0] = idx;
+  win[0] = 1.;
+}
+
+// CIC, S/field.cpp:756-766.
+template <>
+__device__ __forceinline__ void window_1d<2>(double loc, int n, int* ijk, double* win) {
+  int idx = __double2int_rz(loc);
+  ijk[0] = idx;
+  ijk[1] = (idx == n - 1) ? 0 : idx + 1;
+  double s = __dsub_rn(loc, (double)idx);
+  win[0] = __dsub_rn(1., s);
+  win[1] = s;
+}
+
+// TSC, S/field.cpp:867-895.  (The shadow-mesh variant at S/field.cpp:944-950
+// indexes out of range near the upper edge -- SURVEY.md F5b; the periodic wrap
+// of the primary mesh is used for both here.)
+template <>
+__device__ __forceinline__ void window_1d<3>(double loc, int n, int* ijk, double* win) {
+  int idx = __double2int_rz(loc);
+  double s = __dsub_rn(loc, (double)idx);
+  if (s < 0.5) {
+    ijk[0] = (idx == 0) ? n - 1 : idx - 1;
+    ijk[1] = idx;
+    ijk[2] = (idx == n - 1) ? 0 : idx + 1;
+    double a = __dsub_rn(0.5, s), b = __dadd_rn(0.5, s);
+    win[0] = __dmul_rn(__dmul_rn(0.5, a), a);
+    win[1] = __dsub_rn(0.75, __dmul_rn(s, s));
+    win[2] = __dmul_rn(__dmul_rn(0.5, b), b);
+  } else {
+    ijk[0] = idx;
+    ijk[1] = (idx == n - 1) ? 0 : idx + 1;
+    ijk[2] = (ijk[1] == n - 1) ? 0 : ijk[1] + 1;
+    s = __dsub_rn(1., s);
+    double a = __dsub_rn(0.5, s), b = __dadd_rn(0.5, s);
+    win[0] = __dmul_rn(__dmul_rn(0.5, b), b);
+    win[1] = __dsub_rn(0.75, __dmul_rn(s, s));
+    win[2] = __dmul_rn(__dmul_rn(0.5, a), a);
+  }
+}
+
+// PCS, S/field.cpp:1015-1033.
+template <>
+__device__ __forceinline__ void window_1d<4>(double loc, int n, int* ijk, double* win) {
+  int idx = __double2int_rz(loc);
+  ijk[0] = (idx == 0) ? n - 1 : idx - 1;
+  ijk[1] = idx;
+  ijk[2] = (idx == n - 1) ? 0 : idx + 1;
+  ijk[3] = (ijk[2] == n - 1) ? 0 : ijk[2] + 1;
+  const double c6 = 1. / 6;
+  double s = __dsub_rn(loc, (double)idx);
+  double u = __dsub_rn(1., s);
+  win[0] = __dmul_rn(__dmul_rn(__dmul_rn(c6, u), u), u);
+  win[1] = __dmul_rn(c6, __dadd_rn(
+    __dsub_rn(4., __dmul_rn(__dmul_rn(6., s), s)),
+    __dmul_rn(__dmul_rn(__dmul_rn(3., s), s), s)));
+  win[2] = __dmul_rn(c6, __dadd_rn(
+    __dsub_rn(4., __dmul_rn(__dmul_rn(6., u), u)),
+    __dmul_rn(__dmul_rn(__dmul_rn(3., u), u), u)));
+  win[3] = __dmul_rn(__dmul_rn(__dmul_rn(c6, s), s), s);
+}
+
+// Home cell index along one axis (the integer part of loc), clamped.
+__device__ __forceinline__ int home_index(double pos, int n, double L, int shifted) {
+  double loc = grid_loc(pos, n, L, shifted);
+  int idx = __double2int_rz(loc);
+  return min(max(idx, 0), n - 1);
+}
+
+// ---------------------------------------------------------------------
+// Particle weights (kinds in trvb.h).
+// ---------------------------------------------------------------------
+
+struct CatView {
+  const double* x; const double* y; const double* z;
+  const double* w;     // may be null
+  const double* lx; const double* ly; const double* lz;   // may be null
+  const double* cw;    // custom complex weights, may be null
+  long long n;
+};
+
+__device__ __forceinline__ cplx particle_weight(const CatView& c, long long i,
+                                                int kind, int L, int M) {
+  cplx out; out.im = 0.;
+  const double w = c.w ? c.w[i] : 1.;
+  if (kind == TRVB_W_UNIT) { out.re = 1.; return out; }
+  if (kind == TRVB_W_W) { out.re = w; return out; }
+  if (kind == TRVB_W_CUSTOM) { out.re = c.cw[2 * i]; out.im = c.cw[2 * i + 1]; return out; }
+  cplx y; y.re = 1.; y.im = 0.;
+  if (!(L == 0 && M == 0)) y = ylm_reduced(L, M, c.lx[i], c.ly[i], c.lz[i]);
+  if (kind == TRVB_W_YLM_W) {
+    out.re = y.re * w; out.im = y.im * w;
+  } else if (kind == TRVB_W_CYLM_W2) {
+    const double w2 = w * w;
+    out.re = y.re * w2; out.im = -y.im * w2;
+  } else {  // TRVB_W_YLM_W3
+    const double w3 = w * w * w;
+    out.re = y.re * w3; out.im = y.im * w3;
+  }
+  return out;
+}
+
+// ---------------------------------------------------------------------
+// Counting sort by tile (throughput) or by home cell (deterministic).
+// ---------------------------------------------------------------------
+
+constexpr int TILE_SHIFT = 2;   // 4^3-cell tiles for the throughput sort key
+
+struct SortDesc {
+  int n[3]; double L[3]; int shifted;
+  int by_cell;          // 0: tile key, 1: home-cell key
+  int nk[3];            // key-grid extents
+};
+
+__device__ __forceinline__ int sort_key(const SortDesc& d, double x, double y, double z) {
+  int i = home_index(x, d.n[0], d.L[0], d.shifted);
+  int j = home_index(y, d.n[1], d.L[1], d.shifted);
+  int k = home_index(z, d.n[2], d.L[2], d.shifted);
+  if (!d.by_cell) { i >>= TILE_SHIFT; j >>= TILE_SHIFT; k >>= TILE_SHIFT; }
+  return (i * d.nk[1] + j) * d.nk[2] + k;
+}
+
+__global__ void k_sort_count(CatView c, SortDesc d, int* __restrict__ counts) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < c.n;
+       i += (long long)gridDim.x * blockDim.x) {
+    atomicAdd(&counts[sort_key(d, c.x[i], c.y[i], c.z[i])], 1);
+  }
+}
+
+// Exclusive scan of `counts` (length nkeys, plus one trailing total slot),
+// three kernels: chunk sums, scan of chunk sums, chunk scan + offset.
+constexpr int SCAN_CHUNK = 2048;
+constexpr int SCAN_THREADS = 256;
+
+__global__ void k_scan_chunk_sums(const int* __restrict__ counts, long long nkeys,
+                                  int* __restrict__ chunk_sums) {
+  __shared__ int sm[SCAN_THREADS / 32];
+  const long long base = (long long)blockIdx.x * SCAN_CHUNK;
+  int v = 0;
+  for (int t = threadIdx.x; t < SCAN_CHUNK; t += SCAN_THREADS) {
+    long long idx = base + t;
+    if (idx < nkeys) v += counts[idx];
+  }
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int s = 0;
+    for (int wdx = 0; wdx < SCAN_THREADS / 32; wdx++) s += sm[wdx];
+    chunk_sums[blockIdx.x] = s;
+  }
+}
+
+__global__ void k_scan_chunk_offsets(int* __restrict__ chunk_sums, int nchunks) {
+  // Single block: serial over tiles of 1024 with an in-block scan.
+  __shared__ int sm[1024];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nchunks; base += 1024) {
+    int idx = base + threadIdx.x;
+    int v = (idx < nchunks) ? chunk_sums[idx] : 0;
+    sm[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      int t = (threadIdx.x >= o) ? sm[threadIdx.x - o] : 0;
+      __syncthreads();
+      sm[threadIdx.x] += t;
+      __syncthreads();
+    }
+    int incl = sm[threadIdx.x];
+    if (idx < nchunks) chunk_sums[idx] = carry + incl - v;   // exclusive
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += incl;
+    __syncthreads();
+  }
+}
+
+__global__ void k_scan_apply(int* __restrict__ counts, long long nkeys,
+                             const int* __restrict__ chunk_offsets) {
+  // In place: counts -> exclusive offsets.  One block per chunk, thread t
+  // owns SCAN_CHUNK/SCAN_THREADS consecutive entries.
+  constexpr int PER = SCAN_CHUNK / SCAN_THREADS;
+  __shared__ int sm[SCAN_THREADS];
+  const long long base = (long long)blockIdx.x * SCAN_CHUNK + (long long)threadIdx.x * PER;
+  int vals[PER];
+  int local = 0;
+#pragma unroll
+  for (int q = 0; q < PER; q++) {
+    long long idx = base + q;
+    vals[q] = (idx < nkeys) ? counts[idx] : 0;
+    local += vals[q];
+  }
+  sm[threadIdx.x] = local;
+  __syncthreads();
+  for (int o = 1; o < SCAN_THREADS; o <<= 1) {
+    int t = (threadIdx.x >= o) ? sm[threadIdx.x - o] : 0;
+    __syncthreads();
+    sm[threadIdx.x] += t;
+    __syncthreads();
+  }
+  int run = chunk_offsets[blockIdx.x] + sm[threadIdx.x] - local;
+#pragma unroll
+  for (int q = 0; q < PER; q++) {
+    long long idx = base + q;
+    if (idx < nkeys) counts[idx] = run;
+    run += vals[q];
+  }
+}
+
+__global__ void k_sort_scatter(CatView c, SortDesc d, int* __restrict__ cursor,
+                               int* __restrict__ order) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < c.n;
+       i += (long long)gridDim.x * blockDim.x) {
+    int key = sort_key(d, c.x[i], c.y[i], c.z[i]);
+    int pos = atomicAdd(&cursor[key], 1);
+    order[pos] = (int)i;
+  }
+}
+
+// After the atomic scatter the ids inside a cell are in arbitrary order;
+// sort each cell's (short) segment ascending so that the gather kernel sees
+// the reference's particle order.  cursor[key] now holds the segment END.
+__global__ void k_sort_segments(const int* __restrict__ seg_end, long long nkeys,
+                                int* __restrict__ order) {
+  for (long long key = blockIdx.x * (long long)blockDim.x + threadIdx.x; key < nkeys;
+       key += (long long)gridDim.x * blockDim.x) {
+    int b = (key == 0) ? 0 : seg_end[key - 1];
+    int e = seg_end[key];
+    for (int a = b + 1; a < e; a++) {
+      int v = order[a];
+      int q = a - 1;
+      while (q >= b && order[q] > v) { order[q + 1] = order[q]; q--; }
+      order[q + 1] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------
+// Throughput assignment: one thread per (sorted) particle, p^3 REDs.
+// ---------------------------------------------------------------------
+
+template <int ORDER, bool COMPLEX>
+__global__ void __launch_bounds__(256)
+k_assign_scatter(CatView c, const int* __restrict__ order, GridDesc g, int shifted,
+                 int kind, int L, int M, double scale, double* __restrict__ mesh) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < c.n;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long i = order ? order[t] : t;
+    int ijk[3][ORDER];
+    double win[3][ORDER];
+    window_1d<ORDER>(grid_loc(c.x[i], g.n[0], g.L[0], shifted), g.n[0], ijk[0], win[0]);
+    window_1d<ORDER>(grid_loc(c.y[i], g.n[1], g.L[1], shifted), g.n[1], ijk[1], win[1]);
+    window_1d<ORDER>(grid_loc(c.z[i], g.n[2], g.L[2], shifted), g.n[2], ijk[2], win[2]);
+    cplx wt = particle_weight(c, i, kind, L, M);
+    const double bre = __dmul_rn(scale, wt.re);
+    const double bim = COMPLEX ? __dmul_rn(scale, wt.im) : 0.;
+#pragma unroll
+    for (int a = 0; a < ORDER; a++) {
+      const double wa_re = __dmul_rn(bre, win[0][a]);
+      const double wa_im = COMPLEX ? __dmul_rn(bim, win[0][a]) : 0.;
+#pragma unroll
+      for (int b = 0; b < ORDER; b++) {
+        const double wb_re = __dmul_rn(wa_re, win[1][b]);
+        const double wb_im = COMPLEX ? __dmul_rn(wa_im, win[1][b]) : 0.;
+        const long long row = ((long long)ijk[0][a] * g.n[1] + ijk[1][b]) * g.n[2];
+#pragma unroll
+        for (int cidx = 0; cidx < ORDER; cidx++) {
+          const long long gid = row + ijk[2][cidx];
+          if (gid >= 0 && gid < g.nmesh) {   // S/field.cpp:1042
+            if (COMPLEX) {
+              atomicAdd(&mesh[2 * gid], __dmul_rn(wb_re, win[2][cidx]));
+              atomicAdd(&mesh[2 * gid + 1], __dmul_rn(wb_im, win[2][cidx]));
+            } else {
+              atomicAdd(&mesh[gid], __dmul_rn(wb_re, win[2][cidx]));
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------
+// Deterministic assignment: one thread per output cell, ordered gather.
+// ---------------------------------------------------------------------
+
+constexpr int DET_CAP = 96;   // candidates buffered per cell before fallback
+
+template <int ORDER>
+__device__ __forceinline__ bool contribution(
+  const CatView& c, int pid, const GridDesc& g, int shifted,
+  int ci, int cj, int ck, double& wprod_x, double& wprod_y, double& wprod_z
+) {
+  int ijk[ORDER]; double win[ORDER];
+  bool hit;
+  window_1d<ORDER>(grid_loc(c.x[pid], g.n[0], g.L[0], shifted), g.n[0], ijk, win);
+  hit = false;
+#pragma unroll
+  for (int a = 0; a < ORDER; a++) if (ijk[a] == ci) { wprod_x = win[a]; hit = true; }
+  if (!hit) return false;
+  window_1d<ORDER>(grid_loc(c.y[pid], g.n[1], g.L[1], shifted), g.n[1], ijk, win);
+  hit = false;
+#pragma unroll
+  for (int a = 0; a < ORDER; a++) if (ijk[a] == cj) { wprod_y = win[a]; hit = true; }
+  if (!hit) return false;
+  window_1d<ORDER>(grid_loc(c.z[pid], g.n[2], g.L[2], shifted), g.n[2], ijk, win);
+  hit = false;
+#pragma unroll
+  for (int a = 0; a < ORDER; a++) if (ijk[a] == ck) { wprod_z = win[a]; hit = true; }
+  return hit;
+}
+
+template <int ORDER, bool COMPLEX>
+__global__ void __launch_bounds__(128)
+k_assign_gather(CatView c, const int* __restrict__ order,
+                const int* __restrict__ cell_start, GridDesc g, int shifted,
+                int kind, int L, int M, double scale, double pre /* 1/vol_cell or 1 */,
+                int accumulate, double* __restrict__ mesh) {
+  // Home cells whose particles can reach output index q along an axis:
+  // q - LO .. q + HI (periodic).  PCS/TSC: home in {q-2..q+1}; CIC/NGP: {q-1, q}.
+  constexpr int LO = (ORDER >= 3) ? 2 : 1;
+  constexpr int HI = (ORDER >= 3) ? 1 : 0;
+  constexpr int SPAN = LO + HI + 1;
+  const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (gid >= g.nmesh) return;
+  const int ck = (int)(gid % g.n[2]);
+  const int cj = (int)((gid / g.n[2]) % g.n[1]);
+  const int ci = (int)(gid / ((long long)g.n[2] * g.n[1]));
+
+  int cand_pid[DET_CAP];
+  double cand_re[DET_CAP];
+  double cand_im[COMPLEX ? DET_CAP : 1];
+  int ncand = 0;
+  bool overflow = false;
+
+  auto value_of = [&](int pid, double wx, double wy, double wz, double& vre, double& vim) {
+    cplx wt = particle_weight(c, pid, kind, L, M);
+    // ((((inv_vol_cell * w) * Wx) * Wy) * Wz), S/field.cpp:1044-1048.
+    double bre = __dmul_rn(pre, wt.re);
+    if (scale != 1.) bre = __dmul_rn(bre, scale);
+    vre = __dmul_rn(__dmul_rn(__dmul_rn(bre, wx), wy), wz);
+    if (COMPLEX) {
+      double bim = __dmul_rn(pre, wt.im);
+      if (scale != 1.) bim = __dmul_rn(bim, scale);
+      vim = __dmul_rn(__dmul_rn(__dmul_rn(bim, wx), wy), wz);
+    } else {
+      vim = 0.;
+    }
+  };
+
+  for (int da = 0; da < SPAN && !overflow; da++) {
+    int hi_ = ci - LO + da; hi_ = (hi_ % g.n[0] + g.n[0]) % g.n[0];
+    for (int db = 0; db < SPAN && !overflow; db++) {
+      int hj = cj - LO + db; hj = (hj % g.n[1] + g.n[1]) % g.n[1];
+      for (int dc = 0; dc < SPAN; dc++) {
+        int hk = ck - LO + dc; hk = (hk % g.n[2] + g.n[2]) % g.n[2];
+        const long long hcell = ((long long)hi_ * g.n[1] + hj) * g.n[2] + hk;
+        const int b = cell_start[hcell], e = cell_start[hcell + 1];
+        for (int s = b; s < e; s++) {
+          const int pid = order[s];
+          double wx, wy, wz;
+          if (!contribution<ORDER>(c, pid, g, shifted, ci, cj, ck, wx, wy, wz)) continue;
+          if (ncand >= DET_CAP) { overflow = true; break; }
+          double vre, vim;
+          value_of(pid, wx, wy, wz, vre, vim);
+          // Insertion keeps candidates ascending in particle id.
+          int q = ncand - 1;
+          while (q >= 0 && cand_pid[q] > pid) {
+            cand_pid[q + 1] = cand_pid[q];
+            cand_re[q + 1] = cand_re[q];
+            if (COMPLEX) cand_im[q + 1] = cand_im[q];
+            q--;
+          }
+          cand_pid[q + 1] = pid; cand_re[q + 1] = vre;
+          if (COMPLEX) cand_im[q + 1] = vim;
+          ncand++;
+        }
+        if (overflow) break;
+      }
+    }
+  }
+
+  double acc_re = 0., acc_im = 0.;
+  if (accumulate) {
+    acc_re = COMPLEX ? mesh[2 * gid] : mesh[gid];
+    if (COMPLEX) acc_im = mesh[2 * gid + 1];
+  }
+  if (!overflow) {
+    for (int q = 0; q < ncand; q++) {
+      acc_re = __dadd_rn(acc_re, cand_re[q]);
+      if (COMPLEX) acc_im = __dadd_rn(acc_im, cand_im[q]);
+    }
+  } else {
+    // Dense cell: repeated selection of the next particle id (no storage).
+    int last = -1;
+    while (true) {
+      int best = 0x7fffffff; double bx = 0., by = 0., bz = 0.;
+      for (int da = 0; da < SPAN; da++) {
+        int hi_ = ci - LO + da; hi_ = (hi_ % g.n[0] + g.n[0]) % g.n[0];
+        for (int db = 0; db < SPAN; db++) {
+          int hj = cj - LO + db; hj = (hj % g.n[1] + g.n[1]) % g.n[1];
+          for (int dc = 0; dc < SPAN; dc++) {
+            int hk = ck - LO + dc; hk = (hk % g.n[2] + g.n[2]) % g.n[2];
+            const long long hcell = ((long long)hi_ * g.n[1] + hj) * g.n[2] + hk;
+            const int b = cell_start[hcell], e = cell_start[hcell + 1];
+            for (int s = b; s < e; s++) {
+              const int pid = order[s];
+              if (pid <= last || pid >= best) continue;
+              double wx, wy, wz;
+              if (!contribution<ORDER>(c, pid, g, shifted, ci, cj, ck, wx, wy, wz)) continue;
+              best = pid; bx = wx; by = wy; bz = wz;
+            }
+          }
+        }
+      }
+      if (best == 0x7fffffff) break;
+      double vre, vim;
+      value_of(best, bx, by, bz, vre, vim);
+      acc_re = __dadd_rn(acc_re, vre);
+      if (COMPLEX) acc_im = __dadd_rn(acc_im, vim);
+      last = best;
+    }
+  }
+  if (COMPLEX) { mesh[2 * gid] = acc_re; mesh[2 * gid + 1] = acc_im; }
+  else mesh[gid] = acc_re;
+}
+
+// ---------------------------------------------------------------------
+// Catalogue sums.
+// ---------------------------------------------------------------------
+
+__global__ void k_cat_sum(CatView c, int kind, int L, int M,
+                          double* __restrict__ partial /* [gridDim][2] */) {
+  __shared__ double sm[32];
+  double re = 0., im = 0.;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < c.n;
+       i += (long long)gridDim.x * blockDim.x) {
+    cplx wv = particle_weight(c, i, kind, L, M);
+    re += wv.re; im += wv.im;
+  }
+  double sre = block_sum(re, sm);
+  double sim = block_sum(im, sm);
+  if (threadIdx.x == 0) { partial[2 * blockIdx.x] = sre; partial[2 * blockIdx.x + 1] = sim; }
+}
+
+__global__ void k_sum_partials(const double* __restrict__ partial, int nblocks, int width,
+                               double* __restrict__ out) {
+  // Fixed-order second stage: thread t sums column t over blocks.
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= width) return;
+  double s = 0.;
+  for (int b = 0; b < nblocks; b++) s += partial[(long long)b * width + t];
+  out[t] = s;
+}
+
+CatView view_of(const trvb_cat* cat) {
+  CatView v;
+  v.x = cat->x; v.y = cat->y; v.z = cat->z; v.w = cat->w;
+  v.lx = cat->los; v.ly = cat->los ? cat->los + cat->n : nullptr;
+  v.lz = cat->los ? cat->los + 2 * cat->n : nullptr;
+  v.cw = cat->cw;
+  v.n = cat->n;
+  return v;
+}
+
+__global__ void k_aos_to_soa(const double* __restrict__ aos, long long n,
+                             double* x, double* y, double* z, double* w) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double* p = aos + 7 * i;
+    x[i] = p[0]; y[i] = p[1]; z[i] = p[2]; w[i] = p[6];
+  }
+}
+
+__global__ void k_los_to_soa(const double* __restrict__ los, long long n, double* out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    out[i] = los[3 * i]; out[n + i] = los[3 * i + 1]; out[2 * n + i] = los[3 * i + 2];
+  }
+}
+
+int ensure_sorted(trvb_ctx* ctx, trvb_cat* cat, int shifted, int by_cell) {
+  const GridDesc& g = ctx->g;
+  bool valid = cat->order != nullptr && cat->sort_kind == by_cell
+    && cat->sort_shifted == shifted;
+  for (int a = 0; a < 3; a++) {
+    valid = valid && cat->sort_n[a] == g.n[a] && cat->sort_L[a] == g.L[a];
+  }
+  if (valid) return 0;
+  SortDesc d;
+  for (int a = 0; a < 3; a++) {
+    d.n[a] = g.n[a]; d.L[a] = g.L[a];
+    d.nk[a] = by_cell ? g.n[a] : ((g.n[a] + (1 << TILE_SHIFT) - 1) >> TILE_SHIFT);
+  }
+  d.shifted = shifted; d.by_cell = by_cell;
+  const long long nkeys = (long long)d.nk[0] * d.nk[1] * d.nk[2];
+  TRVB_REQUIRE(cat->n < 2147483647LL, "catalogue too large for int indices");
+  if (!cat->order) TRVB_CUDA(cudaMalloc(&cat->order, sizeof(int) * (size_t)cat->n));
+  if (cat->cell_start) {
+    TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
+    TRVB_CUDA(cudaFree(cat->cell_start)); cat->cell_start = nullptr;
+  }
+  int* offsets = nullptr;   // nkeys + 1
+  int* cursor = nullptr;    // nkeys
+  TRVB_CUDA(cudaMalloc(&offsets, sizeof(int) * (size_t)(nkeys + 1)));
+  TRVB_CUDA(cudaMalloc(&cursor, sizeof(int) * (size_t)nkeys));
+  TRVB_CUDA(cudaMemsetAsync(offsets, 0, sizeof(int) * (size_t)(nkeys + 1), ctx->stream));
+  CatView cv = view_of(cat);
+  const int threads = 256;
+  const int blocks = (int)std::min<long long>(div_up(cat->n, threads), (long long)ctx->num_sms * 16);
+  k_sort_count<<<blocks, threads, 0, ctx->stream>>>(cv, d, offsets);
+  TRVB_LAUNCH_CHECK();
+  const long long nscan = nkeys + 1;
+  const int nchunks = div_up(nscan, SCAN_CHUNK);
+  int* chunk_sums = nullptr;
+  TRVB_CUDA(cudaMalloc(&chunk_sums, sizeof(int) * (size_t)nchunks));
+  k_scan_chunk_sums<<<nchunks, SCAN_THREADS, 0, ctx->stream>>>(offsets, nscan, chunk_sums);
+  TRVB_LAUNCH_CHECK();
+  k_scan_chunk_offsets<<<1, 1024, 0, ctx->stream>>>(chunk_sums, nchunks);
+  TRVB_LAUNCH_CHECK();
+  k_scan_apply<<<nchunks, SCAN_THREADS, 0, ctx->stream>>>(offsets, nscan, chunk_sums);
+  TRVB_LAUNCH_CHECK();
+  TRVB_CUDA(cudaMemcpyAsync(cursor, offsets, sizeof(int) * (size_t)nkeys,
+                            cudaMemcpyDeviceToDevice, ctx->stream));
+  k_sort_scatter<<<blocks, threads, 0, ctx->stream>>>(cv, d, cursor, cat->order);
+  TRVB_LAUNCH_CHECK();
+  if (by_cell) {
+    const int sb = (int)std::min<long long>(div_up(nkeys, threads), (long long)ctx->num_sms * 32);
+    k_sort_segments<<<sb, threads, 0, ctx->stream>>>(cursor, nkeys, cat->order);
+    TRVB_LAUNCH_CHECK();
+    cat->cell_start = offsets;
+  }
+  TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  TRVB_CUDA(cudaFree(cursor));
+  TRVB_CUDA(cudaFree(chunk_sums));
+  if (!by_cell) TRVB_CUDA(cudaFree(offsets));
+  for (int a = 0; a < 3; a++) { cat->sort_n[a] = g.n[a]; cat->sort_L[a] = g.L[a]; }
+  cat->sort_shifted = shifted; cat->sort_kind = by_cell;
+  return 0;
+}
+
+template <int ORDER>
+int launch_assign(trvb_ctx* ctx, trvb_cat* cat, int kind, int L, int M, double scale,
+                  int density_units, int accumulate, int shifted, int mode,
+                  trvb_mesh mesh) {
+  const GridDesc& g = ctx->g;
+  const bool cplx_mesh = mesh.layout == TRVB_COMPLEX;
+  CatView cv = view_of(cat);
+  if (mode == 0) {
+    int st = ensure_sorted(ctx, cat, shifted, 0);
+    if (st) return st;
+    if (!accumulate) {
+      TRVB_CUDA(cudaMemsetAsync(mesh.data, 0, trvb_mesh_bytes(ctx, mesh.layout), ctx->stream));
+    }
+    const double s = density_units ? scale * (1. / g.vol_cell) : scale;
+    const int threads = 256;
+    const int blocks = div_up(cat->n, threads);
+    if (cplx_mesh) {
+      k_assign_scatter<ORDER, true><<<blocks, threads, 0, ctx->stream>>>(
+        cv, cat->order, g, shifted, kind, L, M, s, (double*)mesh.data);
+    } else {
+      k_assign_scatter<ORDER, false><<<blocks, threads, 0, ctx->stream>>>(
+        cv, cat->order, g, shifted, kind, L, M, s, (double*)mesh.data);
+    }
+    TRVB_LAUNCH_CHECK();
+  } else {
+    TRVB_REQUIRE(g.n[0] >= 4 && g.n[1] >= 4 && g.n[2] >= 4,
+                 "deterministic assignment needs at least 4 cells per axis");
+    int st = ensure_sorted(ctx, cat, shifted, 1);
+    if (st) return st;
+    const double pre = density_units ? 1. / g.vol_cell : 1.;   // S/field.cpp:996
+    const int threads = 128;
+    const int blocks = div_up(g.nmesh, threads);
+    if (cplx_mesh) {
+      k_assign_gather<ORDER, true><<<blocks, threads, 0, ctx->stream>>>(
+        cv, cat->order, cat->cell_start, g, shifted, kind, L, M, scale, pre,
+        accumulate, (double*)mesh.data);
+    } else {
+      k_assign_gather<ORDER, false><<<blocks, threads, 0, ctx->stream>>>(
+        cv, cat->order, cat->cell_start, g, shifted, kind, L, M, scale, pre,
+        accumulate, (double*)mesh.data);
+    }
+    TRVB_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+}  // namespace
+
+// =====================================================================
+// C ABI
+// =====================================================================
+
+extern "C" int trvb_cat_create(trvb_ctx* ctx, trvb_cat** out, long long n,
+                               const double* x, const double* y, const double* z,
+                               const double* w, const double* los, int src_on_device) {
+  TRVB_REQUIRE(ctx && out && x && y && z && n > 0, "trvb_cat_create: bad argument");
+  TRVB_CUDA(cudaSetDevice(ctx->device));
+  trvb_cat* cat = new trvb_cat();
+  cat->owner = ctx; cat->n = n;
+  const size_t nb = sizeof(double) * (size_t)n;
+  const cudaMemcpyKind kind = src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  TRVB_CUDA(cudaMalloc(&cat->x, nb));
+  TRVB_CUDA(cudaMalloc(&cat->y, nb));
+  TRVB_CUDA(cudaMalloc(&cat->z, nb));
+  TRVB_CUDA(cudaMemcpyAsync(cat->x, x, nb, kind, ctx->stream));
+  TRVB_CUDA(cudaMemcpyAsync(cat->y, y, nb, kind, ctx->stream));
+  TRVB_CUDA(cudaMemcpyAsync(cat->z, z, nb, kind, ctx->stream));
+  if (w) {
+    TRVB_CUDA(cudaMalloc(&cat->w, nb));
+    TRVB_CUDA(cudaMemcpyAsync(cat->w, w, nb, kind, ctx->stream));
+  }
+  if (los) {
+    double* tmp = nullptr;
+    TRVB_CUDA(cudaMalloc(&cat->los, 3 * nb));
+    if (src_on_device) {
+      tmp = const_cast<double*>(los);
+    } else {
+      TRVB_CUDA(cudaMalloc(&tmp, 3 * nb));
+      TRVB_CUDA(cudaMemcpyAsync(tmp, los, 3 * nb, kind, ctx->stream));
+    }
+    k_los_to_soa<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(tmp, n, cat->los);
+    TRVB_LAUNCH_CHECK();
+    if (!src_on_device) {
+      TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
+      TRVB_CUDA(cudaFree(tmp));
+    }
+  }
+  TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = cat;
+  return 0;
+}
+
+extern "C" int trvb_cat_create_aos(trvb_ctx* ctx, trvb_cat** out, long long n,
+                                   const double* pdata, const double* los) {
+  TRVB_REQUIRE(ctx && out && pdata && n > 0, "trvb_cat_create_aos: bad argument");
+  TRVB_CUDA(cudaSetDevice(ctx->device));
+  const size_t nb = sizeof(double) * (size_t)n;
+  double* d_aos = nullptr;
+  TRVB_CUDA(cudaMalloc(&d_aos, 7 * nb));
+  TRVB_CUDA(cudaMemcpyAsync(d_aos, pdata, 7 * nb, cudaMemcpyHostToDevice, ctx->stream));
+  trvb_cat* cat = new trvb_cat();
+  cat->owner = ctx; cat->n = n;
+  TRVB_CUDA(cudaMalloc(&cat->x, nb));
+  TRVB_CUDA(cudaMalloc(&cat->y, nb));
+  TRVB_CUDA(cudaMalloc(&cat->z, nb));
+  TRVB_CUDA(cudaMalloc(&cat->w, nb));
+  k_aos_to_soa<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(d_aos, n, cat->x, cat->y, cat->z, cat->w);
+  TRVB_LAUNCH_CHECK();
+  if (los) {
+    double* tmp = nullptr;
+    TRVB_CUDA(cudaMalloc(&cat->los, 3 * nb));
+    TRVB_CUDA(cudaMalloc(&tmp, 3 * nb));
+    TRVB_CUDA(cudaMemcpyAsync(tmp, los, 3 * nb, cudaMemcpyHostToDevice, ctx->stream));
+    k_los_to_soa<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(tmp, n, cat->los);
+    TRVB_LAUNCH_CHECK();
+    TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
+    TRVB_CUDA(cudaFree(tmp));
+  }
+  TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  TRVB_CUDA(cudaFree(d_aos));
+  *out = cat;
+  return 0;
+}
+
+extern "C" int trvb_cat_set_custom_weights(trvb_ctx* ctx, trvb_cat* cat,
+                                           const double* weights) {
+  TRVB_REQUIRE(ctx && cat && weights, "trvb_cat_set_custom_weights: null argument");
+  TRVB_CUDA(cudaSetDevice(ctx->device));
+  const size_t nb = 2 * sizeof(double) * (size_t)cat->n;
+  if (!cat->cw) TRVB_CUDA(cudaMalloc(&cat->cw, nb));
+  TRVB_CUDA(cudaMemcpyAsync(cat->cw, weights, nb, cudaMemcpyHostToDevice, ctx->stream));
+  TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" void trvb_cat_destroy(trvb_cat* cat) {
+  if (!cat) return;
+  if (cat->owner) { cudaSetDevice(cat->owner->device); cudaStreamSynchronize(cat->owner->stream); }
+  cudaFree(cat->x); cudaFree(cat->y); cudaFree(cat->z);
+  if (cat->w) cudaFree(cat->w);
+  if (cat->los) cudaFree(cat->los);
+  if (cat->cw) cudaFree(cat->cw);
+  if (cat->order) cudaFree(cat->order);
+  if (cat->cell_start) cudaFree(cat->cell_start);
+  delete cat;
+}
+
+extern "C" long long trvb_cat_size(const trvb_cat* cat) { return cat ? cat->n : 0; }
+
+extern "C" int trvb_cat_sum(trvb_ctx* ctx, trvb_cat* cat, int kind, int L, int M,
+                            double out[2]) {
+  TRVB_REQUIRE(ctx && cat && out, "trvb_cat_sum: null argument");
+  TRVB_REQUIRE(kind >= TRVB_W_UNIT && kind <= TRVB_W_YLM_W3, "trvb_cat_sum: kind %d", kind);
+  TRVB_REQUIRE(kind < TRVB_W_YLM_W || (L == 0 && M == 0) || cat->los,
+               "trvb_cat_sum: y_LM weights need lines of sight");
+  const int threads = 256;
+  const int blocks = (int)std::min<long long>(div_up(cat->n, threads), (long long)ctx->num_sms * 8);
+  double* scratch;
+  int st = trvb_scratch(ctx, sizeof(double) * (2 * (size_t)blocks + 2), &scratch);
+  if (st) return st;
+  k_cat_sum<<<blocks, threads, 0, ctx->stream>>>(view_of(cat), kind, L, M, scratch);
+  TRVB_LAUNCH_CHECK();
+  k_sum_partials<<<1, 32, 0, ctx->stream>>>(scratch, blocks, 2, scratch + 2 * blocks);
+  TRVB_LAUNCH_CHECK();
+  TRVB_CUDA(cudaMemcpyAsync(out, scratch + 2 * blocks, 2 * sizeof(double),
+                            cudaMemcpyDeviceToHost, ctx->stream));
+  TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int trvb_assign(trvb_ctx* ctx, trvb_cat* cat, int kind, int L, int M,
+                           double scale, int density_units, int accumulate, int shifted,
+                           int mode, trvb_mesh mesh) {
+  TRVB_REQUIRE(ctx && cat && mesh.data, "trvb_assign: null argument");
+  TRVB_REQUIRE(ctx->parent == nullptr, "trvb_assign: not available on a sub-grid context");
+  TRVB_REQUIRE((kind >= TRVB_W_UNIT && kind <= TRVB_W_CYLM_W2) || kind == TRVB_W_CUSTOM,
+               "trvb_assign: weight kind %d", kind);
+  TRVB_REQUIRE(mesh.layout == TRVB_REAL || mesh.layout == TRVB_COMPLEX,
+               "trvb_assign: mesh layout must be REAL or COMPLEX");
+  TRVB_REQUIRE(kind != TRVB_W_CUSTOM || cat->cw,
+               "trvb_assign: no custom weights attached (trvb_cat_set_custom_weights)");
+  // y_L0 is real-valued, so M == 0 weights may target a REAL mesh.
+  const bool real_weights = kind <= TRVB_W_W || (kind != TRVB_W_CUSTOM && M == 0);
+  TRVB_REQUIRE(real_weights || mesh.layout == TRVB_COMPLEX,
+               "trvb_assign: complex weights need a COMPLEX mesh");
+  const bool needs_los = (kind == TRVB_W_YLM_W || kind == TRVB_W_CYLM_W2) && !(L == 0 && M == 0);
+  TRVB_REQUIRE(!needs_los || cat->los, "trvb_assign: y_LM weights need lines of sight");
+  TRVB_CUDA(cudaSetDevice(ctx->device));
+  switch (ctx->g.order) {
+    case 1: return launch_assign<1>(ctx, cat, kind, L, M, scale, density_units, accumulate, shifted, mode, mesh);
+    case 2: return launch_assign<2>(ctx, cat, kind, L, M, scale, density_units, accumulate, shifted, mode, mesh);
+    case 3: return launch_assign<3>(ctx, cat, kind, L, M, scale, density_units, accumulate, shifted, mode, mesh);
+    case 4: return launch_assign<4>(ctx, cat, kind, L, M, scale, density_units, accumulate, shifted, mode, mesh);
+  }
+  trvb_set_error("trvb_assign: unsupported order %d", ctx->g.order);
+  return 2;
+}

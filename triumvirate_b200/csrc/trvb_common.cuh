@@ -1,0 +1,306 @@
+// trvb_common.cuh -- shared state and device helpers for libtrvb.so
+// (sm_100a; CUDA 12.9).  See include/trvb.h for the C-ABI this implements.
+#ifndef TRVB_COMMON_CUH_
+#define TRVB_COMMON_CUH_
+
+#include <cuda_runtime.h>
+#include <cufft.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "trvb.h"
+
+// ---------------------------------------------------------------------
+// Error handling: every C-ABI entry returns an int and stores a message.
+// ---------------------------------------------------------------------
+
+void trvb_set_error(const char* fmt, ...);
+extern long long g_trvb_launches;
+
+#define TRVB_CUDA(call)                                                    \
+  do {                                                                     \
+    cudaError_t err__ = (call);                                            \
+    if (err__ != cudaSuccess) {                                            \
+      trvb_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,         \
+                     cudaGetErrorString(err__));                           \
+      return 100 + (int)err__;                                             \
+    }                                                                      \
+  } while (0)
+
+#define TRVB_CUFFT(call)                                                   \
+  do {                                                                     \
+    cufftResult err__ = (call);                                            \
+    if (err__ != CUFFT_SUCCESS) {                                          \
+      trvb_set_error("%s:%d: %s -> cufftResult %d", __FILE__, __LINE__,    \
+                     #call, (int)err__);                                   \
+      return 1000 + (int)err__;                                            \
+    }                                                                      \
+  } while (0)
+
+#define TRVB_REQUIRE(cond, ...)                                            \
+  do {                                                                     \
+    if (!(cond)) {                                                         \
+      trvb_set_error(__VA_ARGS__);                                         \
+      return 2;                                                            \
+    }                                                                      \
+  } while (0)
+
+#define TRVB_LAUNCH_CHECK()                                                \
+  do {                                                                     \
+    g_trvb_launches++;                                                     \
+    TRVB_CUDA(cudaGetLastError());                                         \
+  } while (0)
+
+// ---------------------------------------------------------------------
+// Grid description passed by value to kernels.
+// ---------------------------------------------------------------------
+
+struct GridDesc {
+  int n[3];            // cells per axis
+  int nh;              // n[2]/2 + 1 (half-spectrum extent)
+  long long nmesh;     // n0*n1*n2
+  double L[3];         // box size
+  double dr[3];        // L/n      (S/field.cpp:353-355)
+  double dk[3];        // 2 pi / L (S/field.cpp:358-360)
+  double vol;          // L0 L1 L2
+  double vol_cell;     // vol / nmesh (S/field.cpp:363-364)
+  int order;           // assignment order 1..4
+};
+
+struct SjlTable {
+  double* d_y = nullptr;
+  double* d_c = nullptr;
+  int nsample = 0;
+  double step = 0.;
+};
+
+struct trvb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  GridDesc g;
+  trvb_ctx* parent = nullptr;       // non-null for a sub-grid context
+  // Per-axis tables on the PARENT grid, indexed by storage index i < n[ax]:
+  //   sinc[ax][i]  = sin(u)/u, u = pi*m/n  (m signed)   S/field.cpp:1138-1145
+  //   alias[ax][i] = per-axis factor of C1(k)           S/field.cpp:3479-3502
+  double* d_sinc[3] = {nullptr, nullptr, nullptr};
+  double* d_alias[3] = {nullptr, nullptr, nullptr};
+  // cuFFT plans, created lazily.
+  cufftHandle plan_z2z = 0, plan_d2z = 0, plan_z2d = 0;
+  bool has_z2z = false, has_d2z = false, has_z2d = false;
+  // Spherical-Bessel spline tables keyed by ell.
+  std::map<int, SjlTable> sjl;
+  // Scratch for two-stage reductions.
+  double* d_scratch = nullptr;
+  size_t scratch_bytes = 0;
+  int num_sms = 148;
+};
+
+struct trvb_cat {
+  trvb_ctx* owner = nullptr;   // context that owns the allocations (device)
+  long long n = 0;
+  double* x = nullptr; double* y = nullptr; double* z = nullptr;
+  double* w = nullptr;         // nullptr -> unit weights
+  double* los = nullptr;       // SoA: lx[n], ly[n], lz[n] or nullptr
+  double* cw = nullptr;        // custom complex weights (interleaved) or nullptr
+  // Cell-sorted permutation cache (valid for the grid it was built for).
+  int* order = nullptr;        // particle ids sorted by sort key
+  int* cell_start = nullptr;   // deterministic mode: nmesh+1 offsets
+  int sort_n[3] = {0, 0, 0};
+  double sort_L[3] = {0., 0., 0.};
+  int sort_shifted = -1;
+  int sort_kind = -1;          // 0 tile-sorted (throughput), 1 cell-sorted
+  int sort_order = 0;
+};
+
+int trvb_scratch(trvb_ctx* ctx, size_t bytes, double** out);
+
+// ---------------------------------------------------------------------
+// Device helpers
+// ---------------------------------------------------------------------
+
+__host__ __device__ inline int signed_index(int i, int n) {
+  // S/field.cpp:540-544: i < n/2 ? i : i - n.
+  return (i < n / 2) ? i : i - n;
+}
+
+struct cplx {
+  double re, im;
+};
+
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) {
+  cplx r;
+  r.re = a.re * b.re - a.im * b.im;
+  r.im = a.re * b.im + a.im * b.re;
+  return r;
+}
+
+__device__ __forceinline__ cplx cconj(cplx a) {
+  cplx r; r.re = a.re; r.im = -a.im; return r;
+}
+
+// |v| evaluated exactly as std::sqrt(v0*v0 + v1*v1 + v2*v2) on x86-64
+// without FMA contraction (S/maths.cpp:57-59).  Shell membership depends
+// on the last bit of this value, hence the explicit _rn intrinsics.
+__device__ __forceinline__ double vec3_norm_exact(double a, double b, double c) {
+  double s = __dadd_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)),
+                       __dmul_rn(c, c));
+  return __dsqrt_rn(s);
+}
+
+// Mesh accessor for Fourier-space meshes in COMPLEX or HALF layout.
+struct KView {
+  const double2* p;
+  int layout;
+  int n0, n1, n2, nh;
+};
+
+__device__ __forceinline__ cplx kload(const KView& v, int i, int j, int k) {
+  cplx r;
+  if (v.layout == TRVB_COMPLEX) {
+    double2 t = v.p[((long long)i * v.n1 + j) * v.n2 + k];
+    r.re = t.x; r.im = t.y;
+  } else {
+    if (k < v.nh) {
+      double2 t = v.p[((long long)i * v.n1 + j) * v.nh + k];
+      r.re = t.x; r.im = t.y;
+    } else {
+      int ic = i ? v.n0 - i : 0, jc = j ? v.n1 - j : 0, kc = v.n2 - k;
+      double2 t = v.p[((long long)ic * v.n1 + jc) * v.nh + kc];
+      r.re = t.x; r.im = -t.y;
+    }
+  }
+  return r;
+}
+
+// Reduced spherical harmonic exactly as S/maths.cpp:171-220:
+//   y_lm = sqrt(4pi/(2l+1)) (-1)^((m-|m|)/2) conj( e^{i m phi} Nlm P_l^|m|(mu) )
+// with Nlm P_l^|m| the GSL sphPlm (Condon-Shortley phase included),
+// y = 1 for l = m = 0, y = 0 for |r| < 1e-9, phi = acos(x/r_xy)
+// (2pi - phi if y < 0; 0 if r_xy < 1e-9).
+__device__ inline cplx ylm_reduced(int ell, int m, double x, double y, double z) {
+  cplx out;
+  if (ell == 0 && m == 0) { out.re = 1.; out.im = 0.; return out; }
+  const double eps = 1.e-9;
+  const double PI = 3.14159265358979323846;
+  double r2 = x * x + y * y + z * z;
+  double r = sqrt(r2);
+  if (fabs(r) < eps) { out.re = 0.; out.im = 0.; return out; }
+  double mu = z / r;
+  double rxy = sqrt(x * x + y * y);
+  double phi = 0.;
+  if (fabs(rxy) >= eps) {
+    double c = x / rxy;
+    c = fmin(1., fmax(-1., c));
+    phi = acos(c);
+    if (y < 0.) phi = -phi + 2. * PI;
+  }
+  const int am = (m < 0) ? -m : m;
+  // Normalised associated Legendre function sqrt((2l+1)/(4pi) (l-m)!/(l+m)!) P_l^m.
+  double somx2 = sqrt((1. - mu) * (1. + mu));
+  double pmm = sqrt(1. / (4. * PI));
+  for (int i = 1; i <= am; i++) {
+    pmm *= -sqrt((2. * i + 1.) / (2. * i)) * somx2;
+  }
+  double plm;
+  if (ell == am) {
+    plm = pmm;
+  } else {
+    double pmmp1 = mu * sqrt(2. * am + 3.) * pmm;
+    if (ell == am + 1) {
+      plm = pmmp1;
+    } else {
+      double pll = 0.;
+      for (int ll = am + 2; ll <= ell; ll++) {
+        double a = sqrt((4. * ll * ll - 1.) / ((double)ll * ll - (double)am * am));
+        double b = sqrt((((double)ll - 1.) * (ll - 1.) - (double)am * am)
+                        / (4. * (ll - 1.) * (ll - 1.) - 1.));
+        pll = a * (mu * pmmp1 - b * pmm);
+        pmm = pmmp1; pmmp1 = pll;
+      }
+      plm = pll;
+    }
+  }
+  double sn, cs;
+  sincos((double)m * phi, &sn, &cs);
+  // conj(e^{i m phi} P) = (cos, -sin) P; parity (-1)^((m-|m|)/2).
+  double par = (((m - am) / 2) % 2 != 0) ? -1. : 1.;
+  double norm = sqrt(4. * PI / (2. * ell + 1.)) * par * plm;
+  out.re = norm * cs;
+  out.im = -norm * sn;
+  return out;
+}
+
+// Spherical Bessel j_l(x) evaluated directly (x >= split region, or any x for
+// l = 0): upward recurrence, stable for x >= l (S/maths.cpp:368-371 uses
+// gsl_sf_bessel_jl there).
+__device__ inline double sjl_direct(int ell, double x) {
+  if (x == 0.) return (ell == 0) ? 1. : 0.;
+  double s, c;
+  sincos(x, &s, &c);
+  double j0 = s / x;
+  if (ell == 0) return j0;
+  double j1 = (s / x - c) / x;
+  if (ell == 1) return j1;
+  double jm = j0, jc = j1;
+  for (int n = 1; n < ell; n++) {
+    double jn = (2. * n + 1.) / x * jc - jm;
+    jm = jc; jc = jn;
+  }
+  return jc;
+}
+
+struct SjlView {
+  const double* y;
+  const double* c;
+  int nsample;
+  double step;
+  int ell;
+};
+
+// SphericalBesselCalculator::eval (S/maths.cpp:368-375): natural cubic spline
+// (GSL cspline evaluation formula) below `split`, direct evaluation above.
+__device__ __forceinline__ double sjl_eval(const SjlView& t, double x) {
+  const double split = t.step * (t.nsample - 1);
+  if (x >= split) return sjl_direct(t.ell, x);
+  int i = (int)(x / t.step);
+  if (i > t.nsample - 2) i = t.nsample - 2;
+  if (i < 0) i = 0;
+  // Match the bisection result x_i <= x < x_{i+1} with x_i = step * i.
+  while (i < t.nsample - 2 && t.step * (i + 1) <= x) i++;
+  while (i > 0 && t.step * i > x) i--;
+  const double x_lo = t.step * i, x_hi = t.step * (i + 1);
+  const double y_lo = __ldg(t.y + i), y_hi = __ldg(t.y + i + 1);
+  const double c_i = __ldg(t.c + i), c_ip1 = __ldg(t.c + i + 1);
+  const double dx = x_hi - x_lo;
+  const double dy = y_hi - y_lo;
+  const double b_i = (dy / dx) - dx * (c_ip1 + 2.0 * c_i) / 3.0;
+  const double d_i = (c_ip1 - c_i) / (3.0 * dx);
+  const double delx = x - x_lo;
+  return y_lo + delx * (b_i + delx * (c_i + delx * d_i));
+}
+
+// Block-wide sum of one double; result valid in thread 0.  blockDim.x must
+// be a multiple of 32 and <= 1024.
+__device__ __forceinline__ double block_sum(double v, double* smem32) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) smem32[wid] = v;
+  __syncthreads();
+  double r = 0.;
+  if (wid == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    r = (lane < nw) ? smem32[lane] : 0.;
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
+  }
+  return r;
+}
+
+inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+#endif  // TRVB_COMMON_CUH_

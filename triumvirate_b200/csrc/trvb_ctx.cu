@@ -1,0 +1,240 @@
+// trvb_ctx.cu -- context, memory, tables and cuFFT plan cache of libtrvb.so.
+#include "trvb_common.cuh"
+
+#include <cstring>
+
+static thread_local std::string g_err;
+long long g_trvb_launches = 0;
+
+void trvb_set_error(const char* fmt, ...) {
+  char buf[2048];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+
+extern "C" const char* trvb_last_error(void) { return g_err.c_str(); }
+extern "C" const char* trvb_version(void) { return "triumvirate_b200 0.1 (sm_100a)"; }
+extern "C" int trvb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+extern "C" long long trvb_launch_count(void) { return g_trvb_launches; }
+extern "C" void trvb_launch_count_reset(void) { g_trvb_launches = 0; }
+
+int trvb_scratch(trvb_ctx* ctx, size_t bytes, double** out) {
+  if (ctx->scratch_bytes < bytes) {
+    if (ctx->d_scratch) {
+      TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
+      TRVB_CUDA(cudaFree(ctx->d_scratch));
+      ctx->d_scratch = nullptr; ctx->scratch_bytes = 0;
+    }
+    size_t want = bytes < (size_t)(1 << 20) ? (size_t)(1 << 20) : bytes;
+    TRVB_CUDA(cudaMalloc(&ctx->d_scratch, want));
+    ctx->scratch_bytes = want;
+  }
+  *out = ctx->d_scratch;
+  return 0;
+}
+
+// Per-axis correction tables, evaluated on the host with the reference's
+// expressions so the device only multiplies three table entries.
+//   sinc:  S/field.cpp:1136-1145   u = M_PI * m / double(n); sin(u)/u (1 at m=0)
+//   alias: S/field.cpp:3445-3502   s2 = sin(u)^2 (0 at m = 0);
+//          ngp 1; cic 1 - 2/3 s2; tsc 1 - s2 + 2/15 s2^2;
+//          pcs 1 - 4/3 s2 + 2/5 s2^2 - 4/315 s2^3
+static int build_tables(trvb_ctx* ctx) {
+  for (int ax = 0; ax < 3; ax++) {
+    const int n = ctx->g.n[ax];
+    std::vector<double> sinc(n), alias(n);
+    for (int i = 0; i < n; i++) {
+      int m = signed_index(i, n);
+      double u = M_PI * m / double(n);
+      sinc[i] = (m != 0) ? std::sin(u) / u : 1.;
+      double s2 = (m != 0) ? std::sin(u) * std::sin(u) : 0.;
+      double a = 1.;
+      switch (ctx->g.order) {
+        case 1: a = 1.; break;
+        case 2: a = (1. - 2./3. * s2); break;
+        case 3: a = (1. - s2 + 2./15. * s2 * s2); break;
+        case 4: a = (1. - 4./3. * s2 + 2./5. * s2 * s2 - 4./315. * s2 * s2 * s2); break;
+      }
+      alias[i] = a;
+    }
+    TRVB_CUDA(cudaMalloc(&ctx->d_sinc[ax], sizeof(double) * n));
+    TRVB_CUDA(cudaMalloc(&ctx->d_alias[ax], sizeof(double) * n));
+    TRVB_CUDA(cudaMemcpyAsync(ctx->d_sinc[ax], sinc.data(), sizeof(double) * n,
+                              cudaMemcpyHostToDevice, ctx->stream));
+    TRVB_CUDA(cudaMemcpyAsync(ctx->d_alias[ax], alias.data(), sizeof(double) * n,
+                              cudaMemcpyHostToDevice, ctx->stream));
+  }
+  TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+static void fill_grid(GridDesc& g, const int n[3], const double L[3], int order) {
+  for (int i = 0; i < 3; i++) {
+    g.n[i] = n[i]; g.L[i] = L[i];
+    g.dr[i] = L[i] / n[i];
+    g.dk[i] = 2. * M_PI / L[i];
+  }
+  g.nh = n[2] / 2 + 1;
+  g.nmesh = (long long)n[0] * n[1] * n[2];
+  g.vol = L[0] * L[1] * L[2];
+  g.vol_cell = g.vol / double(g.nmesh);
+  g.order = order;
+}
+
+extern "C" int trvb_ctx_create(trvb_ctx** out, int device, const int ngrid[3],
+                               const double boxsize[3], int assignment_order) {
+  TRVB_REQUIRE(out && ngrid && boxsize, "trvb_ctx_create: null argument");
+  TRVB_REQUIRE(assignment_order >= 1 && assignment_order <= 4,
+               "trvb_ctx_create: assignment order %d not in 1..4", assignment_order);
+  for (int i = 0; i < 3; i++) {
+    TRVB_REQUIRE(ngrid[i] > 0 && boxsize[i] > 0.,
+                 "trvb_ctx_create: non-positive grid/box along axis %d", i);
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    trvb_set_error("trvb_ctx_create: no CUDA device available (%s); this "
+                   "library has no CPU fallback", cudaGetErrorString(e));
+    return 3;
+  }
+  TRVB_REQUIRE(device >= 0 && device < ndev, "trvb_ctx_create: device %d of %d",
+               device, ndev);
+  TRVB_CUDA(cudaSetDevice(device));
+  trvb_ctx* ctx = new trvb_ctx();
+  ctx->device = device;
+  fill_grid(ctx->g, ngrid, boxsize, assignment_order);
+  TRVB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  cudaDeviceProp prop;
+  TRVB_CUDA(cudaGetDeviceProperties(&prop, device));
+  ctx->num_sms = prop.multiProcessorCount;
+  int st = build_tables(ctx);
+  if (st) { delete ctx; return st; }
+  *out = ctx;
+  return 0;
+}
+
+extern "C" int trvb_subgrid_create(trvb_ctx* parent, trvb_ctx** out,
+                                   const int nsub[3]) {
+  TRVB_REQUIRE(parent && out && nsub, "trvb_subgrid_create: null argument");
+  TRVB_REQUIRE(parent->parent == nullptr,
+               "trvb_subgrid_create: parent must be a root context");
+  for (int i = 0; i < 3; i++) {
+    TRVB_REQUIRE(nsub[i] > 0 && nsub[i] <= parent->g.n[i],
+                 "trvb_subgrid_create: nsub[%d]=%d outside (0, %d]", i, nsub[i],
+                 parent->g.n[i]);
+  }
+  TRVB_CUDA(cudaSetDevice(parent->device));
+  trvb_ctx* ctx = new trvb_ctx();
+  ctx->device = parent->device;
+  ctx->parent = parent;
+  fill_grid(ctx->g, nsub, parent->g.L, parent->g.order);
+  ctx->stream = parent->stream;   // shares the parent's stream
+  ctx->num_sms = parent->num_sms;
+  *out = ctx;
+  return 0;
+}
+
+extern "C" void trvb_ctx_destroy(trvb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->has_z2z) cufftDestroy(ctx->plan_z2z);
+  if (ctx->has_d2z) cufftDestroy(ctx->plan_d2z);
+  if (ctx->has_z2d) cufftDestroy(ctx->plan_z2d);
+  for (int ax = 0; ax < 3; ax++) {
+    if (ctx->d_sinc[ax]) cudaFree(ctx->d_sinc[ax]);
+    if (ctx->d_alias[ax]) cudaFree(ctx->d_alias[ax]);
+  }
+  for (auto& kv : ctx->sjl) {
+    if (kv.second.d_y) cudaFree(kv.second.d_y);
+    if (kv.second.d_c) cudaFree(kv.second.d_c);
+  }
+  if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+  if (!ctx->parent && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" int trvb_ctx_sync(trvb_ctx* ctx) {
+  TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" void* trvb_ctx_stream(trvb_ctx* ctx) { return (void*)ctx->stream; }
+extern "C" long long trvb_ctx_nmesh(const trvb_ctx* ctx) { return ctx->g.nmesh; }
+
+extern "C" size_t trvb_mesh_bytes(const trvb_ctx* ctx, int layout) {
+  const GridDesc& g = ctx->g;
+  switch (layout) {
+    case TRVB_REAL: return sizeof(double) * (size_t)g.nmesh;
+    case TRVB_COMPLEX: return 2 * sizeof(double) * (size_t)g.nmesh;
+    case TRVB_HALF: return 2 * sizeof(double) * (size_t)g.n[0] * g.n[1] * g.nh;
+  }
+  return 0;
+}
+
+extern "C" int trvb_mem_info(trvb_ctx* ctx, size_t* free_bytes, size_t* total_bytes) {
+  TRVB_CUDA(cudaSetDevice(ctx->device));
+  TRVB_CUDA(cudaMemGetInfo(free_bytes, total_bytes));
+  return 0;
+}
+
+extern "C" int trvb_malloc(trvb_ctx* ctx, void** dptr, size_t bytes) {
+  TRVB_CUDA(cudaSetDevice(ctx->device));
+  TRVB_CUDA(cudaMalloc(dptr, bytes ? bytes : 8));
+  return 0;
+}
+
+extern "C" int trvb_free(trvb_ctx* ctx, void* dptr) {
+  if (!dptr) return 0;
+  TRVB_CUDA(cudaSetDevice(ctx->device));
+  TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  TRVB_CUDA(cudaFree(dptr));
+  return 0;
+}
+
+extern "C" int trvb_memset0(trvb_ctx* ctx, void* dptr, size_t bytes) {
+  TRVB_CUDA(cudaMemsetAsync(dptr, 0, bytes, ctx->stream));
+  return 0;
+}
+
+extern "C" int trvb_h2d(trvb_ctx* ctx, void* dptr, const void* hptr, size_t bytes) {
+  TRVB_CUDA(cudaMemcpyAsync(dptr, hptr, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int trvb_d2h(trvb_ctx* ctx, void* hptr, const void* dptr, size_t bytes) {
+  TRVB_CUDA(cudaMemcpyAsync(hptr, dptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int trvb_d2d(trvb_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  TRVB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  return 0;
+}
+
+extern "C" int trvb_sjl_table(trvb_ctx* ctx, int ell, const double* y,
+                              const double* c, int nsample, double step) {
+  TRVB_REQUIRE(ctx && y && c && nsample >= 2 && step > 0.,
+               "trvb_sjl_table: bad argument");
+  trvb_ctx* root = ctx->parent ? ctx->parent : ctx;
+  SjlTable& t = root->sjl[ell];
+  if (t.d_y) { TRVB_CUDA(cudaStreamSynchronize(root->stream)); cudaFree(t.d_y); cudaFree(t.d_c); }
+  TRVB_CUDA(cudaMalloc(&t.d_y, sizeof(double) * nsample));
+  TRVB_CUDA(cudaMalloc(&t.d_c, sizeof(double) * nsample));
+  TRVB_CUDA(cudaMemcpyAsync(t.d_y, y, sizeof(double) * nsample,
+                            cudaMemcpyHostToDevice, root->stream));
+  TRVB_CUDA(cudaMemcpyAsync(t.d_c, c, sizeof(double) * nsample,
+                            cudaMemcpyHostToDevice, root->stream));
+  TRVB_CUDA(cudaStreamSynchronize(root->stream));
+  t.nsample = nsample; t.step = step;
+  return 0;
+}

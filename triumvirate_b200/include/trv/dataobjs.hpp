@@ -1,0 +1,71 @@
+// dataobjs.hpp -- Binning, LineOfSight and measurement structs
+// (mirror of I/dataobjs.hpp:58-282; S/dataobjs.cpp:134-249).
+#ifndef TRV_B200_DATAOBJS_HPP_
+#define TRV_B200_DATAOBJS_HPP_
+
+#include <complex>
+#include <string>
+#include <vector>
+
+#include "monitor.hpp"
+#include "parameters.hpp"
+
+namespace trv {
+
+class Binning {
+ public:
+  std::string space;
+  std::string scheme;
+  double bin_min = 0.;
+  double bin_max = 0.;
+  int num_bins = 0;
+  std::vector<double> bin_edges;
+  std::vector<double> bin_centres;
+  std::vector<double> bin_widths;
+
+  explicit Binning(std::string space, std::string scheme);
+  explicit Binning(trv::ParameterSet& params);
+
+  void set_bins(double coord_min, double coord_max, int nbin);
+  void set_bins();
+  void set_bins(double boxsize_max, int ngrid_min);
+  void set_bins(std::vector<double> bin_edges);
+
+ private:
+  int nbin_pad = 5;
+  double dbin_pad_fourier = 1.e-3;
+  double dbin_pad_config = 10.;
+  void compute_binning();
+};
+
+struct LineOfSight {
+  double pos[3];
+};
+
+struct BispecMeasurements {
+  int dim = 0;
+  std::vector<double> k1_bin;
+  std::vector<double> k2_bin;
+  std::vector<double> k1_eff;
+  std::vector<double> k2_eff;
+  std::vector<int> nmodes_1;
+  std::vector<int> nmodes_2;
+  std::vector< std::complex<double> > bk_raw;
+  std::vector< std::complex<double> > bk_shot;
+};
+
+struct ThreePCFMeasurements {
+  int dim = 0;
+  std::vector<double> r1_bin;
+  std::vector<double> r2_bin;
+  std::vector<double> r1_eff;
+  std::vector<double> r2_eff;
+  std::vector<int> npairs_1;
+  std::vector<int> npairs_2;
+  std::vector< std::complex<double> > zeta_raw;
+  std::vector< std::complex<double> > zeta_shot;
+};
+
+}  // namespace trv
+
+#endif  // TRV_B200_DATAOBJS_HPP_

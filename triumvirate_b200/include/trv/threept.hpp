@@ -1,0 +1,73 @@
+// threept.hpp -- three-point estimators (mirror of I/threept.hpp:115-314).
+#ifndef TRV_B200_THREEPT_HPP_
+#define TRV_B200_THREEPT_HPP_
+
+#include <complex>
+
+#include "dataobjs.hpp"
+#include "field.hpp"
+#include "maths.hpp"
+#include "monitor.hpp"
+#include "parameters.hpp"
+#include "particles.hpp"
+
+namespace trv {
+
+/// Spherical orders (m1, m2, M) of one term (S/threept.cpp:40-58).
+struct SphericalOrderTriplet {
+  int m1, m2, M;
+  bool is_zeros() const { return m1 == 0 && m2 == 0 && M == 0; }
+  bool is_inverse(const SphericalOrderTriplet& o) const {
+    return m1 + o.m1 == 0 && m2 + o.m2 == 0 && M + o.M == 0;
+  }
+};
+
+/// (2l1+1)(2l2+1)(2L+1) 3j(l1 l2 L; 0 0 0) 3j(l1 l2 L; m1 m2 M)
+/// (S/threept.cpp:65-71).
+double calc_coupling_coeff_3pt(int ell1, int ell2, int ELL, int m1, int m2, int M);
+
+/// Throws if 3j(l1 l2 L; 0 0 0) vanishes (S/threept.cpp:73-89).
+void validate_multipole_coupling(trv::ParameterSet& params);
+
+/// 1 / (alpha sum ws nz^2 wc^3) (S/threept.cpp:96-136).
+double calc_bispec_normalisation_from_particles(
+  ParticleCatalogue& particles, double alpha = 1.);
+
+/// 1 / (dV sum_x n_w(x)^3) / alpha^3 (S/threept.cpp:138-149).
+double calc_bispec_normalisation_from_mesh(
+  ParticleCatalogue& particles, trv::ParameterSet& params, double alpha = 1.);
+
+/// sum_data y_LM w^3 + alpha^3 sum_rand y_LM w^3 (S/threept.cpp:156-208).
+std::complex<double> calc_ylm_wgtd_shotnoise_amp_for_bispec(
+  ParticleCatalogue& particles_data, ParticleCatalogue& particles_rand,
+  LineOfSight* los_data, LineOfSight* los_rand, double alpha, int ell, int m);
+
+/// alpha^3 sum y_LM w^3 (S/threept.cpp:210-236).
+std::complex<double> calc_ylm_wgtd_shotnoise_amp_for_bispec(
+  ParticleCatalogue& particles, LineOfSight* los, double alpha, int ell, int m);
+
+/// Survey-type bispectrum, local plane-parallel (S/threept.cpp:248-1012).
+trv::BispecMeasurements compute_bispec(
+  ParticleCatalogue& catalogue_data, ParticleCatalogue& catalogue_rand,
+  LineOfSight* los_data, LineOfSight* los_rand,
+  trv::ParameterSet& params, trv::Binning& kbinning, double norm_factor);
+
+/// Survey-type 3PCF, local plane-parallel (S/threept.cpp:1014-1471).
+trv::ThreePCFMeasurements compute_3pcf(
+  ParticleCatalogue& catalogue_data, ParticleCatalogue& catalogue_rand,
+  LineOfSight* los_data, LineOfSight* los_rand,
+  trv::ParameterSet& params, trv::Binning& rbinning, double norm_factor);
+
+/// Periodic-box bispectrum, global plane-parallel (S/threept.cpp:1473-2188).
+trv::BispecMeasurements compute_bispec_in_gpp_box(
+  ParticleCatalogue& catalogue_data,
+  trv::ParameterSet& params, trv::Binning kbinning, double norm_factor);
+
+/// Periodic-box 3PCF, global plane-parallel (S/threept.cpp:2190-2619).
+trv::ThreePCFMeasurements compute_3pcf_in_gpp_box(
+  ParticleCatalogue& catalogue_data,
+  trv::ParameterSet& params, trv::Binning& rbinning, double norm_factor);
+
+}  // namespace trv
+
+#endif  // TRV_B200_THREEPT_HPP_

@@ -1,0 +1,268 @@
+// capi.cpp -- flat C entry points over the trv:: C++ API (libtrv_b200.so),
+// the binding surface for Python (ctypes) and other FFI callers.  It plays
+// the role of the reference's Cython layer (T/_threept.pyx:128-248,
+// T/_particles.pyx:17-34, T/parameters.pyx:395-470): marshal arrays into
+// trv::ParticleCatalogue / trv::ParameterSet / trv::Binning, call the
+// estimator, copy the result vectors back.  Unlike the reference's `compute_*`
+// externs (no `except +`), every C++ exception is caught and reported.
+#include <chrono>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "trv/dataobjs.hpp"
+#include "trv/field.hpp"
+#include "trv/maths.hpp"
+#include "trv/monitor.hpp"
+#include "trv/parameters.hpp"
+#include "trv/particles.hpp"
+#include "trv/threept.hpp"
+
+namespace {
+
+thread_local std::string g_capi_err;
+
+template <class F>
+int guarded(F f) {
+  try {
+    f();
+    return 0;
+  } catch (const trv::sys::DeviceError& e) {
+    g_capi_err = e.what(); return 3;
+  } catch (const std::invalid_argument& e) {
+    g_capi_err = e.what(); return 2;
+  } catch (const std::exception& e) {
+    g_capi_err = e.what(); return 1;
+  }
+}
+
+void set_params(
+  trv::ParameterSet& p, const char* catalogue_type, const char* statistic_type,
+  const double* boxsize, const int* ngrid, const char* assignment,
+  const char* interlace, int ell1, int ell2, int ELL, const char* form, int idx_bin,
+  const char* binning, double bin_min, double bin_max, int num_bins,
+  int verbose, int deterministic, int part_rank, int part_count
+) {
+  p.catalogue_type = catalogue_type;
+  p.statistic_type = statistic_type;
+  for (int ax = 0; ax < 3; ax++) { p.boxsize[ax] = boxsize[ax]; p.ngrid[ax] = ngrid[ax]; }
+  p.assignment = assignment;
+  p.interlace = interlace;
+  p.ell1 = ell1; p.ell2 = ell2; p.ELL = ELL;
+  p.form = form; p.idx_bin = idx_bin;
+  p.binning = binning; p.bin_min = bin_min; p.bin_max = bin_max; p.num_bins = num_bins;
+  p.verbose = verbose; p.progbar = "false";
+  p.deterministic = deterministic;
+  p.part_rank = part_rank; p.part_count = part_count;
+  p.validate(false);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* trv_last_error() { return g_capi_err.c_str(); }
+
+int trv_gpu_count() { return trv::sys::get_gpu_count(); }
+
+void trv_counters(int* count_fft, int* count_ifft, double* gib_gpu_max) {
+  *count_fft = trv::sys::count_fft; *count_ifft = trv::sys::count_ifft;
+  *gib_gpu_max = trv::sys::gbytesMaxMemGPU;
+}
+
+/// Three-point estimators.  Arrays as in the reference's Cython bindings:
+/// six float64 columns per catalogue (nz/ws/wc may be null: 0/1/1), LOS as
+/// contiguous (n, 3).  `stat`: "bispec" | "3pcf"; `catalogue_type`: "sim"
+/// (trv::compute_*_in_gpp_box) | "survey" (trv::compute_bispec / compute_3pcf).
+/// Outputs hold dv_dim entries (raw/shot: interleaved re, im).
+int trv_threept(
+  const char* stat, const char* catalogue_type,
+  int nd, const double* xd, const double* yd, const double* zd,
+  const double* nzd, const double* wsd, const double* wcd, const double* los_d,
+  int nr, const double* xr, const double* yr, const double* zr,
+  const double* nzr, const double* wsr, const double* wcr, const double* los_r,
+  const double* boxsize, const int* ngrid, const char* assignment, const char* interlace,
+  int ell1, int ell2, int ELL, const char* form, int idx_bin,
+  const char* binning, double bin_min, double bin_max, int num_bins,
+  const double* custom_edges,
+  double norm_factor, int verbose, int deterministic, int part_rank, int part_count,
+  int* dim, double* c1_bin, double* c2_bin, double* c1_eff, double* c2_eff,
+  int* n1, int* n2, double* raw, double* shot, double* elapsed_s
+) {
+  return guarded([&]() {
+    trv::ParameterSet params;
+    set_params(params, catalogue_type, stat, boxsize, ngrid, assignment, interlace,
+               ell1, ell2, ELL, form, idx_bin, binning, bin_min, bin_max, num_bins,
+               verbose, deterministic, part_rank, part_count);
+    trv::Binning bins(params);
+    if (custom_edges != nullptr) {
+      bins.set_bins(std::vector<double>(custom_edges, custom_edges + num_bins + 1));
+    } else {
+      bins.set_bins();
+    }
+    const bool survey = std::string(catalogue_type) == "survey";
+    trv::ParticleCatalogue data(verbose), rand(verbose);
+    data.load_particle_arrays(nd, xd, yd, zd, nzd, wsd, wcd);
+    if (survey) rand.load_particle_arrays(nr, xr, yr, zr, nzr, wsr, wcr);
+    trv::LineOfSight* ld = (trv::LineOfSight*)los_d;
+    trv::LineOfSight* lr = (trv::LineOfSight*)los_r;
+
+    auto t0 = std::chrono::steady_clock::now();
+    if (std::string(stat) == "bispec") {
+      trv::BispecMeasurements out = survey
+        ? trv::compute_bispec(data, rand, ld, lr, params, bins, norm_factor)
+        : trv::compute_bispec_in_gpp_box(data, params, bins, norm_factor);
+      *dim = out.dim;
+      for (int i = 0; i < out.dim; i++) {
+        c1_bin[i] = out.k1_bin[i]; c2_bin[i] = out.k2_bin[i];
+        c1_eff[i] = out.k1_eff[i]; c2_eff[i] = out.k2_eff[i];
+        n1[i] = out.nmodes_1[i]; n2[i] = out.nmodes_2[i];
+        raw[2*i] = out.bk_raw[i].real(); raw[2*i+1] = out.bk_raw[i].imag();
+        shot[2*i] = out.bk_shot[i].real(); shot[2*i+1] = out.bk_shot[i].imag();
+      }
+    } else {
+      trv::ThreePCFMeasurements out = survey
+        ? trv::compute_3pcf(data, rand, ld, lr, params, bins, norm_factor)
+        : trv::compute_3pcf_in_gpp_box(data, params, bins, norm_factor);
+      *dim = out.dim;
+      for (int i = 0; i < out.dim; i++) {
+        c1_bin[i] = out.r1_bin[i]; c2_bin[i] = out.r2_bin[i];
+        c1_eff[i] = out.r1_eff[i]; c2_eff[i] = out.r2_eff[i];
+        n1[i] = out.npairs_1[i]; n2[i] = out.npairs_2[i];
+        raw[2*i] = out.zeta_raw[i].real(); raw[2*i+1] = out.zeta_raw[i].imag();
+        shot[2*i] = out.zeta_shot[i].real(); shot[2*i+1] = out.zeta_shot[i].imag();
+      }
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    if (elapsed_s) *elapsed_s = std::chrono::duration<double>(t1 - t0).count();
+  });
+}
+
+/// Normalisation factors (trv::calc_bispec_normalisation_from_particles /
+/// _from_mesh).
+int trv_norm(
+  int from_mesh, int n, const double* x, const double* y, const double* z,
+  const double* nz, const double* ws, const double* wc, double alpha,
+  const double* boxsize, const int* ngrid, const char* assignment, double* norm
+) {
+  return guarded([&]() {
+    trv::ParticleCatalogue cat(60);
+    cat.load_particle_arrays(n, x, y, z, nz, ws, wc);
+    if (from_mesh) {
+      trv::ParameterSet params;
+      set_params(params, "sim", "bispec", boxsize, ngrid, assignment, "false",
+                 0, 0, 0, "diag", 0, "lin", 0.005, 0.105, 4, 60, 0, 0, 1);
+      *norm = trv::calc_bispec_normalisation_from_mesh(cat, params, alpha);
+    } else {
+      *norm = trv::calc_bispec_normalisation_from_particles(cat, alpha);
+    }
+  });
+}
+
+/// trv::MeshField pipeline for intermediate checks.  `stage`: 0 assignment,
+/// 1 + fourier_transform, 2 + apply_assignment_compensation,
+/// 3 + inv_fourier_transform.  Weights: complex per particle or null (unit).
+/// `field_out`: 2 * nmesh doubles.
+int trv_mesh(
+  int stage, int subtract_mean, int interlace, int deterministic,
+  int n, const double* x, const double* y, const double* z,
+  const double* w_re, const double* w_im,
+  const double* boxsize, const int* ngrid, const char* assignment,
+  double* field_out, double* elapsed_assign_s
+) {
+  return guarded([&]() {
+    trv::ParameterSet params;
+    set_params(params, "sim", "bispec", boxsize, ngrid, assignment, "false",
+               0, 0, 0, "diag", 0, "lin", 0.005, 0.105, 4, 60, deterministic, 0, 1);
+    if (interlace) params.interlace = "true";   // after validate(): SURVEY.md F2
+    trv::ParticleCatalogue cat(60);
+    cat.load_particle_arrays(n, x, y, z, nullptr, nullptr, nullptr);
+    trv::MeshField mesh(params, true, "`capi_mesh`");
+    std::vector<double> weights(2 * (size_t)n);
+    for (int i = 0; i < n; i++) {
+      weights[2 * i] = w_re ? w_re[i] : 1.;
+      weights[2 * i + 1] = w_im ? w_im[i] : 0.;
+    }
+    auto t0 = std::chrono::steady_clock::now();
+    mesh.assign_weighted_field_to_mesh(cat, reinterpret_cast<double (*)[2]>(weights.data()));
+    trvb_ctx_sync(mesh.context());
+    auto t1 = std::chrono::steady_clock::now();
+    if (elapsed_assign_s) *elapsed_assign_s = std::chrono::duration<double>(t1 - t0).count();
+    if (subtract_mean) {
+      const double nbar = double(cat.ntotal) / mesh.vol;
+      trv::dev::check(trvb_mesh_add_const(mesh.context(), mesh.device_view(), -nbar),
+                      "trvb_mesh_add_const");
+    }
+    if (stage >= 1) mesh.fourier_transform();
+    if (stage >= 2) mesh.apply_assignment_compensation();
+    if (stage >= 3) mesh.inv_fourier_transform();
+    mesh.sync_host();
+    std::memcpy(field_out, mesh.field, 2 * sizeof(double) * (size_t)params.nmesh);
+  });
+}
+
+void trv_ylm(int ell, int m, const double* pos, int n, double* out) {
+  for (int i = 0; i < n; i++) {
+    double p[3] = {pos[3*i], pos[3*i+1], pos[3*i+2]};
+    std::complex<double> y = trv::maths::SphericalHarmonicCalculator::
+      calc_reduced_spherical_harmonic(ell, m, p);
+    out[2*i] = y.real(); out[2*i+1] = y.imag();
+  }
+}
+
+void trv_sjl(int ell, const double* x, int n, double* out) {
+  trv::maths::SphericalBesselCalculator sj(ell);
+  for (int i = 0; i < n; i++) out[i] = sj.eval(x[i]);
+}
+
+double trv_sjl_exact(int ell, double x) { return trv::maths::sph_bessel_jl(ell, x); }
+
+double trv_w3j(int j1, int j2, int j3, int m1, int m2, int m3) {
+  return trv::maths::wigner_3j(j1, j2, j3, m1, m2, m3);
+}
+
+double trv_coupling(int l1, int l2, int L, int m1, int m2, int M) {
+  return trv::calc_coupling_coeff_3pt(l1, l2, L, m1, m2, M);
+}
+
+int trv_binning(
+  const char* space, const char* scheme, double bmin, double bmax, int nb,
+  const double* boxsize, const int* ngrid,
+  double* edges, double* centres, double* widths
+) {
+  return guarded([&]() {
+    trv::ParameterSet params;
+    for (int ax = 0; ax < 3; ax++) { params.boxsize[ax] = boxsize[ax]; params.ngrid[ax] = ngrid[ax]; }
+    params.space = space; params.binning = scheme;
+    params.bin_min = bmin; params.bin_max = bmax; params.num_bins = nb;
+    trv::Binning b(params);
+    b.set_bins();
+    for (int i = 0; i <= nb; i++) edges[i] = b.bin_edges[i];
+    for (int i = 0; i < nb; i++) { centres[i] = b.bin_centres[i]; widths[i] = b.bin_widths[i]; }
+  });
+}
+
+int trv_validate(
+  const char* catalogue_type, const char* statistic_type,
+  const char* assignment, const char* interlace, const char* form,
+  int ell1, int ell2, int ELL, int num_bins, int idx_bin,
+  double bin_min, double bin_max,
+  char* shape_out, char* interlace_out, char* npoint_out, char* space_out,
+  int* assignment_order
+) {
+  return guarded([&]() {
+    trv::ParameterSet params;
+    const double boxsize[3] = {1000., 1000., 1000.};
+    const int ngrid[3] = {64, 64, 64};
+    set_params(params, catalogue_type, statistic_type, boxsize, ngrid, assignment,
+               interlace, ell1, ell2, ELL, form, idx_bin, "lin", bin_min, bin_max,
+               num_bins, 60, 0, 0, 1);
+    std::strcpy(shape_out, params.shape.c_str());
+    std::strcpy(interlace_out, params.interlace.c_str());
+    std::strcpy(npoint_out, params.npoint.c_str());
+    std::strcpy(space_out, params.space.c_str());
+    *assignment_order = params.assignment_order;
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,232 @@
+// particles.cpp -- ParticleCatalogue: host-side AoS catalogue with the
+// reference's public members and alignment helpers (S/particles.cpp:512-888).
+#include "trv/particles.hpp"
+
+#include <cmath>
+
+namespace trvs = trv::sys;
+
+namespace trv {
+
+namespace {
+
+void require_data(const ParticleCatalogue& c) {
+  if (c.pdata == nullptr) {
+    if (trvs::currTask == 0) trvs::logger.error("Particle data are uninitialised.");
+    throw trvs::InvalidDataError("Particle data are uninitialised.");
+  }
+}
+
+void warn_if_overflow(ParticleCatalogue& c, const double boxsize[3], const char* op) {
+  c.calc_pos_extents(false);
+  for (int ax = 0; ax < 3; ax++) {
+    if (c.pos_span[ax] > boxsize[ax] && trvs::currTask == 0) {
+      trvs::logger.warn(
+        "Catalogue extent exceeds the box size along axis %d: span = %.3f, "
+        "boxsize = %.3f (source=%s). Some particles may lie outside the box after %s.",
+        ax, c.pos_span[ax], boxsize[ax], c.source.c_str(), op);
+    }
+  }
+}
+
+}  // namespace
+
+ParticleCatalogue::ParticleCatalogue(int verbose) {
+  if (verbose >= 0) trvs::logger.reset_level(verbose);
+}
+
+ParticleCatalogue::~ParticleCatalogue() { this->finalise_particles(); }
+
+void ParticleCatalogue::initialise_particles(const int num) {
+  if (num <= 0) {
+    if (trvs::currTask == 0) trvs::logger.error("Number of particles is non-positive.");
+    throw trvs::InvalidParameterError("Number of particles is non-positive.");
+  }
+  this->reset_particles();
+  this->ntotal = num;
+  this->pdata = new ParticleData[num];
+  trvs::gbytesMem += trvs::size_in_gb<ParticleData>(num);
+  trvs::update_maxmem();
+}
+
+void ParticleCatalogue::finalise_particles() { this->reset_particles(); }
+
+void ParticleCatalogue::reset_particles() {
+  if (this->pdata != nullptr) {
+    delete[] this->pdata;
+    this->pdata = nullptr;
+    trvs::gbytesMem -= trvs::size_in_gb<ParticleData>(this->ntotal);
+  }
+}
+
+ParticleData& ParticleCatalogue::operator[](const int pid) { return this->pdata[pid]; }
+
+int ParticleCatalogue::load_particle_data(
+  std::vector<double> x, std::vector<double> y, std::vector<double> z,
+  std::vector<double> nz, std::vector<double> ws, std::vector<double> wc
+) {
+  const std::size_t n = x.size();
+  if (!(y.size() == n && z.size() == n && nz.size() == n && ws.size() == n
+        && wc.size() == n)) {
+    this->source = "extdata";
+    if (trvs::currTask == 0) {
+      trvs::logger.error("Inconsistent particle data dimensions (source=%s).",
+                         this->source.c_str());
+    }
+    throw trvs::InvalidDataError("Inconsistent particle data dimensions (source=%s).",
+                                 this->source.c_str());
+  }
+  return this->load_particle_arrays(static_cast<int>(n), x.data(), y.data(), z.data(),
+                                    nz.data(), ws.data(), wc.data());
+}
+
+int ParticleCatalogue::load_particle_arrays(
+  int n, const double* x, const double* y, const double* z,
+  const double* nz, const double* ws, const double* wc
+) {
+  this->source = "extdata";
+  this->initialise_particles(n);
+#pragma omp parallel for
+  for (int pid = 0; pid < n; pid++) {
+    ParticleData& p = this->pdata[pid];
+    p.pos[0] = x[pid]; p.pos[1] = y[pid]; p.pos[2] = z[pid];
+    p.nz = nz ? nz[pid] : 0.;
+    p.ws = ws ? ws[pid] : 1.;
+    p.wc = wc ? wc[pid] : 1.;
+    p.w = p.ws * p.wc;   // S/particles.cpp:556
+  }
+  this->calc_total_weights();
+  this->calc_pos_extents();
+  return 0;
+}
+
+void ParticleCatalogue::calc_total_weights() {
+  require_data(*this);
+  double wt = 0., wst = 0.;
+#pragma omp parallel for reduction(+:wt, wst)
+  for (int pid = 0; pid < this->ntotal; pid++) {
+    wt += this->pdata[pid].w;
+    wst += this->pdata[pid].ws;
+  }
+  this->wtotal = wt;
+  this->wstotal = wst;
+}
+
+void ParticleCatalogue::calc_pos_extents(bool init) {
+  (void)init;
+  require_data(*this);
+  double lo[3], hi[3];
+  for (int ax = 0; ax < 3; ax++) lo[ax] = hi[ax] = this->pdata[0].pos[ax];
+#pragma omp parallel for reduction(min:lo[:3]) reduction(max:hi[:3])
+  for (int pid = 0; pid < this->ntotal; pid++) {
+    for (int ax = 0; ax < 3; ax++) {
+      const double v = this->pdata[pid].pos[ax];
+      if (v < lo[ax]) lo[ax] = v;
+      if (v > hi[ax]) hi[ax] = v;
+    }
+  }
+  for (int ax = 0; ax < 3; ax++) {
+    this->pos_min[ax] = lo[ax];
+    this->pos_max[ax] = hi[ax];
+    this->pos_span[ax] = hi[ax] - lo[ax];
+  }
+}
+
+void ParticleCatalogue::offset_coords(const double dpos[3]) {
+  require_data(*this);
+#pragma omp parallel for
+  for (int pid = 0; pid < this->ntotal; pid++) {
+    for (int ax = 0; ax < 3; ax++) this->pdata[pid].pos[ax] -= dpos[ax];
+  }
+  this->calc_pos_extents();
+}
+
+void ParticleCatalogue::offset_coords_for_periodicity(const double boxsize[3]) {
+  // Wrap only, no centring (S/particles.cpp:678-699).
+#pragma omp parallel for
+  for (int pid = 0; pid < this->ntotal; pid++) {
+    for (int ax = 0; ax < 3; ax++) {
+      double& v = this->pdata[pid].pos[ax];
+      if (v >= boxsize[ax]) v = std::fmod(v, boxsize[ax]);
+      else if (v < 0.) v = std::fmod(v, boxsize[ax]) + boxsize[ax];
+    }
+  }
+  this->calc_pos_extents();
+}
+
+void ParticleCatalogue::centre_in_box(ParticleCatalogue& catalogue, const double boxsize[3]) {
+  warn_if_overflow(catalogue, boxsize, "centring");
+  double dvec[3];
+  for (int ax = 0; ax < 3; ax++) {
+    dvec[ax] = (catalogue.pos_min[ax] + catalogue.pos_max[ax]) / 2. - boxsize[ax] / 2.;
+  }
+  catalogue.offset_coords(dvec);
+}
+
+void ParticleCatalogue::centre_in_box(
+  ParticleCatalogue& catalogue, ParticleCatalogue& catalogue_ref, const double boxsize[3]
+) {
+  warn_if_overflow(catalogue, boxsize, "centring");
+  warn_if_overflow(catalogue_ref, boxsize, "centring");
+  double dvec[3];
+  for (int ax = 0; ax < 3; ax++) {
+    dvec[ax] = (catalogue_ref.pos_min[ax] + catalogue_ref.pos_max[ax]) / 2.
+      - boxsize[ax] / 2.;
+  }
+  catalogue_ref.offset_coords(dvec);
+  catalogue.offset_coords(dvec);
+}
+
+void ParticleCatalogue::pad_in_box(
+  ParticleCatalogue& catalogue, const double boxsize[3], const double boxsize_pad[3]
+) {
+  warn_if_overflow(catalogue, boxsize, "padding");
+  double dvec[3];
+  for (int ax = 0; ax < 3; ax++) {
+    dvec[ax] = catalogue.pos_min[ax] - boxsize_pad[ax] * boxsize[ax];
+  }
+  catalogue.offset_coords(dvec);
+}
+
+void ParticleCatalogue::pad_in_box(
+  ParticleCatalogue& catalogue, ParticleCatalogue& catalogue_ref,
+  const double boxsize[3], const double boxsize_pad[3]
+) {
+  warn_if_overflow(catalogue, boxsize, "padding");
+  warn_if_overflow(catalogue_ref, boxsize, "padding");
+  double dvec[3];
+  for (int ax = 0; ax < 3; ax++) {
+    dvec[ax] = catalogue_ref.pos_min[ax] - boxsize_pad[ax] * boxsize[ax];
+  }
+  catalogue_ref.offset_coords(dvec);
+  catalogue.offset_coords(dvec);
+}
+
+void ParticleCatalogue::pad_grids(
+  ParticleCatalogue& catalogue,
+  const double boxsize[3], const int ngrid[3], const double ngrid_pad[3]
+) {
+  catalogue.calc_pos_extents(false);
+  double dvec[3];
+  for (int ax = 0; ax < 3; ax++) {
+    dvec[ax] = catalogue.pos_min[ax];
+    dvec[ax] -= ngrid_pad[ax] * boxsize[ax] / double(ngrid[ax]);
+  }
+  catalogue.offset_coords(dvec);
+}
+
+void ParticleCatalogue::pad_grids(
+  ParticleCatalogue& catalogue, ParticleCatalogue& catalogue_ref,
+  const double boxsize[3], const int ngrid[3], const double ngrid_pad[3]
+) {
+  catalogue_ref.calc_pos_extents(false);
+  double dvec[3];
+  for (int ax = 0; ax < 3; ax++) {
+    dvec[ax] = catalogue_ref.pos_min[ax]
+      - ngrid_pad[ax] * boxsize[ax] / double(ngrid[ax]);
+  }
+  catalogue_ref.offset_coords(dvec);
+  catalogue.offset_coords(dvec);
+}
+
+}  // namespace trv

@@ -1,0 +1,825 @@
+// threept.cpp -- three-point estimators on the device.
+//
+// Same entry points, output layout and arithmetic conventions as the reference
+// (S/threept.cpp:248-2619; formula sheet in SURVEY.md Appendix A), organised
+// around three observations:
+//   1. A shell field F_b^{lm}(x) depends on the bin b only, so each is built
+//      ONCE per (l, m) and all (a, b) pairs are reduced in a single tiled pass
+//      (trvb_gram_reduce) instead of 2 IFFTs + 1 reduction per pair.
+//   2. sum_x F_a F_b G over the n^3 mesh only involves Fourier modes below
+//      2 k_max; it equals (n^3/ns^3) x the sum over an ns^3 sub-grid with
+//      ns > 4 k_max/dk, so shell fields live on the sub-grid whenever the bins
+//      stay well below the Nyquist wavenumber (else ns = n).
+//   3. The shot-noise mesh xi(x) does not depend on the bin pair: one IFFT per
+//      term and one pass over xi for all pairs (trvb_shot_bispec_reduce).
+#include "trv/threept.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <set>
+
+namespace trvs = trv::sys;
+namespace trvm = trv::maths;
+
+namespace trv {
+
+// =====================================================================
+// Coupling coefficients, normalisation, shot-noise amplitude
+// =====================================================================
+
+double calc_coupling_coeff_3pt(int ell1, int ell2, int ELL, int m1, int m2, int M) {
+  return double(2 * ell1 + 1) * double(2 * ell2 + 1) * double(2 * ELL + 1)
+    * trvm::wigner_3j(ell1, ell2, ELL, 0, 0, 0)
+    * trvm::wigner_3j(ell1, ell2, ELL, m1, m2, M);
+}
+
+void validate_multipole_coupling(trv::ParameterSet& params) {
+  const double coupling = trvm::wigner_3j(params.ell1, params.ell2, params.ELL, 0, 0, 0);
+  if (std::fabs(coupling) < trvm::eps_coupling) {
+    const char* msg =
+      "Specified three-point correlator multipole vanishes identically "
+      "owing to zero-valued Wigner 3-j symbol.";
+    if (trvs::currTask == 0) trvs::logger.error(msg);
+    throw trvs::InvalidParameterError(msg);
+  }
+}
+
+double calc_bispec_normalisation_from_particles(ParticleCatalogue& particles, double alpha) {
+  if (particles.pdata == nullptr) {
+    if (trvs::currTask == 0) trvs::logger.error("Particle data are uninitialised.");
+    throw trvs::InvalidDataError("Particle data are uninitialised.");
+  }
+  double norm = 0.;
+#pragma omp parallel for reduction(+:norm)
+  for (int pid = 0; pid < particles.ntotal; pid++) {
+    const ParticleData& p = particles.pdata[pid];
+    norm += p.ws * (p.nz * p.nz) * (p.wc * p.wc * p.wc);
+  }
+  if (norm == 0.) {
+    const char* msg =
+      "Particle 'nz' values appear to be all zeros. "
+      "Check the input catalogue contains valid 'nz' field.";
+    if (trvs::currTask == 0) trvs::logger.error(msg);
+    throw trvs::InvalidDataError(msg);
+  }
+  return 1. / (alpha * norm);
+}
+
+double calc_bispec_normalisation_from_mesh(
+  ParticleCatalogue& particles, trv::ParameterSet& params, double alpha
+) {
+  MeshField catalogue_mesh(params, false, "`catalogue_mesh`");
+  double norm_factor = catalogue_mesh.calc_grid_based_powlaw_norm(particles, 3);
+  norm_factor /= std::pow(alpha, 3);
+  return norm_factor;
+}
+
+namespace {
+
+std::complex<double> cat_sum(trvb_ctx* ctx, dev::Catalogue& cat, int kind, int ell, int m) {
+  double out[2];
+  dev::check(trvb_cat_sum(ctx, cat.get(), kind, ell, m, out), "trvb_cat_sum");
+  return std::complex<double>(out[0], out[1]);
+}
+
+trv::ParameterSet params_for_context(ParticleCatalogue& particles) {
+  // A context is needed only for its device/stream here; any small grid does.
+  (void)particles;
+  trv::ParameterSet p;
+  for (int ax = 0; ax < 3; ax++) { p.boxsize[ax] = 1.; p.ngrid[ax] = 4; }
+  p.assignment_order = 1;
+  return p;
+}
+
+}  // namespace
+
+std::complex<double> calc_ylm_wgtd_shotnoise_amp_for_bispec(
+  ParticleCatalogue& particles_data, ParticleCatalogue& particles_rand,
+  LineOfSight* los_data, LineOfSight* los_rand, double alpha, int ell, int m
+) {
+  auto ctx = dev::acquire_context(params_for_context(particles_data));
+  dev::Catalogue cd(ctx, particles_data, los_data, true);
+  dev::Catalogue cr(ctx, particles_rand, los_rand, true);
+  // Note the `+`: the code, not the header comment, is authoritative
+  // (S/threept.cpp:207).
+  return cat_sum(ctx.get(), cd, TRVB_W_YLM_W3, ell, m)
+    + std::pow(alpha, 3) * cat_sum(ctx.get(), cr, TRVB_W_YLM_W3, ell, m);
+}
+
+std::complex<double> calc_ylm_wgtd_shotnoise_amp_for_bispec(
+  ParticleCatalogue& particles, LineOfSight* los, double alpha, int ell, int m
+) {
+  auto ctx = dev::acquire_context(params_for_context(particles));
+  dev::Catalogue c(ctx, particles, los, true);
+  return std::pow(alpha, 3) * cat_sum(ctx.get(), c, TRVB_W_YLM_W3, ell, m);
+}
+
+// =====================================================================
+// Shared estimator machinery
+// =====================================================================
+
+namespace {
+
+typedef std::complex<double> cdouble;
+
+/// Data-vector layout for a shape (S/threept.cpp:275-298 and 465-770).
+struct DataVector {
+  int dim = 0;
+  std::vector<int> row, col;   // bin indices of each entry
+};
+
+DataVector make_data_vector(const trv::ParameterSet& params, int num_bins) {
+  DataVector dv;
+  const std::string& shape = params.shape;
+  if (shape == "diag") {
+    for (int b = 0; b < num_bins; b++) { dv.row.push_back(b); dv.col.push_back(b); }
+  } else if (shape == "off-diag") {
+    const int off = std::abs(params.idx_bin);
+    for (int i = 0; i < num_bins - off; i++) {
+      if (params.idx_bin >= 0) { dv.row.push_back(i); dv.col.push_back(i + off); }
+      else { dv.row.push_back(i + off); dv.col.push_back(i); }
+    }
+  } else if (shape == "row") {
+    for (int b = 0; b < num_bins; b++) { dv.row.push_back(params.idx_bin); dv.col.push_back(b); }
+  } else if (shape == "full") {
+    for (int a = 0; a < num_bins; a++)
+      for (int b = 0; b < num_bins; b++) { dv.row.push_back(a); dv.col.push_back(b); }
+  } else if (shape == "triu") {
+    // idx = (2N - a + 1) a / 2 + (b - a), b >= a: row-major upper triangle.
+    for (int a = 0; a < num_bins; a++)
+      for (int b = a; b < num_bins; b++) { dv.row.push_back(a); dv.col.push_back(b); }
+  } else {
+    if (trvs::currTask == 0) {
+      trvs::logger.error(
+        "Three-point statistic form is not recognised: `form` = '%s'.", params.form.c_str());
+    }
+    throw trvs::InvalidParameterError(
+      "Three-point statistic form is not recognised: `form` = '%s'.", params.form.c_str());
+  }
+  dv.dim = static_cast<int>(dv.row.size());
+  return dv;
+}
+
+int next_fft_size(int n) {
+  for (int v = std::max(n, 2);; v++) {
+    int r = v;
+    for (int p : {2, 3, 5, 7}) while (r % p == 0) r /= p;
+    if (r == 1) return v;
+  }
+}
+
+std::vector<int> distinct_sorted(const std::vector<int>& v) {
+  std::set<int> s(v.begin(), v.end());
+  return std::vector<int>(s.begin(), s.end());
+}
+
+/// One surviving (m1, m2, M) term with its coupling and mirror factors
+/// (S/threept.cpp:356-419, 1580-1616).
+struct Term {
+  int m1, m2, M;
+  double coupling;
+  double factor_mirror;       // 0 for (0,0,0), else (-1)^ELL
+  double factor_mirror_w3j;   // 0 for (0,0,0), else 1
+};
+
+std::vector<Term> enumerate_terms(const trv::ParameterSet& params, bool survey) {
+  std::vector<Term> terms;
+  std::vector<SphericalOrderTriplet> computed;
+  for (int m1 = -params.ell1; m1 <= params.ell1; m1++) {
+    for (int m2 = -params.ell2; m2 <= params.ell2; m2++) {
+      const int Mlo = survey ? -params.ELL : 0;
+      const int Mhi = survey ? params.ELL : 0;
+      for (int M = Mlo; M <= Mhi; M++) {
+        SphericalOrderTriplet cur = {m1, m2, M};
+        bool redundant = false;
+        for (const SphericalOrderTriplet& t : computed) {
+          if (cur.is_inverse(t)) redundant = true;
+        }
+        if (redundant) continue;
+        const double coupling = calc_coupling_coeff_3pt(
+          params.ell1, params.ell2, params.ELL, m1, m2, M);
+        if (std::fabs(coupling) < trvm::eps_coupling) continue;
+        Term t;
+        t.m1 = m1; t.m2 = m2; t.M = M; t.coupling = coupling;
+        t.factor_mirror = cur.is_zeros() ? 0. : std::pow(-1., params.ELL);
+        t.factor_mirror_w3j = cur.is_zeros() ? 0. : 1.;
+        terms.push_back(t);
+        computed.push_back(cur);
+      }
+    }
+  }
+  return terms;
+}
+
+/// Everything an estimator call keeps on the device.
+class Engine {
+ public:
+  Engine(trv::ParameterSet& params, ParticleCatalogue& data, ParticleCatalogue* rand,
+         LineOfSight* los_data, LineOfSight* los_rand)
+    : params_(params), survey_(rand != nullptr) {
+    ctx_ = dev::acquire_context(params);
+    c_ = ctx_.get();
+    data_.reset(new dev::Catalogue(ctx_, data, los_data, survey_));
+    if (survey_) rand_.reset(new dev::Catalogue(ctx_, *rand, los_rand, true));
+    ndata_ = data.ntotal;
+    if (survey_) alpha_ = data.wstotal / rand->wstotal;   // S/threept.cpp:269
+    vol_ = params.volume;
+    vol_cell_ = vol_ / double(params.nmesh);
+    mode_ = params.deterministic ? 1 : 0;
+  }
+
+  trvb_ctx* ctx() { return c_; }
+  std::shared_ptr<trvb_ctx> shared() { return ctx_; }
+  double alpha() const { return alpha_; }
+  double vol() const { return vol_; }
+  double vol_cell() const { return vol_cell_; }
+  bool survey() const { return survey_; }
+
+  /// Fourier transform of the (L, M)-weighted number-density fluctuation,
+  /// delta n_LM(k), including the dV factor of S/field.cpp:1503-1510:
+  ///   box    : unit weights, mean subtracted (S/field.cpp:1229-1244)
+  ///   survey : y_LM w for data minus alpha x randoms (S/field.cpp:1246-1323)
+  /// Weights are assigned WITHOUT the 1/dV density factor, which cancels the
+  /// dV of the forward transform exactly (up to rounding).
+  dev::Mesh density_fluctuation(int L, int M) {
+    const bool real_field = (M == 0);
+    dev::Mesh x(ctx_, c_, real_field ? TRVB_REAL : TRVB_COMPLEX);
+    if (!survey_) {
+      assign(*data_, TRVB_W_UNIT, 0, 0, 1., false, x);
+    } else {
+      assign(*data_, TRVB_W_YLM_W, L, M, 1., false, x);
+      assign(*rand_, TRVB_W_YLM_W, L, M, -alpha_, true, x);
+    }
+    dev::Mesh k = forward(x);
+    if (!survey_) {
+      // Mean subtraction touches the k = 0 mode only: FFT[nbar dV] = N delta_k0.
+      dev::check(trvb_kmesh_add_zero_mode(c_, k.view(), -double(ndata_)),
+                 "trvb_kmesh_add_zero_mode");
+    }
+    return k;
+  }
+
+  /// N_LM(k): conj(y_LM) w^2 for data plus alpha^2 x randoms
+  /// (S/field.cpp:1364-1447); box: unit weights, no mean subtraction.
+  dev::Mesh quadratic_field(int L, int M) {
+    const bool real_field = (M == 0);
+    dev::Mesh x(ctx_, c_, real_field ? TRVB_REAL : TRVB_COMPLEX);
+    if (!survey_) {
+      assign(*data_, TRVB_W_UNIT, 0, 0, 1., false, x);
+    } else {
+      assign(*data_, TRVB_W_CYLM_W2, L, M, 1., false, x);
+      assign(*rand_, TRVB_W_CYLM_W2, L, M, std::pow(alpha_, 2), true, x);
+    }
+    return forward(x);
+  }
+
+  /// Box only: N_00(k) obtained from delta n_00(k) by restoring the k = 0
+  /// mode (identical to a second assignment + FFT; saves both).
+  dev::Mesh quadratic_from_fluctuation(const dev::Mesh& dn) {
+    dev::Mesh k(ctx_, c_, dn.layout());
+    dev::check(trvb_d2d(c_, k.data(), dn.data(), trvb_mesh_bytes(c_, dn.layout())),
+               "trvb_d2d");
+    dev::check(trvb_kmesh_add_zero_mode(c_, k.view(), double(ndata_)),
+               "trvb_kmesh_add_zero_mode");
+    return k;
+  }
+
+  cdouble shotnoise_amp(int L, int M) {
+    if (!survey_) return cdouble(double(ndata_), 0.);   // S/threept.cpp:1977-1979
+    return cat_sum(c_, *data_, TRVB_W_YLM_W3, L, M)
+      + std::pow(alpha_, 3) * cat_sum(c_, *rand_, TRVB_W_YLM_W3, L, M);
+  }
+
+  void upload_sjl(trvm::SphericalBesselCalculator& sj) {
+    dev::check(trvb_sjl_table(c_, sj.order, sj.y.data(), sj.c.data(),
+                              static_cast<int>(sj.y.size()), sj.step), "trvb_sjl_table");
+  }
+
+  /// Number of additional meshes of `bytes` each that fit in free HBM.
+  int mesh_capacity(size_t bytes) {
+    size_t free_b = 0, total_b = 0;
+    dev::check(trvb_mem_info(c_, &free_b, &total_b), "trvb_mem_info");
+    const double usable = 0.85 * double(free_b);
+    return static_cast<int>(usable / double(bytes));
+  }
+
+ private:
+  void assign(dev::Catalogue& cat, int kind, int L, int M, double scale, bool accumulate,
+              dev::Mesh& mesh) {
+    dev::check(trvb_assign(c_, cat.get(), kind, L, M, scale, /*density_units=*/0,
+                           accumulate ? 1 : 0, /*shifted=*/0, mode_, mesh.view()),
+               "trvb_assign");
+  }
+
+  dev::Mesh forward(dev::Mesh& x) {
+    if (x.layout() == TRVB_REAL) {
+      dev::Mesh k(ctx_, c_, TRVB_HALF);
+      dev::check(trvb_fft_forward(c_, x.view(), k.view(), 1.), "trvb_fft_forward");
+      trvs::count_fft += 1;
+      return k;
+    }
+    dev::check(trvb_fft_forward(c_, x.view(), x.view(), 1.), "trvb_fft_forward");
+    trvs::count_fft += 1;
+    return std::move(x);
+  }
+
+  trv::ParameterSet& params_;
+  bool survey_;
+  std::shared_ptr<trvb_ctx> ctx_;
+  trvb_ctx* c_ = nullptr;
+  std::unique_ptr<dev::Catalogue> data_, rand_;
+  long long ndata_ = 0;
+  double alpha_ = 1.;
+  double vol_ = 0., vol_cell_ = 0.;
+  int mode_ = 0;
+};
+
+/// Blocked all-pairs reduction: out[idx] = sum_x A_{row(idx)} B_{col(idx)} G
+/// for the entries of `dv` selected by `active`.  `make_a(bin, mesh)` and
+/// `make_b(bin, mesh)` fill a COMPLEX mesh on `grid` for a bin index.
+template <class MakeA, class MakeB>
+void reduce_pairs(Engine& eng, trvb_ctx* grid, const DataVector& dv,
+                  const std::vector<char>& active, bool same_fields,
+                  const dev::Mesh& G, MakeA make_a, MakeB make_b,
+                  std::vector<cdouble>& out) {
+  out.assign(dv.dim, cdouble(0., 0.));
+  std::vector<int> rows_all, cols_all;
+  for (int i = 0; i < dv.dim; i++) {
+    if (active[i]) { rows_all.push_back(dv.row[i]); cols_all.push_back(dv.col[i]); }
+  }
+  if (rows_all.empty()) return;
+  const std::vector<int> rows = distinct_sorted(rows_all);
+  const std::vector<int> cols = distinct_sorted(cols_all);
+
+  const size_t bytes = trvb_mesh_bytes(grid, TRVB_COMPLEX);
+  int cap = eng.mesh_capacity(bytes) - 1;
+  if (cap < 2) {
+    throw trvs::DeviceError(
+      "Insufficient device memory: fewer than two %zu-byte shell meshes fit.", bytes);
+  }
+  const int want = static_cast<int>(rows.size() + cols.size());
+  const int max_tile = 100;   // shared-memory tile limit of trvb_gram_reduce
+  int block_r = static_cast<int>(rows.size());
+  int block_c = static_cast<int>(cols.size());
+  if (want > cap || want > max_tile) {
+    const int half = std::max(1, std::min(cap, max_tile) / 2);
+    block_r = std::min(block_r, half);
+    block_c = std::min(block_c, half);
+  }
+
+  for (size_t r0 = 0; r0 < rows.size(); r0 += block_r) {
+    const size_t r1 = std::min(rows.size(), r0 + block_r);
+    std::map<int, dev::Mesh> fa;
+    for (size_t r = r0; r < r1; r++) {
+      dev::Mesh m(eng.shared(), grid, TRVB_COMPLEX);
+      make_a(rows[r], m);
+      fa.emplace(rows[r], std::move(m));
+    }
+    for (size_t c0 = 0; c0 < cols.size(); c0 += block_c) {
+      const size_t c1 = std::min(cols.size(), c0 + block_c);
+      std::map<int, dev::Mesh> fb_own;
+      std::map<int, const dev::Mesh*> fb;
+      for (size_t c = c0; c < c1; c++) {
+        auto hit = fa.find(cols[c]);
+        if (same_fields && hit != fa.end()) {
+          fb[cols[c]] = &hit->second;
+        } else {
+          dev::Mesh m(eng.shared(), grid, TRVB_COMPLEX);
+          make_b(cols[c], m);
+          auto ins = fb_own.emplace(cols[c], std::move(m));
+          fb[cols[c]] = &ins.first->second;
+        }
+      }
+      // Pair list restricted to this block.
+      std::vector<const void*> pa, pb;
+      std::map<int, int> ia_of, ib_of;
+      for (auto& kv : fa) { ia_of[kv.first] = (int)pa.size(); pa.push_back(kv.second.data()); }
+      for (auto& kv : fb) { ib_of[kv.first] = (int)pb.size(); pb.push_back(kv.second->data()); }
+      std::vector<int> ia, ib, where;
+      for (int i = 0; i < dv.dim; i++) {
+        if (!active[i]) continue;
+        auto fr = ia_of.find(dv.row[i]); auto fc = ib_of.find(dv.col[i]);
+        if (fr == ia_of.end() || fc == ib_of.end()) continue;
+        ia.push_back(fr->second); ib.push_back(fc->second); where.push_back(i);
+      }
+      if (ia.empty()) continue;
+      std::vector<double> sums(2 * ia.size());
+      dev::check(trvb_gram_reduce(grid, pa.data(), (int)pa.size(), pb.data(), (int)pb.size(),
+                                  G.view(), ia.data(), ib.data(), (int)ia.size(),
+                                  sums.data()), "trvb_gram_reduce");
+      for (size_t p = 0; p < ia.size(); p++) {
+        out[where[p]] = cdouble(sums[2 * p], sums[2 * p + 1]);
+      }
+    }
+  }
+}
+
+std::vector<char> active_entries(const trv::ParameterSet& params, int dim) {
+  std::vector<char> active(dim, 0);
+  for (int i = 0; i < dim; i++) active[i] = (i % params.part_count) == params.part_rank;
+  return active;
+}
+
+/// Sub-grid extents for shells reaching k_max (section 2 of the file header).
+void choose_subgrid(const trv::ParameterSet& params, double kmax, int nsub[3]) {
+  bool coarsen = true;
+  for (int ax = 0; ax < 3; ax++) {
+    const double dk = 2. * M_PI / params.boxsize[ax];
+    const long long mcut = static_cast<long long>(std::floor(kmax / dk)) + 1;
+    const long long need = 4 * mcut + 2;
+    if (need >= params.ngrid[ax]) { coarsen = false; break; }
+    nsub[ax] = next_fft_size(static_cast<int>(need));
+    if (nsub[ax] >= params.ngrid[ax]) { coarsen = false; break; }
+  }
+  const char* env = std::getenv("TRV_NO_SUBGRID");
+  if (env != nullptr && std::string(env) == "1") coarsen = false;
+  if (!coarsen) for (int ax = 0; ax < 3; ax++) nsub[ax] = params.ngrid[ax];
+}
+
+}  // namespace
+
+// =====================================================================
+// Bispectrum
+// =====================================================================
+
+namespace {
+
+trv::BispecMeasurements bispec_impl(
+  ParticleCatalogue& catalogue_data, ParticleCatalogue* catalogue_rand,
+  LineOfSight* los_data, LineOfSight* los_rand,
+  trv::ParameterSet& params, trv::Binning& kbinning, double norm_factor
+) {
+  const bool survey = catalogue_rand != nullptr;
+  validate_multipole_coupling(params);
+  const cdouble factor_phase = std::pow(trvm::M_I, params.ell1 + params.ell2);
+  const int nb = kbinning.num_bins;
+  const DataVector dv = make_data_vector(params, nb);
+  const std::vector<char> active = active_entries(params, dv.dim);
+
+  Engine eng(params, catalogue_data, catalogue_rand, los_data, los_rand);
+  trvb_ctx* c = eng.ctx();
+  const double vol_cell = eng.vol_cell();
+
+  // Common fields: delta n_00(k) and N_00(k).
+  dev::Mesh dn_00 = eng.density_fluctuation(0, 0);
+  dev::Mesh N_00 = survey ? eng.quadratic_field(0, 0) : eng.quadratic_from_fluctuation(dn_00);
+
+  trvm::SphericalBesselCalculator sj_a(params.ell1), sj_b(params.ell2);
+  eng.upload_sjl(sj_a);
+  if (params.ell2 != params.ell1) eng.upload_sjl(sj_b);
+
+  // Shell statistics (k_eff, nmodes) for every bin in one pass; they do not
+  // depend on (l, m) (S/field.cpp:1815-1847, 1905).
+  std::vector<long long> nmodes(nb);
+  std::vector<double> ksum(nb), keff(nb);
+  dev::check(trvb_shell_stats(c, kbinning.bin_edges.data(), nb, 0, nmodes.data(),
+                              ksum.data()), "trvb_shell_stats");
+  for (int b = 0; b < nb; b++) keff[b] = ksum[b] / double(nmodes[b]);
+
+  // Sub-grid for the shell fields.
+  int nsub[3];
+  choose_subgrid(params, kbinning.bin_edges.back(), nsub);
+  const bool coarse = nsub[0] != params.ngrid[0];
+  std::shared_ptr<trvb_ctx> sub_holder;
+  trvb_ctx* sub = c;
+  if (coarse) {
+    trvb_ctx* raw = nullptr;
+    dev::check(trvb_subgrid_create(c, &raw, nsub), "trvb_subgrid_create");
+    sub_holder.reset(raw, [](trvb_ctx* p) { trvb_ctx_destroy(p); });
+    sub = raw;
+  }
+  const double nsub_mesh = double(nsub[0]) * nsub[1] * nsub[2];
+  // vol_cell * sum over the n^3 mesh == (V / ns^3) * sum over the sub-grid.
+  const double vol_cell_sub = eng.vol() / nsub_mesh;
+
+  std::vector<cdouble> bk_dv(dv.dim, 0.), sn_dv(dv.dim, 0.);
+  std::vector<double> k1eff(dv.dim), k2eff(dv.dim);
+  for (int i = 0; i < dv.dim; i++) { k1eff[i] = keff[dv.row[i]]; k2eff[i] = keff[dv.col[i]]; }
+
+  const std::vector<Term> terms = enumerate_terms(params, survey);
+  dev::Mesh xi;             // shot-noise mesh, reused across terms in a box
+  dev::Mesh G;              // G_LM(x) on the sub-grid
+  int G_M = 0; bool have_G = false, have_xi = false;
+  dev::Mesh dn_LM;          // survey: delta n_LM(k) of the current M
+  dev::Mesh N_LM;
+  cdouble Sbar_LM = 0.;
+  int cached_M = 0; bool have_LM = false;
+
+  auto shell_field = [&](const dev::Mesh& src, int ell, int m, int bin, dev::Mesh& dst) {
+    dev::check(trvb_shell_ifft(c, sub, src.view(), ell, m, kbinning.bin_edges[bin],
+                               kbinning.bin_edges[bin + 1], 1. / double(nmodes[bin]),
+                               dst.view()), "trvb_shell_ifft");
+    trvs::count_ifft += 1;
+  };
+
+  for (const Term& t : terms) {
+    // ---- fields that depend on (L, M) only -----------------------------
+    if (survey && !(have_LM && cached_M == t.M)) {
+      dn_LM = eng.density_fluctuation(params.ELL, t.M);
+      N_LM = eng.quadratic_field(params.ELL, t.M);
+      Sbar_LM = eng.shotnoise_amp(params.ELL, t.M);
+      cached_M = t.M; have_LM = true; have_G = false; have_xi = false;
+    }
+    if (!survey && !have_LM) {
+      Sbar_LM = eng.shotnoise_amp(0, 0);
+      have_LM = true;
+    }
+    const dev::Mesh& dn_LM_ref = survey ? dn_LM : dn_00;
+    const dev::Mesh& N_LM_ref = survey ? N_LM : N_00;
+
+    // ---- raw bispectrum --------------------------------------------------
+    if (!(have_G && G_M == t.M)) {
+      // G_LM(x) = IFFT[delta n_LM(k) / W(k)] / V (S/threept.cpp:452-459).
+      G = dev::Mesh(eng.shared(), sub, TRVB_COMPLEX);
+      dev::check(trvb_shell_ifft(c, sub, dn_LM_ref.view(), 0, 0, -1., -1., 1. / eng.vol(),
+                                 G.view()), "trvb_shell_ifft (G)");
+      trvs::count_ifft += 1;
+      G_M = t.M; have_G = true;
+    }
+    const bool same_fields = (params.ell1 == params.ell2 && t.m1 == t.m2);
+    std::vector<cdouble> bk_comp;
+    reduce_pairs(
+      eng, sub, dv, active, same_fields, G,
+      [&](int bin, dev::Mesh& m) { shell_field(dn_00, params.ell1, t.m1, bin, m); },
+      [&](int bin, dev::Mesh& m) { shell_field(dn_00, params.ell2, t.m2, bin, m); },
+      bk_comp);
+    for (int i = 0; i < dv.dim; i++) {
+      if (!active[i]) continue;
+      bk_dv[i] += t.coupling * vol_cell_sub * (
+        bk_comp[i] + t.factor_mirror * std::conj(bk_comp[i]));
+    }
+
+    // ---- shot noise ------------------------------------------------------
+    if (params.ell1 == 0 && params.ell2 == 0) {   // S|{i = j = k}
+      const cdouble S_ijk = t.coupling * Sbar_LM;
+      for (int i = 0; i < dv.dim; i++) if (active[i]) sn_dv[i] += S_ijk;
+    }
+    auto binned_term = [&](int ell, int m, bool by_row) {
+      std::vector<long long> nm(nb);
+      std::vector<double> kk(nb), pk(2 * nb), sn(2 * nb);
+      const double S[2] = {Sbar_LM.real(), Sbar_LM.imag()};
+      dev::check(trvb_twopt_fourier(c, dn_00.view(), N_LM_ref.view(), S, ell, m,
+                                    kbinning.bin_edges.data(), kbinning.bin_centres.data(),
+                                    nb, nm.data(), kk.data(), pk.data(), sn.data()),
+                 "trvb_twopt_fourier");
+      for (int i = 0; i < dv.dim; i++) {
+        if (!active[i]) continue;
+        const int b = by_row ? dv.row[i] : dv.col[i];
+        const cdouble S_b = t.coupling * (cdouble(pk[2*b], pk[2*b+1]) - cdouble(sn[2*b], sn[2*b+1]));
+        sn_dv[i] += S_b + t.factor_mirror * std::conj(S_b);
+      }
+    };
+    if (params.ell2 == 0) binned_term(params.ell1, t.m1, true);    // S|{i != j = k}
+    if (params.ell1 == 0) binned_term(params.ell2, t.m2, false);   // S|{j != i = k}
+
+    // S|{i = j != k}: one xi mesh, all pairs in one pass.
+    if (!have_xi) {
+      xi = dev::Mesh(eng.shared(), c, TRVB_COMPLEX);
+      const double S[2] = {Sbar_LM.real(), Sbar_LM.imag()};
+      dev::check(trvb_shot_xi(c, dn_LM_ref.view(), N_00.view(), S, xi.view()), "trvb_shot_xi");
+      trvs::count_ifft += 1;
+      have_xi = true;
+    }
+    {
+      std::vector<double> ka, kb; std::vector<int> where;
+      for (int i = 0; i < dv.dim; i++) {
+        if (!active[i]) continue;
+        ka.push_back(k1eff[i]); kb.push_back(k2eff[i]); where.push_back(i);
+      }
+      if (!where.empty()) {
+        std::vector<double> S(2 * where.size());
+        dev::check(trvb_shot_bispec_reduce(c, xi.view(), params.ell1, t.m1, params.ell2, t.m2,
+                                           ka.data(), kb.data(), (int)where.size(), S.data()),
+                   "trvb_shot_bispec_reduce");
+        for (size_t p = 0; p < where.size(); p++) {
+          const cdouble S_ij_k = t.coupling * cdouble(S[2*p], S[2*p+1]);
+          sn_dv[where[p]] += factor_phase * (
+            S_ij_k + t.factor_mirror_w3j * std::conj(S_ij_k));
+        }
+      }
+    }
+    if (trvs::currTask == 0) {
+      trvs::logger.stat("Bispectrum term computed at orders (m1, m2, M) = +/-(%d, %d, %d).",
+                        t.m1, t.m2, t.M);
+    }
+  }
+
+  trv::BispecMeasurements out;
+  out.dim = dv.dim;
+  for (int i = 0; i < dv.dim; i++) {
+    out.k1_bin.push_back(kbinning.bin_centres[dv.row[i]]);
+    out.k2_bin.push_back(kbinning.bin_centres[dv.col[i]]);
+    out.k1_eff.push_back(k1eff[i]);
+    out.k2_eff.push_back(k2eff[i]);
+    out.nmodes_1.push_back(static_cast<int>(nmodes[dv.row[i]]));
+    out.nmodes_2.push_back(static_cast<int>(nmodes[dv.col[i]]));
+    out.bk_raw.push_back(norm_factor * bk_dv[i]);
+    out.bk_shot.push_back(norm_factor * sn_dv[i]);
+  }
+  return out;
+}
+
+// =====================================================================
+// Three-point correlation function
+// =====================================================================
+
+trv::ThreePCFMeasurements threepcf_impl(
+  ParticleCatalogue& catalogue_data, ParticleCatalogue* catalogue_rand,
+  LineOfSight* los_data, LineOfSight* los_rand,
+  trv::ParameterSet& params, trv::Binning& rbinning, double norm_factor
+) {
+  const bool survey = catalogue_rand != nullptr;
+  validate_multipole_coupling(params);
+  const cdouble factor_phase = std::pow(trvm::M_I, params.ell1 + params.ell2);
+  const double factor_parity = std::pow(-1., params.ell1 + params.ell2);
+  const int nb = rbinning.num_bins;
+  const DataVector dv = make_data_vector(params, nb);
+  const std::vector<char> active = active_entries(params, dv.dim);
+
+  Engine eng(params, catalogue_data, catalogue_rand, los_data, los_rand);
+  trvb_ctx* c = eng.ctx();
+  const double vol_cell = eng.vol_cell();
+
+  dev::Mesh dn_00 = eng.density_fluctuation(0, 0);
+  dev::Mesh N_00 = survey ? eng.quadratic_field(0, 0) : eng.quadratic_from_fluctuation(dn_00);
+
+  trvm::SphericalBesselCalculator sj_a(params.ell1), sj_b(params.ell2);
+  eng.upload_sjl(sj_a);
+  if (params.ell2 != params.ell1) eng.upload_sjl(sj_b);
+
+  std::vector<cdouble> zeta_dv(dv.dim, 0.), sn_dv(dv.dim, 0.);
+  std::vector<double> reff(nb, 0.);
+  std::vector<long long> npairs(nb, 0);
+
+  const std::vector<Term> terms = enumerate_terms(params, survey);
+  dev::Mesh dn_LM, xi, G;
+  cdouble Sbar_LM = 0.;
+  int cached_M = 0; bool have_LM = false, have_xi = false, have_G = false;
+  int count_terms = 0;
+
+  for (const Term& t : terms) {
+    if (survey && !(have_LM && cached_M == t.M)) {
+      dn_LM = eng.density_fluctuation(params.ELL, t.M);
+      Sbar_LM = eng.shotnoise_amp(params.ELL, t.M);
+      cached_M = t.M; have_LM = true; have_xi = false; have_G = false;
+    }
+    if (!survey && !have_LM) { Sbar_LM = eng.shotnoise_amp(0, 0); have_LM = true; }
+    const dev::Mesh& dn_LM_ref = survey ? dn_LM : dn_00;
+
+    // ---- shot noise first: it also yields r_eff and npairs ---------------
+    if (!have_xi) {
+      xi = dev::Mesh(eng.shared(), c, TRVB_COMPLEX);
+      const double S[2] = {Sbar_LM.real(), Sbar_LM.imag()};
+      dev::check(trvb_shot_xi(c, dn_LM_ref.view(), N_00.view(), S, xi.view()), "trvb_shot_xi");
+      trvs::count_ifft += 1;
+      have_xi = true;
+    }
+    std::vector<long long> np(nb);
+    std::vector<double> rr(nb), xib(2 * nb);
+    dev::check(trvb_shot_3pcf_bin(c, xi.view(), params.ell1, t.m1, params.ell2, t.m2,
+                                  rbinning.bin_edges.data(), rbinning.bin_centres.data(), nb,
+                                  factor_parity, np.data(), rr.data(), xib.data()),
+               "trvb_shot_3pcf_bin");
+    // Kronecker delta of eq. (51): shot noise on equal bins only
+    // (S/threept.cpp:2388-2437).
+    for (int i = 0; i < dv.dim; i++) {
+      if (!active[i] || dv.row[i] != dv.col[i]) continue;
+      if (params.shape == "off-diag" && params.idx_bin != 0) continue;
+      const int b = dv.row[i];
+      const cdouble x(xib[2*b], xib[2*b+1]);
+      sn_dv[i] += t.coupling * factor_parity * (x + t.factor_mirror_w3j * std::conj(x));
+    }
+    if (count_terms == 0) { reff = rr; npairs = np; }
+
+    // ---- raw 3PCF ---------------------------------------------------------
+    if (!have_G) {
+      G = dev::Mesh(eng.shared(), c, TRVB_COMPLEX);
+      dev::check(trvb_shell_ifft(c, c, dn_LM_ref.view(), 0, 0, -1., -1., 1. / eng.vol(),
+                                 G.view()), "trvb_shell_ifft (G)");
+      trvs::count_ifft += 1;
+      have_G = true;
+    }
+    auto sjl_field = [&](int ell, int m, int bin, dev::Mesh& dst) {
+      dev::check(trvb_sjl_ifft(c, dn_00.view(), ell, m, reff[bin], 1. / eng.vol(), dst.view()),
+                 "trvb_sjl_ifft");
+      trvs::count_ifft += 1;
+    };
+    const bool same_fields = (params.ell1 == params.ell2 && t.m1 == t.m2);
+    std::vector<cdouble> zeta_comp;
+    reduce_pairs(
+      eng, c, dv, active, same_fields, G,
+      [&](int bin, dev::Mesh& m) { sjl_field(params.ell1, t.m1, bin, m); },
+      [&](int bin, dev::Mesh& m) { sjl_field(params.ell2, t.m2, bin, m); },
+      zeta_comp);
+    for (int i = 0; i < dv.dim; i++) {
+      if (!active[i]) continue;
+      zeta_dv[i] += t.coupling * vol_cell * factor_phase * (
+        zeta_comp[i] + t.factor_mirror * std::conj(zeta_comp[i]));
+    }
+    count_terms++;
+    if (trvs::currTask == 0) {
+      trvs::logger.stat(
+        "Three-point correlation function term computed at orders "
+        "(m1, m2, M) = +/-(%d, %d, %d).", t.m1, t.m2, t.M);
+    }
+  }
+
+  trv::ThreePCFMeasurements out;
+  out.dim = dv.dim;
+  for (int i = 0; i < dv.dim; i++) {
+    out.r1_bin.push_back(rbinning.bin_centres[dv.row[i]]);
+    out.r2_bin.push_back(rbinning.bin_centres[dv.col[i]]);
+    out.r1_eff.push_back(reff[dv.row[i]]);
+    out.r2_eff.push_back(reff[dv.col[i]]);
+    out.npairs_1.push_back(static_cast<int>(npairs[dv.row[i]]));
+    out.npairs_2.push_back(static_cast<int>(npairs[dv.col[i]]));
+    out.zeta_raw.push_back(norm_factor * zeta_dv[i]);
+    out.zeta_shot.push_back(norm_factor * sn_dv[i]);
+  }
+  return out;
+}
+
+}  // namespace
+
+// =====================================================================
+// Public entry points
+// =====================================================================
+
+trv::BispecMeasurements compute_bispec(
+  ParticleCatalogue& catalogue_data, ParticleCatalogue& catalogue_rand,
+  LineOfSight* los_data, LineOfSight* los_rand,
+  trv::ParameterSet& params, trv::Binning& kbinning, double norm_factor
+) {
+  trvs::logger.reset_level(params.verbose);
+  if (trvs::currTask == 0) {
+    trvs::logger.stat("Computing bispectrum from paired survey-type catalogues...");
+  }
+  trv::BispecMeasurements out = bispec_impl(
+    catalogue_data, &catalogue_rand, los_data, los_rand, params, kbinning, norm_factor);
+  if (trvs::currTask == 0) {
+    trvs::logger.stat("... computed bispectrum from paired survey-type catalogues.");
+  }
+  return out;
+}
+
+trv::BispecMeasurements compute_bispec_in_gpp_box(
+  ParticleCatalogue& catalogue_data,
+  trv::ParameterSet& params, trv::Binning kbinning, double norm_factor
+) {
+  trvs::logger.reset_level(params.verbose);
+  if (trvs::currTask == 0) {
+    trvs::logger.stat(
+      "Computing bispectrum from a periodic-box simulation-type catalogue "
+      "in the global plane-parallel approximation...");
+  }
+  trv::BispecMeasurements out = bispec_impl(
+    catalogue_data, nullptr, nullptr, nullptr, params, kbinning, norm_factor);
+  if (trvs::currTask == 0) {
+    trvs::logger.stat(
+      "... computed bispectrum from a periodic-box simulation-type catalogue "
+      "in the global plane-parallel approximation.");
+  }
+  return out;
+}
+
+trv::ThreePCFMeasurements compute_3pcf(
+  ParticleCatalogue& catalogue_data, ParticleCatalogue& catalogue_rand,
+  LineOfSight* los_data, LineOfSight* los_rand,
+  trv::ParameterSet& params, trv::Binning& rbinning, double norm_factor
+) {
+  trvs::logger.reset_level(params.verbose);
+  if (trvs::currTask == 0) {
+    trvs::logger.stat(
+      "Computing three-point correlation function from paired survey-type catalogues...");
+  }
+  trv::ThreePCFMeasurements out = threepcf_impl(
+    catalogue_data, &catalogue_rand, los_data, los_rand, params, rbinning, norm_factor);
+  if (trvs::currTask == 0) {
+    trvs::logger.stat(
+      "... computed three-point correlation function from paired survey-type catalogues.");
+  }
+  return out;
+}
+
+trv::ThreePCFMeasurements compute_3pcf_in_gpp_box(
+  ParticleCatalogue& catalogue_data,
+  trv::ParameterSet& params, trv::Binning& rbinning, double norm_factor
+) {
+  trvs::logger.reset_level(params.verbose);
+  if (trvs::currTask == 0) {
+    trvs::logger.stat(
+      "Computing three-point correlation function from a periodic-box "
+      "simulation-type catalogue in the global plane-parallel approximation...");
+  }
+  trv::ThreePCFMeasurements out = threepcf_impl(
+    catalogue_data, nullptr, nullptr, nullptr, params, rbinning, norm_factor);
+  if (trvs::currTask == 0) {
+    trvs::logger.stat(
+      "... computed three-point correlation function from a periodic-box "
+      "simulation-type catalogue in the global plane-parallel approximation.");
+  }
+  return out;
+}
+
+}  // namespace trv
