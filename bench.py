@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""Benchmark of the three-point estimator hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A "step" is one full estimator call on the workload BASELINE.json quotes the
+metric on (config 2): periodic-box bispectrum B_000, full (k1, k2) bin grid
+(-> upper triangle, 210 pairs), 10^7 synthetic uniform particles, 512^3 mesh,
+PCS assignment (interlacing requested -> switched off by validate(), as in the
+reference), 20 linear bins on [0.005, 0.205] h/Mpc.
+
+Own arm (default):
+  value   time-to-solution per step in seconds with the catalogue already
+          resident in HBM (device pointers into the C-ABI entry point),
+          CUDA events on the estimator's stream, max over ranks;
+  e2e     the same call fed from PINNED HOST arrays, so every step pays the
+          host->device copy of the catalogue and the device->host copy of the
+          result vector inside the timed region;
+  roofline  the dominant hand-written kernel (particle-to-mesh assignment)
+          timed alone with CUDA events against the measured HBM copy bandwidth;
+  cpu_baseline  the reference's own C++ (oracle/_ref) on this host's cores, on
+          a bounded sample (see `sample`), extrapolated to the full pair count.
+Multi-GPU (torchrun, one rank per GPU): the mesh is replicated, the bin pairs
+are dealt round-robin to the ranks and one small NCCL all-reduce sums the
+result vector; the problem size is fixed, so scaling is "strong".
+
+Reference arm (--impl reference): the reference's CPU implementation
+(oracle/_ref) timed on the host cores; each step is one bin-pair unit of the
+reference's loop, the value is setup + 210 x mean(step).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    "C2": dict(
+        name="box B_000 triu, 1e7 uniform particles, 512^3, PCS, 20 lin bins [0.005,0.205]",
+        n=10**7, L=1000., ngrid=512, assignment="pcs", degrees=(0, 0, 0), form="full",
+        bin_range=(0.005, 0.205), num_bins=20, seed=42,
+    ),
+    # reduced problem for quick local checks (not a bench line)
+    "tiny": dict(
+        name="box B_000 triu, 1e5 uniform particles, 64^3, PCS, 6 lin bins",
+        n=10**5, L=1000., ngrid=64, assignment="pcs", degrees=(0, 0, 0), form="full",
+        bin_range=(0.005, 0.065), num_bins=6, seed=42,
+    ),
+}
+
+
+def npairs_of(wl):
+    nb = wl["num_bins"]
+    return nb * (nb + 1) // 2 if wl["form"] == "full" and wl["degrees"][0] == wl["degrees"][1] \
+        else (nb * nb if wl["form"] == "full" else nb)
+
+
+def make_catalogue(wl):
+    gen = np.random.default_rng(wl["seed"])
+    return gen.uniform(0., wl["L"], size=(3, wl["n"]))
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650., "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.file = None
+
+    def start(self):
+        try:
+            self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-i", str(self.index), "-lms", "200"],
+                stdout=self.file, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.file.flush()
+        rows = [ln.strip().split(", ") for ln in open(self.file.name) if ln.strip()]
+        os.unlink(self.file.name)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0])); smax.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(names, r[3:7]):
+                if val.strip().lower() == "active":
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)),
+                       reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ---------------------------------------------------------------------------
+# Own arm
+# ---------------------------------------------------------------------------
+
+def run_b200(args):
+    import torch
+    from triumvirate_b200 import core
+    from triumvirate_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ["TRV_GPU_DEVICE"] = str(local)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    wl = WORKLOADS[args.workload]
+    n, L, ng = wl["n"], wl["L"], wl["ngrid"]
+    pos = make_catalogue(wl)
+    host = torch.from_numpy(pos).pin_memory()
+    dpos = host.to(dev, non_blocking=False)
+    torch.cuda.synchronize()
+    kw = dict(boxsize=L, ngrid=ng, assignment=wl["assignment"], degrees=wl["degrees"],
+              form=wl["form"], bin_range=wl["bin_range"], num_bins=wl["num_bins"],
+              norm_factor=1., part_rank=rank, part_count=world)
+    dim = npairs_of(wl)
+
+    def step(src, on_device):
+        out = core.threept_box_arrays("bispec", n, src[0].data_ptr(), src[1].data_ptr(),
+                                      src[2].data_ptr(), on_device, **kw)
+        if world > 1:
+            # the single small exchange of the path: sum the partial result vectors
+            buf = torch.from_numpy(np.concatenate([
+                out["bk_raw"].view(np.float64), out["bk_shot"].view(np.float64)])).to(dev)
+            dist.all_reduce(buf)
+            res = buf.cpu().numpy()
+            out["bk_raw"] = res[:2 * dim].view(np.complex128)
+            out["bk_shot"] = res[2 * dim:].view(np.complex128)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(src, on_device, steps):
+        """K steps bracketed by barrier + synchronize; CUDA events on the
+        estimator's own stream; returns seconds (max over ranks)."""
+        trv = _lib.trv()
+        trv.trv_last_stream.restype = C.c_void_p
+        sptr = trv.trv_last_stream()
+        stream = torch.cuda.ExternalStream(sptr, device=dev) if sptr else torch.cuda.current_stream()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(steps):
+            out = step(src, on_device)
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        ev = e0.elapsed_time(e1) * 1.e-3
+        # The estimator synchronises its stream when it returns results, so the
+        # event interval and the wall clock agree; keep the larger of the two.
+        sec = max(ev, wall if world == 1 else ev)
+        if world > 1:
+            t = torch.tensor([sec], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t.item())
+        return sec, out
+
+    # warm-up (also builds cuFFT plans, tables and the spline upload)
+    for _ in range(max(args.warmup, 3)):
+        step(dpos, True)
+    tb = _lib.trvb()
+    sampler = ClockSampler(local)
+    sampler.start()
+    tb.trvb_launch_count_reset()
+    sec, out = timed(dpos, True, args.steps)
+    launches = tb.trvb_launch_count() / args.steps
+    fft_execs = tb.trvb_fft_exec_count() / args.steps
+    clocks = sampler.stop()
+
+    # end to end from pinned host memory
+    for _ in range(2):
+        step(host, False)
+    sec_e2e, out_e2e = timed(host, False, args.steps)
+    assert np.all(np.isfinite(out["bk_raw"].view(np.float64)))
+
+    result = {
+        "metric": "bispectrum time-to-solution", "value": sec / args.steps, "unit": "s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": 1.e3 * sec / args.steps, "higher_is_better": False,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {
+            "workload": wl["name"], "baseline_config": 2, "particles": n, "ngrid": ng,
+            "pairs": dim, "parallelism": f"pairs/{world}gpu" if world > 1 else "1gpu",
+            "l2_policy": "inputs larger than L2 (240 MB catalogue, >=1 GB meshes); no flush needed",
+        },
+        "clocks": clocks,
+        "e2e": {"value": sec_e2e / args.steps, "unit": "s",
+                "h2d_bytes_per_step": int(3 * 8 * n),
+                "d2h_bytes_per_step": int(dim * (4 * 8 + 2 * 4 + 4 * 8))},
+        "gpu_launches": launches, "cufft_execs": fft_execs,
+    }
+
+    if rank == 0:
+        result["roofline"], result["particles_per_s"] = assignment_roofline(torch, dev, dpos, wl)
+        if world == 1 and not args.no_cpu_baseline:
+            result["cpu_baseline"] = cpu_baseline(wl, pos, pair_units=2)
+        print(json.dumps(result), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def assignment_roofline(torch, dev, dpos, wl):
+    """Time the dominant hand-written kernel alone: trvb_assign (zero-fill +
+    cell-sorted scatter) of the workload's catalogue onto a REAL mesh.
+    Algorithmic bytes per launch = 32 B/particle (24 B position + 8 B weight)
+    + one mesh write."""
+    from triumvirate_b200 import _lib
+    tb = _lib.trvb()
+    n, L, ng = wl["n"], wl["L"], wl["ngrid"]
+    order = {"ngp": 1, "cic": 2, "tsc": 3, "pcs": 4}[wl["assignment"]]
+    ctx = C.c_void_p()
+    ngrid = (C.c_int * 3)(ng, ng, ng)
+    box = (C.c_double * 3)(L, L, L)
+
+    def chk(st):
+        if st != 0:
+            raise RuntimeError(tb.trvb_last_error().decode())
+
+    chk(tb.trvb_ctx_create(C.byref(ctx), C.c_int(dev.index or 0), ngrid, box, C.c_int(order)))
+    cat = C.c_void_p()
+    chk(tb.trvb_cat_create(ctx, C.byref(cat), C.c_longlong(n), C.c_void_p(dpos[0].data_ptr()),
+                           C.c_void_p(dpos[1].data_ptr()), C.c_void_p(dpos[2].data_ptr()),
+                           None, None, C.c_int(1)))
+    mesh = torch.empty(ng * ng * ng, dtype=torch.float64, device=dev)
+
+    class Mesh(C.Structure):
+        _fields_ = [("data", C.c_void_p), ("layout", C.c_int)]
+
+    m = Mesh(mesh.data_ptr(), 0)
+    tb.trvb_ctx_stream.restype = C.c_void_p
+    stream = torch.cuda.ExternalStream(tb.trvb_ctx_stream(ctx), device=dev)
+
+    def assign():
+        chk(tb.trvb_assign(ctx, cat, C.c_int(0), C.c_int(0), C.c_int(0), C.c_double(1.),
+                           C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0), m))
+
+    for _ in range(3):
+        assign()
+    tb.trvb_ctx_sync(ctx)
+    reps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        assign()
+    e1.record(stream)
+    tb.trvb_ctx_sync(ctx)
+    t = e0.elapsed_time(e1) * 1.e-3 / reps
+    total = float(mesh.sum().item())
+    assert abs(total - n) < 1.e-6 * n, "assignment does not conserve the particle count"
+    tb.trvb_cat_destroy(cat)
+    tb.trvb_ctx_destroy(ctx)
+    alg_bytes = 32. * n + 8. * ng**3
+    peak, how = measured_peaks()
+    achieved = alg_bytes / t / 1.e9
+    roof = {"bound": "hbm", "kernel": "k_assign_scatter<4,false> (+ zero-fill)",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "peak_source": how,
+            "algorithmic_bytes_per_launch": alg_bytes, "launch_seconds": t}
+    return roof, n / t
+
+
+def cpu_baseline(wl, pos, pair_units):
+    """The reference's own C++ (oracle/_ref) on this host: setup once, then
+    `pair_units` bin-pair units; full job = setup + npairs x mean(unit)."""
+    from oracle import ref
+    if not ref.available():
+        return {"value": None, "unit": "s", "kind": "reference", "cores": 0,
+                "sample": "oracle/_ref/libtrv_ref.so missing"}
+    cores = ref.num_threads()
+    t_setup = ref.bispec_setup(pos, wl["L"], wl["ngrid"], wl["assignment"], wl["bin_range"],
+                               wl["num_bins"])
+    units = []
+    nb = wl["num_bins"]
+    for u in range(pair_units):
+        _, _, t = ref.bispec_pair(u % nb, (u + nb // 2) % nb)
+        units.append(t)
+    ref.bispec_teardown()
+    npairs = npairs_of(wl)
+    value = t_setup + npairs * float(np.mean(units))
+    return {"value": value, "unit": "s", "cores": cores, "kind": "reference",
+            "sample": (f"reference C++ (oracle/_ref, OpenMP, shim FFT) on the same catalogue and "
+                       f"mesh: setup (dn_00, N_L0, G_00, y_lm tables) {t_setup:.2f} s measured once + "
+                       f"{pair_units} bin-pair units of its loop, mean {np.mean(units):.3f} s, "
+                       f"extrapolated to {npairs} pairs"),
+            "setup_s": t_setup, "pair_unit_s": float(np.mean(units))}
+
+
+# ---------------------------------------------------------------------------
+# Reference arm
+# ---------------------------------------------------------------------------
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ref
+    wl = WORKLOADS[args.workload]
+    if not ref.available() and not ref.build():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libtrv_ref.so not built"}))
+        return
+    pos = make_catalogue(wl)
+    cores = ref.num_threads()
+    nb = wl["num_bins"]
+    t_setup = ref.bispec_setup(pos, wl["L"], wl["ngrid"], wl["assignment"], wl["bin_range"], nb)
+    pairs = [(a, b) for a in range(nb) for b in range(a, nb)]
+    stride = max(1, len(pairs) // (args.warmup + args.steps))
+    units = []
+    for s in range(args.warmup + args.steps):
+        a, b = pairs[(s * stride) % len(pairs)]
+        _, _, t = ref.bispec_pair(a, b)
+        if s >= args.warmup:
+            units.append(t)
+    ref.bispec_teardown()
+    npairs = npairs_of(wl)
+    unit = float(np.mean(units))
+    value = t_setup + npairs * unit
+    sample = (f"each step = one bin-pair unit of the reference loop (2 band-limited IFFTs + triple "
+              f"product + per-bin shot-noise IFFT and reduction) at the full mesh; value = setup "
+              f"{t_setup:.2f} s + {npairs} x mean step {unit:.3f} s")
+    print(json.dumps({
+        "impl": "reference", "metric": "bispectrum time-to-solution", "value": value, "unit": "s",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1.e3 * value, "higher_is_better": False, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["name"], "baseline_config": 2, "particles": wl["n"],
+                   "ngrid": wl["ngrid"], "pairs": npairs},
+        "cpu_baseline": {"value": value, "unit": "s", "cores": cores, "kind": "reference",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

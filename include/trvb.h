@@ -61,8 +61,10 @@ const char* trvb_version(void);
 /* Number of visible CUDA devices (0 when none / no driver); replaces the
  * probe of S/monitor.cpp:258-282. */
 int trvb_device_count(void);
-/* Number of kernel launches issued by this library since the last reset. */
+/* Number of hand-written kernels launched by this library since the last
+ * reset, and (separately) the number of cuFFT executions. */
 long long trvb_launch_count(void);
+long long trvb_fft_exec_count(void);
 void trvb_launch_count_reset(void);
 
 /* ---- context: replaces MeshField/FieldStats ctor state ----------------
@@ -71,6 +73,10 @@ void trvb_launch_count_reset(void);
 int trvb_ctx_create(trvb_ctx** ctx, int device, const int ngrid[3],
                     const double boxsize[3], int assignment_order);
 void trvb_ctx_destroy(trvb_ctx* ctx);
+/* on != 0: every reduction of this context avoids floating-point atomics so
+ * that results are bit-reproducible from run to run (slower shot-noise
+ * reduction); assignment determinism is selected per trvb_assign call. */
+int trvb_ctx_set_deterministic(trvb_ctx* ctx, int on);
 int trvb_ctx_sync(trvb_ctx* ctx);
 void* trvb_ctx_stream(trvb_ctx* ctx);          /* cudaStream_t */
 long long trvb_ctx_nmesh(const trvb_ctx* ctx);

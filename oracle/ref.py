@@ -191,6 +191,35 @@ def threept(stat, catalogue_type, pos_d, boxsize, ngrid, assignment, degrees,
     return out
 
 
+def bispec_setup(pos, boxsize, ngrid, assignment, bin_range, num_bins):
+    """Bin-pair-independent part of the reference's box bispectrum
+    (S/threept.cpp:1543-1672); returns its wall time in seconds."""
+    pos = np.asarray(pos, dtype=np.float64)
+    boxsize = np.broadcast_to(np.asarray(boxsize, dtype=np.float64), (3,)).copy()
+    ngrid = np.broadcast_to(np.asarray(ngrid, dtype=np.int32), (3,)).copy()
+    x, px = _d(pos[0]); y, py = _d(pos[1]); z, pz = _d(pos[2])
+    t = C.c_double(0.)
+    _check(lib().trvref_bispec_setup(
+        C.c_int(pos.shape[1]), px, py, pz, boxsize.ctypes.data_as(_dp),
+        ngrid.ctypes.data_as(_ip), assignment.encode(), C.c_double(bin_range[0]),
+        C.c_double(bin_range[1]), C.c_int(num_bins), C.byref(t)))
+    return t.value
+
+
+def bispec_pair(idx_row, idx_col):
+    """One bin pair of the reference loop (S/threept.cpp:1900-1968, 2126-2140);
+    returns (bk component, shot component, wall seconds)."""
+    out = np.zeros(4)
+    t = C.c_double(0.)
+    _check(lib().trvref_bispec_pair(C.c_int(idx_row), C.c_int(idx_col),
+                                    out.ctypes.data_as(_dp), C.byref(t)))
+    return complex(out[0], out[1]), complex(out[2], out[3]), t.value
+
+
+def bispec_teardown():
+    lib().trvref_bispec_teardown()
+
+
 def norm_particles(pos, nz, ws=None, wc=None, alpha=1.):
     """``1/(alpha * sum ws nz^2 wc^3)`` (S/threept.cpp:96-136)."""
     return _norm(0, pos, nz, ws, wc, alpha, [1., 1., 1.], [2, 2, 2], "tsc")

@@ -179,6 +179,134 @@ int trvref_threept(
   }
 }
 
+// ---------------------------------------------------------------------
+// Bounded-sample timing of the reference's periodic-box bispectrum.
+//
+// A full `form = full` run at 512^3 takes of order an hour on a CPU, so the
+// bench times the reference in two parts that together are its whole loop
+// (S/threept.cpp:1543-1669 and :1675-2140):
+//   setup   dn_00, N_L0, G_00, the four y_lm tables, Bessel calculators
+//           -- done once per (m1, m2, M) term, independent of the bin pair;
+//   pair    what the reference repeats for EVERY bin pair: two band-limited
+//           inverse transforms, the triple-product sum and the per-bin
+//           shot-noise transform + reduction (3 IFFTs + 5 mesh passes).
+// time(full run) = setup + (number of pairs) x pair, which the caller forms.
+// ---------------------------------------------------------------------
+
+struct RefBispecState {
+  trv::ParameterSet params;
+  trv::ParticleCatalogue* cat = nullptr;
+  trv::Binning* bins = nullptr;
+  trv::MeshField* dn_00 = nullptr;
+  trv::MeshField* N_L0 = nullptr;
+  trv::MeshField* G_00 = nullptr;
+  trv::MeshField* F_a = nullptr;
+  trv::MeshField* F_b = nullptr;
+  trv::FieldStats* stats = nullptr;
+  trv::maths::SphericalBesselCalculator* sj_a = nullptr;
+  trv::maths::SphericalBesselCalculator* sj_b = nullptr;
+  std::vector< std::complex<double> > ylm_k_a, ylm_k_b, ylm_r_a, ylm_r_b;
+};
+static RefBispecState* g_state = nullptr;
+
+void trvref_bispec_teardown() {
+  if (!g_state) return;
+  delete g_state->F_a; delete g_state->F_b; delete g_state->G_00;
+  delete g_state->N_L0; delete g_state->dn_00; delete g_state->stats;
+  delete g_state->sj_a; delete g_state->sj_b; delete g_state->bins; delete g_state->cat;
+  delete g_state; g_state = nullptr;
+}
+
+int trvref_bispec_setup(
+  int n, const double* x, const double* y, const double* z,
+  const double* boxsize, const int* ngrid, const char* assignment,
+  double bin_min, double bin_max, int num_bins, double* elapsed_s
+) {
+  try {
+    trvref_bispec_teardown();
+    g_state = new RefBispecState();
+    RefBispecState& s = *g_state;
+    fill_params(s.params, "sim", "bispec", boxsize, ngrid, assignment, 0, 0, 0, "full", 0,
+                "lin", bin_min, bin_max, num_bins, 0, 60);
+    s.bins = new trv::Binning(s.params);
+    s.bins->set_bins();
+    s.cat = new trv::ParticleCatalogue(60);
+    load_catalogue(*s.cat, n, x, y, z, nullptr, nullptr, nullptr);
+    auto t0 = std::chrono::steady_clock::now();
+    // S/threept.cpp:1543-1569.
+    s.dn_00 = new trv::MeshField(s.params, true, "`dn_00`");
+    s.dn_00->compute_unweighted_field_fluctuations_insitu(*s.cat);
+    s.dn_00->fourier_transform();
+    s.N_L0 = new trv::MeshField(s.params, true, "`N_L0`");
+    s.N_L0->compute_unweighted_field(*s.cat);
+    s.N_L0->fourier_transform();
+    s.sj_a = new trv::maths::SphericalBesselCalculator(0);
+    s.sj_b = new trv::maths::SphericalBesselCalculator(0);
+    s.stats = new trv::FieldStats(s.params);
+    s.ylm_k_a.resize(s.params.nmesh); s.ylm_k_b.resize(s.params.nmesh);
+    s.ylm_r_a.resize(s.params.nmesh); s.ylm_r_b.resize(s.params.nmesh);
+    // S/threept.cpp:1618-1633.
+    typedef trv::maths::SphericalHarmonicCalculator SHC;
+    SHC::store_reduced_spherical_harmonic_in_fourier_space(0, 0, s.params.boxsize, s.params.ngrid, s.ylm_k_a);
+    SHC::store_reduced_spherical_harmonic_in_fourier_space(0, 0, s.params.boxsize, s.params.ngrid, s.ylm_k_b);
+    SHC::store_reduced_spherical_harmonic_in_config_space(0, 0, s.params.boxsize, s.params.ngrid, s.ylm_r_a);
+    SHC::store_reduced_spherical_harmonic_in_config_space(0, 0, s.params.boxsize, s.params.ngrid, s.ylm_r_b);
+    // S/threept.cpp:1665-1672.
+    s.G_00 = new trv::MeshField(s.params, true, "`G_00`");
+    s.G_00->compute_unweighted_field_fluctuations_insitu(*s.cat);
+    s.G_00->fourier_transform();
+    s.G_00->apply_assignment_compensation();
+    s.G_00->inv_fourier_transform();
+    s.F_a = new trv::MeshField(s.params, true, "`F_lm_a`");
+    s.F_b = new trv::MeshField(s.params, true, "`F_lm_b`");
+    auto t1 = std::chrono::steady_clock::now();
+    *elapsed_s = std::chrono::duration<double>(t1 - t0).count();
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+
+// One bin pair (idx_row, idx_col) exactly as the reference's `triu` branch
+// does it (S/threept.cpp:1900-1968) plus its per-pair shot-noise term
+// (S/threept.cpp:2126-2140).  out = {Re bk, Im bk, Re S, Im S}.
+int trvref_bispec_pair(int idx_row, int idx_col, double* out, double* elapsed_s) {
+  try {
+    if (!g_state) { g_err = "trvref_bispec_setup not called"; return 1; }
+    RefBispecState& s = *g_state;
+    auto t0 = std::chrono::steady_clock::now();
+    double k_eff_a, k_eff_b; int nmodes_a, nmodes_b;
+    s.F_a->inv_fourier_transform_ylm_wgtd_field_band_limited(
+      *s.dn_00, s.ylm_k_a, s.bins->bin_edges[idx_row], s.bins->bin_edges[idx_row + 1],
+      k_eff_a, nmodes_a);
+    s.F_b->inv_fourier_transform_ylm_wgtd_field_band_limited(
+      *s.dn_00, s.ylm_k_b, s.bins->bin_edges[idx_col], s.bins->bin_edges[idx_col + 1],
+      k_eff_b, nmodes_b);
+    double bk_re = 0., bk_im = 0.;
+    trv::MeshField& Fa = *s.F_a; trv::MeshField& Fb = *s.F_b; trv::MeshField& G = *s.G_00;
+#pragma omp parallel for reduction(+:bk_re, bk_im)
+    for (long long gid = 0; gid < s.params.nmesh; gid++) {
+      std::complex<double> fa(Fa[gid][0], Fa[gid][1]);
+      std::complex<double> fb(Fb[gid][0], Fb[gid][1]);
+      std::complex<double> g(G[gid][0], G[gid][1]);
+      std::complex<double> v = fa * fb * g;
+      bk_re += v.real(); bk_im += v.imag();
+    }
+    std::complex<double> S = s.stats->compute_uncoupled_shotnoise_for_bispec_per_bin(
+      *s.dn_00, *s.N_L0, s.ylm_r_a, s.ylm_r_b, *s.sj_a, *s.sj_b,
+      double(s.cat->ntotal), k_eff_a, k_eff_b);
+    auto t1 = std::chrono::steady_clock::now();
+    *elapsed_s = std::chrono::duration<double>(t1 - t0).count();
+    out[0] = bk_re * s.dn_00->vol_cell; out[1] = bk_im * s.dn_00->vol_cell;
+    out[2] = S.real(); out[3] = S.imag();
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+
 // Normalisation factors (S/threept.cpp:96-149).
 int trvref_norm(
   int from_mesh, int n, const double* x, const double* y, const double* z,

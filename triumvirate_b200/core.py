@@ -129,6 +129,63 @@ def threept(stat, catalogue_type, pos_d, boxsize, ngrid, assignment, degrees,
     return out
 
 
+def threept_box_arrays(stat, n, x_ptr, y_ptr, z_ptr, on_device, boxsize, ngrid,
+                       assignment, degrees, form, bin_range, num_bins,
+                       norm_factor=1., idx_bin=0, binning="lin", verbose=60,
+                       deterministic=False, part_rank=0, part_count=1):
+    """Periodic-box estimator from three coordinate arrays given by ADDRESS
+    (``x_ptr`` etc. are integers: host addresses, e.g. of pinned numpy/torch
+    buffers, or CUDA device addresses when ``on_device``).  Unit weights."""
+    L = _trv()
+    boxsize, ngrid = _box(boxsize, ngrid)
+    nb = int(num_bins)
+    cap = max(nb * nb, nb) + 8
+    dim = C.c_int(0)
+    c1b = np.zeros(cap); c2b = np.zeros(cap)
+    c1e = np.zeros(cap); c2e = np.zeros(cap)
+    n1 = np.zeros(cap, dtype=np.int32); n2 = np.zeros(cap, dtype=np.int32)
+    raw = np.zeros(2 * cap); shot = np.zeros(2 * cap)
+    status = L.trv_threept_box_arrays(
+        stat.encode(), C.c_longlong(n), C.c_void_p(x_ptr), C.c_void_p(y_ptr),
+        C.c_void_p(z_ptr), C.c_int(1 if on_device else 0),
+        boxsize.ctypes.data_as(_dp), ngrid.ctypes.data_as(_ip), assignment.encode(),
+        C.c_int(degrees[0]), C.c_int(degrees[1]), C.c_int(degrees[2]),
+        form.encode(), C.c_int(idx_bin or 0), binning.encode(),
+        C.c_double(bin_range[0]), C.c_double(bin_range[1]), C.c_int(nb),
+        C.c_double(norm_factor), C.c_int(verbose),
+        C.c_int(1 if deterministic else 0), C.c_int(part_rank), C.c_int(part_count),
+        C.byref(dim),
+        c1b.ctypes.data_as(_dp), c2b.ctypes.data_as(_dp),
+        c1e.ctypes.data_as(_dp), c2e.ctypes.data_as(_dp),
+        n1.ctypes.data_as(_ip), n2.ctypes.data_as(_ip),
+        raw.ctypes.data_as(_dp), shot.ctypes.data_as(_dp),
+    )
+    _check(status)
+    n_ = dim.value
+    raw_c = raw[0:2*n_:2] + 1j * raw[1:2*n_:2]
+    shot_c = shot[0:2*n_:2] + 1j * shot[1:2*n_:2]
+    if stat == "bispec":
+        names = ("k1_bin", "k2_bin", "k1_eff", "k2_eff", "nmodes_1",
+                 "nmodes_2", "bk_raw", "bk_shot")
+    else:
+        names = ("r1_bin", "r2_bin", "r1_eff", "r2_eff", "npairs_1",
+                 "npairs_2", "zeta_raw", "zeta_shot")
+    vals = (c1b[:n_].copy(), c2b[:n_].copy(), c1e[:n_].copy(), c2e[:n_].copy(),
+            n1[:n_].copy(), n2[:n_].copy(), raw_c, shot_c)
+    return dict(zip(names, vals))
+
+
+def profile_enable(on=True):
+    _trv().trv_profile_enable(C.c_int(1 if on else 0))
+
+
+def profile_report():
+    import json
+    buf = C.create_string_buffer(4096)
+    _trv().trv_profile_report(buf, C.c_int(4096))
+    return json.loads(buf.value.decode() or "{}")
+
+
 def norm_particles(pos, nz, ws=None, wc=None, alpha=1.):
     return _norm(0, pos, nz, ws, wc, alpha, [1., 1., 1.], [4, 4, 4], "tsc")
 

@@ -537,15 +537,15 @@ int ensure_sorted(trvb_ctx* ctx, trvb_cat* cat, int shifted, int by_cell) {
   d.shifted = shifted; d.by_cell = by_cell;
   const long long nkeys = (long long)d.nk[0] * d.nk[1] * d.nk[2];
   TRVB_REQUIRE(cat->n < 2147483647LL, "catalogue too large for int indices");
-  if (!cat->order) TRVB_CUDA(cudaMalloc(&cat->order, sizeof(int) * (size_t)cat->n));
+  if (!cat->order) TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->order, sizeof(int) * (size_t)cat->n));
   if (cat->cell_start) {
     TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
-    TRVB_CUDA(cudaFree(cat->cell_start)); cat->cell_start = nullptr;
+    TRVB_CUDA(trvb_dev_free_raw(ctx, cat->cell_start)); cat->cell_start = nullptr;
   }
   int* offsets = nullptr;   // nkeys + 1
   int* cursor = nullptr;    // nkeys
-  TRVB_CUDA(cudaMalloc(&offsets, sizeof(int) * (size_t)(nkeys + 1)));
-  TRVB_CUDA(cudaMalloc(&cursor, sizeof(int) * (size_t)nkeys));
+  TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&offsets, sizeof(int) * (size_t)(nkeys + 1)));
+  TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cursor, sizeof(int) * (size_t)nkeys));
   TRVB_CUDA(cudaMemsetAsync(offsets, 0, sizeof(int) * (size_t)(nkeys + 1), ctx->stream));
   CatView cv = view_of(cat);
   const int threads = 256;
@@ -555,7 +555,7 @@ int ensure_sorted(trvb_ctx* ctx, trvb_cat* cat, int shifted, int by_cell) {
   const long long nscan = nkeys + 1;
   const int nchunks = div_up(nscan, SCAN_CHUNK);
   int* chunk_sums = nullptr;
-  TRVB_CUDA(cudaMalloc(&chunk_sums, sizeof(int) * (size_t)nchunks));
+  TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&chunk_sums, sizeof(int) * (size_t)nchunks));
   k_scan_chunk_sums<<<nchunks, SCAN_THREADS, 0, ctx->stream>>>(offsets, nscan, chunk_sums);
   TRVB_LAUNCH_CHECK();
   k_scan_chunk_offsets<<<1, 1024, 0, ctx->stream>>>(chunk_sums, nchunks);
@@ -573,9 +573,9 @@ int ensure_sorted(trvb_ctx* ctx, trvb_cat* cat, int shifted, int by_cell) {
     cat->cell_start = offsets;
   }
   TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
-  TRVB_CUDA(cudaFree(cursor));
-  TRVB_CUDA(cudaFree(chunk_sums));
-  if (!by_cell) TRVB_CUDA(cudaFree(offsets));
+  TRVB_CUDA(trvb_dev_free_raw(ctx, cursor));
+  TRVB_CUDA(trvb_dev_free_raw(ctx, chunk_sums));
+  if (!by_cell) TRVB_CUDA(trvb_dev_free_raw(ctx, offsets));
   for (int a = 0; a < 3; a++) { cat->sort_n[a] = g.n[a]; cat->sort_L[a] = g.L[a]; }
   cat->sort_shifted = shifted; cat->sort_kind = by_cell;
   return 0;
@@ -642,30 +642,30 @@ extern "C" int trvb_cat_create(trvb_ctx* ctx, trvb_cat** out, long long n,
   cat->owner = ctx; cat->n = n;
   const size_t nb = sizeof(double) * (size_t)n;
   const cudaMemcpyKind kind = src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  TRVB_CUDA(cudaMalloc(&cat->x, nb));
-  TRVB_CUDA(cudaMalloc(&cat->y, nb));
-  TRVB_CUDA(cudaMalloc(&cat->z, nb));
+  TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->x, nb));
+  TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->y, nb));
+  TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->z, nb));
   TRVB_CUDA(cudaMemcpyAsync(cat->x, x, nb, kind, ctx->stream));
   TRVB_CUDA(cudaMemcpyAsync(cat->y, y, nb, kind, ctx->stream));
   TRVB_CUDA(cudaMemcpyAsync(cat->z, z, nb, kind, ctx->stream));
   if (w) {
-    TRVB_CUDA(cudaMalloc(&cat->w, nb));
+    TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->w, nb));
     TRVB_CUDA(cudaMemcpyAsync(cat->w, w, nb, kind, ctx->stream));
   }
   if (los) {
     double* tmp = nullptr;
-    TRVB_CUDA(cudaMalloc(&cat->los, 3 * nb));
+    TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->los, 3 * nb));
     if (src_on_device) {
       tmp = const_cast<double*>(los);
     } else {
-      TRVB_CUDA(cudaMalloc(&tmp, 3 * nb));
+      TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&tmp, 3 * nb));
       TRVB_CUDA(cudaMemcpyAsync(tmp, los, 3 * nb, kind, ctx->stream));
     }
     k_los_to_soa<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(tmp, n, cat->los);
     TRVB_LAUNCH_CHECK();
     if (!src_on_device) {
       TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
-      TRVB_CUDA(cudaFree(tmp));
+      TRVB_CUDA(trvb_dev_free_raw(ctx, tmp));
     }
   }
   TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -679,28 +679,28 @@ extern "C" int trvb_cat_create_aos(trvb_ctx* ctx, trvb_cat** out, long long n,
   TRVB_CUDA(cudaSetDevice(ctx->device));
   const size_t nb = sizeof(double) * (size_t)n;
   double* d_aos = nullptr;
-  TRVB_CUDA(cudaMalloc(&d_aos, 7 * nb));
+  TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&d_aos, 7 * nb));
   TRVB_CUDA(cudaMemcpyAsync(d_aos, pdata, 7 * nb, cudaMemcpyHostToDevice, ctx->stream));
   trvb_cat* cat = new trvb_cat();
   cat->owner = ctx; cat->n = n;
-  TRVB_CUDA(cudaMalloc(&cat->x, nb));
-  TRVB_CUDA(cudaMalloc(&cat->y, nb));
-  TRVB_CUDA(cudaMalloc(&cat->z, nb));
-  TRVB_CUDA(cudaMalloc(&cat->w, nb));
+  TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->x, nb));
+  TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->y, nb));
+  TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->z, nb));
+  TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->w, nb));
   k_aos_to_soa<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(d_aos, n, cat->x, cat->y, cat->z, cat->w);
   TRVB_LAUNCH_CHECK();
   if (los) {
     double* tmp = nullptr;
-    TRVB_CUDA(cudaMalloc(&cat->los, 3 * nb));
-    TRVB_CUDA(cudaMalloc(&tmp, 3 * nb));
+    TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->los, 3 * nb));
+    TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&tmp, 3 * nb));
     TRVB_CUDA(cudaMemcpyAsync(tmp, los, 3 * nb, cudaMemcpyHostToDevice, ctx->stream));
     k_los_to_soa<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(tmp, n, cat->los);
     TRVB_LAUNCH_CHECK();
     TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
-    TRVB_CUDA(cudaFree(tmp));
+    TRVB_CUDA(trvb_dev_free_raw(ctx, tmp));
   }
   TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
-  TRVB_CUDA(cudaFree(d_aos));
+  TRVB_CUDA(trvb_dev_free_raw(ctx, d_aos));
   *out = cat;
   return 0;
 }
@@ -710,7 +710,7 @@ extern "C" int trvb_cat_set_custom_weights(trvb_ctx* ctx, trvb_cat* cat,
   TRVB_REQUIRE(ctx && cat && weights, "trvb_cat_set_custom_weights: null argument");
   TRVB_CUDA(cudaSetDevice(ctx->device));
   const size_t nb = 2 * sizeof(double) * (size_t)cat->n;
-  if (!cat->cw) TRVB_CUDA(cudaMalloc(&cat->cw, nb));
+  if (!cat->cw) TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->cw, nb));
   TRVB_CUDA(cudaMemcpyAsync(cat->cw, weights, nb, cudaMemcpyHostToDevice, ctx->stream));
   TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -718,13 +718,13 @@ extern "C" int trvb_cat_set_custom_weights(trvb_ctx* ctx, trvb_cat* cat,
 
 extern "C" void trvb_cat_destroy(trvb_cat* cat) {
   if (!cat) return;
-  if (cat->owner) { cudaSetDevice(cat->owner->device); cudaStreamSynchronize(cat->owner->stream); }
-  cudaFree(cat->x); cudaFree(cat->y); cudaFree(cat->z);
-  if (cat->w) cudaFree(cat->w);
-  if (cat->los) cudaFree(cat->los);
-  if (cat->cw) cudaFree(cat->cw);
-  if (cat->order) cudaFree(cat->order);
-  if (cat->cell_start) cudaFree(cat->cell_start);
+  if (cat->owner) cudaSetDevice(cat->owner->device);
+  cudaFreeAsync(cat->x, cat->owner->stream); cudaFreeAsync(cat->y, cat->owner->stream); cudaFreeAsync(cat->z, cat->owner->stream);
+  if (cat->w) cudaFreeAsync(cat->w, cat->owner->stream);
+  if (cat->los) cudaFreeAsync(cat->los, cat->owner->stream);
+  if (cat->cw) cudaFreeAsync(cat->cw, cat->owner->stream);
+  if (cat->order) cudaFreeAsync(cat->order, cat->owner->stream);
+  if (cat->cell_start) cudaFreeAsync(cat->cell_start, cat->owner->stream);
   delete cat;
 }
 

@@ -20,7 +20,8 @@
 // ---------------------------------------------------------------------
 
 void trvb_set_error(const char* fmt, ...);
-extern long long g_trvb_launches;
+extern long long g_trvb_launches;    // hand-written kernels launched
+extern long long g_trvb_fft_execs;   // cuFFT executions (library launches)
 
 #define TRVB_CUDA(call)                                                    \
   do {                                                                     \
@@ -98,6 +99,7 @@ struct trvb_ctx {
   double* d_scratch = nullptr;
   size_t scratch_bytes = 0;
   int num_sms = 148;
+  int deterministic = 0;   // 1: reductions avoid atomics (bit-reproducible)
 };
 
 struct trvb_cat {
@@ -118,6 +120,14 @@ struct trvb_cat {
 };
 
 int trvb_scratch(trvb_ctx* ctx, size_t bytes, double** out);
+// Stream-ordered allocation from the device memory pool (no implicit device
+// synchronisation; freed blocks stay cached in the pool for reuse).
+inline cudaError_t trvb_dev_alloc_raw(trvb_ctx* ctx, void** p, size_t bytes) {
+  return cudaMallocAsync(p, bytes ? bytes : 8, ctx->stream);
+}
+inline cudaError_t trvb_dev_free_raw(trvb_ctx* ctx, void* p) {
+  return p ? cudaFreeAsync(p, ctx->stream) : cudaSuccess;
+}
 
 // ---------------------------------------------------------------------
 // Device helpers

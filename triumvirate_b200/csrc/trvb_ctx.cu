@@ -5,6 +5,7 @@
 
 static thread_local std::string g_err;
 long long g_trvb_launches = 0;
+long long g_trvb_fft_execs = 0;
 
 void trvb_set_error(const char* fmt, ...) {
   char buf[2048];
@@ -23,17 +24,18 @@ extern "C" int trvb_device_count(void) {
   return n;
 }
 extern "C" long long trvb_launch_count(void) { return g_trvb_launches; }
-extern "C" void trvb_launch_count_reset(void) { g_trvb_launches = 0; }
+extern "C" void trvb_launch_count_reset(void) { g_trvb_launches = 0; g_trvb_fft_execs = 0; }
+extern "C" long long trvb_fft_exec_count(void) { return g_trvb_fft_execs; }
 
 int trvb_scratch(trvb_ctx* ctx, size_t bytes, double** out) {
   if (ctx->scratch_bytes < bytes) {
     if (ctx->d_scratch) {
       TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
-      TRVB_CUDA(cudaFree(ctx->d_scratch));
+      TRVB_CUDA(trvb_dev_free_raw(ctx, ctx->d_scratch));
       ctx->d_scratch = nullptr; ctx->scratch_bytes = 0;
     }
     size_t want = bytes < (size_t)(1 << 20) ? (size_t)(1 << 20) : bytes;
-    TRVB_CUDA(cudaMalloc(&ctx->d_scratch, want));
+    TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&ctx->d_scratch, want));
     ctx->scratch_bytes = want;
   }
   *out = ctx->d_scratch;
@@ -111,6 +113,14 @@ extern "C" int trvb_ctx_create(trvb_ctx** out, int device, const int ngrid[3],
   ctx->device = device;
   fill_grid(ctx->g, ngrid, boxsize, assignment_order);
   TRVB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  {
+    // Keep freed blocks cached in the stream-ordered pool: meshes of a few GB
+    // are allocated and released many times per estimator call.
+    cudaMemPool_t pool;
+    TRVB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    unsigned long long threshold = ~0ULL;
+    TRVB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+  }
   cudaDeviceProp prop;
   TRVB_CUDA(cudaGetDeviceProperties(&prop, device));
   ctx->num_sms = prop.multiProcessorCount;
@@ -161,6 +171,12 @@ extern "C" void trvb_ctx_destroy(trvb_ctx* ctx) {
   delete ctx;
 }
 
+extern "C" int trvb_ctx_set_deterministic(trvb_ctx* ctx, int on) {
+  TRVB_REQUIRE(ctx != nullptr, "trvb_ctx_set_deterministic: null context");
+  ctx->deterministic = on ? 1 : 0;
+  return 0;
+}
+
 extern "C" int trvb_ctx_sync(trvb_ctx* ctx) {
   TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -182,20 +198,26 @@ extern "C" size_t trvb_mesh_bytes(const trvb_ctx* ctx, int layout) {
 extern "C" int trvb_mem_info(trvb_ctx* ctx, size_t* free_bytes, size_t* total_bytes) {
   TRVB_CUDA(cudaSetDevice(ctx->device));
   TRVB_CUDA(cudaMemGetInfo(free_bytes, total_bytes));
+  // Blocks cached (reserved but unused) by the pool are available to us.
+  cudaMemPool_t pool;
+  TRVB_CUDA(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+  unsigned long long reserved = 0, used = 0;
+  TRVB_CUDA(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved));
+  TRVB_CUDA(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used));
+  if (reserved > used) *free_bytes += (size_t)(reserved - used);
   return 0;
 }
 
 extern "C" int trvb_malloc(trvb_ctx* ctx, void** dptr, size_t bytes) {
   TRVB_CUDA(cudaSetDevice(ctx->device));
-  TRVB_CUDA(cudaMalloc(dptr, bytes ? bytes : 8));
+  TRVB_CUDA(trvb_dev_alloc_raw(ctx, dptr, bytes));
   return 0;
 }
 
 extern "C" int trvb_free(trvb_ctx* ctx, void* dptr) {
   if (!dptr) return 0;
   TRVB_CUDA(cudaSetDevice(ctx->device));
-  TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
-  TRVB_CUDA(cudaFree(dptr));
+  TRVB_CUDA(trvb_dev_free_raw(ctx, dptr));   // stream-ordered: no synchronisation
   return 0;
 }
 

@@ -236,7 +236,7 @@ extern "C" int trvb_fft_forward(trvb_ctx* ctx, trvb_mesh src, trvb_mesh dst,
     TRVB_CUFFT(cufftExecZ2Z(plan, (cufftDoubleComplex*)src.data,
                             (cufftDoubleComplex*)dst.data, CUFFT_FORWARD));
   }
-  g_trvb_launches++;
+  g_trvb_fft_execs++;
   return 0;
 }
 
@@ -256,7 +256,7 @@ extern "C" int trvb_fft_inverse(trvb_ctx* ctx, trvb_mesh src, trvb_mesh dst) {
     TRVB_CUFFT(cufftExecZ2Z(plan, (cufftDoubleComplex*)src.data,
                             (cufftDoubleComplex*)dst.data, CUFFT_INVERSE));
   }
-  g_trvb_launches++;
+  g_trvb_fft_execs++;
   return 0;
 }
 

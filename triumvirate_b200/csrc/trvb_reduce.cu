@@ -14,6 +14,7 @@
 #include "trvb_common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace {
 
@@ -95,6 +96,54 @@ struct ShotLoader {
     cplx xv; xv.re = x.x; xv.im = x.y;
     cplx v = cmul(xv, yy);
     return make_double2(jb * v.re, jb * v.im);
+  }
+};
+
+// Radially binned shot-noise mesh: for cubic cells |x| = dr sqrt(q) with the
+// integer q = i^2 + j^2 + k^2 of the signed cell offset, so the N^3 cells
+// collapse to <= 3 (n/2)^2 + 1 radii before any j_l is evaluated:
+//   hist[q] = sum_{x : q(x) = q} y_a(xhat) y_b(xhat) xi(x).
+__global__ void __launch_bounds__(256)
+k_shot_radial_hist(const double2* __restrict__ xi, GridDesc g, int la, int ma, int lb,
+                   int mb, double* __restrict__ hist) {
+  const bool trivial = (la == 0 && lb == 0);
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < g.nmesh;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int k = signed_index((int)(t % g.n[2]), g.n[2]);
+    const int j = signed_index((int)((t / g.n[2]) % g.n[1]), g.n[1]);
+    const int i = signed_index((int)(t / ((long long)g.n[2] * g.n[1])), g.n[0]);
+    const long long q = (long long)i * i + (long long)j * j + (long long)k * k;
+    const double2 x = xi[t];
+    double re = x.x, im = x.y;
+    if (!trivial) {
+      const double rx = (double)i * g.dr[0], ry = (double)j * g.dr[1], rz = (double)k * g.dr[2];
+      const cplx yy = cmul(ylm_reduced(la, ma, rx, ry, rz), ylm_reduced(lb, mb, rx, ry, rz));
+      cplx xv; xv.re = re; xv.im = im;
+      const cplx v = cmul(xv, yy);
+      re = v.re; im = v.im;
+    }
+    atomicAdd(&hist[2 * q], re);
+    atomicAdd(&hist[2 * q + 1], im);
+  }
+}
+
+struct RadialLoader {
+  const double2* hist;
+  double dr;
+  SjlView sja, sjb;
+  const double* ka; const double* kb;
+  __device__ __forceinline__ double radius(long long q) const {
+    // sqrt(q) dr reproduces the reference's |x| exactly on the axes and to an
+    // ulp elsewhere (j_l is smooth: no discontinuous decision depends on it).
+    return __dmul_rn(sqrt((double)q), dr);
+  }
+  __device__ __forceinline__ double2 a(int ia, long long q) const {
+    return make_double2(sjl_eval(sja, ka[ia] * radius(q)), 0.);
+  }
+  __device__ __forceinline__ double2 hb(int ib, long long q) const {
+    const double jb = sjl_eval(sjb, kb[ib] * radius(q));
+    const double2 h = hist[q];
+    return make_double2(jb * h.x, jb * h.y);
   }
 };
 
@@ -394,15 +443,20 @@ void make_rules(const double* edges, int nbins, int fine, double dsample, int ns
     r.dsample = dsample; r.nsample = nsample;
     r.qlo = 0; r.qhi = 0;
     if (fine) {
-      int qlo = -1, qhi = -1;
-      for (int i = 0; i < nsample; i++) {
-        const double v = i * dsample;
-        if (r.lo <= v && v < r.hi) {
-          if (qlo < 0) qlo = i;
-          qhi = i + 1;
-        }
-      }
-      if (qlo >= 0) { r.qlo = qlo; r.qhi = qhi; }
+      // Indices i with lo <= i*dsample < hi form the range [first(lo), first(hi))
+      // because i*dsample is monotone in i; first(e) = min{i : i*dsample >= e}
+      // is located by a short scan around e/dsample using the reference's own
+      // comparison on i*dsample.
+      auto first_ge = [&](double edge) {
+        long long i = (long long)std::floor(edge / dsample) - 2;
+        if (i < 0) i = 0;
+        while (i < nsample && !((double)i * dsample >= edge)) i++;
+        while (i > 0 && (double)(i - 1) * dsample >= edge) i--;
+        return (int)std::min<long long>(i, nsample);
+      };
+      r.qlo = first_ge(r.lo);
+      r.qhi = first_ge(r.hi);
+      if (r.qhi < r.qlo) r.qhi = r.qlo;
     }
     rules[b] = r;
   }
@@ -476,7 +530,7 @@ extern "C" int trvb_gram_reduce(trvb_ctx* ctx, const void* const* A, int na,
   }
   // Pointer tables live in a small dedicated device buffer.
   const void** d_tab = nullptr;
-  TRVB_CUDA(cudaMalloc(&d_tab, sizeof(void*) * (size_t)(na + nb)));
+  TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&d_tab, sizeof(void*) * (size_t)(na + nb)));
   TRVB_CUDA(cudaMemcpyAsync(d_tab, A, sizeof(void*) * na, cudaMemcpyHostToDevice, ctx->stream));
   TRVB_CUDA(cudaMemcpyAsync(d_tab + na, B, sizeof(void*) * nb, cudaMemcpyHostToDevice, ctx->stream));
   FieldLoader ld;
@@ -485,7 +539,7 @@ extern "C" int trvb_gram_reduce(trvb_ctx* ctx, const void* const* A, int na,
   ld.G = (const double2*)G.data;
   int st = run_gram(ctx, ld, na, nb, ctx->g.nmesh, ia, ib, npairs, out);
   cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_tab);
+  trvb_dev_free_raw(ctx, d_tab);
   return st;
 }
 
@@ -512,21 +566,45 @@ extern "C" int trvb_shot_bispec_reduce(trvb_ctx* ctx, trvb_mesh xi, int la, int 
     else ib[p] = (int)(fb - ub.begin());
   }
   double* d_k = nullptr;
-  TRVB_CUDA(cudaMalloc(&d_k, sizeof(double) * (ua.size() + ub.size())));
+  TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&d_k, sizeof(double) * (ua.size() + ub.size())));
   TRVB_CUDA(cudaMemcpyAsync(d_k, ua.data(), sizeof(double) * ua.size(), cudaMemcpyHostToDevice, ctx->stream));
   TRVB_CUDA(cudaMemcpyAsync(d_k + ua.size(), ub.data(), sizeof(double) * ub.size(), cudaMemcpyHostToDevice, ctx->stream));
-  ShotLoader ld;
-  ld.xi = (const double2*)xi.data; ld.g = ctx->g;
-  ld.sja.y = ita->second.d_y; ld.sja.c = ita->second.d_c;
-  ld.sja.nsample = ita->second.nsample; ld.sja.step = ita->second.step; ld.sja.ell = la;
-  ld.sjb.y = itb->second.d_y; ld.sjb.c = itb->second.d_c;
-  ld.sjb.nsample = itb->second.nsample; ld.sjb.step = itb->second.step; ld.sjb.ell = lb;
-  ld.ka = d_k; ld.kb = d_k + ua.size();
-  ld.la = la; ld.ma = ma; ld.lb = lb; ld.mb = mb;
-  int st = run_gram(ctx, ld, (int)ua.size(), (int)ub.size(), ctx->g.nmesh,
-                    ia.data(), ib.data(), npairs, out);
-  cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_k);
+  SjlView sja, sjb;
+  sja.y = ita->second.d_y; sja.c = ita->second.d_c;
+  sja.nsample = ita->second.nsample; sja.step = ita->second.step; sja.ell = la;
+  sjb.y = itb->second.d_y; sjb.c = itb->second.d_c;
+  sjb.nsample = itb->second.nsample; sjb.step = itb->second.step; sjb.ell = lb;
+  const GridDesc& g = ctx->g;
+  const char* env_direct = getenv("TRV_SHOT_DIRECT");
+  const bool cubic = g.dr[0] == g.dr[1] && g.dr[1] == g.dr[2];
+  const bool radial = cubic && !ctx->deterministic && !(env_direct && env_direct[0] == '1');
+  int st;
+  if (radial) {
+    long long nq = 1;
+    for (int a = 0; a < 3; a++) {
+      const long long h = g.n[a] - g.n[a] / 2;   // largest |signed index|
+      nq += h * h;
+    }
+    double* d_hist = nullptr;
+    TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&d_hist, 2 * sizeof(double) * (size_t)nq));
+    TRVB_CUDA(cudaMemsetAsync(d_hist, 0, 2 * sizeof(double) * (size_t)nq, ctx->stream));
+    const int blocks = (int)std::min<long long>(div_up(g.nmesh, 256), (long long)ctx->num_sms * 16);
+    k_shot_radial_hist<<<blocks, 256, 0, ctx->stream>>>((const double2*)xi.data, g, la, ma, lb, mb, d_hist);
+    TRVB_LAUNCH_CHECK();
+    RadialLoader ld;
+    ld.hist = (const double2*)d_hist; ld.dr = g.dr[0];
+    ld.sja = sja; ld.sjb = sjb; ld.ka = d_k; ld.kb = d_k + ua.size();
+    st = run_gram(ctx, ld, (int)ua.size(), (int)ub.size(), nq, ia.data(), ib.data(), npairs, out);
+    trvb_dev_free_raw(ctx, d_hist);
+  } else {
+    ShotLoader ld;
+    ld.xi = (const double2*)xi.data; ld.g = g;
+    ld.sja = sja; ld.sjb = sjb;
+    ld.ka = d_k; ld.kb = d_k + ua.size();
+    ld.la = la; ld.ma = ma; ld.lb = lb; ld.mb = mb;
+    st = run_gram(ctx, ld, (int)ua.size(), (int)ub.size(), g.nmesh, ia.data(), ib.data(), npairs, out);
+  }
+  trvb_dev_free_raw(ctx, d_k);
   if (st) return st;
   for (int p = 0; p < 2 * npairs; p++) out[p] *= ctx->g.vol_cell;   // S/field.cpp:3393
   return 0;

@@ -31,14 +31,31 @@ namespace dev {
 /// Throw trv::sys::DeviceError carrying trvb_last_error() if `status` != 0.
 void check(int status, const char* what);
 
+/// Optional phase timer (off by default): when enabled, mark() synchronises
+/// the context stream and charges the time since the previous mark to `phase`.
+void profile_enable(bool on);
+void profile_reset();
+void profile_mark(trvb_ctx* ctx, const char* phase);
+std::string profile_report();
+
 /// Shared device context for one (ngrid, boxsize, assignment order).
 std::shared_ptr<trvb_ctx> acquire_context(const trv::ParameterSet& params);
+/// Most recently acquired context (null if none is alive); lets callers put
+/// CUDA events on the stream the estimators enqueue on.
+trvb_ctx* last_context();
+/// Drop the contexts kept alive between calls (plans, tables, scratch).
+void release_contexts();
 
 /// Device catalogue (positions, w, optional LOS) with RAII ownership.
 class Catalogue {
  public:
   Catalogue(std::shared_ptr<trvb_ctx> ctx, ParticleCatalogue& particles,
             LineOfSight* los, bool need_weights);
+  /// From separate coordinate arrays in host or device memory (`w`, `los`
+  /// may be null); no AoS staging copy.
+  Catalogue(std::shared_ptr<trvb_ctx> ctx, long long n, const double* x,
+            const double* y, const double* z, const double* w,
+            const double* los, bool on_device);
   ~Catalogue();
   Catalogue(const Catalogue&) = delete;
   Catalogue& operator=(const Catalogue&) = delete;

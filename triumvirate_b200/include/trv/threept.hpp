@@ -68,6 +68,15 @@ trv::ThreePCFMeasurements compute_3pcf_in_gpp_box(
   ParticleCatalogue& catalogue_data,
   trv::ParameterSet& params, trv::Binning& rbinning, double norm_factor);
 
+/// Array-level overloads (B200 build extension): periodic-box estimators
+/// from coordinate arrays in host (`on_device` false) or device memory.
+trv::BispecMeasurements compute_bispec_in_gpp_box(
+  long long nparticles, const double* x, const double* y, const double* z,
+  bool on_device, trv::ParameterSet& params, trv::Binning kbinning, double norm_factor);
+trv::ThreePCFMeasurements compute_3pcf_in_gpp_box(
+  long long nparticles, const double* x, const double* y, const double* z,
+  bool on_device, trv::ParameterSet& params, trv::Binning& rbinning, double norm_factor);
+
 }  // namespace trv
 
 #endif  // TRV_B200_THREEPT_HPP_

@@ -138,6 +138,71 @@ int trv_threept(
   });
 }
 
+/// Periodic-box estimators from coordinate arrays that may already live in
+/// device memory (`on_device` != 0: x, y, z are CUDA device pointers, e.g. a
+/// torch tensor's data_ptr()); unit weights.  No AoS staging copy.
+int trv_threept_box_arrays(
+  const char* stat, long long n, const double* x, const double* y, const double* z,
+  int on_device,
+  const double* boxsize, const int* ngrid, const char* assignment,
+  int ell1, int ell2, int ELL, const char* form, int idx_bin,
+  const char* binning, double bin_min, double bin_max, int num_bins,
+  double norm_factor, int verbose, int deterministic, int part_rank, int part_count,
+  int* dim, double* c1_bin, double* c2_bin, double* c1_eff, double* c2_eff,
+  int* n1, int* n2, double* raw, double* shot
+) {
+  return guarded([&]() {
+    trv::ParameterSet params;
+    set_params(params, "sim", stat, boxsize, ngrid, assignment, "false",
+               ell1, ell2, ELL, form, idx_bin, binning, bin_min, bin_max, num_bins,
+               verbose, deterministic, part_rank, part_count);
+    trv::Binning bins(params);
+    bins.set_bins();
+    if (std::string(stat) == "bispec") {
+      trv::BispecMeasurements out = trv::compute_bispec_in_gpp_box(
+        n, x, y, z, on_device != 0, params, bins, norm_factor);
+      *dim = out.dim;
+      for (int i = 0; i < out.dim; i++) {
+        c1_bin[i] = out.k1_bin[i]; c2_bin[i] = out.k2_bin[i];
+        c1_eff[i] = out.k1_eff[i]; c2_eff[i] = out.k2_eff[i];
+        n1[i] = out.nmodes_1[i]; n2[i] = out.nmodes_2[i];
+        raw[2*i] = out.bk_raw[i].real(); raw[2*i+1] = out.bk_raw[i].imag();
+        shot[2*i] = out.bk_shot[i].real(); shot[2*i+1] = out.bk_shot[i].imag();
+      }
+    } else {
+      trv::ThreePCFMeasurements out = trv::compute_3pcf_in_gpp_box(
+        n, x, y, z, on_device != 0, params, bins, norm_factor);
+      *dim = out.dim;
+      for (int i = 0; i < out.dim; i++) {
+        c1_bin[i] = out.r1_bin[i]; c2_bin[i] = out.r2_bin[i];
+        c1_eff[i] = out.r1_eff[i]; c2_eff[i] = out.r2_eff[i];
+        n1[i] = out.npairs_1[i]; n2[i] = out.npairs_2[i];
+        raw[2*i] = out.zeta_raw[i].real(); raw[2*i+1] = out.zeta_raw[i].imag();
+        shot[2*i] = out.zeta_shot[i].real(); shot[2*i+1] = out.zeta_shot[i].imag();
+      }
+    }
+  });
+}
+
+/// cudaStream_t of the most recently used estimator context (null before the
+/// first call), so callers can bracket calls with CUDA events on it.
+void* trv_last_stream() {
+  trvb_ctx* c = trv::dev::last_context();
+  return c ? trvb_ctx_stream(c) : nullptr;
+}
+
+void trv_release_contexts() { trv::dev::release_contexts(); }
+
+/// Phase timer of the estimator pipeline (development / bench aid).
+void trv_profile_enable(int on) { trv::dev::profile_enable(on != 0); }
+
+int trv_profile_report(char* buf, int cap) {
+  const std::string rep = trv::dev::profile_report();
+  std::strncpy(buf, rep.c_str(), cap - 1);
+  buf[cap - 1] = '\0';
+  return static_cast<int>(rep.size());
+}
+
 /// Normalisation factors (trv::calc_bispec_normalisation_from_particles /
 /// _from_mesh).
 int trv_norm(

@@ -5,7 +5,9 @@
 // HBM between calls; the host mirror `field` is refreshed on demand only.
 #include "trv/field.hpp"
 
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -37,6 +39,8 @@ namespace {
 typedef std::tuple<int, int, int, double, double, double, int> CtxKey;
 std::mutex g_ctx_mutex;
 std::map<CtxKey, std::weak_ptr<trvb_ctx> > g_ctx_cache;
+std::vector<std::shared_ptr<trvb_ctx> > g_ctx_recent;
+trvb_ctx* g_last_ctx = nullptr;
 
 int device_from_env() {
   // One process per GPU: LOCAL_RANK (torchrun) or TRV_GPU_DEVICE selects it.
@@ -65,14 +69,28 @@ std::shared_ptr<trvb_ctx> acquire_context(const trv::ParameterSet& params) {
   std::lock_guard<std::mutex> lock(g_ctx_mutex);
   auto it = g_ctx_cache.find(key);
   if (it != g_ctx_cache.end()) {
-    if (auto sp = it->second.lock()) return sp;
+    if (auto sp = it->second.lock()) { g_last_ctx = sp.get(); return sp; }
   }
   trvb_ctx* raw = nullptr;
   check(trvb_ctx_create(&raw, device_from_env(), params.ngrid, params.boxsize,
                         params.assignment_order), "trvb_ctx_create");
   std::shared_ptr<trvb_ctx> sp(raw, [](trvb_ctx* c) { trvb_ctx_destroy(c); });
   g_ctx_cache[key] = sp;
+  // Keep the most recent contexts alive between estimator calls so that cuFFT
+  // plans, correction tables and the sort scratch are built once per grid
+  // (the counterpart of the reference's FFTW wisdom, S/field.cpp:90-169).
+  g_ctx_recent.push_back(sp);
+  if (g_ctx_recent.size() > 4) g_ctx_recent.erase(g_ctx_recent.begin());
+  g_last_ctx = raw;
   return sp;
+}
+
+trvb_ctx* last_context() { return g_last_ctx; }
+
+void release_contexts() {
+  std::lock_guard<std::mutex> lock(g_ctx_mutex);
+  g_ctx_recent.clear();
+  g_last_ctx = nullptr;
 }
 
 Catalogue::Catalogue(std::shared_ptr<trvb_ctx> ctx, ParticleCatalogue& particles,
@@ -90,7 +108,50 @@ Catalogue::Catalogue(std::shared_ptr<trvb_ctx> ctx, ParticleCatalogue& particles
         "trvb_cat_create_aos");
 }
 
+Catalogue::Catalogue(std::shared_ptr<trvb_ctx> ctx, long long n, const double* x,
+                     const double* y, const double* z, const double* w,
+                     const double* los, bool on_device) : ctx_(ctx) {
+  check(trvb_cat_create(ctx_.get(), &cat_, n, x, y, z, w, los, on_device ? 1 : 0),
+        "trvb_cat_create");
+}
+
 Catalogue::~Catalogue() { trvb_cat_destroy(cat_); }
+
+namespace {
+bool g_prof_on = false;
+std::chrono::steady_clock::time_point g_prof_last;
+std::vector<std::pair<std::string, double> > g_prof;
+}  // namespace
+
+void profile_enable(bool on) { g_prof_on = on; }
+
+void profile_reset() {
+  g_prof.clear();
+  g_prof_last = std::chrono::steady_clock::now();
+}
+
+void profile_mark(trvb_ctx* ctx, const char* phase) {
+  if (!g_prof_on) return;
+  trvb_ctx_sync(ctx);
+  auto now = std::chrono::steady_clock::now();
+  const double dt = std::chrono::duration<double>(now - g_prof_last).count();
+  g_prof_last = now;
+  for (auto& kv : g_prof) {
+    if (kv.first == phase) { kv.second += dt; return; }
+  }
+  g_prof.emplace_back(phase, dt);
+}
+
+std::string profile_report() {
+  std::string out = "{";
+  char buf[128];
+  for (size_t i = 0; i < g_prof.size(); i++) {
+    std::snprintf(buf, sizeof(buf), "%s\"%s\": %.6f", i ? ", " : "",
+                  g_prof[i].first.c_str(), g_prof[i].second);
+    out += buf;
+  }
+  return out + "}";
+}
 
 void Catalogue::set_custom_weights(const double* weights) {
   check(trvb_cat_set_custom_weights(ctx_.get(), cat_, weights),

@@ -220,13 +220,34 @@ class Engine {
     : params_(params), survey_(rand != nullptr) {
     ctx_ = dev::acquire_context(params);
     c_ = ctx_.get();
+    dev::profile_reset();
     data_.reset(new dev::Catalogue(ctx_, data, los_data, survey_));
     if (survey_) rand_.reset(new dev::Catalogue(ctx_, *rand, los_rand, true));
     ndata_ = data.ntotal;
     if (survey_) alpha_ = data.wstotal / rand->wstotal;   // S/threept.cpp:269
-    vol_ = params.volume;
-    vol_cell_ = vol_ / double(params.nmesh);
-    mode_ = params.deterministic ? 1 : 0;
+    init_common();
+    dev::profile_mark(c_, "upload");
+  }
+
+  /// Periodic-box catalogue given as coordinate arrays (host or device);
+  /// unit weights (S/threept.cpp:1543-1558).
+  Engine(trv::ParameterSet& params, long long n, const double* x, const double* y,
+         const double* z, bool on_device)
+    : params_(params), survey_(false) {
+    ctx_ = dev::acquire_context(params);
+    c_ = ctx_.get();
+    dev::profile_reset();
+    data_.reset(new dev::Catalogue(ctx_, n, x, y, z, nullptr, nullptr, on_device));
+    ndata_ = n;
+    init_common();
+    dev::profile_mark(c_, "upload");
+  }
+
+  void init_common() {
+    vol_ = params_.volume;
+    vol_cell_ = vol_ / double(params_.nmesh);
+    mode_ = params_.deterministic ? 1 : 0;
+    dev::check(trvb_ctx_set_deterministic(c_, mode_), "trvb_ctx_set_deterministic");
   }
 
   trvb_ctx* ctx() { return c_; }
@@ -446,24 +467,20 @@ void choose_subgrid(const trv::ParameterSet& params, double kmax, int nsub[3]) {
 namespace {
 
 trv::BispecMeasurements bispec_impl(
-  ParticleCatalogue& catalogue_data, ParticleCatalogue* catalogue_rand,
-  LineOfSight* los_data, LineOfSight* los_rand,
-  trv::ParameterSet& params, trv::Binning& kbinning, double norm_factor
+  Engine& eng, trv::ParameterSet& params, trv::Binning& kbinning, double norm_factor
 ) {
-  const bool survey = catalogue_rand != nullptr;
-  validate_multipole_coupling(params);
+  const bool survey = eng.survey();
   const cdouble factor_phase = std::pow(trvm::M_I, params.ell1 + params.ell2);
   const int nb = kbinning.num_bins;
   const DataVector dv = make_data_vector(params, nb);
   const std::vector<char> active = active_entries(params, dv.dim);
 
-  Engine eng(params, catalogue_data, catalogue_rand, los_data, los_rand);
   trvb_ctx* c = eng.ctx();
-  const double vol_cell = eng.vol_cell();
 
   // Common fields: delta n_00(k) and N_00(k).
   dev::Mesh dn_00 = eng.density_fluctuation(0, 0);
   dev::Mesh N_00 = survey ? eng.quadratic_field(0, 0) : eng.quadratic_from_fluctuation(dn_00);
+  dev::profile_mark(c, "fields_00");
 
   trvm::SphericalBesselCalculator sj_a(params.ell1), sj_b(params.ell2);
   eng.upload_sjl(sj_a);
@@ -476,6 +493,7 @@ trv::BispecMeasurements bispec_impl(
   dev::check(trvb_shell_stats(c, kbinning.bin_edges.data(), nb, 0, nmodes.data(),
                               ksum.data()), "trvb_shell_stats");
   for (int b = 0; b < nb; b++) keff[b] = ksum[b] / double(nmodes[b]);
+  dev::profile_mark(c, "shell_stats");
 
   // Sub-grid for the shell fields.
   int nsub[3];
@@ -520,6 +538,7 @@ trv::BispecMeasurements bispec_impl(
       N_LM = eng.quadratic_field(params.ELL, t.M);
       Sbar_LM = eng.shotnoise_amp(params.ELL, t.M);
       cached_M = t.M; have_LM = true; have_G = false; have_xi = false;
+      dev::profile_mark(c, "fields_LM");
     }
     if (!survey && !have_LM) {
       Sbar_LM = eng.shotnoise_amp(0, 0);
@@ -549,20 +568,29 @@ trv::BispecMeasurements bispec_impl(
       bk_dv[i] += t.coupling * vol_cell_sub * (
         bk_comp[i] + t.factor_mirror * std::conj(bk_comp[i]));
     }
+    dev::profile_mark(c, "shells_and_pairs");
 
     // ---- shot noise ------------------------------------------------------
     if (params.ell1 == 0 && params.ell2 == 0) {   // S|{i = j = k}
       const cdouble S_ijk = t.coupling * Sbar_LM;
       for (int i = 0; i < dv.dim; i++) if (active[i]) sn_dv[i] += S_ijk;
     }
+    // The binned statistics depend on (ell, m) only: B_000-like cases reuse
+    // one evaluation for both S|{i != j = k} and S|{j != i = k}.
+    std::vector<double> pk, sn;
+    int binned_ell = -1, binned_m = 0;
     auto binned_term = [&](int ell, int m, bool by_row) {
-      std::vector<long long> nm(nb);
-      std::vector<double> kk(nb), pk(2 * nb), sn(2 * nb);
-      const double S[2] = {Sbar_LM.real(), Sbar_LM.imag()};
-      dev::check(trvb_twopt_fourier(c, dn_00.view(), N_LM_ref.view(), S, ell, m,
-                                    kbinning.bin_edges.data(), kbinning.bin_centres.data(),
-                                    nb, nm.data(), kk.data(), pk.data(), sn.data()),
-                 "trvb_twopt_fourier");
+      if (!(binned_ell == ell && binned_m == m)) {
+        std::vector<long long> nm(nb);
+        std::vector<double> kk(nb);
+        pk.assign(2 * nb, 0.); sn.assign(2 * nb, 0.);
+        const double S[2] = {Sbar_LM.real(), Sbar_LM.imag()};
+        dev::check(trvb_twopt_fourier(c, dn_00.view(), N_LM_ref.view(), S, ell, m,
+                                      kbinning.bin_edges.data(), kbinning.bin_centres.data(),
+                                      nb, nm.data(), kk.data(), pk.data(), sn.data()),
+                   "trvb_twopt_fourier");
+        binned_ell = ell; binned_m = m;
+      }
       for (int i = 0; i < dv.dim; i++) {
         if (!active[i]) continue;
         const int b = by_row ? dv.row[i] : dv.col[i];
@@ -572,6 +600,7 @@ trv::BispecMeasurements bispec_impl(
     };
     if (params.ell2 == 0) binned_term(params.ell1, t.m1, true);    // S|{i != j = k}
     if (params.ell1 == 0) binned_term(params.ell2, t.m2, false);   // S|{j != i = k}
+    dev::profile_mark(c, "shot_binned");
 
     // S|{i = j != k}: one xi mesh, all pairs in one pass.
     if (!have_xi) {
@@ -580,6 +609,7 @@ trv::BispecMeasurements bispec_impl(
       dev::check(trvb_shot_xi(c, dn_LM_ref.view(), N_00.view(), S, xi.view()), "trvb_shot_xi");
       trvs::count_ifft += 1;
       have_xi = true;
+      dev::profile_mark(c, "shot_xi");
     }
     {
       std::vector<double> ka, kb; std::vector<int> where;
@@ -599,6 +629,7 @@ trv::BispecMeasurements bispec_impl(
         }
       }
     }
+    dev::profile_mark(c, "shot_reduce");
     if (trvs::currTask == 0) {
       trvs::logger.stat("Bispectrum term computed at orders (m1, m2, M) = +/-(%d, %d, %d).",
                         t.m1, t.m2, t.M);
@@ -625,19 +656,15 @@ trv::BispecMeasurements bispec_impl(
 // =====================================================================
 
 trv::ThreePCFMeasurements threepcf_impl(
-  ParticleCatalogue& catalogue_data, ParticleCatalogue* catalogue_rand,
-  LineOfSight* los_data, LineOfSight* los_rand,
-  trv::ParameterSet& params, trv::Binning& rbinning, double norm_factor
+  Engine& eng, trv::ParameterSet& params, trv::Binning& rbinning, double norm_factor
 ) {
-  const bool survey = catalogue_rand != nullptr;
-  validate_multipole_coupling(params);
+  const bool survey = eng.survey();
   const cdouble factor_phase = std::pow(trvm::M_I, params.ell1 + params.ell2);
   const double factor_parity = std::pow(-1., params.ell1 + params.ell2);
   const int nb = rbinning.num_bins;
   const DataVector dv = make_data_vector(params, nb);
   const std::vector<char> active = active_entries(params, dv.dim);
 
-  Engine eng(params, catalogue_data, catalogue_rand, los_data, los_rand);
   trvb_ctx* c = eng.ctx();
   const double vol_cell = eng.vol_cell();
 
@@ -755,8 +782,9 @@ trv::BispecMeasurements compute_bispec(
   if (trvs::currTask == 0) {
     trvs::logger.stat("Computing bispectrum from paired survey-type catalogues...");
   }
-  trv::BispecMeasurements out = bispec_impl(
-    catalogue_data, &catalogue_rand, los_data, los_rand, params, kbinning, norm_factor);
+  validate_multipole_coupling(params);
+  Engine eng(params, catalogue_data, &catalogue_rand, los_data, los_rand);
+  trv::BispecMeasurements out = bispec_impl(eng, params, kbinning, norm_factor);
   if (trvs::currTask == 0) {
     trvs::logger.stat("... computed bispectrum from paired survey-type catalogues.");
   }
@@ -773,8 +801,9 @@ trv::BispecMeasurements compute_bispec_in_gpp_box(
       "Computing bispectrum from a periodic-box simulation-type catalogue "
       "in the global plane-parallel approximation...");
   }
-  trv::BispecMeasurements out = bispec_impl(
-    catalogue_data, nullptr, nullptr, nullptr, params, kbinning, norm_factor);
+  validate_multipole_coupling(params);
+  Engine eng(params, catalogue_data, nullptr, nullptr, nullptr);
+  trv::BispecMeasurements out = bispec_impl(eng, params, kbinning, norm_factor);
   if (trvs::currTask == 0) {
     trvs::logger.stat(
       "... computed bispectrum from a periodic-box simulation-type catalogue "
@@ -793,8 +822,9 @@ trv::ThreePCFMeasurements compute_3pcf(
     trvs::logger.stat(
       "Computing three-point correlation function from paired survey-type catalogues...");
   }
-  trv::ThreePCFMeasurements out = threepcf_impl(
-    catalogue_data, &catalogue_rand, los_data, los_rand, params, rbinning, norm_factor);
+  validate_multipole_coupling(params);
+  Engine eng(params, catalogue_data, &catalogue_rand, los_data, los_rand);
+  trv::ThreePCFMeasurements out = threepcf_impl(eng, params, rbinning, norm_factor);
   if (trvs::currTask == 0) {
     trvs::logger.stat(
       "... computed three-point correlation function from paired survey-type catalogues.");
@@ -812,14 +842,42 @@ trv::ThreePCFMeasurements compute_3pcf_in_gpp_box(
       "Computing three-point correlation function from a periodic-box "
       "simulation-type catalogue in the global plane-parallel approximation...");
   }
-  trv::ThreePCFMeasurements out = threepcf_impl(
-    catalogue_data, nullptr, nullptr, nullptr, params, rbinning, norm_factor);
+  validate_multipole_coupling(params);
+  Engine eng(params, catalogue_data, nullptr, nullptr, nullptr);
+  trv::ThreePCFMeasurements out = threepcf_impl(eng, params, rbinning, norm_factor);
   if (trvs::currTask == 0) {
     trvs::logger.stat(
       "... computed three-point correlation function from a periodic-box "
       "simulation-type catalogue in the global plane-parallel approximation.");
   }
   return out;
+}
+
+// ---------------------------------------------------------------------
+// Array-level entry points (B200 build extension): the periodic-box
+// estimators fed from coordinate arrays in host or DEVICE memory, skipping
+// the AoS staging copy of ParticleCatalogue.  Same results as the
+// catalogue-based overloads.
+// ---------------------------------------------------------------------
+
+trv::BispecMeasurements compute_bispec_in_gpp_box(
+  long long nparticles, const double* x, const double* y, const double* z,
+  bool on_device, trv::ParameterSet& params, trv::Binning kbinning, double norm_factor
+) {
+  trvs::logger.reset_level(params.verbose);
+  validate_multipole_coupling(params);
+  Engine eng(params, nparticles, x, y, z, on_device);
+  return bispec_impl(eng, params, kbinning, norm_factor);
+}
+
+trv::ThreePCFMeasurements compute_3pcf_in_gpp_box(
+  long long nparticles, const double* x, const double* y, const double* z,
+  bool on_device, trv::ParameterSet& params, trv::Binning& rbinning, double norm_factor
+) {
+  trvs::logger.reset_level(params.verbose);
+  validate_multipole_coupling(params);
+  Engine eng(params, nparticles, x, y, z, on_device);
+  return threepcf_impl(eng, params, rbinning, norm_factor);
 }
 
 }  // namespace trv
