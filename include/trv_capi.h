@@ -1,0 +1,143 @@
+/* trv_capi.h -- flat C entry points of libtrv_b200.so (host C++ API over the
+ * device layer of trvb.h).
+ *
+ * libtrv_b200.so carries the reference's C++ surface (namespace trv::, headers
+ * in triumvirate_b200/include/trv/ mirroring /root/reference/src/triumvirate/
+ * include/ (the .hpp set)) AND the functions below, which play the role of the
+ * reference's Cython layer for FFI callers that cannot link C++ symbols
+ * (ctypes, cgo, JNI, ...): they marshal plain arrays into
+ * trv::ParticleCatalogue / trv::ParameterSet / trv::Binning, call the
+ * estimator and copy the result vectors back.
+ *
+ * Every function returns 0 on success; non-zero: 1 = C++ exception
+ * (trv::sys::*Error), 2 = invalid argument/parameter, 3 = device error
+ * (no CUDA device, CUDA/cuFFT failure).  trv_last_error() holds the message.
+ * Unlike the reference's `compute_*` externs (no `except +`,
+ * T/_threept.pyx:50-95) no exception escapes.  There is no CPU fallback: with
+ * no usable GPU the estimators return 3.
+ *
+ * Citations: T/ = src/triumvirate/, S/ = src/triumvirate/src/ of the reference.
+ */
+#ifndef TRV_CAPI_H_INCLUDED_
+#define TRV_CAPI_H_INCLUDED_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* trv_last_error(void);
+
+/* trv::sys::get_gpu_count (S/monitor.cpp:258-282), honours TRV_GPU_MODE and
+ * TRV_GPU_MAXNUM. */
+int trv_gpu_count(void);
+
+/* trv::sys::count_fft / count_ifft / gbytesMaxMemGPU (I/monitor.hpp:252-266). */
+void trv_counters(int* count_fft, int* count_ifft, double* gib_gpu_max);
+
+/* Three-point estimators: replaces T/_threept.pyx:128-174 (_compute_bispec /
+ * _compute_3pcf -> trv::compute_bispec / compute_3pcf, S/threept.cpp:248,1014)
+ * and T/_threept.pyx:226-248 (_compute_*_in_gpp_box -> S/threept.cpp:1473,2190).
+ *   stat            "bispec" | "3pcf"
+ *   catalogue_type  "sim" (periodic box, global plane-parallel) | "survey"
+ *   per catalogue   n, x/y/z/nz/ws/wc float64 columns of length n (nz, ws, wc
+ *                   may be NULL: 0, 1, 1 -- T/threept.py:1482-1485), LOS as a
+ *                   contiguous (n, 3) array or NULL (I/dataobjs.hpp:186-188)
+ *   parameters      the members of trv::ParameterSet that the path reads
+ *                   (T/parameters.pxd:15-79); validate() is applied
+ *                   (S/parameters.cpp:466-1270), so e.g. `interlace` is forced
+ *                   off and form="full" with ell1==ell2 becomes "triu"
+ *   custom_edges    num_bins+1 edges for binning="custom", else NULL
+ *   deterministic   1: bit-reproducible assignment and reductions
+ *   part_rank/part_count  multi-GPU work split: this call computes the entries
+ *                   idx with idx % part_count == part_rank and leaves zeros
+ *                   elsewhere (sum over ranks = the full result)
+ * Outputs (capacity >= max(num_bins^2, num_bins) entries): *dim = dv_dim;
+ * bin centres, effective coordinates, nmodes/npairs, raw and shot statistics as
+ * interleaved (re, im) already multiplied by norm_factor
+ * (I/dataobjs.hpp:249-282). */
+int trv_threept(
+  const char* stat, const char* catalogue_type,
+  int nd, const double* xd, const double* yd, const double* zd,
+  const double* nzd, const double* wsd, const double* wcd, const double* los_d,
+  int nr, const double* xr, const double* yr, const double* zr,
+  const double* nzr, const double* wsr, const double* wcr, const double* los_r,
+  const double* boxsize, const int* ngrid, const char* assignment, const char* interlace,
+  int ell1, int ell2, int ELL, const char* form, int idx_bin,
+  const char* binning, double bin_min, double bin_max, int num_bins,
+  const double* custom_edges,
+  double norm_factor, int verbose, int deterministic, int part_rank, int part_count,
+  int* dim, double* c1_bin, double* c2_bin, double* c1_eff, double* c2_eff,
+  int* n1, int* n2, double* raw, double* shot, double* elapsed_s);
+
+/* Periodic-box estimators from three coordinate arrays in host memory
+ * (on_device == 0) or CUDA device memory (on_device != 0); unit weights.
+ * Same results as trv_threept("...", "sim", ...) without the AoS staging copy of
+ * trv::ParticleCatalogue::load_particle_data (S/particles.cpp:512-563). */
+int trv_threept_box_arrays(
+  const char* stat, long long n, const double* x, const double* y, const double* z,
+  int on_device,
+  const double* boxsize, const int* ngrid, const char* assignment,
+  int ell1, int ell2, int ELL, const char* form, int idx_bin,
+  const char* binning, double bin_min, double bin_max, int num_bins,
+  double norm_factor, int verbose, int deterministic, int part_rank, int part_count,
+  int* dim, double* c1_bin, double* c2_bin, double* c1_eff, double* c2_eff,
+  int* n1, int* n2, double* raw, double* shot);
+
+/* cudaStream_t of the most recently used estimator context (NULL before the
+ * first call). */
+void* trv_last_stream(void);
+/* Drop the cached contexts (cuFFT plans, tables). */
+void trv_release_contexts(void);
+
+/* Phase timer of the estimator pipeline (bench aid); report is a JSON object
+ * {"phase": seconds, ...}. */
+void trv_profile_enable(int on);
+int trv_profile_report(char* buf, int cap);
+
+/* trv::calc_bispec_normalisation_from_particles (S/threept.cpp:96-136; host
+ * only) or, from_mesh != 0, _from_mesh (S/threept.cpp:138-149). */
+int trv_norm(
+  int from_mesh, int n, const double* x, const double* y, const double* z,
+  const double* nz, const double* ws, const double* wc, double alpha,
+  const double* boxsize, const int* ngrid, const char* assignment, double* norm);
+
+/* trv::MeshField pipeline for intermediate checks (S/field.cpp:569-1112,
+ * 1496-1720, 1764-1785).  stage: 0 assignment, 1 + fourier_transform,
+ * 2 + apply_assignment_compensation, 3 + inv_fourier_transform.  Weights:
+ * complex per particle (w_re, w_im) or NULL (unit).  field_out: 2*nmesh doubles. */
+int trv_mesh(
+  int stage, int subtract_mean, int interlace, int deterministic,
+  int n, const double* x, const double* y, const double* z,
+  const double* w_re, const double* w_im,
+  const double* boxsize, const int* ngrid, const char* assignment,
+  double* field_out, double* elapsed_assign_s);
+
+/* trv::maths (S/maths.cpp:167-375): reduced spherical harmonics at n positions
+ * (pos is (n, 3); out interleaved), spline-evaluated and exact j_l, Wigner 3-j. */
+void trv_ylm(int ell, int m, const double* pos, int n, double* out);
+void trv_sjl(int ell, const double* x, int n, double* out);
+double trv_sjl_exact(int ell, double x);
+double trv_w3j(int j1, int j2, int j3, int m1, int m2, int m3);
+/* trv::calc_coupling_coeff_3pt (S/threept.cpp:65-89). */
+double trv_coupling(int l1, int l2, int L, int m1, int m2, int M);
+
+/* trv::Binning(params).set_bins() (S/dataobjs.cpp:134-249). */
+int trv_binning(
+  const char* space, const char* scheme, double bmin, double bmax, int nb,
+  const double* boxsize, const int* ngrid,
+  double* edges, double* centres, double* widths);
+
+/* trv::ParameterSet::validate (S/parameters.cpp:466-1270): derived members. */
+int trv_validate(
+  const char* catalogue_type, const char* statistic_type,
+  const char* assignment, const char* interlace, const char* form,
+  int ell1, int ell2, int ELL, int num_bins, int idx_bin,
+  double bin_min, double bin_max,
+  char* shape_out, char* interlace_out, char* npoint_out, char* space_out,
+  int* assignment_order);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif  /* TRV_CAPI_H_INCLUDED_ */

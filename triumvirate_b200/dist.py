@@ -1,0 +1,67 @@
+"""Multi-GPU execution of the three-point estimators: one process per GPU.
+
+The reference has no distributed mode (``trv::sys::currTask`` is the constant 0,
+I/monitor.hpp:249-250).  Here the mesh is replicated on every GPU and the
+independent entries of the data vector -- the (k1, k2) bin pairs of every
+(m1, m2, M) term, S/threept.cpp:1902-1904, 2137-2139 -- are dealt to the ranks;
+each entry is produced by exactly one rank (zeros elsewhere), so a single small
+all-reduce(sum) of ``4 * dv_dim`` doubles over NCCL/NVLink completes the result
+and is bit-identical to the single-GPU one.  ``torch.distributed`` is plumbing
+only: ``nccl`` on GPUs, ``gloo`` in the CPU tests.
+"""
+import numpy as np
+
+_STAT_KEYS = {"bispec": ("bk_raw", "bk_shot"), "3pcf": ("zeta_raw", "zeta_shot")}
+
+
+def owner_of(idx, world_size):
+    """Rank that computes data-vector entry ``idx`` (round-robin, the rule of
+    ``active_entries`` in src/threept.cpp)."""
+    return idx % world_size
+
+
+def local_entries(dim, rank, world_size):
+    return np.arange(dim)[np.arange(dim) % world_size == rank]
+
+
+def pack(out, stat):
+    """Partial statistics of one rank -> flat float64 buffer (re, im interleaved)."""
+    raw, shot = _STAT_KEYS[stat]
+    return np.concatenate([np.ascontiguousarray(out[raw]).view(np.float64),
+                           np.ascontiguousarray(out[shot]).view(np.float64)])
+
+
+def unpack(buf, out, stat):
+    raw, shot = _STAT_KEYS[stat]
+    n = len(out[raw])
+    out = dict(out)
+    out[raw] = np.array(buf[:2 * n]).view(np.complex128)
+    out[shot] = np.array(buf[2 * n:4 * n]).view(np.complex128)
+    return out
+
+
+def allreduce_result(out, stat, group=None, device=None):
+    """Sum the ranks' partial result vectors; every rank gets the full result."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return out
+    buf = torch.from_numpy(pack(out, stat))
+    if device is not None:
+        buf = buf.to(device)
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    return unpack(buf.cpu().numpy(), out, stat)
+
+
+def threept(stat, *args, group=None, device=None, **kwargs):
+    """``core.threept`` / ``core.threept_box_arrays`` on this rank's share of the
+    entries followed by the all-reduce.  Pass ``x_ptr=...`` style arguments
+    through ``kwargs`` exactly as for the single-GPU call."""
+    import torch.distributed as dist
+    from . import core
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    kwargs.update(part_rank=rank, part_count=world)
+    fn = core.threept_box_arrays if kwargs.pop("_arrays", False) else core.threept
+    out = fn(stat, *args, **kwargs)
+    return allreduce_result(out, stat, group=group, device=device)
