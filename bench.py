@@ -78,28 +78,84 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region."""
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region.
+
+    NVML is polled from a background thread (clock + event-reason bitmask only,
+    every 20 ms).  A looping ``nvidia-smi -lms`` process was measured to stall
+    the CUDA driver for tens of milliseconds per poll on this box -- several
+    estimator steps -- so it is only the fallback when NVML cannot be loaded.
+    """
+    REASONS = {  # nvmlClocksEventReasons bits
+        0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+        0x4: "sw_power_cap",
+    }
 
     def __init__(self, index):
         self.index = index
-        self.proc = None
-        self.file = None
+        self.samples, self.bits = [], 0
+        self.thread = self.stop_flag = self.handle = None
+        self.sm_max = None
+        self.proc = self.file = None
 
     def start(self):
         try:
+            import threading
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            uuid = None
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                ent = vis.split(",")[self.index].strip()
+                if ent.isdigit():
+                    idx = int(ent)
+                else:
+                    uuid = ent
+            self.handle = (pynvml.nvmlDeviceGetHandleByUUID(uuid) if uuid
+                           else pynvml.nvmlDeviceGetHandleByIndex(idx))
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.stop_flag = threading.Event()
+
+            def loop():
+                while not self.stop_flag.is_set():
+                    try:
+                        self.samples.append(float(self.nv.nvmlDeviceGetClockInfo(
+                            self.handle, self.nv.NVML_CLOCK_SM)))
+                        self.bits |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                    except Exception:
+                        pass
+                    self.stop_flag.wait(0.02)
+
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.thread = None
+            self._start_smi()
+
+    def _start_smi(self):
+        fields = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                  "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                  "clocks_event_reasons.sw_power_cap")
+        try:
             self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                ["nvidia-smi", f"--query-gpu={fields}", "--format=csv,noheader,nounits",
                  "-i", str(self.index), "-lms", "200"],
                 stdout=self.file, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "how": "none"}
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            if self.samples:
+                out.update(sm_mhz=float(np.median(self.samples)), sm_max_mhz=self.sm_max,
+                           reasons=sorted(n for b, n in self.REASONS.items() if self.bits & b),
+                           samples=len(self.samples), how="nvml thread, 20 ms period")
+            return out
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -122,7 +178,7 @@ class ClockSampler:
                     reasons.add(name)
         if sm:
             out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)),
-                       reasons=sorted(reasons), samples=len(sm))
+                       reasons=sorted(reasons), samples=len(sm), how="nvidia-smi -lms 200")
         return out
 
 
@@ -186,12 +242,21 @@ def run_b200(args):
         barrier()
         t0 = time.perf_counter()
         e0.record(stream)
+        per_step = []
         for _ in range(steps):
+            ts = time.perf_counter()
             out = step(src, on_device)
+            per_step.append(time.perf_counter() - ts)
         e1.record(stream)
         barrier()
         wall = time.perf_counter() - t0
         ev = e0.elapsed_time(e1) * 1.e-3
+        if os.environ.get("BENCH_DEBUG"):
+            tbl = _lib.trvb()
+            tbl.trvb_arena_malloc_count.restype = C.c_longlong
+            print(f"[bench debug] on_device={on_device} wall={wall:.4f} ev={ev:.4f} per-step ms="
+                  f"{[round(1e3 * t, 2) for t in per_step]} arena cudaMallocs so far="
+                  f"{tbl.trvb_arena_malloc_count()}", file=sys.stderr)
         # The estimator synchronises its stream when it returns results, so the
         # event interval and the wall clock agree; keep the larger of the two.
         sec = max(ev, wall if world == 1 else ev)
@@ -271,9 +336,9 @@ def assignment_roofline(torch, dev, dpos, wl):
     mesh = torch.empty(ng * ng * ng, dtype=torch.float64, device=dev)
 
     class Mesh(C.Structure):
-        _fields_ = [("data", C.c_void_p), ("layout", C.c_int)]
+        _fields_ = [("data", C.c_void_p), ("layout", C.c_int), ("k0_add", C.c_double)]
 
-    m = Mesh(mesh.data_ptr(), 0)
+    m = Mesh(mesh.data_ptr(), 0, 0.)
     tb.trvb_ctx_stream.restype = C.c_void_p
     stream = torch.cuda.ExternalStream(tb.trvb_ctx_stream(ctx), device=dev)
 

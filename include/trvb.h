@@ -40,8 +40,12 @@ typedef struct trvb_cat trvb_cat;   /* device-resident particle catalogue   */
 enum { TRVB_REAL = 0, TRVB_COMPLEX = 1, TRVB_HALF = 2 };
 
 typedef struct {
-  void* data;   /* device pointer */
-  int layout;   /* TRVB_REAL | TRVB_COMPLEX | TRVB_HALF */
+  void* data;      /* device pointer */
+  int layout;      /* TRVB_REAL | TRVB_COMPLEX | TRVB_HALF */
+  double k0_add;   /* real value added to the k = 0 element whenever the mesh is
+                      READ as a Fourier-space source; lets N_00(k) = dn_00(k) +
+                      N delta_k0 (S/threept.cpp:1554-1558) share dn_00's buffer.
+                      Ignored for configuration-space meshes and destinations. */
 } trvb_mesh;
 
 /* Particle weight kinds for assignment / catalogue sums. */
@@ -66,6 +70,9 @@ int trvb_device_count(void);
 long long trvb_launch_count(void);
 long long trvb_fft_exec_count(void);
 void trvb_launch_count_reset(void);
+/* Number of cudaMalloc calls made by the caching device arena so far (steady
+ * state: constant from one estimator call to the next). */
+long long trvb_arena_malloc_count(void);
 
 /* ---- context: replaces MeshField/FieldStats ctor state ----------------
  * (S/field.cpp:45-365: dr, dk, vol, vol_cell, FFT plans; S/field.cpp:2076).
@@ -158,7 +165,9 @@ int trvb_compensate(trvb_ctx* ctx, trvb_mesh kmesh);
  * sum_x F_a F_b G (S/threept.cpp:1708-1717) only involve Fourier modes with
  * |m_i| <= mcut; the sum over the n^3 mesh equals (n^3/ns^3) times the sum
  * over an ns^3 mesh whenever ns > 4*mcut (no aliasing of the triple product),
- * or ns = n.  A sub-grid context shares the parent's box and tables. */
+ * or ns = n.  A sub-grid context shares the parent's box, tables and stream; it
+ * is cached in and owned by the parent (repeated calls with the same extents
+ * return the same handle, trvb_ctx_destroy on it is a no-op). */
 int trvb_subgrid_create(trvb_ctx* parent, trvb_ctx** sub, const int nsub[3]);
 
 /* Number of modes and sum of |k| per shell [edges[b], edges[b+1]), all bins
@@ -174,9 +183,20 @@ int trvb_shell_stats(trvb_ctx* ctx, const double* edges, int nbins, int fine,
  * (S/field.cpp:1792-1906 with amp = 1/nmodes folded in; src lives on the
  * parent grid `ctx`, dst is a TRVB_COMPLEX mesh of `sub`).  klo < 0 and
  * khi < 0 disable the shell test (all modes representable on `sub`):
- * with l = m = 0 and amp = 1/V this is G(x) (S/field.cpp:1764-1785,1657). */
+ * with l = m = 0 and amp = 1/V this is G(x) (S/field.cpp:1764-1785,1657).
+ * dst may be TRVB_REAL when src is TRVB_HALF, m = 0 and l is even (the filtered
+ * spectrum is then Hermitian). */
 int trvb_shell_ifft(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh src, int ell,
                     int m, double klo, double khi, double amp, trvb_mesh dst);
+
+/* Batched trvb_shell_ifft: the `nbins` shells [klo[q], khi[q]) of one (l, m),
+ * each scaled by amp[q], written as nbins CONSECUTIVE meshes of `sub` starting
+ * at device address `dst`, in one sparse pass over the low-|k| modes and one
+ * batched inverse FFT.  dst_layout: TRVB_COMPLEX, or TRVB_REAL when the filtered
+ * spectrum is Hermitian (src TRVB_HALF, m = 0, even l), which halves the work. */
+int trvb_shell_ifft_batch(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh src, int ell,
+                          int m, const double* klo, const double* khi,
+                          const double* amp, int nbins, void* dst, int dst_layout);
 
 /* dst(x) = IFFT[ amp * j_l(|k| r) * y_lm(khat) * src(k) / W(k) ]
  * (S/field.cpp:1908-2010, amp = 1/V), spline table from trvb_sjl_table. */
@@ -191,7 +211,8 @@ int trvb_sjl_table(trvb_ctx* ctx, int ell, const double* y, const double* c,
 /* ---- reductions -------------------------------------------------------
  * out[p] = sum_x A[ia[p]](x) * B[ib[p]](x) * G(x), complex, for p < npairs
  * (S/threept.cpp:1708-1717 and clones, all pairs in one pass over x).
- * A, B: arrays of na / nb device pointers to TRVB_COMPLEX meshes of `ctx`. */
+ * A, B: arrays of na / nb device pointers to meshes of `ctx` in G's layout:
+ * all TRVB_COMPLEX, or all TRVB_REAL (real fields: a quarter of the flops). */
 int trvb_gram_reduce(trvb_ctx* ctx, const void* const* A, int na,
                      const void* const* B, int nb, trvb_mesh G,
                      const int* ia, const int* ib, int npairs, double* out);
@@ -206,12 +227,15 @@ int trvb_twopt_fourier(trvb_ctx* ctx, trvb_mesh fa, trvb_mesh fb,
                        double* k, double* pk, double* sn);
 
 /* xi(x) = IFFT[ (fa conj(fb)/C1 - S C1/C1) / V ]  (S/field.cpp:3273-3345,
- * 3018-3090); dst TRVB_COMPLEX on the same grid. */
+ * 3018-3090); dst TRVB_COMPLEX on the same grid, or TRVB_REAL when fa and fb
+ * are both TRVB_HALF (spectra of real fields) and Im S = 0: the product is then
+ * Hermitian, xi is real and half the traffic suffices. */
 int trvb_shot_xi(trvb_ctx* ctx, trvb_mesh fa, trvb_mesh fb, const double S[2],
                  trvb_mesh dst);
 
 /* out[p] = vol_cell * sum_x j_la(ka[p] |x|) j_lb(kb[p] |x|) y_la,ma(xhat)
- * y_lb,mb(xhat) xi(x)   (S/field.cpp:3362-3393), all pairs in one pass. */
+ * y_lb,mb(xhat) xi(x)   (S/field.cpp:3362-3393), all pairs in one pass.
+ * xi: TRVB_COMPLEX or TRVB_REAL (see trvb_shot_xi). */
 int trvb_shot_bispec_reduce(trvb_ctx* ctx, trvb_mesh xi, int la, int ma,
                             int lb, int mb, const double* ka, const double* kb,
                             int npairs, double* out);

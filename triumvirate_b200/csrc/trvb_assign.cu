@@ -3,9 +3,13 @@
 //
 // Replaces the OpenMP scatter loops of S/field.cpp:618-1112 and the weight
 // kernels of S/field.cpp:1259-1269,1379-1391.  Two modes:
-//   throughput     particles are counting-sorted by 4^3-cell tile so that a
-//                  warp's red.global.add.f64 traffic stays inside a few cache
-//                  lines of L2; one thread per particle, p^3 REDs each.
+//   throughput     particles are counting-sorted by 4^3-cell tile and their
+//                  columns gathered into that order; for TSC/PCS a warp then
+//                  spreads ONE particle per instruction, lanes = (row, z-cell)
+//                  of its stencil, so the red.global.add.f64 of a stencil row
+//                  coalesce into one or two 32-byte L2 sectors (the L2 retires
+//                  ~one RED sector per slice per clock: sectors, not elements,
+//                  are the cost).  NGP/CIC: one thread per particle.
 //   deterministic  particles are counting-sorted by home cell with ascending
 //                  particle id inside a cell; one thread per OUTPUT cell
 //                  gathers its contributions and adds them in ascending
@@ -141,6 +145,36 @@ __device__ __forceinline__ cplx particle_weight(const CatView& c, long long i,
   return out;
 }
 
+// The catalogue in sort order: positions and weight packed as one 32-byte
+// record per particle (a single sector per particle for the spreading kernels).
+struct SortedView {
+  const double4* p4;                                      // {x, y, z, w}
+  const double* lx; const double* ly; const double* lz;   // may be null
+  const double* cw;                                       // may be null
+  long long n;
+};
+
+__device__ __forceinline__ cplx particle_weight(const SortedView& c, long long i,
+                                                const double4& p, int kind, int L, int M) {
+  cplx out; out.im = 0.;
+  const double w = p.w;
+  if (kind == TRVB_W_UNIT) { out.re = 1.; return out; }
+  if (kind == TRVB_W_W) { out.re = w; return out; }
+  if (kind == TRVB_W_CUSTOM) { out.re = c.cw[2 * i]; out.im = c.cw[2 * i + 1]; return out; }
+  cplx y; y.re = 1.; y.im = 0.;
+  if (!(L == 0 && M == 0)) y = ylm_reduced(L, M, c.lx[i], c.ly[i], c.lz[i]);
+  if (kind == TRVB_W_YLM_W) {
+    out.re = y.re * w; out.im = y.im * w;
+  } else if (kind == TRVB_W_CYLM_W2) {
+    const double w2 = w * w;
+    out.re = y.re * w2; out.im = -y.im * w2;
+  } else {  // TRVB_W_YLM_W3
+    const double w3 = w * w * w;
+    out.re = y.re * w3; out.im = y.im * w3;
+  }
+  return out;
+}
+
 // ---------------------------------------------------------------------
 // Counting sort by tile (throughput) or by home cell (deterministic).
 // ---------------------------------------------------------------------
@@ -249,13 +283,17 @@ __global__ void k_scan_apply(int* __restrict__ counts, long long nkeys,
   }
 }
 
+// `s4` non-null: also store the packed record at its sorted slot (a full
+// 32-byte sector write; no later gather of the positions is needed).
 __global__ void k_sort_scatter(CatView c, SortDesc d, int* __restrict__ cursor,
-                               int* __restrict__ order) {
+                               int* __restrict__ order, double4* __restrict__ s4) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < c.n;
        i += (long long)gridDim.x * blockDim.x) {
-    int key = sort_key(d, c.x[i], c.y[i], c.z[i]);
+    const double x = c.x[i], y = c.y[i], z = c.z[i];
+    int key = sort_key(d, x, y, z);
     int pos = atomicAdd(&cursor[key], 1);
     order[pos] = (int)i;
+    if (s4) s4[pos] = make_double4(x, y, z, c.w ? c.w[i] : 1.);
   }
 }
 
@@ -277,23 +315,38 @@ __global__ void k_sort_segments(const int* __restrict__ seg_end, long long nkeys
   }
 }
 
+// Gather catalogue columns into sorted order: the packed records (when the
+// scatter did not write them), lines of sight and custom weights.
+__global__ void k_gather_sorted(CatView c, const int* __restrict__ order,
+                                double4* __restrict__ s4, double* __restrict__ slos,
+                                double* __restrict__ scw) {
+  for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < c.n;
+       s += (long long)gridDim.x * blockDim.x) {
+    const long long i = order[s];
+    if (s4) s4[s] = make_double4(c.x[i], c.y[i], c.z[i], c.w ? c.w[i] : 1.);
+    if (slos) { slos[s] = c.lx[i]; slos[c.n + s] = c.ly[i]; slos[2 * c.n + s] = c.lz[i]; }
+    if (scw) { scw[2 * s] = c.cw[2 * i]; scw[2 * s + 1] = c.cw[2 * i + 1]; }
+  }
+}
+
 // ---------------------------------------------------------------------
-// Throughput assignment: one thread per (sorted) particle, p^3 REDs.
+// Throughput assignment.
 // ---------------------------------------------------------------------
 
+// One thread per particle, p^3 REDs (NGP/CIC).  `c` is the SORTED view.
 template <int ORDER, bool COMPLEX>
 __global__ void __launch_bounds__(256)
-k_assign_scatter(CatView c, const int* __restrict__ order, GridDesc g, int shifted,
+k_assign_scatter(SortedView c, GridDesc g, int shifted,
                  int kind, int L, int M, double scale, double* __restrict__ mesh) {
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < c.n;
-       t += (long long)gridDim.x * blockDim.x) {
-    const long long i = order ? order[t] : t;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < c.n;
+       i += (long long)gridDim.x * blockDim.x) {
     int ijk[3][ORDER];
     double win[3][ORDER];
-    window_1d<ORDER>(grid_loc(c.x[i], g.n[0], g.L[0], shifted), g.n[0], ijk[0], win[0]);
-    window_1d<ORDER>(grid_loc(c.y[i], g.n[1], g.L[1], shifted), g.n[1], ijk[1], win[1]);
-    window_1d<ORDER>(grid_loc(c.z[i], g.n[2], g.L[2], shifted), g.n[2], ijk[2], win[2]);
-    cplx wt = particle_weight(c, i, kind, L, M);
+    const double4 p = c.p4[i];
+    window_1d<ORDER>(grid_loc(p.x, g.n[0], g.L[0], shifted), g.n[0], ijk[0], win[0]);
+    window_1d<ORDER>(grid_loc(p.y, g.n[1], g.L[1], shifted), g.n[1], ijk[1], win[1]);
+    window_1d<ORDER>(grid_loc(p.z, g.n[2], g.L[2], shifted), g.n[2], ijk[2], win[2]);
+    cplx wt = particle_weight(c, i, p, kind, L, M);
     const double bre = __dmul_rn(scale, wt.re);
     const double bim = COMPLEX ? __dmul_rn(scale, wt.im) : 0.;
 #pragma unroll
@@ -322,6 +375,75 @@ k_assign_scatter(CatView c, const int* __restrict__ order, GridDesc g, int shift
   }
 }
 
+// Warp-cooperative spreading (TSC/PCS).  Each lane first evaluates the 1-D
+// windows of one particle into shared memory; the warp then walks its 32
+// particles, every instruction covering RPP stencil rows x ORDER z-cells
+// (x re/im) of ONE particle, so that the REDs of a row fall into one or two
+// 32-byte sectors.  Same products, in the same order, as k_assign_scatter.
+template <int ORDER, bool COMPLEX>
+__global__ void __launch_bounds__(256)
+k_assign_coop(SortedView c, GridDesc g, int shifted,
+              int kind, int L, int M, double scale, double* __restrict__ mesh) {
+  constexpr int NW = 8;                               // warps per block
+  constexpr int LPR = ORDER * (COMPLEX ? 2 : 1);      // lanes per stencil row
+  constexpr int RPP = 32 / LPR;                       // rows per instruction
+  constexpr int NROW = ORDER * ORDER;
+  constexpr int NPASS = (NROW + RPP - 1) / RPP;
+  __shared__ double s_win[NW][32][3 * ORDER];
+  __shared__ int s_idx[NW][32][3 * ORDER];
+  __shared__ double s_wt[NW][32][2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = lane / LPR, q = lane - r * LPR;
+  const int cz = COMPLEX ? (q >> 1) : q;
+  const int comp = COMPLEX ? (q & 1) : 0;
+  const long long nchunk = (c.n + 31) / 32;
+  for (long long chunk = (long long)blockIdx.x * NW + warp; chunk < nchunk;
+       chunk += (long long)gridDim.x * NW) {
+    const long long i = chunk * 32 + lane;
+    const bool ok = i < c.n;
+    __syncwarp();
+    if (ok) {
+      int ijk[ORDER]; double win[ORDER];
+      const double4 p = c.p4[i];
+      window_1d<ORDER>(grid_loc(p.x, g.n[0], g.L[0], shifted), g.n[0], ijk, win);
+#pragma unroll
+      for (int t = 0; t < ORDER; t++) { s_win[warp][lane][t] = win[t]; s_idx[warp][lane][t] = ijk[t]; }
+      window_1d<ORDER>(grid_loc(p.y, g.n[1], g.L[1], shifted), g.n[1], ijk, win);
+#pragma unroll
+      for (int t = 0; t < ORDER; t++) { s_win[warp][lane][ORDER + t] = win[t]; s_idx[warp][lane][ORDER + t] = ijk[t]; }
+      window_1d<ORDER>(grid_loc(p.z, g.n[2], g.L[2], shifted), g.n[2], ijk, win);
+#pragma unroll
+      for (int t = 0; t < ORDER; t++) { s_win[warp][lane][2 * ORDER + t] = win[t]; s_idx[warp][lane][2 * ORDER + t] = ijk[t]; }
+      const cplx wt = particle_weight(c, i, p, kind, L, M);
+      s_wt[warp][lane][0] = __dmul_rn(scale, wt.re);
+      s_wt[warp][lane][1] = __dmul_rn(scale, wt.im);
+    }
+    __syncwarp();
+    const int count = (int)min((long long)32, c.n - chunk * 32);
+    if (r < RPP) {
+      for (int s = 0; s < count; s++) {
+        const double* w = s_win[warp][s];
+        const int* id = s_idx[warp][s];
+        const double base = s_wt[warp][s][comp];
+        const double wz = w[2 * ORDER + cz];
+        const int kz = id[2 * ORDER + cz];
+#pragma unroll
+        for (int pass = 0; pass < NPASS; pass++) {
+          const int row = r + RPP * pass;
+          if (row < NROW) {
+            const int a = row / ORDER, b = row - a * ORDER;
+            const long long gid = ((long long)id[a] * g.n[1] + id[ORDER + b]) * g.n[2] + kz;
+            const double v = __dmul_rn(__dmul_rn(__dmul_rn(base, w[a]), w[ORDER + b]), wz);
+            if (gid >= 0 && gid < g.nmesh) {   // S/field.cpp:1042
+              atomicAdd(&mesh[COMPLEX ? 2 * gid + comp : gid], v);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------
 // Deterministic assignment: one thread per output cell, ordered gather.
 // ---------------------------------------------------------------------
@@ -330,22 +452,23 @@ constexpr int DET_CAP = 96;   // candidates buffered per cell before fallback
 
 template <int ORDER>
 __device__ __forceinline__ bool contribution(
-  const CatView& c, int pid, const GridDesc& g, int shifted,
+  const SortedView& c, int pid /* slot in the sorted view */, const GridDesc& g, int shifted,
   int ci, int cj, int ck, double& wprod_x, double& wprod_y, double& wprod_z
 ) {
   int ijk[ORDER]; double win[ORDER];
   bool hit;
-  window_1d<ORDER>(grid_loc(c.x[pid], g.n[0], g.L[0], shifted), g.n[0], ijk, win);
+  const double4 p = c.p4[pid];
+  window_1d<ORDER>(grid_loc(p.x, g.n[0], g.L[0], shifted), g.n[0], ijk, win);
   hit = false;
 #pragma unroll
   for (int a = 0; a < ORDER; a++) if (ijk[a] == ci) { wprod_x = win[a]; hit = true; }
   if (!hit) return false;
-  window_1d<ORDER>(grid_loc(c.y[pid], g.n[1], g.L[1], shifted), g.n[1], ijk, win);
+  window_1d<ORDER>(grid_loc(p.y, g.n[1], g.L[1], shifted), g.n[1], ijk, win);
   hit = false;
 #pragma unroll
   for (int a = 0; a < ORDER; a++) if (ijk[a] == cj) { wprod_y = win[a]; hit = true; }
   if (!hit) return false;
-  window_1d<ORDER>(grid_loc(c.z[pid], g.n[2], g.L[2], shifted), g.n[2], ijk, win);
+  window_1d<ORDER>(grid_loc(p.z, g.n[2], g.L[2], shifted), g.n[2], ijk, win);
   hit = false;
 #pragma unroll
   for (int a = 0; a < ORDER; a++) if (ijk[a] == ck) { wprod_z = win[a]; hit = true; }
@@ -354,7 +477,7 @@ __device__ __forceinline__ bool contribution(
 
 template <int ORDER, bool COMPLEX>
 __global__ void __launch_bounds__(128)
-k_assign_gather(CatView c, const int* __restrict__ order,
+k_assign_gather(SortedView c, const int* __restrict__ order,
                 const int* __restrict__ cell_start, GridDesc g, int shifted,
                 int kind, int L, int M, double scale, double pre /* 1/vol_cell or 1 */,
                 int accumulate, double* __restrict__ mesh) {
@@ -375,8 +498,8 @@ k_assign_gather(CatView c, const int* __restrict__ order,
   int ncand = 0;
   bool overflow = false;
 
-  auto value_of = [&](int pid, double wx, double wy, double wz, double& vre, double& vim) {
-    cplx wt = particle_weight(c, pid, kind, L, M);
+  auto value_of = [&](int slot, double wx, double wy, double wz, double& vre, double& vim) {
+    cplx wt = particle_weight(c, slot, c.p4[slot], kind, L, M);
     // ((((inv_vol_cell * w) * Wx) * Wy) * Wz), S/field.cpp:1044-1048.
     double bre = __dmul_rn(pre, wt.re);
     if (scale != 1.) bre = __dmul_rn(bre, scale);
@@ -401,10 +524,10 @@ k_assign_gather(CatView c, const int* __restrict__ order,
         for (int s = b; s < e; s++) {
           const int pid = order[s];
           double wx, wy, wz;
-          if (!contribution<ORDER>(c, pid, g, shifted, ci, cj, ck, wx, wy, wz)) continue;
+          if (!contribution<ORDER>(c, s, g, shifted, ci, cj, ck, wx, wy, wz)) continue;
           if (ncand >= DET_CAP) { overflow = true; break; }
           double vre, vim;
-          value_of(pid, wx, wy, wz, vre, vim);
+          value_of(s, wx, wy, wz, vre, vim);
           // Insertion keeps candidates ascending in particle id.
           int q = ncand - 1;
           while (q >= 0 && cand_pid[q] > pid) {
@@ -436,7 +559,7 @@ k_assign_gather(CatView c, const int* __restrict__ order,
     // Dense cell: repeated selection of the next particle id (no storage).
     int last = -1;
     while (true) {
-      int best = 0x7fffffff; double bx = 0., by = 0., bz = 0.;
+      int best = 0x7fffffff, best_slot = 0; double bx = 0., by = 0., bz = 0.;
       for (int da = 0; da < SPAN; da++) {
         int hi_ = ci - LO + da; hi_ = (hi_ % g.n[0] + g.n[0]) % g.n[0];
         for (int db = 0; db < SPAN; db++) {
@@ -449,15 +572,15 @@ k_assign_gather(CatView c, const int* __restrict__ order,
               const int pid = order[s];
               if (pid <= last || pid >= best) continue;
               double wx, wy, wz;
-              if (!contribution<ORDER>(c, pid, g, shifted, ci, cj, ck, wx, wy, wz)) continue;
-              best = pid; bx = wx; by = wy; bz = wz;
+              if (!contribution<ORDER>(c, s, g, shifted, ci, cj, ck, wx, wy, wz)) continue;
+              best = pid; best_slot = s; bx = wx; by = wy; bz = wz;
             }
           }
         }
       }
       if (best == 0x7fffffff) break;
       double vre, vim;
-      value_of(best, bx, by, bz, vre, vim);
+      value_of(best_slot, bx, by, bz, vre, vim);
       acc_re = __dadd_rn(acc_re, vre);
       if (COMPLEX) acc_im = __dadd_rn(acc_im, vim);
       last = best;
@@ -521,14 +644,55 @@ __global__ void k_los_to_soa(const double* __restrict__ los, long long n, double
   }
 }
 
+SortedView sorted_view_of(const trvb_cat* cat) {
+  SortedView v;
+  v.p4 = cat->s4;
+  v.lx = cat->slos; v.ly = cat->slos ? cat->slos + cat->n : nullptr;
+  v.lz = cat->slos ? cat->slos + 2 * cat->n : nullptr;
+  v.cw = cat->scw;
+  v.n = cat->n;
+  return v;
+}
+
+int alloc_sorted(trvb_ctx* ctx, trvb_cat* cat) {
+  const size_t nb = sizeof(double) * (size_t)cat->n;
+  if (!cat->s4) TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->s4, 4 * nb));
+  if (cat->los && !cat->slos) TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->slos, 3 * nb));
+  if (cat->cw && !cat->scw) TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->scw, 2 * nb));
+  return 0;
+}
+
+// Gather what the scatter did not already place: with_records == false skips
+// the packed {x, y, z, w} records.
+int gather_sorted(trvb_ctx* ctx, trvb_cat* cat, bool with_records) {
+  int st = alloc_sorted(ctx, cat);
+  if (st) return st;
+  cat->scw_valid = cat->cw != nullptr;
+  if (!with_records && !cat->slos && !cat->scw) return 0;
+  const int blocks = (int)std::min<long long>(div_up(cat->n, 256), (long long)ctx->num_sms * 16);
+  k_gather_sorted<<<blocks, 256, 0, ctx->stream>>>(view_of(cat), cat->order,
+                                                  with_records ? cat->s4 : nullptr,
+                                                  cat->slos, cat->scw);
+  TRVB_LAUNCH_CHECK();
+  return 0;
+}
+
+// by_cell == 0: throughput order (4^3-cell tiles of the UNSHIFTED home cell;
+// it only provides locality, so it also serves the shifted shadow mesh).
+// by_cell == 1: home cell of the (possibly shifted) mesh, ascending particle id
+// inside a cell, plus the cell offsets the ordered gather needs.
 int ensure_sorted(trvb_ctx* ctx, trvb_cat* cat, int shifted, int by_cell) {
   const GridDesc& g = ctx->g;
+  if (!by_cell) shifted = 0;
   bool valid = cat->order != nullptr && cat->sort_kind == by_cell
     && cat->sort_shifted == shifted;
   for (int a = 0; a < 3; a++) {
     valid = valid && cat->sort_n[a] == g.n[a] && cat->sort_L[a] == g.L[a];
   }
-  if (valid) return 0;
+  if (valid) {
+    if (cat->cw && !cat->scw_valid) return gather_sorted(ctx, cat, false);
+    return 0;
+  }
   SortDesc d;
   for (int a = 0; a < 3; a++) {
     d.n[a] = g.n[a]; d.L[a] = g.L[a];
@@ -538,8 +702,8 @@ int ensure_sorted(trvb_ctx* ctx, trvb_cat* cat, int shifted, int by_cell) {
   const long long nkeys = (long long)d.nk[0] * d.nk[1] * d.nk[2];
   TRVB_REQUIRE(cat->n < 2147483647LL, "catalogue too large for int indices");
   if (!cat->order) TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->order, sizeof(int) * (size_t)cat->n));
+  { int st = alloc_sorted(ctx, cat); if (st) return st; }
   if (cat->cell_start) {
-    TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
     TRVB_CUDA(trvb_dev_free_raw(ctx, cat->cell_start)); cat->cell_start = nullptr;
   }
   int* offsets = nullptr;   // nkeys + 1
@@ -564,7 +728,10 @@ int ensure_sorted(trvb_ctx* ctx, trvb_cat* cat, int shifted, int by_cell) {
   TRVB_LAUNCH_CHECK();
   TRVB_CUDA(cudaMemcpyAsync(cursor, offsets, sizeof(int) * (size_t)nkeys,
                             cudaMemcpyDeviceToDevice, ctx->stream));
-  k_sort_scatter<<<blocks, threads, 0, ctx->stream>>>(cv, d, cursor, cat->order);
+  // Throughput order: the scatter places the packed records itself.  Cell
+  // order: ids are sorted inside each cell first, records gathered after.
+  k_sort_scatter<<<blocks, threads, 0, ctx->stream>>>(cv, d, cursor, cat->order,
+                                                     by_cell ? nullptr : cat->s4);
   TRVB_LAUNCH_CHECK();
   if (by_cell) {
     const int sb = (int)std::min<long long>(div_up(nkeys, threads), (long long)ctx->num_sms * 32);
@@ -572,13 +739,12 @@ int ensure_sorted(trvb_ctx* ctx, trvb_cat* cat, int shifted, int by_cell) {
     TRVB_LAUNCH_CHECK();
     cat->cell_start = offsets;
   }
-  TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
-  TRVB_CUDA(trvb_dev_free_raw(ctx, cursor));
+  TRVB_CUDA(trvb_dev_free_raw(ctx, cursor));   // stream-ordered reuse: no sync
   TRVB_CUDA(trvb_dev_free_raw(ctx, chunk_sums));
   if (!by_cell) TRVB_CUDA(trvb_dev_free_raw(ctx, offsets));
   for (int a = 0; a < 3; a++) { cat->sort_n[a] = g.n[a]; cat->sort_L[a] = g.L[a]; }
   cat->sort_shifted = shifted; cat->sort_kind = by_cell;
-  return 0;
+  return gather_sorted(ctx, cat, by_cell != 0);
 }
 
 template <int ORDER>
@@ -587,22 +753,34 @@ int launch_assign(trvb_ctx* ctx, trvb_cat* cat, int kind, int L, int M, double s
                   trvb_mesh mesh) {
   const GridDesc& g = ctx->g;
   const bool cplx_mesh = mesh.layout == TRVB_COMPLEX;
-  CatView cv = view_of(cat);
   if (mode == 0) {
     int st = ensure_sorted(ctx, cat, shifted, 0);
     if (st) return st;
+    SortedView cv = sorted_view_of(cat);
     if (!accumulate) {
       TRVB_CUDA(cudaMemsetAsync(mesh.data, 0, trvb_mesh_bytes(ctx, mesh.layout), ctx->stream));
     }
     const double s = density_units ? scale * (1. / g.vol_cell) : scale;
     const int threads = 256;
-    const int blocks = div_up(cat->n, threads);
-    if (cplx_mesh) {
-      k_assign_scatter<ORDER, true><<<blocks, threads, 0, ctx->stream>>>(
-        cv, cat->order, g, shifted, kind, L, M, s, (double*)mesh.data);
+    if (ORDER >= 3) {
+      const long long nchunk = (cat->n + 31) / 32;
+      const int blocks = (int)std::min<long long>(div_up(nchunk, 8), (long long)ctx->num_sms * 64);
+      if (cplx_mesh) {
+        k_assign_coop<(ORDER >= 3 ? ORDER : 3), true><<<blocks, threads, 0, ctx->stream>>>(
+          cv, g, shifted, kind, L, M, s, (double*)mesh.data);
+      } else {
+        k_assign_coop<(ORDER >= 3 ? ORDER : 3), false><<<blocks, threads, 0, ctx->stream>>>(
+          cv, g, shifted, kind, L, M, s, (double*)mesh.data);
+      }
     } else {
-      k_assign_scatter<ORDER, false><<<blocks, threads, 0, ctx->stream>>>(
-        cv, cat->order, g, shifted, kind, L, M, s, (double*)mesh.data);
+      const int blocks = div_up(cat->n, threads);
+      if (cplx_mesh) {
+        k_assign_scatter<ORDER, true><<<blocks, threads, 0, ctx->stream>>>(
+          cv, g, shifted, kind, L, M, s, (double*)mesh.data);
+      } else {
+        k_assign_scatter<ORDER, false><<<blocks, threads, 0, ctx->stream>>>(
+          cv, g, shifted, kind, L, M, s, (double*)mesh.data);
+      }
     }
     TRVB_LAUNCH_CHECK();
   } else {
@@ -610,6 +788,7 @@ int launch_assign(trvb_ctx* ctx, trvb_cat* cat, int kind, int L, int M, double s
                  "deterministic assignment needs at least 4 cells per axis");
     int st = ensure_sorted(ctx, cat, shifted, 1);
     if (st) return st;
+    SortedView cv = sorted_view_of(cat);
     const double pre = density_units ? 1. / g.vol_cell : 1.;   // S/field.cpp:996
     const int threads = 128;
     const int blocks = div_up(g.nmesh, threads);
@@ -713,18 +892,18 @@ extern "C" int trvb_cat_set_custom_weights(trvb_ctx* ctx, trvb_cat* cat,
   if (!cat->cw) TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->cw, nb));
   TRVB_CUDA(cudaMemcpyAsync(cat->cw, weights, nb, cudaMemcpyHostToDevice, ctx->stream));
   TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  cat->scw_valid = false;   // re-gather into sorted order on next use
   return 0;
 }
 
 extern "C" void trvb_cat_destroy(trvb_cat* cat) {
   if (!cat) return;
   if (cat->owner) cudaSetDevice(cat->owner->device);
-  cudaFreeAsync(cat->x, cat->owner->stream); cudaFreeAsync(cat->y, cat->owner->stream); cudaFreeAsync(cat->z, cat->owner->stream);
-  if (cat->w) cudaFreeAsync(cat->w, cat->owner->stream);
-  if (cat->los) cudaFreeAsync(cat->los, cat->owner->stream);
-  if (cat->cw) cudaFreeAsync(cat->cw, cat->owner->stream);
-  if (cat->order) cudaFreeAsync(cat->order, cat->owner->stream);
-  if (cat->cell_start) cudaFreeAsync(cat->cell_start, cat->owner->stream);
+  trvb_ctx* o = cat->owner;
+  trvb_dev_free_raw(o, cat->x); trvb_dev_free_raw(o, cat->y); trvb_dev_free_raw(o, cat->z);
+  trvb_dev_free_raw(o, cat->w); trvb_dev_free_raw(o, cat->los); trvb_dev_free_raw(o, cat->cw);
+  trvb_dev_free_raw(o, cat->order); trvb_dev_free_raw(o, cat->cell_start);
+  trvb_dev_free_raw(o, cat->s4); trvb_dev_free_raw(o, cat->slos); trvb_dev_free_raw(o, cat->scw);
   delete cat;
 }
 

@@ -76,6 +76,7 @@ struct GridDesc {
 struct SjlTable {
   double* d_y = nullptr;
   double* d_c = nullptr;
+  std::vector<double> h_y, h_c;   // host copies: skip re-uploading an identical table
   int nsample = 0;
   double step = 0.;
 };
@@ -85,14 +86,20 @@ struct trvb_ctx {
   cudaStream_t stream = nullptr;
   GridDesc g;
   trvb_ctx* parent = nullptr;       // non-null for a sub-grid context
+  // Sub-grid contexts handed out by trvb_subgrid_create, keyed by extents;
+  // owned by this (root) context so that their cuFFT plans persist.
+  std::map<std::vector<int>, trvb_ctx*> subgrids;
   // Per-axis tables on the PARENT grid, indexed by storage index i < n[ax]:
   //   sinc[ax][i]  = sin(u)/u, u = pi*m/n  (m signed)   S/field.cpp:1138-1145
   //   alias[ax][i] = per-axis factor of C1(k)           S/field.cpp:3479-3502
   double* d_sinc[3] = {nullptr, nullptr, nullptr};
   double* d_alias[3] = {nullptr, nullptr, nullptr};
+  double* d_ralias[3] = {nullptr, nullptr, nullptr};   // 1 / alias
   // cuFFT plans, created lazily.
   cufftHandle plan_z2z = 0, plan_d2z = 0, plan_z2d = 0;
   bool has_z2z = false, has_d2z = false, has_z2d = false;
+  // Batched out-of-place/in-place plans keyed by (cufftType, batch).
+  std::map<std::pair<int, int>, cufftHandle> batch_plans;
   // Spherical-Bessel spline tables keyed by ell.
   std::map<int, SjlTable> sjl;
   // Scratch for two-stage reductions.
@@ -109,8 +116,12 @@ struct trvb_cat {
   double* w = nullptr;         // nullptr -> unit weights
   double* los = nullptr;       // SoA: lx[n], ly[n], lz[n] or nullptr
   double* cw = nullptr;        // custom complex weights (interleaved) or nullptr
-  // Cell-sorted permutation cache (valid for the grid it was built for).
+  // Cell-sorted permutation cache (valid for the grid it was built for) and
+  // the catalogue columns gathered into that order (coalesced kernel reads).
   int* order = nullptr;        // particle ids sorted by sort key
+  double4* s4 = nullptr;       // {x, y, z, w} per particle: one 32-byte sector
+  double* slos = nullptr; double* scw = nullptr;
+  bool scw_valid = false;
   int* cell_start = nullptr;   // deterministic mode: nmesh+1 offsets
   int sort_n[3] = {0, 0, 0};
   double sort_L[3] = {0., 0., 0.};
@@ -120,13 +131,23 @@ struct trvb_cat {
 };
 
 int trvb_scratch(trvb_ctx* ctx, size_t bytes, double** out);
-// Stream-ordered allocation from the device memory pool (no implicit device
-// synchronisation; freed blocks stay cached in the pool for reuse).
+// Device memory comes from a process-wide caching arena (trvb_ctx.cu): blocks
+// are cudaMalloc'ed once, handed back to a size-keyed free list on release and
+// reused without touching the driver (meshes of a few GB are allocated and
+// released many times per estimator call; the driver's own pool re-maps
+// physical memory when block sizes vary, which costs milliseconds per GB).
+// Reuse is stream-ordered: a block released on stream s is reusable at once
+// by work enqueued later on s; another stream first synchronises s.
+cudaError_t trvb_arena_alloc(int device, cudaStream_t stream, void** p, size_t bytes);
+cudaError_t trvb_arena_free(int device, cudaStream_t stream, void* p);
+size_t trvb_arena_cached_bytes(int device);
+void trvb_arena_trim(int device);   // cudaFree every cached (unused) block
+void trvb_arena_retire_stream(int device, cudaStream_t stream);   // stream synced + about to die
 inline cudaError_t trvb_dev_alloc_raw(trvb_ctx* ctx, void** p, size_t bytes) {
-  return cudaMallocAsync(p, bytes ? bytes : 8, ctx->stream);
+  return trvb_arena_alloc(ctx->device, ctx->stream, p, bytes);
 }
 inline cudaError_t trvb_dev_free_raw(trvb_ctx* ctx, void* p) {
-  return p ? cudaFreeAsync(p, ctx->stream) : cudaSuccess;
+  return p ? trvb_arena_free(ctx->device, ctx->stream, p) : cudaSuccess;
 }
 
 // ---------------------------------------------------------------------
@@ -167,10 +188,26 @@ struct KView {
   const double2* p;
   int layout;
   int n0, n1, n2, nh;
+  double add0;   // trvb_mesh::k0_add
 };
+
+// Configuration-space mesh read as complex values (REAL meshes have Im = 0).
+struct XView {
+  const double* p;
+  int cplx;
+};
+__device__ __forceinline__ double2 xload(const XView& v, long long cell) {
+  if (v.cplx) return reinterpret_cast<const double2*>(v.p)[cell];
+  return make_double2(v.p[cell], 0.);
+}
 
 __device__ __forceinline__ cplx kload(const KView& v, int i, int j, int k) {
   cplx r;
+  if ((i | j | k) == 0) {
+    double2 t = v.p[0];
+    r.re = t.x + v.add0; r.im = t.y;
+    return r;
+  }
   if (v.layout == TRVB_COMPLEX) {
     double2 t = v.p[((long long)i * v.n1 + j) * v.n2 + k];
     r.re = t.x; r.im = t.y;
@@ -312,5 +349,31 @@ __device__ __forceinline__ double block_sum(double v, double* smem32) {
 }
 
 inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// Row-wise traversal of an [n0][n1][n2s] mesh without 64-bit divisions:
+// rows (i, j) are dealt to (blockIdx.x, threadIdx.y), the contiguous last
+// axis to threadIdx.x.  f(i, j, k, flat_index).
+template <class F>
+__device__ __forceinline__ void for_each_cell(int n0, int n1, int n2s, F f) {
+  const int rows = n0 * n1;
+  for (int row = blockIdx.x * blockDim.y + threadIdx.y; row < rows;
+       row += gridDim.x * blockDim.y) {
+    const int i = row / n1, j = row - i * n1;
+    const long long base = (long long)row * n2s;
+    for (int k = threadIdx.x; k < n2s; k += blockDim.x) f(i, j, k, base + k);
+  }
+}
+
+struct RowLaunch { dim3 grid, block; };
+inline RowLaunch row_launch(int num_sms, int n0, int n1, int n2s) {
+  int bx = ((n2s < 256 ? n2s : 256) + 31) / 32 * 32;
+  int by = 256 / bx; if (by < 1) by = 1;
+  const long long rows = (long long)n0 * n1;
+  long long gx = (rows + by - 1) / by;
+  const long long cap = (long long)num_sms * 32;
+  if (gx > cap) gx = cap;
+  RowLaunch r; r.grid = dim3((unsigned)gx, 1, 1); r.block = dim3(bx, by, 1);
+  return r;
+}
 
 #endif  // TRVB_COMMON_CUH_

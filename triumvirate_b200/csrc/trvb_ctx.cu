@@ -2,10 +2,13 @@
 #include "trvb_common.cuh"
 
 #include <cstring>
+#include <mutex>
+#include <unordered_map>
 
 static thread_local std::string g_err;
 long long g_trvb_launches = 0;
 long long g_trvb_fft_execs = 0;
+static long long g_arena_mallocs = 0;
 
 void trvb_set_error(const char* fmt, ...) {
   char buf[2048];
@@ -26,11 +29,105 @@ extern "C" int trvb_device_count(void) {
 extern "C" long long trvb_launch_count(void) { return g_trvb_launches; }
 extern "C" void trvb_launch_count_reset(void) { g_trvb_launches = 0; g_trvb_fft_execs = 0; }
 extern "C" long long trvb_fft_exec_count(void) { return g_trvb_fft_execs; }
+extern "C" long long trvb_arena_malloc_count(void) { return g_arena_mallocs; }
+
+// ---------------------------------------------------------------------
+// Caching arena.
+// ---------------------------------------------------------------------
+namespace {
+
+struct ArenaBlock { void* p; size_t bytes; cudaStream_t stream; };
+struct Arena {
+  std::mutex mu;
+  std::multimap<size_t, ArenaBlock> free_blocks;          // by size
+  std::unordered_map<void*, size_t> live;                 // handed out
+  size_t cached = 0;
+};
+Arena g_arena[64];
+const cudaStream_t kRetired = (cudaStream_t)(-1);   // owner stream drained and destroyed
+
+size_t arena_round(size_t bytes) {
+  const size_t q = bytes < (1u << 20) ? 512 : (size_t)(2u << 20);
+  return ((bytes ? bytes : 8) + q - 1) / q * q;
+}
+
+}  // namespace
+
+cudaError_t trvb_arena_alloc(int device, cudaStream_t stream, void** p, size_t bytes) {
+  Arena& a = g_arena[device & 63];
+  const size_t want = arena_round(bytes);
+  {
+    std::lock_guard<std::mutex> lock(a.mu);
+    // Exact size classes only: the estimator asks for a handful of distinct
+    // sizes, and a near fit would take the block the next request needs.
+    auto it = a.free_blocks.find(want);
+    if (it != a.free_blocks.end()) {
+      ArenaBlock b = it->second;
+      a.free_blocks.erase(it);
+      a.cached -= b.bytes;
+      if (b.stream != stream && b.stream != kRetired) {
+        cudaError_t e = cudaStreamSynchronize(b.stream);
+        if (e != cudaSuccess) return e;
+      }
+      a.live[b.p] = b.bytes;
+      *p = b.p;
+      return cudaSuccess;
+    }
+  }
+  g_arena_mallocs++;
+  cudaError_t e = cudaMalloc(p, want);
+  if (e == cudaErrorMemoryAllocation) {
+    cudaGetLastError();
+    trvb_arena_trim(device);      // give cached blocks back and retry once
+    e = cudaMalloc(p, want);
+  }
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(a.mu);
+  a.live[*p] = want;
+  return cudaSuccess;
+}
+
+cudaError_t trvb_arena_free(int device, cudaStream_t stream, void* p) {
+  if (!p) return cudaSuccess;
+  Arena& a = g_arena[device & 63];
+  std::lock_guard<std::mutex> lock(a.mu);
+  auto it = a.live.find(p);
+  if (it == a.live.end()) return cudaErrorInvalidValue;
+  ArenaBlock b{p, it->second, stream};
+  a.live.erase(it);
+  a.free_blocks.emplace(b.bytes, b);
+  a.cached += b.bytes;
+  return cudaSuccess;
+}
+
+void trvb_arena_retire_stream(int device, cudaStream_t stream) {
+  Arena& a = g_arena[device & 63];
+  std::lock_guard<std::mutex> lock(a.mu);
+  for (auto& kv : a.free_blocks) if (kv.second.stream == stream) kv.second.stream = kRetired;
+}
+
+size_t trvb_arena_cached_bytes(int device) {
+  Arena& a = g_arena[device & 63];
+  std::lock_guard<std::mutex> lock(a.mu);
+  return a.cached;
+}
+
+void trvb_arena_trim(int device) {
+  Arena& a = g_arena[device & 63];
+  std::multimap<size_t, ArenaBlock> blocks;
+  {
+    std::lock_guard<std::mutex> lock(a.mu);
+    blocks.swap(a.free_blocks);
+    a.cached = 0;
+  }
+  if (blocks.empty()) return;
+  cudaDeviceSynchronize();
+  for (auto& kv : blocks) cudaFree(kv.second.p);
+}
 
 int trvb_scratch(trvb_ctx* ctx, size_t bytes, double** out) {
   if (ctx->scratch_bytes < bytes) {
     if (ctx->d_scratch) {
-      TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
       TRVB_CUDA(trvb_dev_free_raw(ctx, ctx->d_scratch));
       ctx->d_scratch = nullptr; ctx->scratch_bytes = 0;
     }
@@ -51,7 +148,7 @@ int trvb_scratch(trvb_ctx* ctx, size_t bytes, double** out) {
 static int build_tables(trvb_ctx* ctx) {
   for (int ax = 0; ax < 3; ax++) {
     const int n = ctx->g.n[ax];
-    std::vector<double> sinc(n), alias(n);
+    std::vector<double> sinc(n), alias(n), ralias(n);
     for (int i = 0; i < n; i++) {
       int m = signed_index(i, n);
       double u = M_PI * m / double(n);
@@ -65,12 +162,16 @@ static int build_tables(trvb_ctx* ctx) {
         case 4: a = (1. - 4./3. * s2 + 2./5. * s2 * s2 - 4./315. * s2 * s2 * s2); break;
       }
       alias[i] = a;
+      ralias[i] = 1. / a;
     }
     TRVB_CUDA(cudaMalloc(&ctx->d_sinc[ax], sizeof(double) * n));
     TRVB_CUDA(cudaMalloc(&ctx->d_alias[ax], sizeof(double) * n));
     TRVB_CUDA(cudaMemcpyAsync(ctx->d_sinc[ax], sinc.data(), sizeof(double) * n,
                               cudaMemcpyHostToDevice, ctx->stream));
     TRVB_CUDA(cudaMemcpyAsync(ctx->d_alias[ax], alias.data(), sizeof(double) * n,
+                              cudaMemcpyHostToDevice, ctx->stream));
+    TRVB_CUDA(cudaMalloc(&ctx->d_ralias[ax], sizeof(double) * n));
+    TRVB_CUDA(cudaMemcpyAsync(ctx->d_ralias[ax], ralias.data(), sizeof(double) * n,
                               cudaMemcpyHostToDevice, ctx->stream));
   }
   TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -113,14 +214,6 @@ extern "C" int trvb_ctx_create(trvb_ctx** out, int device, const int ngrid[3],
   ctx->device = device;
   fill_grid(ctx->g, ngrid, boxsize, assignment_order);
   TRVB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-  {
-    // Keep freed blocks cached in the stream-ordered pool: meshes of a few GB
-    // are allocated and released many times per estimator call.
-    cudaMemPool_t pool;
-    TRVB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-    unsigned long long threshold = ~0ULL;
-    TRVB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
-  }
   cudaDeviceProp prop;
   TRVB_CUDA(cudaGetDeviceProperties(&prop, device));
   ctx->num_sms = prop.multiProcessorCount;
@@ -140,6 +233,9 @@ extern "C" int trvb_subgrid_create(trvb_ctx* parent, trvb_ctx** out,
                  "trvb_subgrid_create: nsub[%d]=%d outside (0, %d]", i, nsub[i],
                  parent->g.n[i]);
   }
+  const std::vector<int> key(nsub, nsub + 3);
+  auto hit = parent->subgrids.find(key);
+  if (hit != parent->subgrids.end()) { *out = hit->second; return 0; }
   TRVB_CUDA(cudaSetDevice(parent->device));
   trvb_ctx* ctx = new trvb_ctx();
   ctx->device = parent->device;
@@ -147,27 +243,42 @@ extern "C" int trvb_subgrid_create(trvb_ctx* parent, trvb_ctx** out,
   fill_grid(ctx->g, nsub, parent->g.L, parent->g.order);
   ctx->stream = parent->stream;   // shares the parent's stream
   ctx->num_sms = parent->num_sms;
+  parent->subgrids[key] = ctx;
   *out = ctx;
   return 0;
 }
 
+static void destroy_ctx_now(trvb_ctx* ctx);
+
 extern "C" void trvb_ctx_destroy(trvb_ctx* ctx) {
   if (!ctx) return;
+  if (ctx->parent) return;   // sub-grid contexts live and die with their parent
+  for (auto& kv : ctx->subgrids) destroy_ctx_now(kv.second);
+  ctx->subgrids.clear();
+  destroy_ctx_now(ctx);
+}
+
+static void destroy_ctx_now(trvb_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->has_z2z) cufftDestroy(ctx->plan_z2z);
   if (ctx->has_d2z) cufftDestroy(ctx->plan_d2z);
   if (ctx->has_z2d) cufftDestroy(ctx->plan_z2d);
+  for (auto& kv : ctx->batch_plans) cufftDestroy(kv.second);
   for (int ax = 0; ax < 3; ax++) {
     if (ctx->d_sinc[ax]) cudaFree(ctx->d_sinc[ax]);
     if (ctx->d_alias[ax]) cudaFree(ctx->d_alias[ax]);
+    if (ctx->d_ralias[ax]) cudaFree(ctx->d_ralias[ax]);
   }
   for (auto& kv : ctx->sjl) {
     if (kv.second.d_y) cudaFree(kv.second.d_y);
     if (kv.second.d_c) cudaFree(kv.second.d_c);
   }
-  if (ctx->d_scratch) cudaFree(ctx->d_scratch);
-  if (!ctx->parent && ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->d_scratch) trvb_arena_free(ctx->device, ctx->stream, ctx->d_scratch);
+  if (!ctx->parent && ctx->stream) {
+    trvb_arena_retire_stream(ctx->device, ctx->stream);
+    cudaStreamDestroy(ctx->stream);
+  }
   delete ctx;
 }
 
@@ -198,13 +309,8 @@ extern "C" size_t trvb_mesh_bytes(const trvb_ctx* ctx, int layout) {
 extern "C" int trvb_mem_info(trvb_ctx* ctx, size_t* free_bytes, size_t* total_bytes) {
   TRVB_CUDA(cudaSetDevice(ctx->device));
   TRVB_CUDA(cudaMemGetInfo(free_bytes, total_bytes));
-  // Blocks cached (reserved but unused) by the pool are available to us.
-  cudaMemPool_t pool;
-  TRVB_CUDA(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
-  unsigned long long reserved = 0, used = 0;
-  TRVB_CUDA(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved));
-  TRVB_CUDA(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used));
-  if (reserved > used) *free_bytes += (size_t)(reserved - used);
+  // Blocks cached by the arena are available to this library.
+  *free_bytes += trvb_arena_cached_bytes(ctx->device);
   return 0;
 }
 
@@ -249,6 +355,9 @@ extern "C" int trvb_sjl_table(trvb_ctx* ctx, int ell, const double* y,
                "trvb_sjl_table: bad argument");
   trvb_ctx* root = ctx->parent ? ctx->parent : ctx;
   SjlTable& t = root->sjl[ell];
+  if (t.d_y && t.nsample == nsample && t.step == step
+      && std::memcmp(t.h_y.data(), y, sizeof(double) * nsample) == 0
+      && std::memcmp(t.h_c.data(), c, sizeof(double) * nsample) == 0) return 0;
   if (t.d_y) { TRVB_CUDA(cudaStreamSynchronize(root->stream)); cudaFree(t.d_y); cudaFree(t.d_c); }
   TRVB_CUDA(cudaMalloc(&t.d_y, sizeof(double) * nsample));
   TRVB_CUDA(cudaMalloc(&t.d_c, sizeof(double) * nsample));
@@ -258,5 +367,6 @@ extern "C" int trvb_sjl_table(trvb_ctx* ctx, int ell, const double* y,
                             cudaMemcpyHostToDevice, root->stream));
   TRVB_CUDA(cudaStreamSynchronize(root->stream));
   t.nsample = nsample; t.step = step;
+  t.h_y.assign(y, y + nsample); t.h_c.assign(c, c + nsample);
   return 0;
 }

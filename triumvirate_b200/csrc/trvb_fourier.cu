@@ -8,6 +8,8 @@
 // 1792-1906 (band-limited y_lm-weighted IFFT), 1908-2010 (j_l-weighted IFFT).
 #include "trvb_common.cuh"
 
+#include <algorithm>
+
 namespace {
 
 __global__ void k_scale(double* __restrict__ p, long long n, double s) {
@@ -35,15 +37,10 @@ __host__ __device__ inline int kdim2(const GridDesc& g, int layout) {
 
 // f = (f + e^{+i pi (mx+my+mz)} f_s) / 2 with m = i/n or i/n - 1
 // (S/field.cpp:1618-1653).
-__global__ void k_interlace(double2* __restrict__ f, const double2* __restrict__ fs,
-                            GridDesc g, int layout) {
-  const int n2s = kdim2(g, layout);
-  const long long total = (long long)g.n[0] * g.n[1] * n2s;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
-       t += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(t % n2s);
-    const int j = (int)((t / n2s) % g.n[1]);
-    const int i = (int)(t / ((long long)n2s * g.n[1]));
+__global__ void __launch_bounds__(256)
+k_interlace(double2* __restrict__ f, const double2* __restrict__ fs,
+            GridDesc g, int layout) {
+  for_each_cell(g.n[0], g.n[1], kdim2(g, layout), [&](int i, int j, int k, long long t) {
     double m0 = (i < g.n[0] / 2) ? double(i) / g.n[0] : double(i) / g.n[0] - 1;
     double m1 = (j < g.n[1] / 2) ? double(j) / g.n[1] : double(j) / g.n[1] - 1;
     double m2 = (k < g.n[2] / 2) ? double(k) / g.n[2] : double(k) / g.n[2] - 1;
@@ -55,7 +52,7 @@ __global__ void k_interlace(double2* __restrict__ f, const double2* __restrict__
     a.y += sn * b.x + cs * b.y;
     a.x /= 2.; a.y /= 2.;
     f[t] = a;
-  }
+  });
 }
 
 struct Tables {
@@ -71,50 +68,48 @@ __device__ __forceinline__ double window_at(const Tables& t, int order, int i, i
   return w;
 }
 
-__global__ void k_compensate(double2* __restrict__ f, GridDesc g, int layout, Tables tb) {
-  const int n2s = kdim2(g, layout);
-  const long long total = (long long)g.n[0] * g.n[1] * n2s;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
-       t += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(t % n2s);
-    const int j = (int)((t / n2s) % g.n[1]);
-    const int i = (int)(t / ((long long)n2s * g.n[1]));
+__global__ void __launch_bounds__(256)
+k_compensate(double2* __restrict__ f, GridDesc g, int layout, Tables tb) {
+  for_each_cell(g.n[0], g.n[1], kdim2(g, layout), [&](int i, int j, int k, long long t) {
     const double w = window_at(tb, g.order, i, j, k);
     double2 a = f[t];
     a.x /= w; a.y /= w;
     f[t] = a;
-  }
+  });
 }
 
-// Shell-filtered, y_lm-weighted, window-compensated spectrum on the sub grid
-// (S/field.cpp:1815-1847).  One thread per sub-grid Fourier cell.
-//   gs = sub grid, gp = parent grid (tables and `src` live on the parent).
+// One Fourier mode of the filtered spectrum (S/field.cpp:1815-1847):
+// y_lm(khat) src(k) / W(k) * amp for the signed mode (mi, mj, mk).
+__device__ __forceinline__ double2 shell_mode(const KView& src, const GridDesc& gp,
+                                              const Tables& tb, int ell, int m,
+                                              int mi, int mj, int mk, double kx, double ky,
+                                              double kz, double amp) {
+  const int ip = mi >= 0 ? mi : mi + gp.n[0];
+  const int jp = mj >= 0 ? mj : mj + gp.n[1];
+  const int kp = mk >= 0 ? mk : mk + gp.n[2];
+  cplx fk = kload(src, ip, jp, kp);
+  const double rw = 1. / window_at(tb, gp.order, ip, jp, kp);
+  fk.re *= rw; fk.im *= rw;
+  const cplx y = ylm_reduced(ell, m, kx, ky, kz);
+  const cplx v = cmul(y, fk);
+  return make_double2(v.re * amp, v.im * amp);
+}
+
+// Dense form: every cell of the destination (sub-)grid spectrum is written.
+//   gs = sub grid, gp = parent grid (tables and `src` live on the parent);
+//   n2s = stored extent of dst's last axis: gs.n[2] (COMPLEX) or gs.nh (HALF).
 __global__ void __launch_bounds__(256)
 k_shell_spectrum(KView src, GridDesc gp, GridDesc gs, Tables tb, int ell, int m,
-                 double klo, double khi, int use_shell, double amp,
+                 double klo, double khi, int use_shell, double amp, int n2s,
                  double2* __restrict__ dst) {
   const bool same = gs.n[0] == gp.n[0] && gs.n[1] == gp.n[1] && gs.n[2] == gp.n[2];
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < gs.nmesh;
-       t += (long long)gridDim.x * blockDim.x) {
-    const int ks = (int)(t % gs.n[2]);
-    const int js = (int)((t / gs.n[2]) % gs.n[1]);
-    const int is = (int)(t / ((long long)gs.n[2] * gs.n[1]));
-    int mi, mj, mk, ip, jp, kp;
-    bool rep = true;
-    if (same) {
-      ip = is; jp = js; kp = ks;
-      mi = signed_index(ip, gp.n[0]); mj = signed_index(jp, gp.n[1]);
-      mk = signed_index(kp, gp.n[2]);
-    } else {
-      mi = signed_index(is, gs.n[0]); mj = signed_index(js, gs.n[1]);
-      mk = signed_index(ks, gs.n[2]);
-      // Only modes strictly inside the sub-grid Nyquist are representable
-      // on both grids without ambiguity.
-      rep = (2 * abs(mi) < gs.n[0]) && (2 * abs(mj) < gs.n[1]) && (2 * abs(mk) < gs.n[2]);
-      ip = mi >= 0 ? mi : mi + gp.n[0];
-      jp = mj >= 0 ? mj : mj + gp.n[1];
-      kp = mk >= 0 ? mk : mk + gp.n[2];
-    }
+  for_each_cell(gs.n[0], gs.n[1], n2s, [&](int is, int js, int ks, long long t) {
+    const int mi = signed_index(is, gs.n[0]), mj = signed_index(js, gs.n[1]);
+    const int mk = signed_index(ks, gs.n[2]);
+    // On a coarser grid only modes strictly inside its Nyquist frequency are
+    // representable on both grids without ambiguity.
+    const bool rep = same
+      || ((2 * abs(mi) < gs.n[0]) && (2 * abs(mj) < gs.n[1]) && (2 * abs(mk) < gs.n[2]));
     double2 out = make_double2(0., 0.);
     if (rep) {
       // kv = i * dk (S/field.cpp:555-562), |k| without contraction.
@@ -123,39 +118,92 @@ k_shell_spectrum(KView src, GridDesc gp, GridDesc gs, Tables tb, int ell, int m,
       const double kz = __dmul_rn((double)mk, gp.dk[2]);
       const double kmag = vec3_norm_exact(kx, ky, kz);
       if (!use_shell || (klo <= kmag && kmag < khi)) {
-        cplx fk = kload(src, ip, jp, kp);
-        const double w = window_at(tb, gp.order, ip, jp, kp);
-        fk.re /= w; fk.im /= w;
-        cplx y = ylm_reduced(ell, m, kx, ky, kz);
-        cplx v = cmul(y, fk);
-        out.x = v.re * amp; out.y = v.im * amp;
+        out = shell_mode(src, gp, tb, ell, m, mi, mj, mk, kx, ky, kz, amp);
       }
     }
     dst[t] = out;
-  }
+  });
+}
+
+// Sparse batched form: the destination slab (nbins consecutive spectra on the
+// sub grid) has been zero-filled; only the modes of the low-|k| cube are
+// visited and each is written into the spectrum of every bin that holds it.
+struct ShellBatch {
+  const double* klo; const double* khi; const double* amp;   // device, [nbins]
+  int nbins;
+};
+
+__global__ void __launch_bounds__(256)
+k_shell_scatter(KView src, GridDesc gp, GridDesc gs, Tables tb, int ell, int m,
+                int lo0, int lo1, int lo2, int c0, int c1, int c2,
+                ShellBatch sb, int n2s, long long bin_stride, double2* __restrict__ dst) {
+  for_each_cell(c0, c1, c2, [&](int a, int b, int c, long long) {
+    const int mi = lo0 + a, mj = lo1 + b, mk = lo2 + c;
+    // HALF destination: mk >= 0 stored, plus the Nyquist plane (signed -n/2).
+    if (n2s != gs.n[2] && mk < 0 && 2 * (-mk) != gs.n[2]) return;
+    const double kx = __dmul_rn((double)mi, gp.dk[0]);
+    const double ky = __dmul_rn((double)mj, gp.dk[1]);
+    const double kz = __dmul_rn((double)mk, gp.dk[2]);
+    const double kmag = vec3_norm_exact(kx, ky, kz);
+    bool loaded = false;
+    double2 base = make_double2(0., 0.);
+    for (int q = 0; q < sb.nbins; q++) {
+      if (!(sb.klo[q] <= kmag && kmag < sb.khi[q])) continue;
+      if (!loaded) {
+        base = shell_mode(src, gp, tb, ell, m, mi, mj, mk, kx, ky, kz, 1.);
+        loaded = true;
+      }
+      const int is = mi >= 0 ? mi : mi + gs.n[0];
+      const int js = mj >= 0 ? mj : mj + gs.n[1];
+      const int ks = mk >= 0 ? mk : mk + gs.n[2];
+      const double amp = sb.amp[q];
+      dst[q * bin_stride + ((long long)is * gs.n[1] + js) * n2s + ks] =
+        make_double2(base.x * amp, base.y * amp);
+    }
+  });
 }
 
 // j_l(|k| r) y_lm(khat) src(k)/W(k) * amp on the full grid (S/field.cpp:1936-1961).
 __global__ void __launch_bounds__(256)
 k_sjl_spectrum(KView src, GridDesc g, Tables tb, SjlView sj, int ell, int m,
                double r, double amp, double2* __restrict__ dst) {
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < g.nmesh;
-       t += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(t % g.n[2]);
-    const int j = (int)((t / g.n[2]) % g.n[1]);
-    const int i = (int)(t / ((long long)g.n[2] * g.n[1]));
+  for_each_cell(g.n[0], g.n[1], g.n[2], [&](int i, int j, int k, long long t) {
     const double kx = __dmul_rn((double)signed_index(i, g.n[0]), g.dk[0]);
     const double ky = __dmul_rn((double)signed_index(j, g.n[1]), g.dk[1]);
     const double kz = __dmul_rn((double)signed_index(k, g.n[2]), g.dk[2]);
     const double kmag = vec3_norm_exact(kx, ky, kz);
     cplx fk = kload(src, i, j, k);
-    const double w = window_at(tb, g.order, i, j, k);
-    fk.re /= w; fk.im /= w;
+    const double rw = 1. / window_at(tb, g.order, i, j, k);
+    fk.re *= rw; fk.im *= rw;
     cplx y = ylm_reduced(ell, m, kx, ky, kz);
     cplx v = cmul(y, fk);
     const double jl = sjl_eval(sj, __dmul_rn(kmag, r));
     dst[t] = make_double2(jl * v.re * amp, jl * v.im * amp);
+  });
+}
+
+// Batched plan over `batch` consecutive meshes of ctx's grid.
+int get_batch_plan(trvb_ctx* ctx, cufftType type, int batch, cufftHandle* out) {
+  auto key = std::make_pair((int)type, batch);
+  auto it = ctx->batch_plans.find(key);
+  if (it == ctx->batch_plans.end()) {
+    const GridDesc& g = ctx->g;
+    int dims[3] = {g.n[0], g.n[1], g.n[2]};
+    const long long nfull = g.nmesh, nhalf = (long long)g.n[0] * g.n[1] * g.nh;
+    TRVB_REQUIRE(nfull < 2147483647LL, "batched FFT: grid too large for a batched plan");
+    cufftHandle plan;
+    if (type == CUFFT_Z2Z) {
+      TRVB_CUFFT(cufftPlanMany(&plan, 3, dims, nullptr, 1, (int)nfull, nullptr, 1, (int)nfull,
+                               CUFFT_Z2Z, batch));
+    } else {   // Z2D, out of place: HALF spectra -> REAL meshes
+      TRVB_CUFFT(cufftPlanMany(&plan, 3, dims, nullptr, 1, (int)nhalf, nullptr, 1, (int)nfull,
+                               CUFFT_Z2D, batch));
+    }
+    TRVB_CUFFT(cufftSetStream(plan, ctx->stream));
+    it = ctx->batch_plans.emplace(key, plan).first;
   }
+  *out = it->second;
+  return 0;
 }
 
 int get_plan(trvb_ctx* ctx, cufftType type, cufftHandle* out) {
@@ -183,6 +231,7 @@ KView kview_of(const trvb_ctx* ctx, trvb_mesh m) {
   KView v;
   v.p = (const double2*)m.data; v.layout = m.layout;
   v.n0 = ctx->g.n[0]; v.n1 = ctx->g.n[1]; v.n2 = ctx->g.n[2]; v.nh = ctx->g.nh;
+  v.add0 = m.k0_add;
   return v;
 }
 
@@ -272,8 +321,8 @@ extern "C" int trvb_interlace_combine(trvb_ctx* ctx, trvb_mesh kmesh, trvb_mesh 
   TRVB_REQUIRE(ctx && kmesh.data && kmesh_s.data, "trvb_interlace_combine: null argument");
   TRVB_REQUIRE(kmesh.layout == kmesh_s.layout && kmesh.layout != TRVB_REAL,
                "trvb_interlace_combine: both meshes must share a Fourier layout");
-  const long long n = (long long)ctx->g.n[0] * ctx->g.n[1] * kdim2(ctx->g, kmesh.layout);
-  k_interlace<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(
+  const RowLaunch rl = row_launch(ctx->num_sms, ctx->g.n[0], ctx->g.n[1], kdim2(ctx->g, kmesh.layout));
+  k_interlace<<<rl.grid, rl.block, 0, ctx->stream>>>(
     (double2*)kmesh.data, (const double2*)kmesh_s.data, ctx->g, kmesh.layout);
   TRVB_LAUNCH_CHECK();
   return 0;
@@ -283,8 +332,8 @@ extern "C" int trvb_compensate(trvb_ctx* ctx, trvb_mesh kmesh) {
   TRVB_REQUIRE(ctx && kmesh.data && kmesh.layout != TRVB_REAL,
                "trvb_compensate: needs a Fourier-space mesh");
   TRVB_REQUIRE(ctx->parent == nullptr, "trvb_compensate: root context only");
-  const long long n = (long long)ctx->g.n[0] * ctx->g.n[1] * kdim2(ctx->g, kmesh.layout);
-  k_compensate<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(
+  const RowLaunch rl = row_launch(ctx->num_sms, ctx->g.n[0], ctx->g.n[1], kdim2(ctx->g, kmesh.layout));
+  k_compensate<<<rl.grid, rl.block, 0, ctx->stream>>>(
     (double2*)kmesh.data, ctx->g, kmesh.layout, tables_of(ctx));
   TRVB_LAUNCH_CHECK();
   return 0;
@@ -296,17 +345,99 @@ extern "C" int trvb_shell_ifft(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh src, int 
   TRVB_REQUIRE(ctx && sub && src.data && dst.data, "trvb_shell_ifft: null argument");
   TRVB_REQUIRE(ctx->parent == nullptr && (sub == ctx || sub->parent == ctx),
                "trvb_shell_ifft: `sub` must be `ctx` or a sub-grid of it");
-  TRVB_REQUIRE(src.layout != TRVB_REAL && dst.layout == TRVB_COMPLEX,
-               "trvb_shell_ifft: src must be a Fourier mesh, dst COMPLEX");
+  TRVB_REQUIRE(src.layout != TRVB_REAL, "trvb_shell_ifft: src must be a Fourier mesh");
+  // A REAL destination is allowed when the filtered spectrum is Hermitian:
+  // spectrum of a real field (HALF) times a real, even-parity y_l0.
+  const bool herm = src.layout == TRVB_HALF && m == 0 && (ell % 2) == 0;
+  TRVB_REQUIRE(dst.layout == TRVB_COMPLEX || (dst.layout == TRVB_REAL && herm),
+               "trvb_shell_ifft: dst must be COMPLEX (REAL only for a HALF source, m = 0, even l)");
   TRVB_REQUIRE(abs(m) <= ell && ell >= 0, "trvb_shell_ifft: bad (l, m) = (%d, %d)", ell, m);
-  TRVB_REQUIRE(dst.data != src.data || sub == ctx, "trvb_shell_ifft: aliasing across grids");
   TRVB_REQUIRE(dst.data != src.data, "trvb_shell_ifft: src and dst must differ");
   const int use_shell = !(klo < 0. && khi < 0.);
-  k_shell_spectrum<<<grid_for(sub, sub->g.nmesh, 256), 256, 0, ctx->stream>>>(
-    kview_of(ctx, src), ctx->g, sub->g, tables_of(ctx), ell, m, klo, khi, use_shell,
-    amp, (double2*)dst.data);
+  const GridDesc& gs = sub->g;
+  if (dst.layout == TRVB_REAL) {
+    trvb_mesh half; half.layout = TRVB_HALF; half.k0_add = 0.; half.data = nullptr;
+    TRVB_CUDA(trvb_dev_alloc_raw(ctx, &half.data, trvb_mesh_bytes(sub, TRVB_HALF)));
+    const RowLaunch rl = row_launch(ctx->num_sms, gs.n[0], gs.n[1], gs.nh);
+    k_shell_spectrum<<<rl.grid, rl.block, 0, ctx->stream>>>(
+      kview_of(ctx, src), ctx->g, gs, tables_of(ctx), ell, m, klo, khi, use_shell, amp,
+      gs.nh, (double2*)half.data);
+    TRVB_LAUNCH_CHECK();
+    int st = trvb_fft_inverse(sub, half, dst);
+    trvb_dev_free_raw(ctx, half.data);
+    return st;
+  }
+  const RowLaunch rl = row_launch(ctx->num_sms, gs.n[0], gs.n[1], gs.n[2]);
+  k_shell_spectrum<<<rl.grid, rl.block, 0, ctx->stream>>>(
+    kview_of(ctx, src), ctx->g, gs, tables_of(ctx), ell, m, klo, khi, use_shell, amp,
+    gs.n[2], (double2*)dst.data);
   TRVB_LAUNCH_CHECK();
   return trvb_fft_inverse(sub, dst, dst);
+}
+
+extern "C" int trvb_shell_ifft_batch(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh src, int ell,
+                                     int m, const double* klo, const double* khi,
+                                     const double* amp, int nbins, void* dst,
+                                     int dst_layout) {
+  TRVB_REQUIRE(ctx && sub && src.data && dst && klo && khi && amp && nbins > 0,
+               "trvb_shell_ifft_batch: bad argument");
+  TRVB_REQUIRE(ctx->parent == nullptr && (sub == ctx || sub->parent == ctx),
+               "trvb_shell_ifft_batch: `sub` must be `ctx` or a sub-grid of it");
+  TRVB_REQUIRE(src.layout != TRVB_REAL, "trvb_shell_ifft_batch: src must be a Fourier mesh");
+  const bool herm = src.layout == TRVB_HALF && m == 0 && (ell % 2) == 0;
+  TRVB_REQUIRE(dst_layout == TRVB_COMPLEX || (dst_layout == TRVB_REAL && herm),
+               "trvb_shell_ifft_batch: dst must be COMPLEX (REAL only for a HALF source, m = 0, even l)");
+  TRVB_REQUIRE(abs(m) <= ell && ell >= 0, "trvb_shell_ifft_batch: bad (l, m) = (%d, %d)", ell, m);
+  const GridDesc& gp = ctx->g;
+  const GridDesc& gs = sub->g;
+  const bool real_out = dst_layout == TRVB_REAL;
+  const int n2s = real_out ? gs.nh : gs.n[2];
+  const long long bin_stride = (long long)gs.n[0] * gs.n[1] * n2s;   // complex elements
+  const size_t spec_bytes = sizeof(double2) * (size_t)bin_stride * nbins;
+  void* spec = dst;
+  if (real_out) TRVB_CUDA(trvb_dev_alloc_raw(ctx, &spec, spec_bytes));
+  TRVB_CUDA(cudaMemsetAsync(spec, 0, spec_bytes, ctx->stream));
+  // Low-|k| cube that holds every shell; clipped to what the sub grid represents.
+  double kmax = 0.;
+  for (int q = 0; q < nbins; q++) kmax = std::max(kmax, khi[q]);
+  int lo[3], cnt[3];
+  for (int a = 0; a < 3; a++) {
+    long long mc = (long long)std::floor(kmax / gp.dk[a]) + 1;
+    const long long rep = (sub == ctx) ? (gs.n[a] - gs.n[a] / 2) : (gs.n[a] - 1) / 2;
+    int lo_a = (int)std::max<long long>(-mc, (sub == ctx) ? -(long long)(gs.n[a] - gs.n[a] / 2) : -rep);
+    int hi_a = (int)std::min<long long>(mc, (sub == ctx) ? (long long)(gs.n[a] / 2 - 1) : rep);
+    if (gs.n[a] == 1) { lo_a = 0; hi_a = 0; }
+    lo[a] = lo_a; cnt[a] = hi_a - lo_a + 1;
+  }
+  double* d_par = nullptr;
+  TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&d_par, sizeof(double) * 3 * (size_t)nbins));
+  std::vector<double> h_par(3 * (size_t)nbins);
+  for (int q = 0; q < nbins; q++) {
+    h_par[q] = klo[q]; h_par[nbins + q] = khi[q]; h_par[2 * nbins + q] = amp[q];
+  }
+  // Pageable source: the copy is staged before cudaMemcpyAsync returns.
+  TRVB_CUDA(cudaMemcpyAsync(d_par, h_par.data(), sizeof(double) * h_par.size(),
+                            cudaMemcpyHostToDevice, ctx->stream));
+  ShellBatch sb; sb.klo = d_par; sb.khi = d_par + nbins; sb.amp = d_par + 2 * nbins;
+  sb.nbins = nbins;
+  const RowLaunch rl = row_launch(ctx->num_sms, cnt[0], cnt[1], cnt[2]);
+  k_shell_scatter<<<rl.grid, rl.block, 0, ctx->stream>>>(
+    kview_of(ctx, src), gp, gs, tables_of(ctx), ell, m, lo[0], lo[1], lo[2], cnt[0], cnt[1],
+    cnt[2], sb, n2s, bin_stride, (double2*)spec);
+  TRVB_LAUNCH_CHECK();
+  trvb_dev_free_raw(ctx, d_par);
+  cufftHandle plan;
+  int st = get_batch_plan(sub, real_out ? CUFFT_Z2D : CUFFT_Z2Z, nbins, &plan);
+  if (st) { if (real_out) trvb_dev_free_raw(ctx, spec); return st; }
+  if (real_out) {
+    TRVB_CUFFT(cufftExecZ2D(plan, (cufftDoubleComplex*)spec, (cufftDoubleReal*)dst));
+    trvb_dev_free_raw(ctx, spec);
+  } else {
+    TRVB_CUFFT(cufftExecZ2Z(plan, (cufftDoubleComplex*)dst, (cufftDoubleComplex*)dst,
+                            CUFFT_INVERSE));
+  }
+  g_trvb_fft_execs++;
+  return 0;
 }
 
 extern "C" int trvb_sjl_ifft(trvb_ctx* ctx, trvb_mesh src, int ell, int m, double r,
@@ -321,7 +452,8 @@ extern "C" int trvb_sjl_ifft(trvb_ctx* ctx, trvb_mesh src, int ell, int m, doubl
   SjlView sj;
   sj.y = it->second.d_y; sj.c = it->second.d_c;
   sj.nsample = it->second.nsample; sj.step = it->second.step; sj.ell = ell;
-  k_sjl_spectrum<<<grid_for(ctx, ctx->g.nmesh, 256), 256, 0, ctx->stream>>>(
+  const RowLaunch rl = row_launch(ctx->num_sms, ctx->g.n[0], ctx->g.n[1], ctx->g.n[2]);
+  k_sjl_spectrum<<<rl.grid, rl.block, 0, ctx->stream>>>(
     kview_of(ctx, src), ctx->g, tables_of(ctx), sj, ell, m, r, amp, (double2*)dst.data);
   TRVB_LAUNCH_CHECK();
   return trvb_fft_inverse(ctx, dst, dst);

@@ -21,12 +21,15 @@ namespace {
 struct Tables {
   const double* sinc[3];
   const double* alias[3];
+  const double* ralias[3];   // 1 / alias
 };
 
 Tables tables_of(const trvb_ctx* ctx) {
   const trvb_ctx* root = ctx->parent ? ctx->parent : ctx;
   Tables t;
-  for (int a = 0; a < 3; a++) { t.sinc[a] = root->d_sinc[a]; t.alias[a] = root->d_alias[a]; }
+  for (int a = 0; a < 3; a++) {
+    t.sinc[a] = root->d_sinc[a]; t.alias[a] = root->d_alias[a]; t.ralias[a] = root->d_ralias[a];
+  }
   return t;
 }
 
@@ -34,6 +37,7 @@ KView kview_of(const trvb_ctx* ctx, trvb_mesh m) {
   KView v;
   v.p = (const double2*)m.data; v.layout = m.layout;
   v.n0 = ctx->g.n[0]; v.n1 = ctx->g.n[1]; v.n2 = ctx->g.n[2]; v.nh = ctx->g.nh;
+  v.add0 = m.k0_add;
   return v;
 }
 
@@ -46,18 +50,56 @@ __global__ void k_sum_cols(const double* __restrict__ partial, int nblocks, int 
   out[t] = s;
 }
 
+// partial is [bin][nblocks][width]; block `bin` sums its slab in fixed order.
+__global__ void k_sum_binned(const double* __restrict__ partial, int nblocks, int width,
+                             double* __restrict__ out) {
+  const int t = threadIdx.x;
+  if (t >= width) return;
+  const double* slab = partial + (size_t)blockIdx.x * nblocks * width;
+  double s = 0.;
+  for (int b = 0; b < nblocks; b++) s += slab[(size_t)b * width + t];
+  out[(size_t)blockIdx.x * width + t] = s;
+}
+
 // ---------------------------------------------------------------------
-// Tiled all-pairs ("Gram") reduction.
+// Tiled all-pairs ("Gram") reduction:  out[a][b] = sum_x A_a(x) * H_b(x),
+// H_b = B_b * G.  It is a skinny matrix product (K = cells, M = N = bins): a
+// tile of GRAM_T cells of every field is staged in shared memory and each
+// warp accumulates 4 x 4 blocks of (a, b) pairs in registers, so one shared
+// load feeds four multiply-adds.  Values are complex (double2) or, when all
+// operands are real meshes, plain doubles (VT).
 // ---------------------------------------------------------------------
 
 constexpr int GRAM_T = 64;        // cells per tile (two per lane)
 constexpr int GRAM_WARPS = 8;
 constexpr int GRAM_THREADS = GRAM_WARPS * 32;
+constexpr int GRAM_B = 4;         // pair block edge
 
+__device__ __forceinline__ void vt_zero(double& v) { v = 0.; }
+__device__ __forceinline__ void vt_zero(double2& v) { v.x = 0.; v.y = 0.; }
+__device__ __forceinline__ void vt_fma(double& acc, double a, double b) { acc += a * b; }
+__device__ __forceinline__ void vt_fma(double2& acc, double2 a, double2 b) {
+  acc.x += a.x * b.x - a.y * b.y;
+  acc.y += a.x * b.y + a.y * b.x;
+}
+__device__ __forceinline__ double vt_shfl_down(double v, int o) {
+  return __shfl_down_sync(0xffffffffu, v, o);
+}
+__device__ __forceinline__ double2 vt_shfl_down(double2 v, int o) {
+  return make_double2(__shfl_down_sync(0xffffffffu, v.x, o), __shfl_down_sync(0xffffffffu, v.y, o));
+}
+__device__ __forceinline__ void vt_add(double& a, double b) { a += b; }
+__device__ __forceinline__ void vt_add(double2& a, double2 b) { a.x += b.x; a.y += b.y; }
+__device__ __forceinline__ void vt_store(double* p, double v) { p[0] = v; p[1] = 0.; }
+__device__ __forceinline__ void vt_store(double* p, double2 v) { p[0] = v.x; p[1] = v.y; }
+
+// Complex meshes A_a, B_b, G.
 struct FieldLoader {
+  typedef double2 VT;
   const double2* const* A;
   const double2* const* B;
   const double2* G;
+  bool aligned16;   // every mesh 16-byte aligned: TMA bulk copies are usable
   __device__ __forceinline__ double2 a(int ia, long long cell) const { return A[ia][cell]; }
   __device__ __forceinline__ double2 hb(int ib, long long cell) const {
     double2 b = B[ib][cell], g = G[cell];
@@ -65,8 +107,20 @@ struct FieldLoader {
   }
 };
 
+// Real meshes A_a, B_b, G (B_000-like statistics of a periodic box).
+struct RealFieldLoader {
+  typedef double VT;
+  const double* const* A;
+  const double* const* B;
+  const double* G;
+  bool aligned16;
+  __device__ __forceinline__ double a(int ia, long long cell) const { return A[ia][cell]; }
+  __device__ __forceinline__ double hb(int ib, long long cell) const { return B[ib][cell] * G[cell]; }
+};
+
 struct ShotLoader {
-  const double2* xi;
+  typedef double2 VT;
+  XView xi;
   GridDesc g;
   SjlView sja, sjb;
   const double* ka; const double* kb;
@@ -92,7 +146,7 @@ struct ShotLoader {
     cplx ya = ylm_reduced(la, ma, rx, ry, rz);
     cplx yb = ylm_reduced(lb, mb, rx, ry, rz);
     cplx yy = cmul(ya, yb);
-    double2 x = xi[cell];
+    double2 x = xload(xi, cell);
     cplx xv; xv.re = x.x; xv.im = x.y;
     cplx v = cmul(xv, yy);
     return make_double2(jb * v.re, jb * v.im);
@@ -103,31 +157,50 @@ struct ShotLoader {
 // integer q = i^2 + j^2 + k^2 of the signed cell offset, so the N^3 cells
 // collapse to <= 3 (n/2)^2 + 1 radii before any j_l is evaluated:
 //   hist[q] = sum_{x : q(x) = q} y_a(xhat) y_b(xhat) xi(x).
+// The eight cells (+-i, +-j, +-k) share q: they are loaded together (eight
+// independent loads in flight per thread), summed in registers and sent as
+// ONE RED.  TRIVIAL: y_a y_b = 1 (l_a = l_b = 0).
+template <bool TRIVIAL>
 __global__ void __launch_bounds__(256)
-k_shot_radial_hist(const double2* __restrict__ xi, GridDesc g, int la, int ma, int lb,
+k_shot_radial_hist(XView xi, GridDesc g, int la, int ma, int lb,
                    int mb, double* __restrict__ hist) {
-  const bool trivial = (la == 0 && lb == 0);
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < g.nmesh;
-       t += (long long)gridDim.x * blockDim.x) {
-    const int k = signed_index((int)(t % g.n[2]), g.n[2]);
-    const int j = signed_index((int)((t / g.n[2]) % g.n[1]), g.n[1]);
-    const int i = signed_index((int)(t / ((long long)g.n[2] * g.n[1])), g.n[0]);
-    const long long q = (long long)i * i + (long long)j * j + (long long)k * k;
-    const double2 x = xi[t];
-    double re = x.x, im = x.y;
-    if (!trivial) {
-      const double rx = (double)i * g.dr[0], ry = (double)j * g.dr[1], rz = (double)k * g.dr[2];
-      const cplx yy = cmul(ylm_reduced(la, ma, rx, ry, rz), ylm_reduced(lb, mb, rx, ry, rz));
-      cplx xv; xv.re = re; xv.im = im;
-      const cplx v = cmul(xv, yy);
-      re = v.re; im = v.im;
+  const int n0 = g.n[0], n1 = g.n[1], n2 = g.n[2];
+  for_each_cell(n0 / 2 + 1, n1 / 2 + 1, n2 / 2 + 1, [&](int ci, int cj, int ck, long long) {
+    const int pi = ci ? n0 - ci : 0, pj = cj ? n1 - cj : 0, pk = ck ? n2 - ck : 0;
+    int ii[2] = {ci, pi}, jj[2] = {cj, pj}, kk[2] = {ck, pk};
+    double2 x[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+      const int a = e >> 2, b = (e >> 1) & 1, c = e & 1;
+      // A mirrored index equal to the original one is the same cell: skip it.
+      const bool dup = (a && pi == ci) || (b && pj == cj) || (c && pk == ck);
+      x[e] = make_double2(0., 0.);
+      if (!dup) x[e] = xload(xi, ((long long)ii[a] * n1 + jj[b]) * n2 + kk[c]);
     }
+    double re = 0., im = 0.;
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+      if (TRIVIAL) { re += x[e].x; im += x[e].y; continue; }
+      const int a = e >> 2, b = (e >> 1) & 1, c = e & 1;
+      const bool dup = (a && pi == ci) || (b && pj == cj) || (c && pk == ck);
+      if (dup) continue;
+      const double rx = (double)signed_index(ii[a], n0) * g.dr[0];
+      const double ry = (double)signed_index(jj[b], n1) * g.dr[1];
+      const double rz = (double)signed_index(kk[c], n2) * g.dr[2];
+      const cplx yy = cmul(ylm_reduced(la, ma, rx, ry, rz), ylm_reduced(lb, mb, rx, ry, rz));
+      cplx xv; xv.re = x[e].x; xv.im = x[e].y;
+      const cplx v = cmul(xv, yy);
+      re += v.re; im += v.im;
+    }
+    const int si = signed_index(ci, n0), sj = signed_index(cj, n1), sk = signed_index(ck, n2);
+    const long long q = (long long)si * si + (long long)sj * sj + (long long)sk * sk;
     atomicAdd(&hist[2 * q], re);
-    atomicAdd(&hist[2 * q + 1], im);
-  }
+    if (xi.cplx || !TRIVIAL) atomicAdd(&hist[2 * q + 1], im);
+  });
 }
 
 struct RadialLoader {
+  typedef double2 VT;
   const double2* hist;
   double dr;
   SjlView sja, sjb;
@@ -147,24 +220,30 @@ struct RadialLoader {
   }
 };
 
-// Each warp owns up to PPW pairs; each lane owns two cells of the tile and
-// keeps PPW complex accumulators in registers.
-template <class Loader, int PPW>
+// Pair blocks: block t covers a in [4 ta[t], +4) x b in [4 tb[t], +4) of the
+// (padded) staged field lists.  Each warp owns up to TPW blocks.
+//   sel_a / sel_b  staged field -> loader index (padded to multiples of 4)
+//   partial        [gridDim.x][nblk][16] values (re, im)
+template <class Loader, int TPW>
 __global__ void __launch_bounds__(GRAM_THREADS, 1)
-k_gram(Loader ld, int na, int nb, long long ncells, const int* __restrict__ pair_ia,
-       const int* __restrict__ pair_ib, int npairs, double* __restrict__ partial) {
-  extern __shared__ double2 smem[];
-  double2* sA = smem;                         // [na][GRAM_T]
-  double2* sB = smem + (size_t)na * GRAM_T;   // [nb][GRAM_T]
-  __shared__ short s_ia[GRAM_WARPS * PPW], s_ib[GRAM_WARPS * PPW];
-  for (int p = threadIdx.x; p < GRAM_WARPS * PPW; p += GRAM_THREADS) {
-    s_ia[p] = (p < npairs) ? (short)pair_ia[p] : (short)0;
-    s_ib[p] = (p < npairs) ? (short)pair_ib[p] : (short)0;
-  }
+k_gram(Loader ld, const int* __restrict__ sel_a, int na, const int* __restrict__ sel_b, int nb,
+       long long ncells, const int* __restrict__ blk_a, const int* __restrict__ blk_b, int nblk,
+       double* __restrict__ partial) {
+  typedef typename Loader::VT VT;
+  extern __shared__ double2 smem_raw[];
+  VT* sA = reinterpret_cast<VT*>(smem_raw);   // [na][GRAM_T]
+  VT* sB = sA + (size_t)na * GRAM_T;          // [nb][GRAM_T]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double acc_re[PPW], acc_im[PPW];
+  VT acc[TPW][GRAM_B * GRAM_B];
+  int a0[TPW], b0[TPW];
 #pragma unroll
-  for (int q = 0; q < PPW; q++) { acc_re[q] = 0.; acc_im[q] = 0.; }
+  for (int q = 0; q < TPW; q++) {
+    const int t = warp + q * GRAM_WARPS;
+    a0[q] = (t < nblk) ? blk_a[t] * GRAM_B : 0;
+    b0[q] = (t < nblk) ? blk_b[t] * GRAM_B : 0;
+#pragma unroll
+    for (int e = 0; e < GRAM_B * GRAM_B; e++) vt_zero(acc[q][e]);
+  }
 
   const long long ntiles = (ncells + GRAM_T - 1) / GRAM_T;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -173,97 +252,441 @@ k_gram(Loader ld, int na, int nb, long long ncells, const int* __restrict__ pair
     for (int idx = threadIdx.x; idx < na * GRAM_T; idx += GRAM_THREADS) {
       const int a = idx / GRAM_T, x = idx % GRAM_T;
       const long long cell = base + x;
-      sA[idx] = (cell < ncells) ? ld.a(a, cell) : make_double2(0., 0.);
+      VT v; vt_zero(v);
+      if (cell < ncells) v = ld.a(sel_a[a], cell);
+      sA[idx] = v;
     }
     for (int idx = threadIdx.x; idx < nb * GRAM_T; idx += GRAM_THREADS) {
       const int b = idx / GRAM_T, x = idx % GRAM_T;
       const long long cell = base + x;
-      sB[idx] = (cell < ncells) ? ld.hb(b, cell) : make_double2(0., 0.);
+      VT v; vt_zero(v);
+      if (cell < ncells) v = ld.hb(sel_b[b], cell);
+      sB[idx] = v;
     }
     __syncthreads();
 #pragma unroll
-    for (int q = 0; q < PPW; q++) {
-      const int p = warp + q * GRAM_WARPS;
-      if (p < npairs) {
-        const double2* ra = sA + (int)s_ia[p] * GRAM_T;
-        const double2* rb = sB + (int)s_ib[p] * GRAM_T;
-        const double2 a0 = ra[lane], b0 = rb[lane];
-        const double2 a1 = ra[lane + 32], b1 = rb[lane + 32];
-        acc_re[q] += a0.x * b0.x - a0.y * b0.y;
-        acc_im[q] += a0.x * b0.y + a0.y * b0.x;
-        acc_re[q] += a1.x * b1.x - a1.y * b1.y;
-        acc_im[q] += a1.x * b1.y + a1.y * b1.x;
+    for (int q = 0; q < TPW; q++) {
+      if (warp + q * GRAM_WARPS < nblk) {
+        const VT* ra = sA + a0[q] * GRAM_T;
+        const VT* rb = sB + b0[q] * GRAM_T;
+#pragma unroll
+        for (int h = 0; h < GRAM_T / 32; h++) {
+          const int x = lane + 32 * h;
+          VT va[GRAM_B], vb[GRAM_B];
+#pragma unroll
+          for (int e = 0; e < GRAM_B; e++) { va[e] = ra[e * GRAM_T + x]; vb[e] = rb[e * GRAM_T + x]; }
+#pragma unroll
+          for (int ea = 0; ea < GRAM_B; ea++)
+#pragma unroll
+            for (int eb = 0; eb < GRAM_B; eb++) vt_fma(acc[q][ea * GRAM_B + eb], va[ea], vb[eb]);
+        }
       }
     }
   }
 #pragma unroll
-  for (int q = 0; q < PPW; q++) {
-    double re = acc_re[q], im = acc_im[q];
-    for (int o = 16; o > 0; o >>= 1) {
-      re += __shfl_down_sync(0xffffffffu, re, o);
-      im += __shfl_down_sync(0xffffffffu, im, o);
-    }
-    const int p = warp + q * GRAM_WARPS;
-    if (lane == 0 && p < npairs) {
-      partial[((long long)blockIdx.x * npairs + p) * 2] = re;
-      partial[((long long)blockIdx.x * npairs + p) * 2 + 1] = im;
+  for (int q = 0; q < TPW; q++) {
+    const int t = warp + q * GRAM_WARPS;
+#pragma unroll
+    for (int e = 0; e < GRAM_B * GRAM_B; e++) {
+      VT v = acc[q][e];
+      for (int o = 16; o > 0; o >>= 1) vt_add(v, vt_shfl_down(v, o));
+      if (lane == 0 && t < nblk) {
+        vt_store(partial + (((long long)blockIdx.x * nblk + t) * (GRAM_B * GRAM_B) + e) * 2, v);
+      }
     }
   }
 }
 
-template <class Loader, int PPW>
-int launch_gram_chunk(trvb_ctx* ctx, const Loader& ld, int na, int nb, long long ncells,
-                      const int* d_ia, const int* d_ib, int npairs, double* d_partial,
-                      int nblocks) {
-  const size_t smem = sizeof(double2) * (size_t)(na + nb) * GRAM_T;
-  TRVB_REQUIRE(smem <= 200 * 1024, "gram reduce: %d + %d fields exceed the shared-memory tile", na, nb);
-  TRVB_CUDA(cudaFuncSetAttribute(k_gram<Loader, PPW>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_gram<Loader, PPW><<<nblocks, GRAM_THREADS, smem, ctx->stream>>>(
-    ld, na, nb, ncells, d_ia, d_ib, npairs, d_partial);
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" :: "n"(N));
+}
+__device__ __forceinline__ double vt_mul(double a, double b) { return a * b; }
+__device__ __forceinline__ double2 vt_mul(double2 a, double2 b) {
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// Same reduction for fields that are plain meshes in memory: raw tiles of
+// A_a, B_b and G stream into a double-buffered shared-memory stage with
+// cp.async (the next tile is in flight while the current one is reduced) and
+// B_b * G is formed at use.
+template <class VT, int TPW>
+__global__ void __launch_bounds__(GRAM_THREADS, 1)
+k_gram_fields(const VT* const* __restrict__ A, const VT* const* __restrict__ B,
+              const VT* __restrict__ G, const int* __restrict__ sel_a, int na,
+              const int* __restrict__ sel_b, int nb, long long ncells,
+              const int* __restrict__ blk_a, const int* __restrict__ blk_b, int nblk,
+              double* __restrict__ partial) {
+  constexpr int T = GRAM_T;
+  constexpr int EPC = 16 / (int)sizeof(VT);   // elements per 16-byte chunk
+  constexpr int CH = T / EPC;                 // chunks per staged row
+  extern __shared__ double2 smem_raw[];
+  const int rows = na + nb + 1;
+  VT* buf0 = reinterpret_cast<VT*>(smem_raw);
+  VT* buf1 = buf0 + (size_t)rows * T;
+  const VT** s_ptr = reinterpret_cast<const VT**>(buf1 + (size_t)rows * T);
+  for (int r = threadIdx.x; r < rows; r += GRAM_THREADS) {
+    s_ptr[r] = r < na ? A[sel_a[r]] : (r < na + nb ? B[sel_b[r - na]] : G);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  VT acc[TPW][GRAM_B * GRAM_B];
+  int a0[TPW], b0[TPW];
+#pragma unroll
+  for (int q = 0; q < TPW; q++) {
+    const int t = warp + q * GRAM_WARPS;
+    a0[q] = (t < nblk) ? blk_a[t] * GRAM_B : 0;
+    b0[q] = (t < nblk) ? blk_b[t] * GRAM_B : 0;
+#pragma unroll
+    for (int e = 0; e < GRAM_B * GRAM_B; e++) vt_zero(acc[q][e]);
+  }
+  auto stage = [&](long long tile, VT* dst) {
+    const long long base = tile * T;
+    for (int idx = threadIdx.x; idx < rows * CH; idx += GRAM_THREADS) {
+      const int r = idx / CH, ch = idx - r * CH;
+      const long long cell = base + (long long)ch * EPC;
+      VT* d = dst + (size_t)r * T + ch * EPC;
+      const VT* src = s_ptr[r] + cell;
+      if (cell + EPC <= ncells && (reinterpret_cast<unsigned long long>(src) & 15ull) == 0) {
+        cp_async16(d, src);
+      } else {
+#pragma unroll
+        for (int e = 0; e < EPC; e++) {
+          VT v; vt_zero(v);
+          if (cell + e < ncells) v = src[e];
+          d[e] = v;
+        }
+      }
+    }
+    cp_async_commit();
+  };
+  const long long ntiles = (ncells + T - 1) / T;
+  if ((long long)blockIdx.x < ntiles) stage(blockIdx.x, buf0);
+  int it = 0;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+    VT* cur = (it & 1) ? buf1 : buf0;
+    VT* nxt = (it & 1) ? buf0 : buf1;
+    const long long next = tile + gridDim.x;
+    if (next < ntiles) stage(next, nxt); else cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const VT* sA = cur;
+    const VT* sB = cur + (size_t)na * T;
+    const VT* sG = cur + (size_t)(na + nb) * T;
+#pragma unroll
+    for (int q = 0; q < TPW; q++) {
+      if (warp + q * GRAM_WARPS < nblk) {
+        const VT* ra = sA + a0[q] * T;
+        const VT* rb = sB + b0[q] * T;
+#pragma unroll
+        for (int h = 0; h < T / 32; h++) {
+          const int x = lane + 32 * h;
+          const VT gx = sG[x];
+          VT va[GRAM_B], vb[GRAM_B];
+#pragma unroll
+          for (int e = 0; e < GRAM_B; e++) { va[e] = ra[e * T + x]; vb[e] = vt_mul(rb[e * T + x], gx); }
+#pragma unroll
+          for (int ea = 0; ea < GRAM_B; ea++)
+#pragma unroll
+            for (int eb = 0; eb < GRAM_B; eb++) vt_fma(acc[q][ea * GRAM_B + eb], va[ea], vb[eb]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int q = 0; q < TPW; q++) {
+    const int t = warp + q * GRAM_WARPS;
+#pragma unroll
+    for (int e = 0; e < GRAM_B * GRAM_B; e++) {
+      VT v = acc[q][e];
+      for (int o = 16; o > 0; o >>= 1) vt_add(v, vt_shfl_down(v, o));
+      if (lane == 0 && t < nblk) {
+        vt_store(partial + (((long long)blockIdx.x * nblk + t) * (GRAM_B * GRAM_B) + e) * 2, v);
+      }
+    }
+  }
+}
+
+// --- TMA (bulk async copy) + mbarrier primitives ----------------------------
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(a), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+    "{\n"
+    ".reg .pred p;\n"
+    "WAIT_LOOP:\n"
+    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+    "@p bra DONE;\n"
+    "bra WAIT_LOOP;\n"
+    "DONE:\n"
+    "}\n" :: "r"(a), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on `bar`
+// (SASS: UBLKCP).  dst, src 16-byte aligned; bytes a multiple of 16.
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, unsigned bytes,
+                                            unsigned long long* bar) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+    :: "r"(d), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
+}
+
+// The field reduction with the tile stage fed by the TMA engine: warp 0 issues
+// one bulk copy per field row (64 cells) of the NEXT tile and arms that
+// stage's mbarrier with the byte count; every warp waits on the barrier of the
+// CURRENT stage, reduces its 4 x 4 pair blocks from it, and a block barrier
+// hands the stage back.  No address arithmetic or staging instructions are
+// spent by the compute warps.  Requires 16-byte aligned meshes.
+template <class VT, int TPW>
+__global__ void __launch_bounds__(GRAM_THREADS, 1)
+k_gram_fields_tma(const VT* const* __restrict__ A, const VT* const* __restrict__ B,
+                  const VT* __restrict__ G, const int* __restrict__ sel_a, int na,
+                  const int* __restrict__ sel_b, int nb, long long ncells,
+                  const int* __restrict__ blk_a, const int* __restrict__ blk_b, int nblk,
+                  double* __restrict__ partial) {
+  constexpr int T = GRAM_T;
+  extern __shared__ __align__(128) double2 smem_raw[];
+  const int rows = na + nb + 1;
+  VT* buf0 = reinterpret_cast<VT*>(smem_raw);
+  VT* buf1 = buf0 + (size_t)rows * T;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(buf1 + (size_t)rows * T);
+  const VT** s_ptr = reinterpret_cast<const VT**>(bars + 2);
+  for (int r = threadIdx.x; r < rows; r += GRAM_THREADS) {
+    s_ptr[r] = r < na ? A[sel_a[r]] : (r < na + nb ? B[sel_b[r - na]] : G);
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  VT acc[TPW][GRAM_B * GRAM_B];
+  int a0[TPW], b0[TPW];
+#pragma unroll
+  for (int q = 0; q < TPW; q++) {
+    const int t = warp + q * GRAM_WARPS;
+    a0[q] = (t < nblk) ? blk_a[t] * GRAM_B : 0;
+    b0[q] = (t < nblk) ? blk_b[t] * GRAM_B : 0;
+#pragma unroll
+    for (int e = 0; e < GRAM_B * GRAM_B; e++) vt_zero(acc[q][e]);
+  }
+  const long long ntiles = (ncells + T - 1) / T;
+  auto issue = [&](long long tile, VT* dst, unsigned long long* bar) {   // warp 0 only
+    const long long base = tile * T;
+    const int valid = (int)min((long long)T, ncells - base);
+    const unsigned row_bytes = (unsigned)(valid * sizeof(VT));
+    if (lane == 0) mbar_arrive_expect_tx(bar, row_bytes * (unsigned)rows);
+    __syncwarp();
+    for (int r = lane; r < rows; r += 32) tma_load_1d(dst + (size_t)r * T, s_ptr[r] + base, row_bytes, bar);
+  };
+  if (warp == 0 && (long long)blockIdx.x < ntiles) issue(blockIdx.x, buf0, &bars[0]);
+  int it = 0;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+    VT* cur = (it & 1) ? buf1 : buf0;
+    const long long next = tile + gridDim.x;
+    if (warp == 0 && next < ntiles) issue(next, (it & 1) ? buf0 : buf1, &bars[(it + 1) & 1]);
+    mbar_wait(&bars[it & 1], (unsigned)((it >> 1) & 1));
+    const int valid = (int)min((long long)T, ncells - tile * T);
+    const VT* sA = cur;
+    const VT* sB = cur + (size_t)na * T;
+    const VT* sG = cur + (size_t)(na + nb) * T;
+#pragma unroll
+    for (int q = 0; q < TPW; q++) {
+      if (warp + q * GRAM_WARPS < nblk) {
+        const VT* ra = sA + a0[q] * T;
+        const VT* rb = sB + b0[q] * T;
+#pragma unroll
+        for (int h = 0; h < T / 32; h++) {
+          const int x = lane + 32 * h;
+          if (x < valid) {
+            const VT gx = sG[x];
+            VT va[GRAM_B], vb[GRAM_B];
+#pragma unroll
+            for (int e = 0; e < GRAM_B; e++) { va[e] = ra[e * T + x]; vb[e] = vt_mul(rb[e * T + x], gx); }
+#pragma unroll
+            for (int ea = 0; ea < GRAM_B; ea++)
+#pragma unroll
+              for (int eb = 0; eb < GRAM_B; eb++) vt_fma(acc[q][ea * GRAM_B + eb], va[ea], vb[eb]);
+          }
+        }
+      }
+    }
+    __syncthreads();   // stage `cur` may be refilled from the next iteration on
+  }
+#pragma unroll
+  for (int q = 0; q < TPW; q++) {
+    const int t = warp + q * GRAM_WARPS;
+#pragma unroll
+    for (int e = 0; e < GRAM_B * GRAM_B; e++) {
+      VT v = acc[q][e];
+      for (int o = 16; o > 0; o >>= 1) vt_add(v, vt_shfl_down(v, o));
+      if (lane == 0 && t < nblk) {
+        vt_store(partial + (((long long)blockIdx.x * nblk + t) * (GRAM_B * GRAM_B) + e) * 2, v);
+      }
+    }
+  }
+}
+
+template <class Loader> struct GramTraits {
+  static constexpr bool kFields = false;
+};
+template <> struct GramTraits<FieldLoader> { static constexpr bool kFields = true; };
+template <> struct GramTraits<RealFieldLoader> { static constexpr bool kFields = true; };
+
+// Staged fields a launch may hold in shared memory (200 KB budget).
+template <class Loader>
+int gram_max_fields() {
+  const size_t per_field = sizeof(typename Loader::VT) * GRAM_T;
+  if (GramTraits<Loader>::kFields) return (int)((200 * 1024 - 4096) / (2 * per_field)) - 1;
+  return (int)((200 * 1024) / per_field);
+}
+
+template <class Loader, int TPW>
+int launch_gram_chunk(trvb_ctx* ctx, const Loader& ld, const int* d_sel_a, int na,
+                      const int* d_sel_b, int nb, long long ncells, const int* d_blk_a,
+                      const int* d_blk_b, int nblk, double* d_partial, int nblocks) {
+  typedef typename Loader::VT VT;
+  if constexpr (GramTraits<Loader>::kFields) {
+    const size_t smem = sizeof(VT) * 2 * (size_t)(na + nb + 1) * GRAM_T + 16
+      + sizeof(void*) * (size_t)(na + nb + 1);
+    TRVB_REQUIRE(smem <= 200 * 1024, "gram reduce: %d + %d fields exceed the shared-memory stage", na, nb);
+    if (ld.aligned16) {
+      TRVB_CUDA(cudaFuncSetAttribute(k_gram_fields_tma<VT, TPW>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_gram_fields_tma<VT, TPW><<<nblocks, GRAM_THREADS, smem, ctx->stream>>>(
+        ld.A, ld.B, ld.G, d_sel_a, na, d_sel_b, nb, ncells, d_blk_a, d_blk_b, nblk, d_partial);
+    } else {
+      TRVB_CUDA(cudaFuncSetAttribute(k_gram_fields<VT, TPW>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_gram_fields<VT, TPW><<<nblocks, GRAM_THREADS, smem, ctx->stream>>>(
+        ld.A, ld.B, ld.G, d_sel_a, na, d_sel_b, nb, ncells, d_blk_a, d_blk_b, nblk, d_partial);
+    }
+  } else {
+    const size_t smem = sizeof(VT) * (size_t)(na + nb) * GRAM_T;
+    TRVB_REQUIRE(smem <= 200 * 1024, "gram reduce: %d + %d fields exceed the shared-memory tile", na, nb);
+    TRVB_CUDA(cudaFuncSetAttribute(k_gram<Loader, TPW>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_gram<Loader, TPW><<<nblocks, GRAM_THREADS, smem, ctx->stream>>>(
+      ld, d_sel_a, na, d_sel_b, nb, ncells, d_blk_a, d_blk_b, nblk, d_partial);
+  }
   TRVB_LAUNCH_CHECK();
   return 0;
 }
 
-// Runs the tiled reduction over all pairs (chunks of <= 256 pairs) and
-// returns the complex sums in host array `out` (2 * npairs doubles).
+// Runs the tiled reduction for `npairs` (ia, ib) pairs over `na_all` x
+// `nb_all` loader fields and returns the complex sums in host array `out`
+// (2 * npairs doubles).  Pairs are grouped into 4 x 4 blocks; launches cover
+// up to GRAM_WARPS * 4 blocks and stage only the fields their blocks touch.
 template <class Loader>
-int run_gram(trvb_ctx* ctx, const Loader& ld, int na, int nb, long long ncells,
+int run_gram(trvb_ctx* ctx, const Loader& ld, int na_all, int nb_all, long long ncells,
              const int* ia, const int* ib, int npairs, double* out) {
-  TRVB_REQUIRE(na > 0 && nb > 0 && npairs > 0, "gram reduce: empty problem");
-  TRVB_REQUIRE(na < 32768 && nb < 32768, "gram reduce: too many fields");
+  TRVB_REQUIRE(na_all > 0 && nb_all > 0 && npairs > 0, "gram reduce: empty problem");
+  constexpr int E = GRAM_B * GRAM_B;
+  // Needed blocks in (a-block, b-block) order.
+  const int nba = (na_all + GRAM_B - 1) / GRAM_B, nbb = (nb_all + GRAM_B - 1) / GRAM_B;
+  std::vector<char> need((size_t)nba * nbb, 0);
+  for (int p = 0; p < npairs; p++) need[(size_t)(ia[p] / GRAM_B) * nbb + ib[p] / GRAM_B] = 1;
+  std::vector<std::pair<int, int> > blocks;
+  for (int a = 0; a < nba; a++)
+    for (int b = 0; b < nbb; b++) if (need[(size_t)a * nbb + b]) blocks.emplace_back(a, b);
+  // Complex accumulators: 3 blocks per warp fit the register file without spills.
+  constexpr int MAX_TPW = sizeof(typename Loader::VT) == sizeof(double) ? 4 : 3;
+  const int max_blk = GRAM_WARPS * MAX_TPW;
   const long long ntiles = (ncells + GRAM_T - 1) / GRAM_T;
   const int nblocks = (int)std::min<long long>(ntiles, (long long)ctx->num_sms);
-  const int max_chunk = GRAM_WARPS * 32;
-  // Scratch: pair tables (ints) + partials + result.
-  const size_t bytes_pairs = sizeof(int) * 2 * (size_t)npairs;
-  const size_t pad_pairs = (bytes_pairs + 255) / 256 * 256;
-  const size_t bytes_partial = sizeof(double) * 2 * (size_t)nblocks * max_chunk;
-  const size_t bytes_out = sizeof(double) * 2 * (size_t)npairs;
+
+  // Chunk plan (host): per launch the staged field lists and block tables.
+  struct Chunk { std::vector<int> sel_a, sel_b, blk_a, blk_b; size_t first; };
+  std::vector<Chunk> chunks;
+  const int max_fields = gram_max_fields<Loader>();
+  for (size_t b0 = 0; b0 < blocks.size();) {
+    Chunk c; c.first = b0;
+    std::vector<int> slot_a(nba, -1), slot_b(nbb, -1);
+    size_t t = b0;
+    for (; t < blocks.size() && (int)c.blk_a.size() < max_blk; t++) {
+      const int a = blocks[t].first, b = blocks[t].second;
+      const int extra = (slot_a[a] < 0 ? GRAM_B : 0) + (slot_b[b] < 0 ? GRAM_B : 0);
+      if (!c.blk_a.empty() && (int)(c.sel_a.size() + c.sel_b.size()) + extra > max_fields) break;
+      if (slot_a[a] < 0) {
+        slot_a[a] = (int)c.sel_a.size() / GRAM_B;
+        for (int e = 0; e < GRAM_B; e++) c.sel_a.push_back(std::min(a * GRAM_B + e, na_all - 1));
+      }
+      if (slot_b[b] < 0) {
+        slot_b[b] = (int)c.sel_b.size() / GRAM_B;
+        for (int e = 0; e < GRAM_B; e++) c.sel_b.push_back(std::min(b * GRAM_B + e, nb_all - 1));
+      }
+      c.blk_a.push_back(slot_a[a]); c.blk_b.push_back(slot_b[b]);
+    }
+    b0 = t;
+    chunks.push_back(std::move(c));
+  }
+  // One scratch buffer: [int tables of all chunks][partials][block results].
+  size_t nints = 0;
+  for (const Chunk& c : chunks) nints += c.sel_a.size() + c.sel_b.size() + 2 * c.blk_a.size();
+  const size_t bytes_tab = (sizeof(int) * nints + 255) / 256 * 256;
+  const size_t bytes_partial = sizeof(double) * 2 * E * (size_t)nblocks * max_blk;
+  const size_t bytes_res = sizeof(double) * 2 * E * blocks.size();
   double* scratch;
-  int st = trvb_scratch(ctx, pad_pairs + bytes_partial + bytes_out + 512, &scratch);
+  int st = trvb_scratch(ctx, bytes_tab + bytes_partial + bytes_res + 512, &scratch);
   if (st) return st;
-  int* d_ia = (int*)scratch;
-  int* d_ib = d_ia + npairs;
-  double* d_partial = (double*)((char*)scratch + pad_pairs);
-  double* d_out = (double*)((char*)d_partial + bytes_partial);
-  TRVB_CUDA(cudaMemcpyAsync(d_ia, ia, sizeof(int) * npairs, cudaMemcpyHostToDevice, ctx->stream));
-  TRVB_CUDA(cudaMemcpyAsync(d_ib, ib, sizeof(int) * npairs, cudaMemcpyHostToDevice, ctx->stream));
-  for (int p0 = 0; p0 < npairs; p0 += max_chunk) {
-    const int np = std::min(max_chunk, npairs - p0);
-    if (np <= GRAM_WARPS * 4) {
-      st = launch_gram_chunk<Loader, 4>(ctx, ld, na, nb, ncells, d_ia + p0, d_ib + p0, np, d_partial, nblocks);
-    } else if (np <= GRAM_WARPS * 16) {
-      st = launch_gram_chunk<Loader, 16>(ctx, ld, na, nb, ncells, d_ia + p0, d_ib + p0, np, d_partial, nblocks);
+  int* d_tab = (int*)scratch;
+  double* d_partial = (double*)((char*)scratch + bytes_tab);
+  double* d_res = (double*)((char*)d_partial + bytes_partial);
+  std::vector<int> h_tab; h_tab.reserve(nints);
+  std::vector<size_t> off;
+  for (const Chunk& c : chunks) {
+    off.push_back(h_tab.size());
+    h_tab.insert(h_tab.end(), c.sel_a.begin(), c.sel_a.end());
+    h_tab.insert(h_tab.end(), c.sel_b.begin(), c.sel_b.end());
+    h_tab.insert(h_tab.end(), c.blk_a.begin(), c.blk_a.end());
+    h_tab.insert(h_tab.end(), c.blk_b.begin(), c.blk_b.end());
+  }
+  TRVB_CUDA(cudaMemcpyAsync(d_tab, h_tab.data(), sizeof(int) * h_tab.size(),
+                            cudaMemcpyHostToDevice, ctx->stream));
+  for (size_t ci = 0; ci < chunks.size(); ci++) {
+    const Chunk& c = chunks[ci];
+    const int na = (int)c.sel_a.size(), nb = (int)c.sel_b.size(), nblk = (int)c.blk_a.size();
+    const int* d_sel_a = d_tab + off[ci];
+    const int* d_sel_b = d_sel_a + na;
+    const int* d_blk_a = d_sel_b + nb;
+    const int* d_blk_b = d_blk_a + nblk;
+    if (nblk <= GRAM_WARPS) {
+      st = launch_gram_chunk<Loader, 1>(ctx, ld, d_sel_a, na, d_sel_b, nb, ncells, d_blk_a, d_blk_b, nblk, d_partial, nblocks);
+    } else if (nblk <= GRAM_WARPS * 2) {
+      st = launch_gram_chunk<Loader, 2>(ctx, ld, d_sel_a, na, d_sel_b, nb, ncells, d_blk_a, d_blk_b, nblk, d_partial, nblocks);
     } else {
-      st = launch_gram_chunk<Loader, 32>(ctx, ld, na, nb, ncells, d_ia + p0, d_ib + p0, np, d_partial, nblocks);
+      st = launch_gram_chunk<Loader, MAX_TPW>(ctx, ld, d_sel_a, na, d_sel_b, nb, ncells, d_blk_a, d_blk_b, nblk, d_partial, nblocks);
     }
     if (st) return st;
-    k_sum_cols<<<div_up(2 * np, 128), 128, 0, ctx->stream>>>(d_partial, nblocks, 2 * np, d_out + 2 * p0);
+    k_sum_cols<<<div_up(2 * E * nblk, 128), 128, 0, ctx->stream>>>(
+      d_partial, nblocks, 2 * E * nblk, d_res + 2 * E * c.first);
     TRVB_LAUNCH_CHECK();
   }
-  TRVB_CUDA(cudaMemcpyAsync(out, d_out, bytes_out, cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<double> h_res(2 * E * blocks.size());
+  TRVB_CUDA(cudaMemcpyAsync(h_res.data(), d_res, bytes_res, cudaMemcpyDeviceToHost, ctx->stream));
   TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<int> block_of((size_t)nba * nbb, -1);
+  for (size_t t = 0; t < blocks.size(); t++) block_of[(size_t)blocks[t].first * nbb + blocks[t].second] = (int)t;
+  for (int p = 0; p < npairs; p++) {
+    const int t = block_of[(size_t)(ia[p] / GRAM_B) * nbb + ib[p] / GRAM_B];
+    const int e = (ia[p] % GRAM_B) * GRAM_B + ib[p] % GRAM_B;
+    out[2 * p] = h_res[((size_t)t * E + e) * 2];
+    out[2 * p + 1] = h_res[((size_t)t * E + e) * 2 + 1];
+  }
   return 0;
 }
 
@@ -375,46 +798,44 @@ k_twopt_fourier(KView fa, KView fb, GridDesc g, Tables tb, Cube cube,
 }
 
 // (fa conj(fb)/C1 - S C1/C1) / V on the full grid (S/field.cpp:3273-3298).
+// `n2s` = stored extent of the last axis of dst: n2 (COMPLEX) or n2/2+1 (HALF).
 __global__ void __launch_bounds__(256)
 k_shot_spectrum(KView fa, KView fb, GridDesc g, Tables tb, double S_re, double S_im,
-                double2* __restrict__ dst) {
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < g.nmesh;
-       t += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(t % g.n[2]);
-    const int j = (int)((t / g.n[2]) % g.n[1]);
-    const int i = (int)(t / ((long long)g.n[2] * g.n[1]));
+                int n2s, double2* __restrict__ dst) {
+  const double inv_vol = 1. / g.vol;
+  for_each_cell(g.n[0], g.n[1], n2s, [&](int i, int j, int k, long long t) {
     const cplx a = kload(fa, i, j, k), b = kload(fb, i, j, k);
-    const double c1 = tb.alias[0][i] * tb.alias[1][j] * tb.alias[2][k];
-    double re = (a.re * b.re + a.im * b.im) / c1 - (S_re * c1) / c1;
-    double im = (a.im * b.re - a.re * b.im) / c1 - (S_im * c1) / c1;
-    dst[t] = make_double2(re / g.vol, im / g.vol);
-  }
+    // fa conj(fb)/C1 - S C1/C1, then /V, with tabulated per-axis reciprocals of
+    // C1 instead of six fp64 divisions per mode (the pass was bound by the
+    // divide sequence, not by HBM).
+    const double rc1 = tb.ralias[0][i] * tb.ralias[1][j] * tb.ralias[2][k];
+    const double re = (a.re * b.re + a.im * b.im) * rc1 - S_re;
+    const double im = (a.im * b.re - a.re * b.im) * rc1 - S_im;
+    dst[t] = make_double2(re * inv_vol, im * inv_vol);
+  });
 }
 
 __global__ void __launch_bounds__(256)
-k_shot_3pcf_bin(const double2* __restrict__ xi, GridDesc g,
+k_shot_3pcf_bin(XView xi, GridDesc g,
                 const BinRule* __restrict__ rules, int la, int ma, int lb, int mb,
                 double* __restrict__ partial) {
   __shared__ double sm[32];
   const BinRule rule = rules[blockIdx.y];
   double v[4] = {0., 0., 0., 0.};
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < g.nmesh;
-       t += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(t % g.n[2]);
-    const int j = (int)((t / g.n[2]) % g.n[1]);
-    const int i = (int)(t / ((long long)g.n[2] * g.n[1]));
+  // 1-D block (blockDim.y == 1): rows over blockIdx.x, last axis over threads.
+  for_each_cell(g.n[0], g.n[1], g.n[2], [&](int i, int j, int k, long long t) {
     const double rx = __dmul_rn((double)signed_index(i, g.n[0]), g.dr[0]);
     const double ry = __dmul_rn((double)signed_index(j, g.n[1]), g.dr[1]);
     const double rz = __dmul_rn((double)signed_index(k, g.n[2]), g.dr[2]);
     const double r = vec3_norm_exact(rx, ry, rz);
-    if (!in_bin(rule, r)) continue;
+    if (!in_bin(rule, r)) return;
     const cplx ya = ylm_reduced(la, ma, rx, ry, rz);
     const cplx yb = ylm_reduced(lb, mb, rx, ry, rz);
-    const double2 x = xi[t];
+    const double2 x = xload(xi, t);
     cplx xv; xv.re = x.x; xv.im = x.y;
     const cplx val = cmul(xv, cmul(ya, yb));
     v[0] += 1.; v[1] += r; v[2] += val.re; v[3] += val.im;
-  }
+  });
   store_partials<4>(v, sm, partial);
 }
 
@@ -484,11 +905,8 @@ int run_binned(trvb_ctx* ctx, const std::vector<BinRule>& rules, long long nwork
   launch(grid, d_rules, d_partial);
   TRVB_LAUNCH_CHECK();
   // partial is [bin][bx][NQ]; sum over bx for each (bin, q).
-  for (int b = 0; b < nbins; b++) {
-    k_sum_cols<<<1, 32, 0, ctx->stream>>>(d_partial + (size_t)b * bx * NQ, bx, NQ, d_out + (size_t)b * NQ);
-    g_trvb_launches++;
-  }
-  TRVB_CUDA(cudaGetLastError());
+  k_sum_binned<<<nbins, 32, 0, ctx->stream>>>(d_partial, bx, NQ, d_out);
+  TRVB_LAUNCH_CHECK();
   host_out.resize((size_t)nbins * NQ);
   TRVB_CUDA(cudaMemcpyAsync(host_out.data(), d_out, bytes_out, cudaMemcpyDeviceToHost, ctx->stream));
   TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -523,7 +941,8 @@ extern "C" int trvb_gram_reduce(trvb_ctx* ctx, const void* const* A, int na,
                                 const void* const* B, int nb, trvb_mesh G,
                                 const int* ia, const int* ib, int npairs, double* out) {
   TRVB_REQUIRE(ctx && A && B && G.data && ia && ib && out, "trvb_gram_reduce: null argument");
-  TRVB_REQUIRE(G.layout == TRVB_COMPLEX, "trvb_gram_reduce: G must be a COMPLEX mesh");
+  TRVB_REQUIRE(G.layout == TRVB_COMPLEX || G.layout == TRVB_REAL,
+               "trvb_gram_reduce: G must be a configuration-space mesh");
   for (int p = 0; p < npairs; p++) {
     TRVB_REQUIRE(ia[p] >= 0 && ia[p] < na && ib[p] >= 0 && ib[p] < nb,
                  "trvb_gram_reduce: pair %d = (%d, %d) out of range", p, ia[p], ib[p]);
@@ -533,12 +952,29 @@ extern "C" int trvb_gram_reduce(trvb_ctx* ctx, const void* const* A, int na,
   TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&d_tab, sizeof(void*) * (size_t)(na + nb)));
   TRVB_CUDA(cudaMemcpyAsync(d_tab, A, sizeof(void*) * na, cudaMemcpyHostToDevice, ctx->stream));
   TRVB_CUDA(cudaMemcpyAsync(d_tab + na, B, sizeof(void*) * nb, cudaMemcpyHostToDevice, ctx->stream));
-  FieldLoader ld;
-  ld.A = (const double2* const*)d_tab;
-  ld.B = (const double2* const*)(d_tab + na);
-  ld.G = (const double2*)G.data;
-  int st = run_gram(ctx, ld, na, nb, ctx->g.nmesh, ia, ib, npairs, out);
-  cudaStreamSynchronize(ctx->stream);
+  bool aligned = (reinterpret_cast<unsigned long long>(G.data) & 15ull) == 0;
+  for (int i = 0; i < na; i++) aligned = aligned && (reinterpret_cast<unsigned long long>(A[i]) & 15ull) == 0;
+  for (int i = 0; i < nb; i++) aligned = aligned && (reinterpret_cast<unsigned long long>(B[i]) & 15ull) == 0;
+  // Real meshes with an odd cell count end in a half chunk: keep the cp.async path.
+  if (G.layout == TRVB_REAL && (ctx->g.nmesh & 1)) aligned = false;
+  const char* env_tma = getenv("TRV_GRAM_NO_TMA");
+  if (env_tma && env_tma[0] == '1') aligned = false;
+  int st;
+  if (G.layout == TRVB_REAL) {
+    RealFieldLoader ld;
+    ld.aligned16 = aligned;
+    ld.A = (const double* const*)d_tab;
+    ld.B = (const double* const*)(d_tab + na);
+    ld.G = (const double*)G.data;
+    st = run_gram(ctx, ld, na, nb, ctx->g.nmesh, ia, ib, npairs, out);
+  } else {
+    FieldLoader ld;
+    ld.aligned16 = aligned;
+    ld.A = (const double2* const*)d_tab;
+    ld.B = (const double2* const*)(d_tab + na);
+    ld.G = (const double2*)G.data;
+    st = run_gram(ctx, ld, na, nb, ctx->g.nmesh, ia, ib, npairs, out);
+  }
   trvb_dev_free_raw(ctx, d_tab);
   return st;
 }
@@ -548,7 +984,9 @@ extern "C" int trvb_shot_bispec_reduce(trvb_ctx* ctx, trvb_mesh xi, int la, int 
                                        int npairs, double* out) {
   TRVB_REQUIRE(ctx && xi.data && ka && kb && out && npairs > 0,
                "trvb_shot_bispec_reduce: bad argument");
-  TRVB_REQUIRE(xi.layout == TRVB_COMPLEX, "trvb_shot_bispec_reduce: xi must be COMPLEX");
+  TRVB_REQUIRE(xi.layout == TRVB_COMPLEX || xi.layout == TRVB_REAL,
+               "trvb_shot_bispec_reduce: xi must be a configuration-space mesh");
+  XView xv; xv.p = (const double*)xi.data; xv.cplx = xi.layout == TRVB_COMPLEX;
   TRVB_REQUIRE(ctx->parent == nullptr, "trvb_shot_bispec_reduce: root context only");
   auto ita = ctx->sjl.find(la), itb = ctx->sjl.find(lb);
   TRVB_REQUIRE(ita != ctx->sjl.end() && itb != ctx->sjl.end(),
@@ -588,8 +1026,12 @@ extern "C" int trvb_shot_bispec_reduce(trvb_ctx* ctx, trvb_mesh xi, int la, int 
     double* d_hist = nullptr;
     TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&d_hist, 2 * sizeof(double) * (size_t)nq));
     TRVB_CUDA(cudaMemsetAsync(d_hist, 0, 2 * sizeof(double) * (size_t)nq, ctx->stream));
-    const int blocks = (int)std::min<long long>(div_up(g.nmesh, 256), (long long)ctx->num_sms * 16);
-    k_shot_radial_hist<<<blocks, 256, 0, ctx->stream>>>((const double2*)xi.data, g, la, ma, lb, mb, d_hist);
+    const RowLaunch rl = row_launch(ctx->num_sms, g.n[0] / 2 + 1, g.n[1] / 2 + 1, g.n[2] / 2 + 1);
+    if (la == 0 && lb == 0) {
+      k_shot_radial_hist<true><<<rl.grid, rl.block, 0, ctx->stream>>>(xv, g, la, ma, lb, mb, d_hist);
+    } else {
+      k_shot_radial_hist<false><<<rl.grid, rl.block, 0, ctx->stream>>>(xv, g, la, ma, lb, mb, d_hist);
+    }
     TRVB_LAUNCH_CHECK();
     RadialLoader ld;
     ld.hist = (const double2*)d_hist; ld.dr = g.dr[0];
@@ -598,7 +1040,7 @@ extern "C" int trvb_shot_bispec_reduce(trvb_ctx* ctx, trvb_mesh xi, int la, int 
     trvb_dev_free_raw(ctx, d_hist);
   } else {
     ShotLoader ld;
-    ld.xi = (const double2*)xi.data; ld.g = g;
+    ld.xi = xv; ld.g = g;
     ld.sja = sja; ld.sjb = sjb;
     ld.ka = d_k; ld.kb = d_k + ua.size();
     ld.la = la; ld.ma = ma; ld.lb = lb; ld.mb = mb;
@@ -672,13 +1114,32 @@ extern "C" int trvb_twopt_fourier(trvb_ctx* ctx, trvb_mesh fa, trvb_mesh fb,
 extern "C" int trvb_shot_xi(trvb_ctx* ctx, trvb_mesh fa, trvb_mesh fb, const double S[2],
                             trvb_mesh dst) {
   TRVB_REQUIRE(ctx && fa.data && fb.data && S && dst.data, "trvb_shot_xi: null argument");
-  TRVB_REQUIRE(fa.layout != TRVB_REAL && fb.layout != TRVB_REAL && dst.layout == TRVB_COMPLEX,
-               "trvb_shot_xi: Fourier-space inputs and a COMPLEX output required");
+  TRVB_REQUIRE(fa.layout != TRVB_REAL && fb.layout != TRVB_REAL,
+               "trvb_shot_xi: Fourier-space inputs required");
+  TRVB_REQUIRE(dst.layout == TRVB_COMPLEX
+               || (dst.layout == TRVB_REAL && fa.layout == TRVB_HALF && fb.layout == TRVB_HALF
+                   && S[1] == 0.),
+               "trvb_shot_xi: dst must be COMPLEX (or REAL for two HALF inputs and real S)");
   TRVB_REQUIRE(dst.data != fa.data && dst.data != fb.data, "trvb_shot_xi: dst aliases an input");
   TRVB_REQUIRE(ctx->parent == nullptr, "trvb_shot_xi: root context only");
-  const int blocks = (int)std::min<long long>(div_up(ctx->g.nmesh, 256), (long long)ctx->num_sms * 32);
-  k_shot_spectrum<<<blocks, 256, 0, ctx->stream>>>(
-    kview_of(ctx, fa), kview_of(ctx, fb), ctx->g, tables_of(ctx), S[0], S[1], (double2*)dst.data);
+  const GridDesc& g = ctx->g;
+  if (dst.layout == TRVB_REAL) {
+    // Hermitian product: build the half spectrum in a temporary, Z2D into dst.
+    trvb_mesh half; half.layout = TRVB_HALF; half.k0_add = 0.; half.data = nullptr;
+    TRVB_CUDA(trvb_dev_alloc_raw(ctx, &half.data, trvb_mesh_bytes(ctx, TRVB_HALF)));
+    const RowLaunch rl = row_launch(ctx->num_sms, g.n[0], g.n[1], g.nh);
+    k_shot_spectrum<<<rl.grid, rl.block, 0, ctx->stream>>>(
+      kview_of(ctx, fa), kview_of(ctx, fb), g, tables_of(ctx), S[0], S[1], g.nh,
+      (double2*)half.data);
+    TRVB_LAUNCH_CHECK();
+    int st = trvb_fft_inverse(ctx, half, dst);
+    trvb_dev_free_raw(ctx, half.data);
+    return st;
+  }
+  const RowLaunch rl = row_launch(ctx->num_sms, g.n[0], g.n[1], g.n[2]);
+  k_shot_spectrum<<<rl.grid, rl.block, 0, ctx->stream>>>(
+    kview_of(ctx, fa), kview_of(ctx, fb), g, tables_of(ctx), S[0], S[1], g.n[2],
+    (double2*)dst.data);
   TRVB_LAUNCH_CHECK();
   return trvb_fft_inverse(ctx, dst, dst);
 }
@@ -689,12 +1150,13 @@ extern "C" int trvb_shot_3pcf_bin(trvb_ctx* ctx, trvb_mesh xi, int la, int ma, i
                                   double* xi_out) {
   TRVB_REQUIRE(ctx && xi.data && edges && centres && npairs && r && xi_out,
                "trvb_shot_3pcf_bin: null argument");
-  TRVB_REQUIRE(xi.layout == TRVB_COMPLEX, "trvb_shot_3pcf_bin: xi must be COMPLEX");
+  TRVB_REQUIRE(xi.layout == TRVB_COMPLEX || xi.layout == TRVB_REAL,
+               "trvb_shot_3pcf_bin: xi must be a configuration-space mesh");
   TRVB_REQUIRE(ctx->parent == nullptr, "trvb_shot_3pcf_bin: root context only");
   std::vector<BinRule> rules;
   make_rules(edges, nbins, 1, 1., 100000, rules);   // S/field.cpp:3095-3096
   const GridDesc g = ctx->g;
-  const double2* d_xi = (const double2*)xi.data;
+  XView d_xi; d_xi.p = (const double*)xi.data; d_xi.cplx = xi.layout == TRVB_COMPLEX;
   std::vector<double> host;
   int st = run_binned<4>(ctx, rules, g.nmesh,
     [&](dim3 grid, const BinRule* d_rules, double* d_partial) {

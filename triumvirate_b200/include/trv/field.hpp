@@ -77,7 +77,11 @@ class Mesh {
   Mesh& operator=(Mesh&& other) noexcept;
   Mesh(const Mesh&) = delete;
   Mesh& operator=(const Mesh&) = delete;
-  trvb_mesh view() const { trvb_mesh m; m.data = data_; m.layout = layout_; return m; }
+  trvb_mesh view() const {
+    trvb_mesh m; m.data = data_; m.layout = layout_; m.k0_add = 0.; return m;
+  }
+  /// Fourier-space view whose k = 0 element reads as stored + `add`.
+  trvb_mesh view_k0(double add) const { trvb_mesh m = view(); m.k0_add = add; return m; }
   void* data() const { return data_; }
   int layout() const { return layout_; }
   bool empty() const { return data_ == nullptr; }

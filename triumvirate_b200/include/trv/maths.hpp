@@ -47,7 +47,11 @@ class SphericalBesselCalculator {
 
   explicit SphericalBesselCalculator(const int ell);
   SphericalBesselCalculator(const SphericalBesselCalculator& other) = default;
+  SphericalBesselCalculator& operator=(const SphericalBesselCalculator& other) = default;
   double eval(double x);
+
+ private:
+  void build_table();
 };
 
 }  // namespace maths

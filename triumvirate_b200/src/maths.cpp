@@ -8,6 +8,9 @@
 // j_l on the device would fail 1e-8 parity.
 #include "trv/maths.hpp"
 
+#include <map>
+#include <mutex>
+
 #include <cmath>
 
 namespace trv {
@@ -169,7 +172,26 @@ std::complex<double> SphericalHarmonicCalculator::calc_reduced_spherical_harmoni
 // Spline-interpolated spherical Bessel calculator.
 // ---------------------------------------------------------------------
 
+namespace {
+// The table is a pure function of ell: build it once per process (the
+// reference rebuilds it -- 20001 exact j_l evaluations and a tridiagonal
+// solve -- in every estimator call, S/threept.cpp:1560-1561).
+std::mutex g_sjl_mutex;
+std::map<int, SphericalBesselCalculator> g_sjl_cache;
+}  // namespace
+
 SphericalBesselCalculator::SphericalBesselCalculator(const int ell) : order(ell) {
+  {
+    std::lock_guard<std::mutex> lock(g_sjl_mutex);
+    auto it = g_sjl_cache.find(ell);
+    if (it != g_sjl_cache.end()) { *this = it->second; return; }
+  }
+  this->build_table();
+  std::lock_guard<std::mutex> lock(g_sjl_mutex);
+  g_sjl_cache.emplace(ell, *this);
+}
+
+void SphericalBesselCalculator::build_table() {
   this->split = (this->split >= this->order * this->order)
     ? this->split : this->order * this->order;            // S/maths.cpp:313-314
   const double xmin = 0., xmax = this->split, dx = this->step;

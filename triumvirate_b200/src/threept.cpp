@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cmath>
 #include <map>
+#include <memory>
 #include <set>
 
 namespace trvs = trv::sys;
@@ -161,12 +162,26 @@ DataVector make_data_vector(const trv::ParameterSet& params, int num_bins) {
   return dv;
 }
 
+/// Transform length >= n that minimises the measured cuFFT cost per 3-D
+/// transform among nearby 7-smooth sizes.  On B200 (fp64, batched Z2Z/Z2D)
+/// lengths 2^a 3^b with a >= 4 run at ~15 ns per 1000 cells, other 5-smooth
+/// multiples of 16 ~20 % slower, lengths with odd or factor-7 structure
+/// ~1.7x slower (135^3: 70 us vs 144^3: 44 us).
 int next_fft_size(int n) {
-  for (int v = std::max(n, 2);; v++) {
-    int r = v;
-    for (int p : {2, 3, 5, 7}) while (r % p == 0) r /= p;
-    if (r == 1) return v;
+  int best = 0; double best_cost = 0.;
+  const int lo = std::max(n, 2), hi = std::max(lo + 16, (int)(1.35 * lo));
+  for (int v = lo; v <= hi; v++) {
+    int r = v, n5 = 0, n7 = 0;
+    while (r % 2 == 0) r /= 2;
+    while (r % 3 == 0) r /= 3;
+    while (r % 5 == 0) { r /= 5; n5++; }
+    while (r % 7 == 0) { r /= 7; n7++; }
+    if (r != 1) continue;
+    double penalty = (v % 16 == 0 && n7 == 0) ? 1. + 0.2 * n5 : 1.7;
+    const double cost = penalty * double(v) * double(v) * double(v);
+    if (best == 0 || cost < best_cost) { best = v; best_cost = cost; }
   }
+  return best;
 }
 
 std::vector<int> distinct_sorted(const std::vector<int>& v) {
@@ -295,15 +310,11 @@ class Engine {
     return forward(x);
   }
 
-  /// Box only: N_00(k) obtained from delta n_00(k) by restoring the k = 0
-  /// mode (identical to a second assignment + FFT; saves both).
-  dev::Mesh quadratic_from_fluctuation(const dev::Mesh& dn) {
-    dev::Mesh k(ctx_, c_, dn.layout());
-    dev::check(trvb_d2d(c_, k.data(), dn.data(), trvb_mesh_bytes(c_, dn.layout())),
-               "trvb_d2d");
-    dev::check(trvb_kmesh_add_zero_mode(c_, k.view(), double(ndata_)),
-               "trvb_kmesh_add_zero_mode");
-    return k;
+  /// Box only: N_00(k) is delta n_00(k) with the k = 0 mode restored
+  /// (S/threept.cpp:1554-1558 assigns and transforms the same catalogue a
+  /// second time); expressed as a shifted view of the same buffer.
+  trvb_mesh quadratic_view_of_fluctuation(const dev::Mesh& dn) const {
+    return dn.view_k0(double(ndata_));
   }
 
   cdouble shotnoise_amp(int L, int M) {
@@ -356,13 +367,41 @@ class Engine {
   int mode_ = 0;
 };
 
+/// `count` consecutive meshes of one grid in a single device allocation (the
+/// unit the batched transforms write and the pair reduction reads).
+class Slab {
+ public:
+  Slab(std::shared_ptr<trvb_ctx> owner, trvb_ctx* grid, int layout, int count)
+    : owner_(owner), stride_(trvb_mesh_bytes(grid, layout)), count_(count) {
+    dev::check(trvb_malloc(owner_.get(), &data_, stride_ * (size_t)std::max(count, 1)),
+               "trvb_malloc");
+    trvs::gbytesMemGPU += gib();
+    trvs::update_maxmem(true);
+  }
+  ~Slab() {
+    if (data_) { trvb_free(owner_.get(), data_); trvs::gbytesMemGPU -= gib(); }
+  }
+  Slab(const Slab&) = delete;
+  Slab& operator=(const Slab&) = delete;
+  void* data() const { return data_; }
+  void* mesh(int i) const { return static_cast<char*>(data_) + stride_ * (size_t)i; }
+  int count() const { return count_; }
+ private:
+  double gib() const { return double(stride_) * count_ / (1024. * 1024. * 1024.); }
+  std::shared_ptr<trvb_ctx> owner_;
+  void* data_ = nullptr;
+  size_t stride_;
+  int count_;
+};
+
 /// Blocked all-pairs reduction: out[idx] = sum_x A_{row(idx)} B_{col(idx)} G
-/// for the entries of `dv` selected by `active`.  `make_a(bin, mesh)` and
-/// `make_b(bin, mesh)` fill a COMPLEX mesh on `grid` for a bin index.
+/// for the entries of `dv` selected by `active`.  `make_a(bins, slab)` and
+/// `make_b(bins, slab)` fill slab mesh i (layout of G, on `grid`) with the
+/// field of bin bins[i].
 template <class MakeA, class MakeB>
 void reduce_pairs(Engine& eng, trvb_ctx* grid, const DataVector& dv,
                   const std::vector<char>& active, bool same_fields,
-                  const dev::Mesh& G, MakeA make_a, MakeB make_b,
+                  trvb_mesh G, MakeA make_a, MakeB make_b,
                   std::vector<cdouble>& out) {
   out.assign(dv.dim, cdouble(0., 0.));
   std::vector<int> rows_all, cols_all;
@@ -373,50 +412,52 @@ void reduce_pairs(Engine& eng, trvb_ctx* grid, const DataVector& dv,
   const std::vector<int> rows = distinct_sorted(rows_all);
   const std::vector<int> cols = distinct_sorted(cols_all);
 
-  const size_t bytes = trvb_mesh_bytes(grid, TRVB_COMPLEX);
-  int cap = eng.mesh_capacity(bytes) - 1;
+  // Memory plan: a REAL field is produced from a transient half spectrum of
+  // about the same size.
+  const size_t bytes = trvb_mesh_bytes(grid, G.layout) * (G.layout == TRVB_REAL ? 2 : 1);
+  const int cap = eng.mesh_capacity(bytes) - 1;
   if (cap < 2) {
     throw trvs::DeviceError(
       "Insufficient device memory: fewer than two %zu-byte shell meshes fit.", bytes);
   }
   const int want = static_cast<int>(rows.size() + cols.size());
-  const int max_tile = 100;   // shared-memory tile limit of trvb_gram_reduce
   int block_r = static_cast<int>(rows.size());
   int block_c = static_cast<int>(cols.size());
-  if (want > cap || want > max_tile) {
-    const int half = std::max(1, std::min(cap, max_tile) / 2);
+  if (want > cap) {
+    const int half = std::max(1, cap / 2);
     block_r = std::min(block_r, half);
     block_c = std::min(block_c, half);
   }
 
   for (size_t r0 = 0; r0 < rows.size(); r0 += block_r) {
     const size_t r1 = std::min(rows.size(), r0 + block_r);
-    std::map<int, dev::Mesh> fa;
-    for (size_t r = r0; r < r1; r++) {
-      dev::Mesh m(eng.shared(), grid, TRVB_COMPLEX);
-      make_a(rows[r], m);
-      fa.emplace(rows[r], std::move(m));
-    }
+    const std::vector<int> bins_a(rows.begin() + r0, rows.begin() + r1);
+    Slab fa(eng.shared(), grid, G.layout, (int)bins_a.size());
+    make_a(bins_a, fa);
+    std::map<int, int> ia_of;
+    std::vector<const void*> pa;
+    for (size_t i = 0; i < bins_a.size(); i++) { ia_of[bins_a[i]] = (int)i; pa.push_back(fa.mesh((int)i)); }
     for (size_t c0 = 0; c0 < cols.size(); c0 += block_c) {
       const size_t c1 = std::min(cols.size(), c0 + block_c);
-      std::map<int, dev::Mesh> fb_own;
-      std::map<int, const dev::Mesh*> fb;
+      // Columns whose field already exists among the rows share it.
+      std::vector<int> bins_b;
       for (size_t c = c0; c < c1; c++) {
-        auto hit = fa.find(cols[c]);
-        if (same_fields && hit != fa.end()) {
-          fb[cols[c]] = &hit->second;
-        } else {
-          dev::Mesh m(eng.shared(), grid, TRVB_COMPLEX);
-          make_b(cols[c], m);
-          auto ins = fb_own.emplace(cols[c], std::move(m));
-          fb[cols[c]] = &ins.first->second;
-        }
+        if (!(same_fields && ia_of.count(cols[c]))) bins_b.push_back(cols[c]);
+      }
+      std::unique_ptr<Slab> fb;
+      if (!bins_b.empty()) {
+        fb.reset(new Slab(eng.shared(), grid, G.layout, (int)bins_b.size()));
+        make_b(bins_b, *fb);
+      }
+      std::map<int, int> ib_of;
+      std::vector<const void*> pb;
+      int next_own = 0;
+      for (size_t c = c0; c < c1; c++) {
+        ib_of[cols[c]] = (int)pb.size();
+        if (same_fields && ia_of.count(cols[c])) pb.push_back(fa.mesh(ia_of[cols[c]]));
+        else pb.push_back(fb->mesh(next_own++));
       }
       // Pair list restricted to this block.
-      std::vector<const void*> pa, pb;
-      std::map<int, int> ia_of, ib_of;
-      for (auto& kv : fa) { ia_of[kv.first] = (int)pa.size(); pa.push_back(kv.second.data()); }
-      for (auto& kv : fb) { ib_of[kv.first] = (int)pb.size(); pb.push_back(kv.second->data()); }
       std::vector<int> ia, ib, where;
       for (int i = 0; i < dv.dim; i++) {
         if (!active[i]) continue;
@@ -427,7 +468,7 @@ void reduce_pairs(Engine& eng, trvb_ctx* grid, const DataVector& dv,
       if (ia.empty()) continue;
       std::vector<double> sums(2 * ia.size());
       dev::check(trvb_gram_reduce(grid, pa.data(), (int)pa.size(), pb.data(), (int)pb.size(),
-                                  G.view(), ia.data(), ib.data(), (int)ia.size(),
+                                  G, ia.data(), ib.data(), (int)ia.size(),
                                   sums.data()), "trvb_gram_reduce");
       for (size_t p = 0; p < ia.size(); p++) {
         out[where[p]] = cdouble(sums[2 * p], sums[2 * p + 1]);
@@ -479,7 +520,9 @@ trv::BispecMeasurements bispec_impl(
 
   // Common fields: delta n_00(k) and N_00(k).
   dev::Mesh dn_00 = eng.density_fluctuation(0, 0);
-  dev::Mesh N_00 = survey ? eng.quadratic_field(0, 0) : eng.quadratic_from_fluctuation(dn_00);
+  dev::Mesh N_00_own;
+  if (survey) N_00_own = eng.quadratic_field(0, 0);
+  const trvb_mesh N_00 = survey ? N_00_own.view() : eng.quadratic_view_of_fluctuation(dn_00);
   dev::profile_mark(c, "fields_00");
 
   trvm::SphericalBesselCalculator sj_a(params.ell1), sj_b(params.ell2);
@@ -524,11 +567,23 @@ trv::BispecMeasurements bispec_impl(
   cdouble Sbar_LM = 0.;
   int cached_M = 0; bool have_LM = false;
 
-  auto shell_field = [&](const dev::Mesh& src, int ell, int m, int bin, dev::Mesh& dst) {
-    dev::check(trvb_shell_ifft(c, sub, src.view(), ell, m, kbinning.bin_edges[bin],
-                               kbinning.bin_edges[bin + 1], 1. / double(nmodes[bin]),
-                               dst.view()), "trvb_shell_ifft");
-    trvs::count_ifft += 1;
+  // All shells of one (ell, m) in a single sparse pass + one batched IFFT.
+  auto shell_fields = [&](const dev::Mesh& src, int ell, int m, const std::vector<int>& bins,
+                          int layout, Slab& dst) {
+    std::vector<double> klo, khi, amp;
+    for (int b : bins) {
+      klo.push_back(kbinning.bin_edges[b]);
+      khi.push_back(kbinning.bin_edges[b + 1]);
+      amp.push_back(1. / double(nmodes[b]));   // F /= nmodes, S/field.cpp:1900-1905
+    }
+    dev::check(trvb_shell_ifft_batch(c, sub, src.view(), ell, m, klo.data(), khi.data(),
+                                     amp.data(), (int)bins.size(), dst.data(), layout),
+               "trvb_shell_ifft_batch");
+    trvs::count_ifft += (int)bins.size();
+  };
+  // A shell field is real when the filtered spectrum is Hermitian.
+  auto shell_is_real = [&](const dev::Mesh& src, int ell, int m) {
+    return src.layout() == TRVB_HALF && m == 0 && ell % 2 == 0;
   };
 
   for (const Term& t : terms) {
@@ -545,12 +600,16 @@ trv::BispecMeasurements bispec_impl(
       have_LM = true;
     }
     const dev::Mesh& dn_LM_ref = survey ? dn_LM : dn_00;
-    const dev::Mesh& N_LM_ref = survey ? N_LM : N_00;
+    const trvb_mesh N_LM_ref = survey ? N_LM.view() : N_00;
 
     // ---- raw bispectrum --------------------------------------------------
-    if (!(have_G && G_M == t.M)) {
+    // Real arithmetic throughout when G and both shell fields are real.
+    const bool real_path = dn_LM_ref.layout() == TRVB_HALF
+      && shell_is_real(dn_00, params.ell1, t.m1) && shell_is_real(dn_00, params.ell2, t.m2);
+    const int layout = real_path ? TRVB_REAL : TRVB_COMPLEX;
+    if (!(have_G && G_M == t.M && G.layout() == layout)) {
       // G_LM(x) = IFFT[delta n_LM(k) / W(k)] / V (S/threept.cpp:452-459).
-      G = dev::Mesh(eng.shared(), sub, TRVB_COMPLEX);
+      G = dev::Mesh(eng.shared(), sub, layout);
       dev::check(trvb_shell_ifft(c, sub, dn_LM_ref.view(), 0, 0, -1., -1., 1. / eng.vol(),
                                  G.view()), "trvb_shell_ifft (G)");
       trvs::count_ifft += 1;
@@ -559,9 +618,13 @@ trv::BispecMeasurements bispec_impl(
     const bool same_fields = (params.ell1 == params.ell2 && t.m1 == t.m2);
     std::vector<cdouble> bk_comp;
     reduce_pairs(
-      eng, sub, dv, active, same_fields, G,
-      [&](int bin, dev::Mesh& m) { shell_field(dn_00, params.ell1, t.m1, bin, m); },
-      [&](int bin, dev::Mesh& m) { shell_field(dn_00, params.ell2, t.m2, bin, m); },
+      eng, sub, dv, active, same_fields, G.view(),
+      [&](const std::vector<int>& bins, Slab& dst) {
+        shell_fields(dn_00, params.ell1, t.m1, bins, layout, dst);
+      },
+      [&](const std::vector<int>& bins, Slab& dst) {
+        shell_fields(dn_00, params.ell2, t.m2, bins, layout, dst);
+      },
       bk_comp);
     for (int i = 0; i < dv.dim; i++) {
       if (!active[i]) continue;
@@ -585,7 +648,7 @@ trv::BispecMeasurements bispec_impl(
         std::vector<double> kk(nb);
         pk.assign(2 * nb, 0.); sn.assign(2 * nb, 0.);
         const double S[2] = {Sbar_LM.real(), Sbar_LM.imag()};
-        dev::check(trvb_twopt_fourier(c, dn_00.view(), N_LM_ref.view(), S, ell, m,
+        dev::check(trvb_twopt_fourier(c, dn_00.view(), N_LM_ref, S, ell, m,
                                       kbinning.bin_edges.data(), kbinning.bin_centres.data(),
                                       nb, nm.data(), kk.data(), pk.data(), sn.data()),
                    "trvb_twopt_fourier");
@@ -604,9 +667,12 @@ trv::BispecMeasurements bispec_impl(
 
     // S|{i = j != k}: one xi mesh, all pairs in one pass.
     if (!have_xi) {
-      xi = dev::Mesh(eng.shared(), c, TRVB_COMPLEX);
       const double S[2] = {Sbar_LM.real(), Sbar_LM.imag()};
-      dev::check(trvb_shot_xi(c, dn_LM_ref.view(), N_00.view(), S, xi.view()), "trvb_shot_xi");
+      // Spectra of two real fields and a real amplitude: xi(x) is real.
+      const bool real_xi = dn_LM_ref.layout() == TRVB_HALF && N_00.layout == TRVB_HALF
+        && S[1] == 0.;
+      xi = dev::Mesh(eng.shared(), c, real_xi ? TRVB_REAL : TRVB_COMPLEX);
+      dev::check(trvb_shot_xi(c, dn_LM_ref.view(), N_00, S, xi.view()), "trvb_shot_xi");
       trvs::count_ifft += 1;
       have_xi = true;
       dev::profile_mark(c, "shot_xi");
@@ -669,7 +735,9 @@ trv::ThreePCFMeasurements threepcf_impl(
   const double vol_cell = eng.vol_cell();
 
   dev::Mesh dn_00 = eng.density_fluctuation(0, 0);
-  dev::Mesh N_00 = survey ? eng.quadratic_field(0, 0) : eng.quadratic_from_fluctuation(dn_00);
+  dev::Mesh N_00_own;
+  if (survey) N_00_own = eng.quadratic_field(0, 0);
+  const trvb_mesh N_00 = survey ? N_00_own.view() : eng.quadratic_view_of_fluctuation(dn_00);
 
   trvm::SphericalBesselCalculator sj_a(params.ell1), sj_b(params.ell2);
   eng.upload_sjl(sj_a);
@@ -696,9 +764,11 @@ trv::ThreePCFMeasurements threepcf_impl(
 
     // ---- shot noise first: it also yields r_eff and npairs ---------------
     if (!have_xi) {
-      xi = dev::Mesh(eng.shared(), c, TRVB_COMPLEX);
       const double S[2] = {Sbar_LM.real(), Sbar_LM.imag()};
-      dev::check(trvb_shot_xi(c, dn_LM_ref.view(), N_00.view(), S, xi.view()), "trvb_shot_xi");
+      const bool real_xi = dn_LM_ref.layout() == TRVB_HALF && N_00.layout == TRVB_HALF
+        && S[1] == 0.;
+      xi = dev::Mesh(eng.shared(), c, real_xi ? TRVB_REAL : TRVB_COMPLEX);
+      dev::check(trvb_shot_xi(c, dn_LM_ref.view(), N_00, S, xi.view()), "trvb_shot_xi");
       trvs::count_ifft += 1;
       have_xi = true;
     }
@@ -727,17 +797,20 @@ trv::ThreePCFMeasurements threepcf_impl(
       trvs::count_ifft += 1;
       have_G = true;
     }
-    auto sjl_field = [&](int ell, int m, int bin, dev::Mesh& dst) {
-      dev::check(trvb_sjl_ifft(c, dn_00.view(), ell, m, reff[bin], 1. / eng.vol(), dst.view()),
-                 "trvb_sjl_ifft");
-      trvs::count_ifft += 1;
+    auto sjl_fields = [&](int ell, int m, const std::vector<int>& bins, Slab& dst) {
+      for (size_t i = 0; i < bins.size(); i++) {
+        trvb_mesh out; out.data = dst.mesh((int)i); out.layout = TRVB_COMPLEX; out.k0_add = 0.;
+        dev::check(trvb_sjl_ifft(c, dn_00.view(), ell, m, reff[bins[i]], 1. / eng.vol(), out),
+                   "trvb_sjl_ifft");
+        trvs::count_ifft += 1;
+      }
     };
     const bool same_fields = (params.ell1 == params.ell2 && t.m1 == t.m2);
     std::vector<cdouble> zeta_comp;
     reduce_pairs(
-      eng, c, dv, active, same_fields, G,
-      [&](int bin, dev::Mesh& m) { sjl_field(params.ell1, t.m1, bin, m); },
-      [&](int bin, dev::Mesh& m) { sjl_field(params.ell2, t.m2, bin, m); },
+      eng, c, dv, active, same_fields, G.view(),
+      [&](const std::vector<int>& bins, Slab& dst) { sjl_fields(params.ell1, t.m1, bins, dst); },
+      [&](const std::vector<int>& bins, Slab& dst) { sjl_fields(params.ell2, t.m2, bins, dst); },
       zeta_comp);
     for (int i = 0; i < dv.dim; i++) {
       if (!active[i]) continue;
