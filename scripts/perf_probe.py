@@ -8,7 +8,7 @@ from triumvirate_b200 import core
 n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 10**7
 ng = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 nb = int(sys.argv[3]) if len(sys.argv) > 3 else 20
-L = 1000.
+L = float(sys.argv[4]) if len(sys.argv) > 4 else 1000.
 kmax = 0.005 + 0.01 * nb
 pos = np.random.default_rng(42).uniform(0., L, size=(3, n))
 dev = torch.device('cuda:0')

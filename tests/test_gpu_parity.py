@@ -316,8 +316,8 @@ def test_partitioned_pairs_sum_to_full(core):
 
 def test_gram_tma_and_cp_async_stages_agree(core, monkeypatch):
     """The pair reduction has two tile-staging engines (TMA bulk copies for
-    16-byte aligned meshes, cp.async otherwise); same accumulation order, so
-    the results are bit-identical.  Real (B_000) and complex (B_110) fields."""
+    16-byte aligned meshes, cp.async otherwise); they tile the cells differently,
+    so the sums agree to round-off.  Real (B_000) and complex (B_110) fields."""
     gen = np.random.default_rng(46)
     L, ng = 600., 96
     pos = gen.uniform(0., L, size=(3, 20000))
@@ -329,7 +329,8 @@ def test_gram_tma_and_cp_async_stages_agree(core, monkeypatch):
         monkeypatch.setenv("TRV_GRAM_NO_TMA", "1")
         b = core.threept("bispec", "sim", **kw)
         monkeypatch.delenv("TRV_GRAM_NO_TMA", raising=False)
-        assert np.array_equal(a["bk_raw"], b["bk_raw"]), degrees
+        err = np.abs(a["bk_raw"] - b["bk_raw"]) / np.abs(b["bk_raw"]).max()
+        assert err.max() < 1.e-13, degrees
 
 
 def test_subgrid_equals_full_grid_at_production_shape(core, monkeypatch):

@@ -155,14 +155,15 @@ struct SortedView {
 };
 
 __device__ __forceinline__ cplx particle_weight(const SortedView& c, long long i,
-                                                const double4& p, int kind, int L, int M) {
+                                                const double4& p, int kind, const YlmCoef& yc) {
+  const int L = yc.ell, M = yc.m;
   cplx out; out.im = 0.;
   const double w = p.w;
   if (kind == TRVB_W_UNIT) { out.re = 1.; return out; }
   if (kind == TRVB_W_W) { out.re = w; return out; }
   if (kind == TRVB_W_CUSTOM) { out.re = c.cw[2 * i]; out.im = c.cw[2 * i + 1]; return out; }
   cplx y; y.re = 1.; y.im = 0.;
-  if (!(L == 0 && M == 0)) y = ylm_reduced(L, M, c.lx[i], c.ly[i], c.lz[i]);
+  if (!(L == 0 && M == 0)) y = ylm_eval(yc, c.lx[i], c.ly[i], c.lz[i]);
   if (kind == TRVB_W_YLM_W) {
     out.re = y.re * w; out.im = y.im * w;
   } else if (kind == TRVB_W_CYLM_W2) {
@@ -338,6 +339,7 @@ template <int ORDER, bool COMPLEX>
 __global__ void __launch_bounds__(256)
 k_assign_scatter(SortedView c, GridDesc g, int shifted,
                  int kind, int L, int M, double scale, double* __restrict__ mesh) {
+  const YlmCoef yc = ylm_coef(L, M);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < c.n;
        i += (long long)gridDim.x * blockDim.x) {
     int ijk[3][ORDER];
@@ -346,7 +348,7 @@ k_assign_scatter(SortedView c, GridDesc g, int shifted,
     window_1d<ORDER>(grid_loc(p.x, g.n[0], g.L[0], shifted), g.n[0], ijk[0], win[0]);
     window_1d<ORDER>(grid_loc(p.y, g.n[1], g.L[1], shifted), g.n[1], ijk[1], win[1]);
     window_1d<ORDER>(grid_loc(p.z, g.n[2], g.L[2], shifted), g.n[2], ijk[2], win[2]);
-    cplx wt = particle_weight(c, i, p, kind, L, M);
+    cplx wt = particle_weight(c, i, p, kind, yc);
     const double bre = __dmul_rn(scale, wt.re);
     const double bim = COMPLEX ? __dmul_rn(scale, wt.im) : 0.;
 #pragma unroll
@@ -397,6 +399,7 @@ k_assign_coop(SortedView c, GridDesc g, int shifted,
   const int cz = COMPLEX ? (q >> 1) : q;
   const int comp = COMPLEX ? (q & 1) : 0;
   const long long nchunk = (c.n + 31) / 32;
+  const YlmCoef yc = ylm_coef(L, M);
   for (long long chunk = (long long)blockIdx.x * NW + warp; chunk < nchunk;
        chunk += (long long)gridDim.x * NW) {
     const long long i = chunk * 32 + lane;
@@ -414,7 +417,7 @@ k_assign_coop(SortedView c, GridDesc g, int shifted,
       window_1d<ORDER>(grid_loc(p.z, g.n[2], g.L[2], shifted), g.n[2], ijk, win);
 #pragma unroll
       for (int t = 0; t < ORDER; t++) { s_win[warp][lane][2 * ORDER + t] = win[t]; s_idx[warp][lane][2 * ORDER + t] = ijk[t]; }
-      const cplx wt = particle_weight(c, i, p, kind, L, M);
+      const cplx wt = particle_weight(c, i, p, kind, yc);
       s_wt[warp][lane][0] = __dmul_rn(scale, wt.re);
       s_wt[warp][lane][1] = __dmul_rn(scale, wt.im);
     }
@@ -498,8 +501,9 @@ k_assign_gather(SortedView c, const int* __restrict__ order,
   int ncand = 0;
   bool overflow = false;
 
+  const YlmCoef yc = ylm_coef(L, M);
   auto value_of = [&](int slot, double wx, double wy, double wz, double& vre, double& vim) {
-    cplx wt = particle_weight(c, slot, c.p4[slot], kind, L, M);
+    cplx wt = particle_weight(c, slot, c.p4[slot], kind, yc);
     // ((((inv_vol_cell * w) * Wx) * Wy) * Wz), S/field.cpp:1044-1048.
     double bre = __dmul_rn(pre, wt.re);
     if (scale != 1.) bre = __dmul_rn(bre, scale);

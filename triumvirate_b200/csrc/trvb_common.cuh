@@ -282,6 +282,79 @@ __device__ inline cplx ylm_reduced(int ell, int m, double x, double y, double z)
   return out;
 }
 
+// The same function with everything that depends on (l, m) only hoisted into
+// a coefficient set: per evaluation 3 square roots and 2 divisions remain, and
+// e^{i m phi} comes from (x + i y)/r_xy by repeated multiplication instead of
+// acos + sincos (identical in exact arithmetic: phi = acos(x/r_xy), reflected
+// for y < 0, means cos phi = x/r_xy and sin phi = y/r_xy).  Agreement with
+// ylm_reduced is at the 1e-15 level.
+constexpr int YLM_NREC = 8;   // recursion steps held in registers: l - |m| - 1 <= 8
+struct YlmCoef {
+  int ell, m, am, nrec;
+  bool generic;               // l beyond the register budget: use ylm_reduced
+  double pmm0;                // sqrt(1/4pi) prod_i -sqrt((2i+1)/(2i)), i = 1..|m|
+  double c1;                  // sqrt(2|m| + 3)
+  double a[YLM_NREC], b[YLM_NREC];
+  double norm;                // sqrt(4pi/(2l+1)) (-1)^((m-|m|)/2)
+};
+
+__host__ __device__ inline YlmCoef ylm_coef(int ell, int m) {
+  YlmCoef y;
+  const double PI = 3.14159265358979323846;
+  y.ell = ell; y.m = m; y.am = (m < 0) ? -m : m;
+  y.nrec = ell - y.am - 1; if (y.nrec < 0) y.nrec = 0;
+  y.generic = y.nrec > YLM_NREC;
+  y.pmm0 = sqrt(1. / (4. * PI));
+  for (int i = 1; i <= y.am; i++) y.pmm0 *= -sqrt((2. * i + 1.) / (2. * i));
+  y.c1 = sqrt(2. * y.am + 3.);
+  for (int t = 0; t < YLM_NREC; t++) {
+    const int ll = y.am + 2 + t;
+    y.a[t] = sqrt((4. * ll * ll - 1.) / ((double)ll * ll - (double)y.am * y.am));
+    y.b[t] = sqrt((((double)ll - 1.) * (ll - 1.) - (double)y.am * y.am)
+                  / (4. * (ll - 1.) * (ll - 1.) - 1.));
+  }
+  const double par = (((m - y.am) / 2) % 2 != 0) ? -1. : 1.;
+  y.norm = sqrt(4. * PI / (2. * ell + 1.)) * par;
+  return y;
+}
+
+__device__ __forceinline__ cplx ylm_eval(const YlmCoef& c, double x, double y, double z) {
+  cplx out;
+  if (c.ell == 0) { out.re = 1.; out.im = 0.; return out; }
+  if (c.generic) return ylm_reduced(c.ell, c.m, x, y, z);
+  const double eps = 1.e-9;
+  const double rxy2 = x * x + y * y;
+  const double r = sqrt(rxy2 + z * z);
+  if (r < eps) { out.re = 0.; out.im = 0.; return out; }
+  const double mu = z / r;
+  const double rxy = sqrt(rxy2);
+  double cs = 1., sn = 0.;   // phi = 0 when r_xy < eps
+  if (rxy >= eps) { const double ir = 1. / rxy; cs = x * ir; sn = y * ir; }
+  // (cs + i sn)^|m|
+  double er = 1., ei = 0.;
+  for (int i = 0; i < c.am; i++) { const double t = er * cs - ei * sn; ei = er * sn + ei * cs; er = t; }
+  const double somx2 = sqrt((1. - mu) * (1. + mu));
+  double pmm = c.pmm0;
+  for (int i = 0; i < c.am; i++) pmm *= somx2;
+  double plm = pmm;
+  if (c.ell > c.am) {
+    double pmmp1 = mu * c.c1 * pmm;
+    plm = pmmp1;
+#pragma unroll
+    for (int t = 0; t < YLM_NREC; t++) {
+      if (t < c.nrec) {
+        const double pll = c.a[t] * (mu * pmmp1 - c.b[t] * pmm);
+        pmm = pmmp1; pmmp1 = pll; plm = pll;
+      }
+    }
+  }
+  // conj(e^{i m phi}) P: e^{i m phi} = (er, sign(m) ei).
+  const double v = c.norm * plm;
+  out.re = v * er;
+  out.im = (c.m < 0) ? v * ei : -v * ei;
+  return out;
+}
+
 // Spherical Bessel j_l(x) evaluated directly (x >= split region, or any x for
 // l = 0): upward recurrence, stable for x >= l (S/maths.cpp:368-371 uses
 // gsl_sf_bessel_jl there).

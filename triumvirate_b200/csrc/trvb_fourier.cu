@@ -81,7 +81,7 @@ k_compensate(double2* __restrict__ f, GridDesc g, int layout, Tables tb) {
 // One Fourier mode of the filtered spectrum (S/field.cpp:1815-1847):
 // y_lm(khat) src(k) / W(k) * amp for the signed mode (mi, mj, mk).
 __device__ __forceinline__ double2 shell_mode(const KView& src, const GridDesc& gp,
-                                              const Tables& tb, int ell, int m,
+                                              const Tables& tb, const YlmCoef& yc,
                                               int mi, int mj, int mk, double kx, double ky,
                                               double kz, double amp) {
   const int ip = mi >= 0 ? mi : mi + gp.n[0];
@@ -90,7 +90,7 @@ __device__ __forceinline__ double2 shell_mode(const KView& src, const GridDesc& 
   cplx fk = kload(src, ip, jp, kp);
   const double rw = 1. / window_at(tb, gp.order, ip, jp, kp);
   fk.re *= rw; fk.im *= rw;
-  const cplx y = ylm_reduced(ell, m, kx, ky, kz);
+  const cplx y = ylm_eval(yc, kx, ky, kz);
   const cplx v = cmul(y, fk);
   return make_double2(v.re * amp, v.im * amp);
 }
@@ -103,6 +103,7 @@ k_shell_spectrum(KView src, GridDesc gp, GridDesc gs, Tables tb, int ell, int m,
                  double klo, double khi, int use_shell, double amp, int n2s,
                  double2* __restrict__ dst) {
   const bool same = gs.n[0] == gp.n[0] && gs.n[1] == gp.n[1] && gs.n[2] == gp.n[2];
+  const YlmCoef yc = ylm_coef(ell, m);
   for_each_cell(gs.n[0], gs.n[1], n2s, [&](int is, int js, int ks, long long t) {
     const int mi = signed_index(is, gs.n[0]), mj = signed_index(js, gs.n[1]);
     const int mk = signed_index(ks, gs.n[2]);
@@ -118,7 +119,7 @@ k_shell_spectrum(KView src, GridDesc gp, GridDesc gs, Tables tb, int ell, int m,
       const double kz = __dmul_rn((double)mk, gp.dk[2]);
       const double kmag = vec3_norm_exact(kx, ky, kz);
       if (!use_shell || (klo <= kmag && kmag < khi)) {
-        out = shell_mode(src, gp, tb, ell, m, mi, mj, mk, kx, ky, kz, amp);
+        out = shell_mode(src, gp, tb, yc, mi, mj, mk, kx, ky, kz, amp);
       }
     }
     dst[t] = out;
@@ -137,6 +138,7 @@ __global__ void __launch_bounds__(256)
 k_shell_scatter(KView src, GridDesc gp, GridDesc gs, Tables tb, int ell, int m,
                 int lo0, int lo1, int lo2, int c0, int c1, int c2,
                 ShellBatch sb, int n2s, long long bin_stride, double2* __restrict__ dst) {
+  const YlmCoef yc = ylm_coef(ell, m);
   for_each_cell(c0, c1, c2, [&](int a, int b, int c, long long) {
     const int mi = lo0 + a, mj = lo1 + b, mk = lo2 + c;
     // HALF destination: mk >= 0 stored, plus the Nyquist plane (signed -n/2).
@@ -150,7 +152,7 @@ k_shell_scatter(KView src, GridDesc gp, GridDesc gs, Tables tb, int ell, int m,
     for (int q = 0; q < sb.nbins; q++) {
       if (!(sb.klo[q] <= kmag && kmag < sb.khi[q])) continue;
       if (!loaded) {
-        base = shell_mode(src, gp, tb, ell, m, mi, mj, mk, kx, ky, kz, 1.);
+        base = shell_mode(src, gp, tb, yc, mi, mj, mk, kx, ky, kz, 1.);
         loaded = true;
       }
       const int is = mi >= 0 ? mi : mi + gs.n[0];
@@ -167,6 +169,7 @@ k_shell_scatter(KView src, GridDesc gp, GridDesc gs, Tables tb, int ell, int m,
 __global__ void __launch_bounds__(256)
 k_sjl_spectrum(KView src, GridDesc g, Tables tb, SjlView sj, int ell, int m,
                double r, double amp, double2* __restrict__ dst) {
+  const YlmCoef yc = ylm_coef(ell, m);
   for_each_cell(g.n[0], g.n[1], g.n[2], [&](int i, int j, int k, long long t) {
     const double kx = __dmul_rn((double)signed_index(i, g.n[0]), g.dk[0]);
     const double ky = __dmul_rn((double)signed_index(j, g.n[1]), g.dk[1]);
@@ -175,7 +178,7 @@ k_sjl_spectrum(KView src, GridDesc g, Tables tb, SjlView sj, int ell, int m,
     cplx fk = kload(src, i, j, k);
     const double rw = 1. / window_at(tb, g.order, i, j, k);
     fk.re *= rw; fk.im *= rw;
-    cplx y = ylm_reduced(ell, m, kx, ky, kz);
+    cplx y = ylm_eval(yc, kx, ky, kz);
     cplx v = cmul(y, fk);
     const double jl = sjl_eval(sj, __dmul_rn(kmag, r));
     dst[t] = make_double2(jl * v.re * amp, jl * v.im * amp);
@@ -393,19 +396,26 @@ extern "C" int trvb_shell_ifft_batch(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh src
   const bool real_out = dst_layout == TRVB_REAL;
   const int n2s = real_out ? gs.nh : gs.n[2];
   const long long bin_stride = (long long)gs.n[0] * gs.n[1] * n2s;   // complex elements
-  const size_t spec_bytes = sizeof(double2) * (size_t)bin_stride * nbins;
-  void* spec = dst;
-  if (real_out) TRVB_CUDA(trvb_dev_alloc_raw(ctx, &spec, spec_bytes));
-  TRVB_CUDA(cudaMemsetAsync(spec, 0, spec_bytes, ctx->stream));
+  const size_t dst_stride = trvb_mesh_bytes(sub, dst_layout);
+  // Sub-batches bound the transient half-spectrum slab (and cuFFT's work
+  // area) to a few GiB whatever the number of bins and the grid size.
+  const size_t spec_bin_bytes = sizeof(double2) * (size_t)bin_stride;
+  int maxb = (int)std::max<size_t>(1, ((size_t)6 << 30) / spec_bin_bytes);
+  maxb = std::min(maxb, nbins);
+  void* spec_tmp = nullptr;
+  if (real_out) TRVB_CUDA(trvb_dev_alloc_raw(ctx, &spec_tmp, spec_bin_bytes * maxb));
   // Low-|k| cube that holds every shell; clipped to what the sub grid represents.
   double kmax = 0.;
   for (int q = 0; q < nbins; q++) kmax = std::max(kmax, khi[q]);
   int lo[3], cnt[3];
   for (int a = 0; a < 3; a++) {
-    long long mc = (long long)std::floor(kmax / gp.dk[a]) + 1;
-    const long long rep = (sub == ctx) ? (gs.n[a] - gs.n[a] / 2) : (gs.n[a] - 1) / 2;
-    int lo_a = (int)std::max<long long>(-mc, (sub == ctx) ? -(long long)(gs.n[a] - gs.n[a] / 2) : -rep);
-    int hi_a = (int)std::min<long long>(mc, (sub == ctx) ? (long long)(gs.n[a] / 2 - 1) : rep);
+    const long long mc = (long long)std::floor(kmax / gp.dk[a]) + 1;
+    // Signed indices present on the destination grid: the full range when it is
+    // the parent grid itself, else strictly inside its Nyquist frequency.
+    const long long smin = (sub == ctx) ? -(long long)(gs.n[a] - gs.n[a] / 2) : -(long long)((gs.n[a] - 1) / 2);
+    const long long smax = (sub == ctx) ? (long long)(gs.n[a] / 2 - 1) : (long long)((gs.n[a] - 1) / 2);
+    int lo_a = (int)std::max<long long>(-mc, smin);
+    int hi_a = (int)std::min<long long>(mc, smax);
     if (gs.n[a] == 1) { lo_a = 0; hi_a = 0; }
     lo[a] = lo_a; cnt[a] = hi_a - lo_a + 1;
   }
@@ -418,26 +428,33 @@ extern "C" int trvb_shell_ifft_batch(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh src
   // Pageable source: the copy is staged before cudaMemcpyAsync returns.
   TRVB_CUDA(cudaMemcpyAsync(d_par, h_par.data(), sizeof(double) * h_par.size(),
                             cudaMemcpyHostToDevice, ctx->stream));
-  ShellBatch sb; sb.klo = d_par; sb.khi = d_par + nbins; sb.amp = d_par + 2 * nbins;
-  sb.nbins = nbins;
   const RowLaunch rl = row_launch(ctx->num_sms, cnt[0], cnt[1], cnt[2]);
-  k_shell_scatter<<<rl.grid, rl.block, 0, ctx->stream>>>(
-    kview_of(ctx, src), gp, gs, tables_of(ctx), ell, m, lo[0], lo[1], lo[2], cnt[0], cnt[1],
-    cnt[2], sb, n2s, bin_stride, (double2*)spec);
-  TRVB_LAUNCH_CHECK();
-  trvb_dev_free_raw(ctx, d_par);
-  cufftHandle plan;
-  int st = get_batch_plan(sub, real_out ? CUFFT_Z2D : CUFFT_Z2Z, nbins, &plan);
-  if (st) { if (real_out) trvb_dev_free_raw(ctx, spec); return st; }
-  if (real_out) {
-    TRVB_CUFFT(cufftExecZ2D(plan, (cufftDoubleComplex*)spec, (cufftDoubleReal*)dst));
-    trvb_dev_free_raw(ctx, spec);
-  } else {
-    TRVB_CUFFT(cufftExecZ2Z(plan, (cufftDoubleComplex*)dst, (cufftDoubleComplex*)dst,
-                            CUFFT_INVERSE));
+  int st = 0;
+  for (int q0 = 0; q0 < nbins && st == 0; q0 += maxb) {
+    const int nq = std::min(maxb, nbins - q0);
+    void* out = static_cast<char*>(dst) + dst_stride * (size_t)q0;
+    void* spec = real_out ? spec_tmp : out;
+    TRVB_CUDA(cudaMemsetAsync(spec, 0, spec_bin_bytes * nq, ctx->stream));
+    ShellBatch sb; sb.klo = d_par + q0; sb.khi = d_par + nbins + q0; sb.amp = d_par + 2 * nbins + q0;
+    sb.nbins = nq;
+    k_shell_scatter<<<rl.grid, rl.block, 0, ctx->stream>>>(
+      kview_of(ctx, src), gp, gs, tables_of(ctx), ell, m, lo[0], lo[1], lo[2], cnt[0], cnt[1],
+      cnt[2], sb, n2s, bin_stride, (double2*)spec);
+    TRVB_LAUNCH_CHECK();
+    cufftHandle plan;
+    st = get_batch_plan(sub, real_out ? CUFFT_Z2D : CUFFT_Z2Z, nq, &plan);
+    if (st) break;
+    if (real_out) {
+      TRVB_CUFFT(cufftExecZ2D(plan, (cufftDoubleComplex*)spec, (cufftDoubleReal*)out));
+    } else {
+      TRVB_CUFFT(cufftExecZ2Z(plan, (cufftDoubleComplex*)out, (cufftDoubleComplex*)out,
+                              CUFFT_INVERSE));
+    }
+    g_trvb_fft_execs++;
   }
-  g_trvb_fft_execs++;
-  return 0;
+  trvb_dev_free_raw(ctx, d_par);
+  if (real_out) trvb_dev_free_raw(ctx, spec_tmp);
+  return st;
 }
 
 extern "C" int trvb_sjl_ifft(trvb_ctx* ctx, trvb_mesh src, int ell, int m, double r,

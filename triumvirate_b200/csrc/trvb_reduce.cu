@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 namespace {
 
@@ -124,7 +125,7 @@ struct ShotLoader {
   GridDesc g;
   SjlView sja, sjb;
   const double* ka; const double* kb;
-  int la, ma, lb, mb;
+  YlmCoef ya_c, yb_c;
   __device__ __forceinline__ void rvec(long long cell, double& rx, double& ry, double& rz,
                                        double& r) const {
     const int k = (int)(cell % g.n[2]);
@@ -143,8 +144,8 @@ struct ShotLoader {
   __device__ __forceinline__ double2 hb(int ib, long long cell) const {
     double rx, ry, rz, r; rvec(cell, rx, ry, rz, r);
     const double jb = sjl_eval(sjb, kb[ib] * r);
-    cplx ya = ylm_reduced(la, ma, rx, ry, rz);
-    cplx yb = ylm_reduced(lb, mb, rx, ry, rz);
+    cplx ya = ylm_eval(ya_c, rx, ry, rz);
+    cplx yb = ylm_eval(yb_c, rx, ry, rz);
     cplx yy = cmul(ya, yb);
     double2 x = xload(xi, cell);
     cplx xv; xv.re = x.x; xv.im = x.y;
@@ -165,6 +166,7 @@ __global__ void __launch_bounds__(256)
 k_shot_radial_hist(XView xi, GridDesc g, int la, int ma, int lb,
                    int mb, double* __restrict__ hist) {
   const int n0 = g.n[0], n1 = g.n[1], n2 = g.n[2];
+  const YlmCoef ya_c = ylm_coef(la, ma), yb_c = ylm_coef(lb, mb);
   for_each_cell(n0 / 2 + 1, n1 / 2 + 1, n2 / 2 + 1, [&](int ci, int cj, int ck, long long) {
     const int pi = ci ? n0 - ci : 0, pj = cj ? n1 - cj : 0, pk = ck ? n2 - ck : 0;
     int ii[2] = {ci, pi}, jj[2] = {cj, pj}, kk[2] = {ck, pk};
@@ -187,7 +189,7 @@ k_shot_radial_hist(XView xi, GridDesc g, int la, int ma, int lb,
       const double rx = (double)signed_index(ii[a], n0) * g.dr[0];
       const double ry = (double)signed_index(jj[b], n1) * g.dr[1];
       const double rz = (double)signed_index(kk[c], n2) * g.dr[2];
-      const cplx yy = cmul(ylm_reduced(la, ma, rx, ry, rz), ylm_reduced(lb, mb, rx, ry, rz));
+      const cplx yy = cmul(ylm_eval(ya_c, rx, ry, rz), ylm_eval(yb_c, rx, ry, rz));
       cplx xv; xv.re = x[e].x; xv.im = x[e].y;
       const cplx v = cmul(xv, yy);
       re += v.re; im += v.im;
@@ -451,14 +453,13 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, un
 // CURRENT stage, reduces its 4 x 4 pair blocks from it, and a block barrier
 // hands the stage back.  No address arithmetic or staging instructions are
 // spent by the compute warps.  Requires 16-byte aligned meshes.
-template <class VT, int TPW>
+template <class VT, int TPW, int T>
 __global__ void __launch_bounds__(GRAM_THREADS, 1)
 k_gram_fields_tma(const VT* const* __restrict__ A, const VT* const* __restrict__ B,
                   const VT* __restrict__ G, const int* __restrict__ sel_a, int na,
                   const int* __restrict__ sel_b, int nb, long long ncells,
                   const int* __restrict__ blk_a, const int* __restrict__ blk_b, int nblk,
                   double* __restrict__ partial) {
-  constexpr int T = GRAM_T;
   extern __shared__ __align__(128) double2 smem_raw[];
   const int rows = na + nb + 1;
   VT* buf0 = reinterpret_cast<VT*>(smem_raw);
@@ -565,10 +566,31 @@ int launch_gram_chunk(trvb_ctx* ctx, const Loader& ld, const int* d_sel_a, int n
       + sizeof(void*) * (size_t)(na + nb + 1);
     TRVB_REQUIRE(smem <= 200 * 1024, "gram reduce: %d + %d fields exceed the shared-memory stage", na, nb);
     if (ld.aligned16) {
-      TRVB_CUDA(cudaFuncSetAttribute(k_gram_fields_tma<VT, TPW>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_gram_fields_tma<VT, TPW><<<nblocks, GRAM_THREADS, smem, ctx->stream>>>(
-        ld.A, ld.B, ld.G, d_sel_a, na, d_sel_b, nb, ncells, d_blk_a, d_blk_b, nblk, d_partial);
+      // Longest rows (cells per bulk copy) whose two stages fit in shared memory:
+      // the TMA engine is fed per copy, so 2 KB rows beat 512 B rows.
+      const size_t fixed = 16 + sizeof(void*) * (size_t)(na + nb + 1);
+      auto stage_bytes = [&](int t) { return sizeof(VT) * 2 * (size_t)(na + nb + 1) * t + fixed; };
+      auto launch_t = [&](auto tag) -> int {
+        constexpr int TT = decltype(tag)::value;
+        const size_t sm = stage_bytes(TT);
+        const long long nt = (ncells + TT - 1) / TT;
+        const int nbk = (int)std::min<long long>(nt, (long long)nblocks);
+        TRVB_CUDA(cudaFuncSetAttribute(k_gram_fields_tma<VT, TPW, TT>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        // Partials are laid out for `nblocks` blocks: idle ones must write zeros.
+        if (nbk < nblocks) {
+          TRVB_CUDA(cudaMemsetAsync(d_partial, 0, sizeof(double) * 2 * GRAM_B * GRAM_B * (size_t)nblocks * nblk,
+                                    ctx->stream));
+        }
+        k_gram_fields_tma<VT, TPW, TT><<<nbk, GRAM_THREADS, sm, ctx->stream>>>(
+          ld.A, ld.B, ld.G, d_sel_a, na, d_sel_b, nb, ncells, d_blk_a, d_blk_b, nblk, d_partial);
+        return 0;
+      };
+      int st = 0;
+      if (stage_bytes(256) <= 200 * 1024) st = launch_t(std::integral_constant<int, 256>());
+      else if (stage_bytes(128) <= 200 * 1024) st = launch_t(std::integral_constant<int, 128>());
+      else st = launch_t(std::integral_constant<int, 64>());
+      if (st) return st;
     } else {
       TRVB_CUDA(cudaFuncSetAttribute(k_gram_fields<VT, TPW>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -771,6 +793,7 @@ k_twopt_fourier(KView fa, KView fb, GridDesc g, Tables tb, Cube cube,
                 int ell, int m, double* __restrict__ partial) {
   __shared__ double sm[32];
   const BinRule rule = rules[blockIdx.y];
+  const YlmCoef yc = ylm_coef(ell, m);
   double v[6] = {0., 0., 0., 0., 0., 0.};
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < cube.total;
        t += (long long)gridDim.x * blockDim.x) {
@@ -790,7 +813,7 @@ k_twopt_fourier(KView fa, KView fb, GridDesc g, Tables tb, Cube cube,
     const double c1 = tb.alias[0][i] * tb.alias[1][j] * tb.alias[2][k];
     cplx pk; pk.re = (a.re * b.re + a.im * b.im) / c1; pk.im = (a.im * b.re - a.re * b.im) / c1;
     cplx sn; sn.re = (S_re * c1) / c1; sn.im = (S_im * c1) / c1;
-    const cplx y = ylm_reduced(ell, m, kx, ky, kz);
+    const cplx y = ylm_eval(yc, kx, ky, kz);
     pk = cmul(pk, y); sn = cmul(sn, y);
     v[0] += 1.; v[1] += kmag; v[2] += pk.re; v[3] += pk.im; v[4] += sn.re; v[5] += sn.im;
   }
@@ -815,23 +838,31 @@ k_shot_spectrum(KView fa, KView fb, GridDesc g, Tables tb, double S_re, double S
   });
 }
 
+// Cells visited: the cube of signed offsets |i| dr <= r_max (bins are
+// spherical shells, so the corners of the mesh never contribute).
 __global__ void __launch_bounds__(256)
-k_shot_3pcf_bin(XView xi, GridDesc g,
+k_shot_3pcf_bin(XView xi, GridDesc g, Cube cube,
                 const BinRule* __restrict__ rules, int la, int ma, int lb, int mb,
                 double* __restrict__ partial) {
   __shared__ double sm[32];
   const BinRule rule = rules[blockIdx.y];
+  const YlmCoef ya_c = ylm_coef(la, ma), yb_c = ylm_coef(lb, mb);
   double v[4] = {0., 0., 0., 0.};
   // 1-D block (blockDim.y == 1): rows over blockIdx.x, last axis over threads.
-  for_each_cell(g.n[0], g.n[1], g.n[2], [&](int i, int j, int k, long long t) {
-    const double rx = __dmul_rn((double)signed_index(i, g.n[0]), g.dr[0]);
-    const double ry = __dmul_rn((double)signed_index(j, g.n[1]), g.dr[1]);
-    const double rz = __dmul_rn((double)signed_index(k, g.n[2]), g.dr[2]);
+  for_each_cell(cube.cnt[0], cube.cnt[1], cube.cnt[2], [&](int a, int b, int c, long long) {
+    const int si = cube.lo[0] + a, sj = cube.lo[1] + b, sk = cube.lo[2] + c;
+    // S/field.cpp:546-553: i*dr or (i-n)*dr.
+    const double rx = __dmul_rn((double)si, g.dr[0]);
+    const double ry = __dmul_rn((double)sj, g.dr[1]);
+    const double rz = __dmul_rn((double)sk, g.dr[2]);
     const double r = vec3_norm_exact(rx, ry, rz);
     if (!in_bin(rule, r)) return;
-    const cplx ya = ylm_reduced(la, ma, rx, ry, rz);
-    const cplx yb = ylm_reduced(lb, mb, rx, ry, rz);
-    const double2 x = xload(xi, t);
+    const int i = si >= 0 ? si : si + g.n[0];
+    const int j = sj >= 0 ? sj : sj + g.n[1];
+    const int k = sk >= 0 ? sk : sk + g.n[2];
+    const cplx ya = ylm_eval(ya_c, rx, ry, rz);
+    const cplx yb = ylm_eval(yb_c, rx, ry, rz);
+    const double2 x = xload(xi, ((long long)i * g.n[1] + j) * g.n[2] + k);
     cplx xv; xv.re = x.x; xv.im = x.y;
     const cplx val = cmul(xv, cmul(ya, yb));
     v[0] += 1.; v[1] += r; v[2] += val.re; v[3] += val.im;
@@ -1043,7 +1074,7 @@ extern "C" int trvb_shot_bispec_reduce(trvb_ctx* ctx, trvb_mesh xi, int la, int 
     ld.xi = xv; ld.g = g;
     ld.sja = sja; ld.sjb = sjb;
     ld.ka = d_k; ld.kb = d_k + ua.size();
-    ld.la = la; ld.ma = ma; ld.lb = lb; ld.mb = mb;
+    ld.ya_c = ylm_coef(la, ma); ld.yb_c = ylm_coef(lb, mb);
     st = run_gram(ctx, ld, (int)ua.size(), (int)ub.size(), g.nmesh, ia.data(), ib.data(), npairs, out);
   }
   trvb_dev_free_raw(ctx, d_k);
@@ -1157,10 +1188,20 @@ extern "C" int trvb_shot_3pcf_bin(trvb_ctx* ctx, trvb_mesh xi, int la, int ma, i
   make_rules(edges, nbins, 1, 1., 100000, rules);   // S/field.cpp:3095-3096
   const GridDesc g = ctx->g;
   XView d_xi; d_xi.p = (const double*)xi.data; d_xi.cplx = xi.layout == TRVB_COMPLEX;
+  // Real-space analogue of cube_for: signed offsets with |i| dr <= r_max + slack.
+  Cube cube; cube.total = 1;
+  for (int a = 0; a < 3; a++) {
+    const int n = g.n[a];
+    const int smin = -(n - n / 2), smax = n / 2 - 1;
+    const long long mc = (long long)std::floor((edges[nbins] + 2.) / g.dr[a]) + 2;
+    int lo = (int)std::max<long long>(smin, -mc), hi = (int)std::min<long long>(smax, mc);
+    if (n == 1) { lo = 0; hi = 0; }
+    cube.lo[a] = lo; cube.cnt[a] = hi - lo + 1; cube.total *= cube.cnt[a];
+  }
   std::vector<double> host;
-  int st = run_binned<4>(ctx, rules, g.nmesh,
+  int st = run_binned<4>(ctx, rules, cube.total,
     [&](dim3 grid, const BinRule* d_rules, double* d_partial) {
-      k_shot_3pcf_bin<<<grid, 256, 0, ctx->stream>>>(d_xi, g, d_rules, la, ma, lb, mb, d_partial);
+      k_shot_3pcf_bin<<<grid, 256, 0, ctx->stream>>>(d_xi, g, cube, d_rules, la, ma, lb, mb, d_partial);
     }, host);
   if (st) return st;
   const double norm_factors = 1 / g.vol_cell * parity;   // S/field.cpp:3181-3182

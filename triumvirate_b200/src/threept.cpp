@@ -19,6 +19,7 @@
 #include <map>
 #include <memory>
 #include <set>
+#include <tuple>
 
 namespace trvs = trv::sys;
 namespace trvm = trv::maths;
@@ -162,26 +163,45 @@ DataVector make_data_vector(const trv::ParameterSet& params, int num_bins) {
   return dv;
 }
 
-/// Transform length >= n that minimises the measured cuFFT cost per 3-D
-/// transform among nearby 7-smooth sizes.  On B200 (fp64, batched Z2Z/Z2D)
-/// lengths 2^a 3^b with a >= 4 run at ~15 ns per 1000 cells, other 5-smooth
-/// multiples of 16 ~20 % slower, lengths with odd or factor-7 structure
-/// ~1.7x slower (135^3: 70 us vs 144^3: 44 us).
+/// Measured cost of a batched fp64 3-D cuFFT transform (Z2D, out of place) on
+/// B200, in ns per 1000 cells, for every 7-smooth length 32..735
+/// (lab/fft_sweep.cu, cuFFT 11.4; profiles/r01_fft_sweep.txt).  Lengths that
+/// factor as a^2 / a^3 of a small radix (100, 128, 144, 256, 343, 512, 729)
+/// run at 9-12; most others at 14-24.
+const struct { int n; double ns_per_kcell; } kFftCost[] = {
+  {32, 31.2}, {35, 27.2}, {36, 21.0}, {40, 21.6}, {42, 20.1}, {45, 19.7}, {48, 16.8},
+  {49, 14.2}, {50, 18.1}, {54, 14.6}, {56, 12.0}, {60, 14.2}, {63, 12.6}, {64, 12.7},
+  {70, 12.7}, {72, 13.0}, {75, 21.9}, {80, 14.2}, {81, 9.9}, {84, 12.9}, {90, 10.9},
+  {96, 16.9}, {98, 18.7}, {100, 9.6}, {105, 18.9}, {108, 11.2}, {112, 13.9}, {120, 11.9},
+  {125, 11.6}, {126, 19.0}, {128, 9.9}, {135, 19.2}, {140, 16.8}, {144, 8.8}, {147, 19.2},
+  {150, 14.4}, {160, 10.3}, {162, 20.0}, {168, 17.7}, {175, 14.9}, {180, 17.3}, {189, 20.6},
+  {192, 10.5}, {196, 10.5}, {200, 18.5}, {210, 15.6}, {216, 10.5}, {224, 19.0}, {225, 16.9},
+  {240, 17.4}, {243, 10.4}, {245, 18.6}, {250, 16.0}, {252, 14.8}, {256, 9.2}, {270, 13.1},
+  {280, 19.4}, {288, 14.9}, {294, 23.6}, {300, 22.1}, {315, 15.8}, {320, 15.8}, {324, 14.4},
+  {336, 18.9}, {343, 11.2}, {350, 22.2}, {360, 15.7}, {375, 19.3}, {378, 15.2}, {384, 16.4},
+  {392, 17.0}, {400, 23.7}, {405, 23.1}, {420, 22.2}, {432, 20.0}, {441, 14.9}, {448, 19.3},
+  {450, 17.4}, {480, 22.4}, {486, 30.2}, {490, 20.6}, {500, 16.5}, {504, 14.2}, {512, 10.5},
+  {525, 24.4}, {540, 22.1}, {560, 20.4}, {567, 28.0}, {576, 22.1}, {588, 23.3}, {600, 23.9},
+  {625, 14.4}, {630, 28.7}, {640, 18.5}, {648, 18.9}, {672, 24.2}, {675, 22.7}, {686, 20.0},
+  {700, 21.9}, {720, 23.7}, {729, 12.5}, {735, 30.6}
+};
+
+/// Transform length >= n with the least measured cost n^3 * cost(n) among the
+/// candidates up to 1.4 n; beyond the table, the next 5-smooth multiple of 16.
 int next_fft_size(int n) {
   int best = 0; double best_cost = 0.;
-  const int lo = std::max(n, 2), hi = std::max(lo + 16, (int)(1.35 * lo));
-  for (int v = lo; v <= hi; v++) {
-    int r = v, n5 = 0, n7 = 0;
-    while (r % 2 == 0) r /= 2;
-    while (r % 3 == 0) r /= 3;
-    while (r % 5 == 0) { r /= 5; n5++; }
-    while (r % 7 == 0) { r /= 7; n7++; }
-    if (r != 1) continue;
-    double penalty = (v % 16 == 0 && n7 == 0) ? 1. + 0.2 * n5 : 1.7;
-    const double cost = penalty * double(v) * double(v) * double(v);
-    if (best == 0 || cost < best_cost) { best = v; best_cost = cost; }
+  const int lo = std::max(n, 2), hi = std::max(lo + 16, (int)(1.4 * lo));
+  for (const auto& e : kFftCost) {
+    if (e.n < lo || e.n > hi) continue;
+    const double cost = e.ns_per_kcell * double(e.n) * double(e.n) * double(e.n);
+    if (best == 0 || cost < best_cost) { best = e.n; best_cost = cost; }
   }
-  return best;
+  if (best) return best;
+  for (int v = (lo + 15) / 16 * 16;; v += 16) {
+    int r = v;
+    for (int p : {2, 3, 5}) while (r % p == 0) r /= p;
+    if (r == 1) return v;
+  }
 }
 
 std::vector<int> distinct_sorted(const std::vector<int>& v) {
@@ -395,13 +415,13 @@ class Slab {
 };
 
 /// Blocked all-pairs reduction: out[idx] = sum_x A_{row(idx)} B_{col(idx)} G
-/// for the entries of `dv` selected by `active`.  `make_a(bins, slab)` and
-/// `make_b(bins, slab)` fill slab mesh i (layout of G, on `grid`) with the
-/// field of bin bins[i].
+/// for the entries of `dv` selected by `active`.  `get_a(bins)` and
+/// `get_b(bins)` return a slab whose mesh i (layout of G, on `grid`) holds the
+/// field of bin bins[i]; they may hand back a slab cached from an earlier term.
 template <class MakeA, class MakeB>
 void reduce_pairs(Engine& eng, trvb_ctx* grid, const DataVector& dv,
                   const std::vector<char>& active, bool same_fields,
-                  trvb_mesh G, MakeA make_a, MakeB make_b,
+                  trvb_mesh G, MakeA get_a, MakeB get_b,
                   std::vector<cdouble>& out) {
   out.assign(dv.dim, cdouble(0., 0.));
   std::vector<int> rows_all, cols_all;
@@ -432,8 +452,8 @@ void reduce_pairs(Engine& eng, trvb_ctx* grid, const DataVector& dv,
   for (size_t r0 = 0; r0 < rows.size(); r0 += block_r) {
     const size_t r1 = std::min(rows.size(), r0 + block_r);
     const std::vector<int> bins_a(rows.begin() + r0, rows.begin() + r1);
-    Slab fa(eng.shared(), grid, G.layout, (int)bins_a.size());
-    make_a(bins_a, fa);
+    const std::shared_ptr<Slab> fa_holder = get_a(bins_a);
+    const Slab& fa = *fa_holder;
     std::map<int, int> ia_of;
     std::vector<const void*> pa;
     for (size_t i = 0; i < bins_a.size(); i++) { ia_of[bins_a[i]] = (int)i; pa.push_back(fa.mesh((int)i)); }
@@ -444,11 +464,8 @@ void reduce_pairs(Engine& eng, trvb_ctx* grid, const DataVector& dv,
       for (size_t c = c0; c < c1; c++) {
         if (!(same_fields && ia_of.count(cols[c]))) bins_b.push_back(cols[c]);
       }
-      std::unique_ptr<Slab> fb;
-      if (!bins_b.empty()) {
-        fb.reset(new Slab(eng.shared(), grid, G.layout, (int)bins_b.size()));
-        make_b(bins_b, *fb);
-      }
+      std::shared_ptr<Slab> fb;
+      if (!bins_b.empty()) fb = get_b(bins_b);
       std::map<int, int> ib_of;
       std::vector<const void*> pb;
       int next_own = 0;
@@ -581,6 +598,21 @@ trv::BispecMeasurements bispec_impl(
                "trvb_shell_ifft_batch");
     trvs::count_ifft += (int)bins.size();
   };
+  // Shell fields depend on (ell, m, bin) only: terms that share a side (e.g.
+  // the (l2, m2) = (0, 0) side of every B_202 term) reuse its slab while
+  // device memory is plentiful.
+  typedef std::tuple<int, int, int, std::vector<int> > SlabKey;
+  std::map<SlabKey, std::shared_ptr<Slab> > slab_cache;
+  auto shell_slab = [&](int ell, int m, const std::vector<int>& bins, int layout) {
+    const SlabKey key(ell, m, layout, bins);
+    auto hit = slab_cache.find(key);
+    if (hit != slab_cache.end()) return hit->second;
+    auto slab = std::make_shared<Slab>(eng.shared(), sub, layout, (int)bins.size());
+    shell_fields(dn_00, ell, m, bins, layout, *slab);
+    const size_t bytes = trvb_mesh_bytes(sub, layout) * bins.size();
+    if (terms.size() > 1 && eng.mesh_capacity(bytes) >= 6) slab_cache[key] = slab;
+    return slab;
+  };
   // A shell field is real when the filtered spectrum is Hermitian.
   auto shell_is_real = [&](const dev::Mesh& src, int ell, int m) {
     return src.layout() == TRVB_HALF && m == 0 && ell % 2 == 0;
@@ -619,12 +651,8 @@ trv::BispecMeasurements bispec_impl(
     std::vector<cdouble> bk_comp;
     reduce_pairs(
       eng, sub, dv, active, same_fields, G.view(),
-      [&](const std::vector<int>& bins, Slab& dst) {
-        shell_fields(dn_00, params.ell1, t.m1, bins, layout, dst);
-      },
-      [&](const std::vector<int>& bins, Slab& dst) {
-        shell_fields(dn_00, params.ell2, t.m2, bins, layout, dst);
-      },
+      [&](const std::vector<int>& bins) { return shell_slab(params.ell1, t.m1, bins, layout); },
+      [&](const std::vector<int>& bins) { return shell_slab(params.ell2, t.m2, bins, layout); },
       bk_comp);
     for (int i = 0; i < dv.dim; i++) {
       if (!active[i]) continue;
@@ -738,6 +766,7 @@ trv::ThreePCFMeasurements threepcf_impl(
   dev::Mesh N_00_own;
   if (survey) N_00_own = eng.quadratic_field(0, 0);
   const trvb_mesh N_00 = survey ? N_00_own.view() : eng.quadratic_view_of_fluctuation(dn_00);
+  dev::profile_mark(c, "fields_00");
 
   trvm::SphericalBesselCalculator sj_a(params.ell1), sj_b(params.ell2);
   eng.upload_sjl(sj_a);
@@ -758,6 +787,7 @@ trv::ThreePCFMeasurements threepcf_impl(
       dn_LM = eng.density_fluctuation(params.ELL, t.M);
       Sbar_LM = eng.shotnoise_amp(params.ELL, t.M);
       cached_M = t.M; have_LM = true; have_xi = false; have_G = false;
+      dev::profile_mark(c, "fields_LM");
     }
     if (!survey && !have_LM) { Sbar_LM = eng.shotnoise_amp(0, 0); have_LM = true; }
     const dev::Mesh& dn_LM_ref = survey ? dn_LM : dn_00;
@@ -771,6 +801,7 @@ trv::ThreePCFMeasurements threepcf_impl(
       dev::check(trvb_shot_xi(c, dn_LM_ref.view(), N_00, S, xi.view()), "trvb_shot_xi");
       trvs::count_ifft += 1;
       have_xi = true;
+      dev::profile_mark(c, "shot_xi");
     }
     std::vector<long long> np(nb);
     std::vector<double> rr(nb), xib(2 * nb);
@@ -788,6 +819,7 @@ trv::ThreePCFMeasurements threepcf_impl(
       sn_dv[i] += t.coupling * factor_parity * (x + t.factor_mirror_w3j * std::conj(x));
     }
     if (count_terms == 0) { reff = rr; npairs = np; }
+    dev::profile_mark(c, "shot_3pcf_bin");
 
     // ---- raw 3PCF ---------------------------------------------------------
     if (!have_G) {
@@ -797,26 +829,29 @@ trv::ThreePCFMeasurements threepcf_impl(
       trvs::count_ifft += 1;
       have_G = true;
     }
-    auto sjl_fields = [&](int ell, int m, const std::vector<int>& bins, Slab& dst) {
+    auto sjl_fields = [&](int ell, int m, const std::vector<int>& bins) {
+      auto slab = std::make_shared<Slab>(eng.shared(), c, TRVB_COMPLEX, (int)bins.size());
       for (size_t i = 0; i < bins.size(); i++) {
-        trvb_mesh out; out.data = dst.mesh((int)i); out.layout = TRVB_COMPLEX; out.k0_add = 0.;
+        trvb_mesh out; out.data = slab->mesh((int)i); out.layout = TRVB_COMPLEX; out.k0_add = 0.;
         dev::check(trvb_sjl_ifft(c, dn_00.view(), ell, m, reff[bins[i]], 1. / eng.vol(), out),
                    "trvb_sjl_ifft");
         trvs::count_ifft += 1;
       }
+      return slab;
     };
     const bool same_fields = (params.ell1 == params.ell2 && t.m1 == t.m2);
     std::vector<cdouble> zeta_comp;
     reduce_pairs(
       eng, c, dv, active, same_fields, G.view(),
-      [&](const std::vector<int>& bins, Slab& dst) { sjl_fields(params.ell1, t.m1, bins, dst); },
-      [&](const std::vector<int>& bins, Slab& dst) { sjl_fields(params.ell2, t.m2, bins, dst); },
+      [&](const std::vector<int>& bins) { return sjl_fields(params.ell1, t.m1, bins); },
+      [&](const std::vector<int>& bins) { return sjl_fields(params.ell2, t.m2, bins); },
       zeta_comp);
     for (int i = 0; i < dv.dim; i++) {
       if (!active[i]) continue;
       zeta_dv[i] += t.coupling * vol_cell * factor_phase * (
         zeta_comp[i] + t.factor_mirror * std::conj(zeta_comp[i]));
     }
+    dev::profile_mark(c, "sjl_fields_and_pairs");
     count_terms++;
     if (trvs::currTask == 0) {
       trvs::logger.stat(
