@@ -91,7 +91,14 @@ long long trvb_ctx_nmesh(const trvb_ctx* ctx);
 size_t trvb_mesh_bytes(const trvb_ctx* ctx, int layout);
 
 /* ---- memory (replaces S/arrayops.cpp:273-343 H2D/D2H helpers) ---------- */
+/* Free/total device memory as seen by this library: the driver's free memory
+ * measured once (at context creation, after an arena trim or a failed
+ * allocation) and kept current with the arena's own allocations, plus the blocks
+ * the arena holds for reuse.  trvb_mem_info_invalidate forces the next call to
+ * measure again (S/monitor.cpp:117-156 gbytesMem* accounting plays this role in
+ * the reference). */
 int trvb_mem_info(trvb_ctx* ctx, size_t* free_bytes, size_t* total_bytes);
+void trvb_mem_info_invalidate(int device);
 int trvb_malloc(trvb_ctx* ctx, void** dptr, size_t bytes);
 int trvb_free(trvb_ctx* ctx, void* dptr);
 int trvb_memset0(trvb_ctx* ctx, void* dptr, size_t bytes);
@@ -114,6 +121,10 @@ int trvb_cat_create_aos(trvb_ctx* ctx, trvb_cat** cat, long long n,
  * memory) for TRVB_W_CUSTOM. */
 int trvb_cat_set_custom_weights(trvb_ctx* ctx, trvb_cat* cat,
                                 const double* weights);
+/* Forget the cached cell-sorted order, so that the next trvb_assign sorts the
+ * catalogue again (measurement aid: the reference scatters in catalogue order,
+ * S/field.cpp:618-1112, and has no sort to cache). */
+void trvb_cat_invalidate_sort(trvb_cat* cat);
 void trvb_cat_destroy(trvb_cat* cat);
 long long trvb_cat_size(const trvb_cat* cat);
 /* sum_i weight(kind, L, M)_i, complex, e.g. Sbar_LM (S/threept.cpp:156-236). */

@@ -911,6 +911,10 @@ extern "C" void trvb_cat_destroy(trvb_cat* cat) {
   delete cat;
 }
 
+extern "C" void trvb_cat_invalidate_sort(trvb_cat* cat) {
+  if (cat) { cat->sort_kind = -1; cat->sort_shifted = -1; }
+}
+
 extern "C" long long trvb_cat_size(const trvb_cat* cat) { return cat ? cat->n : 0; }
 
 extern "C" int trvb_cat_sum(trvb_ctx* ctx, trvb_cat* cat, int kind, int L, int M,

@@ -42,6 +42,11 @@ struct Arena {
   std::multimap<size_t, ArenaBlock> free_blocks;          // by size
   std::unordered_map<void*, size_t> live;                 // handed out
   size_t cached = 0;
+  // Driver-side free memory as last measured, kept current by subtracting the
+  // arena's own cudaMallocs: cudaMemGetInfo costs ~1 ms and was seen to stall
+  // for up to 100 ms on B200 hosts, so it is not called per estimator step.
+  bool free_known = false;
+  size_t driver_free = 0, driver_total = 0;
 };
 Arena g_arena[64];
 const cudaStream_t kRetired = (cudaStream_t)(-1);   // owner stream drained and destroyed
@@ -81,9 +86,10 @@ cudaError_t trvb_arena_alloc(int device, cudaStream_t stream, void** p, size_t b
     trvb_arena_trim(device);      // give cached blocks back and retry once
     e = cudaMalloc(p, want);
   }
-  if (e != cudaSuccess) return e;
   std::lock_guard<std::mutex> lock(a.mu);
+  if (e != cudaSuccess) { a.free_known = false; return e; }
   a.live[*p] = want;
+  if (a.free_known) a.driver_free = a.driver_free > want ? a.driver_free - want : 0;
   return cudaSuccess;
 }
 
@@ -119,11 +125,14 @@ void trvb_arena_trim(int device) {
     std::lock_guard<std::mutex> lock(a.mu);
     blocks.swap(a.free_blocks);
     a.cached = 0;
+    a.free_known = false;
   }
   if (blocks.empty()) return;
   cudaDeviceSynchronize();
   for (auto& kv : blocks) cudaFree(kv.second.p);
 }
+
+extern "C" void trvb_mem_info_invalidate(int device);
 
 int trvb_scratch(trvb_ctx* ctx, size_t bytes, double** out) {
   if (ctx->scratch_bytes < bytes) {
@@ -219,6 +228,7 @@ extern "C" int trvb_ctx_create(trvb_ctx** out, int device, const int ngrid[3],
   ctx->num_sms = prop.multiProcessorCount;
   int st = build_tables(ctx);
   if (st) { delete ctx; return st; }
+  trvb_mem_info_invalidate(device);   // the next trvb_mem_info measures afresh
   *out = ctx;
   return 0;
 }
@@ -308,10 +318,22 @@ extern "C" size_t trvb_mesh_bytes(const trvb_ctx* ctx, int layout) {
 
 extern "C" int trvb_mem_info(trvb_ctx* ctx, size_t* free_bytes, size_t* total_bytes) {
   TRVB_CUDA(cudaSetDevice(ctx->device));
-  TRVB_CUDA(cudaMemGetInfo(free_bytes, total_bytes));
+  Arena& a = g_arena[ctx->device & 63];
+  std::lock_guard<std::mutex> lock(a.mu);
+  if (!a.free_known) {
+    TRVB_CUDA(cudaMemGetInfo(&a.driver_free, &a.driver_total));
+    a.free_known = true;
+  }
   // Blocks cached by the arena are available to this library.
-  *free_bytes += trvb_arena_cached_bytes(ctx->device);
+  *free_bytes = a.driver_free + a.cached;
+  *total_bytes = a.driver_total;
   return 0;
+}
+
+extern "C" void trvb_mem_info_invalidate(int device) {
+  Arena& a = g_arena[device & 63];
+  std::lock_guard<std::mutex> lock(a.mu);
+  a.free_known = false;
 }
 
 extern "C" int trvb_malloc(trvb_ctx* ctx, void** dptr, size_t bytes) {

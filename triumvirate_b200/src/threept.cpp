@@ -436,6 +436,7 @@ void reduce_pairs(Engine& eng, trvb_ctx* grid, const DataVector& dv,
   // about the same size.
   const size_t bytes = trvb_mesh_bytes(grid, G.layout) * (G.layout == TRVB_REAL ? 2 : 1);
   const int cap = eng.mesh_capacity(bytes) - 1;
+  dev::profile_mark(eng.ctx(), "pairs:capacity");
   if (cap < 2) {
     throw trvs::DeviceError(
       "Insufficient device memory: fewer than two %zu-byte shell meshes fit.", bytes);
@@ -454,6 +455,7 @@ void reduce_pairs(Engine& eng, trvb_ctx* grid, const DataVector& dv,
     const std::vector<int> bins_a(rows.begin() + r0, rows.begin() + r1);
     const std::shared_ptr<Slab> fa_holder = get_a(bins_a);
     const Slab& fa = *fa_holder;
+    dev::profile_mark(eng.ctx(), "pairs:fields_a");
     std::map<int, int> ia_of;
     std::vector<const void*> pa;
     for (size_t i = 0; i < bins_a.size(); i++) { ia_of[bins_a[i]] = (int)i; pa.push_back(fa.mesh((int)i)); }
@@ -466,6 +468,7 @@ void reduce_pairs(Engine& eng, trvb_ctx* grid, const DataVector& dv,
       }
       std::shared_ptr<Slab> fb;
       if (!bins_b.empty()) fb = get_b(bins_b);
+      dev::profile_mark(eng.ctx(), "pairs:fields_b");
       std::map<int, int> ib_of;
       std::vector<const void*> pb;
       int next_own = 0;
@@ -487,6 +490,7 @@ void reduce_pairs(Engine& eng, trvb_ctx* grid, const DataVector& dv,
       dev::check(trvb_gram_reduce(grid, pa.data(), (int)pa.size(), pb.data(), (int)pb.size(),
                                   G, ia.data(), ib.data(), (int)ia.size(),
                                   sums.data()), "trvb_gram_reduce");
+      dev::profile_mark(eng.ctx(), "pairs:gram");
       for (size_t p = 0; p < ia.size(); p++) {
         out[where[p]] = cdouble(sums[2 * p], sums[2 * p + 1]);
       }
@@ -646,6 +650,7 @@ trv::BispecMeasurements bispec_impl(
                                  G.view()), "trvb_shell_ifft (G)");
       trvs::count_ifft += 1;
       G_M = t.M; have_G = true;
+      dev::profile_mark(c, "G_field");
     }
     const bool same_fields = (params.ell1 == params.ell2 && t.m1 == t.m2);
     std::vector<cdouble> bk_comp;
