@@ -83,6 +83,24 @@ int trv_threept_box_arrays(
   int* dim, double* c1_bin, double* c2_bin, double* c1_eff, double* c2_eff,
   int* n1, int* n2, double* raw, double* shot);
 
+/* 3PCF window function from a random catalogue: replaces T/_threept.pyx:276-314
+ * (_compute_3pcf_window -> trv::compute_3pcf_window, S/threept.cpp:2621-3077).
+ * The catalogue is used with the given alpha contrast (the Python front end
+ * passes alpha = 1, T/threept.py:2052-2056); wide_angle != 0 multiplies G_LM(x)
+ * by |x|^(-i_wa-j_wa) (S/field.cpp:1727-1762).  Other arguments and outputs as
+ * trv_threept. */
+int trv_threept_window(
+  int nr, const double* xr, const double* yr, const double* zr,
+  const double* nzr, const double* wsr, const double* wcr, const double* los_r,
+  const double* boxsize, const int* ngrid, const char* assignment,
+  int ell1, int ell2, int ELL, int i_wa, int j_wa, const char* form, int idx_bin,
+  const char* binning, double bin_min, double bin_max, int num_bins,
+  const double* custom_edges,
+  double alpha, double norm_factor, int wide_angle,
+  int verbose, int deterministic, int part_rank, int part_count,
+  int* dim, double* c1_bin, double* c2_bin, double* c1_eff, double* c2_eff,
+  int* n1, int* n2, double* raw, double* shot);
+
 /* cudaStream_t of the most recently used estimator context (NULL before the
  * first call). */
 void* trv_last_stream(void);

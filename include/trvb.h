@@ -150,6 +150,10 @@ int trvb_mesh_add_const(trvb_ctx* ctx, trvb_mesh mesh, double c);
  * (S/field.cpp:1309-1312, 1433-1436, 1358-1361). */
 int trvb_mesh_axpby(trvb_ctx* ctx, trvb_mesh dst, double a, trvb_mesh src,
                     double b);
+/* mesh(x) *= |x|^(-power) where |x| >= 1e-6, x = signed cell offset vector
+ * (MeshField::apply_wide_angle_pow_law_kernel with power = i_wa + j_wa,
+ * S/field.cpp:1727-1762). */
+int trvb_mesh_pow_law(trvb_ctx* ctx, trvb_mesh mesh, int power);
 /* sum_x Re(mesh)^3 (S/field.cpp:2056-2058). */
 int trvb_mesh_sum_pow3(trvb_ctx* ctx, trvb_mesh mesh, double* out);
 

@@ -6,7 +6,8 @@
 // cpu_baseline / --impl reference legs call the reference's own
 // implementation of the hot path:
 //   trv::compute_bispec / compute_3pcf / compute_bispec_in_gpp_box /
-//   compute_3pcf_in_gpp_box                 (S/threept.cpp:248,1014,1473,2190)
+//   compute_3pcf_in_gpp_box / compute_3pcf_window
+//                                           (S/threept.cpp:248,1014,1473,2190,2621)
 //   trv::MeshField assignment / FFT / compensation (S/field.cpp:569-1785)
 //   trv::calc_bispec_normalisation_from_{particles,mesh} (S/threept.cpp:96,138)
 //   trv::maths calculators                  (S/maths.cpp:167-375)
@@ -171,6 +172,45 @@ int trvref_threept(
         raw[2*i] = out.zeta_raw[i].real(); raw[2*i+1] = out.zeta_raw[i].imag();
         shot[2*i] = out.zeta_shot[i].real(); shot[2*i+1] = out.zeta_shot[i].imag();
       }
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+
+// 3PCF window function (trv::compute_3pcf_window, S/threept.cpp:2621-3077).
+int trvref_threept_window(
+  int nr, const double* xr, const double* yr, const double* zr,
+  const double* nzr, const double* wsr, const double* wcr, const double* los_r,
+  const double* boxsize, const int* ngrid, const char* assignment,
+  int ell1, int ell2, int ELL, int i_wa, int j_wa, const char* form, int idx_bin,
+  const char* binning, double bin_min, double bin_max, int num_bins,
+  double alpha, double norm_factor, int wide_angle, int verbose,
+  int* dim, double* c1_bin, double* c2_bin, double* c1_eff, double* c2_eff,
+  int* n1, int* n2, double* raw, double* shot
+) {
+  try {
+    trv::ParameterSet params;
+    params.i_wa = i_wa; params.j_wa = j_wa;
+    fill_params(
+      params, "random", wide_angle ? "3pcf-win-wa" : "3pcf-win", boxsize, ngrid, assignment,
+      ell1, ell2, ELL, form, idx_bin, binning, bin_min, bin_max, num_bins, 0, verbose
+    );
+    trv::Binning bins(params);
+    bins.set_bins();
+    trv::ParticleCatalogue rand(verbose);
+    load_catalogue(rand, nr, xr, yr, zr, nzr, wsr, wcr);
+    trv::ThreePCFWindowMeasurements out = trv::compute_3pcf_window(
+      rand, (trv::LineOfSight*)los_r, params, bins, alpha, norm_factor, wide_angle != 0);
+    *dim = out.dim;
+    for (int i = 0; i < out.dim; i++) {
+      c1_bin[i] = out.r1_bin[i]; c2_bin[i] = out.r2_bin[i];
+      c1_eff[i] = out.r1_eff[i]; c2_eff[i] = out.r2_eff[i];
+      n1[i] = out.npairs_1[i]; n2[i] = out.npairs_2[i];
+      raw[2*i] = out.zeta_raw[i].real(); raw[2*i+1] = out.zeta_raw[i].imag();
+      shot[2*i] = out.zeta_shot[i].real(); shot[2*i+1] = out.zeta_shot[i].imag();
     }
     return 0;
   } catch (const std::exception& e) {

@@ -1,0 +1,181 @@
+"""Drop-in proof at the reference's own binding layer.
+
+``oracle/build_refcy.py`` compiles the reference's UNMODIFIED Cython modules
+(``T/_threept.pyx``, ``_particles.pyx``, ``dataobjs.pyx``, ``parameters.pyx``)
+against ``triumvirate_b200/include/trv_compat`` and links them to
+``libtrv_b200.so``.  These tests then drive the GPU path exactly as the
+reference's Python package does (``T/threept.py:1467-1560``): a ``ParameterSet``
+from the reference's test parameter file, a ``Binning``, ``_ParticleCatalogue``
+objects and the ``_compute_*`` functions -- and compare with the reference's
+golden files.  Skipped when the compiled modules are absent and cannot be
+built (no /root/reference).
+"""
+import copy
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+
+# Contents of the reference's tests/test_input/params/test_params.yml.
+TEST_PARAMS = {
+    "directories": {"catalogues": "", "measurements": ""},
+    "files": {"data_catalogue": None, "rand_catalogue": None},
+    "catalogue_columns": [],
+    "tags": {"output": None},
+    "boxsize": {"x": 1000., "y": 1000., "z": 1000.},
+    "ngrid": {"x": 64, "y": 64, "z": 64},
+    "expand": 1.,
+    "cutoff_nyq": None,
+    "alignment": "centre",
+    "padscale": "box",
+    "padfactor": None,
+    "assignment": "tsc",
+    "interlace": False,
+    "catalogue_type": None,
+    "statistic_type": None,
+    "degrees": {"ell1": None, "ell2": None, "ELL": 0},
+    "wa_orders": {"i": None, "j": None},
+    "form": "diag",
+    "norm_convention": "particle",
+    "binning": "lin",
+    "range": [0.005, 0.105],
+    "num_bins": 4,
+    "idx_bin": None,
+    "fftw_scheme": "measure",
+    "use_fftw_wisdom": False,
+    "save_binned_vectors": False,
+    "verbose": 20,
+    "progbar": False,
+}
+
+
+@pytest.fixture(scope="module")
+def trvcy():
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import build_refcy
+    if not build_refcy.build():
+        pytest.skip("oracle/_ref/trvcy not built and /root/reference absent")
+    sys.path.insert(0, str(ROOT / "oracle" / "_ref"))
+    import trvcy._particles   # noqa: F401
+    import trvcy._threept     # noqa: F401
+    import trvcy.dataobjs     # noqa: F401
+    import trvcy.parameters   # noqa: F401
+    return trvcy
+
+
+def _paramset(trvcy, catalogue_type, statistic_type, degrees, form, idx_bin, rng):
+    """What T/threept.py:_amalgamate_parameters does to the template."""
+    d = copy.deepcopy(TEST_PARAMS)
+    d["catalogue_type"], d["statistic_type"] = catalogue_type, statistic_type
+    d["degrees"] = dict(zip(("ell1", "ell2", "ELL"), degrees))
+    d["form"], d["idx_bin"] = form, idx_bin
+    d["range"] = list(rng)
+    return trvcy.parameters.ParameterSet(param_dict=d)
+
+
+def _catalogue(trvcy, pos, nz):
+    n = pos.shape[1]
+    cols = [np.ascontiguousarray(c, dtype=np.float64) for c in pos]
+    return trvcy._particles._ParticleCatalogue(
+        cols[0], cols[1], cols[2], np.ascontiguousarray(nz, dtype=np.float64),
+        np.ones(n), np.ones(n), verbose=20)
+
+
+def test_reference_cython_layer_links_against_libtrv_b200(trvcy):
+    names = ["_calc_bispec_normalisation_from_mesh", "_calc_bispec_normalisation_from_particles",
+             "_compute_3pcf", "_compute_3pcf_in_gpp_box", "_compute_3pcf_window",
+             "_compute_bispec", "_compute_bispec_in_gpp_box"]
+    for n in names:
+        assert callable(getattr(trvcy._threept, n)), n
+    with open("/proc/self/maps") as f:
+        assert "triumvirate_b200/libtrv_b200.so" in f.read()
+
+
+def test_reference_cython_host_objects(trvcy, golden_data_catalogue):
+    """ParameterSet.validate(), Binning and the particle normalisation run on
+    the host: usable without a GPU."""
+    from triumvirate_b200 import catalogue as tcat
+    ps = _paramset(trvcy, "sim", "bispec", (0, 0, 0), "diag", None, (0.005, 0.105))
+    assert ps["npoint"] == "3pt" and ps["space"] == "fourier"
+    b = trvcy.dataobjs.Binning.from_parameter_set(ps)
+    assert np.allclose(b.bin_edges, np.linspace(0.005, 0.105, 5), rtol=1e-15)
+    assert b.bin_edges[-1] == 0.105
+    data = golden_data_catalogue
+    cat = _catalogue(trvcy, tcat.periodise(data[:3], 1000.), data[3])
+    norm = trvcy._threept._calc_bispec_normalisation_from_particles(cat, alpha=1.)
+    assert abs(norm - 1. / (3. * 3.e-9**2)) < 1e-12 * norm      # golden header: 3.703703704e+16
+    with pytest.raises(Exception):
+        _paramset(trvcy, "sim", "bispec", (0, 0, 0), "nonsense-form", None, (0.005, 0.105))
+
+
+CASES = [((0, 0, 0), "diag", None), ((2, 0, 2), "diag", None), ((0, 0, 0), "row", 0)]
+
+
+def _check(out, ext, prefix):
+    c = "k" if prefix == "bk" else "r"
+    cnt = "nmodes" if prefix == "bk" else "npairs"
+    stat = "bk" if prefix == "bk" else "zeta"
+    assert np.allclose(out[f"{c}1_bin"], ext[0]) and np.allclose(out[f"{c}2_bin"], ext[3])
+    assert np.allclose(out[f"{c}1_eff"], ext[1]) and np.allclose(out[f"{c}2_eff"], ext[4])
+    assert np.array_equal(out[f"{cnt}_1"], ext[2]) and np.array_equal(out[f"{cnt}_2"], ext[5])
+    raw, shot = ext[-4] + 1j * ext[-3], ext[-2] + 1j * ext[-1]
+
+    def rel(a, b):
+        return np.max(np.abs(a - b) / np.where(np.abs(b) > 0., np.abs(b), 1.))
+    assert rel(out[f"{stat}_raw"], raw) < 2.e-9
+    assert rel(out[f"{stat}_shot"], shot) < 2.e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("stat,prefix", [("bispec", "bk"), ("3pcf", "zeta")])
+@pytest.mark.parametrize("degrees,form,idx_bin", CASES)
+def test_goldens_through_reference_cython_box(trvcy, stat, prefix, degrees, form, idx_bin,
+                                              golden_data_catalogue):
+    from triumvirate_b200 import catalogue as tcat
+    rng = (0.005, 0.105) if stat == "bispec" else (50., 150.)
+    ps = _paramset(trvcy, "sim", stat, degrees, form, idx_bin, rng)
+    binning = trvcy.dataobjs.Binning.from_parameter_set(ps)
+    data = golden_data_catalogue
+    cat = _catalogue(trvcy, tcat.periodise(data[:3], 1000.), data[3])
+    norm = trvcy._threept._calc_bispec_normalisation_from_particles(cat, alpha=1.)
+    fn = getattr(trvcy._threept, f"_compute_{stat}_in_gpp_box")
+    out = fn(cat, ps, binning, norm)
+    ftag = form if form != "row" else f"row{idx_bin}"
+    _check(out, load_golden(f"{prefix}{''.join(map(str, degrees))}_{ftag}_gpp.txt"), prefix)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("stat,prefix", [("bispec", "bk"), ("3pcf", "zeta")])
+@pytest.mark.parametrize("degrees,form,idx_bin", CASES[:2])
+def test_goldens_through_reference_cython_survey(trvcy, stat, prefix, degrees, form, idx_bin,
+                                                 golden_data_catalogue, golden_rand_catalogue):
+    from triumvirate_b200 import catalogue as tcat
+    rng = (0.005, 0.105) if stat == "bispec" else (50., 150.)
+    ps = _paramset(trvcy, "survey", stat, degrees, form, idx_bin, rng)
+    binning = trvcy.dataobjs.Binning.from_parameter_set(ps)
+    data, rand = golden_data_catalogue, golden_rand_catalogue
+    los_d, los_r = tcat.compute_los(data[:3]), tcat.compute_los(rand[:3])
+    pos_d, pos_r = tcat.centre(data[:3], rand[:3], 1000.)
+    cat_d, cat_r = _catalogue(trvcy, pos_d, data[3]), _catalogue(trvcy, pos_r, rand[3])
+    alpha = data.shape[1] / rand.shape[1]
+    norm = trvcy._threept._calc_bispec_normalisation_from_particles(cat_r, alpha=alpha)
+    fn = getattr(trvcy._threept, f"_compute_{stat}")
+    out = fn(cat_d, cat_r, los_d, los_r, ps, binning, norm)
+    _check(out, load_golden(f"{prefix}{''.join(map(str, degrees))}_{form}_lpp.txt"), prefix)
+
+
+@pytest.mark.gpu
+def test_window_golden_through_reference_cython(trvcy, golden_rand_catalogue):
+    from triumvirate_b200 import catalogue as tcat
+    ps = _paramset(trvcy, "random", "3pcf-win", (2, 0, 2), "diag", None, (50., 150.))
+    binning = trvcy.dataobjs.Binning.from_parameter_set(ps)
+    rand = golden_rand_catalogue
+    los_r = tcat.compute_los(rand[:3])
+    pos_r, _ = tcat.centre(rand[:3], rand[:3], 1000.)
+    cat_r = _catalogue(trvcy, tcat.periodise(pos_r, 1000.), rand[3])
+    norm = trvcy._threept._calc_bispec_normalisation_from_particles(cat_r, alpha=1.)
+    out = trvcy._threept._compute_3pcf_window(cat_r, los_r, ps, binning, alpha=1.,
+                                              norm_factor=norm, wide_angle=False)
+    _check(out, load_golden("zetaw202_diag.txt"), "zeta")

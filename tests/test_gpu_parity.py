@@ -270,6 +270,73 @@ def test_survey_against_oracle(core, oracle, stat, degrees, form, idx_bin, assig
     _assert_close(out, ref, label=f"{stat}{degrees}{form}: ")
 
 
+# ---------------------------------------------------------------------------
+# 3PCF window function (S/threept.cpp:2621-3077)
+# ---------------------------------------------------------------------------
+
+def _window_inputs(rand, L):
+    """T/threept.py:1969-2010: LOS before alignment, centre, periodise."""
+    from triumvirate_b200 import catalogue as tcat
+    los_r = tcat.compute_los(rand[:3])
+    pos_r, _ = tcat.centre(rand[:3], rand[:3], L)
+    return tcat.periodise(pos_r, L), los_r
+
+
+@pytest.mark.parametrize("degrees,form,idx_bin", CASES)
+def test_reference_window_goldens(core, degrees, form, idx_bin, golden_rand_catalogue):
+    """zetaw*.txt, the reference's tests/test_threept.py:278-335."""
+    L, ng = 1000., 64
+    rand = golden_rand_catalogue
+    pos_r, los_r = _window_inputs(rand, L)
+    norm = core.norm_particles(pos_r, rand[3], alpha=1.)
+    out = core.threept_window(pos_r, L, ng, "tsc", degrees, form, (50., 150.), 4, norm, los_r,
+                              alpha=1., idx_bin=idx_bin or 0, nz_r=rand[3])
+    tag = "".join(map(str, degrees))
+    ftag = form if form != "row" else f"row{idx_bin}"
+    ext = load_golden(f"zetaw{tag}_{ftag}.txt")
+    assert np.allclose(out["r1_bin"], ext[0])
+    assert np.allclose(out["r1_eff"], ext[1])
+    assert np.array_equal(out["npairs_1"], ext[2])
+    assert np.allclose(out["r2_bin"], ext[3])
+    assert np.allclose(out["r2_eff"], ext[4])
+    assert np.array_equal(out["npairs_2"], ext[5])
+    raw = ext[-4] + 1j * ext[-3]
+    shot = ext[-2] + 1j * ext[-1]
+    assert np.allclose(out["zeta_raw"], raw)
+    assert np.allclose(out["zeta_shot"], shot)
+
+    def rel(a, b):
+        return np.max(np.abs(a - b) / np.where(np.abs(b) > 0., np.abs(b), 1.))
+    assert rel(out["zeta_raw"], raw) < 2.e-9
+    assert rel(out["zeta_shot"], shot) < 2.e-9
+
+
+@pytest.mark.parametrize("degrees,form,idx_bin,assignment,wide_angle,wa_orders", [
+    ((0, 0, 0), "full", 0, "pcs", False, (0, 0)),
+    ((2, 0, 2), "diag", 0, "tsc", False, (0, 0)),
+    ((1, 1, 0), "off-diag", 1, "cic", False, (0, 0)),
+    ((2, 0, 2), "diag", 0, "tsc", True, (1, 0)),
+    ((1, 1, 2), "row", 2, "pcs", True, (1, 1)),
+])
+def test_window_against_oracle(core, oracle, degrees, form, idx_bin, assignment, wide_angle,
+                               wa_orders):
+    from triumvirate_b200 import catalogue as tcat
+    L, ng = 1000., 32
+    _, pr_, _, nzr, _, wsr, _, wcr = _survey_inputs(57, 10, 5000, L)
+    los_r = tcat.compute_los(pr_)
+    pos_r, _ = tcat.centre(pr_, pr_, L)
+    pos_r = tcat.periodise(pos_r, L)
+    alpha = 0.37
+    norm = oracle.norm_particles(pos_r, nzr, ws=wsr, wc=wcr, alpha=alpha)
+    kw = dict(pos_r=pos_r, boxsize=L, ngrid=ng, assignment=assignment, degrees=degrees,
+              form=form, bin_range=(40., 280.), num_bins=4, norm_factor=norm, los_r=los_r,
+              alpha=alpha, idx_bin=idx_bin, nz_r=nzr, ws_r=wsr, wc_r=wcr,
+              wide_angle=wide_angle, wa_orders=wa_orders)
+    ref = oracle.threept_window(**kw)
+    out = core.threept_window(**kw)
+    _assert_close(out, ref, label=f"window{degrees}{form}wa{wa_orders}: ")
+
+
 @pytest.mark.parametrize("binning", ["log", "linpad"])
 def test_box_binning_schemes_against_oracle(core, oracle, binning):
     gen = np.random.default_rng(33)

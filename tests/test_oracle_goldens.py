@@ -60,6 +60,43 @@ def test_oracle_reproduces_reference_goldens(oracle, stat, prefix, kind, degrees
     assert rel(out[names[7]], shot) < 2.e-9
 
 
+def _window_inputs(mod, rand, L):
+    """Python-side preparation of compute_3pcf_window (T/threept.py:1969-2010):
+    LOS from the original coordinates, centre on the catalogue's own extents, then
+    periodise; alpha = 1; particle normalisation with alpha = 1."""
+    los_r = mod.compute_los(rand[:3])
+    pos_r, _ = mod.centre(rand[:3], rand[:3], L)
+    pos_r = mod.periodise(pos_r, L)
+    return pos_r, los_r
+
+
+@pytest.mark.parametrize("degrees,form,idx_bin", CASES)
+def test_oracle_reproduces_window_goldens(oracle, degrees, form, idx_bin, golden_rand_catalogue):
+    """zetaw*.txt of the reference (tests/test_threept.py:278-335)."""
+    L, ng = 1000., 64
+    rand = golden_rand_catalogue
+    pos_r, los_r = _window_inputs(oracle, rand, L)
+    norm = oracle.norm_particles(pos_r, rand[3], alpha=1.)
+    out = oracle.threept_window(pos_r, L, ng, "tsc", degrees, form, (50., 150.), 4, norm, los_r,
+                                alpha=1., idx_bin=idx_bin or 0, nz_r=rand[3])
+    tag = "".join(map(str, degrees))
+    ftag = form if form != "row" else f"row{idx_bin}"
+    ext = load_golden(f"zetaw{tag}_{ftag}.txt")
+    assert np.allclose(out["r1_bin"], ext[0])
+    assert np.allclose(out["r1_eff"], ext[1], rtol=1.e-9, atol=0.)
+    assert np.array_equal(out["npairs_1"], ext[2])
+    assert np.allclose(out["r2_bin"], ext[3])
+    assert np.allclose(out["r2_eff"], ext[4], rtol=1.e-9, atol=0.)
+    assert np.array_equal(out["npairs_2"], ext[5])
+    raw = ext[-4] + 1j * ext[-3]
+    shot = ext[-2] + 1j * ext[-1]
+
+    def rel(a, b):
+        return np.max(np.abs(a - b) / np.where(np.abs(b) > 0., np.abs(b), 1.))
+    assert rel(out["zeta_raw"], raw) < 2.e-9
+    assert rel(out["zeta_shot"], shot) < 2.e-9
+
+
 def test_oracle_fixture_file_is_current(oracle):
     """tests/golden/oracle_*.npz (used by the GPU tests where /root/reference is
     absent) still equals what the oracle computes from the committed seed."""

@@ -129,6 +129,56 @@ def threept(stat, catalogue_type, pos_d, boxsize, ngrid, assignment, degrees,
     return out
 
 
+def threept_window(pos_r, boxsize, ngrid, assignment, degrees, form, bin_range,
+                   num_bins, norm_factor, los_r, alpha=1., idx_bin=0, binning="lin",
+                   nz_r=None, ws_r=None, wc_r=None, wide_angle=False,
+                   wa_orders=(0, 0), verbose=60,
+                   custom_edges=None, deterministic=False, part_rank=0, part_count=1):
+    """3PCF window function of a random catalogue on the GPU
+    (``trv::compute_3pcf_window``, binding ``T/_threept.pyx:276-314``).  ``pos_r`` is
+    ``(3, N)`` already aligned in the box, ``los_r`` is ``(N, 3)``."""
+    L = _trv()
+    boxsize = np.broadcast_to(np.asarray(boxsize, dtype=np.float64), (3,)).copy()
+    ngrid = np.broadcast_to(np.asarray(ngrid, dtype=np.int32), (3,)).copy()
+    pos_r = np.asarray(pos_r, dtype=np.float64)
+    keep = [np.ascontiguousarray(a, dtype=np.float64) if a is not None else None
+            for a in (pos_r[0], pos_r[1], pos_r[2], nz_r, ws_r, wc_r, los_r)]
+    ptrs = [a.ctypes.data_as(_dp) if a is not None else None for a in keep]
+    nb = int(num_bins)
+    cap = max(nb * nb, nb) + 8
+    dim = C.c_int(0)
+    c1b = np.zeros(cap); c2b = np.zeros(cap)
+    c1e = np.zeros(cap); c2e = np.zeros(cap)
+    n1 = np.zeros(cap, dtype=np.int32); n2 = np.zeros(cap, dtype=np.int32)
+    raw = np.zeros(2 * cap); shot = np.zeros(2 * cap)
+    status = L.trv_threept_window(
+        C.c_int(pos_r.shape[1]), *ptrs,
+        boxsize.ctypes.data_as(_dp), ngrid.ctypes.data_as(_ip), assignment.encode(),
+        C.c_int(degrees[0]), C.c_int(degrees[1]), C.c_int(degrees[2]),
+        C.c_int(wa_orders[0]), C.c_int(wa_orders[1]),
+        form.encode(), C.c_int(idx_bin or 0), binning.encode(),
+        C.c_double(bin_range[0]), C.c_double(bin_range[1]), C.c_int(nb),
+        (np.ascontiguousarray(custom_edges, dtype=np.float64).ctypes.data_as(_dp)
+         if custom_edges is not None else None),
+        C.c_double(alpha), C.c_double(norm_factor), C.c_int(1 if wide_angle else 0),
+        C.c_int(verbose),
+        C.c_int(1 if deterministic else 0), C.c_int(part_rank), C.c_int(part_count),
+        C.byref(dim),
+        c1b.ctypes.data_as(_dp), c2b.ctypes.data_as(_dp),
+        c1e.ctypes.data_as(_dp), c2e.ctypes.data_as(_dp),
+        n1.ctypes.data_as(_ip), n2.ctypes.data_as(_ip),
+        raw.ctypes.data_as(_dp), shot.ctypes.data_as(_dp),
+    )
+    _check(status)
+    n = dim.value
+    names = ("r1_bin", "r2_bin", "r1_eff", "r2_eff", "npairs_1", "npairs_2",
+             "zeta_raw", "zeta_shot")
+    vals = (c1b[:n].copy(), c2b[:n].copy(), c1e[:n].copy(), c2e[:n].copy(),
+            n1[:n].copy(), n2[:n].copy(),
+            raw[0:2*n:2] + 1j * raw[1:2*n:2], shot[0:2*n:2] + 1j * shot[1:2*n:2])
+    return dict(zip(names, vals))
+
+
 def threept_box_arrays(stat, n, x_ptr, y_ptr, z_ptr, on_device, boxsize, ngrid,
                        assignment, degrees, form, bin_range, num_bins,
                        norm_factor=1., idx_bin=0, binning="lin", verbose=60,

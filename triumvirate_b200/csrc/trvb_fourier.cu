@@ -78,6 +78,21 @@ k_compensate(double2* __restrict__ f, GridDesc g, int layout, Tables tb) {
   });
 }
 
+// f(x) *= |x|^(-power) for |x| >= 1e-6, x the signed cell offset vector
+// (S/field.cpp:1727-1762, 546-553); `stride` = doubles per cell.
+__global__ void __launch_bounds__(256)
+k_pow_law(double* __restrict__ f, GridDesc g, int stride, int power) {
+  for_each_cell(g.n[0], g.n[1], g.n[2], [&](int i, int j, int k, long long t) {
+    const double rx = __dmul_rn((double)signed_index(i, g.n[0]), g.dr[0]);
+    const double ry = __dmul_rn((double)signed_index(j, g.n[1]), g.dr[1]);
+    const double rz = __dmul_rn((double)signed_index(k, g.n[2]), g.dr[2]);
+    const double r = vec3_norm_exact(rx, ry, rz);
+    if (r < 1.e-6) return;
+    const double w = pow(r, (double)(-power));
+    for (int c = 0; c < stride; c++) f[t * stride + c] *= w;
+  });
+}
+
 // One Fourier mode of the filtered spectrum (S/field.cpp:1815-1847):
 // y_lm(khat) src(k) / W(k) * amp for the signed mode (mi, mj, mk).
 __device__ __forceinline__ double2 shell_mode(const KView& src, const GridDesc& gp,
@@ -262,6 +277,17 @@ extern "C" int trvb_mesh_axpby(trvb_ctx* ctx, trvb_mesh dst, double a, trvb_mesh
   const long long n = (long long)(trvb_mesh_bytes(ctx, dst.layout) / sizeof(double));
   k_axpby<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(
     (double*)dst.data, (const double*)src.data, n, a, b);
+  TRVB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int trvb_mesh_pow_law(trvb_ctx* ctx, trvb_mesh mesh, int power) {
+  TRVB_REQUIRE(ctx && mesh.data, "trvb_mesh_pow_law: null argument");
+  TRVB_REQUIRE(mesh.layout == TRVB_REAL || mesh.layout == TRVB_COMPLEX,
+               "trvb_mesh_pow_law: configuration-space layouts only");
+  const int stride = mesh.layout == TRVB_COMPLEX ? 2 : 1;
+  const RowLaunch rl = row_launch(ctx->num_sms, ctx->g.n[0], ctx->g.n[1], ctx->g.n[2]);
+  k_pow_law<<<rl.grid, rl.block, 0, ctx->stream>>>((double*)mesh.data, ctx->g, stride, power);
   TRVB_LAUNCH_CHECK();
   return 0;
 }

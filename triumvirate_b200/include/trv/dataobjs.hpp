@@ -66,6 +66,20 @@ struct ThreePCFMeasurements {
   std::vector< std::complex<double> > zeta_shot;
 };
 
+/// 3PCF window measurements (I/dataobjs.hpp:288-303); same members as
+/// ThreePCFMeasurements.
+struct ThreePCFWindowMeasurements {
+  int dim = 0;
+  std::vector<double> r1_bin;
+  std::vector<double> r2_bin;
+  std::vector<double> r1_eff;
+  std::vector<double> r2_eff;
+  std::vector<int> npairs_1;
+  std::vector<int> npairs_2;
+  std::vector< std::complex<double> > zeta_raw;
+  std::vector< std::complex<double> > zeta_shot;
+};
+
 }  // namespace trv
 
 #endif  // TRV_B200_DATAOBJS_HPP_

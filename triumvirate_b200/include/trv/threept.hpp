@@ -68,6 +68,13 @@ trv::ThreePCFMeasurements compute_3pcf_in_gpp_box(
   ParticleCatalogue& catalogue_data,
   trv::ParameterSet& params, trv::Binning& rbinning, double norm_factor);
 
+/// 3PCF window from a random catalogue, optionally with the wide-angle
+/// power-law kernel r^{-i_wa-j_wa} on G_LM (S/threept.cpp:2621-3077).
+trv::ThreePCFWindowMeasurements compute_3pcf_window(
+  ParticleCatalogue& catalogue_rand, LineOfSight* los_rand,
+  trv::ParameterSet& params, trv::Binning& rbinning,
+  double alpha, double norm_factor, bool wide_angle = false);
+
 /// Array-level overloads (B200 build extension): periodic-box estimators
 /// from coordinate arrays in host (`on_device` false) or device memory.
 trv::BispecMeasurements compute_bispec_in_gpp_box(

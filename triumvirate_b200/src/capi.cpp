@@ -138,6 +138,48 @@ int trv_threept(
   });
 }
 
+/// 3PCF window function of a random catalogue (trv::compute_3pcf_window,
+/// S/threept.cpp:2621-3077; binding T/_threept.pyx:276-314).  `wide_angle` != 0
+/// applies the r^{-i_wa-j_wa} kernel to G_LM.
+int trv_threept_window(
+  int nr, const double* xr, const double* yr, const double* zr,
+  const double* nzr, const double* wsr, const double* wcr, const double* los_r,
+  const double* boxsize, const int* ngrid, const char* assignment,
+  int ell1, int ell2, int ELL, int i_wa, int j_wa, const char* form, int idx_bin,
+  const char* binning, double bin_min, double bin_max, int num_bins,
+  const double* custom_edges,
+  double alpha, double norm_factor, int wide_angle,
+  int verbose, int deterministic, int part_rank, int part_count,
+  int* dim, double* c1_bin, double* c2_bin, double* c1_eff, double* c2_eff,
+  int* n1, int* n2, double* raw, double* shot
+) {
+  return guarded([&]() {
+    trv::ParameterSet params;
+    params.i_wa = i_wa; params.j_wa = j_wa;
+    set_params(params, "random", wide_angle ? "3pcf-win-wa" : "3pcf-win", boxsize, ngrid,
+               assignment, "false", ell1, ell2, ELL, form, idx_bin, binning, bin_min, bin_max,
+               num_bins, verbose, deterministic, part_rank, part_count);
+    trv::Binning bins(params);
+    if (custom_edges != nullptr) {
+      bins.set_bins(std::vector<double>(custom_edges, custom_edges + num_bins + 1));
+    } else {
+      bins.set_bins();
+    }
+    trv::ParticleCatalogue rand(verbose);
+    rand.load_particle_arrays(nr, xr, yr, zr, nzr, wsr, wcr);
+    trv::ThreePCFWindowMeasurements out = trv::compute_3pcf_window(
+      rand, (trv::LineOfSight*)los_r, params, bins, alpha, norm_factor, wide_angle != 0);
+    *dim = out.dim;
+    for (int i = 0; i < out.dim; i++) {
+      c1_bin[i] = out.r1_bin[i]; c2_bin[i] = out.r2_bin[i];
+      c1_eff[i] = out.r1_eff[i]; c2_eff[i] = out.r2_eff[i];
+      n1[i] = out.npairs_1[i]; n2[i] = out.npairs_2[i];
+      raw[2*i] = out.zeta_raw[i].real(); raw[2*i+1] = out.zeta_raw[i].imag();
+      shot[2*i] = out.zeta_shot[i].real(); shot[2*i+1] = out.zeta_shot[i].imag();
+    }
+  });
+}
+
 /// Periodic-box estimators from coordinate arrays that may already live in
 /// device memory (`on_device` != 0: x, y, z are CUDA device pointers, e.g. a
 /// torch tensor's data_ptr()); unit weights.  No AoS staging copy.

@@ -264,6 +264,21 @@ class Engine {
     dev::profile_mark(c_, "upload");
   }
 
+  /// Window mode: one (random) catalogue with lines of sight and a given
+  /// alpha contrast (S/threept.cpp:2696-2702, S/field.cpp:1325-1362,1449-1489).
+  Engine(trv::ParameterSet& params, ParticleCatalogue& rand, LineOfSight* los_rand,
+         double alpha)
+    : params_(params), survey_(true), window_(true) {
+    ctx_ = dev::acquire_context(params);
+    c_ = ctx_.get();
+    dev::profile_reset();
+    data_.reset(new dev::Catalogue(ctx_, rand, los_rand, true));
+    ndata_ = rand.ntotal;
+    alpha_ = alpha;
+    init_common();
+    dev::profile_mark(c_, "upload");
+  }
+
   /// Periodic-box catalogue given as coordinate arrays (host or device);
   /// unit weights (S/threept.cpp:1543-1558).
   Engine(trv::ParameterSet& params, long long n, const double* x, const double* y,
@@ -291,6 +306,7 @@ class Engine {
   double vol() const { return vol_; }
   double vol_cell() const { return vol_cell_; }
   bool survey() const { return survey_; }
+  bool window() const { return window_; }
 
   /// Fourier transform of the (L, M)-weighted number-density fluctuation,
   /// delta n_LM(k), including the dV factor of S/field.cpp:1503-1510:
@@ -303,6 +319,8 @@ class Engine {
     dev::Mesh x(ctx_, c_, real_field ? TRVB_REAL : TRVB_COMPLEX);
     if (!survey_) {
       assign(*data_, TRVB_W_UNIT, 0, 0, 1., false, x);
+    } else if (window_) {
+      assign(*data_, TRVB_W_YLM_W, L, M, alpha_, false, x);
     } else {
       assign(*data_, TRVB_W_YLM_W, L, M, 1., false, x);
       assign(*rand_, TRVB_W_YLM_W, L, M, -alpha_, true, x);
@@ -323,6 +341,8 @@ class Engine {
     dev::Mesh x(ctx_, c_, real_field ? TRVB_REAL : TRVB_COMPLEX);
     if (!survey_) {
       assign(*data_, TRVB_W_UNIT, 0, 0, 1., false, x);
+    } else if (window_) {
+      assign(*data_, TRVB_W_CYLM_W2, L, M, std::pow(alpha_, 2), false, x);
     } else {
       assign(*data_, TRVB_W_CYLM_W2, L, M, 1., false, x);
       assign(*rand_, TRVB_W_CYLM_W2, L, M, std::pow(alpha_, 2), true, x);
@@ -339,6 +359,9 @@ class Engine {
 
   cdouble shotnoise_amp(int L, int M) {
     if (!survey_) return cdouble(double(ndata_), 0.);   // S/threept.cpp:1977-1979
+    if (window_) {                                       // S/threept.cpp:210-236
+      return std::pow(alpha_, 3) * cat_sum(c_, *data_, TRVB_W_YLM_W3, L, M);
+    }
     return cat_sum(c_, *data_, TRVB_W_YLM_W3, L, M)
       + std::pow(alpha_, 3) * cat_sum(c_, *rand_, TRVB_W_YLM_W3, L, M);
   }
@@ -378,6 +401,7 @@ class Engine {
 
   trv::ParameterSet& params_;
   bool survey_;
+  bool window_ = false;
   std::shared_ptr<trvb_ctx> ctx_;
   trvb_ctx* c_ = nullptr;
   std::unique_ptr<dev::Catalogue> data_, rand_;
@@ -755,7 +779,8 @@ trv::BispecMeasurements bispec_impl(
 // =====================================================================
 
 trv::ThreePCFMeasurements threepcf_impl(
-  Engine& eng, trv::ParameterSet& params, trv::Binning& rbinning, double norm_factor
+  Engine& eng, trv::ParameterSet& params, trv::Binning& rbinning, double norm_factor,
+  bool wide_angle = false
 ) {
   const bool survey = eng.survey();
   const cdouble factor_phase = std::pow(trvm::M_I, params.ell1 + params.ell2);
@@ -832,6 +857,10 @@ trv::ThreePCFMeasurements threepcf_impl(
       dev::check(trvb_shell_ifft(c, c, dn_LM_ref.view(), 0, 0, -1., -1., 1. / eng.vol(),
                                  G.view()), "trvb_shell_ifft (G)");
       trvs::count_ifft += 1;
+      if (wide_angle) {   // window only: G_LM(x) r^{-i-j} (S/threept.cpp:2978-2980)
+        dev::check(trvb_mesh_pow_law(c, G.view(), params.i_wa + params.j_wa),
+                   "trvb_mesh_pow_law");
+      }
       have_G = true;
     }
     auto sjl_fields = [&](int ell, int m, const std::vector<int>& bins) {
@@ -962,6 +991,33 @@ trv::ThreePCFMeasurements compute_3pcf_in_gpp_box(
     trvs::logger.stat(
       "... computed three-point correlation function from a periodic-box "
       "simulation-type catalogue in the global plane-parallel approximation.");
+  }
+  return out;
+}
+
+trv::ThreePCFWindowMeasurements compute_3pcf_window(
+  ParticleCatalogue& catalogue_rand, LineOfSight* los_rand,
+  trv::ParameterSet& params, trv::Binning& rbinning,
+  double alpha, double norm_factor, bool wide_angle
+) {
+  trvs::logger.reset_level(params.verbose);
+  const char* tag = wide_angle ? "wide-angle corrections " : "";
+  if (trvs::currTask == 0) {
+    trvs::logger.stat(
+      "Computing three-point correlation function window %sfrom random catalogue...", tag);
+  }
+  validate_multipole_coupling(params);
+  Engine eng(params, catalogue_rand, los_rand, alpha);
+  trv::ThreePCFMeasurements res = threepcf_impl(eng, params, rbinning, norm_factor, wide_angle);
+  trv::ThreePCFWindowMeasurements out;
+  out.dim = res.dim;
+  out.r1_bin = std::move(res.r1_bin); out.r2_bin = std::move(res.r2_bin);
+  out.r1_eff = std::move(res.r1_eff); out.r2_eff = std::move(res.r2_eff);
+  out.npairs_1 = std::move(res.npairs_1); out.npairs_2 = std::move(res.npairs_2);
+  out.zeta_raw = std::move(res.zeta_raw); out.zeta_shot = std::move(res.zeta_shot);
+  if (trvs::currTask == 0) {
+    trvs::logger.stat(
+      "... computed three-point correlation function window %sfrom random catalogue.", tag);
   }
   return out;
 }
