@@ -191,6 +191,41 @@ def test_assignment_bit_exact(core, oracle, assignment, clustered):
     oracle.set_num_threads(nthreads)
 
 
+@pytest.mark.parametrize("assignment", ["tsc", "pcs"])
+@pytest.mark.parametrize("ngrid", [(4, 4, 4), (16, 8, 24), (35, 19, 11), (50, 36, 20), (64, 64, 64), (96, 40, 24)])
+@pytest.mark.parametrize("complex_weights", [False, True])
+def test_throughput_assignment_tiles(core, oracle, assignment, ngrid, complex_weights, monkeypatch):
+    """Both throughput kernels -- the default warp-cooperative scatter
+    (k_assign_coop) and the opt-in tile-owned shared-memory accumulation
+    (k_assign_tile, TRV_ASSIGN_TILE=1) -- on grids that are smaller than a tile,
+    not multiples of the tile and anisotropic, with clustered positions and with
+    positions ON or BEYOND the box edge (the reference applies no wrap in
+    assignment, only the `0 <= gid < nmesh` guard, S/field.cpp:1042): equal to the
+    reference up to summation order."""
+    gen = np.random.default_rng(1000 * sum(ngrid) + 10 * len(assignment) + int(complex_weights))
+    L = np.array([300., 240., 410.])
+    n = 6000
+    pos = np.concatenate([
+        gen.uniform(0., 1., size=(3, n // 2)) * L[:, None],
+        np.mod(gen.normal(0.31, 0.02, size=(3, n // 2)), 1.) * L[:, None]], axis=1)
+    pos[:, 0] = L                  # exactly on the upper edge
+    pos[:, 1] = 0.
+    pos[0, 2] = L[0] * (1. + 1.e-3)   # beyond the edge
+    pos[2, 3] = -L[2] * 1.e-3
+    w = (gen.normal(size=pos.shape[1]) + 1j * gen.normal(size=pos.shape[1])) if complex_weights else None
+    nthreads = oracle.num_threads()
+    oracle.set_num_threads(1)
+    ref = oracle.mesh(pos, L, ngrid, assignment, stage=0, weights=w)
+    oracle.set_num_threads(nthreads)
+    scale = np.max(np.abs(ref))
+    monkeypatch.delenv("TRV_ASSIGN_TILE", raising=False)
+    coop = core.mesh(pos, L, ngrid, assignment, stage=0, weights=w)
+    assert np.max(np.abs(coop - ref)) <= 1.e-13 * scale
+    monkeypatch.setenv("TRV_ASSIGN_TILE", "1")
+    tile = core.mesh(pos, L, ngrid, assignment, stage=0, weights=w)
+    assert np.max(np.abs(tile - ref)) <= 1.e-13 * scale
+
+
 @pytest.mark.parametrize("assignment", ["cic", "pcs"])
 def test_assignment_shadow_mesh_and_interlacing(core, oracle, assignment):
     """Half-cell-shifted shadow mesh + interlaced FFT (S/field.cpp:1056-1111,

@@ -3,13 +3,23 @@
 //
 // Replaces the OpenMP scatter loops of S/field.cpp:618-1112 and the weight
 // kernels of S/field.cpp:1259-1269,1379-1391.  Two modes:
-//   throughput     particles are counting-sorted by 4^3-cell tile and their
-//                  columns gathered into that order; for TSC/PCS a warp then
-//                  spreads ONE particle per instruction, lanes = (row, z-cell)
-//                  of its stencil, so the red.global.add.f64 of a stencil row
-//                  coalesce into one or two 32-byte L2 sectors (the L2 retires
-//                  ~one RED sector per slice per clock: sectors, not elements,
-//                  are the cost).  NGP/CIC: one thread per particle.
+//   throughput     particles are counting-sorted by (32x16x8-cell tile, 4x4 column
+//                  of the tile) and their columns gathered into that order as
+//                  32-byte records {n x / L, w}.  TSC/PCS (k_assign_coop): a warp
+//                  spreads ONE particle per instruction, lanes = (row, z-cell) of
+//                  its stencil, so the red.global.add.f64 of a stencil row coalesce
+//                  into one or two 32-byte L2 sectors (the L2 retires ~one RED
+//                  sector per slice per clock: sectors, not elements, are the
+//                  cost).  NGP/CIC: one thread per particle.  Opt-in
+//                  (TRV_ASSIGN_TILE=1, unshifted TSC/PCS): k_assign_tile, one CTA
+//                  per tile accumulates the tile's footprint (35x19x11 cells) in
+//                  SHARED memory -- half-warps spread one particle per step with
+//                  plain LDS/DFMA/STS, columns of equal (x, y) parity have
+//                  disjoint stencils so the 8 half-warps of a CTA work without
+//                  atomics -- and flushes it with one RED per footprint cell
+//                  (3.4x fewer RED sectors).  Measured: no faster than the
+//                  cooperative scatter (SM-latency bound at 8 warps per SM), see
+//                  profiles/r01d_assign_tile_vs_coop.txt.
 //   deterministic  particles are counting-sorted by home cell with ascending
 //                  particle id inside a cell; one thread per OUTPUT cell
 //                  gathers its contributions and adds them in ascending
@@ -25,13 +35,16 @@ namespace {
 
 // loc_grid = ngrid * pos / boxsize (+0.5 and wrap for the shadow mesh),
 // S/field.cpp:643-644, 689-694.
-__device__ __forceinline__ double grid_loc(double pos, int n, double L, int shifted) {
-  double loc = __ddiv_rn(__dmul_rn((double)n, pos), L);
+__device__ __forceinline__ double shift_loc(double loc, int n, int shifted) {
   if (shifted) {
     loc = __dadd_rn(loc, 0.5);
     if (loc > (double)n) loc = __dsub_rn(loc, (double)n);
   }
   return loc;
+}
+
+__device__ __forceinline__ double grid_loc(double pos, int n, double L, int shifted) {
+  return shift_loc(__ddiv_rn(__dmul_rn((double)n, pos), L), n, shifted);
 }
 
 template <int ORDER>
@@ -145,10 +158,12 @@ __device__ __forceinline__ cplx particle_weight(const CatView& c, long long i,
   return out;
 }
 
-// The catalogue in sort order: positions and weight packed as one 32-byte
-// record per particle (a single sector per particle for the spreading kernels).
+// The catalogue in sort order: one 32-byte record per particle (a single sector
+// for the spreading kernels) holding the GRID coordinates loc = n x / L of the
+// unshifted mesh -- evaluated once by the sort, with the reference's operation
+// order, instead of three fp64 divisions per particle per assignment -- and w.
 struct SortedView {
-  const double4* p4;                                      // {x, y, z, w}
+  const double4* p4;                                      // {loc_x, loc_y, loc_z, w}
   const double* lx; const double* ly; const double* lz;   // may be null
   const double* cw;                                       // may be null
   long long n;
@@ -180,19 +195,26 @@ __device__ __forceinline__ cplx particle_weight(const SortedView& c, long long i
 // Counting sort by tile (throughput) or by home cell (deterministic).
 // ---------------------------------------------------------------------
 
-constexpr int TILE_SHIFT = 2;   // 4^3-cell tiles for the throughput sort key
+// Throughput sort key: home-cell tile of TILE_X x TILE_Y x TILE_Z cells, then the
+// column (COL_W x COL_W cells in x, y; full tile depth) inside it.
+constexpr int TILE_X = 32, TILE_Y = 16, TILE_Z = 8, COL_W = 4;
+constexpr int COLS_X = TILE_X / COL_W, COLS_Y = TILE_Y / COL_W;   // columns per tile edge
+constexpr int KEYS_PER_TILE = COLS_X * COLS_Y;
 
 struct SortDesc {
   int n[3]; double L[3]; int shifted;
-  int by_cell;          // 0: tile key, 1: home-cell key
-  int nk[3];            // key-grid extents
+  int by_cell;          // 0: (tile, column) key, 1: home-cell key
+  int nk[3];            // key-grid extents: tiles (by_cell == 0) or cells
 };
 
 __device__ __forceinline__ int sort_key(const SortDesc& d, double x, double y, double z) {
   int i = home_index(x, d.n[0], d.L[0], d.shifted);
   int j = home_index(y, d.n[1], d.L[1], d.shifted);
   int k = home_index(z, d.n[2], d.L[2], d.shifted);
-  if (!d.by_cell) { i >>= TILE_SHIFT; j >>= TILE_SHIFT; k >>= TILE_SHIFT; }
+  if (!d.by_cell) {
+    const int tile = ((i / TILE_X) * d.nk[1] + j / TILE_Y) * d.nk[2] + k / TILE_Z;
+    return tile * KEYS_PER_TILE + ((i % TILE_X) / COL_W) * COLS_Y + (j % TILE_Y) / COL_W;
+  }
   return (i * d.nk[1] + j) * d.nk[2] + k;
 }
 
@@ -294,7 +316,10 @@ __global__ void k_sort_scatter(CatView c, SortDesc d, int* __restrict__ cursor,
     int key = sort_key(d, x, y, z);
     int pos = atomicAdd(&cursor[key], 1);
     order[pos] = (int)i;
-    if (s4) s4[pos] = make_double4(x, y, z, c.w ? c.w[i] : 1.);
+    if (s4) {
+      s4[pos] = make_double4(grid_loc(x, d.n[0], d.L[0], 0), grid_loc(y, d.n[1], d.L[1], 0),
+                             grid_loc(z, d.n[2], d.L[2], 0), c.w ? c.w[i] : 1.);
+    }
   }
 }
 
@@ -318,13 +343,16 @@ __global__ void k_sort_segments(const int* __restrict__ seg_end, long long nkeys
 
 // Gather catalogue columns into sorted order: the packed records (when the
 // scatter did not write them), lines of sight and custom weights.
-__global__ void k_gather_sorted(CatView c, const int* __restrict__ order,
+__global__ void k_gather_sorted(CatView c, SortDesc d, const int* __restrict__ order,
                                 double4* __restrict__ s4, double* __restrict__ slos,
                                 double* __restrict__ scw) {
   for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < c.n;
        s += (long long)gridDim.x * blockDim.x) {
     const long long i = order[s];
-    if (s4) s4[s] = make_double4(c.x[i], c.y[i], c.z[i], c.w ? c.w[i] : 1.);
+    if (s4) {
+      s4[s] = make_double4(grid_loc(c.x[i], d.n[0], d.L[0], 0), grid_loc(c.y[i], d.n[1], d.L[1], 0),
+                           grid_loc(c.z[i], d.n[2], d.L[2], 0), c.w ? c.w[i] : 1.);
+    }
     if (slos) { slos[s] = c.lx[i]; slos[c.n + s] = c.ly[i]; slos[2 * c.n + s] = c.lz[i]; }
     if (scw) { scw[2 * s] = c.cw[2 * i]; scw[2 * s + 1] = c.cw[2 * i + 1]; }
   }
@@ -338,16 +366,15 @@ __global__ void k_gather_sorted(CatView c, const int* __restrict__ order,
 template <int ORDER, bool COMPLEX>
 __global__ void __launch_bounds__(256)
 k_assign_scatter(SortedView c, GridDesc g, int shifted,
-                 int kind, int L, int M, double scale, double* __restrict__ mesh) {
-  const YlmCoef yc = ylm_coef(L, M);
+                 int kind, YlmCoef yc, double scale, double* __restrict__ mesh) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < c.n;
        i += (long long)gridDim.x * blockDim.x) {
     int ijk[3][ORDER];
     double win[3][ORDER];
     const double4 p = c.p4[i];
-    window_1d<ORDER>(grid_loc(p.x, g.n[0], g.L[0], shifted), g.n[0], ijk[0], win[0]);
-    window_1d<ORDER>(grid_loc(p.y, g.n[1], g.L[1], shifted), g.n[1], ijk[1], win[1]);
-    window_1d<ORDER>(grid_loc(p.z, g.n[2], g.L[2], shifted), g.n[2], ijk[2], win[2]);
+    window_1d<ORDER>(shift_loc(p.x, g.n[0], shifted), g.n[0], ijk[0], win[0]);
+    window_1d<ORDER>(shift_loc(p.y, g.n[1], shifted), g.n[1], ijk[1], win[1]);
+    window_1d<ORDER>(shift_loc(p.z, g.n[2], shifted), g.n[2], ijk[2], win[2]);
     cplx wt = particle_weight(c, i, p, kind, yc);
     const double bre = __dmul_rn(scale, wt.re);
     const double bim = COMPLEX ? __dmul_rn(scale, wt.im) : 0.;
@@ -385,7 +412,7 @@ k_assign_scatter(SortedView c, GridDesc g, int shifted,
 template <int ORDER, bool COMPLEX>
 __global__ void __launch_bounds__(256)
 k_assign_coop(SortedView c, GridDesc g, int shifted,
-              int kind, int L, int M, double scale, double* __restrict__ mesh) {
+              int kind, YlmCoef yc, double scale, double* __restrict__ mesh) {
   constexpr int NW = 8;                               // warps per block
   constexpr int LPR = ORDER * (COMPLEX ? 2 : 1);      // lanes per stencil row
   constexpr int RPP = 32 / LPR;                       // rows per instruction
@@ -399,7 +426,6 @@ k_assign_coop(SortedView c, GridDesc g, int shifted,
   const int cz = COMPLEX ? (q >> 1) : q;
   const int comp = COMPLEX ? (q & 1) : 0;
   const long long nchunk = (c.n + 31) / 32;
-  const YlmCoef yc = ylm_coef(L, M);
   for (long long chunk = (long long)blockIdx.x * NW + warp; chunk < nchunk;
        chunk += (long long)gridDim.x * NW) {
     const long long i = chunk * 32 + lane;
@@ -408,13 +434,13 @@ k_assign_coop(SortedView c, GridDesc g, int shifted,
     if (ok) {
       int ijk[ORDER]; double win[ORDER];
       const double4 p = c.p4[i];
-      window_1d<ORDER>(grid_loc(p.x, g.n[0], g.L[0], shifted), g.n[0], ijk, win);
+      window_1d<ORDER>(shift_loc(p.x, g.n[0], shifted), g.n[0], ijk, win);
 #pragma unroll
       for (int t = 0; t < ORDER; t++) { s_win[warp][lane][t] = win[t]; s_idx[warp][lane][t] = ijk[t]; }
-      window_1d<ORDER>(grid_loc(p.y, g.n[1], g.L[1], shifted), g.n[1], ijk, win);
+      window_1d<ORDER>(shift_loc(p.y, g.n[1], shifted), g.n[1], ijk, win);
 #pragma unroll
       for (int t = 0; t < ORDER; t++) { s_win[warp][lane][ORDER + t] = win[t]; s_idx[warp][lane][ORDER + t] = ijk[t]; }
-      window_1d<ORDER>(grid_loc(p.z, g.n[2], g.L[2], shifted), g.n[2], ijk, win);
+      window_1d<ORDER>(shift_loc(p.z, g.n[2], shifted), g.n[2], ijk, win);
 #pragma unroll
       for (int t = 0; t < ORDER; t++) { s_win[warp][lane][2 * ORDER + t] = win[t]; s_idx[warp][lane][2 * ORDER + t] = ijk[t]; }
       const cplx wt = particle_weight(c, i, p, kind, yc);
@@ -448,6 +474,291 @@ k_assign_coop(SortedView c, GridDesc g, int shifted,
 }
 
 // ---------------------------------------------------------------------
+// Tile-owned shared-memory accumulation (TSC/PCS, unshifted mesh).
+// ---------------------------------------------------------------------
+
+// Footprint of a tile's stencils: cells [t0 - 1, t0 + TILE + 1] per axis.
+constexpr int FP_X = TILE_X + 3, FP_Y = TILE_Y + 3, FP_Z = TILE_Z + 3;
+constexpr int TILE_SLOTS = 32;     // particles staged per warp per round (16 per column)
+constexpr int TILE_WARPS = 4;      // x 2 columns each = the 8 columns of one colour
+
+// Shared-tile pitches in doubles.  A half-warp spreads one particle: lane ->
+// stencil row (a, b), walking the row's z-cells.  REAL: row pitch 24 words puts
+// b = 0..3 on banks {0, 24, 16, 8}; plane pitch == 2 (mod 32) words shifts a by one
+// double: the 16 rows of a half-warp hit 16 distinct bank pairs.  COMPLEX (16-byte
+// cells): row pitch 56 words, plane pitch == 4 (mod 32): each quarter-warp covers
+// all 32 banks once.
+template <bool COMPLEX> struct TileGeom;
+template <> struct TileGeom<false> {
+  static constexpr int CW = 1, ROW = 12, PLANE = FP_Y * 12 + 13;      // 241 doubles = 482 words
+};
+template <> struct TileGeom<true> {
+  static constexpr int CW = 2, ROW = 28, PLANE = FP_Y * 28 + 14;      // 546 doubles = 1092 words
+};
+
+// Per-particle staging, read as 16-byte words during the spread: per stencil
+// entry along x {window weight, (z offset << 32) | x offset} and along y {window
+// weight, y offset}; the z weights, already multiplied by the particle weight.
+// The z-run of a stencil row is contiguous in the tile.
+template <bool COMPLEX> struct StageT;
+template <> struct StageT<false> { double2 x[4], y[4]; double2 zp[2]; };     // 160 B
+template <> struct StageT<true> { double2 x[4], y[4]; double2 zp[4]; };      // 192 B
+
+template <bool COMPLEX>
+constexpr size_t tile_smem_bytes() {
+  return sizeof(double) * ((FP_X * TileGeom<COMPLEX>::PLANE + 1) & ~1)
+    + sizeof(StageT<COMPLEX>) * TILE_SLOTS * TILE_WARPS;
+}
+
+// Reference-order scatter of ONE particle straight to global memory (the body
+// of k_assign_scatter): slow path for particles outside [0, L).
+template <int ORDER, bool COMPLEX>
+__device__ void scatter_one(const double4& p, double bre, double bim, const GridDesc& g,
+                            double* __restrict__ mesh) {
+  int ijk[3][ORDER];
+  double win[3][ORDER];
+  window_1d<ORDER>(p.x, g.n[0], ijk[0], win[0]);
+  window_1d<ORDER>(p.y, g.n[1], ijk[1], win[1]);
+  window_1d<ORDER>(p.z, g.n[2], ijk[2], win[2]);
+  for (int a = 0; a < ORDER; a++) {
+    for (int b = 0; b < ORDER; b++) {
+      const long long row = ((long long)ijk[0][a] * g.n[1] + ijk[1][b]) * g.n[2];
+      const double wab = __dmul_rn(win[0][a], win[1][b]);
+      for (int cidx = 0; cidx < ORDER; cidx++) {
+        const long long gid = row + ijk[2][cidx];
+        if (gid >= 0 && gid < g.nmesh) {   // S/field.cpp:1042
+          const double wabc = __dmul_rn(wab, win[2][cidx]);
+          if (COMPLEX) {
+            atomicAdd(&mesh[2 * gid], __dmul_rn(bre, wabc));
+            atomicAdd(&mesh[2 * gid + 1], __dmul_rn(bim, wabc));
+          } else {
+            atomicAdd(&mesh[gid], __dmul_rn(bre, wabc));
+          }
+        }
+      }
+    }
+  }
+}
+
+// Local (tile footprint) index of mesh cell `idx` along an axis of n cells whose
+// footprint starts at cell `origin` (= t0 - 1, may be -1); -1 if outside the
+// footprint or outside the mesh (positions beyond the box edge: the reference
+// does not wrap those, see scatter_one).  Requires n >= extent.
+__device__ __forceinline__ int local_index(int idx, int origin, int n, int extent) {
+  if ((unsigned)idx >= (unsigned)n) return -1;
+  int la = idx - origin;
+  if (la >= n) la -= n;
+  if (la < 0) la += n;
+  return ((unsigned)la < (unsigned)extent) ? la : -1;
+}
+
+template <int ORDER, bool COMPLEX>
+__global__ void __launch_bounds__(TILE_WARPS * 32)
+k_assign_tile(SortedView c, const int* __restrict__ key_start, int nt1, int nt2,
+              GridDesc g, int kind, YlmCoef yc, double scale, double* __restrict__ mesh) {
+  typedef TileGeom<COMPLEX> G;
+  typedef StageT<COMPLEX> Stage;
+  constexpr int NT = (FP_X * G::PLANE + 1) & ~1;        // doubles in the shared tile (even)
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* tile = reinterpret_cast<double*>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  Stage* st = reinterpret_cast<Stage*>(tile + NT) + warp * TILE_SLOTS;
+
+  // The tile's KEYS_PER_TILE (= 32) column offsets live in one register per lane
+  // (+ the end offset in every lane): one load latency per warp, no further
+  // dependent offset loads.
+  static_assert(KEYS_PER_TILE == 32, "one column offset per lane");
+  const int key0 = blockIdx.x * KEYS_PER_TILE;
+  const int key_lane = key_start[key0 + lane];
+  const int key_end = key_start[key0 + KEYS_PER_TILE];
+  if (__shfl_sync(0xffffffffu, key_lane, 0) == key_end) return;   // empty: mesh already zero
+  const int tk = blockIdx.x % nt2, tj = (blockIdx.x / nt2) % nt1, ti = blockIdx.x / (nt2 * nt1);
+  const int o0 = ti * TILE_X - 1, o1 = tj * TILE_Y - 1, o2 = tk * TILE_Z - 1;
+
+  // Spreading role of a lane: half-warp h works on column h of the warp's pair,
+  // lane & 15 is the stencil row (a, b).  Idle lanes and idle steps add zeros to
+  // a private scratch run in the padding of plane `lane` (no divergence).
+  const int h = lane >> 4, row = lane & 15;
+  const int ra = (row < ORDER * ORDER) ? row / ORDER : 0;
+  const int rb = (row < ORDER * ORDER) ? row - ra * ORDER : 0;
+  const bool row_active = row < ORDER * ORDER;
+  const int scratch_off = lane * G::PLANE + FP_Y * G::ROW;
+
+  // Segments [b, e) of the two columns this warp spreads in a colour: the 8 columns
+  // with (cx, cy) == (colour & 1, colour >> 1) (mod 2) have disjoint 7-cell-wide
+  // footprints; column q = 2 * warp + h of them goes to half-warp h.
+  auto segments = [&](int colour, int* seg_b, int* seg_e) {
+#pragma unroll
+    for (int hh = 0; hh < 2; hh++) {
+      const int q = 2 * warp + hh;
+      const int cx = (colour & 1) + 2 * (q & 3), cy = (colour >> 1) + 2 * (q >> 2);
+      const int key = cx * COLS_Y + cy;
+      seg_b[hh] = __shfl_sync(0xffffffffu, key_lane, key);
+      const int nxt = __shfl_sync(0xffffffffu, key_lane, (key + 1) & 31);
+      seg_e[hh] = (key + 1 < KEYS_PER_TILE) ? nxt : key_end;
+    }
+  };
+  // Records are requested ahead of use so that their HBM latency hides behind the
+  // zero-fill and the spreading: the first round of ALL four colours up front (at
+  // survey densities a column rarely holds more than the 16 particles of a round),
+  // later rounds of a colour one round ahead.
+  auto fetch = [&](int colour, int r0, double4& dst) {
+    int sb[2], se[2];
+    segments(colour, sb, se);
+    const int idx = (h ? sb[1] : sb[0]) + r0 + row;
+    if (idx < (h ? se[1] : se[0])) dst = c.p4[idx];
+  };
+  double4 p_first[4];
+#pragma unroll
+  for (int colour = 0; colour < 4; colour++) {
+    p_first[colour] = make_double4(0., 0., 0., 0.);
+    fetch(colour, 0, p_first[colour]);
+  }
+
+  for (int t = threadIdx.x; t < NT / 2; t += blockDim.x) {
+    reinterpret_cast<double2*>(tile)[t] = make_double2(0., 0.);
+  }
+  __syncthreads();
+
+  for (int colour = 0; colour < 4; colour++) {
+    int seg_b[2], seg_e[2];
+    segments(colour, seg_b, seg_e);
+    const int my_b = h ? seg_b[1] : seg_b[0], my_e = h ? seg_e[1] : seg_e[0];
+    const int longest = max(seg_e[0] - seg_b[0], seg_e[1] - seg_b[1]);
+    double4 p_next = p_first[0];
+#pragma unroll
+    for (int t = 1; t < 4; t++) if (colour == t) p_next = p_first[t];   // registers, no local array
+    for (int r0 = 0; r0 < longest; r0 += 16) {
+      const double4 p = p_next;
+      if (r0 + 16 < longest) fetch(colour, r0 + 16, p_next);
+      // ---- stage: one lane per particle, slot = lane ---------------------------
+      __syncwarp();
+      if (my_b + r0 + row < my_e) {
+        const long long i = my_b + r0 + row;
+        const cplx wt = particle_weight(c, i, p, kind, yc);
+        const double bre = __dmul_rn(scale, wt.re);
+        const double bim = COMPLEX ? __dmul_rn(scale, wt.im) : 0.;
+        Stage& s = st[lane];
+        int ix[ORDER], iy[ORDER], iz[ORDER];
+        double wx[ORDER], wy[ORDER], wz[ORDER];
+        window_1d<ORDER>(p.x, g.n[0], ix, wx);
+        window_1d<ORDER>(p.y, g.n[1], iy, wy);
+        window_1d<ORDER>(p.z, g.n[2], iz, wz);
+        // Inside the box the stencil indices are consecutive (mod n), so the first
+        // one fixes the run in the tile footprint.
+        bool ok = true;
+#pragma unroll
+        for (int t = 0; t < ORDER; t++) {
+          ok = ok && (unsigned)ix[t] < (unsigned)g.n[0] && (unsigned)iy[t] < (unsigned)g.n[1]
+            && (unsigned)iz[t] < (unsigned)g.n[2];
+        }
+        const int lx0 = local_index(ix[0], o0, g.n[0], FP_X - ORDER + 1);
+        const int ly0 = local_index(iy[0], o1, g.n[1], FP_Y - ORDER + 1);
+        const int lz0 = local_index(iz[0], o2, g.n[2], FP_Z - ORDER + 1);
+        ok = ok && lx0 >= 0 && ly0 >= 0 && lz0 >= 0;
+        if (!ok) {
+          // Position outside [0, L): follow the reference's index arithmetic and
+          // its bounds guard in global memory; contribute nothing to the tile.
+          scatter_one<ORDER, COMPLEX>(p, bre, bim, g, mesh);
+        }
+        const int zoff = ok ? lz0 * G::CW : 0;
+#pragma unroll
+        for (int t = 0; t < ORDER; t++) {
+          s.x[t] = make_double2(wx[t], __hiloint2double(zoff, ok ? (lx0 + t) * G::PLANE : 0));
+          s.y[t] = make_double2(wy[t], __hiloint2double(0, ok ? (ly0 + t) * G::ROW : 0));
+        }
+        double zr[4], zi[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+          zr[t] = (ok && t < ORDER) ? __dmul_rn(bre, wz[t < ORDER ? t : 0]) : 0.;
+          zi[t] = (COMPLEX && ok && t < ORDER) ? __dmul_rn(bim, wz[t < ORDER ? t : 0]) : 0.;
+        }
+        if constexpr (COMPLEX) {
+#pragma unroll
+          for (int t = 0; t < 4; t++) s.zp[t] = make_double2(zr[t], zi[t]);
+        } else {
+          s.zp[0] = make_double2(zr[0], zr[1]);
+          s.zp[1] = make_double2(zr[2], zr[3]);
+        }
+      }
+      __syncwarp();
+      // ---- spread: one particle per half-warp per step, staging prefetched ------
+      const int cnt = min(16, my_e - my_b - r0);
+      const int steps = min(16, longest - r0);
+      const Stage* sp = st + h * 16;
+      double2 X = sp->x[ra], Y = sp->y[rb];
+      double2 Z[COMPLEX ? 4 : 2];
+#pragma unroll
+      for (int t = 0; t < (COMPLEX ? 4 : 2); t++) Z[t] = sp->zp[t];
+      for (int sdx = 0; sdx < steps; sdx++) {
+        const bool live = row_active && sdx < cnt;
+        const double wxy = live ? X.x * Y.x : 0.;
+        double* cell = tile
+          + (live ? __double2loint(X.y) + __double2loint(Y.y) + __double2hiint(X.y) : scratch_off);
+        double2 Zc[COMPLEX ? 4 : 2];
+#pragma unroll
+        for (int t = 0; t < (COMPLEX ? 4 : 2); t++) Zc[t] = Z[t];
+        if constexpr (COMPLEX) {
+          double2 v[ORDER];
+#pragma unroll
+          for (int t = 0; t < ORDER; t++) v[t] = reinterpret_cast<const double2*>(cell)[t];
+          // next particle's staging (slots past the column's end hold stale, masked data)
+          sp = st + h * 16 + min(sdx + 1, 15);
+          X = sp->x[ra]; Y = sp->y[rb];
+#pragma unroll
+          for (int t = 0; t < 4; t++) Z[t] = sp->zp[t];
+#pragma unroll
+          for (int t = 0; t < ORDER; t++) {
+            v[t].x = fma(wxy, Zc[t].x, v[t].x);
+            v[t].y = fma(wxy, Zc[t].y, v[t].y);
+            reinterpret_cast<double2*>(cell)[t] = v[t];
+          }
+        } else {
+          double v[ORDER];
+#pragma unroll
+          for (int t = 0; t < ORDER; t++) v[t] = cell[t];
+          sp = st + h * 16 + min(sdx + 1, 15);
+          X = sp->x[ra]; Y = sp->y[rb];
+          Z[0] = sp->zp[0]; Z[1] = sp->zp[1];
+          const double zc[4] = {Zc[0].x, Zc[0].y, Zc[1].x, Zc[1].y};
+#pragma unroll
+          for (int t = 0; t < ORDER; t++) cell[t] = fma(wxy, zc[t], v[t]);
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+  }
+
+  // Flush the footprint with REDs.  A thread owns one (ly, lz) of the 19 x 11 plane
+  // (two passes) and walks the planes along x: constant strides, consecutive lanes
+  // along z, no index arithmetic in the loop.
+  const long long xstride = (long long)g.n[1] * g.n[2] * G::CW;
+  for (int pq = threadIdx.x; pq < FP_Y * FP_Z; pq += blockDim.x) {
+    const int ly = pq / FP_Z, lz = pq - ly * FP_Z;
+    int gy = o1 + ly, gz = o2 + lz;                     // n >= footprint: one wrap suffices
+    gy += (gy < 0) ? g.n[1] : 0; gy -= (gy >= g.n[1]) ? g.n[1] : 0;
+    gz += (gz < 0) ? g.n[2] : 0; gz -= (gz >= g.n[2]) ? g.n[2] : 0;
+    int gx = (o0 < 0) ? o0 + g.n[0] : o0;
+    double* dst = mesh + (((long long)gx * g.n[1] + gy) * g.n[2] + gz) * G::CW;
+    const double* src = tile + ly * G::ROW + lz * G::CW;
+#pragma unroll 5
+    for (int lx = 0; lx < FP_X; lx++) {
+      const double vre = src[0];
+      if (COMPLEX) {
+        const double vim = src[1];
+        if (vre != 0. || vim != 0.) { atomicAdd(dst, vre); atomicAdd(dst + 1, vim); }
+      } else {
+        if (vre != 0.) atomicAdd(dst, vre);
+      }
+      src += G::PLANE;
+      dst += xstride;
+      if (++gx == g.n[0]) { gx = 0; dst -= xstride * g.n[0]; }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------
 // Deterministic assignment: one thread per output cell, ordered gather.
 // ---------------------------------------------------------------------
 
@@ -461,17 +772,17 @@ __device__ __forceinline__ bool contribution(
   int ijk[ORDER]; double win[ORDER];
   bool hit;
   const double4 p = c.p4[pid];
-  window_1d<ORDER>(grid_loc(p.x, g.n[0], g.L[0], shifted), g.n[0], ijk, win);
+  window_1d<ORDER>(shift_loc(p.x, g.n[0], shifted), g.n[0], ijk, win);
   hit = false;
 #pragma unroll
   for (int a = 0; a < ORDER; a++) if (ijk[a] == ci) { wprod_x = win[a]; hit = true; }
   if (!hit) return false;
-  window_1d<ORDER>(grid_loc(p.y, g.n[1], g.L[1], shifted), g.n[1], ijk, win);
+  window_1d<ORDER>(shift_loc(p.y, g.n[1], shifted), g.n[1], ijk, win);
   hit = false;
 #pragma unroll
   for (int a = 0; a < ORDER; a++) if (ijk[a] == cj) { wprod_y = win[a]; hit = true; }
   if (!hit) return false;
-  window_1d<ORDER>(grid_loc(p.z, g.n[2], g.L[2], shifted), g.n[2], ijk, win);
+  window_1d<ORDER>(shift_loc(p.z, g.n[2], shifted), g.n[2], ijk, win);
   hit = false;
 #pragma unroll
   for (int a = 0; a < ORDER; a++) if (ijk[a] == ck) { wprod_z = win[a]; hit = true; }
@@ -482,7 +793,7 @@ template <int ORDER, bool COMPLEX>
 __global__ void __launch_bounds__(128)
 k_assign_gather(SortedView c, const int* __restrict__ order,
                 const int* __restrict__ cell_start, GridDesc g, int shifted,
-                int kind, int L, int M, double scale, double pre /* 1/vol_cell or 1 */,
+                int kind, YlmCoef yc, double scale, double pre /* 1/vol_cell or 1 */,
                 int accumulate, double* __restrict__ mesh) {
   // Home cells whose particles can reach output index q along an axis:
   // q - LO .. q + HI (periodic).  PCS/TSC: home in {q-2..q+1}; CIC/NGP: {q-1, q}.
@@ -501,7 +812,6 @@ k_assign_gather(SortedView c, const int* __restrict__ order,
   int ncand = 0;
   bool overflow = false;
 
-  const YlmCoef yc = ylm_coef(L, M);
   auto value_of = [&](int slot, double wx, double wy, double wz, double& vre, double& vim) {
     cplx wt = particle_weight(c, slot, c.p4[slot], kind, yc);
     // ((((inv_vol_cell * w) * Wx) * Wy) * Wz), S/field.cpp:1044-1048.
@@ -674,15 +984,19 @@ int gather_sorted(trvb_ctx* ctx, trvb_cat* cat, bool with_records) {
   cat->scw_valid = cat->cw != nullptr;
   if (!with_records && !cat->slos && !cat->scw) return 0;
   const int blocks = (int)std::min<long long>(div_up(cat->n, 256), (long long)ctx->num_sms * 16);
-  k_gather_sorted<<<blocks, 256, 0, ctx->stream>>>(view_of(cat), cat->order,
+  SortDesc d;
+  for (int a = 0; a < 3; a++) { d.n[a] = ctx->g.n[a]; d.L[a] = ctx->g.L[a]; d.nk[a] = 0; }
+  d.shifted = 0; d.by_cell = 0;
+  k_gather_sorted<<<blocks, 256, 0, ctx->stream>>>(view_of(cat), d, cat->order,
                                                   with_records ? cat->s4 : nullptr,
                                                   cat->slos, cat->scw);
   TRVB_LAUNCH_CHECK();
   return 0;
 }
 
-// by_cell == 0: throughput order (4^3-cell tiles of the UNSHIFTED home cell;
-// it only provides locality, so it also serves the shifted shadow mesh).
+// by_cell == 0: throughput order ((tile, column) of the UNSHIFTED home cell, plus
+// the key offsets k_assign_tile needs; for the shifted shadow mesh it only
+// provides locality).
 // by_cell == 1: home cell of the (possibly shifted) mesh, ascending particle id
 // inside a cell, plus the cell offsets the ordered gather needs.
 int ensure_sorted(trvb_ctx* ctx, trvb_cat* cat, int shifted, int by_cell) {
@@ -700,10 +1014,12 @@ int ensure_sorted(trvb_ctx* ctx, trvb_cat* cat, int shifted, int by_cell) {
   SortDesc d;
   for (int a = 0; a < 3; a++) {
     d.n[a] = g.n[a]; d.L[a] = g.L[a];
-    d.nk[a] = by_cell ? g.n[a] : ((g.n[a] + (1 << TILE_SHIFT) - 1) >> TILE_SHIFT);
+    const int tile = (a == 0) ? TILE_X : (a == 1) ? TILE_Y : TILE_Z;
+    d.nk[a] = by_cell ? g.n[a] : (g.n[a] + tile - 1) / tile;
   }
   d.shifted = shifted; d.by_cell = by_cell;
-  const long long nkeys = (long long)d.nk[0] * d.nk[1] * d.nk[2];
+  const long long nkeys = (long long)d.nk[0] * d.nk[1] * d.nk[2] * (by_cell ? 1 : KEYS_PER_TILE);
+  TRVB_REQUIRE(nkeys < 2147483647LL, "mesh too large for int sort keys");
   TRVB_REQUIRE(cat->n < 2147483647LL, "catalogue too large for int indices");
   if (!cat->order) TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->order, sizeof(int) * (size_t)cat->n));
   { int st = alloc_sorted(ctx, cat); if (st) return st; }
@@ -741,11 +1057,10 @@ int ensure_sorted(trvb_ctx* ctx, trvb_cat* cat, int shifted, int by_cell) {
     const int sb = (int)std::min<long long>(div_up(nkeys, threads), (long long)ctx->num_sms * 32);
     k_sort_segments<<<sb, threads, 0, ctx->stream>>>(cursor, nkeys, cat->order);
     TRVB_LAUNCH_CHECK();
-    cat->cell_start = offsets;
   }
+  cat->cell_start = offsets;   // key offsets: cells (deterministic) or (tile, column)
   TRVB_CUDA(trvb_dev_free_raw(ctx, cursor));   // stream-ordered reuse: no sync
   TRVB_CUDA(trvb_dev_free_raw(ctx, chunk_sums));
-  if (!by_cell) TRVB_CUDA(trvb_dev_free_raw(ctx, offsets));
   for (int a = 0; a < 3; a++) { cat->sort_n[a] = g.n[a]; cat->sort_L[a] = g.L[a]; }
   cat->sort_shifted = shifted; cat->sort_kind = by_cell;
   return gather_sorted(ctx, cat, by_cell != 0);
@@ -757,6 +1072,9 @@ int launch_assign(trvb_ctx* ctx, trvb_cat* cat, int kind, int L, int M, double s
                   trvb_mesh mesh) {
   const GridDesc& g = ctx->g;
   const bool cplx_mesh = mesh.layout == TRVB_COMPLEX;
+  // y_LM recursion coefficients: evaluated once on the host (IEEE sqrt and division,
+  // the same bits as on the device) instead of once per thread.
+  const YlmCoef yc = ylm_coef(L, M);
   if (mode == 0) {
     int st = ensure_sorted(ctx, cat, shifted, 0);
     if (st) return st;
@@ -766,24 +1084,52 @@ int launch_assign(trvb_ctx* ctx, trvb_cat* cat, int kind, int L, int M, double s
     }
     const double s = density_units ? scale * (1. / g.vol_cell) : scale;
     const int threads = 256;
-    if (ORDER >= 3) {
+    // TRV_ASSIGN_TILE=1 selects the tile-owned shared-memory kernel.  Measured on
+    // B200 (profiles/r01d_assign_tile_vs_coop.txt) it only ties the cooperative
+    // scatter on C2 (1.67 vs 1.61 ms) and loses on the dense C3 randoms: it trades
+    // the L2 RED-sector bound for an SM latency bound at 8 warps per SM, so the
+    // cooperative scatter stays the default.
+    const char* env_tile = getenv("TRV_ASSIGN_TILE");
+    const bool use_tile = env_tile != nullptr && env_tile[0] == '1';
+    // The tile kernel needs the mesh to be at least one footprint wide (no
+    // self-overlap of a tile's periodic footprint).
+    const bool fits = g.n[0] >= FP_X && g.n[1] >= FP_Y && g.n[2] >= FP_Z;
+    if (ORDER >= 3 && !shifted && use_tile && fits) {
+      constexpr int O = ORDER >= 3 ? ORDER : 3;
+      const int nt[3] = {(g.n[0] + TILE_X - 1) / TILE_X, (g.n[1] + TILE_Y - 1) / TILE_Y,
+                         (g.n[2] + TILE_Z - 1) / TILE_Z};
+      const int ntiles = nt[0] * nt[1] * nt[2];
+      if (cplx_mesh) {
+        TRVB_CUDA(cudaFuncSetAttribute(k_assign_tile<O, true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)tile_smem_bytes<true>()));
+        k_assign_tile<O, true><<<ntiles, TILE_WARPS * 32, tile_smem_bytes<true>(), ctx->stream>>>(
+          cv, cat->cell_start, nt[1], nt[2], g, kind, yc, s, (double*)mesh.data);
+      } else {
+        TRVB_CUDA(cudaFuncSetAttribute(k_assign_tile<O, false>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)tile_smem_bytes<false>()));
+        k_assign_tile<O, false><<<ntiles, TILE_WARPS * 32, tile_smem_bytes<false>(), ctx->stream>>>(
+          cv, cat->cell_start, nt[1], nt[2], g, kind, yc, s, (double*)mesh.data);
+      }
+    } else if (ORDER >= 3) {
       const long long nchunk = (cat->n + 31) / 32;
       const int blocks = (int)std::min<long long>(div_up(nchunk, 8), (long long)ctx->num_sms * 64);
       if (cplx_mesh) {
         k_assign_coop<(ORDER >= 3 ? ORDER : 3), true><<<blocks, threads, 0, ctx->stream>>>(
-          cv, g, shifted, kind, L, M, s, (double*)mesh.data);
+          cv, g, shifted, kind, yc, s, (double*)mesh.data);
       } else {
         k_assign_coop<(ORDER >= 3 ? ORDER : 3), false><<<blocks, threads, 0, ctx->stream>>>(
-          cv, g, shifted, kind, L, M, s, (double*)mesh.data);
+          cv, g, shifted, kind, yc, s, (double*)mesh.data);
       }
     } else {
       const int blocks = div_up(cat->n, threads);
       if (cplx_mesh) {
         k_assign_scatter<ORDER, true><<<blocks, threads, 0, ctx->stream>>>(
-          cv, g, shifted, kind, L, M, s, (double*)mesh.data);
+          cv, g, shifted, kind, yc, s, (double*)mesh.data);
       } else {
         k_assign_scatter<ORDER, false><<<blocks, threads, 0, ctx->stream>>>(
-          cv, g, shifted, kind, L, M, s, (double*)mesh.data);
+          cv, g, shifted, kind, yc, s, (double*)mesh.data);
       }
     }
     TRVB_LAUNCH_CHECK();
@@ -798,11 +1144,11 @@ int launch_assign(trvb_ctx* ctx, trvb_cat* cat, int kind, int L, int M, double s
     const int blocks = div_up(g.nmesh, threads);
     if (cplx_mesh) {
       k_assign_gather<ORDER, true><<<blocks, threads, 0, ctx->stream>>>(
-        cv, cat->order, cat->cell_start, g, shifted, kind, L, M, scale, pre,
+        cv, cat->order, cat->cell_start, g, shifted, kind, yc, scale, pre,
         accumulate, (double*)mesh.data);
     } else {
       k_assign_gather<ORDER, false><<<blocks, threads, 0, ctx->stream>>>(
-        cv, cat->order, cat->cell_start, g, shifted, kind, L, M, scale, pre,
+        cv, cat->order, cat->cell_start, g, shifted, kind, yc, scale, pre,
         accumulate, (double*)mesh.data);
     }
     TRVB_LAUNCH_CHECK();
