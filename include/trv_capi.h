@@ -31,6 +31,15 @@ const char* trv_last_error(void);
  * TRV_GPU_MAXNUM. */
 int trv_gpu_count(void);
 
+/* Multi-GPU work split (no reference counterpart: trv::sys::currTask is the
+ * constant 0, I/monitor.hpp:249-250).  Owner rank in [0, world) of each of the
+ * *dim data-vector entries of a `form` ("diag" | "off-diag" | "row" | "full";
+ * "full" with ell1 == ell2 is the upper triangle, S/parameters.cpp:829-849)
+ * over num_bins bins; `owner` holds >= num_bins^2 ints.  Shares are equal in
+ * size (+-1) and compact in the (row bin, column bin) matrix. */
+int trv_partition_owners(const char* form, int ell1, int ell2, int idx_bin, int num_bins,
+                         int world, int* owner, int* dim);
+
 /* trv::sys::count_fft / count_ifft / gbytesMaxMemGPU (I/monitor.hpp:252-266). */
 void trv_counters(int* count_fft, int* count_ifft, double* gib_gpu_max);
 
@@ -49,8 +58,10 @@ void trv_counters(int* count_fft, int* count_ifft, double* gib_gpu_max);
  *   custom_edges    num_bins+1 edges for binning="custom", else NULL
  *   deterministic   1: bit-reproducible assignment and reductions
  *   part_rank/part_count  multi-GPU work split: this call computes the entries
- *                   idx with idx % part_count == part_rank and leaves zeros
- *                   elsewhere (sum over ranks = the full result)
+ *                   that trv_partition_owners() gives to part_rank (compact
+ *                   blocks of the bin-pair matrix, so that a rank transforms
+ *                   only the shells it pairs) and leaves zeros elsewhere (sum
+ *                   over ranks = the full result)
  * Outputs (capacity >= max(num_bins^2, num_bins) entries): *dim = dv_dim;
  * bin centres, effective coordinates, nmodes/npairs, raw and shot statistics as
  * interleaved (re, im) already multiplied by norm_factor

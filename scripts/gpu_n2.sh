@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_n2.log 2> gpurun_out/bench_n2.err
+echo "rc=$?"; tail -c 1500 gpurun_out/bench_n2.log; tail -5 gpurun_out/bench_n2.err
+timeout 900 python scripts/c5_probe.py > gpurun_out/c5_probe.txt 2>&1; cat gpurun_out/c5_probe.txt

@@ -27,7 +27,7 @@ def _worker(rank, world, port, q):
         gen = np.random.default_rng(99)                     # same "full" result on every rank
         full_raw = gen.normal(size=dim) + 1j * gen.normal(size=dim)
         full_shot = gen.normal(size=dim) + 1j * gen.normal(size=dim)
-        mine = tdist.local_entries(dim, rank, world)
+        mine = tdist.local_entries("full", (0, 0), 20, rank, world)
         part = {"bk_raw": np.zeros(dim, complex), "bk_shot": np.zeros(dim, complex),
                 "k1_eff": np.arange(dim, dtype=float)}
         part["bk_raw"][mine] = full_raw[mine]
@@ -40,16 +40,53 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _pairs_of(form, degrees, nb, idx_bin=0):
+    """(row, col) of every data-vector entry (make_data_vector, src/threept.cpp)."""
+    if form == "full" and degrees[0] == degrees[1]:
+        return [(a, b) for a in range(nb) for b in range(a, nb)]
+    if form == "full":
+        return [(a, b) for a in range(nb) for b in range(nb)]
+    if form == "diag":
+        return [(b, b) for b in range(nb)]
+    if form == "row":
+        return [(idx_bin, b) for b in range(nb)]
+    off = abs(idx_bin)
+    return [(i, i + off) if idx_bin >= 0 else (i + off, i) for i in range(nb - off)]
+
+
 def test_partition_covers_every_entry_once():
     from triumvirate_b200 import dist as tdist
-    for dim in (1, 4, 10, 210, 820):
+    cases = [("full", (0, 0), 1), ("full", (0, 0), 4), ("full", (0, 0), 20), ("full", (0, 0), 40),
+             ("full", (2, 0), 20), ("diag", (2, 0), 20), ("row", (1, 1), 20), ("off-diag", (0, 0), 10)]
+    for form, deg, nb in cases:
+        idx_bin = 3 if form in ("row", "off-diag") else 0
+        pairs = _pairs_of(form, deg, nb, idx_bin)
+        dim = len(pairs)
         for world in (1, 2, 3, 8):
-            seen = np.concatenate([tdist.local_entries(dim, r, world) for r in range(world)])
+            own = tdist.owners(form, deg, nb, world, idx_bin=idx_bin)
+            assert len(own) == dim and own.min() >= 0 and own.max() < world
+            seen = np.concatenate([tdist.local_entries(form, deg, nb, r, world, idx_bin=idx_bin)
+                                   for r in range(world)])
             assert sorted(seen) == list(range(dim))
-            sizes = [len(tdist.local_entries(dim, r, world)) for r in range(world)]
-            assert max(sizes) - min(sizes) <= 1          # balanced
-            for r in range(world):
-                assert all(tdist.owner_of(i, world) == r for i in tdist.local_entries(dim, r, world))
+            sizes = np.bincount(own, minlength=world)
+            assert sizes.max() - sizes.min() <= 1          # balanced
+
+
+def test_partition_is_compact_in_the_pair_matrix():
+    """A rank needs the shell field of every bin that appears in its entries:
+    the block partition must keep that well below `all bins` (the round-robin
+    split of the first version needed all 40 on every one of 8 ranks)."""
+    from triumvirate_b200 import dist as tdist
+    nb, world = 40, 8
+    pairs = np.array(_pairs_of("full", (0, 0), nb))
+    own = tdist.owners("full", (0, 0), nb, world)
+    fields = [len(set(pairs[own == r].ravel())) for r in range(world)]
+    assert max(fields) <= 28 and np.mean(fields) <= 24, fields
+    own2 = tdist.owners("full", (2, 0), 20, 4)       # 20 x 20 entries, distinct row/col fields
+    pairs2 = np.array(_pairs_of("full", (2, 0), 20))
+    for r in range(4):
+        mine = pairs2[own2 == r]
+        assert len(set(mine[:, 0])) + len(set(mine[:, 1])) <= 26
 
 
 def test_pack_unpack_roundtrip():

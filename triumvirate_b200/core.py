@@ -44,6 +44,18 @@ def gpu_count():
     return _trv().trv_gpu_count()
 
 
+def partition_owners(form, degrees, num_bins, world, idx_bin=0):
+    """Owner rank of every data-vector entry (trv::partition_owners)."""
+    owner = np.zeros(max(num_bins * num_bins, num_bins), dtype=np.int32)
+    dim = C.c_int(0)
+    st = _trv().trv_partition_owners(form.encode(), C.c_int(degrees[0]), C.c_int(degrees[1]),
+                                     C.c_int(idx_bin), C.c_int(num_bins), C.c_int(world),
+                                     owner.ctypes.data_as(C.c_void_p), C.byref(dim))
+    if st != 0:
+        raise RuntimeError(_trv().trv_last_error().decode())
+    return owner[:dim.value].copy()
+
+
 def counters():
     f = C.c_int(0); i = C.c_int(0); g = C.c_double(0.)
     _trv().trv_counters(C.byref(f), C.byref(i), C.byref(g))

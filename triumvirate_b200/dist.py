@@ -14,14 +14,16 @@ import numpy as np
 _STAT_KEYS = {"bispec": ("bk_raw", "bk_shot"), "3pcf": ("zeta_raw", "zeta_shot")}
 
 
-def owner_of(idx, world_size):
-    """Rank that computes data-vector entry ``idx`` (round-robin, the rule of
-    ``active_entries`` in src/threept.cpp)."""
-    return idx % world_size
+def owners(form, degrees, num_bins, world_size, idx_bin=0):
+    """Owner rank of every data-vector entry: the rule of ``active_entries`` in
+    src/threept.cpp (``trv::partition_owners``) -- compact blocks of the bin-pair
+    matrix, equal shares (+-1), so that a rank only transforms the shells it pairs."""
+    from . import core
+    return core.partition_owners(form, degrees, num_bins, world_size, idx_bin=idx_bin)
 
 
-def local_entries(dim, rank, world_size):
-    return np.arange(dim)[np.arange(dim) % world_size == rank]
+def local_entries(form, degrees, num_bins, rank, world_size, idx_bin=0):
+    return np.nonzero(owners(form, degrees, num_bins, world_size, idx_bin=idx_bin) == rank)[0]
 
 
 def pack(out, stat):

@@ -67,10 +67,10 @@ class ParameterSet {
   /// 1 selects the deterministic (bit-reproducible) mesh assignment; also
   /// taken from the environment variable TRV_DETERMINISTIC at validate().
   int deterministic = 0;
-  /// Work partition for multi-GPU runs: this process computes the bin
-  /// pairs / terms with (index % part_count) == part_rank and returns
-  /// zeros elsewhere, so a sum over ranks (one small all-reduce) gives the
-  /// full result.
+  /// Work partition for multi-GPU runs: this process computes the data-vector
+  /// entries that trv::partition_owners() gives to part_rank (compact blocks of
+  /// the bin-pair matrix) and returns zeros elsewhere, so a sum over ranks (one
+  /// small all-reduce) gives the full result.
   int part_rank = 0;
   int part_count = 1;
 

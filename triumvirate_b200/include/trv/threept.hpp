@@ -84,6 +84,15 @@ trv::ThreePCFMeasurements compute_3pcf_in_gpp_box(
   long long nparticles, const double* x, const double* y, const double* z,
   bool on_device, trv::ParameterSet& params, trv::Binning& rbinning, double norm_factor);
 
+/// Multi-GPU work split (B200 build extension): owner rank in [0, world) of
+/// every data-vector entry given its (row bin, column bin); the estimators
+/// compute the entries owned by `ParameterSet::part_rank` and leave zeros elsewhere.
+std::vector<int> partition_owners(
+  const std::vector<int>& row, const std::vector<int>& col, int world);
+
+/// The same for a parameter set's data-vector shape (after validate()).
+std::vector<int> partition_owners(const trv::ParameterSet& params, int num_bins, int world);
+
 }  // namespace trv
 
 #endif  // TRV_B200_THREEPT_HPP_

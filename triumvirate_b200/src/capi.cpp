@@ -65,6 +65,23 @@ const char* trv_last_error() { return g_capi_err.c_str(); }
 
 int trv_gpu_count() { return trv::sys::get_gpu_count(); }
 
+int trv_partition_owners(const char* form, int ell1, int ell2, int idx_bin, int num_bins,
+                         int world, int* owner, int* dim) {
+  try {
+    trv::ParameterSet p;
+    p.form = form; p.ell1 = ell1; p.ell2 = ell2; p.idx_bin = idx_bin;
+    // Form -> shape as validate() derives it (S/parameters.cpp:829-849).
+    p.shape = (p.form == "full" && ell1 == ell2) ? "triu" : p.form;
+    const std::vector<int> own = trv::partition_owners(p, num_bins, world);
+    *dim = static_cast<int>(own.size());
+    for (size_t i = 0; i < own.size(); i++) owner[i] = own[i];
+    return 0;
+  } catch (const std::exception& e) {
+    g_capi_err = e.what();
+    return 1;
+  }
+}
+
 void trv_counters(int* count_fft, int* count_ifft, double* gib_gpu_max) {
   *count_fft = trv::sys::count_fft; *count_ifft = trv::sys::count_ifft;
   *gib_gpu_max = trv::sys::gbytesMaxMemGPU;

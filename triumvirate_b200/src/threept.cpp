@@ -15,6 +15,7 @@
 #include "trv/threept.hpp"
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <map>
 #include <memory>
@@ -372,11 +373,11 @@ class Engine {
   }
 
   /// Number of additional meshes of `bytes` each that fit in free HBM.
-  int mesh_capacity(size_t bytes) {
+  int mesh_capacity(size_t bytes, size_t reserve = 0) {
     size_t free_b = 0, total_b = 0;
     dev::check(trvb_mem_info(c_, &free_b, &total_b), "trvb_mem_info");
-    const double usable = 0.85 * double(free_b);
-    return static_cast<int>(usable / double(bytes));
+    const double usable = 0.92 * double(free_b) - double(reserve);
+    return usable <= 0. ? 0 : static_cast<int>(usable / double(bytes));
   }
 
  private:
@@ -456,16 +457,21 @@ void reduce_pairs(Engine& eng, trvb_ctx* grid, const DataVector& dv,
   const std::vector<int> rows = distinct_sorted(rows_all);
   const std::vector<int> cols = distinct_sorted(cols_all);
 
-  // Memory plan: a REAL field is produced from a transient half spectrum of
-  // about the same size.
-  const size_t bytes = trvb_mesh_bytes(grid, G.layout) * (G.layout == TRVB_REAL ? 2 : 1);
-  const int cap = eng.mesh_capacity(bytes) - 1;
+  // Memory plan.  The batched shell transform keeps a transient half-spectrum slab
+  // and cuFFT's work area, both bounded by its sub-batching (<= 6 GiB each, or the
+  // whole batch when that is smaller); everything else can hold fields.
+  const size_t bytes = trvb_mesh_bytes(grid, G.layout);
+  std::vector<int> all_bins = rows;
+  all_bins.insert(all_bins.end(), cols.begin(), cols.end());
+  const int want = same_fields ? static_cast<int>(distinct_sorted(all_bins).size())
+                               : static_cast<int>(rows.size() + cols.size());
+  const size_t transient = std::min<size_t>(size_t(14) << 30, 2 * bytes * size_t(want));
+  const int cap = eng.mesh_capacity(bytes, transient);
   dev::profile_mark(eng.ctx(), "pairs:capacity");
   if (cap < 2) {
     throw trvs::DeviceError(
       "Insufficient device memory: fewer than two %zu-byte shell meshes fit.", bytes);
   }
-  const int want = static_cast<int>(rows.size() + cols.size());
   int block_r = static_cast<int>(rows.size());
   int block_c = static_cast<int>(cols.size());
   if (want > cap) {
@@ -485,10 +491,17 @@ void reduce_pairs(Engine& eng, trvb_ctx* grid, const DataVector& dv,
     for (size_t i = 0; i < bins_a.size(); i++) { ia_of[bins_a[i]] = (int)i; pa.push_back(fa.mesh((int)i)); }
     for (size_t c0 = 0; c0 < cols.size(); c0 += block_c) {
       const size_t c1 = std::min(cols.size(), c0 + block_c);
-      // Columns whose field already exists among the rows share it.
+      // Columns of this block that pair with one of its rows; those whose field
+      // already exists among the rows share it.
+      std::set<int> cols_used;
+      for (int i = 0; i < dv.dim; i++) {
+        if (!active[i] || !ia_of.count(dv.row[i])) continue;
+        if (dv.col[i] >= cols[c0] && dv.col[i] <= cols[c1 - 1]) cols_used.insert(dv.col[i]);
+      }
+      if (cols_used.empty()) continue;
       std::vector<int> bins_b;
-      for (size_t c = c0; c < c1; c++) {
-        if (!(same_fields && ia_of.count(cols[c]))) bins_b.push_back(cols[c]);
+      for (int cb : cols_used) {
+        if (!(same_fields && ia_of.count(cb))) bins_b.push_back(cb);
       }
       std::shared_ptr<Slab> fb;
       if (!bins_b.empty()) fb = get_b(bins_b);
@@ -496,9 +509,9 @@ void reduce_pairs(Engine& eng, trvb_ctx* grid, const DataVector& dv,
       std::map<int, int> ib_of;
       std::vector<const void*> pb;
       int next_own = 0;
-      for (size_t c = c0; c < c1; c++) {
-        ib_of[cols[c]] = (int)pb.size();
-        if (same_fields && ia_of.count(cols[c])) pb.push_back(fa.mesh(ia_of[cols[c]]));
+      for (int cb : cols_used) {
+        ib_of[cb] = (int)pb.size();
+        if (same_fields && ia_of.count(cb)) pb.push_back(fa.mesh(ia_of[cb]));
         else pb.push_back(fb->mesh(next_own++));
       }
       // Pair list restricted to this block.
@@ -522,9 +535,51 @@ void reduce_pairs(Engine& eng, trvb_ctx* grid, const DataVector& dv,
   }
 }
 
-std::vector<char> active_entries(const trv::ParameterSet& params, int dim) {
-  std::vector<char> active(dim, 0);
-  for (int i = 0; i < dim; i++) active[i] = (i % params.part_count) == params.part_rank;
+}  // namespace
+
+/// Owner rank of every data-vector entry.  An entry (row bin, column bin) needs
+/// the shell fields of both bins on its rank and those inverse transforms are
+/// what the pair phase costs, so a rank should own a compact rectangle of the
+/// (row, column) matrix rather than scattered entries: the entries are ordered by
+/// (strip of h consecutive rows, column -- serpentine, so that a share crossing
+/// into the next strip keeps its columns --, row) with h^2 ~ entries per rank, and
+/// that order is cut into `world` contiguous shares of equal size (+-1).  For
+/// `diag`, `off-diag` and `row` shapes this degenerates to contiguous bin ranges.
+std::vector<int> partition_owners(const std::vector<int>& row, const std::vector<int>& col,
+                                  int world) {
+  const int dim = static_cast<int>(row.size());
+  std::vector<int> owner(dim, 0);
+  if (world <= 1 || dim == 0) return owner;
+  const std::vector<int> rows = distinct_sorted(row), cols = distinct_sorted(col);
+  auto rank_in = [](const std::vector<int>& sorted, int v) {
+    return static_cast<int>(std::lower_bound(sorted.begin(), sorted.end(), v) - sorted.begin());
+  };
+  const double per = double(dim) / double(world);
+  const int h = std::max(1, static_cast<int>(std::floor(std::sqrt(per) + 0.5)));
+  std::vector<std::array<int, 4> > keyed(dim);
+  for (int i = 0; i < dim; i++) {
+    const int r = rank_in(rows, row[i]), c = rank_in(cols, col[i]);
+    const int strip = r / h;
+    keyed[i] = {strip, (strip % 2 == 0) ? c : -c, r, i};
+  }
+  std::sort(keyed.begin(), keyed.end());
+  for (int t = 0; t < dim; t++) {
+    owner[keyed[t][3]] = static_cast<int>((static_cast<long long>(t) * world) / dim);
+  }
+  return owner;
+}
+
+std::vector<int> partition_owners(const trv::ParameterSet& params, int num_bins, int world) {
+  const DataVector dv = make_data_vector(params, num_bins);
+  return partition_owners(dv.row, dv.col, world);
+}
+
+namespace {
+
+std::vector<char> active_entries(const trv::ParameterSet& params, const DataVector& dv) {
+  std::vector<char> active(dv.dim, 0);
+  const std::vector<int> owner = partition_owners(dv.row, dv.col, params.part_count);
+  for (int i = 0; i < dv.dim; i++) active[i] = owner[i] == params.part_rank;
   return active;
 }
 
@@ -559,7 +614,7 @@ trv::BispecMeasurements bispec_impl(
   const cdouble factor_phase = std::pow(trvm::M_I, params.ell1 + params.ell2);
   const int nb = kbinning.num_bins;
   const DataVector dv = make_data_vector(params, nb);
-  const std::vector<char> active = active_entries(params, dv.dim);
+  const std::vector<char> active = active_entries(params, dv);
 
   trvb_ctx* c = eng.ctx();
 
@@ -787,7 +842,7 @@ trv::ThreePCFMeasurements threepcf_impl(
   const double factor_parity = std::pow(-1., params.ell1 + params.ell2);
   const int nb = rbinning.num_bins;
   const DataVector dv = make_data_vector(params, nb);
-  const std::vector<char> active = active_entries(params, dv.dim);
+  const std::vector<char> active = active_entries(params, dv);
 
   trvb_ctx* c = eng.ctx();
   const double vol_cell = eng.vol_cell();
