@@ -94,6 +94,28 @@ int trv_threept_box_arrays(
   int* dim, double* c1_bin, double* c2_bin, double* c1_eff, double* c2_eff,
   int* n1, int* n2, double* raw, double* shot);
 
+/* Two-point estimators: replaces T/_twopt.pyx:164-380 (_compute_powspec,
+ * _compute_corrfunc, _compute_powspec_in_gpp_box, _compute_corrfunc_in_gpp_box,
+ * _compute_corrfunc_window -> S/twopt.cpp:388-901).  stat = "powspec" | "2pcf" |
+ * "2pcf-win"; catalogue_type = "sim" | "survey" | "random" (for "2pcf-win": the
+ * random catalogue goes in the `r` slot, used with `alpha`, T/twopt.py:1538).
+ * `interlace` = "true" | "false" is honoured (two-point statistics are the only
+ * ones for which validate() keeps it, S/parameters.cpp:1240-1249).  ELL is the
+ * multipole degree.  Outputs hold >= num_bins entries: bin centres, effective
+ * coordinates, nmodes/npairs, raw statistic and (power spectrum only) shot noise
+ * as interleaved (re, im), multiplied by norm_factor. */
+int trv_twopt(
+  const char* stat, const char* catalogue_type,
+  int nd, const double* xd, const double* yd, const double* zd,
+  const double* nzd, const double* wsd, const double* wcd, const double* los_d,
+  int nr, const double* xr, const double* yr, const double* zr,
+  const double* nzr, const double* wsr, const double* wcr, const double* los_r,
+  const double* boxsize, const int* ngrid, const char* assignment, const char* interlace,
+  int ELL, const char* binning, double bin_min, double bin_max, int num_bins,
+  const double* custom_edges, double alpha, double norm_factor, int verbose, int deterministic,
+  int* dim, double* c_bin, double* c_eff, int* count, double* raw, double* shot,
+  double* elapsed_s);
+
 /* 3PCF window function from a random catalogue: replaces T/_threept.pyx:276-314
  * (_compute_3pcf_window -> trv::compute_3pcf_window, S/threept.cpp:2621-3077).
  * The catalogue is used with the given alpha contrast (the Python front end
@@ -126,6 +148,13 @@ int trv_profile_report(char* buf, int cap);
 /* trv::calc_bispec_normalisation_from_particles (S/threept.cpp:96-136; host
  * only) or, from_mesh != 0, _from_mesh (S/threept.cpp:138-149). */
 int trv_norm(
+  int from_mesh, int n, const double* x, const double* y, const double* z,
+  const double* nz, const double* ws, const double* wc, double alpha,
+  const double* boxsize, const int* ngrid, const char* assignment, double* norm);
+
+/* trv::calc_powspec_normalisation_from_particles (S/twopt.cpp:56-96; host only)
+ * or, from_mesh != 0, _from_mesh (S/twopt.cpp:98-109). */
+int trv_norm_powspec(
   int from_mesh, int n, const double* x, const double* y, const double* z,
   const double* nz, const double* ws, const double* wc, double alpha,
   const double* boxsize, const int* ngrid, const char* assignment, double* norm);

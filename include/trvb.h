@@ -235,18 +235,21 @@ int trvb_gram_reduce(trvb_ctx* ctx, const void* const* A, int na,
 /* Binned pseudo-2pt statistics in Fourier space with the fine-bin rule
  * (S/field.cpp:2511-2703): per bin nmodes, mean |k|, mean
  * y_lm fa conj(fb)/C1 and mean y_lm S (C1/C1).  Empty bins follow
- * S/field.cpp:2688-2692 (k = centre, pk = sn = 0). */
+ * S/field.cpp:2688-2692 (k = centre, pk = sn = 0).  interlaced != 0 selects the
+ * branch of interlaced meshes (two-point statistics only, S/field.cpp:2543-2552):
+ * division by the product of the assignment windows, and the isotropic
+ * shot-noise aliasing function of S/field.cpp:3504-3527. */
 int trvb_twopt_fourier(trvb_ctx* ctx, trvb_mesh fa, trvb_mesh fb,
-                       const double S[2], int ell, int m, const double* edges,
-                       const double* centres, int nbins, long long* nmodes,
-                       double* k, double* pk, double* sn);
+                       const double S[2], int ell, int m, int interlaced,
+                       const double* edges, const double* centres, int nbins,
+                       long long* nmodes, double* k, double* pk, double* sn);
 
 /* xi(x) = IFFT[ (fa conj(fb)/C1 - S C1/C1) / V ]  (S/field.cpp:3273-3345,
  * 3018-3090); dst TRVB_COMPLEX on the same grid, or TRVB_REAL when fa and fb
  * are both TRVB_HALF (spectra of real fields) and Im S = 0: the product is then
  * Hermitian, xi is real and half the traffic suffices. */
 int trvb_shot_xi(trvb_ctx* ctx, trvb_mesh fa, trvb_mesh fb, const double S[2],
-                 trvb_mesh dst);
+                 int interlaced, trvb_mesh dst);
 
 /* out[p] = vol_cell * sum_x j_la(ka[p] |x|) j_lb(kb[p] |x|) y_la,ma(xhat)
  * y_lb,mb(xhat) xi(x)   (S/field.cpp:3362-3393), all pairs in one pass.
@@ -262,6 +265,13 @@ int trvb_shot_3pcf_bin(trvb_ctx* ctx, trvb_mesh xi, int la, int ma, int lb,
                        int mb, const double* edges, const double* centres,
                        int nbins, double parity, long long* npairs, double* r,
                        double* xi_out);
+
+/* Radially binned y_lm xi(x) of the two-point correlation function with the
+ * fine-bin rule, dr_sample = 0.1, n_sample = 1e6 (S/field.cpp:2846-2931): per
+ * bin npairs, mean |x| and mean y_lm xi; empty bins: r = centre, xi = 0. */
+int trvb_twopt_config_bin(trvb_ctx* ctx, trvb_mesh xi, int ell, int m,
+                          const double* edges, const double* centres, int nbins,
+                          long long* npairs, double* r, double* xi_out);
 
 #ifdef __cplusplus
 }

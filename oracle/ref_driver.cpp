@@ -10,6 +10,8 @@
 //                                           (S/threept.cpp:248,1014,1473,2190,2621)
 //   trv::MeshField assignment / FFT / compensation (S/field.cpp:569-1785)
 //   trv::calc_bispec_normalisation_from_{particles,mesh} (S/threept.cpp:96,138)
+//   trv::compute_powspec / compute_corrfunc / *_in_gpp_box / compute_corrfunc_window
+//                                           (S/twopt.cpp:388,498,609,703,795)
 //   trv::maths calculators                  (S/maths.cpp:167-375)
 // Nothing here re-implements reference logic: it only marshals arrays.
 
@@ -26,6 +28,7 @@
 #include "parameters.hpp"
 #include "particles.hpp"
 #include "threept.hpp"
+#include "twopt.hpp"
 
 #ifdef _OPENMP
 #include <omp.h>
@@ -364,6 +367,117 @@ int trvref_norm(
       *norm = trv::calc_bispec_normalisation_from_mesh(cat, params, alpha);
     } else {
       *norm = trv::calc_bispec_normalisation_from_particles(cat, alpha);
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+
+// Two-point estimators (S/twopt.cpp:388-901).  `stat` = "powspec" | "2pcf" |
+// "2pcf-win"; interlacing is honoured by validate() for these statistics.
+int trvref_twopt(
+  const char* stat, const char* catalogue_type,
+  int nd, const double* xd, const double* yd, const double* zd,
+  const double* nzd, const double* wsd, const double* wcd, const double* los_d,
+  int nr, const double* xr, const double* yr, const double* zr,
+  const double* nzr, const double* wsr, const double* wcr, const double* los_r,
+  const double* boxsize, const int* ngrid, const char* assignment, int interlace,
+  int ELL, const char* binning, double bin_min, double bin_max, int num_bins,
+  double alpha, double norm_factor, int verbose,
+  int* dim, double* c_bin, double* c_eff, int* count, double* raw, double* shot,
+  double* elapsed_s
+) {
+  try {
+    const std::string st(stat);
+    trv::ParameterSet params;
+    params.catalogue_type = catalogue_type;
+    params.statistic_type = stat;
+    for (int i = 0; i < 3; i++) { params.boxsize[i] = boxsize[i]; params.ngrid[i] = ngrid[i]; }
+    params.alignment = "centre";
+    params.padscale = "box";
+    params.assignment = assignment;
+    params.interlace = interlace ? "true" : "false";
+    params.ell1 = ELL; params.ell2 = 0; params.ELL = ELL;
+    params.form = "diag";
+    params.idx_bin = 0;
+    params.norm_convention = "particle";
+    params.binning = binning;
+    params.bin_min = bin_min; params.bin_max = bin_max;
+    params.num_bins = num_bins;
+    params.fftw_scheme = "estimate";
+    params.use_fftw_wisdom = "false";
+    params.verbose = verbose;
+    params.progbar = "false";
+    params.validate(false);
+    trv::Binning bins(params);
+    bins.set_bins();
+
+    const bool survey = std::string(catalogue_type) == "survey";
+    const bool window = st == "2pcf-win";
+    trv::ParticleCatalogue data(verbose), rand(verbose);
+    if (!window) load_catalogue(data, nd, xd, yd, zd, nzd, wsd, wcd);
+    if (survey || window) load_catalogue(rand, nr, xr, yr, zr, nzr, wsr, wcr);
+    trv::LineOfSight* ld = (trv::LineOfSight*)los_d;
+    trv::LineOfSight* lr = (trv::LineOfSight*)los_r;
+
+    auto t0 = std::chrono::steady_clock::now();
+    if (st == "powspec") {
+      trv::PowspecMeasurements out = survey
+        ? trv::compute_powspec(data, rand, ld, lr, params, bins, norm_factor)
+        : trv::compute_powspec_in_gpp_box(data, params, bins, norm_factor);
+      *dim = out.dim;
+      for (int i = 0; i < out.dim; i++) {
+        c_bin[i] = out.kbin[i]; c_eff[i] = out.keff[i]; count[i] = out.nmodes[i];
+        raw[2*i] = out.pk_raw[i].real(); raw[2*i+1] = out.pk_raw[i].imag();
+        shot[2*i] = out.pk_shot[i].real(); shot[2*i+1] = out.pk_shot[i].imag();
+      }
+    } else if (window) {
+      trv::TwoPCFWindowMeasurements out = trv::compute_corrfunc_window(
+        rand, lr, params, bins, alpha, norm_factor);
+      *dim = out.dim;
+      for (int i = 0; i < out.dim; i++) {
+        c_bin[i] = out.rbin[i]; c_eff[i] = out.reff[i]; count[i] = out.npairs[i];
+        raw[2*i] = out.xi[i].real(); raw[2*i+1] = out.xi[i].imag();
+        shot[2*i] = 0.; shot[2*i+1] = 0.;
+      }
+    } else {
+      trv::TwoPCFMeasurements out = survey
+        ? trv::compute_corrfunc(data, rand, ld, lr, params, bins, norm_factor)
+        : trv::compute_corrfunc_in_gpp_box(data, params, bins, norm_factor);
+      *dim = out.dim;
+      for (int i = 0; i < out.dim; i++) {
+        c_bin[i] = out.rbin[i]; c_eff[i] = out.reff[i]; count[i] = out.npairs[i];
+        raw[2*i] = out.xi[i].real(); raw[2*i+1] = out.xi[i].imag();
+        shot[2*i] = 0.; shot[2*i+1] = 0.;
+      }
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    if (elapsed_s) *elapsed_s = std::chrono::duration<double>(t1 - t0).count();
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+
+int trvref_norm_powspec(
+  int from_mesh, int n, const double* x, const double* y, const double* z,
+  const double* nz, const double* ws, const double* wc, double alpha,
+  const double* boxsize, const int* ngrid, const char* assignment,
+  double* norm
+) {
+  try {
+    trv::ParticleCatalogue cat(60);
+    load_catalogue(cat, n, x, y, z, nz, ws, wc);
+    if (from_mesh) {
+      trv::ParameterSet params;
+      fill_params(params, "sim", "powspec", boxsize, ngrid, assignment,
+                  0, 0, 0, "diag", 0, "lin", 0.005, 0.105, 4, 0, 60);
+      *norm = trv::calc_powspec_normalisation_from_mesh(cat, params, alpha);
+    } else {
+      *norm = trv::calc_powspec_normalisation_from_particles(cat, alpha);
     }
     return 0;
   } catch (const std::exception& e) {

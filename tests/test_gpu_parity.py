@@ -13,7 +13,8 @@ deterministic assignment mode.
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, load_golden
+from conftest import (GOLDEN, load_golden, twopt_case, check_twopt_against_golden,
+                      TWOPT_CASES)
 
 pytestmark = pytest.mark.gpu
 
@@ -303,6 +304,96 @@ def test_survey_against_oracle(core, oracle, stat, degrees, form, idx_bin, assig
     ref = oracle.threept(stat, "survey", **kw)
     out = core.threept(stat, "survey", **kw)
     _assert_close(out, ref, label=f"{stat}{degrees}{form}: ")
+
+
+# ---------------------------------------------------------------------------
+# Two-point estimators (S/twopt.cpp:388-901)
+# ---------------------------------------------------------------------------
+
+def _product_module(core):
+    """The product's counterparts of the oracle's helper functions."""
+    from types import SimpleNamespace
+    from triumvirate_b200 import catalogue as tcat
+    return SimpleNamespace(periodise=tcat.periodise, centre=tcat.centre,
+                           compute_los=tcat.compute_los,
+                           norm_particles_2pt=core.norm_particles_2pt)
+
+
+@pytest.mark.parametrize("degree", [0, 2])
+@pytest.mark.parametrize("stat,kind,fname", TWOPT_CASES)
+def test_reference_twopt_goldens(core, stat, kind, fname, degree,
+                                 golden_data_catalogue, golden_rand_catalogue):
+    """pk*, xi*, xiw* golden files of the reference (tests/test_twopt.py)."""
+    args = twopt_case(_product_module(core), stat, kind, degree,
+                      golden_data_catalogue, golden_rand_catalogue)
+    out = core.twopt(**args)
+    check_twopt_against_golden(out, load_golden(fname.format(degree)), stat)
+
+
+@pytest.mark.parametrize("stat,catalogue_type,degree,assignment,interlace", [
+    ("powspec", "survey", 0, "tsc", False),
+    ("powspec", "survey", 2, "pcs", True),
+    ("powspec", "survey", 4, "cic", True),
+    ("powspec", "sim", 2, "pcs", True),
+    ("powspec", "sim", 0, "ngp", False),
+    ("2pcf", "survey", 2, "tsc", True),
+    ("2pcf", "survey", 1, "pcs", False),
+    ("2pcf", "sim", 0, "cic", True),
+    ("2pcf", "sim", 2, "tsc", False),
+    ("2pcf-win", "random", 2, "tsc", True),
+    ("2pcf-win", "random", 0, "pcs", False),
+])
+def test_twopt_against_oracle(core, oracle, stat, catalogue_type, degree, assignment, interlace):
+    """Weighted catalogues, every assignment scheme, with and without interlacing
+    (the branch of S/field.cpp:2543-2552 and the isotropic aliasing function of
+    S/field.cpp:3504-3527), bins that reach the Nyquist wavenumber."""
+    from triumvirate_b200 import catalogue as tcat
+    L, ng = 1000., 32
+    pd_, pr_, nzd, nzr, wsd, wsr, wcd, wcr = _survey_inputs(33, 1500, 6000, L)
+    rng = (0.01, 0.10) if stat == "powspec" else (40., 280.)
+    kw = dict(boxsize=L, ngrid=ng, assignment=assignment, degree=degree, bin_range=rng,
+              num_bins=5, interlace=interlace)
+    if catalogue_type == "survey":
+        los_d, los_r = tcat.compute_los(pd_), tcat.compute_los(pr_)
+        pd_c, pr_c = tcat.centre(pd_, pr_, L)
+        alpha = wsd.sum() / wsr.sum()
+        norm = oracle.norm_particles_2pt(pr_c, nzr, ws=wsr, wc=wcr, alpha=alpha)
+        assert abs(core.norm_particles_2pt(pr_c, nzr, ws=wsr, wc=wcr, alpha=alpha) - norm) \
+            <= 1e-13 * abs(norm)
+        kw.update(pos_d=pd_c, nz_d=nzd, ws_d=wsd, wc_d=wcd, los_d=los_d,
+                  pos_r=pr_c, nz_r=nzr, ws_r=wsr, wc_r=wcr, los_r=los_r, norm_factor=norm)
+    elif catalogue_type == "random":
+        los_r = tcat.compute_los(pr_)
+        pr_c, _ = tcat.centre(pr_, pr_, L)
+        pr_c = tcat.periodise(pr_c, L)
+        norm = oracle.norm_particles_2pt(pr_c, nzr, ws=wsr, wc=wcr, alpha=1.)
+        kw.update(pos_r=pr_c, nz_r=nzr, ws_r=wsr, wc_r=wcr, los_r=los_r, alpha=0.37,
+                  norm_factor=norm)
+    else:
+        pos = np.random.default_rng(5).uniform(0., L, size=(3, 4000))
+        kw.update(pos_d=pos, nz_d=np.full(4000, 4000 / L**3), norm_factor=L**3 / 4000.**2)
+    ref = oracle.twopt(stat, catalogue_type, **kw)
+    out = core.twopt(stat, catalogue_type, **kw)
+    label = f"{stat} {catalogue_type} L={degree} {assignment} il={interlace}: "
+    if stat == "powspec":
+        # The shot-noise multipoles of degree > 0 vanish identically (angular mean of
+        # y_lm over a shell; both sides return 1e-14 round-off): their error is
+        # measured against the scale of the raw spectrum.
+        shot_out, shot_ref = out.pop("pk_shot"), ref.pop("pk_shot")
+        scale = max(np.abs(shot_ref).max(), np.abs(ref["pk_raw"]).max())
+        assert np.max(np.abs(shot_out - shot_ref)) <= RTOL * scale, label + "pk_shot"
+        if degree == 0:
+            assert np.max(np.abs(shot_out - shot_ref) / np.abs(shot_ref)) <= RTOL, label + "pk_shot"
+    _assert_close(out, ref, label=label)
+
+
+def test_twopt_mesh_normalisation(core, oracle):
+    gen = np.random.default_rng(8)
+    pos = gen.uniform(0., 500., size=(3, 3000))
+    ws = gen.uniform(0.5, 1.5, 3000)
+    a = oracle.norm_mesh_2pt(pos, 500., 32, "tsc", ws=ws, alpha=0.2)
+    b = core.norm_mesh_2pt(pos, 500., 32, "tsc", ws=ws, alpha=0.2)
+    assert abs(a - b) <= 1.e-12 * abs(a)
 
 
 # ---------------------------------------------------------------------------

@@ -10,7 +10,7 @@ is present.
 import numpy as np
 import pytest
 
-from conftest import load_golden
+from conftest import load_golden, twopt_case, check_twopt_against_golden, TWOPT_CASES, window_inputs
 
 CASES = [((0, 0, 0), "diag", None), ((2, 0, 2), "diag", None), ((0, 0, 0), "row", 0)]
 
@@ -60,14 +60,7 @@ def test_oracle_reproduces_reference_goldens(oracle, stat, prefix, kind, degrees
     assert rel(out[names[7]], shot) < 2.e-9
 
 
-def _window_inputs(mod, rand, L):
-    """Python-side preparation of compute_3pcf_window (T/threept.py:1969-2010):
-    LOS from the original coordinates, centre on the catalogue's own extents, then
-    periodise; alpha = 1; particle normalisation with alpha = 1."""
-    los_r = mod.compute_los(rand[:3])
-    pos_r, _ = mod.centre(rand[:3], rand[:3], L)
-    pos_r = mod.periodise(pos_r, L)
-    return pos_r, los_r
+_window_inputs = window_inputs
 
 
 @pytest.mark.parametrize("degrees,form,idx_bin", CASES)
@@ -95,6 +88,18 @@ def test_oracle_reproduces_window_goldens(oracle, degrees, form, idx_bin, golden
         return np.max(np.abs(a - b) / np.where(np.abs(b) > 0., np.abs(b), 1.))
     assert rel(out["zeta_raw"], raw) < 2.e-9
     assert rel(out["zeta_shot"], shot) < 2.e-9
+
+
+# ---- two-point estimators (reference tests/test_twopt.py) -----------------
+
+@pytest.mark.parametrize("degree", [0, 2])
+@pytest.mark.parametrize("stat,kind,fname", TWOPT_CASES)
+def test_oracle_reproduces_twopt_goldens(oracle, stat, kind, fname, degree,
+                                         golden_data_catalogue, golden_rand_catalogue):
+    """pk*, xi*, xiw* of the reference (tests/test_twopt.py)."""
+    args = twopt_case(oracle, stat, kind, degree, golden_data_catalogue, golden_rand_catalogue)
+    out = oracle.twopt(**args)
+    check_twopt_against_golden(out, load_golden(fname.format(degree)), stat)
 
 
 def test_oracle_fixture_file_is_current(oracle):

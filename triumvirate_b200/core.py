@@ -62,6 +62,70 @@ def counters():
     return {"count_fft": f.value, "count_ifft": i.value, "gib_gpu_max": g.value}
 
 
+def twopt(stat, catalogue_type, boxsize, ngrid, assignment, degree, bin_range, num_bins,
+          norm_factor, pos_d=None, nz_d=None, ws_d=None, wc_d=None, los_d=None,
+          pos_r=None, nz_r=None, ws_r=None, wc_r=None, los_r=None,
+          interlace="false", binning="lin", custom_edges=None, alpha=1., verbose=60,
+          deterministic=False):
+    """Run a two-point estimator on the GPU.
+
+    ``stat`` is ``'powspec'``, ``'2pcf'`` or ``'2pcf-win'``; ``catalogue_type`` is
+    ``'sim'`` (``trv::compute_*_in_gpp_box``), ``'survey'`` (``trv::compute_powspec``
+    / ``trv::compute_corrfunc``) or ``'random'`` (``trv::compute_corrfunc_window``:
+    the catalogue is ``pos_r`` with ``alpha``).  Returns a dict with the
+    reference's result-struct field names.
+    """
+    L = _trv()
+    boxsize, ngrid = _box(boxsize, ngrid)
+    keep = []
+
+    def arr(a):
+        a_, p = _d(a)
+        keep.append(a_)
+        return p
+
+    def cat(pos, nz, ws, wc, los):
+        if pos is None:
+            return 0, [None] * 7
+        pos = np.asarray(pos, dtype=np.float64)
+        return pos.shape[1], [arr(pos[0]), arr(pos[1]), arr(pos[2]), arr(nz), arr(ws), arr(wc),
+                              arr(los)]
+
+    nd, args_d = cat(pos_d, nz_d, ws_d, wc_d, los_d)
+    nr, args_r = cat(pos_r, nz_r, ws_r, wc_r, los_r)
+    nb = int(num_bins)
+    dim = C.c_int(0)
+    cb = np.zeros(nb + 8); ce = np.zeros(nb + 8)
+    cnt = np.zeros(nb + 8, dtype=np.int32)
+    raw = np.zeros(2 * (nb + 8)); shot = np.zeros(2 * (nb + 8))
+    elapsed = C.c_double(0.)
+    if isinstance(interlace, bool):
+        interlace = "true" if interlace else "false"
+    status = L.trv_twopt(
+        stat.encode(), catalogue_type.encode(),
+        C.c_int(nd), *args_d, C.c_int(nr), *args_r,
+        boxsize.ctypes.data_as(_dp), ngrid.ctypes.data_as(_ip),
+        assignment.encode(), interlace.encode(), C.c_int(degree), binning.encode(),
+        C.c_double(bin_range[0]), C.c_double(bin_range[1]), C.c_int(nb), arr(custom_edges),
+        C.c_double(alpha), C.c_double(norm_factor), C.c_int(verbose),
+        C.c_int(1 if deterministic else 0),
+        C.byref(dim), cb.ctypes.data_as(_dp), ce.ctypes.data_as(_dp), cnt.ctypes.data_as(_ip),
+        raw.ctypes.data_as(_dp), shot.ctypes.data_as(_dp), C.byref(elapsed),
+    )
+    _check(status)
+    n = dim.value
+    raw_c = raw[0:2*n:2] + 1j * raw[1:2*n:2]
+    shot_c = shot[0:2*n:2] + 1j * shot[1:2*n:2]
+    if stat == "powspec":
+        out = {"kbin": cb[:n].copy(), "keff": ce[:n].copy(), "nmodes": cnt[:n].copy(),
+               "pk_raw": raw_c, "pk_shot": shot_c}
+    else:
+        out = {"rbin": cb[:n].copy(), "reff": ce[:n].copy(), "npairs": cnt[:n].copy(),
+               "xi": raw_c}
+    out["elapsed_s"] = elapsed.value
+    return out
+
+
 def threept(stat, catalogue_type, pos_d, boxsize, ngrid, assignment, degrees,
             form, bin_range, num_bins, norm_factor, idx_bin=0, binning="lin",
             nz_d=None, ws_d=None, wc_d=None, los_d=None,
@@ -256,14 +320,22 @@ def norm_mesh(pos, boxsize, ngrid, assignment, ws=None, wc=None, alpha=1.):
     return _norm(1, pos, None, ws, wc, alpha, boxsize, ngrid, assignment)
 
 
-def _norm(from_mesh, pos, nz, ws, wc, alpha, boxsize, ngrid, assignment):
+def norm_particles_2pt(pos, nz, ws=None, wc=None, alpha=1.):
+    return _norm(0, pos, nz, ws, wc, alpha, [1., 1., 1.], [4, 4, 4], "tsc", fn="trv_norm_powspec")
+
+
+def norm_mesh_2pt(pos, boxsize, ngrid, assignment, ws=None, wc=None, alpha=1.):
+    return _norm(1, pos, None, ws, wc, alpha, boxsize, ngrid, assignment, fn="trv_norm_powspec")
+
+
+def _norm(from_mesh, pos, nz, ws, wc, alpha, boxsize, ngrid, assignment, fn="trv_norm"):
     pos = np.asarray(pos, dtype=np.float64)
     n = pos.shape[1]
     boxsize, ngrid = _box(boxsize, ngrid)
     x, px = _d(pos[0]); y, py = _d(pos[1]); z, pz = _d(pos[2])
     nz_, pnz = _d(nz); ws_, pws = _d(ws); wc_, pwc = _d(wc)
     out = C.c_double(0.)
-    _check(_trv().trv_norm(
+    _check(getattr(_trv(), fn)(
         C.c_int(from_mesh), C.c_int(n), px, py, pz, pnz, pws, pwc,
         C.c_double(alpha), boxsize.ctypes.data_as(_dp),
         ngrid.ctypes.data_as(_ip), assignment.encode(), C.byref(out)))

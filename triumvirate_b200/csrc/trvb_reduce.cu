@@ -787,10 +787,37 @@ k_shell_stats(GridDesc g, Cube cube, const BinRule* __restrict__ rules,
   store_partials<2>(v, sm, partial);
 }
 
+// Interlaced two-point statistics (S/field.cpp:2543-2552, 3504-3527): the mode
+// is divided by the product of the two assignment windows,
+// pow(sinc_x sinc_y sinc_z, order)^2, and the shot-noise aliasing function is the
+// isotropic approximation cos^2(u/2)^order * C1_order(sin^2(u/2)), u = |pi m / n|.
+__device__ __forceinline__ double window_sq(const Tables& tb, int order, int i, int j, int k) {
+  const double wk = tb.sinc[0][i] * tb.sinc[1][j] * tb.sinc[2][k];
+  double w = wk;
+  for (int q = 1; q < order; q++) w *= wk;
+  return w * w;
+}
+
+__device__ __forceinline__ double alias_iso(const GridDesc& g, int mi, int mj, int mk) {
+  const double PI = 3.14159265358979323846;
+  const double ux = PI * mi / double(g.n[0]);
+  const double uy = PI * mj / double(g.n[1]);
+  const double uz = PI * mk / double(g.n[2]);
+  const double uhalf = sqrt(ux * ux + uy * uy + uz * uz) / 2.;
+  const double s2h = sin(uhalf) * sin(uhalf), c2h = cos(uhalf) * cos(uhalf);
+  double cc = 1.;
+  for (int q = 0; q < g.order; q++) cc *= c2h;
+  double cs = 1.;
+  if (g.order == 2) cs = 1. - 2. / 3. * s2h;
+  else if (g.order == 3) cs = 1. - s2h + 2. / 15. * s2h * s2h;
+  else if (g.order == 4) cs = 1. - 4. / 3. * s2h + 2. / 5. * s2h * s2h - 4. / 315. * s2h * s2h * s2h;
+  return cc * cs;
+}
+
 __global__ void __launch_bounds__(256)
 k_twopt_fourier(KView fa, KView fb, GridDesc g, Tables tb, Cube cube,
                 const BinRule* __restrict__ rules, double S_re, double S_im,
-                int ell, int m, double* __restrict__ partial) {
+                int ell, int m, int interlaced, double* __restrict__ partial) {
   __shared__ double sm[32];
   const BinRule rule = rules[blockIdx.y];
   const YlmCoef yc = ylm_coef(ell, m);
@@ -810,9 +837,11 @@ k_twopt_fourier(KView fa, KView fb, GridDesc g, Tables tb, Cube cube,
     const int k = mk >= 0 ? mk : mk + g.n[2];
     const cplx a = kload(fa, i, j, k), b = kload(fb, i, j, k);
     // pk_mode = fa conj(fb) / C1 ; sn_mode = S C1 / C1  (S/field.cpp:2621-2633).
-    const double c1 = tb.alias[0][i] * tb.alias[1][j] * tb.alias[2][k];
-    cplx pk; pk.re = (a.re * b.re + a.im * b.im) / c1; pk.im = (a.im * b.re - a.re * b.im) / c1;
-    cplx sn; sn.re = (S_re * c1) / c1; sn.im = (S_im * c1) / c1;
+    double c1 = tb.alias[0][i] * tb.alias[1][j] * tb.alias[2][k];
+    double win = c1;
+    if (interlaced) { c1 = alias_iso(g, mi, mj, mk); win = window_sq(tb, g.order, i, j, k); }
+    cplx pk; pk.re = (a.re * b.re + a.im * b.im) / win; pk.im = (a.im * b.re - a.re * b.im) / win;
+    cplx sn; sn.re = (S_re * c1) / win; sn.im = (S_im * c1) / win;
     const cplx y = ylm_eval(yc, kx, ky, kz);
     pk = cmul(pk, y); sn = cmul(sn, y);
     v[0] += 1.; v[1] += kmag; v[2] += pk.re; v[3] += pk.im; v[4] += sn.re; v[5] += sn.im;
@@ -824,10 +853,21 @@ k_twopt_fourier(KView fa, KView fb, GridDesc g, Tables tb, Cube cube,
 // `n2s` = stored extent of the last axis of dst: n2 (COMPLEX) or n2/2+1 (HALF).
 __global__ void __launch_bounds__(256)
 k_shot_spectrum(KView fa, KView fb, GridDesc g, Tables tb, double S_re, double S_im,
-                int n2s, double2* __restrict__ dst) {
+                int n2s, int interlaced, double2* __restrict__ dst) {
   const double inv_vol = 1. / g.vol;
   for_each_cell(g.n[0], g.n[1], n2s, [&](int i, int j, int k, long long t) {
     const cplx a = kload(fa, i, j, k), b = kload(fb, i, j, k);
+    if (interlaced) {
+      // (fa conj(fb) - S C1_iso) / (W_a W_b) / V, S/field.cpp:2760-2781.
+      const int mi = i < g.n[0] / 2 ? i : i - g.n[0];   // S/field.cpp:538-544
+      const int mj = j < g.n[1] / 2 ? j : j - g.n[1];
+      const int mk = k < g.n[2] / 2 ? k : k - g.n[2];
+      const double c1 = alias_iso(g, mi, mj, mk), win = window_sq(tb, g.order, i, j, k);
+      const double re = (a.re * b.re + a.im * b.im) / win - (S_re * c1) / win;
+      const double im = (a.im * b.re - a.re * b.im) / win - (S_im * c1) / win;
+      dst[t] = make_double2(re * inv_vol, im * inv_vol);
+      return;
+    }
     // fa conj(fb)/C1 - S C1/C1, then /V, with tabulated per-axis reciprocals of
     // C1 instead of six fp64 divisions per mode (the pass was bound by the
     // divide sequence, not by HBM).
@@ -1105,9 +1145,9 @@ extern "C" int trvb_shell_stats(trvb_ctx* ctx, const double* edges, int nbins, i
 }
 
 extern "C" int trvb_twopt_fourier(trvb_ctx* ctx, trvb_mesh fa, trvb_mesh fb,
-                                  const double S[2], int ell, int m, const double* edges,
-                                  const double* centres, int nbins, long long* nmodes,
-                                  double* k, double* pk, double* sn) {
+                                  const double S[2], int ell, int m, int interlaced,
+                                  const double* edges, const double* centres, int nbins,
+                                  long long* nmodes, double* k, double* pk, double* sn) {
   TRVB_REQUIRE(ctx && fa.data && fb.data && S && edges && centres && nmodes && k && pk && sn,
                "trvb_twopt_fourier: null argument");
   TRVB_REQUIRE(fa.layout != TRVB_REAL && fb.layout != TRVB_REAL,
@@ -1123,7 +1163,7 @@ extern "C" int trvb_twopt_fourier(trvb_ctx* ctx, trvb_mesh fa, trvb_mesh fb,
   int st = run_binned<6>(ctx, rules, cube.total,
     [&](dim3 grid, const BinRule* d_rules, double* d_partial) {
       k_twopt_fourier<<<grid, 256, 0, ctx->stream>>>(va, vb, g, tb, cube, d_rules,
-                                                    S[0], S[1], ell, m, d_partial);
+                                                    S[0], S[1], ell, m, interlaced, d_partial);
     }, host);
   if (st) return st;
   for (int b = 0; b < nbins; b++) {
@@ -1143,7 +1183,7 @@ extern "C" int trvb_twopt_fourier(trvb_ctx* ctx, trvb_mesh fa, trvb_mesh fb,
 }
 
 extern "C" int trvb_shot_xi(trvb_ctx* ctx, trvb_mesh fa, trvb_mesh fb, const double S[2],
-                            trvb_mesh dst) {
+                            int interlaced, trvb_mesh dst) {
   TRVB_REQUIRE(ctx && fa.data && fb.data && S && dst.data, "trvb_shot_xi: null argument");
   TRVB_REQUIRE(fa.layout != TRVB_REAL && fb.layout != TRVB_REAL,
                "trvb_shot_xi: Fourier-space inputs required");
@@ -1160,7 +1200,7 @@ extern "C" int trvb_shot_xi(trvb_ctx* ctx, trvb_mesh fa, trvb_mesh fb, const dou
     TRVB_CUDA(trvb_dev_alloc_raw(ctx, &half.data, trvb_mesh_bytes(ctx, TRVB_HALF)));
     const RowLaunch rl = row_launch(ctx->num_sms, g.n[0], g.n[1], g.nh);
     k_shot_spectrum<<<rl.grid, rl.block, 0, ctx->stream>>>(
-      kview_of(ctx, fa), kview_of(ctx, fb), g, tables_of(ctx), S[0], S[1], g.nh,
+      kview_of(ctx, fa), kview_of(ctx, fb), g, tables_of(ctx), S[0], S[1], g.nh, interlaced,
       (double2*)half.data);
     TRVB_LAUNCH_CHECK();
     int st = trvb_fft_inverse(ctx, half, dst);
@@ -1169,23 +1209,22 @@ extern "C" int trvb_shot_xi(trvb_ctx* ctx, trvb_mesh fa, trvb_mesh fb, const dou
   }
   const RowLaunch rl = row_launch(ctx->num_sms, g.n[0], g.n[1], g.n[2]);
   k_shot_spectrum<<<rl.grid, rl.block, 0, ctx->stream>>>(
-    kview_of(ctx, fa), kview_of(ctx, fb), g, tables_of(ctx), S[0], S[1], g.n[2],
+    kview_of(ctx, fa), kview_of(ctx, fb), g, tables_of(ctx), S[0], S[1], g.n[2], interlaced,
     (double2*)dst.data);
   TRVB_LAUNCH_CHECK();
   return trvb_fft_inverse(ctx, dst, dst);
 }
 
-extern "C" int trvb_shot_3pcf_bin(trvb_ctx* ctx, trvb_mesh xi, int la, int ma, int lb,
-                                  int mb, const double* edges, const double* centres,
-                                  int nbins, double parity, long long* npairs, double* r,
-                                  double* xi_out) {
-  TRVB_REQUIRE(ctx && xi.data && edges && centres && npairs && r && xi_out,
-               "trvb_shot_3pcf_bin: null argument");
-  TRVB_REQUIRE(xi.layout == TRVB_COMPLEX || xi.layout == TRVB_REAL,
-               "trvb_shot_3pcf_bin: xi must be a configuration-space mesh");
-  TRVB_REQUIRE(ctx->parent == nullptr, "trvb_shot_3pcf_bin: root context only");
+namespace {
+
+// Per-bin {count, sum r, sum Re, sum Im} of y_{la ma}(r) y_{lb mb}(r) xi(r) over the
+// cells whose separation falls in the bin by the reference's sampled-histogram rule
+// (index int(r / dsample) < nsample, S/field.cpp:2862-2921 and 3095-3169).
+int binned_xi_sums(trvb_ctx* ctx, trvb_mesh xi, int la, int ma, int lb, int mb,
+                   const double* edges, int nbins, double dsample, int nsample,
+                   std::vector<double>& host) {
   std::vector<BinRule> rules;
-  make_rules(edges, nbins, 1, 1., 100000, rules);   // S/field.cpp:3095-3096
+  make_rules(edges, nbins, 1, dsample, nsample, rules);
   const GridDesc g = ctx->g;
   XView d_xi; d_xi.p = (const double*)xi.data; d_xi.cplx = xi.layout == TRVB_COMPLEX;
   // Real-space analogue of cube_for: signed offsets with |i| dr <= r_max + slack.
@@ -1198,11 +1237,54 @@ extern "C" int trvb_shot_3pcf_bin(trvb_ctx* ctx, trvb_mesh xi, int la, int ma, i
     if (n == 1) { lo = 0; hi = 0; }
     cube.lo[a] = lo; cube.cnt[a] = hi - lo + 1; cube.total *= cube.cnt[a];
   }
-  std::vector<double> host;
-  int st = run_binned<4>(ctx, rules, cube.total,
+  return run_binned<4>(ctx, rules, cube.total,
     [&](dim3 grid, const BinRule* d_rules, double* d_partial) {
       k_shot_3pcf_bin<<<grid, 256, 0, ctx->stream>>>(d_xi, g, cube, d_rules, la, ma, lb, mb, d_partial);
     }, host);
+}
+
+}  // namespace
+
+extern "C" int trvb_twopt_config_bin(trvb_ctx* ctx, trvb_mesh xi, int ell, int m,
+                                     const double* edges, const double* centres, int nbins,
+                                     long long* npairs, double* r, double* xi_out) {
+  TRVB_REQUIRE(ctx && xi.data && edges && centres && npairs && r && xi_out,
+               "trvb_twopt_config_bin: null argument");
+  TRVB_REQUIRE(xi.layout == TRVB_COMPLEX || xi.layout == TRVB_REAL,
+               "trvb_twopt_config_bin: xi must be a configuration-space mesh");
+  TRVB_REQUIRE(ctx->parent == nullptr, "trvb_twopt_config_bin: root context only");
+  std::vector<double> host;
+  // dr_sample = 0.1, n_sample = 1e6 (S/field.cpp:2846-2847); y_00 = 1 exactly.
+  int st = binned_xi_sums(ctx, xi, ell, m, 0, 0, edges, nbins, 1.e-1, 1000000, host);
+  if (st) return st;
+  for (int b = 0; b < nbins; b++) {
+    const double* h = &host[4 * b];
+    const long long np = (long long)llround(h[0]);
+    npairs[b] = np;
+    if (np != 0) {   // S/field.cpp:2923-2931
+      r[b] = h[1] / double(np);
+      xi_out[2 * b] = h[2] / double(np); xi_out[2 * b + 1] = h[3] / double(np);
+    } else {
+      r[b] = centres[b];
+      xi_out[2 * b] = 0.; xi_out[2 * b + 1] = 0.;
+    }
+  }
+  return 0;
+}
+
+extern "C" int trvb_shot_3pcf_bin(trvb_ctx* ctx, trvb_mesh xi, int la, int ma, int lb,
+                                  int mb, const double* edges, const double* centres,
+                                  int nbins, double parity, long long* npairs, double* r,
+                                  double* xi_out) {
+  TRVB_REQUIRE(ctx && xi.data && edges && centres && npairs && r && xi_out,
+               "trvb_shot_3pcf_bin: null argument");
+  TRVB_REQUIRE(xi.layout == TRVB_COMPLEX || xi.layout == TRVB_REAL,
+               "trvb_shot_3pcf_bin: xi must be a configuration-space mesh");
+  TRVB_REQUIRE(ctx->parent == nullptr, "trvb_shot_3pcf_bin: root context only");
+  const GridDesc g = ctx->g;
+  std::vector<double> host;
+  // dr_sample = 1, n_sample = 1e5 (S/field.cpp:3095-3096).
+  int st = binned_xi_sums(ctx, xi, la, ma, lb, mb, edges, nbins, 1., 100000, host);
   if (st) return st;
   const double norm_factors = 1 / g.vol_cell * parity;   // S/field.cpp:3181-3182
   for (int b = 0; b < nbins; b++) {

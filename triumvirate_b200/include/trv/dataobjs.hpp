@@ -80,6 +80,34 @@ struct ThreePCFWindowMeasurements {
   std::vector< std::complex<double> > zeta_shot;
 };
 
+/// Power spectrum measurements (I/dataobjs.hpp:202-211).
+struct PowspecMeasurements {
+  int dim = 0;
+  std::vector<double> kbin;
+  std::vector<double> keff;
+  std::vector<int> nmodes;
+  std::vector< std::complex<double> > pk_raw;
+  std::vector< std::complex<double> > pk_shot;
+};
+
+/// Two-point correlation function measurements (I/dataobjs.hpp:217-224).
+struct TwoPCFMeasurements {
+  int dim = 0;
+  std::vector<double> rbin;
+  std::vector<double> reff;
+  std::vector<int> npairs;
+  std::vector< std::complex<double> > xi;
+};
+
+/// Two-point correlation function window measurements (I/dataobjs.hpp:230-238).
+struct TwoPCFWindowMeasurements {
+  int dim = 0;
+  std::vector<double> rbin;
+  std::vector<double> reff;
+  std::vector<int> npairs;
+  std::vector< std::complex<double> > xi;
+};
+
 }  // namespace trv
 
 #endif  // TRV_B200_DATAOBJS_HPP_

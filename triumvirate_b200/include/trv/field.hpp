@@ -189,6 +189,11 @@ class FieldStats {
     MeshField& field_a, MeshField& field_b, std::complex<double> shotnoise_amp,
     int ell, int m, trv::Binning& kbinning);
 
+  /// S/field.cpp:2705-2945.
+  void compute_ylm_wgtd_2pt_stats_in_config(
+    MeshField& field_a, MeshField& field_b, std::complex<double> shotnoise_amp,
+    int ell, int m, trv::Binning& rbinning);
+
   /// S/field.cpp:2947-3196; y_lm tables replaced by their orders.
   void compute_uncoupled_shotnoise_for_3pcf(
     MeshField& field_a, MeshField& field_b,
@@ -208,6 +213,7 @@ class FieldStats {
   std::shared_ptr<trvb_ctx> ctx_;
   void resize_stats(int num_bins);
   bool if_fields_compatible(MeshField& field_a, MeshField& field_b);
+  int interlaced_() const { return this->params.interlace == "true" ? 1 : 0; }
 };
 
 }  // namespace trv

@@ -17,6 +17,7 @@
 #include "trv/parameters.hpp"
 #include "trv/particles.hpp"
 #include "trv/threept.hpp"
+#include "trv/twopt.hpp"
 
 namespace {
 
@@ -155,6 +156,78 @@ int trv_threept(
   });
 }
 
+/// Two-point estimators (trv::compute_powspec / compute_corrfunc and their
+/// `_in_gpp_box` forms, trv::compute_corrfunc_window; S/twopt.cpp:388-901; bindings
+/// T/_twopt.pyx).  `stat` = "powspec" | "2pcf" | "2pcf-win"; for "2pcf-win" the
+/// catalogue is passed in the `r` slot with `alpha`.
+int trv_twopt(
+  const char* stat, const char* catalogue_type,
+  int nd, const double* xd, const double* yd, const double* zd,
+  const double* nzd, const double* wsd, const double* wcd, const double* los_d,
+  int nr, const double* xr, const double* yr, const double* zr,
+  const double* nzr, const double* wsr, const double* wcr, const double* los_r,
+  const double* boxsize, const int* ngrid, const char* assignment, const char* interlace,
+  int ELL, const char* binning, double bin_min, double bin_max, int num_bins,
+  const double* custom_edges, double alpha, double norm_factor, int verbose, int deterministic,
+  int* dim, double* c_bin, double* c_eff, int* count, double* raw, double* shot,
+  double* elapsed_s
+) {
+  return guarded([&]() {
+    const std::string st(stat);
+    trv::ParameterSet params;
+    set_params(params, catalogue_type, stat, boxsize, ngrid, assignment, interlace,
+               ELL, 0, ELL, "diag", 0, binning, bin_min, bin_max, num_bins,
+               verbose, deterministic, 0, 1);
+    trv::Binning bins(params);
+    if (custom_edges != nullptr) {
+      bins.set_bins(std::vector<double>(custom_edges, custom_edges + num_bins + 1));
+    } else {
+      bins.set_bins();
+    }
+    const bool survey = std::string(catalogue_type) == "survey";
+    const bool window = st == "2pcf-win";
+    trv::ParticleCatalogue data(verbose), rand(verbose);
+    if (!window) data.load_particle_arrays(nd, xd, yd, zd, nzd, wsd, wcd);
+    if (survey || window) rand.load_particle_arrays(nr, xr, yr, zr, nzr, wsr, wcr);
+    trv::LineOfSight* ld = (trv::LineOfSight*)los_d;
+    trv::LineOfSight* lr = (trv::LineOfSight*)los_r;
+
+    auto t0 = std::chrono::steady_clock::now();
+    if (st == "powspec") {
+      trv::PowspecMeasurements out = survey
+        ? trv::compute_powspec(data, rand, ld, lr, params, bins, norm_factor)
+        : trv::compute_powspec_in_gpp_box(data, params, bins, norm_factor);
+      *dim = out.dim;
+      for (int i = 0; i < out.dim; i++) {
+        c_bin[i] = out.kbin[i]; c_eff[i] = out.keff[i]; count[i] = out.nmodes[i];
+        raw[2*i] = out.pk_raw[i].real(); raw[2*i+1] = out.pk_raw[i].imag();
+        shot[2*i] = out.pk_shot[i].real(); shot[2*i+1] = out.pk_shot[i].imag();
+      }
+    } else if (window) {
+      trv::TwoPCFWindowMeasurements out = trv::compute_corrfunc_window(
+        rand, lr, params, bins, alpha, norm_factor);
+      *dim = out.dim;
+      for (int i = 0; i < out.dim; i++) {
+        c_bin[i] = out.rbin[i]; c_eff[i] = out.reff[i]; count[i] = out.npairs[i];
+        raw[2*i] = out.xi[i].real(); raw[2*i+1] = out.xi[i].imag();
+        shot[2*i] = 0.; shot[2*i+1] = 0.;
+      }
+    } else {
+      trv::TwoPCFMeasurements out = survey
+        ? trv::compute_corrfunc(data, rand, ld, lr, params, bins, norm_factor)
+        : trv::compute_corrfunc_in_gpp_box(data, params, bins, norm_factor);
+      *dim = out.dim;
+      for (int i = 0; i < out.dim; i++) {
+        c_bin[i] = out.rbin[i]; c_eff[i] = out.reff[i]; count[i] = out.npairs[i];
+        raw[2*i] = out.xi[i].real(); raw[2*i+1] = out.xi[i].imag();
+        shot[2*i] = 0.; shot[2*i+1] = 0.;
+      }
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    if (elapsed_s) *elapsed_s = std::chrono::duration<double>(t1 - t0).count();
+  });
+}
+
 /// 3PCF window function of a random catalogue (trv::compute_3pcf_window,
 /// S/threept.cpp:2621-3077; binding T/_threept.pyx:276-314).  `wide_angle` != 0
 /// applies the r^{-i_wa-j_wa} kernel to G_LM.
@@ -279,6 +352,25 @@ int trv_norm(
       *norm = trv::calc_bispec_normalisation_from_mesh(cat, params, alpha);
     } else {
       *norm = trv::calc_bispec_normalisation_from_particles(cat, alpha);
+    }
+  });
+}
+
+int trv_norm_powspec(
+  int from_mesh, int n, const double* x, const double* y, const double* z,
+  const double* nz, const double* ws, const double* wc, double alpha,
+  const double* boxsize, const int* ngrid, const char* assignment, double* norm
+) {
+  return guarded([&]() {
+    trv::ParticleCatalogue cat(60);
+    cat.load_particle_arrays(n, x, y, z, nz, ws, wc);
+    if (from_mesh) {
+      trv::ParameterSet params;
+      set_params(params, "sim", "powspec", boxsize, ngrid, assignment, "false",
+                 0, 0, 0, "diag", 0, "lin", 0.005, 0.105, 4, 60, 0, 0, 1);
+      *norm = trv::calc_powspec_normalisation_from_mesh(cat, params, alpha);
+    } else {
+      *norm = trv::calc_powspec_normalisation_from_particles(cat, alpha);
     }
   });
 }

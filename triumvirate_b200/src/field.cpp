@@ -471,7 +471,7 @@ void FieldStats::compute_ylm_wgtd_2pt_stats_in_fourier(
   std::vector<double> pk2(2 * nb), sn2(2 * nb);
   const double S[2] = {shotnoise_amp.real(), shotnoise_amp.imag()};
   dev::check(trvb_twopt_fourier(this->ctx_.get(), field_a.device_view(),
-                                field_b.device_view(), S, ell, m,
+                                field_b.device_view(), S, ell, m, this->interlaced_(),
                                 kbinning.bin_edges.data(), kbinning.bin_centres.data(), nb,
                                 nm.data(), this->k.data(), pk2.data(), sn2.data()),
              "trvb_twopt_fourier");
@@ -479,6 +479,33 @@ void FieldStats::compute_ylm_wgtd_2pt_stats_in_fourier(
     this->nmodes[b] = static_cast<int>(nm[b]);
     this->pk[b] = std::complex<double>(pk2[2 * b], pk2[2 * b + 1]);
     this->sn[b] = std::complex<double>(sn2[2 * b], sn2[2 * b + 1]);
+  }
+}
+
+void FieldStats::compute_ylm_wgtd_2pt_stats_in_config(
+  MeshField& field_a, MeshField& field_b, std::complex<double> shotnoise_amp,
+  int ell, int m, trv::Binning& rbinning
+) {
+  this->resize_stats(rbinning.num_bins);
+  if (!this->if_fields_compatible(field_a, field_b)) {
+    throw trvs::InvalidDataError("Input mesh fields have incompatible physical properties.");
+  }
+  this->reset_stats();
+  trvb_ctx* c = this->ctx_.get();
+  dev::Mesh xi3d(this->ctx_, c, TRVB_COMPLEX);
+  const double S[2] = {shotnoise_amp.real(), shotnoise_amp.imag()};
+  dev::check(trvb_shot_xi(c, field_a.device_view(), field_b.device_view(), S,
+                          this->interlaced_(), xi3d.view()), "trvb_shot_xi");
+  trvs::count_ifft += 1;
+  const int nb = rbinning.num_bins;
+  std::vector<long long> np(nb);
+  std::vector<double> xi2(2 * nb);
+  dev::check(trvb_twopt_config_bin(c, xi3d.view(), ell, m, rbinning.bin_edges.data(),
+                                   rbinning.bin_centres.data(), nb, np.data(),
+                                   this->r.data(), xi2.data()), "trvb_twopt_config_bin");
+  for (int b = 0; b < nb; b++) {
+    this->npairs[b] = static_cast<int>(np[b]);
+    this->xi[b] = std::complex<double>(xi2[2 * b], xi2[2 * b + 1]);
   }
 }
 
@@ -494,7 +521,7 @@ void FieldStats::compute_uncoupled_shotnoise_for_3pcf(
   trvb_ctx* c = this->ctx_.get();
   dev::Mesh xi(this->ctx_, c, TRVB_COMPLEX);
   const double S[2] = {shotnoise_amp.real(), shotnoise_amp.imag()};
-  dev::check(trvb_shot_xi(c, field_a.device_view(), field_b.device_view(), S, xi.view()),
+  dev::check(trvb_shot_xi(c, field_a.device_view(), field_b.device_view(), S, this->interlaced_(), xi.view()),
              "trvb_shot_xi");
   trvs::count_ifft += 1;
   const int nb = rbinning.num_bins;
@@ -522,7 +549,7 @@ std::complex<double> FieldStats::compute_uncoupled_shotnoise_for_bispec_per_bin(
   trvb_ctx* c = this->ctx_.get();
   dev::Mesh xi(this->ctx_, c, TRVB_COMPLEX);
   const double S[2] = {shotnoise_amp.real(), shotnoise_amp.imag()};
-  dev::check(trvb_shot_xi(c, field_a.device_view(), field_b.device_view(), S, xi.view()),
+  dev::check(trvb_shot_xi(c, field_a.device_view(), field_b.device_view(), S, this->interlaced_(), xi.view()),
              "trvb_shot_xi");
   trvs::count_ifft += 1;
   dev::check(trvb_sjl_table(c, sj_a.order, sj_a.y.data(), sj_a.c.data(),

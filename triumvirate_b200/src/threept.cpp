@@ -760,7 +760,7 @@ trv::BispecMeasurements bispec_impl(
         std::vector<double> kk(nb);
         pk.assign(2 * nb, 0.); sn.assign(2 * nb, 0.);
         const double S[2] = {Sbar_LM.real(), Sbar_LM.imag()};
-        dev::check(trvb_twopt_fourier(c, dn_00.view(), N_LM_ref, S, ell, m,
+        dev::check(trvb_twopt_fourier(c, dn_00.view(), N_LM_ref, S, ell, m, /*interlaced=*/0,
                                       kbinning.bin_edges.data(), kbinning.bin_centres.data(),
                                       nb, nm.data(), kk.data(), pk.data(), sn.data()),
                    "trvb_twopt_fourier");
@@ -784,7 +784,7 @@ trv::BispecMeasurements bispec_impl(
       const bool real_xi = dn_LM_ref.layout() == TRVB_HALF && N_00.layout == TRVB_HALF
         && S[1] == 0.;
       xi = dev::Mesh(eng.shared(), c, real_xi ? TRVB_REAL : TRVB_COMPLEX);
-      dev::check(trvb_shot_xi(c, dn_LM_ref.view(), N_00, S, xi.view()), "trvb_shot_xi");
+      dev::check(trvb_shot_xi(c, dn_LM_ref.view(), N_00, S, /*interlaced=*/0, xi.view()), "trvb_shot_xi");
       trvs::count_ifft += 1;
       have_xi = true;
       dev::profile_mark(c, "shot_xi");
@@ -883,7 +883,7 @@ trv::ThreePCFMeasurements threepcf_impl(
       const bool real_xi = dn_LM_ref.layout() == TRVB_HALF && N_00.layout == TRVB_HALF
         && S[1] == 0.;
       xi = dev::Mesh(eng.shared(), c, real_xi ? TRVB_REAL : TRVB_COMPLEX);
-      dev::check(trvb_shot_xi(c, dn_LM_ref.view(), N_00, S, xi.view()), "trvb_shot_xi");
+      dev::check(trvb_shot_xi(c, dn_LM_ref.view(), N_00, S, /*interlaced=*/0, xi.view()), "trvb_shot_xi");
       trvs::count_ifft += 1;
       have_xi = true;
       dev::profile_mark(c, "shot_xi");
