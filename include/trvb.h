@@ -154,7 +154,8 @@ int trvb_mesh_axpby(trvb_ctx* ctx, trvb_mesh dst, double a, trvb_mesh src,
  * (MeshField::apply_wide_angle_pow_law_kernel with power = i_wa + j_wa,
  * S/field.cpp:1727-1762). */
 int trvb_mesh_pow_law(trvb_ctx* ctx, trvb_mesh mesh, int power);
-/* sum_x Re(mesh)^3 (S/field.cpp:2056-2058). */
+/* sum_x Re(mesh)^order, order >= 2 (S/field.cpp:2056-2058); _pow3 is order 3. */
+int trvb_mesh_sum_pow(trvb_ctx* ctx, trvb_mesh mesh, int order, double* out);
 int trvb_mesh_sum_pow3(trvb_ctx* ctx, trvb_mesh mesh, double* out);
 
 /* ---- transforms (replace S/field.cpp:1496-1720) ------------------------

@@ -911,14 +911,16 @@ k_shot_3pcf_bin(XView xi, GridDesc g, Cube cube,
 }
 
 __global__ void __launch_bounds__(256)
-k_sum_pow3(const double* __restrict__ p, long long n, int stride,
+k_sum_pow3(const double* __restrict__ p, long long n, int stride, int order,
            double* __restrict__ partial) {
   __shared__ double sm[32];
   double s = 0.;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     const double v = p[i * stride];
-    s += v * v * v;
+    double t = v * v;                       // order 2 (power spectrum) or 3 (bispectrum)
+    for (int q = 2; q < order; q++) t *= v;
+    s += t;
   }
   s = block_sum(s, sm);
   if (threadIdx.x == 0) partial[blockIdx.x] = s;
@@ -991,15 +993,20 @@ int run_binned(trvb_ctx* ctx, const std::vector<BinRule>& rules, long long nwork
 // =====================================================================
 
 extern "C" int trvb_mesh_sum_pow3(trvb_ctx* ctx, trvb_mesh mesh, double* out) {
-  TRVB_REQUIRE(ctx && mesh.data && out, "trvb_mesh_sum_pow3: null argument");
+  return trvb_mesh_sum_pow(ctx, mesh, 3, out);
+}
+
+extern "C" int trvb_mesh_sum_pow(trvb_ctx* ctx, trvb_mesh mesh, int order, double* out) {
+  TRVB_REQUIRE(ctx && mesh.data && out, "trvb_mesh_sum_pow: null argument");
+  TRVB_REQUIRE(order >= 2, "trvb_mesh_sum_pow: order must be >= 2, got %d", order);
   TRVB_REQUIRE(mesh.layout == TRVB_REAL || mesh.layout == TRVB_COMPLEX,
-               "trvb_mesh_sum_pow3: configuration-space layouts only");
+               "trvb_mesh_sum_pow: configuration-space layouts only");
   const int stride = mesh.layout == TRVB_COMPLEX ? 2 : 1;
   const int blocks = ctx->num_sms * 8;
   double* scratch;
   int st = trvb_scratch(ctx, sizeof(double) * (blocks + 8), &scratch);
   if (st) return st;
-  k_sum_pow3<<<blocks, 256, 0, ctx->stream>>>((const double*)mesh.data, ctx->g.nmesh, stride, scratch);
+  k_sum_pow3<<<blocks, 256, 0, ctx->stream>>>((const double*)mesh.data, ctx->g.nmesh, stride, order, scratch);
   TRVB_LAUNCH_CHECK();
   k_sum_cols<<<1, 32, 0, ctx->stream>>>(scratch, blocks, 1, scratch + blocks);
   TRVB_LAUNCH_CHECK();

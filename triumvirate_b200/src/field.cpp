@@ -406,15 +406,15 @@ void MeshField::inv_fourier_transform_sjl_ylm_wgtd_field(
 }
 
 double MeshField::calc_grid_based_powlaw_norm(ParticleCatalogue& particles, int order) {
-  if (order != 3) {
-    throw trvs::UnimplementedError(
-      "calc_grid_based_powlaw_norm: only order 3 (bispectrum) is on the "
-      "three-point path; got %d.", order);
+  if (order < 2) {
+    throw trvs::InvalidParameterError(
+      "calc_grid_based_powlaw_norm: order must be 2 (power spectrum) or 3 (bispectrum); "
+      "got %d.", order);
   }
   this->assign_kind(particles, nullptr, TRVB_W_W, 0, 0, 1., false);
   double vol_int = 0.;
-  dev::check(trvb_mesh_sum_pow3(this->ctx_.get(), this->mesh_.view(), &vol_int),
-             "trvb_mesh_sum_pow3");
+  dev::check(trvb_mesh_sum_pow(this->ctx_.get(), this->mesh_.view(), order, &vol_int),
+             "trvb_mesh_sum_pow");
   vol_int *= this->vol_cell;
   return 1. / vol_int;
 }
