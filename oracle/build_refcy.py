@@ -1,5 +1,5 @@
 """TEST INFRASTRUCTURE ONLY -- builds the reference's OWN Cython binding layer
-(``T/_threept.pyx``, ``_particles.pyx``, ``dataobjs.pyx``, ``parameters.pyx`` with
+(``T/_threept.pyx``, ``_twopt.pyx``, ``_particles.pyx``, ``dataobjs.pyx``, ``parameters.pyx`` with
 their ``.pxd`` files) UNMODIFIED against the headers and the shared library of
 triumvirate_b200, as the drop-in proof of SURVEY.md section 8b: the extern
 blocks ``T/_threept.pyx:27-95``, ``T/_particles.pxd:7-15``, ``T/dataobjs.pxd:16-128``
@@ -23,7 +23,7 @@ HERE = Path(__file__).resolve().parent
 ROOT = HERE.parent
 REF = Path("/root/reference/src/triumvirate")
 OUT = HERE / "_ref" / "trvcy"
-MODULES = ("parameters", "dataobjs", "_particles", "_threept")
+MODULES = ("parameters", "dataobjs", "_particles", "_threept", "_twopt")
 
 SETUP = '''
 from setuptools import setup, Extension
@@ -46,7 +46,7 @@ setup(name="trvcy", ext_modules=cythonize(
 
 
 def available():
-    return OUT.exists() and len(list(OUT.glob("_threept*.so"))) == 1
+    return OUT.exists() and all(len(list(OUT.glob(f"{m}.*.so"))) == 1 for m in MODULES)
 
 
 def build(force=False):

@@ -9,10 +9,18 @@ from triumvirate_b200 import core, catalogue as tcat
 which = sys.argv[1:] or ["C1", "C4", "C3", "C5"]
 res = {}
 
+import os
+PROFILE = bool(os.environ.get("TRV_PROFILE"))
+if PROFILE:
+    core.profile_enable(True)
+
 def timed(fn, reps=2):
     out = None; ts = []
     for _ in range(reps):
         t = time.perf_counter(); out = fn(); ts.append(time.perf_counter() - t)
+        if PROFILE:
+            print(json.dumps({k: round(v * 1e3, 2) for k, v in core.profile_report().items()}),
+                  file=sys.stderr, flush=True)
     return out, ts
 
 def shell_octant(gen, n):

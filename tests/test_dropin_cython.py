@@ -60,6 +60,7 @@ def trvcy():
     sys.path.insert(0, str(ROOT / "oracle" / "_ref"))
     import trvcy._particles   # noqa: F401
     import trvcy._threept     # noqa: F401
+    import trvcy._twopt       # noqa: F401
     import trvcy.dataobjs     # noqa: F401
     import trvcy.parameters   # noqa: F401
     return trvcy
@@ -89,6 +90,11 @@ def test_reference_cython_layer_links_against_libtrv_b200(trvcy):
              "_compute_bispec", "_compute_bispec_in_gpp_box"]
     for n in names:
         assert callable(getattr(trvcy._threept, n)), n
+    for n in ["_calc_powspec_normalisation_from_particles", "_calc_powspec_normalisation_from_mesh",
+              "_calc_powspec_normalisation_from_meshes", "_compute_powspec", "_compute_corrfunc",
+              "_compute_powspec_in_gpp_box", "_compute_corrfunc_in_gpp_box",
+              "_compute_corrfunc_window"]:
+        assert callable(getattr(trvcy._twopt, n)), n
     with open("/proc/self/maps") as f:
         assert "triumvirate_b200/libtrv_b200.so" in f.read()
 
@@ -179,3 +185,45 @@ def test_window_golden_through_reference_cython(trvcy, golden_rand_catalogue):
     out = trvcy._threept._compute_3pcf_window(cat_r, los_r, ps, binning, alpha=1.,
                                               norm_factor=norm, wide_angle=False)
     _check(out, load_golden("zetaw202_diag.txt"), "zeta")
+
+
+# ---- two-point estimators through the reference's own T/_twopt.pyx -----------
+
+def _paramset_2pt(trvcy, catalogue_type, statistic_type, degree, rng):
+    d = copy.deepcopy(TEST_PARAMS)
+    d["catalogue_type"], d["statistic_type"] = catalogue_type, statistic_type
+    d["degrees"] = {"ell1": None, "ell2": None, "ELL": degree}
+    d["range"] = list(rng)
+    return trvcy.parameters.ParameterSet(param_dict=d)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("degree", [0, 2])
+@pytest.mark.parametrize("stat", ["powspec", "2pcf"])
+def test_twopt_goldens_through_reference_cython(trvcy, stat, degree, golden_data_catalogue,
+                                                golden_rand_catalogue):
+    """pk*_gpp / xi*_gpp / pk*_lpp / xi*_lpp through `_compute_powspec*` and
+    `_compute_corrfunc*` of the reference's unmodified Cython module."""
+    from conftest import check_twopt_against_golden
+    from triumvirate_b200 import catalogue as tcat
+    rng = (0.005, 0.105) if stat == "powspec" else (50., 150.)
+    data, rand = golden_data_catalogue, golden_rand_catalogue
+    name = "powspec" if stat == "powspec" else "corrfunc"
+    prefix = "pk" if stat == "powspec" else "xi"
+    # periodic box
+    ps = _paramset_2pt(trvcy, "sim", stat, degree, rng)
+    binning = trvcy.dataobjs.Binning.from_parameter_set(ps)
+    cat = _catalogue(trvcy, tcat.periodise(data[:3], 1000.), data[3])
+    norm = trvcy._twopt._calc_powspec_normalisation_from_particles(cat, alpha=1.)
+    out = getattr(trvcy._twopt, f"_compute_{name}_in_gpp_box")(cat, ps, binning, norm)
+    check_twopt_against_golden(out, load_golden(f"{prefix}{degree}_gpp.txt"), stat)
+    # survey
+    ps = _paramset_2pt(trvcy, "survey", stat, degree, rng)
+    binning = trvcy.dataobjs.Binning.from_parameter_set(ps)
+    los_d, los_r = tcat.compute_los(data[:3]), tcat.compute_los(rand[:3])
+    pos_d, pos_r = tcat.centre(data[:3], rand[:3], 1000.)
+    cat_d, cat_r = _catalogue(trvcy, pos_d, data[3]), _catalogue(trvcy, pos_r, rand[3])
+    alpha = data.shape[1] / rand.shape[1]
+    norm = trvcy._twopt._calc_powspec_normalisation_from_particles(cat_r, alpha=alpha)
+    out = getattr(trvcy._twopt, f"_compute_{name}")(cat_d, cat_r, los_d, los_r, ps, binning, norm)
+    check_twopt_against_golden(out, load_golden(f"{prefix}{degree}_lpp.txt"), stat)

@@ -9,10 +9,10 @@
 #include <complex>
 #include <string>
 
-#include "trv/dataobjs.hpp"
-#include "trv/field.hpp"
-#include "trv/parameters.hpp"
-#include "trv/particles.hpp"
+#include "dataobjs.hpp"
+#include "field.hpp"
+#include "parameters.hpp"
+#include "particles.hpp"
 
 namespace trv {
 
