@@ -218,6 +218,11 @@ int trvb_shell_ifft_batch(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh src, int ell,
  * (S/field.cpp:1908-2010, amp = 1/V), spline table from trvb_sjl_table. */
 int trvb_sjl_ifft(trvb_ctx* ctx, trvb_mesh src, int ell, int m, double r,
                   double amp, trvb_mesh dst);
+/* The same for `nbins` radii r[q] of one (l, m), written as nbins CONSECUTIVE
+ * TRVB_COMPLEX meshes starting at device address `dst`: y_lm src / W and |k| are
+ * evaluated once, then each pass over them emits four weighted spectra. */
+int trvb_sjl_ifft_batch(trvb_ctx* ctx, trvb_mesh src, int ell, int m,
+                        const double* r, double amp, int nbins, void* dst);
 /* Upload the natural-cubic-spline table of j_ell (I/maths.hpp:305-306,
  * S/maths.cpp:309-375): knots x_i = step*i, values y[i], coefficients c[i],
  * i < nsample; beyond split = step*(nsample-1) j_ell is evaluated directly. */

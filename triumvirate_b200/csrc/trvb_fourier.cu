@@ -200,6 +200,48 @@ k_sjl_spectrum(KView src, GridDesc g, Tables tb, SjlView sj, int ell, int m,
   });
 }
 
+// The bin-independent part of k_sjl_spectrum, evaluated once per (l, m):
+// A(k) = amp y_lm(khat) src(k) / W(k) and |k|.
+__global__ void __launch_bounds__(256)
+k_sjl_prepare(KView src, GridDesc g, Tables tb, int ell, int m, double amp,
+              double2* __restrict__ A, double* __restrict__ kmag_out) {
+  const YlmCoef yc = ylm_coef(ell, m);
+  for_each_cell(g.n[0], g.n[1], g.n[2], [&](int i, int j, int k, long long t) {
+    const double kx = __dmul_rn((double)signed_index(i, g.n[0]), g.dk[0]);
+    const double ky = __dmul_rn((double)signed_index(j, g.n[1]), g.dk[1]);
+    const double kz = __dmul_rn((double)signed_index(k, g.n[2]), g.dk[2]);
+    cplx fk = kload(src, i, j, k);
+    const double rw = 1. / window_at(tb, g.order, i, j, k);
+    fk.re *= rw; fk.im *= rw;
+    const cplx v = cmul(ylm_eval(yc, kx, ky, kz), fk);
+    A[t] = make_double2(v.re * amp, v.im * amp);
+    kmag_out[t] = vec3_norm_exact(kx, ky, kz);
+  });
+}
+
+// NB spectra j_l(|k| r_q) A(k) per pass over A and |k| (24 B read, 16 B written per
+// bin and mode; no division, no square root).
+constexpr int SJL_NB = 4;
+struct SjlBatch { double r[SJL_NB]; double2* dst[SJL_NB]; int count; };
+
+__global__ void __launch_bounds__(256)
+k_sjl_apply(const double2* __restrict__ A, const double* __restrict__ kmag, long long nmesh,
+            SjlView sj, SjlBatch b) {
+  const double inv_step = 1. / sj.step;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nmesh;
+       t += (long long)gridDim.x * blockDim.x) {
+    const double2 a = A[t];
+    const double kk = kmag[t];
+#pragma unroll
+    for (int q = 0; q < SJL_NB; q++) {
+      if (q < b.count) {
+        const double jl = sjl_eval_fast(sj, __dmul_rn(kk, b.r[q]), inv_step);
+        b.dst[q][t] = make_double2(jl * a.x, jl * a.y);
+      }
+    }
+  }
+}
+
 // Batched plan over `batch` consecutive meshes of ctx's grid.
 int get_batch_plan(trvb_ctx* ctx, cufftType type, int batch, cufftHandle* out) {
   auto key = std::make_pair((int)type, batch);
@@ -480,6 +522,48 @@ extern "C" int trvb_shell_ifft_batch(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh src
   }
   trvb_dev_free_raw(ctx, d_par);
   if (real_out) trvb_dev_free_raw(ctx, spec_tmp);
+  return st;
+}
+
+extern "C" int trvb_sjl_ifft_batch(trvb_ctx* ctx, trvb_mesh src, int ell, int m,
+                                   const double* r, double amp, int nbins, void* dst) {
+  TRVB_REQUIRE(ctx && src.data && r && dst && nbins > 0, "trvb_sjl_ifft_batch: bad argument");
+  TRVB_REQUIRE(ctx->parent == nullptr, "trvb_sjl_ifft_batch: root context only");
+  TRVB_REQUIRE(src.layout != TRVB_REAL, "trvb_sjl_ifft_batch: src must be a Fourier mesh");
+  auto it = ctx->sjl.find(ell);
+  TRVB_REQUIRE(it != ctx->sjl.end(), "trvb_sjl_ifft_batch: no spline table for ell = %d "
+               "(call trvb_sjl_table first)", ell);
+  SjlView sj;
+  sj.y = it->second.d_y; sj.c = it->second.d_c;
+  sj.nsample = it->second.nsample; sj.step = it->second.step; sj.ell = ell;
+  const GridDesc& g = ctx->g;
+  const size_t mesh_bytes = trvb_mesh_bytes(ctx, TRVB_COMPLEX);
+  double2* A = nullptr; double* kmag = nullptr;
+  TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&A, mesh_bytes));
+  TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&kmag, mesh_bytes / 2));
+  const RowLaunch rl = row_launch(ctx->num_sms, g.n[0], g.n[1], g.n[2]);
+  k_sjl_prepare<<<rl.grid, rl.block, 0, ctx->stream>>>(
+    kview_of(ctx, src), g, tables_of(ctx), ell, m, amp, A, kmag);
+  TRVB_LAUNCH_CHECK();
+  const int blocks = (int)std::min<long long>((g.nmesh + 255) / 256, (long long)ctx->num_sms * 16);
+  int st = 0;
+  for (int q0 = 0; q0 < nbins && st == 0; q0 += SJL_NB) {
+    SjlBatch b;
+    b.count = std::min(SJL_NB, nbins - q0);
+    for (int q = 0; q < SJL_NB; q++) {
+      const int qq = q0 + std::min(q, b.count - 1);
+      b.r[q] = r[qq];
+      b.dst[q] = (double2*)((char*)dst + mesh_bytes * (size_t)qq);
+    }
+    k_sjl_apply<<<blocks, 256, 0, ctx->stream>>>(A, kmag, g.nmesh, sj, b);
+    TRVB_LAUNCH_CHECK();
+    for (int q = 0; q < b.count && st == 0; q++) {
+      trvb_mesh out; out.data = b.dst[q]; out.layout = TRVB_COMPLEX; out.k0_add = 0.;
+      st = trvb_fft_inverse(ctx, out, out);
+    }
+  }
+  trvb_dev_free_raw(ctx, A);      // stream-ordered reuse
+  trvb_dev_free_raw(ctx, kmag);
   return st;
 }
 

@@ -851,13 +851,14 @@ k_twopt_fourier(KView fa, KView fb, GridDesc g, Tables tb, Cube cube,
 
 // (fa conj(fb)/C1 - S C1/C1) / V on the full grid (S/field.cpp:3273-3298).
 // `n2s` = stored extent of the last axis of dst: n2 (COMPLEX) or n2/2+1 (HALF).
+template <bool INTERLACED>
 __global__ void __launch_bounds__(256)
 k_shot_spectrum(KView fa, KView fb, GridDesc g, Tables tb, double S_re, double S_im,
-                int n2s, int interlaced, double2* __restrict__ dst) {
+                int n2s, double2* __restrict__ dst) {
   const double inv_vol = 1. / g.vol;
   for_each_cell(g.n[0], g.n[1], n2s, [&](int i, int j, int k, long long t) {
     const cplx a = kload(fa, i, j, k), b = kload(fb, i, j, k);
-    if (interlaced) {
+    if constexpr (INTERLACED) {
       // (fa conj(fb) - S C1_iso) / (W_a W_b) / V, S/field.cpp:2760-2781.
       const int mi = i < g.n[0] / 2 ? i : i - g.n[0];   // S/field.cpp:538-544
       const int mj = j < g.n[1] / 2 ? j : j - g.n[1];
@@ -1206,18 +1207,30 @@ extern "C" int trvb_shot_xi(trvb_ctx* ctx, trvb_mesh fa, trvb_mesh fb, const dou
     trvb_mesh half; half.layout = TRVB_HALF; half.k0_add = 0.; half.data = nullptr;
     TRVB_CUDA(trvb_dev_alloc_raw(ctx, &half.data, trvb_mesh_bytes(ctx, TRVB_HALF)));
     const RowLaunch rl = row_launch(ctx->num_sms, g.n[0], g.n[1], g.nh);
-    k_shot_spectrum<<<rl.grid, rl.block, 0, ctx->stream>>>(
-      kview_of(ctx, fa), kview_of(ctx, fb), g, tables_of(ctx), S[0], S[1], g.nh, interlaced,
-      (double2*)half.data);
+    if (interlaced) {
+      k_shot_spectrum<true><<<rl.grid, rl.block, 0, ctx->stream>>>(
+        kview_of(ctx, fa), kview_of(ctx, fb), g, tables_of(ctx), S[0], S[1], g.nh,
+        (double2*)half.data);
+    } else {
+      k_shot_spectrum<false><<<rl.grid, rl.block, 0, ctx->stream>>>(
+        kview_of(ctx, fa), kview_of(ctx, fb), g, tables_of(ctx), S[0], S[1], g.nh,
+        (double2*)half.data);
+    }
     TRVB_LAUNCH_CHECK();
     int st = trvb_fft_inverse(ctx, half, dst);
     trvb_dev_free_raw(ctx, half.data);
     return st;
   }
   const RowLaunch rl = row_launch(ctx->num_sms, g.n[0], g.n[1], g.n[2]);
-  k_shot_spectrum<<<rl.grid, rl.block, 0, ctx->stream>>>(
-    kview_of(ctx, fa), kview_of(ctx, fb), g, tables_of(ctx), S[0], S[1], g.n[2], interlaced,
-    (double2*)dst.data);
+  if (interlaced) {
+    k_shot_spectrum<true><<<rl.grid, rl.block, 0, ctx->stream>>>(
+      kview_of(ctx, fa), kview_of(ctx, fb), g, tables_of(ctx), S[0], S[1], g.n[2],
+      (double2*)dst.data);
+  } else {
+    k_shot_spectrum<false><<<rl.grid, rl.block, 0, ctx->stream>>>(
+      kview_of(ctx, fa), kview_of(ctx, fb), g, tables_of(ctx), S[0], S[1], g.n[2],
+      (double2*)dst.data);
+  }
   TRVB_LAUNCH_CHECK();
   return trvb_fft_inverse(ctx, dst, dst);
 }

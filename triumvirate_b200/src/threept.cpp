@@ -920,12 +920,11 @@ trv::ThreePCFMeasurements threepcf_impl(
     }
     auto sjl_fields = [&](int ell, int m, const std::vector<int>& bins) {
       auto slab = std::make_shared<Slab>(eng.shared(), c, TRVB_COMPLEX, (int)bins.size());
-      for (size_t i = 0; i < bins.size(); i++) {
-        trvb_mesh out; out.data = slab->mesh((int)i); out.layout = TRVB_COMPLEX; out.k0_add = 0.;
-        dev::check(trvb_sjl_ifft(c, dn_00.view(), ell, m, reff[bins[i]], 1. / eng.vol(), out),
-                   "trvb_sjl_ifft");
-        trvs::count_ifft += 1;
-      }
+      std::vector<double> radii;
+      for (int b : bins) radii.push_back(reff[b]);
+      dev::check(trvb_sjl_ifft_batch(c, dn_00.view(), ell, m, radii.data(), 1. / eng.vol(),
+                                     (int)bins.size(), slab->data()), "trvb_sjl_ifft_batch");
+      trvs::count_ifft += (int)bins.size();
       return slab;
     };
     const bool same_fields = (params.ell1 == params.ell2 && t.m1 == t.m2);
