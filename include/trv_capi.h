@@ -61,7 +61,9 @@ void trv_counters(int* count_fft, int* count_ifft, double* gib_gpu_max);
  *                   that trv_partition_owners() gives to part_rank (compact
  *                   blocks of the bin-pair matrix, so that a rank transforms
  *                   only the shells it pairs) and leaves zeros elsewhere (sum
- *                   over ranks = the full result)
+ *                   over ranks = the full result).  Bispectrum with two or
+ *                   more ranks: the last rank computes the shot noise of every
+ *                   entry and no pairs; the pairs are dealt to the others
  * Outputs (capacity >= max(num_bins^2, num_bins) entries): *dim = dv_dim;
  * bin centres, effective coordinates, nmodes/npairs, raw and shot statistics as
  * interleaved (re, im) already multiplied by norm_factor

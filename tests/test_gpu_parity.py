@@ -505,6 +505,46 @@ def test_partitioned_pairs_sum_to_full(core):
     for key in ("bk_raw", "bk_shot"):
         total = sum(p[key] for p in parts)
         assert np.array_equal(total, full[key])
+    # the last rank owns the shot noise of every entry and no pairs
+    assert not parts[2]["bk_raw"].any() and parts[2]["bk_shot"].all()
+    assert not parts[0]["bk_shot"].any() and not parts[1]["bk_shot"].any()
+    for world in (2, 4):
+        parts = [core.threept("bispec", "sim", part_rank=r, part_count=world, **kw)
+                 for r in range(world)]
+        for key in ("bk_raw", "bk_shot"):
+            assert np.array_equal(sum(p[key] for p in parts), full[key])
+
+
+@pytest.mark.parametrize("stat,degrees,form", [("bispec", (2, 0, 2), "diag"),
+                                                ("bispec", (1, 1, 0), "full"),
+                                                ("3pcf", (1, 1, 0), "diag")])
+def test_partitioned_survey_sums_to_full(core, stat, degrees, form):
+    """The same for paired survey catalogues (y_LM-weighted fields, several (m1, m2, M)
+    terms): the ranks without a shot-noise share skip N_LM, the rank without pairs
+    skips the shell fields, and the partial vectors still add up to the full result.
+    Equality is up to summation order here (1e-12): the staging engine of the pair
+    reduction and the radial histogram's atomics are not pinned across calls."""
+    from triumvirate_b200 import catalogue as tcat
+    L, ng = 1000., 32
+    pd_, pr_, nzd, nzr, wsd, wsr, wcd, wcr = _survey_inputs(77, 1200, 5000, L)
+    los_d, los_r = tcat.compute_los(pd_), tcat.compute_los(pr_)
+    pd_c, pr_c = tcat.centre(pd_, pr_, L)
+    rng = (0.01, 0.09) if stat == "bispec" else (40., 280.)
+    kw = dict(boxsize=L, ngrid=ng, assignment="tsc", degrees=degrees, form=form, bin_range=rng,
+              num_bins=4, norm_factor=1., pos_d=pd_c, nz_d=nzd, ws_d=wsd, wc_d=wcd, los_d=los_d,
+              pos_r=pr_c, nz_r=nzr, ws_r=wsr, wc_r=wcr, los_r=los_r, deterministic=True)
+    full = core.threept(stat, "survey", **kw)
+    raw, shot = ("bk_raw", "bk_shot") if stat == "bispec" else ("zeta_raw", "zeta_shot")
+    for world in (2, 3):
+        parts = [core.threept(stat, "survey", part_rank=r, part_count=world, **kw)
+                 for r in range(world)]
+        for key in (raw, shot):
+            total = sum(p[key] for p in parts)
+            assert np.max(np.abs(total - full[key])) <= 1.e-12 * np.max(np.abs(full[key])), \
+                (world, key)
+        # every entry comes from exactly one rank
+        for key in (raw, shot):
+            assert np.all(sum((p[key] != 0).astype(int) for p in parts) <= 1), (world, key)
 
 
 def test_gram_tma_and_cp_async_stages_agree(core, monkeypatch):

@@ -22,6 +22,19 @@ def owners(form, degrees, num_bins, world_size, idx_bin=0):
     return core.partition_owners(form, degrees, num_bins, world_size, idx_bin=idx_bin)
 
 
+def bispec_owners(form, degrees, num_bins, world_size, idx_bin=0):
+    """(pair owner, shot-noise owner) of every bispectrum entry: with two or more
+    ranks the LAST rank computes the shot noise of every entry (its full-grid inverse
+    FFT does not depend on the pair partition) and the pairs are dealt to the other
+    ranks (``bispec_share`` in src/threept.cpp).  The 3PCF keeps both on the pair
+    owner."""
+    if world_size < 2:
+        own = owners(form, degrees, num_bins, 1, idx_bin=idx_bin)
+        return own, own
+    own = owners(form, degrees, num_bins, world_size - 1, idx_bin=idx_bin)
+    return own, np.full_like(own, world_size - 1)
+
+
 def local_entries(form, degrees, num_bins, rank, world_size, idx_bin=0):
     return np.nonzero(owners(form, degrees, num_bins, world_size, idx_bin=idx_bin) == rank)[0]
 

@@ -583,6 +583,33 @@ std::vector<char> active_entries(const trv::ParameterSet& params, const DataVect
   return active;
 }
 
+/// Bispectrum work split.  The shot-noise branch (one full-grid inverse FFT and its
+/// reductions, about as expensive as the whole pair phase after the restructuring)
+/// does not depend on the pair partition, so with two or more ranks it goes to the
+/// LAST rank for every entry, and the pair entries are dealt to the other ranks.
+struct BispecShare {
+  std::vector<char> pairs;   // entries whose raw bispectrum this rank computes
+  std::vector<char> shot;    // entries whose shot noise this rank computes
+  bool any_pairs = false, any_shot = false;
+};
+
+BispecShare bispec_share(const trv::ParameterSet& params, const DataVector& dv) {
+  BispecShare sh;
+  sh.pairs.assign(dv.dim, 0); sh.shot.assign(dv.dim, 0);
+  const int world = params.part_count, rank = params.part_rank;
+  if (world < 2) {
+    sh.pairs.assign(dv.dim, 1); sh.shot.assign(dv.dim, 1);
+  } else {
+    const std::vector<int> owner = partition_owners(dv.row, dv.col, world - 1);
+    for (int i = 0; i < dv.dim; i++) {
+      sh.pairs[i] = owner[i] == rank;
+      sh.shot[i] = rank == world - 1;
+    }
+  }
+  for (int i = 0; i < dv.dim; i++) { sh.any_pairs |= sh.pairs[i]; sh.any_shot |= sh.shot[i]; }
+  return sh;
+}
+
 /// Sub-grid extents for shells reaching k_max (section 2 of the file header).
 void choose_subgrid(const trv::ParameterSet& params, double kmax, int nsub[3]) {
   bool coarsen = true;
@@ -614,15 +641,18 @@ trv::BispecMeasurements bispec_impl(
   const cdouble factor_phase = std::pow(trvm::M_I, params.ell1 + params.ell2);
   const int nb = kbinning.num_bins;
   const DataVector dv = make_data_vector(params, nb);
-  const std::vector<char> active = active_entries(params, dv);
+  const BispecShare share = bispec_share(params, dv);
+  const std::vector<char>& active = share.pairs;
+  const std::vector<char>& shot_active = share.shot;
 
   trvb_ctx* c = eng.ctx();
 
   // Common fields: delta n_00(k) and N_00(k).
   dev::Mesh dn_00 = eng.density_fluctuation(0, 0);
   dev::Mesh N_00_own;
-  if (survey) N_00_own = eng.quadratic_field(0, 0);
-  const trvb_mesh N_00 = survey ? N_00_own.view() : eng.quadratic_view_of_fluctuation(dn_00);
+  if (survey && share.any_shot) N_00_own = eng.quadratic_field(0, 0);   // shot noise only
+  const trvb_mesh N_00 = (survey && share.any_shot)
+    ? N_00_own.view() : eng.quadratic_view_of_fluctuation(dn_00);
   dev::profile_mark(c, "fields_00");
 
   trvm::SphericalBesselCalculator sj_a(params.ell1), sj_b(params.ell2);
@@ -705,8 +735,10 @@ trv::BispecMeasurements bispec_impl(
     // ---- fields that depend on (L, M) only -----------------------------
     if (survey && !(have_LM && cached_M == t.M)) {
       dn_LM = eng.density_fluctuation(params.ELL, t.M);
-      N_LM = eng.quadratic_field(params.ELL, t.M);
-      Sbar_LM = eng.shotnoise_amp(params.ELL, t.M);
+      if (share.any_shot) {   // N_LM and the amplitude feed the shot-noise branch only
+        N_LM = eng.quadratic_field(params.ELL, t.M);
+        Sbar_LM = eng.shotnoise_amp(params.ELL, t.M);
+      }
       cached_M = t.M; have_LM = true; have_G = false; have_xi = false;
       dev::profile_mark(c, "fields_LM");
     }
@@ -715,95 +747,99 @@ trv::BispecMeasurements bispec_impl(
       have_LM = true;
     }
     const dev::Mesh& dn_LM_ref = survey ? dn_LM : dn_00;
-    const trvb_mesh N_LM_ref = survey ? N_LM.view() : N_00;
+    const trvb_mesh N_LM_ref = (survey && share.any_shot) ? N_LM.view() : N_00;
 
-    // ---- raw bispectrum --------------------------------------------------
-    // Real arithmetic throughout when G and both shell fields are real.
-    const bool real_path = dn_LM_ref.layout() == TRVB_HALF
-      && shell_is_real(dn_00, params.ell1, t.m1) && shell_is_real(dn_00, params.ell2, t.m2);
-    const int layout = real_path ? TRVB_REAL : TRVB_COMPLEX;
-    if (!(have_G && G_M == t.M && G.layout() == layout)) {
-      // G_LM(x) = IFFT[delta n_LM(k) / W(k)] / V (S/threept.cpp:452-459).
-      G = dev::Mesh(eng.shared(), sub, layout);
-      dev::check(trvb_shell_ifft(c, sub, dn_LM_ref.view(), 0, 0, -1., -1., 1. / eng.vol(),
-                                 G.view()), "trvb_shell_ifft (G)");
-      trvs::count_ifft += 1;
-      G_M = t.M; have_G = true;
-      dev::profile_mark(c, "G_field");
+    if (share.any_pairs) {
+      // ---- raw bispectrum --------------------------------------------------
+      // Real arithmetic throughout when G and both shell fields are real.
+      const bool real_path = dn_LM_ref.layout() == TRVB_HALF
+        && shell_is_real(dn_00, params.ell1, t.m1) && shell_is_real(dn_00, params.ell2, t.m2);
+      const int layout = real_path ? TRVB_REAL : TRVB_COMPLEX;
+      if (!(have_G && G_M == t.M && G.layout() == layout)) {
+        // G_LM(x) = IFFT[delta n_LM(k) / W(k)] / V (S/threept.cpp:452-459).
+        G = dev::Mesh(eng.shared(), sub, layout);
+        dev::check(trvb_shell_ifft(c, sub, dn_LM_ref.view(), 0, 0, -1., -1., 1. / eng.vol(),
+                                   G.view()), "trvb_shell_ifft (G)");
+        trvs::count_ifft += 1;
+        G_M = t.M; have_G = true;
+        dev::profile_mark(c, "G_field");
+      }
+      const bool same_fields = (params.ell1 == params.ell2 && t.m1 == t.m2);
+      std::vector<cdouble> bk_comp;
+      reduce_pairs(
+        eng, sub, dv, active, same_fields, G.view(),
+        [&](const std::vector<int>& bins) { return shell_slab(params.ell1, t.m1, bins, layout); },
+        [&](const std::vector<int>& bins) { return shell_slab(params.ell2, t.m2, bins, layout); },
+        bk_comp);
+      for (int i = 0; i < dv.dim; i++) {
+        if (!active[i]) continue;
+        bk_dv[i] += t.coupling * vol_cell_sub * (
+          bk_comp[i] + t.factor_mirror * std::conj(bk_comp[i]));
+      }
+      dev::profile_mark(c, "shells_and_pairs");
     }
-    const bool same_fields = (params.ell1 == params.ell2 && t.m1 == t.m2);
-    std::vector<cdouble> bk_comp;
-    reduce_pairs(
-      eng, sub, dv, active, same_fields, G.view(),
-      [&](const std::vector<int>& bins) { return shell_slab(params.ell1, t.m1, bins, layout); },
-      [&](const std::vector<int>& bins) { return shell_slab(params.ell2, t.m2, bins, layout); },
-      bk_comp);
-    for (int i = 0; i < dv.dim; i++) {
-      if (!active[i]) continue;
-      bk_dv[i] += t.coupling * vol_cell_sub * (
-        bk_comp[i] + t.factor_mirror * std::conj(bk_comp[i]));
-    }
-    dev::profile_mark(c, "shells_and_pairs");
 
-    // ---- shot noise ------------------------------------------------------
-    if (params.ell1 == 0 && params.ell2 == 0) {   // S|{i = j = k}
-      const cdouble S_ijk = t.coupling * Sbar_LM;
-      for (int i = 0; i < dv.dim; i++) if (active[i]) sn_dv[i] += S_ijk;
-    }
-    // The binned statistics depend on (ell, m) only: B_000-like cases reuse
-    // one evaluation for both S|{i != j = k} and S|{j != i = k}.
-    std::vector<double> pk, sn;
-    int binned_ell = -1, binned_m = 0;
-    auto binned_term = [&](int ell, int m, bool by_row) {
-      if (!(binned_ell == ell && binned_m == m)) {
-        std::vector<long long> nm(nb);
-        std::vector<double> kk(nb);
-        pk.assign(2 * nb, 0.); sn.assign(2 * nb, 0.);
+    if (share.any_shot) {
+      // ---- shot noise ------------------------------------------------------
+      if (params.ell1 == 0 && params.ell2 == 0) {   // S|{i = j = k}
+        const cdouble S_ijk = t.coupling * Sbar_LM;
+        for (int i = 0; i < dv.dim; i++) if (shot_active[i]) sn_dv[i] += S_ijk;
+      }
+      // The binned statistics depend on (ell, m) only: B_000-like cases reuse
+      // one evaluation for both S|{i != j = k} and S|{j != i = k}.
+      std::vector<double> pk, sn;
+      int binned_ell = -1, binned_m = 0;
+      auto binned_term = [&](int ell, int m, bool by_row) {
+        if (!(binned_ell == ell && binned_m == m)) {
+          std::vector<long long> nm(nb);
+          std::vector<double> kk(nb);
+          pk.assign(2 * nb, 0.); sn.assign(2 * nb, 0.);
+          const double S[2] = {Sbar_LM.real(), Sbar_LM.imag()};
+          dev::check(trvb_twopt_fourier(c, dn_00.view(), N_LM_ref, S, ell, m, /*interlaced=*/0,
+                                        kbinning.bin_edges.data(), kbinning.bin_centres.data(),
+                                        nb, nm.data(), kk.data(), pk.data(), sn.data()),
+                     "trvb_twopt_fourier");
+          binned_ell = ell; binned_m = m;
+        }
+        for (int i = 0; i < dv.dim; i++) {
+          if (!shot_active[i]) continue;
+          const int b = by_row ? dv.row[i] : dv.col[i];
+          const cdouble S_b = t.coupling * (cdouble(pk[2*b], pk[2*b+1]) - cdouble(sn[2*b], sn[2*b+1]));
+          sn_dv[i] += S_b + t.factor_mirror * std::conj(S_b);
+        }
+      };
+      if (params.ell2 == 0) binned_term(params.ell1, t.m1, true);    // S|{i != j = k}
+      if (params.ell1 == 0) binned_term(params.ell2, t.m2, false);   // S|{j != i = k}
+      dev::profile_mark(c, "shot_binned");
+
+      // S|{i = j != k}: one xi mesh, all pairs in one pass.
+      if (!have_xi) {
         const double S[2] = {Sbar_LM.real(), Sbar_LM.imag()};
-        dev::check(trvb_twopt_fourier(c, dn_00.view(), N_LM_ref, S, ell, m, /*interlaced=*/0,
-                                      kbinning.bin_edges.data(), kbinning.bin_centres.data(),
-                                      nb, nm.data(), kk.data(), pk.data(), sn.data()),
-                   "trvb_twopt_fourier");
-        binned_ell = ell; binned_m = m;
+        // Spectra of two real fields and a real amplitude: xi(x) is real.
+        const bool real_xi = dn_LM_ref.layout() == TRVB_HALF && N_00.layout == TRVB_HALF
+          && S[1] == 0.;
+        xi = dev::Mesh(eng.shared(), c, real_xi ? TRVB_REAL : TRVB_COMPLEX);
+        dev::check(trvb_shot_xi(c, dn_LM_ref.view(), N_00, S, /*interlaced=*/0, xi.view()), "trvb_shot_xi");
+        trvs::count_ifft += 1;
+        have_xi = true;
+        dev::profile_mark(c, "shot_xi");
       }
-      for (int i = 0; i < dv.dim; i++) {
-        if (!active[i]) continue;
-        const int b = by_row ? dv.row[i] : dv.col[i];
-        const cdouble S_b = t.coupling * (cdouble(pk[2*b], pk[2*b+1]) - cdouble(sn[2*b], sn[2*b+1]));
-        sn_dv[i] += S_b + t.factor_mirror * std::conj(S_b);
-      }
-    };
-    if (params.ell2 == 0) binned_term(params.ell1, t.m1, true);    // S|{i != j = k}
-    if (params.ell1 == 0) binned_term(params.ell2, t.m2, false);   // S|{j != i = k}
-    dev::profile_mark(c, "shot_binned");
-
-    // S|{i = j != k}: one xi mesh, all pairs in one pass.
-    if (!have_xi) {
-      const double S[2] = {Sbar_LM.real(), Sbar_LM.imag()};
-      // Spectra of two real fields and a real amplitude: xi(x) is real.
-      const bool real_xi = dn_LM_ref.layout() == TRVB_HALF && N_00.layout == TRVB_HALF
-        && S[1] == 0.;
-      xi = dev::Mesh(eng.shared(), c, real_xi ? TRVB_REAL : TRVB_COMPLEX);
-      dev::check(trvb_shot_xi(c, dn_LM_ref.view(), N_00, S, /*interlaced=*/0, xi.view()), "trvb_shot_xi");
-      trvs::count_ifft += 1;
-      have_xi = true;
-      dev::profile_mark(c, "shot_xi");
-    }
-    {
-      std::vector<double> ka, kb; std::vector<int> where;
-      for (int i = 0; i < dv.dim; i++) {
-        if (!active[i]) continue;
-        ka.push_back(k1eff[i]); kb.push_back(k2eff[i]); where.push_back(i);
-      }
-      if (!where.empty()) {
-        std::vector<double> S(2 * where.size());
-        dev::check(trvb_shot_bispec_reduce(c, xi.view(), params.ell1, t.m1, params.ell2, t.m2,
-                                           ka.data(), kb.data(), (int)where.size(), S.data()),
-                   "trvb_shot_bispec_reduce");
-        for (size_t p = 0; p < where.size(); p++) {
-          const cdouble S_ij_k = t.coupling * cdouble(S[2*p], S[2*p+1]);
-          sn_dv[where[p]] += factor_phase * (
-            S_ij_k + t.factor_mirror_w3j * std::conj(S_ij_k));
+      {
+        std::vector<double> ka, kb; std::vector<int> where;
+        for (int i = 0; i < dv.dim; i++) {
+          if (!shot_active[i]) continue;
+          ka.push_back(k1eff[i]); kb.push_back(k2eff[i]); where.push_back(i);
+        }
+        if (!where.empty()) {
+          std::vector<double> S(2 * where.size());
+          dev::check(trvb_shot_bispec_reduce(c, xi.view(), params.ell1, t.m1, params.ell2, t.m2,
+                                             ka.data(), kb.data(), (int)where.size(), S.data()),
+                     "trvb_shot_bispec_reduce");
+          for (size_t p = 0; p < where.size(); p++) {
+            const cdouble S_ij_k = t.coupling * cdouble(S[2*p], S[2*p+1]);
+            sn_dv[where[p]] += factor_phase * (
+              S_ij_k + t.factor_mirror_w3j * std::conj(S_ij_k));
+          }
         }
       }
     }
