@@ -185,6 +185,13 @@ int trvb_compensate(trvb_ctx* ctx, trvb_mesh kmesh);
  * is cached in and owned by the parent (repeated calls with the same extents
  * return the same handle, trvb_ctx_destroy on it is a no-op). */
 int trvb_subgrid_create(trvb_ctx* parent, trvb_ctx** sub, const int nsub[3]);
+/* With TRV_OVERLAP=1 a sub-grid context enqueues on its own stream.  trvb_ctx_fork makes
+ * that stream wait for everything enqueued so far on the parent's (the Fourier meshes
+ * the sub-grid kernels read); trvb_ctx_join makes the parent's stream wait for the
+ * sub-grid's.  Between the two, work on `sub` and work on `parent` may run concurrently.
+ * No-ops when both share a stream (the default). */
+int trvb_ctx_fork(trvb_ctx* parent, trvb_ctx* sub);
+int trvb_ctx_join(trvb_ctx* parent, trvb_ctx* sub);
 
 /* Number of modes and sum of |k| per shell [edges[b], edges[b+1]), all bins
  * in one pass (the k_eff / nmodes side of S/field.cpp:1815-1847).  `fine`

@@ -578,3 +578,33 @@ def test_subgrid_equals_full_grid_at_production_shape(core, monkeypatch):
     monkeypatch.setenv("TRV_NO_SUBGRID", "1")
     b = core.threept("bispec", "sim", **kw)
     _assert_close(a, b, rtol=1.e-10)
+
+
+def test_pair_branch_on_its_own_stream(core, monkeypatch):
+    """TRV_OVERLAP=1: the sub-grid context gets its own high-priority stream and the
+    shot-noise xi(x) is enqueued before the pair branch (trvb_ctx_fork / trvb_ctx_join);
+    box and survey results must not change."""
+    import ctypes as C
+    from triumvirate_b200 import _lib, catalogue as tcat
+    gen = np.random.default_rng(48)
+    L, ng = 1000., 160
+    pos = gen.uniform(0., L, size=(3, 100000))
+    kw = dict(boxsize=L, ngrid=ng, assignment="pcs", degrees=(0, 0, 0), form="full",
+              bin_range=(0.005, 0.085), num_bins=8, norm_factor=1., pos_d=pos, deterministic=True)
+    pd_, pr_, nzd, nzr, wsd, wsr, wcd, wcr = _survey_inputs(49, 3000, 12000, L)
+    pd_c, pr_c = tcat.centre(pd_, pr_, L)
+    ks = dict(boxsize=L, ngrid=ng, assignment="tsc", degrees=(2, 0, 2), form="diag",
+              bin_range=(0.005, 0.065), num_bins=6, norm_factor=1., pos_d=pd_c, nz_d=nzd, ws_d=wsd,
+              wc_d=wcd, los_d=tcat.compute_los(pd_), pos_r=pr_c, nz_r=nzr, ws_r=wsr, wc_r=wcr,
+              los_r=tcat.compute_los(pr_), deterministic=True)
+    a_box, a_sur = core.threept("bispec", "sim", **kw), core.threept("bispec", "survey", **ks)
+    _lib.trv().trv_release_contexts()          # the stream is chosen when the context is built
+    monkeypatch.setenv("TRV_OVERLAP", "1")
+    try:
+        for _ in range(3):                      # repeated: a race would not be deterministic
+            b_box, b_sur = core.threept("bispec", "sim", **kw), core.threept("bispec", "survey", **ks)
+            _assert_close(b_box, a_box, rtol=1.e-12)
+            _assert_close(b_sur, a_sur, rtol=1.e-12)
+    finally:
+        monkeypatch.delenv("TRV_OVERLAP")
+        _lib.trv().trv_release_contexts()

@@ -84,6 +84,8 @@ struct SjlTable {
 struct trvb_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  bool own_stream = false;          // sub-grid context with a stream of its own
+  cudaEvent_t fork_event = nullptr; // orders that stream against the parent's
   GridDesc g;
   trvb_ctx* parent = nullptr;       // non-null for a sub-grid context
   // Sub-grid contexts handed out by trvb_subgrid_create, keyed by extents;

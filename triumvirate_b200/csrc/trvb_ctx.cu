@@ -251,7 +251,25 @@ extern "C" int trvb_subgrid_create(trvb_ctx* parent, trvb_ctx** out,
   ctx->device = parent->device;
   ctx->parent = parent;
   fill_grid(ctx->g, nsub, parent->g.L, parent->g.order);
-  ctx->stream = parent->stream;   // shares the parent's stream
+  // TRV_OVERLAP=1 gives the sub-grid its own (highest-priority) stream so that the pair
+  // branch can run beside the shot-noise branch of the parent grid (trvb_ctx_fork /
+  // trvb_ctx_join order the two).  Measured on B200 it gains nothing on C2 or C5 (7.61 vs
+  // 7.57 ms; both branches are bandwidth-bound and the timeline has no gaps to fill), so
+  // by default everything stays on the parent's stream.
+  const char* want_overlap = getenv("TRV_OVERLAP");
+  const bool no_overlap_flag = !(want_overlap != nullptr && want_overlap[0] == '1');
+  if (no_overlap_flag) {
+    ctx->stream = parent->stream;
+  } else {
+    // Highest priority: the block scheduler hands free SM slots to the sub-grid's small
+    // kernels first, so they interleave with the parent grid's long bandwidth-bound
+    // kernels instead of queueing behind their thousands of blocks.
+    int prio_lo = 0, prio_hi = 0;
+    TRVB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    TRVB_CUDA(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi));
+    TRVB_CUDA(cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
+    ctx->own_stream = true;
+  }
   ctx->num_sms = parent->num_sms;
   parent->subgrids[key] = ctx;
   *out = ctx;
@@ -285,11 +303,28 @@ static void destroy_ctx_now(trvb_ctx* ctx) {
     if (kv.second.d_c) cudaFree(kv.second.d_c);
   }
   if (ctx->d_scratch) trvb_arena_free(ctx->device, ctx->stream, ctx->d_scratch);
-  if (!ctx->parent && ctx->stream) {
+  if ((!ctx->parent || ctx->own_stream) && ctx->stream) {
     trvb_arena_retire_stream(ctx->device, ctx->stream);
     cudaStreamDestroy(ctx->stream);
+    if (ctx->own_stream) cudaEventDestroy(ctx->fork_event);
   }
   delete ctx;
+}
+
+extern "C" int trvb_ctx_fork(trvb_ctx* parent, trvb_ctx* sub) {
+  TRVB_REQUIRE(parent && sub, "trvb_ctx_fork: null context");
+  if (sub->stream == parent->stream) return 0;
+  TRVB_CUDA(cudaEventRecord(sub->fork_event, parent->stream));
+  TRVB_CUDA(cudaStreamWaitEvent(sub->stream, sub->fork_event, 0));
+  return 0;
+}
+
+extern "C" int trvb_ctx_join(trvb_ctx* parent, trvb_ctx* sub) {
+  TRVB_REQUIRE(parent && sub, "trvb_ctx_join: null context");
+  if (sub->stream == parent->stream) return 0;
+  TRVB_CUDA(cudaEventRecord(sub->fork_event, sub->stream));
+  TRVB_CUDA(cudaStreamWaitEvent(parent->stream, sub->fork_event, 0));
+  return 0;
 }
 
 extern "C" int trvb_ctx_set_deterministic(trvb_ctx* ctx, int on) {

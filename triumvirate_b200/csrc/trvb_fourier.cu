@@ -428,18 +428,18 @@ extern "C" int trvb_shell_ifft(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh src, int 
   const GridDesc& gs = sub->g;
   if (dst.layout == TRVB_REAL) {
     trvb_mesh half; half.layout = TRVB_HALF; half.k0_add = 0.; half.data = nullptr;
-    TRVB_CUDA(trvb_dev_alloc_raw(ctx, &half.data, trvb_mesh_bytes(sub, TRVB_HALF)));
+    TRVB_CUDA(trvb_dev_alloc_raw(sub, &half.data, trvb_mesh_bytes(sub, TRVB_HALF)));
     const RowLaunch rl = row_launch(ctx->num_sms, gs.n[0], gs.n[1], gs.nh);
-    k_shell_spectrum<<<rl.grid, rl.block, 0, ctx->stream>>>(
+    k_shell_spectrum<<<rl.grid, rl.block, 0, sub->stream>>>(
       kview_of(ctx, src), ctx->g, gs, tables_of(ctx), ell, m, klo, khi, use_shell, amp,
       gs.nh, (double2*)half.data);
     TRVB_LAUNCH_CHECK();
     int st = trvb_fft_inverse(sub, half, dst);
-    trvb_dev_free_raw(ctx, half.data);
+    trvb_dev_free_raw(sub, half.data);
     return st;
   }
   const RowLaunch rl = row_launch(ctx->num_sms, gs.n[0], gs.n[1], gs.n[2]);
-  k_shell_spectrum<<<rl.grid, rl.block, 0, ctx->stream>>>(
+  k_shell_spectrum<<<rl.grid, rl.block, 0, sub->stream>>>(
     kview_of(ctx, src), ctx->g, gs, tables_of(ctx), ell, m, klo, khi, use_shell, amp,
     gs.n[2], (double2*)dst.data);
   TRVB_LAUNCH_CHECK();
@@ -471,7 +471,7 @@ extern "C" int trvb_shell_ifft_batch(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh src
   int maxb = (int)std::max<size_t>(1, ((size_t)6 << 30) / spec_bin_bytes);
   maxb = std::min(maxb, nbins);
   void* spec_tmp = nullptr;
-  if (real_out) TRVB_CUDA(trvb_dev_alloc_raw(ctx, &spec_tmp, spec_bin_bytes * maxb));
+  if (real_out) TRVB_CUDA(trvb_dev_alloc_raw(sub, &spec_tmp, spec_bin_bytes * maxb));
   // Low-|k| cube that holds every shell; clipped to what the sub grid represents.
   double kmax = 0.;
   for (int q = 0; q < nbins; q++) kmax = std::max(kmax, khi[q]);
@@ -488,24 +488,24 @@ extern "C" int trvb_shell_ifft_batch(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh src
     lo[a] = lo_a; cnt[a] = hi_a - lo_a + 1;
   }
   double* d_par = nullptr;
-  TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&d_par, sizeof(double) * 3 * (size_t)nbins));
+  TRVB_CUDA(trvb_dev_alloc_raw(sub, (void**)&d_par, sizeof(double) * 3 * (size_t)nbins));
   std::vector<double> h_par(3 * (size_t)nbins);
   for (int q = 0; q < nbins; q++) {
     h_par[q] = klo[q]; h_par[nbins + q] = khi[q]; h_par[2 * nbins + q] = amp[q];
   }
   // Pageable source: the copy is staged before cudaMemcpyAsync returns.
   TRVB_CUDA(cudaMemcpyAsync(d_par, h_par.data(), sizeof(double) * h_par.size(),
-                            cudaMemcpyHostToDevice, ctx->stream));
+                            cudaMemcpyHostToDevice, sub->stream));
   const RowLaunch rl = row_launch(ctx->num_sms, cnt[0], cnt[1], cnt[2]);
   int st = 0;
   for (int q0 = 0; q0 < nbins && st == 0; q0 += maxb) {
     const int nq = std::min(maxb, nbins - q0);
     void* out = static_cast<char*>(dst) + dst_stride * (size_t)q0;
     void* spec = real_out ? spec_tmp : out;
-    TRVB_CUDA(cudaMemsetAsync(spec, 0, spec_bin_bytes * nq, ctx->stream));
+    TRVB_CUDA(cudaMemsetAsync(spec, 0, spec_bin_bytes * nq, sub->stream));
     ShellBatch sb; sb.klo = d_par + q0; sb.khi = d_par + nbins + q0; sb.amp = d_par + 2 * nbins + q0;
     sb.nbins = nq;
-    k_shell_scatter<<<rl.grid, rl.block, 0, ctx->stream>>>(
+    k_shell_scatter<<<rl.grid, rl.block, 0, sub->stream>>>(
       kview_of(ctx, src), gp, gs, tables_of(ctx), ell, m, lo[0], lo[1], lo[2], cnt[0], cnt[1],
       cnt[2], sb, n2s, bin_stride, (double2*)spec);
     TRVB_LAUNCH_CHECK();
@@ -520,8 +520,8 @@ extern "C" int trvb_shell_ifft_batch(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh src
     }
     g_trvb_fft_execs++;
   }
-  trvb_dev_free_raw(ctx, d_par);
-  if (real_out) trvb_dev_free_raw(ctx, spec_tmp);
+  trvb_dev_free_raw(sub, d_par);
+  if (real_out) trvb_dev_free_raw(sub, spec_tmp);
   return st;
 }
 

@@ -34,6 +34,7 @@ void check(int status, const char* what);
 /// Optional phase timer (off by default): when enabled, mark() synchronises
 /// the context stream and charges the time since the previous mark to `phase`.
 void profile_enable(bool on);
+bool profile_enabled();
 void profile_reset();
 void profile_mark(trvb_ctx* ctx, const char* phase);
 std::string profile_report();

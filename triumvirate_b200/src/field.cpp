@@ -124,6 +124,7 @@ std::vector<std::pair<std::string, double> > g_prof;
 }  // namespace
 
 void profile_enable(bool on) { g_prof_on = on; }
+bool profile_enabled() { return g_prof_on; }
 
 void profile_reset() {
   g_prof.clear();

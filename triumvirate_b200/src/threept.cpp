@@ -731,6 +731,11 @@ trv::BispecMeasurements bispec_impl(
     return src.layout() == TRVB_HALF && m == 0 && ell % 2 == 0;
   };
 
+  // With TRV_OVERLAP=1 the pair branch lives on the sub-grid's own stream: xi(x)
+  // (spectrum + full-grid inverse FFT, no host synchronisation) is then enqueued BEFORE
+  // the pair branch and may run beside it.  On one stream the order is immaterial.
+  const bool overlap = coarse && share.any_pairs && share.any_shot && !dev::profile_enabled();
+
   for (const Term& t : terms) {
     // ---- fields that depend on (L, M) only -----------------------------
     if (survey && !(have_LM && cached_M == t.M)) {
@@ -748,6 +753,23 @@ trv::BispecMeasurements bispec_impl(
     }
     const dev::Mesh& dn_LM_ref = survey ? dn_LM : dn_00;
     const trvb_mesh N_LM_ref = (survey && share.any_shot) ? N_LM.view() : N_00;
+
+    // S|{i = j != k}: one xi mesh per (L, M), all pairs in one pass later.
+    auto ensure_xi = [&]() {
+      if (have_xi) return;
+      const double S[2] = {Sbar_LM.real(), Sbar_LM.imag()};
+      // Spectra of two real fields and a real amplitude: xi(x) is real.
+      const bool real_xi = dn_LM_ref.layout() == TRVB_HALF && N_00.layout == TRVB_HALF
+        && S[1] == 0.;
+      xi = dev::Mesh(eng.shared(), c, real_xi ? TRVB_REAL : TRVB_COMPLEX);
+      dev::check(trvb_shot_xi(c, dn_LM_ref.view(), N_00, S, /*interlaced=*/0, xi.view()), "trvb_shot_xi");
+      trvs::count_ifft += 1;
+      have_xi = true;
+      dev::profile_mark(c, "shot_xi");
+    };
+    // The sub-grid stream may start once the Fourier meshes above are complete.
+    dev::check(trvb_ctx_fork(c, sub), "trvb_ctx_fork");
+    if (overlap) ensure_xi();
 
     if (share.any_pairs) {
       // ---- raw bispectrum --------------------------------------------------
@@ -812,18 +834,7 @@ trv::BispecMeasurements bispec_impl(
       if (params.ell1 == 0) binned_term(params.ell2, t.m2, false);   // S|{j != i = k}
       dev::profile_mark(c, "shot_binned");
 
-      // S|{i = j != k}: one xi mesh, all pairs in one pass.
-      if (!have_xi) {
-        const double S[2] = {Sbar_LM.real(), Sbar_LM.imag()};
-        // Spectra of two real fields and a real amplitude: xi(x) is real.
-        const bool real_xi = dn_LM_ref.layout() == TRVB_HALF && N_00.layout == TRVB_HALF
-          && S[1] == 0.;
-        xi = dev::Mesh(eng.shared(), c, real_xi ? TRVB_REAL : TRVB_COMPLEX);
-        dev::check(trvb_shot_xi(c, dn_LM_ref.view(), N_00, S, /*interlaced=*/0, xi.view()), "trvb_shot_xi");
-        trvs::count_ifft += 1;
-        have_xi = true;
-        dev::profile_mark(c, "shot_xi");
-      }
+      ensure_xi();
       {
         std::vector<double> ka, kb; std::vector<int> where;
         for (int i = 0; i < dv.dim; i++) {
@@ -844,6 +855,7 @@ trv::BispecMeasurements bispec_impl(
       }
     }
     dev::profile_mark(c, "shot_reduce");
+    dev::check(trvb_ctx_join(c, sub), "trvb_ctx_join");
     if (trvs::currTask == 0) {
       trvs::logger.stat("Bispectrum term computed at orders (m1, m2, M) = +/-(%d, %d, %d).",
                         t.m1, t.m2, t.M);
