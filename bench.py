@@ -46,8 +46,8 @@ sys.path.insert(0, str(ROOT))
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the assignment
 # kernel on the C2 workload, from the committed `ncu --set full` capture
 # (the zero-fill memset adds one mesh write, 8 n^3 bytes, on top).
-NCU_TRAFFIC = {"k_assign_coop<4,false>": 1.345986e9 + 1.447989e9}
-NCU_TRAFFIC_SOURCE = "profiles/r01b_ncu_full_k_assign_coop.csv (kernel only; + 1.07e9 B memset)"
+NCU_TRAFFIC = {"k_assign_coop<4,false>": 1.497749e9 + 1.132951e9}
+NCU_TRAFFIC_SOURCE = "profiles/r01d_ncu_full_k_assign_coop.csv (kernel only; + 1.07e9 B memset)"
 
 WORKLOADS = {
     "C2": dict(
