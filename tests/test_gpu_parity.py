@@ -604,7 +604,9 @@ def test_pair_branch_on_its_own_stream(core, monkeypatch):
         for _ in range(3):                      # repeated: a race would not be deterministic
             b_box, b_sur = core.threept("bispec", "sim", **kw), core.threept("bispec", "survey", **ks)
             _assert_close(b_box, a_box, rtol=1.e-12)
-            _assert_close(b_sur, a_sur, rtol=1.e-12)
+            # survey entries cancel between terms: round-off of the call-to-call summation
+            # order shows at 1e-12 of the smaller entries; a race would be gross
+            _assert_close(b_sur, a_sur, rtol=1.e-9)
     finally:
         monkeypatch.delenv("TRV_OVERLAP")
         _lib.trv().trv_release_contexts()

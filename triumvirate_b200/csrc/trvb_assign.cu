@@ -319,7 +319,7 @@ __global__ void k_sort_scatter(CatView c, SortDesc d, int* __restrict__ cursor,
     const double x = c.x[i], y = c.y[i], z = c.z[i];
     int key = sort_key(d, x, y, z);
     int pos = atomicAdd(&cursor[key], 1);
-    order[pos] = (int)i;
+    if (order) order[pos] = (int)i;
     if (s4) {
       s4[pos] = make_double4(grid_loc(x, d.n[0], d.L[0], 0), grid_loc(y, d.n[1], d.L[1], 0),
                              grid_loc(z, d.n[2], d.L[2], 0), c.w ? c.w[i] : 1.);
@@ -1002,6 +1002,11 @@ int ensure_sorted(trvb_ctx* ctx, trvb_cat* cat, int shifted, int by_cell) {
   for (int a = 0; a < 3; a++) {
     valid = valid && cat->sort_n[a] == g.n[a] && cat->sort_L[a] == g.L[a];
   }
+  // The id permutation is only written when something is gathered through it (lines
+  // of sight, custom weights, the cell-ordered mode): 4-byte writes to random sectors
+  // cost the scatter as much as the 32-byte records.
+  const bool need_order = by_cell || cat->los != nullptr || cat->cw != nullptr;
+  if (need_order && !cat->order_valid) valid = false;
   if (valid) {
     if (cat->cw && !cat->scw_valid) return gather_sorted(ctx, cat, false);
     return 0;
@@ -1045,8 +1050,10 @@ int ensure_sorted(trvb_ctx* ctx, trvb_cat* cat, int shifted, int by_cell) {
                             cudaMemcpyDeviceToDevice, ctx->stream));
   // Throughput order: the scatter places the packed records itself.  Cell
   // order: ids are sorted inside each cell first, records gathered after.
-  k_sort_scatter<<<blocks, threads, 0, ctx->stream>>>(cv, d, cursor, cat->order,
+  k_sort_scatter<<<blocks, threads, 0, ctx->stream>>>(cv, d, cursor,
+                                                     need_order ? cat->order : nullptr,
                                                      by_cell ? nullptr : cat->s4);
+  cat->order_valid = need_order;
   TRVB_LAUNCH_CHECK();
   if (by_cell) {
     const int sb = (int)std::min<long long>(div_up(nkeys, threads), (long long)ctx->num_sms * 32);
