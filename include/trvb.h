@@ -117,6 +117,16 @@ int trvb_cat_create(trvb_ctx* ctx, trvb_cat** cat, long long n,
  * {x, y, z, nz, ws, wc, w} (I/particles.hpp:63-69). */
 int trvb_cat_create_aos(trvb_ctx* ctx, trvb_cat** cat, long long n,
                         const double* pdata, const double* los);
+/* Periodic-box fast path for HOST coordinate arrays (pinned memory preferred): the
+ * catalogue is uploaded in chunks on a copy stream and every chunk is tile-sorted and
+ * spread onto `mesh` (zero-filled here; unit weights times `scale`, no density units)
+ * while the next chunk is on the wire, so the counting sort and the assignment hide
+ * behind the PCIe transfer.  Returns the catalogue (chunk-wise sorted: valid for the
+ * throughput assignment of later calls).  Equivalent to trvb_cat_create followed by
+ * trvb_assign(kind = TRVB_W_UNIT) up to summation order. */
+int trvb_cat_create_assign(trvb_ctx* ctx, trvb_cat** out, long long n,
+                           const double* x, const double* y, const double* z,
+                           double scale, trvb_mesh mesh);
 /* Attach caller-supplied complex weights (n interleaved (re, im) pairs, host
  * memory) for TRVB_W_CUSTOM. */
 int trvb_cat_set_custom_weights(trvb_ctx* ctx, trvb_cat* cat,

@@ -610,3 +610,31 @@ def test_pair_branch_on_its_own_stream(core, monkeypatch):
     finally:
         monkeypatch.delenv("TRV_OVERLAP")
         _lib.trv().trv_release_contexts()
+
+
+@pytest.mark.parametrize("stat,assignment,n", [("bispec", "pcs", 300000), ("bispec", "cic", 50000),
+                                               ("3pcf", "tsc", 2500000)])
+def test_box_arrays_streamed_upload(core, stat, assignment, n):
+    """`trv_threept_box_arrays` from HOST arrays streams the upload with the first
+    assignment (trvb_cat_create_assign: chunked copies, per-chunk sort + spread); from
+    DEVICE arrays and through a ParticleCatalogue it sorts globally.  Same result up to
+    summation order; several chunks at n = 2.5e6."""
+    import torch
+    gen = np.random.default_rng(52)
+    L, ng = 800., 64
+    pos = gen.uniform(0., L, size=(3, n))
+    rng = (0.02, 0.2) if stat == "bispec" else (30., 230.)
+    kw = dict(boxsize=L, ngrid=ng, assignment=assignment, degrees=(0, 0, 0), form="diag",
+              bin_range=rng, num_bins=5, norm_factor=1.)
+    ref = core.threept(stat, "sim", pos_d=pos, **kw)
+    host = torch.from_numpy(pos).pin_memory()
+    a = core.threept_box_arrays(stat, n, host[0].data_ptr(), host[1].data_ptr(),
+                                host[2].data_ptr(), False, **kw)
+    dev = host.to("cuda:0"); torch.cuda.synchronize()
+    b = core.threept_box_arrays(stat, n, dev[0].data_ptr(), dev[1].data_ptr(),
+                                dev[2].data_ptr(), True, **kw)
+    pageable = np.ascontiguousarray(pos)            # not pinned: still correct
+    c = core.threept_box_arrays(stat, n, pageable[0].ctypes.data, pageable[1].ctypes.data,
+                                pageable[2].ctypes.data, False, **kw)
+    for out in (a, b, c):
+        _assert_close(out, ref, rtol=1.e-10)

@@ -28,6 +28,7 @@
 #include "trvb_common.cuh"
 
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <thread>
 
@@ -989,6 +990,31 @@ int gather_sorted(trvb_ctx* ctx, trvb_cat* cat, bool with_records) {
   return 0;
 }
 
+// Counting sort of the particles of `cv` by sort key, enqueued on the context's
+// stream: histogram, exclusive scan (offsets, nkeys + 1 entries), scatter of the ids
+// (`order`, may be null) and of the packed records (`s4`, may be null).
+int enqueue_counting_sort(trvb_ctx* ctx, const CatView& cv, const SortDesc& d, long long nkeys,
+                          int* offsets, int* cursor, int* chunk_sums, int* order, double4* s4) {
+  TRVB_CUDA(cudaMemsetAsync(offsets, 0, sizeof(int) * (size_t)(nkeys + 1), ctx->stream));
+  const int threads = 256;
+  const int blocks = (int)std::min<long long>(div_up(cv.n, threads), (long long)ctx->num_sms * 16);
+  k_sort_count<<<blocks, threads, 0, ctx->stream>>>(cv, d, offsets);
+  TRVB_LAUNCH_CHECK();
+  const long long nscan = nkeys + 1;
+  const int nchunks = div_up(nscan, SCAN_CHUNK);
+  k_scan_chunk_sums<<<nchunks, SCAN_THREADS, 0, ctx->stream>>>(offsets, nscan, chunk_sums);
+  TRVB_LAUNCH_CHECK();
+  k_scan_chunk_offsets<<<1, 1024, 0, ctx->stream>>>(chunk_sums, nchunks);
+  TRVB_LAUNCH_CHECK();
+  k_scan_apply<<<nchunks, SCAN_THREADS, 0, ctx->stream>>>(offsets, nscan, chunk_sums);
+  TRVB_LAUNCH_CHECK();
+  TRVB_CUDA(cudaMemcpyAsync(cursor, offsets, sizeof(int) * (size_t)nkeys,
+                            cudaMemcpyDeviceToDevice, ctx->stream));
+  k_sort_scatter<<<blocks, threads, 0, ctx->stream>>>(cv, d, cursor, order, s4);
+  TRVB_LAUNCH_CHECK();
+  return 0;
+}
+
 // by_cell == 0: throughput order ((tile, column) of the UNSHIFTED home cell, plus
 // the key offsets k_assign_tile needs; for the shifted shadow mesh it only
 // provides locality).
@@ -1030,31 +1056,19 @@ int ensure_sorted(trvb_ctx* ctx, trvb_cat* cat, int shifted, int by_cell) {
   int* cursor = nullptr;    // nkeys
   TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&offsets, sizeof(int) * (size_t)(nkeys + 1)));
   TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cursor, sizeof(int) * (size_t)nkeys));
-  TRVB_CUDA(cudaMemsetAsync(offsets, 0, sizeof(int) * (size_t)(nkeys + 1), ctx->stream));
-  CatView cv = view_of(cat);
-  const int threads = 256;
-  const int blocks = (int)std::min<long long>(div_up(cat->n, threads), (long long)ctx->num_sms * 16);
-  k_sort_count<<<blocks, threads, 0, ctx->stream>>>(cv, d, offsets);
-  TRVB_LAUNCH_CHECK();
-  const long long nscan = nkeys + 1;
-  const int nchunks = div_up(nscan, SCAN_CHUNK);
+  const int nchunks = div_up(nkeys + 1, SCAN_CHUNK);
   int* chunk_sums = nullptr;
   TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&chunk_sums, sizeof(int) * (size_t)nchunks));
-  k_scan_chunk_sums<<<nchunks, SCAN_THREADS, 0, ctx->stream>>>(offsets, nscan, chunk_sums);
-  TRVB_LAUNCH_CHECK();
-  k_scan_chunk_offsets<<<1, 1024, 0, ctx->stream>>>(chunk_sums, nchunks);
-  TRVB_LAUNCH_CHECK();
-  k_scan_apply<<<nchunks, SCAN_THREADS, 0, ctx->stream>>>(offsets, nscan, chunk_sums);
-  TRVB_LAUNCH_CHECK();
-  TRVB_CUDA(cudaMemcpyAsync(cursor, offsets, sizeof(int) * (size_t)nkeys,
-                            cudaMemcpyDeviceToDevice, ctx->stream));
+  CatView cv = view_of(cat);
+  const int threads = 256;
   // Throughput order: the scatter places the packed records itself.  Cell
   // order: ids are sorted inside each cell first, records gathered after.
-  k_sort_scatter<<<blocks, threads, 0, ctx->stream>>>(cv, d, cursor,
-                                                     need_order ? cat->order : nullptr,
-                                                     by_cell ? nullptr : cat->s4);
+  { int st = enqueue_counting_sort(ctx, cv, d, nkeys, offsets, cursor, chunk_sums,
+                                   need_order ? cat->order : nullptr,
+                                   by_cell ? nullptr : cat->s4);
+    if (st) return st; }
   cat->order_valid = need_order;
-  TRVB_LAUNCH_CHECK();
+  cat->chunked = false;
   if (by_cell) {
     const int sb = (int)std::min<long long>(div_up(nkeys, threads), (long long)ctx->num_sms * 32);
     k_sort_segments<<<sb, threads, 0, ctx->stream>>>(cursor, nkeys, cat->order);
@@ -1162,6 +1176,35 @@ k_assign_gather_warp(SortedView c, const int* __restrict__ order,
   }
 }
 
+// Particle-wise scatter of a sorted view: warp-cooperative for TSC/PCS, thread per
+// particle for NGP/CIC.
+template <int ORDER>
+void launch_throughput_scatter(trvb_ctx* ctx, const SortedView& cv, int kind, const YlmCoef& yc,
+                               double s, int shifted, bool cplx_mesh, double* mesh) {
+  const GridDesc& g = ctx->g;
+  const int threads = 256;
+  if (ORDER >= 3) {
+    const long long nchunk = (cv.n + 31) / 32;
+    const int blocks = (int)std::min<long long>(div_up(nchunk, 8), (long long)ctx->num_sms * 64);
+    if (cplx_mesh) {
+      k_assign_coop<(ORDER >= 3 ? ORDER : 3), true><<<blocks, threads, 0, ctx->stream>>>(
+        cv, g, shifted, kind, yc, s, mesh);
+    } else {
+      k_assign_coop<(ORDER >= 3 ? ORDER : 3), false><<<blocks, threads, 0, ctx->stream>>>(
+        cv, g, shifted, kind, yc, s, mesh);
+    }
+  } else {
+    const int blocks = div_up(cv.n, threads);
+    if (cplx_mesh) {
+      k_assign_scatter<ORDER, true><<<blocks, threads, 0, ctx->stream>>>(
+        cv, g, shifted, kind, yc, s, mesh);
+    } else {
+      k_assign_scatter<ORDER, false><<<blocks, threads, 0, ctx->stream>>>(
+        cv, g, shifted, kind, yc, s, mesh);
+    }
+  }
+}
+
 template <int ORDER>
 int launch_assign(trvb_ctx* ctx, trvb_cat* cat, int kind, int L, int M, double scale,
                   int density_units, int accumulate, int shifted, int mode,
@@ -1172,6 +1215,11 @@ int launch_assign(trvb_ctx* ctx, trvb_cat* cat, int kind, int L, int M, double s
   // the same bits as on the device) instead of once per thread.
   const YlmCoef yc = ylm_coef(L, M);
   if (mode == 0) {
+    {
+      const char* env_tile_pre = getenv("TRV_ASSIGN_TILE");
+      // the tile kernel needs global (tile, column) offsets: re-sort a chunked order
+      if (env_tile_pre != nullptr && env_tile_pre[0] == '1' && cat->chunked) trvb_cat_invalidate_sort(cat);
+    }
     int st = ensure_sorted(ctx, cat, shifted, 0);
     if (st) return st;
     SortedView cv = sorted_view_of(cat);
@@ -1208,25 +1256,8 @@ int launch_assign(trvb_ctx* ctx, trvb_cat* cat, int kind, int L, int M, double s
         k_assign_tile<O, false><<<ntiles, TILE_WARPS * 32, tile_smem_bytes<false>(), ctx->stream>>>(
           cv, cat->cell_start, nt[1], nt[2], g, kind, yc, s, (double*)mesh.data);
       }
-    } else if (ORDER >= 3) {
-      const long long nchunk = (cat->n + 31) / 32;
-      const int blocks = (int)std::min<long long>(div_up(nchunk, 8), (long long)ctx->num_sms * 64);
-      if (cplx_mesh) {
-        k_assign_coop<(ORDER >= 3 ? ORDER : 3), true><<<blocks, threads, 0, ctx->stream>>>(
-          cv, g, shifted, kind, yc, s, (double*)mesh.data);
-      } else {
-        k_assign_coop<(ORDER >= 3 ? ORDER : 3), false><<<blocks, threads, 0, ctx->stream>>>(
-          cv, g, shifted, kind, yc, s, (double*)mesh.data);
-      }
     } else {
-      const int blocks = div_up(cat->n, threads);
-      if (cplx_mesh) {
-        k_assign_scatter<ORDER, true><<<blocks, threads, 0, ctx->stream>>>(
-          cv, g, shifted, kind, yc, s, (double*)mesh.data);
-      } else {
-        k_assign_scatter<ORDER, false><<<blocks, threads, 0, ctx->stream>>>(
-          cv, g, shifted, kind, yc, s, (double*)mesh.data);
-      }
+      launch_throughput_scatter<ORDER>(ctx, cv, kind, yc, s, shifted, cplx_mesh, (double*)mesh.data);
     }
     TRVB_LAUNCH_CHECK();
   } else {
@@ -1424,6 +1455,125 @@ extern "C" int trvb_cat_create_aos(trvb_ctx* ctx, trvb_cat** out, long long n,
   TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
   TRVB_CUDA(trvb_dev_free_raw(ctx, d_chunk[0]));
   TRVB_CUDA(trvb_dev_free_raw(ctx, d_chunk[1]));
+  *out = cat;
+  return 0;
+}
+
+// ---------------------------------------------------------------------
+// Streamed upload + assignment of a host catalogue (unit weights).
+// ---------------------------------------------------------------------
+namespace {
+
+struct UploadLane { cudaStream_t stream = nullptr; std::vector<cudaEvent_t> done; };
+std::map<int, UploadLane> g_upload_lane;   // per device; guarded by g_stage_mutex
+
+template <int ORDER>
+int streamed_assign(trvb_ctx* ctx, trvb_cat* cat, const double* hx, const double* hy,
+                    const double* hz, double scale, trvb_mesh mesh) {
+  const GridDesc& g = ctx->g;
+  const long long n = cat->n;
+  const bool cplx_mesh = mesh.layout == TRVB_COMPLEX;
+  UploadLane& lane = g_upload_lane[ctx->device];
+  if (!lane.stream) TRVB_CUDA(cudaStreamCreateWithFlags(&lane.stream, cudaStreamNonBlocking));
+  // Every chunk costs one sweep over the mesh (its REDs touch sectors all over it), so
+  // chunks are few and shrink geometrically: 1/2, 1/4, 1/8, 1/8 of the catalogue -- the
+  // work left after the last byte has arrived is an eighth of the sort + assignment.
+  std::vector<long long> bounds(1, 0);
+  {
+    const long long min_chunk = 1LL << 20;
+    long long left = n;
+    for (int level = 0; level < 3 && left > 2 * min_chunk; level++) {
+      const long long take = std::max(min_chunk, left / 2);
+      bounds.push_back(bounds.back() + take);
+      left -= take;
+    }
+    bounds.push_back(n);
+  }
+  const int nchunks = (int)bounds.size() - 1;
+  while ((int)lane.done.size() < nchunks) {
+    cudaEvent_t e; TRVB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    lane.done.push_back(e);
+  }
+  SortDesc d;
+  for (int a = 0; a < 3; a++) {
+    d.n[a] = g.n[a]; d.L[a] = g.L[a];
+    const int tile = (a == 0) ? TILE_X : (a == 1) ? TILE_Y : TILE_Z;
+    d.nk[a] = (g.n[a] + tile - 1) / tile;
+  }
+  d.shifted = 0; d.by_cell = 0;
+  const long long nkeys = (long long)d.nk[0] * d.nk[1] * d.nk[2] * KEYS_PER_TILE;
+  TRVB_REQUIRE(nkeys < 2147483647LL, "mesh too large for int sort keys");
+  { int st = alloc_sorted(ctx, cat); if (st) return st; }
+  int* offsets = nullptr; int* cursor = nullptr; int* chunk_sums = nullptr;
+  TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&offsets, sizeof(int) * (size_t)(nkeys + 1)));
+  TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cursor, sizeof(int) * (size_t)nkeys));
+  TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&chunk_sums,
+                               sizeof(int) * (size_t)div_up(nkeys + 1, SCAN_CHUNK)));
+  // The upload lane must not overtake work still queued on the compute stream that
+  // may use the freshly allocated blocks (stream-ordered arena).
+  cudaEvent_t start = lane.done[0];
+  TRVB_CUDA(cudaEventRecord(start, ctx->stream));
+  TRVB_CUDA(cudaStreamWaitEvent(lane.stream, start, 0));
+  TRVB_CUDA(cudaMemsetAsync(mesh.data, 0, trvb_mesh_bytes(ctx, mesh.layout), ctx->stream));
+  const YlmCoef yc = ylm_coef(0, 0);
+  for (int c = 0; c < nchunks; c++) {
+    const long long off = bounds[c], m = bounds[c + 1] - off;
+    const size_t mb = sizeof(double) * (size_t)m;
+    TRVB_CUDA(cudaMemcpyAsync(cat->x + off, hx + off, mb, cudaMemcpyHostToDevice, lane.stream));
+    TRVB_CUDA(cudaMemcpyAsync(cat->y + off, hy + off, mb, cudaMemcpyHostToDevice, lane.stream));
+    TRVB_CUDA(cudaMemcpyAsync(cat->z + off, hz + off, mb, cudaMemcpyHostToDevice, lane.stream));
+    TRVB_CUDA(cudaEventRecord(lane.done[c], lane.stream));
+    TRVB_CUDA(cudaStreamWaitEvent(ctx->stream, lane.done[c], 0));
+    // sort this chunk by (tile, column) and spread it while the next one is on the wire
+    CatView cv; cv.x = cat->x + off; cv.y = cat->y + off; cv.z = cat->z + off;
+    cv.w = nullptr; cv.lx = cv.ly = cv.lz = nullptr; cv.cw = nullptr; cv.n = m;
+    int st = enqueue_counting_sort(ctx, cv, d, nkeys, offsets, cursor, chunk_sums, nullptr,
+                                   cat->s4 + off);
+    if (st) return st;
+    SortedView sv; sv.p4 = cat->s4 + off; sv.lx = sv.ly = sv.lz = nullptr; sv.cw = nullptr; sv.n = m;
+    launch_throughput_scatter<ORDER>(ctx, sv, TRVB_W_UNIT, yc, scale, 0, cplx_mesh,
+                                     (double*)mesh.data);
+    TRVB_LAUNCH_CHECK();
+  }
+  TRVB_CUDA(trvb_dev_free_raw(ctx, offsets));
+  TRVB_CUDA(trvb_dev_free_raw(ctx, cursor));
+  TRVB_CUDA(trvb_dev_free_raw(ctx, chunk_sums));
+  for (int a = 0; a < 3; a++) { cat->sort_n[a] = g.n[a]; cat->sort_L[a] = g.L[a]; }
+  cat->sort_shifted = 0; cat->sort_kind = 0;
+  cat->order_valid = false; cat->chunked = true; cat->scw_valid = false;
+  // the host arrays are the caller's: every copy must have left them
+  TRVB_CUDA(cudaStreamSynchronize(lane.stream));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int trvb_cat_create_assign(trvb_ctx* ctx, trvb_cat** out, long long n,
+                                      const double* x, const double* y, const double* z,
+                                      double scale, trvb_mesh mesh) {
+  TRVB_REQUIRE(ctx && out && x && y && z && n > 0 && mesh.data,
+               "trvb_cat_create_assign: bad argument");
+  TRVB_REQUIRE(mesh.layout == TRVB_REAL || mesh.layout == TRVB_COMPLEX,
+               "trvb_cat_create_assign: configuration-space mesh required");
+  TRVB_REQUIRE(ctx->parent == nullptr, "trvb_cat_create_assign: root context only");
+  TRVB_REQUIRE(n < 2147483647LL, "catalogue too large for int indices");
+  TRVB_CUDA(cudaSetDevice(ctx->device));
+  std::lock_guard<std::mutex> lock(g_stage_mutex);
+  trvb_cat* cat = new trvb_cat();
+  cat->owner = ctx; cat->n = n;
+  const size_t nb = sizeof(double) * (size_t)n;
+  TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->x, nb));
+  TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->y, nb));
+  TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->z, nb));
+  int st = 0;
+  switch (ctx->g.order) {
+    case 1: st = streamed_assign<1>(ctx, cat, x, y, z, scale, mesh); break;
+    case 2: st = streamed_assign<2>(ctx, cat, x, y, z, scale, mesh); break;
+    case 3: st = streamed_assign<3>(ctx, cat, x, y, z, scale, mesh); break;
+    case 4: st = streamed_assign<4>(ctx, cat, x, y, z, scale, mesh); break;
+    default: st = 2;
+  }
+  if (st) { trvb_cat_destroy(cat); return st; }
   *out = cat;
   return 0;
 }

@@ -122,6 +122,7 @@ struct trvb_cat {
   // the catalogue columns gathered into that order (coalesced kernel reads).
   int* order = nullptr;        // particle ids sorted by sort key
   bool order_valid = false;    // false when the last sort did not need (and skipped) it
+  bool chunked = false;        // throughput order built chunk by chunk: no global key offsets
   double4* s4 = nullptr;       // {x, y, z, w} per particle: one 32-byte sector
   double* slos = nullptr; double* scw = nullptr;
   bool scw_valid = false;

@@ -57,6 +57,8 @@ class Catalogue {
   Catalogue(std::shared_ptr<trvb_ctx> ctx, long long n, const double* x,
             const double* y, const double* z, const double* w,
             const double* los, bool on_device);
+  /// Adopts a device catalogue built by the device layer (trvb_cat_create_assign).
+  Catalogue(std::shared_ptr<trvb_ctx> ctx, trvb_cat* adopted) : ctx_(ctx), cat_(adopted) {}
   ~Catalogue();
   Catalogue(const Catalogue&) = delete;
   Catalogue& operator=(const Catalogue&) = delete;

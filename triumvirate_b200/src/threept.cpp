@@ -288,9 +288,15 @@ class Engine {
     ctx_ = dev::acquire_context(params);
     c_ = ctx_.get();
     dev::profile_reset();
-    data_.reset(new dev::Catalogue(ctx_, n, x, y, z, nullptr, nullptr, on_device));
     ndata_ = n;
     init_common();
+    if (!on_device && !params.deterministic) {
+      // Host arrays, throughput mode: the upload is streamed together with the first
+      // assignment (density_fluctuation), chunk by chunk.
+      host_x_ = x; host_y_ = y; host_z_ = z;
+    } else {
+      data_.reset(new dev::Catalogue(ctx_, n, x, y, z, nullptr, nullptr, on_device));
+    }
     dev::profile_mark(c_, "upload");
   }
 
@@ -318,7 +324,14 @@ class Engine {
   dev::Mesh density_fluctuation(int L, int M) {
     const bool real_field = (M == 0);
     dev::Mesh x(ctx_, c_, real_field ? TRVB_REAL : TRVB_COMPLEX);
-    if (!survey_) {
+    if (!survey_ && !data_) {
+      // Pending host arrays: chunked upload, each chunk tile-sorted and spread while the
+      // next one is on the wire (trvb_cat_create_assign).
+      trvb_cat* cat = nullptr;
+      dev::check(trvb_cat_create_assign(c_, &cat, ndata_, host_x_, host_y_, host_z_, 1., x.view()),
+                 "trvb_cat_create_assign");
+      data_.reset(new dev::Catalogue(ctx_, cat));
+    } else if (!survey_) {
       assign(*data_, TRVB_W_UNIT, 0, 0, 1., false, x);
     } else if (window_) {
       assign(*data_, TRVB_W_YLM_W, L, M, alpha_, false, x);
@@ -410,6 +423,9 @@ class Engine {
   double alpha_ = 1.;
   double vol_ = 0., vol_cell_ = 0.;
   int mode_ = 0;
+  const double* host_x_ = nullptr;   // box arrays awaiting the streamed upload
+  const double* host_y_ = nullptr;
+  const double* host_z_ = nullptr;
 };
 
 /// `count` consecutive meshes of one grid in a single device allocation (the
