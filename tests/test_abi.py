@@ -59,6 +59,18 @@ def test_no_cpu_fallback_without_a_device():
                      (0.1, 0.5), 3, 1.)
     with pytest.raises(core.TriumvirateError):
         core.mesh(pos, 100., 16, "tsc")
+    # two-point estimators and the array fast path likewise
+    with pytest.raises(core.TriumvirateError, match="no CPU fallback"):
+        core.twopt("powspec", "sim", 100., 16, "tsc", 0, (0.1, 0.5), 3, 1., pos_d=pos)
+    x = np.ascontiguousarray(pos)
+    with pytest.raises(core.TriumvirateError, match="no CPU fallback"):
+        core.threept_box_arrays("bispec", 100, x[0].ctypes.data, x[1].ctypes.data,
+                                x[2].ctypes.data, False, 100., 16, "tsc", (0, 0, 0), "diag",
+                                (0.1, 0.5), 3)
+    # host-only helpers keep working without a device
+    own = core.partition_owners("full", (0, 0), 6, 4)
+    assert len(own) == 21 and set(own) == {0, 1, 2, 3}
+    assert abs(core.norm_particles_2pt(pos, np.full(100, 1.e-4)) - 1. / (100 * 1.e-4)) < 1e-9
     # the device layer itself refuses to create a context
     ctx = C.c_void_p()
     st = _lib.trvb().trvb_ctx_create(C.byref(ctx), 0, (C.c_int * 3)(8, 8, 8),
