@@ -377,7 +377,7 @@ k_gram_fields(const VT* const* __restrict__ A, const VT* const* __restrict__ B,
     cp_async_wait<1>();
     __syncthreads();
     const VT* sA = cur;
-    const VT* sB = cur + (size_t)na * T;
+    const VT* sB = (nb == 0) ? cur : cur + (size_t)na * T;   // nb == 0: B rows are the A rows
     const VT* sG = cur + (size_t)(na + nb) * T;
 #pragma unroll
     for (int q = 0; q < TPW; q++) {
@@ -503,7 +503,7 @@ k_gram_fields_tma(const VT* const* __restrict__ A, const VT* const* __restrict__
     mbar_wait(&bars[it & 1], (unsigned)((it >> 1) & 1));
     const int valid = (int)min((long long)T, ncells - tile * T);
     const VT* sA = cur;
-    const VT* sB = cur + (size_t)na * T;
+    const VT* sB = (nb == 0) ? cur : cur + (size_t)na * T;   // nb == 0: B rows are the A rows
     const VT* sG = cur + (size_t)(na + nb) * T;
 #pragma unroll
     for (int q = 0; q < TPW; q++) {
@@ -615,7 +615,7 @@ int launch_gram_chunk(trvb_ctx* ctx, const Loader& ld, const int* d_sel_a, int n
 // up to GRAM_WARPS * 4 blocks and stage only the fields their blocks touch.
 template <class Loader>
 int run_gram(trvb_ctx* ctx, const Loader& ld, int na_all, int nb_all, long long ncells,
-             const int* ia, const int* ib, int npairs, double* out) {
+             const int* ia, const int* ib, int npairs, double* out, bool b_is_a = false) {
   TRVB_REQUIRE(na_all > 0 && nb_all > 0 && npairs > 0, "gram reduce: empty problem");
   constexpr int E = GRAM_B * GRAM_B;
   // Needed blocks in (a-block, b-block) order.
@@ -638,20 +638,26 @@ int run_gram(trvb_ctx* ctx, const Loader& ld, int na_all, int nb_all, long long 
   for (size_t b0 = 0; b0 < blocks.size();) {
     Chunk c; c.first = b0;
     std::vector<int> slot_a(nba, -1), slot_b(nbb, -1);
+    // When both sides are the same list of fields (b_is_a) a field is staged once:
+    // the b-blocks take their rows from the a-list and the kernel sees nb == 0.
+    std::vector<int>& slot_bb = b_is_a ? slot_a : slot_b;
+    std::vector<int>& sel_bb = b_is_a ? c.sel_a : c.sel_b;
     size_t t = b0;
     for (; t < blocks.size() && (int)c.blk_a.size() < max_blk; t++) {
       const int a = blocks[t].first, b = blocks[t].second;
-      const int extra = (slot_a[a] < 0 ? GRAM_B : 0) + (slot_b[b] < 0 ? GRAM_B : 0);
+      const bool same_block = b_is_a && a == b;
+      const int extra = (slot_a[a] < 0 ? GRAM_B : 0)
+        + ((slot_bb[b] < 0 && !same_block) ? GRAM_B : 0);
       if (!c.blk_a.empty() && (int)(c.sel_a.size() + c.sel_b.size()) + extra > max_fields) break;
       if (slot_a[a] < 0) {
         slot_a[a] = (int)c.sel_a.size() / GRAM_B;
         for (int e = 0; e < GRAM_B; e++) c.sel_a.push_back(std::min(a * GRAM_B + e, na_all - 1));
       }
-      if (slot_b[b] < 0) {
-        slot_b[b] = (int)c.sel_b.size() / GRAM_B;
-        for (int e = 0; e < GRAM_B; e++) c.sel_b.push_back(std::min(b * GRAM_B + e, nb_all - 1));
+      if (slot_bb[b] < 0) {
+        slot_bb[b] = (int)sel_bb.size() / GRAM_B;
+        for (int e = 0; e < GRAM_B; e++) sel_bb.push_back(std::min(b * GRAM_B + e, nb_all - 1));
       }
-      c.blk_a.push_back(slot_a[a]); c.blk_b.push_back(slot_b[b]);
+      c.blk_a.push_back(slot_a[a]); c.blk_b.push_back(slot_bb[b]);
     }
     b0 = t;
     chunks.push_back(std::move(c));
@@ -1038,6 +1044,9 @@ extern "C" int trvb_gram_reduce(trvb_ctx* ctx, const void* const* A, int na,
   if (G.layout == TRVB_REAL && (ctx->g.nmesh & 1)) aligned = false;
   const char* env_tma = getenv("TRV_GRAM_NO_TMA");
   if (env_tma && env_tma[0] == '1') aligned = false;
+  // Both sides the same list of meshes (auto-correlation-like pair grids): stage once.
+  bool b_is_a = na == nb;
+  for (int i = 0; i < na && b_is_a; i++) b_is_a = A[i] == B[i];
   int st;
   if (G.layout == TRVB_REAL) {
     RealFieldLoader ld;
@@ -1045,14 +1054,14 @@ extern "C" int trvb_gram_reduce(trvb_ctx* ctx, const void* const* A, int na,
     ld.A = (const double* const*)d_tab;
     ld.B = (const double* const*)(d_tab + na);
     ld.G = (const double*)G.data;
-    st = run_gram(ctx, ld, na, nb, ctx->g.nmesh, ia, ib, npairs, out);
+    st = run_gram(ctx, ld, na, nb, ctx->g.nmesh, ia, ib, npairs, out, b_is_a);
   } else {
     FieldLoader ld;
     ld.aligned16 = aligned;
     ld.A = (const double2* const*)d_tab;
     ld.B = (const double2* const*)(d_tab + na);
     ld.G = (const double2*)G.data;
-    st = run_gram(ctx, ld, na, nb, ctx->g.nmesh, ia, ib, npairs, out);
+    st = run_gram(ctx, ld, na, nb, ctx->g.nmesh, ia, ib, npairs, out, b_is_a);
   }
   trvb_dev_free_raw(ctx, d_tab);
   return st;
