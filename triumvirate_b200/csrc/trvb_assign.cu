@@ -1475,14 +1475,19 @@ int streamed_assign(trvb_ctx* ctx, trvb_cat* cat, const double* hx, const double
   const bool cplx_mesh = mesh.layout == TRVB_COMPLEX;
   UploadLane& lane = g_upload_lane[ctx->device];
   if (!lane.stream) TRVB_CUDA(cudaStreamCreateWithFlags(&lane.stream, cudaStreamNonBlocking));
-  // Every chunk costs one sweep over the mesh (its REDs touch sectors all over it), so
-  // chunks are few and shrink geometrically: 1/2, 1/4, 1/8, 1/8 of the catalogue -- the
-  // work left after the last byte has arrived is an eighth of the sort + assignment.
+  // Every chunk costs one sweep over the mesh (its REDs touch sectors all over it: the
+  // four-chunk form spends 2.6 ms in the scatter kernels instead of 1.4), so chunks are
+  // few and shrink geometrically: 1/2, 1/4, 1/4 of the catalogue by default -- the work
+  // left after the last byte has arrived is a quarter of the sort + assignment.
+  // TRV_STREAM_LEVELS = number of halvings (C2 end to end: 1: 10.66, 2: 10.40, 3: 10.58,
+  // 4: 10.53 ms).
   std::vector<long long> bounds(1, 0);
   {
+    const char* env_levels = getenv("TRV_STREAM_LEVELS");
+    const int TRVB_STREAM_LEVELS = env_levels ? atoi(env_levels) : 2;   // measured best on C2
     const long long min_chunk = 1LL << 20;
     long long left = n;
-    for (int level = 0; level < 3 && left > 2 * min_chunk; level++) {
+    for (int level = 0; level < TRVB_STREAM_LEVELS && left > 2 * min_chunk; level++) {
       const long long take = std::max(min_chunk, left / 2);
       bounds.push_back(bounds.back() + take);
       left -= take;
