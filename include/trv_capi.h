@@ -35,8 +35,9 @@ int trv_gpu_count(void);
  * constant 0, I/monitor.hpp:249-250).  Owner rank in [0, world) of each of the
  * *dim data-vector entries of a `form` ("diag" | "off-diag" | "row" | "full";
  * "full" with ell1 == ell2 is the upper triangle, S/parameters.cpp:829-849)
- * over num_bins bins; `owner` holds >= num_bins^2 ints.  Shares are equal in
- * size (+-1) and compact in the (row bin, column bin) matrix. */
+ * over num_bins bins; `owner` holds >= num_bins^2 ints.  Shares are compact in
+ * the (row bin, column bin) matrix and equal in distinct shell fields (the
+ * transforms a share costs), not in entries. */
 int trv_partition_owners(const char* form, int ell1, int ell2, int idx_bin, int num_bins,
                          int world, int* owner, int* dim);
 

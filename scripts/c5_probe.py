@@ -11,7 +11,7 @@ d = torch.from_numpy(pos).to('cuda:0'); torch.cuda.synchronize()
 kw = dict(boxsize=L, ngrid=ng, assignment='pcs', degrees=(0, 0, 0), form='full',
           bin_range=(0.005, 0.405), num_bins=nb, norm_factor=1.)
 core.profile_enable(True)
-for rank, count in ((0, 1), (0, 8), (3, 8), (6, 8), (7, 8)):
+for rank, count in ((0, 1), (0, 8), (1, 8), (3, 8), (5, 8), (6, 8), (7, 8)):
     for it in range(2):
         t = time.perf_counter()
         out = core.threept_box_arrays('bispec', n, d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), True,

@@ -10,4 +10,4 @@ for l in open("gpurun_out/bench_n$n.log"):
         d=json.loads(l); print("N=$n ms_per_step", d["ms_per_step"], "e2e", d["e2e"]["value"])
 PY
 done
-timeout 900 python scripts/c5_probe.py > gpurun_out/c5_probe.txt 2>&1; cat gpurun_out/c5_probe.txt
+timeout 900 python scripts/c5_probe.py > gpurun_out/c5_probe.txt 2>&1; grep "iter 1" gpurun_out/c5_probe.txt | cut -c1-340

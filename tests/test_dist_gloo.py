@@ -68,25 +68,30 @@ def test_partition_covers_every_entry_once():
             seen = np.concatenate([tdist.local_entries(form, deg, nb, r, world, idx_bin=idx_bin)
                                    for r in range(world)])
             assert sorted(seen) == list(range(dim))
-            sizes = np.bincount(own, minlength=world)
-            assert sizes.max() - sizes.min() <= 1          # balanced
+            if form != "full":
+                # one (or two) fields per entry: the largest share is as small as it can be
+                sizes = np.bincount(own, minlength=world)
+                assert sizes.max() == -(-dim // world)
 
 
 def test_partition_is_compact_in_the_pair_matrix():
-    """A rank needs the shell field of every bin that appears in its entries:
-    the block partition must keep that well below `all bins` (the round-robin
-    split of the first version needed all 40 on every one of 8 ranks)."""
+    """A rank needs the shell field of every bin that appears in its entries, and those
+    transforms are what the pair phase costs: the shares are compact blocks, equal in
+    FIELDS (the round-robin split of the first version needed all 40 on every one of 8
+    ranks; equal-pair cuts of the serpentine order still left 15 ... 26)."""
     from triumvirate_b200 import dist as tdist
-    nb, world = 40, 8
+    nb = 40
     pairs = np.array(_pairs_of("full", (0, 0), nb))
-    own = tdist.owners("full", (0, 0), nb, world)
-    fields = [len(set(pairs[own == r].ravel())) for r in range(world)]
-    assert max(fields) <= 28 and np.mean(fields) <= 24, fields
+    for world, cap in ((8, 19), (7, 20), (4, 25), (2, 40)):
+        own = tdist.owners("full", (0, 0), nb, world)
+        assert own.max() == world - 1
+        fields = [len(set(pairs[own == r].ravel())) for r in range(world)]
+        assert max(fields) <= cap, (world, fields)
     own2 = tdist.owners("full", (2, 0), 20, 4)       # 20 x 20 entries, distinct row/col fields
     pairs2 = np.array(_pairs_of("full", (2, 0), 20))
     for r in range(4):
         mine = pairs2[own2 == r]
-        assert len(set(mine[:, 0])) + len(set(mine[:, 1])) <= 26
+        assert len(set(mine[:, 0])) + len(set(mine[:, 1])) <= 20
 
 
 def test_pack_unpack_roundtrip():

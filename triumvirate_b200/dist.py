@@ -17,22 +17,23 @@ _STAT_KEYS = {"bispec": ("bk_raw", "bk_shot"), "3pcf": ("zeta_raw", "zeta_shot")
 def owners(form, degrees, num_bins, world_size, idx_bin=0):
     """Owner rank of every data-vector entry: the rule of ``active_entries`` in
     src/threept.cpp (``trv::partition_owners``) -- compact blocks of the bin-pair
-    matrix, equal shares (+-1), so that a rank only transforms the shells it pairs."""
+    matrix with equal numbers of distinct shell fields (not of entries): the shell
+    transforms are what a rank's share costs."""
     from . import core
     return core.partition_owners(form, degrees, num_bins, world_size, idx_bin=idx_bin)
 
 
 def bispec_owners(form, degrees, num_bins, world_size, idx_bin=0):
-    """(pair owner, shot-noise owner) of every bispectrum entry: with two or more
-    ranks the LAST rank computes the shot noise of every entry (its full-grid inverse
-    FFT does not depend on the pair partition) and the pairs are dealt to the other
-    ranks (``bispec_share`` in src/threept.cpp).  The 3PCF keeps both on the pair
+    """Shot-noise owner of every bispectrum entry: with two or more ranks the LAST rank
+    computes the shot noise of every entry (its full-grid inverse FFT does not depend on
+    the pair partition); the pairs are dealt to all ranks with the last one handicapped
+    by the cost of that branch (``bispec_share`` in src/threept.cpp -- the exact pair
+    owners depend on the mesh and sub-grid sizes).  The 3PCF keeps both on the pair
     owner."""
+    own = owners(form, degrees, num_bins, max(world_size, 1), idx_bin=idx_bin)
     if world_size < 2:
-        own = owners(form, degrees, num_bins, 1, idx_bin=idx_bin)
-        return own, own
-    own = owners(form, degrees, num_bins, world_size - 1, idx_bin=idx_bin)
-    return own, np.full_like(own, world_size - 1)
+        return own
+    return np.full_like(own, world_size - 1)
 
 
 def local_entries(form, degrees, num_bins, rank, world_size, idx_bin=0):

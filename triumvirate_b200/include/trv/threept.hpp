@@ -88,7 +88,8 @@ trv::ThreePCFMeasurements compute_3pcf_in_gpp_box(
 /// every data-vector entry given its (row bin, column bin); the estimators
 /// compute the entries owned by `ParameterSet::part_rank` and leave zeros elsewhere.
 std::vector<int> partition_owners(
-  const std::vector<int>& row, const std::vector<int>& col, int world);
+  const std::vector<int>& row, const std::vector<int>& col, int world, bool same_fields = true,
+  double handicap_last = 0.);
 
 /// The same for a parameter set's data-vector shape (after validate()).
 std::vector<int> partition_owners(const trv::ParameterSet& params, int num_bins, int world);

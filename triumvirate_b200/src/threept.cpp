@@ -555,14 +555,18 @@ void reduce_pairs(Engine& eng, trvb_ctx* grid, const DataVector& dv,
 
 /// Owner rank of every data-vector entry.  An entry (row bin, column bin) needs
 /// the shell fields of both bins on its rank and those inverse transforms are
-/// what the pair phase costs, so a rank should own a compact rectangle of the
-/// (row, column) matrix rather than scattered entries: the entries are ordered by
-/// (strip of h consecutive rows, column -- serpentine, so that a share crossing
-/// into the next strip keeps its columns --, row) with h^2 ~ entries per rank, and
-/// that order is cut into `world` contiguous shares of equal size (+-1).  For
-/// `diag`, `off-diag` and `row` shapes this degenerates to contiguous bin ranges.
+/// what the pair phase costs (two orders of magnitude more than a pair product), so
+/// a rank should own a compact rectangle of the (row, column) matrix and the shares
+/// should be equal in FIELDS rather than in entries: the entries are ordered by
+/// (strip of h consecutive rows, column -- serpentine, so that a share crossing into
+/// the next strip keeps its columns --, row) and that order is cut greedily under the
+/// smallest cost cap (distinct fields + pairs / 100) that needs no more than `world`
+/// shares; h is scanned around sqrt(entries per rank).  `same_fields`: row and column
+/// bins index the same set of fields (equal degrees), so a bin on both sides of a
+/// share counts once.  For `diag`, `off-diag` and `row` shapes this degenerates to
+/// contiguous bin ranges.
 std::vector<int> partition_owners(const std::vector<int>& row, const std::vector<int>& col,
-                                  int world) {
+                                  int world, bool same_fields, double handicap_last) {
   const int dim = static_cast<int>(row.size());
   std::vector<int> owner(dim, 0);
   if (world <= 1 || dim == 0) return owner;
@@ -570,53 +574,108 @@ std::vector<int> partition_owners(const std::vector<int>& row, const std::vector
   auto rank_in = [](const std::vector<int>& sorted, int v) {
     return static_cast<int>(std::lower_bound(sorted.begin(), sorted.end(), v) - sorted.begin());
   };
-  const double per = double(dim) / double(world);
-  const int h = std::max(1, static_cast<int>(std::floor(std::sqrt(per) + 0.5)));
-  std::vector<std::array<int, 4> > keyed(dim);
+  // Field ids: rows and columns share ids when they index the same fields.
+  std::vector<int> all = rows;
+  all.insert(all.end(), cols.begin(), cols.end());
+  const std::vector<int> fields = distinct_sorted(all);
+  const int nfield = same_fields ? static_cast<int>(fields.size())
+                                 : static_cast<int>(rows.size() + cols.size());
+  std::vector<int> fr(dim), fc(dim), rr(dim), cc(dim);
   for (int i = 0; i < dim; i++) {
-    const int r = rank_in(rows, row[i]), c = rank_in(cols, col[i]);
-    const int strip = r / h;
-    keyed[i] = {strip, (strip % 2 == 0) ? c : -c, r, i};
+    rr[i] = rank_in(rows, row[i]); cc[i] = rank_in(cols, col[i]);
+    fr[i] = same_fields ? rank_in(fields, row[i]) : rr[i];
+    fc[i] = same_fields ? rank_in(fields, col[i]) : static_cast<int>(rows.size()) + cc[i];
   }
-  std::sort(keyed.begin(), keyed.end());
-  for (int t = 0; t < dim; t++) {
-    owner[keyed[t][3]] = static_cast<int>((static_cast<long long>(t) * world) / dim);
+  const double pair_weight = 0.01;
+
+  // Greedy cut of `order` under a cost cap; returns the number of shares.
+  std::vector<int> stamp(nfield, -1);
+  // The last share may carry other work worth `handicap_last` fields (the shot-noise
+  // branch of the bispectrum): its cap is lower by that much, possibly leaving it empty.
+  auto cut = [&](const std::vector<int>& order, double cap, std::vector<int>* out) {
+    int share = 0, nf = 0, np = 0;
+    std::fill(stamp.begin(), stamp.end(), -1);
+    for (int idx : order) {
+      for (;;) {
+        const int add = (stamp[fr[idx]] != share) + (fc[idx] != fr[idx] && stamp[fc[idx]] != share);
+        const double cap_here = (share == world - 1) ? cap - handicap_last : cap;
+        if (nf + add + pair_weight * (np + 1) <= cap_here) {
+          stamp[fr[idx]] = share; stamp[fc[idx]] = share;
+          nf += add; np++;
+          if (out) (*out)[idx] = share;
+          break;
+        }
+        if (np == 0 || share == world - 1) return world + 1;   // does not fit under this cap
+        share++; nf = 0; np = 0;
+      }
+    }
+    return share + 1;
+  };
+
+  const double per = double(dim) / double(world);
+  const int h0 = std::max(1, static_cast<int>(std::floor(std::sqrt(per) + 0.5)));
+  double best_cap = 0.; std::vector<int> best_order;
+  for (int h = std::max(1, h0 / 2); h <= 2 * h0 + 1; h++) {
+    std::vector<std::array<int, 4> > keyed(dim);
+    for (int i = 0; i < dim; i++) {
+      const int strip = rr[i] / h;
+      keyed[i] = {strip, (strip % 2 == 0) ? cc[i] : -cc[i], rr[i], i};
+    }
+    std::sort(keyed.begin(), keyed.end());
+    std::vector<int> order(dim);
+    for (int t = 0; t < dim; t++) order[t] = keyed[t][3];
+    // one share always fits under hi
+    double lo = 0., hi = nfield + pair_weight * dim + 1. + std::max(0., handicap_last);
+    for (int it = 0; it < 40; it++) {
+      const double mid = 0.5 * (lo + hi);
+      if (cut(order, mid, nullptr) <= world) hi = mid; else lo = mid;
+    }
+    if (best_order.empty() || hi < best_cap - 1.e-9) { best_cap = hi; best_order = order; }
   }
+  cut(best_order, best_cap, &owner);
   return owner;
 }
 
 std::vector<int> partition_owners(const trv::ParameterSet& params, int num_bins, int world) {
   const DataVector dv = make_data_vector(params, num_bins);
-  return partition_owners(dv.row, dv.col, world);
+  return partition_owners(dv.row, dv.col, world, params.ell1 == params.ell2);
 }
 
 namespace {
 
 std::vector<char> active_entries(const trv::ParameterSet& params, const DataVector& dv) {
   std::vector<char> active(dv.dim, 0);
-  const std::vector<int> owner = partition_owners(dv.row, dv.col, params.part_count);
+  const std::vector<int> owner = partition_owners(dv.row, dv.col, params.part_count,
+                                                  params.ell1 == params.ell2);
   for (int i = 0; i < dv.dim; i++) active[i] = owner[i] == params.part_rank;
   return active;
 }
 
 /// Bispectrum work split.  The shot-noise branch (one full-grid inverse FFT and its
-/// reductions, about as expensive as the whole pair phase after the restructuring)
-/// does not depend on the pair partition, so with two or more ranks it goes to the
-/// LAST rank for every entry, and the pair entries are dealt to the other ranks.
+/// reductions) does not depend on the pair partition, so with two or more ranks it
+/// goes to the LAST rank for every entry; the pair entries are dealt to all ranks with
+/// the last one handicapped by the cost of that branch in units of one shell field
+/// (measured: a full-grid shot-noise pass costs 1.7x a sub-grid shell transform per
+/// cell).
 struct BispecShare {
   std::vector<char> pairs;   // entries whose raw bispectrum this rank computes
   std::vector<char> shot;    // entries whose shot noise this rank computes
   bool any_pairs = false, any_shot = false;
 };
 
-BispecShare bispec_share(const trv::ParameterSet& params, const DataVector& dv) {
+BispecShare bispec_share(const trv::ParameterSet& params, const DataVector& dv,
+                         double shot_cost_in_fields) {
   BispecShare sh;
   sh.pairs.assign(dv.dim, 0); sh.shot.assign(dv.dim, 0);
   const int world = params.part_count, rank = params.part_rank;
   if (world < 2) {
     sh.pairs.assign(dv.dim, 1); sh.shot.assign(dv.dim, 1);
   } else {
-    const std::vector<int> owner = partition_owners(dv.row, dv.col, world - 1);
+    // The last rank's share of the pairs is cut short by what the shot-noise branch costs
+    // (none at all when that exceeds a fair share).
+    const std::vector<int> owner = partition_owners(dv.row, dv.col, world,
+                                                    params.ell1 == params.ell2,
+                                                    shot_cost_in_fields);
     for (int i = 0; i < dv.dim; i++) {
       sh.pairs[i] = owner[i] == rank;
       sh.shot[i] = rank == world - 1;
@@ -657,7 +716,13 @@ trv::BispecMeasurements bispec_impl(
   const cdouble factor_phase = std::pow(trvm::M_I, params.ell1 + params.ell2);
   const int nb = kbinning.num_bins;
   const DataVector dv = make_data_vector(params, nb);
-  const BispecShare share = bispec_share(params, dv);
+  // Sub-grid for the shell fields (decided here: the work split weighs the shot-noise
+  // branch on the full grid against shell transforms on the sub-grid).
+  int nsub[3];
+  choose_subgrid(params, kbinning.bin_edges.back(), nsub);
+  const double shot_cost_in_fields = 1.7 * double(params.nmesh)
+    / (double(nsub[0]) * double(nsub[1]) * double(nsub[2]));
+  const BispecShare share = bispec_share(params, dv, shot_cost_in_fields);
   const std::vector<char>& active = share.pairs;
   const std::vector<char>& shot_active = share.shot;
 
@@ -684,9 +749,6 @@ trv::BispecMeasurements bispec_impl(
   for (int b = 0; b < nb; b++) keff[b] = ksum[b] / double(nmodes[b]);
   dev::profile_mark(c, "shell_stats");
 
-  // Sub-grid for the shell fields.
-  int nsub[3];
-  choose_subgrid(params, kbinning.bin_edges.back(), nsub);
   const bool coarse = nsub[0] != params.ngrid[0];
   std::shared_ptr<trvb_ctx> sub_holder;
   trvb_ctx* sub = c;
