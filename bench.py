@@ -55,6 +55,13 @@ WORKLOADS = {
         n=10**7, L=1000., ngrid=512, assignment="pcs", degrees=(0, 0, 0), form="full",
         bin_range=(0.005, 0.205), num_bins=20, seed=42,
     ),
+    # BASELINE config 5 (the 8-GPU configuration; fits one B200 with 84 GiB): not the
+    # default bench line, run with --workload C5 --no-cpu-baseline
+    "C5": dict(
+        name="box B_000 triu, 1e8 uniform particles, 1024^3, PCS, 40 lin bins [0.005,0.405]",
+        n=10**8, L=2000., ngrid=1024, assignment="pcs", degrees=(0, 0, 0), form="full",
+        bin_range=(0.005, 0.405), num_bins=40, seed=42,
+    ),
     # reduced problem for quick local checks (not a bench line)
     "tiny": dict(
         name="box B_000 triu, 1e5 uniform particles, 64^3, PCS, 6 lin bins",
@@ -315,7 +322,8 @@ def run_b200(args):
         "ms_per_step": 1.e3 * sec / args.steps, "higher_is_better": False,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {
-            "workload": wl["name"], "baseline_config": 2, "particles": n, "ngrid": ng,
+            "workload": wl["name"], "baseline_config": 5 if args.workload == "C5" else 2,
+            "particles": n, "ngrid": ng,
             "pairs": dim, "parallelism": f"pairs/{world}gpu" if world > 1 else "1gpu",
             "e2e_upload": ("1/N slice per rank from pinned host memory + NCCL all-gather"
                            if world > 1 else "pinned host -> device"),
