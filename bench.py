@@ -55,6 +55,12 @@ WORKLOADS = {
         n=10**7, L=1000., ngrid=512, assignment="pcs", degrees=(0, 0, 0), form="full",
         bin_range=(0.005, 0.205), num_bins=20, seed=42,
     ),
+    # C2 on the clustered catalogue of SURVEY section 8d (not the default bench line)
+    "C2-lognormal": dict(
+        name="box B_000 triu, 1e7 lognormal particles (P(k)=2e4 (k/0.05)^-1.5), 512^3, PCS, 20 lin bins",
+        n=10**7, L=1000., ngrid=512, assignment="pcs", degrees=(0, 0, 0), form="full",
+        bin_range=(0.005, 0.205), num_bins=20, seed=69, catalogue="lognormal",
+    ),
     # BASELINE config 5 (the 8-GPU configuration; fits one B200 with 84 GiB): not the
     # default bench line, run with --workload C5 --no-cpu-baseline
     "C5": dict(
@@ -77,7 +83,40 @@ def npairs_of(wl):
         else (nb * nb if wl["form"] == "full" else nb)
 
 
+def lognormal_catalogue(n, L, ngf=256, seed=69):
+    """SURVEY section 8d, C2's second catalogue: Gaussian field on 256^3 with
+    P(k) = 2e4 (k/0.05)^-1.5 truncated at the Nyquist wavenumber, delta_LN =
+    exp(delta_G - sigma^2/2) - 1, Poisson-sampled to ~n points with uniform sub-cell
+    jitter, default_rng(69).  Returns exactly n points (resampled if the draw differs)."""
+    gen = np.random.default_rng(seed)
+    kf = 2 * np.pi / L
+    kx = np.fft.fftfreq(ngf, 1. / ngf) * kf
+    kz = np.fft.rfftfreq(ngf, 1. / ngf) * kf
+    kk = np.sqrt(kx[:, None, None]**2 + kx[None, :, None]**2 + kz[None, None, :]**2)
+    pk = np.zeros_like(kk)
+    nz = kk > 0
+    pk[nz] = 2.e4 * (kk[nz] / 0.05) ** -1.5
+    pk[kk > np.pi * ngf / L] = 0.
+    white = np.fft.rfftn(gen.normal(size=(ngf, ngf, ngf)))
+    dg = np.fft.irfftn(white * np.sqrt(pk / L**3) * ngf**1.5, s=(ngf, ngf, ngf), axes=(0, 1, 2))
+    dln = np.exp(dg - dg.var() / 2.)
+    cnt = gen.poisson(dln * (n / dln.sum()))
+    idx = np.repeat(np.arange(ngf**3), cnt.ravel())
+    idx = gen.permutation(idx)                 # catalogue order carries no spatial order
+    if idx.size >= n:
+        idx = idx[:n]
+    else:
+        idx = np.concatenate([idx, gen.choice(idx, n - idx.size)])
+    i, j, k = np.unravel_index(idx, (ngf, ngf, ngf))
+    cell = L / ngf
+    return np.ascontiguousarray(np.stack([(i + gen.uniform(size=n)) * cell,
+                                          (j + gen.uniform(size=n)) * cell,
+                                          (k + gen.uniform(size=n)) * cell]))
+
+
 def make_catalogue(wl):
+    if wl.get("catalogue") == "lognormal":
+        return lognormal_catalogue(wl["n"], wl["L"], seed=wl["seed"])
     gen = np.random.default_rng(wl["seed"])
     return gen.uniform(0., wl["L"], size=(3, wl["n"]))
 
