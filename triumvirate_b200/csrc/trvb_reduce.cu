@@ -761,6 +761,34 @@ __device__ __forceinline__ bool in_bin(const BinRule& r, double v) {
   return (0 <= q && q < r.nsample) && (r.qlo <= q && q < r.qhi);
 }
 
+// Cells of `cube` whose radius can fall in the bin: the rows (a, b) of the cube are dealt
+// to the threads of blockIdx.x (1-D blocks), and on a row only the third coordinates with
+// lo - slack <= |r| < hi + slack are visited (two short runs, one per sign), instead of
+// the whole cube for every bin.  `f(s0, s1, s2)` receives signed indices and applies the
+// exact bin rule itself, so the set of accepted cells is unchanged.
+template <class F>
+__device__ __forceinline__ void for_each_cell_near_shell(const Cube& cube, double d0, double d1,
+                                                         double d2, const BinRule& rule, F f) {
+  const double slack = (rule.fine ? rule.dsample : 0.) + 1.e-9 * rule.hi;
+  const double rlo = fmax(rule.lo - slack, 0.), rhi = rule.hi + slack;
+  const long long nrows = (long long)cube.cnt[0] * cube.cnt[1];
+  const int cmin = cube.lo[2], cmax = cube.lo[2] + cube.cnt[2] - 1;
+  for (long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x; row < nrows;
+       row += (long long)gridDim.x * blockDim.x) {
+    const int a = (int)(row / cube.cnt[1]), b = (int)(row - (long long)a * cube.cnt[1]);
+    const int s0 = cube.lo[0] + a, s1 = cube.lo[1] + b;
+    const double x = s0 * d0, y = s1 * d1;
+    const double rxy2 = x * x + y * y;
+    const double zhi2 = rhi * rhi - rxy2;
+    if (zhi2 < 0.) continue;
+    const double zlo2 = rlo * rlo - rxy2;
+    const int mhi = (int)(sqrt(zhi2) / d2) + 1;
+    const int mlo = zlo2 > 0. ? max((int)(sqrt(zlo2) / d2) - 1, 0) : 0;
+    for (int s2 = max(mlo, cmin); s2 <= min(mhi, cmax); s2++) f(s0, s1, s2);
+    for (int s2 = max(-mhi, cmin); s2 <= min(-max(mlo, 1), cmax); s2++) f(s0, s1, s2);
+  }
+}
+
 // blockIdx.y = bin.  partial layout: [bin][blockIdx.x][NQ].
 template <int NQ>
 __device__ __forceinline__ void store_partials(double (&v)[NQ], double* smem32,
@@ -780,16 +808,12 @@ k_shell_stats(GridDesc g, Cube cube, const BinRule* __restrict__ rules,
   __shared__ double sm[32];
   const BinRule rule = rules[blockIdx.y];
   double v[2] = {0., 0.};
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < cube.total;
-       t += (long long)gridDim.x * blockDim.x) {
-    const int mk = cube.lo[2] + (int)(t % cube.cnt[2]);
-    const int mj = cube.lo[1] + (int)((t / cube.cnt[2]) % cube.cnt[1]);
-    const int mi = cube.lo[0] + (int)(t / ((long long)cube.cnt[2] * cube.cnt[1]));
+  for_each_cell_near_shell(cube, g.dk[0], g.dk[1], g.dk[2], rule, [&](int mi, int mj, int mk) {
     const double kmag = vec3_norm_exact(__dmul_rn((double)mi, g.dk[0]),
                                         __dmul_rn((double)mj, g.dk[1]),
                                         __dmul_rn((double)mk, g.dk[2]));
     if (in_bin(rule, kmag)) { v[0] += 1.; v[1] += kmag; }
-  }
+  });
   store_partials<2>(v, sm, partial);
 }
 
@@ -828,16 +852,12 @@ k_twopt_fourier(KView fa, KView fb, GridDesc g, Tables tb, Cube cube,
   const BinRule rule = rules[blockIdx.y];
   const YlmCoef yc = ylm_coef(ell, m);
   double v[6] = {0., 0., 0., 0., 0., 0.};
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < cube.total;
-       t += (long long)gridDim.x * blockDim.x) {
-    const int mk = cube.lo[2] + (int)(t % cube.cnt[2]);
-    const int mj = cube.lo[1] + (int)((t / cube.cnt[2]) % cube.cnt[1]);
-    const int mi = cube.lo[0] + (int)(t / ((long long)cube.cnt[2] * cube.cnt[1]));
+  for_each_cell_near_shell(cube, g.dk[0], g.dk[1], g.dk[2], rule, [&](int mi, int mj, int mk) {
     const double kx = __dmul_rn((double)mi, g.dk[0]);
     const double ky = __dmul_rn((double)mj, g.dk[1]);
     const double kz = __dmul_rn((double)mk, g.dk[2]);
     const double kmag = vec3_norm_exact(kx, ky, kz);
-    if (!in_bin(rule, kmag)) continue;
+    if (!in_bin(rule, kmag)) return;
     const int i = mi >= 0 ? mi : mi + g.n[0];
     const int j = mj >= 0 ? mj : mj + g.n[1];
     const int k = mk >= 0 ? mk : mk + g.n[2];
@@ -851,7 +871,7 @@ k_twopt_fourier(KView fa, KView fb, GridDesc g, Tables tb, Cube cube,
     const cplx y = ylm_eval(yc, kx, ky, kz);
     pk = cmul(pk, y); sn = cmul(sn, y);
     v[0] += 1.; v[1] += kmag; v[2] += pk.re; v[3] += pk.im; v[4] += sn.re; v[5] += sn.im;
-  }
+  });
   store_partials<6>(v, sm, partial);
 }
 
@@ -895,9 +915,7 @@ k_shot_3pcf_bin(XView xi, GridDesc g, Cube cube,
   const BinRule rule = rules[blockIdx.y];
   const YlmCoef ya_c = ylm_coef(la, ma), yb_c = ylm_coef(lb, mb);
   double v[4] = {0., 0., 0., 0.};
-  // 1-D block (blockDim.y == 1): rows over blockIdx.x, last axis over threads.
-  for_each_cell(cube.cnt[0], cube.cnt[1], cube.cnt[2], [&](int a, int b, int c, long long) {
-    const int si = cube.lo[0] + a, sj = cube.lo[1] + b, sk = cube.lo[2] + c;
+  for_each_cell_near_shell(cube, g.dr[0], g.dr[1], g.dr[2], rule, [&](int si, int sj, int sk) {
     // S/field.cpp:546-553: i*dr or (i-n)*dr.
     const double rx = __dmul_rn((double)si, g.dr[0]);
     const double ry = __dmul_rn((double)sj, g.dr[1]);
@@ -968,8 +986,9 @@ template <int NQ, class Launch>
 int run_binned(trvb_ctx* ctx, const std::vector<BinRule>& rules, long long nwork,
                Launch launch, std::vector<double>& host_out) {
   const int nbins = (int)rules.size();
-  const int bx = (int)std::max<long long>(1, std::min<long long>(div_up(nwork, 256 * 4),
-                                          (long long)ctx->num_sms * 4));
+  // `nwork` rows of the cube, one or two per thread
+  const int bx = (int)std::max<long long>(1, std::min<long long>(div_up(nwork, 256),
+                                          (long long)ctx->num_sms * 8));
   const size_t bytes_rules = (sizeof(BinRule) * nbins + 255) / 256 * 256;
   const size_t bytes_partial = sizeof(double) * (size_t)nbins * bx * NQ;
   const size_t bytes_out = sizeof(double) * (size_t)nbins * NQ;
@@ -1149,7 +1168,7 @@ extern "C" int trvb_shell_stats(trvb_ctx* ctx, const double* edges, int nbins, i
   const GridDesc g = ctx->g;
   const Cube cube = cube_for(g, edges[nbins] + 2.e-5);
   std::vector<double> host;
-  int st = run_binned<2>(ctx, rules, cube.total,
+  int st = run_binned<2>(ctx, rules, (long long)cube.cnt[0] * cube.cnt[1],
     [&](dim3 grid, const BinRule* d_rules, double* d_partial) {
       k_shell_stats<<<grid, 256, 0, ctx->stream>>>(g, cube, d_rules, d_partial);
     }, host);
@@ -1177,7 +1196,7 @@ extern "C" int trvb_twopt_fourier(trvb_ctx* ctx, trvb_mesh fa, trvb_mesh fb,
   const KView va = kview_of(ctx, fa), vb = kview_of(ctx, fb);
   const Tables tb = tables_of(ctx);
   std::vector<double> host;
-  int st = run_binned<6>(ctx, rules, cube.total,
+  int st = run_binned<6>(ctx, rules, (long long)cube.cnt[0] * cube.cnt[1],
     [&](dim3 grid, const BinRule* d_rules, double* d_partial) {
       k_twopt_fourier<<<grid, 256, 0, ctx->stream>>>(va, vb, g, tb, cube, d_rules,
                                                     S[0], S[1], ell, m, interlaced, d_partial);
@@ -1266,7 +1285,7 @@ int binned_xi_sums(trvb_ctx* ctx, trvb_mesh xi, int la, int ma, int lb, int mb,
     if (n == 1) { lo = 0; hi = 0; }
     cube.lo[a] = lo; cube.cnt[a] = hi - lo + 1; cube.total *= cube.cnt[a];
   }
-  return run_binned<4>(ctx, rules, cube.total,
+  return run_binned<4>(ctx, rules, (long long)cube.cnt[0] * cube.cnt[1],
     [&](dim3 grid, const BinRule* d_rules, double* d_partial) {
       k_shot_3pcf_bin<<<grid, 256, 0, ctx->stream>>>(d_xi, g, cube, d_rules, la, ma, lb, mb, d_partial);
     }, host);
