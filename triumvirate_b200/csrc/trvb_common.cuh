@@ -408,6 +408,22 @@ __device__ __forceinline__ double sjl_eval(const SjlView& t, double x) {
   return y_lo + delx * (b_i + delx * (c_i + delx * d_i));
 }
 
+// y_lm at the mirror image (+-x, +-y, +-z) of a point from its value y0 there, by the
+// parity rules of the factors of ylm_eval: P_l^|m|(-mu) = (-1)^(l-|m|) P_l^|m|(mu),
+// (-cs + i sn)^|m| = (-1)^|m| conj((cs + i sn)^|m|), (cs - i sn)^|m| = conj(...).
+// Sign flips commute with every rounding in ylm_eval, so the result is bit-identical to
+// evaluating at the mirrored point.  Not valid for the generic (large l) evaluator.
+__device__ __forceinline__ cplx ylm_mirror(const YlmCoef& c, const cplx& y0, bool fx, bool fy,
+                                           bool fz) {
+  const double par_am = (c.am & 1) ? -1. : 1.;
+  const double par_l = ((c.ell - c.am) & 1) ? -1. : 1.;
+  const double sz = fz ? par_l : 1.;
+  cplx out;
+  out.re = y0.re * ((fx ? par_am : 1.) * sz);
+  out.im = y0.im * ((fx ? -par_am : 1.) * (fy ? -1. : 1.) * sz);
+  return out;
+}
+
 // The same interpolant with the three divisions of the evaluation formula replaced
 // by multiplications with precomputed reciprocals (1/step, 1/3): equal to sjl_eval
 // to a few ulp, for passes that evaluate it once per mesh cell and bin.

@@ -180,16 +180,32 @@ k_shot_radial_hist(XView xi, GridDesc g, int la, int ma, int lb,
       if (!dup) x[e] = xload(xi, ((long long)ii[a] * n1 + jj[b]) * n2 + kk[c]);
     }
     double re = 0., im = 0.;
+    // y_lm of the eight mirror cells follow from the value at (ci, cj, ck) by parity
+    // (ylm_mirror, bit-identical to direct evaluation): two evaluations per octant cell
+    // instead of sixteen -- the pass was bound by their square roots and divisions.
+    const bool by_parity = !TRIVIAL && !ya_c.generic && !yb_c.generic;
+    cplx ya0, yb0;
+    if (by_parity) {
+      const double rx0 = (double)signed_index(ci, n0) * g.dr[0];
+      const double ry0 = (double)signed_index(cj, n1) * g.dr[1];
+      const double rz0 = (double)signed_index(ck, n2) * g.dr[2];
+      ya0 = ylm_eval(ya_c, rx0, ry0, rz0); yb0 = ylm_eval(yb_c, rx0, ry0, rz0);
+    }
 #pragma unroll
     for (int e = 0; e < 8; e++) {
       if (TRIVIAL) { re += x[e].x; im += x[e].y; continue; }
       const int a = e >> 2, b = (e >> 1) & 1, c = e & 1;
       const bool dup = (a && pi == ci) || (b && pj == cj) || (c && pk == ck);
       if (dup) continue;
-      const double rx = (double)signed_index(ii[a], n0) * g.dr[0];
-      const double ry = (double)signed_index(jj[b], n1) * g.dr[1];
-      const double rz = (double)signed_index(kk[c], n2) * g.dr[2];
-      const cplx yy = cmul(ylm_eval(ya_c, rx, ry, rz), ylm_eval(yb_c, rx, ry, rz));
+      cplx yy;
+      if (by_parity) {
+        yy = cmul(ylm_mirror(ya_c, ya0, a, b, c), ylm_mirror(yb_c, yb0, a, b, c));
+      } else {
+        const double rx = (double)signed_index(ii[a], n0) * g.dr[0];
+        const double ry = (double)signed_index(jj[b], n1) * g.dr[1];
+        const double rz = (double)signed_index(kk[c], n2) * g.dr[2];
+        yy = cmul(ylm_eval(ya_c, rx, ry, rz), ylm_eval(yb_c, rx, ry, rz));
+      }
       cplx xv; xv.re = x[e].x; xv.im = x[e].y;
       const cplx v = cmul(xv, yy);
       re += v.re; im += v.im;
