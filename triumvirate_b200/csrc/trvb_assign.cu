@@ -1381,7 +1381,9 @@ cudaError_t ensure_stage() {
 template <class F>
 void host_parallel(long long m, F body) {
   const unsigned hw = std::thread::hardware_concurrency();
-  const int nt = (int)std::max(1u, std::min(8u, hw ? hw : 1u));
+  const char* env_nt = getenv("TRV_UPLOAD_THREADS");
+  const unsigned cap = env_nt ? (unsigned)std::max(1, atoi(env_nt)) : 8u;
+  const int nt = (int)std::max(1u, std::min(cap, hw ? hw : 1u));
   if (nt == 1 || m < 65536) { body(0, m); return; }
   std::vector<std::thread> pool;
   const long long per = (m + nt - 1) / nt;
