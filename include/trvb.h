@@ -250,10 +250,13 @@ int trvb_sjl_table(trvb_ctx* ctx, int ell, const double* y, const double* c,
  * out[p] = sum_x A[ia[p]](x) * B[ib[p]](x) * G(x), complex, for p < npairs
  * (S/threept.cpp:1708-1717 and clones, all pairs in one pass over x).
  * A, B: arrays of na / nb device pointers to meshes of `ctx` in G's layout:
- * all TRVB_COMPLEX, or all TRVB_REAL (real fields: a quarter of the flops). */
+ * all TRVB_COMPLEX, or all TRVB_REAL (real fields: a quarter of the flops).
+ * conj_b != 0 uses conj(B[ib[p]]) (complex meshes only): the fields of the mirror
+ * harmonic (l, -m) of a real density are (-1)^(l+m) conj of those of (l, m), so one set
+ * of inverse transforms serves both sides of an (m, -m) term. */
 int trvb_gram_reduce(trvb_ctx* ctx, const void* const* A, int na,
                      const void* const* B, int nb, trvb_mesh G,
-                     const int* ia, const int* ib, int npairs, double* out);
+                     const int* ia, const int* ib, int npairs, int conj_b, double* out);
 
 /* Binned pseudo-2pt statistics in Fourier space with the fine-bin rule
  * (S/field.cpp:2511-2703): per bin nmodes, mean |k|, mean

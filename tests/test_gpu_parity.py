@@ -639,3 +639,21 @@ def test_box_arrays_streamed_upload(core, stat, assignment, n):
                                 pageable[2].ctypes.data, False, **kw)
     for out in (a, b, c):
         _assert_close(out, ref, rtol=1.e-10)
+
+
+@pytest.mark.parametrize("stat,degrees,form", [("bispec", (2, 2, 0), "diag"), ("bispec", (1, 1, 0), "full"),
+                                                ("3pcf", (1, 1, 0), "full"), ("3pcf", (2, 2, 0), "diag")])
+def test_mirror_harmonic_terms_against_oracle(core, oracle, stat, degrees, form):
+    """Bispectrum terms with l1 = l2 and m2 = -m1 below the Nyquist wavenumber: the (l, -m)
+    shell fields are taken as (-1)^(l+m) conj of the (l, m) ones (mirror_harmonics, conj_b in
+    the pair reduction) instead of being transformed.  The 3PCF cases (all modes weighted,
+    Nyquist planes included) must NOT take the shortcut.  Periodic box against the oracle."""
+    gen = np.random.default_rng(61)
+    L, ng = 700., 32
+    pos = gen.uniform(0., L, size=(3, 3000))
+    rng = (0.02, 0.13) if stat == "bispec" else (40., 260.)
+    kw = dict(boxsize=L, ngrid=ng, assignment="tsc", degrees=degrees, form=form, bin_range=rng,
+              num_bins=4, norm_factor=1., pos_d=pos)
+    ref = oracle.threept(stat, "sim", **kw)
+    out = core.threept(stat, "sim", **kw)
+    _assert_close(out, ref, label=f"{stat}{degrees}{form}: ")

@@ -101,6 +101,7 @@ struct FieldLoader {
   const double2* const* B;
   const double2* G;
   bool aligned16;   // every mesh 16-byte aligned: TMA bulk copies are usable
+  int conj_b = 0;   // use conj(B) (B fields given as the mirror harmonic of the A fields)
   __device__ __forceinline__ double2 a(int ia, long long cell) const { return A[ia][cell]; }
   __device__ __forceinline__ double2 hb(int ib, long long cell) const {
     double2 b = B[ib][cell], g = G[cell];
@@ -115,6 +116,7 @@ struct RealFieldLoader {
   const double* const* B;
   const double* G;
   bool aligned16;
+  int conj_b = 0;   // no-op for real fields
   __device__ __forceinline__ double a(int ia, long long cell) const { return A[ia][cell]; }
   __device__ __forceinline__ double hb(int ib, long long cell) const { return B[ib][cell] * G[cell]; }
 };
@@ -323,6 +325,8 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" :: "n"(N));
 }
+__device__ __forceinline__ double vt_conj_if(double a, int) { return a; }
+__device__ __forceinline__ double2 vt_conj_if(double2 a, int c) { if (c) a.y = -a.y; return a; }
 __device__ __forceinline__ double vt_mul(double a, double b) { return a * b; }
 __device__ __forceinline__ double2 vt_mul(double2 a, double2 b) {
   return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -338,7 +342,7 @@ k_gram_fields(const VT* const* __restrict__ A, const VT* const* __restrict__ B,
               const VT* __restrict__ G, const int* __restrict__ sel_a, int na,
               const int* __restrict__ sel_b, int nb, long long ncells,
               const int* __restrict__ blk_a, const int* __restrict__ blk_b, int nblk,
-              double* __restrict__ partial) {
+              double* __restrict__ partial, int conj_b) {
   constexpr int T = GRAM_T;
   constexpr int EPC = 16 / (int)sizeof(VT);   // elements per 16-byte chunk
   constexpr int CH = T / EPC;                 // chunks per staged row
@@ -406,7 +410,7 @@ k_gram_fields(const VT* const* __restrict__ A, const VT* const* __restrict__ B,
           const VT gx = sG[x];
           VT va[GRAM_B], vb[GRAM_B];
 #pragma unroll
-          for (int e = 0; e < GRAM_B; e++) { va[e] = ra[e * T + x]; vb[e] = vt_mul(rb[e * T + x], gx); }
+          for (int e = 0; e < GRAM_B; e++) { va[e] = ra[e * T + x]; vb[e] = vt_mul(vt_conj_if(rb[e * T + x], conj_b), gx); }
 #pragma unroll
           for (int ea = 0; ea < GRAM_B; ea++)
 #pragma unroll
@@ -475,7 +479,7 @@ k_gram_fields_tma(const VT* const* __restrict__ A, const VT* const* __restrict__
                   const VT* __restrict__ G, const int* __restrict__ sel_a, int na,
                   const int* __restrict__ sel_b, int nb, long long ncells,
                   const int* __restrict__ blk_a, const int* __restrict__ blk_b, int nblk,
-                  double* __restrict__ partial) {
+                  double* __restrict__ partial, int conj_b) {
   extern __shared__ __align__(128) double2 smem_raw[];
   const int rows = na + nb + 1;
   VT* buf0 = reinterpret_cast<VT*>(smem_raw);
@@ -533,7 +537,7 @@ k_gram_fields_tma(const VT* const* __restrict__ A, const VT* const* __restrict__
             const VT gx = sG[x];
             VT va[GRAM_B], vb[GRAM_B];
 #pragma unroll
-            for (int e = 0; e < GRAM_B; e++) { va[e] = ra[e * T + x]; vb[e] = vt_mul(rb[e * T + x], gx); }
+            for (int e = 0; e < GRAM_B; e++) { va[e] = ra[e * T + x]; vb[e] = vt_mul(vt_conj_if(rb[e * T + x], conj_b), gx); }
 #pragma unroll
             for (int ea = 0; ea < GRAM_B; ea++)
 #pragma unroll
@@ -599,7 +603,8 @@ int launch_gram_chunk(trvb_ctx* ctx, const Loader& ld, const int* d_sel_a, int n
                                     ctx->stream));
         }
         k_gram_fields_tma<VT, TPW, TT><<<nbk, GRAM_THREADS, sm, ctx->stream>>>(
-          ld.A, ld.B, ld.G, d_sel_a, na, d_sel_b, nb, ncells, d_blk_a, d_blk_b, nblk, d_partial);
+          ld.A, ld.B, ld.G, d_sel_a, na, d_sel_b, nb, ncells, d_blk_a, d_blk_b, nblk, d_partial,
+          ld.conj_b);
         return 0;
       };
       int st = 0;
@@ -611,7 +616,8 @@ int launch_gram_chunk(trvb_ctx* ctx, const Loader& ld, const int* d_sel_a, int n
       TRVB_CUDA(cudaFuncSetAttribute(k_gram_fields<VT, TPW>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k_gram_fields<VT, TPW><<<nblocks, GRAM_THREADS, smem, ctx->stream>>>(
-        ld.A, ld.B, ld.G, d_sel_a, na, d_sel_b, nb, ncells, d_blk_a, d_blk_b, nblk, d_partial);
+        ld.A, ld.B, ld.G, d_sel_a, na, d_sel_b, nb, ncells, d_blk_a, d_blk_b, nblk, d_partial,
+        ld.conj_b);
     }
   } else {
     const size_t smem = sizeof(VT) * (size_t)(na + nb) * GRAM_T;
@@ -1059,7 +1065,8 @@ extern "C" int trvb_mesh_sum_pow(trvb_ctx* ctx, trvb_mesh mesh, int order, doubl
 
 extern "C" int trvb_gram_reduce(trvb_ctx* ctx, const void* const* A, int na,
                                 const void* const* B, int nb, trvb_mesh G,
-                                const int* ia, const int* ib, int npairs, double* out) {
+                                const int* ia, const int* ib, int npairs, int conj_b,
+                                double* out) {
   TRVB_REQUIRE(ctx && A && B && G.data && ia && ib && out, "trvb_gram_reduce: null argument");
   TRVB_REQUIRE(G.layout == TRVB_COMPLEX || G.layout == TRVB_REAL,
                "trvb_gram_reduce: G must be a configuration-space mesh");
@@ -1093,6 +1100,7 @@ extern "C" int trvb_gram_reduce(trvb_ctx* ctx, const void* const* A, int na,
   } else {
     FieldLoader ld;
     ld.aligned16 = aligned;
+    ld.conj_b = conj_b ? 1 : 0;
     ld.A = (const double2* const*)d_tab;
     ld.B = (const double2* const*)(d_tab + na);
     ld.G = (const double2*)G.data;

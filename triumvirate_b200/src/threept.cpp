@@ -459,11 +459,13 @@ class Slab {
 /// for the entries of `dv` selected by `active`.  `get_a(bins)` and
 /// `get_b(bins)` return a slab whose mesh i (layout of G, on `grid`) holds the
 /// field of bin bins[i]; they may hand back a slab cached from an earlier term.
+/// `conj_b`: the B fields are used complex-conjugated (mirror harmonics, see
+/// mirror_harmonics()).
 template <class MakeA, class MakeB>
 void reduce_pairs(Engine& eng, trvb_ctx* grid, const DataVector& dv,
                   const std::vector<char>& active, bool same_fields,
                   trvb_mesh G, MakeA get_a, MakeB get_b,
-                  std::vector<cdouble>& out) {
+                  std::vector<cdouble>& out, bool conj_b = false) {
   out.assign(dv.dim, cdouble(0., 0.));
   std::vector<int> rows_all, cols_all;
   for (int i = 0; i < dv.dim; i++) {
@@ -541,7 +543,7 @@ void reduce_pairs(Engine& eng, trvb_ctx* grid, const DataVector& dv,
       if (ia.empty()) continue;
       std::vector<double> sums(2 * ia.size());
       dev::check(trvb_gram_reduce(grid, pa.data(), (int)pa.size(), pb.data(), (int)pb.size(),
-                                  G, ia.data(), ib.data(), (int)ia.size(),
+                                  G, ia.data(), ib.data(), (int)ia.size(), conj_b ? 1 : 0,
                                   sums.data()), "trvb_gram_reduce");
       dev::profile_mark(eng.ctx(), "pairs:gram");
       for (size_t p = 0; p < ia.size(); p++) {
@@ -642,6 +644,25 @@ std::vector<int> partition_owners(const trv::ParameterSet& params, int num_bins,
 }
 
 namespace {
+
+/// For a REAL source field (its spectrum is stored as a half spectrum) the shell fields of
+/// the mirror harmonic satisfy F_{l,-m}(x) = (-1)^(l+m) conj F_{l,m}(x)
+/// [y_{l,-m} = (-1)^m conj y_{lm}, y_lm(-k) = (-1)^l y_lm(k), delta n(-k) = conj delta n(k),
+/// every other factor real and even], so a term with l1 = l2 and m2 = -m1 needs only the
+/// (l1, m1) transforms: the pair reduction takes conj(B) and the sign is applied after.
+/// The identity fails for modes ON a Nyquist plane (index n/2 stands for -n/2 only, it has
+/// no partner), so it is used only when no shell can reach one: k_max <= (n_a/2) dk_a on
+/// every axis.  The spherical-Bessel fields of the 3PCF weight ALL modes and never qualify.
+bool mirror_harmonics(const trv::ParameterSet& params, const Term& t, const dev::Mesh& source,
+                      double kmax) {
+  if (!(params.ell1 == params.ell2 && t.m2 == -t.m1 && t.m1 != 0
+        && source.layout() == TRVB_HALF && kmax > 0.)) return false;
+  for (int ax = 0; ax < 3; ax++) {
+    const double k_nyq = (params.ngrid[ax] / 2) * (2. * M_PI / params.boxsize[ax]);
+    if (kmax > k_nyq) return false;
+  }
+  return true;
+}
 
 std::vector<char> active_entries(const trv::ParameterSet& params, const DataVector& dv) {
   std::vector<char> active(dv.dim, 0);
@@ -865,16 +886,21 @@ trv::BispecMeasurements bispec_impl(
         dev::profile_mark(c, "G_field");
       }
       const bool same_fields = (params.ell1 == params.ell2 && t.m1 == t.m2);
+      // (l, -m) fields are (-1)^(l+m) conj of the (l, m) ones: one set of transforms.
+      const bool mirror = layout == TRVB_COMPLEX
+        && mirror_harmonics(params, t, dn_00, kbinning.bin_edges.back());
+      const int m_b = mirror ? t.m1 : t.m2;
       std::vector<cdouble> bk_comp;
       reduce_pairs(
-        eng, sub, dv, active, same_fields, G.view(),
+        eng, sub, dv, active, same_fields || mirror, G.view(),
         [&](const std::vector<int>& bins) { return shell_slab(params.ell1, t.m1, bins, layout); },
-        [&](const std::vector<int>& bins) { return shell_slab(params.ell2, t.m2, bins, layout); },
-        bk_comp);
+        [&](const std::vector<int>& bins) { return shell_slab(params.ell2, m_b, bins, layout); },
+        bk_comp, mirror);
+      const double sign_b = (mirror && ((params.ell2 + t.m1) % 2 != 0)) ? -1. : 1.;
       for (int i = 0; i < dv.dim; i++) {
         if (!active[i]) continue;
-        bk_dv[i] += t.coupling * vol_cell_sub * (
-          bk_comp[i] + t.factor_mirror * std::conj(bk_comp[i]));
+        const cdouble comp = sign_b * bk_comp[i];
+        bk_dv[i] += t.coupling * vol_cell_sub * (comp + t.factor_mirror * std::conj(comp));
       }
       dev::profile_mark(c, "shells_and_pairs");
     }
@@ -1054,6 +1080,7 @@ trv::ThreePCFMeasurements threepcf_impl(
       return slab;
     };
     const bool same_fields = (params.ell1 == params.ell2 && t.m1 == t.m2);
+    // (No mirror-harmonic shortcut here: j_l(kr) weights the Nyquist planes too.)
     std::vector<cdouble> zeta_comp;
     reduce_pairs(
       eng, c, dv, active, same_fields, G.view(),
