@@ -617,7 +617,9 @@ std::vector<int> partition_owners(const std::vector<int>& row, const std::vector
   const double per = double(dim) / double(world);
   const int h0 = std::max(1, static_cast<int>(std::floor(std::sqrt(per) + 0.5)));
   double best_cap = 0.; std::vector<int> best_order;
-  for (int h = std::max(1, h0 / 2); h <= 2 * h0 + 1; h++) {
+  const int h_lo = std::max(1, h0 / 2), h_hi = 2 * h0 + 1;
+  const int h_step = std::max(1, (h_hi - h_lo + 23) / 24);   // at most 24 candidates
+  for (int h = h_lo; h <= h_hi; h += h_step) {
     std::vector<std::array<int, 4> > keyed(dim);
     for (int i = 0; i < dim; i++) {
       const int strip = rr[i] / h;
