@@ -109,7 +109,9 @@ int trvb_d2d(trvb_ctx* ctx, void* dst, const void* src, size_t bytes);
 /* ---- catalogue (replaces I/particles.hpp:63-90 on the device) ----------
  * Host (or device, if src_on_device) arrays of length n; `w` may be NULL
  * (unit weights), `los` is n x 3 row-major unit vectors or NULL
- * (I/dataobjs.hpp:186-188).  Positions must already be aligned in the box. */
+ * (I/dataobjs.hpp:186-188).  Positions must already be aligned in the box.
+ * src_on_device == 2 BORROWS the device arrays x, y, z instead of copying them:
+ * the caller keeps them alive and unchanged until trvb_cat_destroy. */
 int trvb_cat_create(trvb_ctx* ctx, trvb_cat** cat, long long n,
                     const double* x, const double* y, const double* z,
                     const double* w, const double* los, int src_on_device);

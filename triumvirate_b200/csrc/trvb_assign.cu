@@ -1317,12 +1317,19 @@ extern "C" int trvb_cat_create(trvb_ctx* ctx, trvb_cat** out, long long n,
   cat->owner = ctx; cat->n = n;
   const size_t nb = sizeof(double) * (size_t)n;
   const cudaMemcpyKind kind = src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->x, nb));
-  TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->y, nb));
-  TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->z, nb));
-  TRVB_CUDA(cudaMemcpyAsync(cat->x, x, nb, kind, ctx->stream));
-  TRVB_CUDA(cudaMemcpyAsync(cat->y, y, nb, kind, ctx->stream));
-  TRVB_CUDA(cudaMemcpyAsync(cat->z, z, nb, kind, ctx->stream));
+  if (src_on_device == 2) {
+    // Borrowed: the caller keeps the coordinate arrays alive and unchanged for the
+    // life of the catalogue (one estimator call); no copy, never freed here.
+    cat->x = const_cast<double*>(x); cat->y = const_cast<double*>(y); cat->z = const_cast<double*>(z);
+    cat->borrowed_xyz = true;
+  } else {
+    TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->x, nb));
+    TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->y, nb));
+    TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->z, nb));
+    TRVB_CUDA(cudaMemcpyAsync(cat->x, x, nb, kind, ctx->stream));
+    TRVB_CUDA(cudaMemcpyAsync(cat->y, y, nb, kind, ctx->stream));
+    TRVB_CUDA(cudaMemcpyAsync(cat->z, z, nb, kind, ctx->stream));
+  }
   if (w) {
     TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->w, nb));
     TRVB_CUDA(cudaMemcpyAsync(cat->w, w, nb, kind, ctx->stream));
@@ -1601,7 +1608,9 @@ extern "C" void trvb_cat_destroy(trvb_cat* cat) {
   if (!cat) return;
   if (cat->owner) cudaSetDevice(cat->owner->device);
   trvb_ctx* o = cat->owner;
-  trvb_dev_free_raw(o, cat->x); trvb_dev_free_raw(o, cat->y); trvb_dev_free_raw(o, cat->z);
+  if (!cat->borrowed_xyz) {
+    trvb_dev_free_raw(o, cat->x); trvb_dev_free_raw(o, cat->y); trvb_dev_free_raw(o, cat->z);
+  }
   trvb_dev_free_raw(o, cat->w); trvb_dev_free_raw(o, cat->los); trvb_dev_free_raw(o, cat->cw);
   trvb_dev_free_raw(o, cat->order); trvb_dev_free_raw(o, cat->cell_start);
   trvb_dev_free_raw(o, cat->s4); trvb_dev_free_raw(o, cat->slos); trvb_dev_free_raw(o, cat->scw);

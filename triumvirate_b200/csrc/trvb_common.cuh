@@ -115,6 +115,7 @@ struct trvb_cat {
   trvb_ctx* owner = nullptr;   // context that owns the allocations (device)
   long long n = 0;
   double* x = nullptr; double* y = nullptr; double* z = nullptr;
+  bool borrowed_xyz = false;   // x, y, z are the caller's device arrays (not freed here)
   double* w = nullptr;         // nullptr -> unit weights
   double* los = nullptr;       // SoA: lx[n], ly[n], lz[n] or nullptr
   double* cw = nullptr;        // custom complex weights (interleaved) or nullptr

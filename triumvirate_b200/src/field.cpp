@@ -111,7 +111,8 @@ Catalogue::Catalogue(std::shared_ptr<trvb_ctx> ctx, ParticleCatalogue& particles
 Catalogue::Catalogue(std::shared_ptr<trvb_ctx> ctx, long long n, const double* x,
                      const double* y, const double* z, const double* w,
                      const double* los, bool on_device) : ctx_(ctx) {
-  check(trvb_cat_create(ctx_.get(), &cat_, n, x, y, z, w, los, on_device ? 1 : 0),
+  // Device arrays are borrowed for the life of this catalogue (one estimator call).
+  check(trvb_cat_create(ctx_.get(), &cat_, n, x, y, z, w, los, on_device ? 2 : 0),
         "trvb_cat_create");
 }
 
