@@ -196,9 +196,9 @@ def test_assignment_bit_exact(core, oracle, assignment, clustered):
 @pytest.mark.parametrize("ngrid", [(4, 4, 4), (16, 8, 24), (35, 19, 11), (50, 36, 20), (64, 64, 64), (96, 40, 24)])
 @pytest.mark.parametrize("complex_weights", [False, True])
 def test_throughput_assignment_tiles(core, oracle, assignment, ngrid, complex_weights, monkeypatch):
-    """Both throughput kernels -- the default warp-cooperative scatter
-    (k_assign_coop) and the opt-in tile-owned shared-memory accumulation
-    (k_assign_tile, TRV_ASSIGN_TILE=1) -- on grids that are smaller than a tile,
+    """The throughput kernels -- the default warp-cooperative scatter (k_assign_coop),
+    the opt-in tile-owned shared-memory accumulation (k_assign_tile, TRV_ASSIGN_TILE=1)
+    and the opt-in column-owned accumulation (k_assign_col, TRV_ASSIGN_COL=1) -- on grids that are smaller than a tile,
     not multiples of the tile and anisotropic, with clustered positions and with
     positions ON or BEYOND the box edge (the reference applies no wrap in
     assignment, only the `0 <= gid < nmesh` guard, S/field.cpp:1042): equal to the
@@ -225,6 +225,11 @@ def test_throughput_assignment_tiles(core, oracle, assignment, ngrid, complex_we
     monkeypatch.setenv("TRV_ASSIGN_TILE", "1")
     tile = core.mesh(pos, L, ngrid, assignment, stage=0, weights=w)
     assert np.max(np.abs(tile - ref)) <= 1.e-13 * scale
+    monkeypatch.delenv("TRV_ASSIGN_TILE")
+    # column-owned accumulation (k_assign_col, opt-in)
+    monkeypatch.setenv("TRV_ASSIGN_COL", "1")
+    col = core.mesh(pos, L, ngrid, assignment, stage=0, weights=w)
+    assert np.max(np.abs(col - ref)) <= 1.e-13 * scale
 
 
 @pytest.mark.parametrize("assignment", ["cic", "pcs"])

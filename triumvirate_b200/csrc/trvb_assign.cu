@@ -764,6 +764,150 @@ k_assign_tile(SortedView c, const int* __restrict__ key_start, int nt1, int nt2,
 }
 
 // ---------------------------------------------------------------------
+// Column-owned shared-memory accumulation (TSC/PCS, unshifted mesh, DENSE catalogues).
+// ---------------------------------------------------------------------
+// A warp owns one sort key = one 4x4x8-cell column: it accumulates the column's particles
+// into its footprint (7 x 7 x 11 cells) in shared memory with plain LDS/DADD/STS -- one
+// particle per instruction group, lanes = (stencil row, z-cell) exactly as in
+// k_assign_coop -- and flushes the footprint with one RED per non-zero cell.  No block
+// barriers, no colouring, 5-10 KB of shared memory per warp.  REDs per particle drop from
+// 28 sectors to 539 / (particles in the column).  Opt-in (TRV_ASSIGN_COL=1): even on
+// well-filled columns (the 5e7 randoms of BASELINE config 3, ~220 per occupied column) the
+// serial LDS -> DADD -> STS chain per particle makes it slower than the direct scatter.
+constexpr int COLF_X = COL_W + 3, COLF_Y = COL_W + 3, COLF_Z = TILE_Z + 3;   // 7 x 7 x 11
+constexpr int COL_ROW = 12;                       // z pitch (doubles or cells)
+constexpr int COL_PLANE = COLF_Y * COL_ROW + 1;   // 85: rows of a stencil spread over the banks
+constexpr int COL_CELLS = COLF_X * COL_PLANE;     // 595 cells per warp tile
+constexpr int COL_WARPS = 4;
+
+template <int ORDER, bool COMPLEX>
+constexpr size_t col_smem_bytes() {
+  return (size_t)COL_WARPS * (sizeof(double) * COL_CELLS * (COMPLEX ? 2 : 1)
+                              + sizeof(double) * 32 * 3 * ORDER + sizeof(int) * 32 * 3 * ORDER
+                              + sizeof(double) * 32 * 2);
+}
+
+template <int ORDER, bool COMPLEX>
+__global__ void __launch_bounds__(COL_WARPS * 32)
+k_assign_col(SortedView c, const int* __restrict__ key_start, long long nkeys, int nt1, int nt2,
+             GridDesc g, int kind, YlmCoef yc, double scale, double* __restrict__ mesh) {
+  constexpr int CW = COMPLEX ? 2 : 1;
+  constexpr int LPR = ORDER * CW;                     // lanes per stencil row
+  constexpr int RPP = 32 / LPR;                       // rows per instruction
+  constexpr int NROW = ORDER * ORDER;
+  constexpr int NPASS = (NROW + RPP - 1) / RPP;
+  extern __shared__ __align__(16) unsigned char col_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* tile = reinterpret_cast<double*>(col_smem) + (size_t)warp * COL_CELLS * CW;
+  double* s_win = reinterpret_cast<double*>(col_smem) + (size_t)COL_WARPS * COL_CELLS * CW
+    + (size_t)warp * 32 * 3 * ORDER;
+  double* s_wt = reinterpret_cast<double*>(col_smem) + (size_t)COL_WARPS * COL_CELLS * CW
+    + (size_t)COL_WARPS * 32 * 3 * ORDER + (size_t)warp * 32 * 2;
+  int* s_idx = reinterpret_cast<int*>(reinterpret_cast<double*>(col_smem)
+    + (size_t)COL_WARPS * COL_CELLS * CW + (size_t)COL_WARPS * 32 * 3 * ORDER
+    + (size_t)COL_WARPS * 32 * 2) + (size_t)warp * 32 * 3 * ORDER;
+  const int r = lane / LPR, q = lane - r * LPR;
+  const int cz = COMPLEX ? (q >> 1) : q;
+  const int comp = COMPLEX ? (q & 1) : 0;
+
+  for (long long key = (long long)blockIdx.x * COL_WARPS + warp; key < nkeys;
+       key += (long long)gridDim.x * COL_WARPS) {
+    const int seg_b = key_start[key], seg_e = key_start[key + 1];
+    if (seg_b == seg_e) continue;                      // warp-uniform
+    // key = tile * KEYS_PER_TILE + cx * COLS_Y + cy (sort_key)
+    const int col = (int)(key % KEYS_PER_TILE);
+    const long long tl = key / KEYS_PER_TILE;
+    const int tk = (int)(tl % nt2), tj = (int)((tl / nt2) % nt1), ti = (int)(tl / ((long long)nt2 * nt1));
+    const int o0 = ti * TILE_X + (col / COLS_Y) * COL_W - 1;
+    const int o1 = tj * TILE_Y + (col % COLS_Y) * COL_W - 1;
+    const int o2 = tk * TILE_Z - 1;
+    __syncwarp();
+    for (int t = lane; t < COL_CELLS * CW; t += 32) tile[t] = 0.;
+    for (int base = seg_b; base < seg_e; base += 32) {
+      const int i = base + lane;
+      __syncwarp();
+      if (i < seg_e) {
+        int ijk[ORDER]; double win[ORDER];
+        const double4 p = c.p4[i];
+        bool ok = true;
+        window_1d<ORDER>(p.x, g.n[0], ijk, win);
+#pragma unroll
+        for (int t = 0; t < ORDER; t++) {
+          const int l = local_index(ijk[t], o0, g.n[0], COLF_X);
+          ok = ok && l >= 0; s_win[lane * 3 * ORDER + t] = win[t]; s_idx[lane * 3 * ORDER + t] = l;
+        }
+        window_1d<ORDER>(p.y, g.n[1], ijk, win);
+#pragma unroll
+        for (int t = 0; t < ORDER; t++) {
+          const int l = local_index(ijk[t], o1, g.n[1], COLF_Y);
+          ok = ok && l >= 0; s_win[lane * 3 * ORDER + ORDER + t] = win[t]; s_idx[lane * 3 * ORDER + ORDER + t] = l;
+        }
+        window_1d<ORDER>(p.z, g.n[2], ijk, win);
+#pragma unroll
+        for (int t = 0; t < ORDER; t++) {
+          const int l = local_index(ijk[t], o2, g.n[2], COLF_Z);
+          ok = ok && l >= 0; s_win[lane * 3 * ORDER + 2 * ORDER + t] = win[t]; s_idx[lane * 3 * ORDER + 2 * ORDER + t] = l;
+        }
+        const cplx wt = particle_weight(c, i, p, kind, yc);
+        double bre = __dmul_rn(scale, wt.re), bim = __dmul_rn(scale, wt.im);
+        if (!ok) {
+          // Position outside [0, L): the reference's index arithmetic and bounds guard,
+          // straight to global memory; nothing for the tile.
+          scatter_one<ORDER, COMPLEX>(p, bre, COMPLEX ? bim : 0., g, mesh);
+          bre = 0.; bim = 0.;
+#pragma unroll
+          for (int t = 0; t < 3 * ORDER; t++) s_idx[lane * 3 * ORDER + t] = 0;
+        }
+        s_wt[lane * 2] = bre; s_wt[lane * 2 + 1] = bim;
+      }
+      __syncwarp();
+      const int count = min(32, seg_e - base);
+      for (int sdx = 0; sdx < count; sdx++) {
+        if (r < RPP) {
+          const double* w = s_win + sdx * 3 * ORDER;
+          const int* id = s_idx + sdx * 3 * ORDER;
+          const double bw = s_wt[sdx * 2 + comp];
+          const double wz = w[2 * ORDER + cz];
+          const int lz = id[2 * ORDER + cz];
+#pragma unroll
+          for (int pass = 0; pass < NPASS; pass++) {
+            const int row = r + RPP * pass;
+            if (row < NROW) {
+              const int a = row / ORDER, b = row - a * ORDER;
+              const int cell = id[a] * COL_PLANE + id[ORDER + b] * COL_ROW + lz;
+              const double v = __dmul_rn(__dmul_rn(__dmul_rn(bw, w[a]), w[ORDER + b]), wz);
+              tile[cell * CW + comp] += v;
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    // Flush the footprint: lanes over (ly, lz), planes along x.
+    for (int pq = lane; pq < COLF_Y * COLF_Z; pq += 32) {
+      const int ly = pq / COLF_Z, lz = pq - ly * COLF_Z;
+      int gy = o1 + ly, gz = o2 + lz;
+      gy += (gy < 0) ? g.n[1] : 0; gy -= (gy >= g.n[1]) ? g.n[1] : 0;
+      gz += (gz < 0) ? g.n[2] : 0; gz -= (gz >= g.n[2]) ? g.n[2] : 0;
+#pragma unroll
+      for (int lx = 0; lx < COLF_X; lx++) {
+        int gx = o0 + lx;
+        gx += (gx < 0) ? g.n[0] : 0; gx -= (gx >= g.n[0]) ? g.n[0] : 0;
+        const int cell = lx * COL_PLANE + ly * COL_ROW + lz;
+        const long long gid = ((long long)gx * g.n[1] + gy) * g.n[2] + gz;
+        const double vre = tile[cell * CW];
+        if (COMPLEX) {
+          const double vim = tile[cell * CW + 1];
+          if (vre != 0. || vim != 0.) { atomicAdd(&mesh[2 * gid], vre); atomicAdd(&mesh[2 * gid + 1], vim); }
+        } else if (vre != 0.) {
+          atomicAdd(&mesh[gid], vre);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------
 // Deterministic assignment: one thread per output cell, ordered gather.
 // ---------------------------------------------------------------------
 
@@ -1238,7 +1382,35 @@ int launch_assign(trvb_ctx* ctx, trvb_cat* cat, int kind, int L, int M, double s
     // The tile kernel needs the mesh to be at least one footprint wide (no
     // self-overlap of a tile's periodic footprint).
     const bool fits = g.n[0] >= FP_X && g.n[1] >= FP_Y && g.n[2] >= FP_Z;
-    if (ORDER >= 3 && !shifted && use_tile && fits) {
+    // Column-owned accumulation (TRV_ASSIGN_COL=1).  Measured on the 5e7 randoms of config 3
+    // (~220 particles per occupied column, complex TSC meshes) it is SLOWER than the
+    // cooperative scatter (fields_LM 58.7 vs 47.5 ms): the per-particle LDS -> DADD -> STS
+    // chain is latency bound at 12-20 warps per SM, like the tile-owned variant.  Opt-in.
+    const char* env_col = getenv("TRV_ASSIGN_COL");
+    const long long nkeys_col = (long long)((g.n[0] + TILE_X - 1) / TILE_X)
+      * ((g.n[1] + TILE_Y - 1) / TILE_Y) * ((g.n[2] + TILE_Z - 1) / TILE_Z) * KEYS_PER_TILE;
+    const bool use_col = ORDER >= 3 && !shifted && !use_tile && !cat->chunked && cat->cell_start
+      && g.n[0] >= COLF_X && g.n[1] >= COLF_Y && g.n[2] >= COLF_Z
+      && env_col != nullptr && env_col[0] == '1';
+    if (use_col) {
+      constexpr int O = ORDER >= 3 ? ORDER : 3;
+      const int nt1 = (g.n[1] + TILE_Y - 1) / TILE_Y, nt2 = (g.n[2] + TILE_Z - 1) / TILE_Z;
+      const int blocks = (int)std::min<long long>(div_up(nkeys_col, COL_WARPS),
+                                                  (long long)ctx->num_sms * 32);
+      if (cplx_mesh) {
+        TRVB_CUDA(cudaFuncSetAttribute(k_assign_col<O, true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)col_smem_bytes<O, true>()));
+        k_assign_col<O, true><<<blocks, COL_WARPS * 32, col_smem_bytes<O, true>(), ctx->stream>>>(
+          cv, cat->cell_start, nkeys_col, nt1, nt2, g, kind, yc, s, (double*)mesh.data);
+      } else {
+        TRVB_CUDA(cudaFuncSetAttribute(k_assign_col<O, false>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)col_smem_bytes<O, false>()));
+        k_assign_col<O, false><<<blocks, COL_WARPS * 32, col_smem_bytes<O, false>(), ctx->stream>>>(
+          cv, cat->cell_start, nkeys_col, nt1, nt2, g, kind, yc, s, (double*)mesh.data);
+      }
+    } else if (ORDER >= 3 && !shifted && use_tile && fits) {
       constexpr int O = ORDER >= 3 ? ORDER : 3;
       const int nt[3] = {(g.n[0] + TILE_X - 1) / TILE_X, (g.n[1] + TILE_Y - 1) / TILE_Y,
                          (g.n[2] + TILE_Z - 1) / TILE_Z};
