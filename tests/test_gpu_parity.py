@@ -693,3 +693,36 @@ def test_anisotropic_box_against_oracle(core, oracle, stat, degrees, form, assig
             scale = max(np.abs(shot_ref).max(), np.abs(ref["pk_raw"]).max())
             assert np.max(np.abs(shot_out - shot_ref)) <= RTOL * scale
     _assert_close(out, ref, label=f"{stat}{degrees}: ")
+
+
+@pytest.mark.parametrize("stat,rng", [("bispec", (0.001, 0.02)), ("3pcf", (5., 45.)),
+                                      ("powspec", (0.001, 0.02)), ("2pcf", (5., 45.))])
+def test_empty_bins_follow_the_reference(core, oracle, stat, rng):
+    """Bins narrower than the mode / separation spacing hold no modes or pairs: counts are
+    zero, the effective coordinate is the bin centre and the statistics follow the
+    reference (zeros, or the non-finite values its division by a zero count produces)."""
+    gen = np.random.default_rng(3)
+    L, ng = 1000., 32
+    pos = gen.uniform(0., L, size=(3, 3000))
+    if stat in ("bispec", "3pcf"):
+        kw = dict(boxsize=L, ngrid=ng, assignment="tsc", degrees=(0, 0, 0), form="diag",
+                  bin_range=rng, num_bins=10, norm_factor=1., pos_d=pos)
+        ref, out = oracle.threept(stat, "sim", **kw), core.threept(stat, "sim", **kw)
+        counts = "nmodes_1" if stat == "bispec" else "npairs_1"
+    else:
+        kw = dict(boxsize=L, ngrid=ng, assignment="tsc", degree=0, bin_range=rng, num_bins=10,
+                  norm_factor=1., pos_d=pos, nz_d=np.full(3000, 3.e-6))
+        ref, out = oracle.twopt(stat, "sim", **kw), core.twopt(stat, "sim", **kw)
+        counts = "nmodes" if stat == "powspec" else "npairs"
+    assert (ref[counts] == 0).any(), "the case must contain empty bins"
+    for k in ref:
+        if k == "elapsed_s":
+            continue
+        a, b = np.asarray(out[k]), np.asarray(ref[k])
+        if np.issubdtype(b.dtype, np.integer):
+            assert np.array_equal(a, b), k
+        else:
+            fin = np.isfinite(b.view(np.float64).reshape(len(b), -1)).all(axis=1)
+            assert np.array_equal(np.isfinite(a.view(np.float64).reshape(len(a), -1)).all(axis=1), fin), k
+            scale = np.abs(b[fin]).max() if fin.any() else 1.
+            assert np.max(np.abs(a[fin] - b[fin]), initial=0.) <= 1.e-8 * max(scale, 1.e-300), k

@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <array>
 #include <cmath>
+#include <limits>
 #include <map>
 #include <memory>
 #include <set>
@@ -965,6 +966,22 @@ trv::BispecMeasurements bispec_impl(
     if (trvs::currTask == 0) {
       trvs::logger.stat("Bispectrum term computed at orders (m1, m2, M) = +/-(%d, %d, %d).",
                         t.m1, t.m2, t.M);
+    }
+  }
+
+  // Bins without modes: the reference divides the shell field and its effective
+  // wavenumber by a zero mode count (S/field.cpp:1895-1905), so every entry that
+  // touches such a bin comes out as NaN there -- reproduced (by the entry's owner,
+  // so that the sum over ranks stays NaN) rather than returned as a silent zero.
+  {
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    for (int i = 0; i < dv.dim; i++) {
+      const bool empty_row = nmodes[dv.row[i]] == 0, empty_col = nmodes[dv.col[i]] == 0;
+      if (empty_row) k1eff[i] = nan;
+      if (empty_col) k2eff[i] = nan;
+      if (!(empty_row || empty_col)) continue;
+      if (active[i]) bk_dv[i] = cdouble(nan, nan);
+      if (shot_active[i]) sn_dv[i] = cdouble(nan, nan);
     }
   }
 
