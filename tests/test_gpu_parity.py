@@ -726,3 +726,44 @@ def test_empty_bins_follow_the_reference(core, oracle, stat, rng):
             assert np.array_equal(np.isfinite(a.view(np.float64).reshape(len(a), -1)).all(axis=1), fin), k
             scale = np.abs(b[fin]).max() if fin.any() else 1.
             assert np.max(np.abs(a[fin] - b[fin]), initial=0.) <= 1.e-8 * max(scale, 1.e-300), k
+
+
+@pytest.mark.parametrize("case", ["one_particle", "tiny_grid", "outside_box", "signed_weights"])
+def test_degenerate_inputs_against_oracle(core, oracle, case):
+    """Inputs at the edge of the domain: a single particle, an 8^3 mesh (smaller than every
+    tile / footprint of the assignment kernels), positions outside [0, L) (the reference
+    does not wrap in assignment, S/field.cpp:1042), weights of both signs."""
+    gen = np.random.default_rng(81)
+    L, ng, n = 400., 16, 500
+    kw = dict(assignment="pcs", degrees=(0, 0, 0), form="diag", bin_range=(0.03, 0.11),
+              num_bins=4, norm_factor=1.)
+    extra = {}
+    pos = gen.uniform(0., L, size=(3, n))
+    if case == "one_particle":
+        pos = pos[:, :1]
+    elif case == "tiny_grid":
+        ng = 8
+        kw["bin_range"] = (0.02, 0.06)
+    elif case == "outside_box":
+        pos[:, :40] += gen.normal(0., 0.02 * L, size=(3, 40)) + np.array([[L], [0.], [-L]]) * 0.02
+        pos[0, :5] = L * (1. + 1.e-12)
+        pos[2, 5:10] = -1.e-9
+    elif case == "signed_weights":
+        extra = dict(ws_d=gen.normal(size=n), wc_d=gen.uniform(0.5, 2., n), nz_d=np.full(n, 1.e-5))
+    for stat in ("bispec", "3pcf"):
+        kws = dict(kw, boxsize=L, ngrid=ng, pos_d=pos, **extra)
+        if stat == "3pcf":
+            kws["bin_range"] = (30., 150.)
+        ref = oracle.threept(stat, "sim", **kws)
+        out = core.threept(stat, "sim", **kws)
+        for k in ref:
+            if k == "elapsed_s":
+                continue
+            a, b = np.asarray(out[k]), np.asarray(ref[k])
+            if np.issubdtype(b.dtype, np.integer):
+                assert np.array_equal(a, b), (stat, k)
+            else:
+                fin = np.isfinite(b.view(np.float64).reshape(len(b), -1)).all(axis=1)
+                assert np.array_equal(np.isfinite(a.view(np.float64).reshape(len(a), -1)).all(axis=1), fin), (stat, k)
+                scale = np.abs(b[fin]).max() if fin.any() else 0.
+                assert np.max(np.abs(a[fin] - b[fin]), initial=0.) <= 1.e-8 * scale + 1.e-300, (stat, k)
