@@ -767,3 +767,24 @@ def test_degenerate_inputs_against_oracle(core, oracle, case):
                 assert np.array_equal(np.isfinite(a.view(np.float64).reshape(len(a), -1)).all(axis=1), fin), (stat, k)
                 scale = np.abs(b[fin]).max() if fin.any() else 0.
                 assert np.max(np.abs(a[fin] - b[fin]), initial=0.) <= 1.e-8 * scale + 1.e-300, (stat, k)
+
+
+@pytest.mark.parametrize("stat,degrees", [("bispec", (2, 0, 2)), ("3pcf", (0, 0, 0))])
+def test_deterministic_mode_is_bit_reproducible_for_survey_catalogues(core, stat, degrees):
+    """deterministic=True: identical bits from call to call for paired survey catalogues
+    too (ordered assignment, fixed-order reductions, and catalogue weight totals -- hence
+    alpha -- summed in fixed chunks rather than by an OpenMP reduction)."""
+    from triumvirate_b200 import catalogue as tcat
+    L, ng = 1000., 32
+    pd_, pr_, nzd, nzr, wsd, wsr, wcd, wcr = _survey_inputs(77, 70000, 200000, L)
+    pd_c, pr_c = tcat.centre(pd_, pr_, L)
+    rng = (0.01, 0.09) if stat == "bispec" else (40., 280.)
+    kw = dict(boxsize=L, ngrid=ng, assignment="tsc", degrees=degrees, form="diag", bin_range=rng,
+              num_bins=4, norm_factor=1., pos_d=pd_c, nz_d=nzd, ws_d=wsd, wc_d=wcd,
+              los_d=tcat.compute_los(pd_), pos_r=pr_c, nz_r=nzr, ws_r=wsr, wc_r=wcr,
+              los_r=tcat.compute_los(pr_), deterministic=True)
+    outs = [core.threept(stat, "survey", **kw) for _ in range(4)]
+    for o in outs[1:]:
+        for k in o:
+            if k != "elapsed_s":
+                assert np.array_equal(o[k], outs[0][k]), k

@@ -2,7 +2,9 @@
 // reference's public members and alignment helpers (S/particles.cpp:512-888).
 #include "trv/particles.hpp"
 
+#include <algorithm>
 #include <cmath>
+#include <vector>
 
 namespace trvs = trv::sys;
 
@@ -102,12 +104,26 @@ int ParticleCatalogue::load_particle_arrays(
 
 void ParticleCatalogue::calc_total_weights() {
   require_data(*this);
-  double wt = 0., wst = 0.;
-#pragma omp parallel for reduction(+:wt, wst)
-  for (int pid = 0; pid < this->ntotal; pid++) {
-    wt += this->pdata[pid].w;
-    wst += this->pdata[pid].ws;
+  // Fixed chunks summed in parallel, chunk sums added in order: the totals (and the
+  // alpha contrast derived from them) are the same bits whatever the thread count or
+  // schedule -- an OpenMP `reduction` (S/particles.cpp:578-591) combines in an
+  // unspecified order, which made survey statistics differ in the last bit from call
+  // to call.
+  const int chunk = 1 << 16;
+  const int nchunks = (this->ntotal + chunk - 1) / chunk;
+  std::vector<double> part_w(nchunks, 0.), part_ws(nchunks, 0.);
+#pragma omp parallel for schedule(static)
+  for (int c = 0; c < nchunks; c++) {
+    const int lo = c * chunk, hi = std::min(this->ntotal, lo + chunk);
+    double wt = 0., wst = 0.;
+    for (int pid = lo; pid < hi; pid++) {
+      wt += this->pdata[pid].w;
+      wst += this->pdata[pid].ws;
+    }
+    part_w[c] = wt; part_ws[c] = wst;
   }
+  double wt = 0., wst = 0.;
+  for (int c = 0; c < nchunks; c++) { wt += part_w[c]; wst += part_ws[c]; }
   this->wtotal = wt;
   this->wstotal = wst;
 }
