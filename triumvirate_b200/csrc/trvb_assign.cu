@@ -670,7 +670,8 @@ k_assign_tile(SortedView c, const int* __restrict__ key_start, int nt1, int nt2,
 #pragma unroll
         for (int t = 0; t < ORDER; t++) {
           s.x[t] = make_double2(wx[t], __hiloint2double(zoff, ok ? (lx0 + t) * G::PLANE : 0));
-          s.y[t] = make_double2(wy[t], __hiloint2double(0, ok ? (ly0 + t) * G::ROW : 0));
+          // high word: 1 marks a particle that contributes nothing to the tile
+          s.y[t] = make_double2(wy[t], __hiloint2double(ok ? 0 : 1, ok ? (ly0 + t) * G::ROW : 0));
         }
         double zr[4], zi[4];
 #pragma unroll
@@ -696,7 +697,9 @@ k_assign_tile(SortedView c, const int* __restrict__ key_start, int nt1, int nt2,
 #pragma unroll
       for (int t = 0; t < (COMPLEX ? 4 : 2); t++) Z[t] = sp->zp[t];
       for (int sdx = 0; sdx < steps; sdx++) {
-        const bool live = row_active && sdx < cnt;
+        // Idle rows / steps and particles outside the box touch no memory at all (a dummy
+        // zero-add to a real cell could lose another warp's update to it).
+        const bool live = row_active && sdx < cnt && __double2hiint(Y.y) == 0;
         const double wxy = live ? X.x * Y.x : 0.;
         double* cell = tile
           + (live ? __double2loint(X.y) + __double2loint(Y.y) + __double2hiint(X.y) : scratch_off);
@@ -706,7 +709,9 @@ k_assign_tile(SortedView c, const int* __restrict__ key_start, int nt1, int nt2,
         if constexpr (COMPLEX) {
           double2 v[ORDER];
 #pragma unroll
-          for (int t = 0; t < ORDER; t++) v[t] = reinterpret_cast<const double2*>(cell)[t];
+          for (int t = 0; t < ORDER; t++) {
+            v[t] = live ? reinterpret_cast<const double2*>(cell)[t] : make_double2(0., 0.);
+          }
           // next particle's staging (slots past the column's end hold stale, masked data)
           sp = st + h * 16 + min(sdx + 1, 15);
           X = sp->x[ra]; Y = sp->y[rb];
@@ -716,18 +721,18 @@ k_assign_tile(SortedView c, const int* __restrict__ key_start, int nt1, int nt2,
           for (int t = 0; t < ORDER; t++) {
             v[t].x = fma(wxy, Zc[t].x, v[t].x);
             v[t].y = fma(wxy, Zc[t].y, v[t].y);
-            reinterpret_cast<double2*>(cell)[t] = v[t];
+            if (live) reinterpret_cast<double2*>(cell)[t] = v[t];
           }
         } else {
           double v[ORDER];
 #pragma unroll
-          for (int t = 0; t < ORDER; t++) v[t] = cell[t];
+          for (int t = 0; t < ORDER; t++) v[t] = live ? cell[t] : 0.;
           sp = st + h * 16 + min(sdx + 1, 15);
           X = sp->x[ra]; Y = sp->y[rb];
           Z[0] = sp->zp[0]; Z[1] = sp->zp[1];
           const double zc[4] = {Zc[0].x, Zc[0].y, Zc[1].x, Zc[1].y};
 #pragma unroll
-          for (int t = 0; t < ORDER; t++) cell[t] = fma(wxy, zc[t], v[t]);
+          for (int t = 0; t < ORDER; t++) if (live) cell[t] = fma(wxy, zc[t], v[t]);
         }
         __syncwarp();
       }
@@ -856,7 +861,7 @@ k_assign_col(SortedView c, const int* __restrict__ key_start, long long nkeys, i
           scatter_one<ORDER, COMPLEX>(p, bre, COMPLEX ? bim : 0., g, mesh);
           bre = 0.; bim = 0.;
 #pragma unroll
-          for (int t = 0; t < 3 * ORDER; t++) s_idx[lane * 3 * ORDER + t] = 0;
+          for (int t = 0; t < 3 * ORDER; t++) s_idx[lane * 3 * ORDER + t] = -1;   // skipped below
         }
         s_wt[lane * 2] = bre; s_wt[lane * 2 + 1] = bim;
       }
@@ -872,7 +877,7 @@ k_assign_col(SortedView c, const int* __restrict__ key_start, long long nkeys, i
 #pragma unroll
           for (int pass = 0; pass < NPASS; pass++) {
             const int row = r + RPP * pass;
-            if (row < NROW) {
+            if (row < NROW && lz >= 0) {
               const int a = row / ORDER, b = row - a * ORDER;
               const int cell = id[a] * COL_PLANE + id[ORDER + b] * COL_ROW + lz;
               const double v = __dmul_rn(__dmul_rn(__dmul_rn(bw, w[a]), w[ORDER + b]), wz);
