@@ -19,14 +19,27 @@ Own arm (default):
   roofline  the dominant hand-written kernel (particle-to-mesh assignment)
           timed alone with CUDA events against the measured HBM copy bandwidth;
   cpu_baseline  the reference's own C++ (oracle/_ref) on this host's cores, on
-          a bounded sample (see `sample`), extrapolated to the full pair count.
+          a bounded sample (see `sample`), extrapolated to the full pair count;
+  parity_check  the data-vector entries of the bin pairs that the cpu_baseline
+          leg computed with the reference's code, compared with the entries the
+          GPU produced in the timed region (tolerance 1e-8, BASELINE.json);
+  result  SHA-256 of the result vector of one extra step in deterministic mode
+          (bit-identical for every N) and head/tail entries of the timed result.
 Multi-GPU (torchrun, one rank per GPU): the mesh is replicated, the bin pairs
-are dealt round-robin to the ranks and one small NCCL all-reduce sums the
+are dealt to the ranks in compact blocks and one small NCCL all-reduce sums the
 result vector; the problem size is fixed, so scaling is "strong".
 
 Reference arm (--impl reference): the reference's CPU implementation
-(oracle/_ref) timed on the host cores; each step is one bin-pair unit of the
-reference's loop, the value is setup + 210 x mean(step).
+(oracle/_ref) timed on the host cores with every host thread
+(TRV_REF_THREADS overrides; torchrun's OMP_NUM_THREADS=1 is not inherited).
+Each step is one MEASURED bin-pair unit of the reference's loop (`ms_per_step`
+is that measured time); `value` = measured setup + 210 x mean(step) is the
+full-job figure and is labelled extrapolated in `sample`.  When the time budget
+(TRV_REF_BUDGET_S, default 240 s) allows, one stock reference call is also
+measured in full -- trv::compute_bispec_in_gpp_box with form = diag (20 pairs,
+the configuration of the reference's JOSS paper) -- and reported under
+`measured_full_call`, next to the calibration of the FFTW stand-in against
+scipy.fft on the same host (`fft_calibration`).
 """
 import argparse
 import ctypes as C
@@ -112,6 +125,54 @@ def lognormal_catalogue(n, L, ngf=256, seed=69):
     return np.ascontiguousarray(np.stack([(i + gen.uniform(size=n)) * cell,
                                           (j + gen.uniform(size=n)) * cell,
                                           (k + gen.uniform(size=n)) * cell]))
+
+
+L2_POLICY = "inputs larger than L2 (240 MB catalogue, >=1 GB meshes); no flush needed"
+
+
+def config_of(args, wl):
+    """The `config` object: identical in both arms (the driver compares them)."""
+    return {"workload": wl["name"], "baseline_config": 5 if args.workload == "C5" else 2,
+            "particles": wl["n"], "ngrid": wl["ngrid"], "pairs": npairs_of(wl),
+            "l2_policy": L2_POLICY}
+
+
+def host_threads():
+    """Threads for the reference's OpenMP code: every host core, whatever
+    OMP_NUM_THREADS says (torch.distributed.run exports OMP_NUM_THREADS=1)."""
+    env = os.environ.get("TRV_REF_THREADS")
+    if env:
+        return max(1, int(env))
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def fft_calibration(ref, n=512):
+    """The FFTW stand-in of the oracle build against scipy's pocketfft on the same
+    host and thread count: one complex n^3 forward transform each."""
+    out = {"n": n, "threads": ref.num_threads()}
+    try:
+        out["shim_s"] = ref.fft_time(n, 2)
+    except Exception as exc:   # an older oracle/_ref without the entry point
+        out["shim_s"] = None
+        out["note"] = f"shim timing unavailable: {exc}"
+    try:
+        import scipy.fft
+        a = np.random.default_rng(0).standard_normal((n, n, n)).astype(np.complex128)
+        best = 1.e300
+        for _ in range(2):
+            t0 = time.perf_counter()
+            scipy.fft.fftn(a, workers=out["threads"], overwrite_x=False)
+            best = min(best, time.perf_counter() - t0)
+        out["scipy_fftn_s"] = best
+        if out.get("shim_s"):
+            out["shim_over_scipy"] = out["shim_s"] / best
+    except Exception as exc:
+        out["scipy_fftn_s"] = None
+        out["note"] = f"scipy timing unavailable: {exc}"
+    return out
 
 
 def make_catalogue(wl):
@@ -282,11 +343,12 @@ def run_b200(args):
         torch.cuda.current_stream().synchronize()   # the estimator enqueues on its own stream
         return gathered
 
-    def step(src, on_device):
+    def step(src, on_device, deterministic=False):
         if world > 1 and not on_device:
             src, on_device = upload_sharded(src), True
         out = core.threept_box_arrays("bispec", n, src[0].data_ptr(), src[1].data_ptr(),
-                                      src[2].data_ptr(), on_device, **kw)
+                                      src[2].data_ptr(), on_device, deterministic=deterministic,
+                                      **kw)
         if world > 1:
             # the single small exchange of the path: sum the partial result vectors
             buf = torch.from_numpy(np.concatenate([
@@ -355,30 +417,48 @@ def run_b200(args):
     sec_e2e, out_e2e = timed(host, False, args.steps)
     assert np.all(np.isfinite(out["bk_raw"].view(np.float64)))
 
+    # One extra step in deterministic mode (outside every timed region): its result
+    # vector is bit-identical from run to run and for every N, so its SHA-256 shows
+    # that the N = 1, 2, 4, 8 runs computed the same statistics.
+    import hashlib
+    out_det = step(dpos, True, deterministic=True)
+    vec_det = np.concatenate([out_det["bk_raw"].view(np.float64), out_det["bk_shot"].view(np.float64),
+                              out_det["k1_eff"], out_det["k2_eff"],
+                              out_det["nmodes_1"].astype(np.float64),
+                              out_det["nmodes_2"].astype(np.float64)])
+    vec = np.concatenate([out["bk_raw"].view(np.float64), out["bk_shot"].view(np.float64)])
+    dev_det = float(np.max(np.abs(vec - vec_det[:vec.size]) / np.maximum(np.abs(vec_det[:vec.size]), 1.e-300)))
+
     result = {
         "metric": "bispectrum time-to-solution", "value": sec / args.steps, "unit": "s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": 1.e3 * sec / args.steps, "higher_is_better": False,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {
-            "workload": wl["name"], "baseline_config": 5 if args.workload == "C5" else 2,
-            "particles": n, "ngrid": ng,
-            "pairs": dim, "parallelism": f"pairs/{world}gpu" if world > 1 else "1gpu",
-            "e2e_upload": ("1/N slice per rank from pinned host memory + NCCL all-gather"
-                           if world > 1 else "pinned host -> device"),
-            "l2_policy": "inputs larger than L2 (240 MB catalogue, >=1 GB meshes); no flush needed",
-        },
+        "config": config_of(args, wl),
+        "run": {"parallelism": f"pairs/{world}gpu" if world > 1 else "1gpu",
+                "e2e_upload": ("1/N slice per rank from pinned host memory + NCCL all-gather"
+                               if world > 1 else "pinned host -> device")},
         "clocks": clocks,
         "e2e": {"value": sec_e2e / args.steps, "unit": "s",
                 "h2d_bytes_per_step": int(3 * 8 * n),
                 "d2h_bytes_per_step": int(dim * (4 * 8 + 2 * 4 + 4 * 8))},
         "gpu_launches": launches, "cufft_execs": fft_execs,
+        "result": {
+            "sha256_deterministic_step": hashlib.sha256(vec_det.tobytes()).hexdigest(),
+            "timed_vs_deterministic_max_rel": dev_det,
+            "bk_raw_first": [float(out["bk_raw"][0].real), float(out["bk_raw"][0].imag)],
+            "bk_raw_last": [float(out["bk_raw"][-1].real), float(out["bk_raw"][-1].imag)],
+            "bk_shot_first": [float(out["bk_shot"][0].real), float(out["bk_shot"][0].imag)],
+            "nmodes_first_last": [int(out["nmodes_1"][0]), int(out["nmodes_2"][-1])],
+        },
     }
 
     if rank == 0:
         result["roofline"], result["particles_per_s"] = assignment_roofline(torch, dev, dpos, wl)
         if world == 1 and not args.no_cpu_baseline:
-            result["cpu_baseline"] = cpu_baseline(wl, pos, pair_units=2)
+            base, check = cpu_baseline(wl, pos, out, out_e2e)
+            result["cpu_baseline"] = base
+            result["parity_check"] = check
         print(json.dumps(result), flush=True)
     if world > 1:
         dist.barrier()
@@ -456,30 +536,68 @@ def assignment_roofline(torch, dev, dpos, wl):
     return roof, n / t_sorted
 
 
-def cpu_baseline(wl, pos, pair_units):
-    """The reference's own C++ (oracle/_ref) on this host: setup once, then
-    `pair_units` bin-pair units; full job = setup + npairs x mean(unit)."""
+PARITY_TOL = 1.e-8   # BASELINE.json: relative tolerance against the reference's CPU code
+
+
+def parity_pairs(nb):
+    """Bin pairs the cpu_baseline leg runs through the reference's loop: first and
+    last bin, diagonal and off-diagonal."""
+    return [(0, 0), (nb - 1, nb - 1), (0, nb - 1), (nb // 3, (2 * nb) // 3)]
+
+
+def compare_entries(ent, idx, out):
+    """Largest deviation of the GPU's entries `out[...][idx]` from the reference's."""
+    def rel(a, b):
+        return float(np.max(np.abs(a - b) / np.abs(b)))
+    return {
+        "bk_raw": rel(out["bk_raw"][idx], ent["bk_raw"]),
+        "bk_shot": rel(out["bk_shot"][idx], ent["bk_shot"]),
+        "k_eff": max(rel(out["k1_eff"][idx], ent["k1_eff"]), rel(out["k2_eff"][idx], ent["k2_eff"])),
+        "nmodes_equal": bool(np.array_equal(out["nmodes_1"][idx], ent["nmodes_1"])
+                             and np.array_equal(out["nmodes_2"][idx], ent["nmodes_2"])),
+    }
+
+
+def cpu_baseline(wl, pos, out, out_e2e):
+    """The reference's own C++ (oracle/_ref) on this host: setup once, then the bin-pair
+    units of `parity_pairs`; full job = setup + npairs x mean(unit).  The entries those
+    units produce are the oracle's values for the same catalogue at the full mesh: they
+    are compared with what the GPU returned in the timed region (`parity_check`)."""
     from oracle import ref
     if not ref.available():
-        return {"value": None, "unit": "s", "kind": "reference", "cores": 0,
-                "sample": "oracle/_ref/libtrv_ref.so missing"}
+        return ({"value": None, "unit": "s", "kind": "reference", "cores": 0,
+                 "sample": "oracle/_ref/libtrv_ref.so missing"},
+                {"pairs": 0, "max_rel_err": None, "tol": PARITY_TOL, "passed": False,
+                 "note": "oracle/_ref/libtrv_ref.so missing"})
+    ref.set_num_threads(host_threads())
     cores = ref.num_threads()
-    t_setup = ref.bispec_setup(pos, wl["L"], wl["ngrid"], wl["assignment"], wl["bin_range"],
-                               wl["num_bins"])
-    units = []
     nb = wl["num_bins"]
-    for u in range(pair_units):
-        _, _, t = ref.bispec_pair(u % nb, (u + nb // 2) % nb)
-        units.append(t)
+    t_setup = ref.bispec_setup(pos, wl["L"], wl["ngrid"], wl["assignment"], wl["bin_range"], nb)
+    pairs = parity_pairs(nb)
+    ent = ref.bispec_entries(pairs, nb, wl["n"], 1.)
     ref.bispec_teardown()
+    units = ent["unit_s"]
     npairs = npairs_of(wl)
     value = t_setup + npairs * float(np.mean(units))
-    return {"value": value, "unit": "s", "cores": cores, "kind": "reference",
-            "sample": (f"reference C++ (oracle/_ref, OpenMP, shim FFT) on the same catalogue and "
-                       f"mesh: setup (dn_00, N_L0, G_00, y_lm tables) {t_setup:.2f} s measured once + "
-                       f"{pair_units} bin-pair units of its loop, mean {np.mean(units):.3f} s, "
-                       f"extrapolated to {npairs} pairs"),
-            "setup_s": t_setup, "pair_unit_s": float(np.mean(units))}
+    base = {"value": value, "unit": "s", "cores": cores, "kind": "reference",
+            "sample": (f"reference C++ (oracle/_ref, OpenMP on {cores} threads, shim FFT) on the same "
+                       f"catalogue and mesh: setup (dn_00, N_L0, G_00, y_lm tables) {t_setup:.2f} s "
+                       f"MEASURED once + {len(pairs)} bin-pair units of its loop MEASURED, mean "
+                       f"{np.mean(units):.3f} s; value EXTRAPOLATED to {npairs} pairs"),
+            "setup_s": t_setup, "pair_unit_s": float(np.mean(units)),
+            "measured_s": t_setup + float(np.sum(units))}
+    idx = np.array([ref.triu_index(a, b, nb) for a, b in pairs])
+    dev = compare_entries(ent, idx, out)
+    dev_e2e = compare_entries(ent, idx, out_e2e)
+    worst = max(dev["bk_raw"], dev["bk_shot"], dev_e2e["bk_raw"], dev_e2e["bk_shot"])
+    check = {"pairs": len(pairs), "bin_pairs": [list(p) for p in pairs],
+             "max_rel_err": worst, "tol": PARITY_TOL,
+             "passed": bool(worst <= PARITY_TOL and dev["nmodes_equal"] and dev_e2e["nmodes_equal"]
+                            and dev["k_eff"] <= 1.e-12 and dev_e2e["k_eff"] <= 1.e-12),
+             "device_resident_call": dev, "host_array_call": dev_e2e,
+             "against": "reference C++ loop body per bin pair at the full mesh (oracle/_ref: "
+                        "S/threept.cpp:1900-1968, 1981-2140)"}
+    return base, check
 
 
 # ---------------------------------------------------------------------------
@@ -495,36 +613,67 @@ def run_reference(args):
     if not ref.available() and not ref.build():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libtrv_ref.so not built"}))
         return
-    pos = make_catalogue(wl)
+    t_start = time.perf_counter()
+    budget = float(os.environ.get("TRV_REF_BUDGET_S", "240"))
+    ref.set_num_threads(host_threads())
     cores = ref.num_threads()
+    pos = make_catalogue(wl)
     nb = wl["num_bins"]
+    npairs = npairs_of(wl)
     t_setup = ref.bispec_setup(pos, wl["L"], wl["ngrid"], wl["assignment"], wl["bin_range"], nb)
     pairs = [(a, b) for a in range(nb) for b in range(a, nb)]
-    stride = max(1, len(pairs) // (args.warmup + args.steps))
-    units = []
-    for s in range(args.warmup + args.steps):
+    want = args.warmup + args.steps
+    stride = max(1, len(pairs) // want)
+    units, done = [], 0
+    for s in range(want):
         a, b = pairs[(s * stride) % len(pairs)]
         _, _, t = ref.bispec_pair(a, b)
+        done += 1
         if s >= args.warmup:
             units.append(t)
+        # never outrun the lease: stop sampling once the budget is spent (at least one
+        # timed unit is always taken)
+        if units and time.perf_counter() - t_start > budget:
+            break
     ref.bispec_teardown()
-    npairs = npairs_of(wl)
     unit = float(np.mean(units))
     value = t_setup + npairs * unit
-    sample = (f"each step = one bin-pair unit of the reference loop (2 band-limited IFFTs + triple "
-              f"product + per-bin shot-noise IFFT and reduction) at the full mesh; value = setup "
-              f"{t_setup:.2f} s + {npairs} x mean step {unit:.3f} s")
-    print(json.dumps({
+    steps_done = len(units)
+    sample = (f"MEASURED: setup {t_setup:.2f} s (dn_00, N_L0, G_00, y_lm tables) and {steps_done} "
+              f"bin-pair units of the reference loop at the full mesh (2 band-limited IFFTs + triple "
+              f"product + per-pair shot-noise IFFT and reduction), mean {unit:.3f} s = ms_per_step; "
+              f"EXTRAPOLATED: value = setup + {npairs} x mean unit")
+    line = {
         "impl": "reference", "metric": "bispectrum time-to-solution", "value": value, "unit": "s",
-        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1.e3 * value, "higher_is_better": False, "scaling": "strong",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps_done, "warmup": args.warmup,
+        "ms_per_step": 1.e3 * unit, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["name"], "baseline_config": 2, "particles": wl["n"],
-                   "ngrid": wl["ngrid"], "pairs": npairs},
+        "config": config_of(args, wl),
         "cpu_baseline": {"value": value, "unit": "s", "cores": cores, "kind": "reference",
-                         "sample": sample},
+                         "sample": sample, "setup_s": t_setup, "pair_unit_s": unit,
+                         "measured_s": t_setup + float(np.sum(units)), "extrapolated": True},
         "e2e": {"value": value, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    }
+    # One stock call measured in full, when it fits: the `diag` form (nb pairs) costs about
+    # setup + nb units.
+    est_full = 1.3 * (t_setup + nb * unit)
+    left = budget - (time.perf_counter() - t_start)
+    if wl["ngrid"] <= 512 and left > est_full:
+        full = ref.threept("bispec", "sim", pos, wl["L"], wl["ngrid"], wl["assignment"],
+                           wl["degrees"], "diag", wl["bin_range"], nb, 1.)
+        line["measured_full_call"] = {
+            "what": f"trv::compute_bispec_in_gpp_box, form = diag ({nb} pairs), same catalogue and mesh, "
+                    f"entry to result, {cores} threads (the reference's JOSS configuration: 59 s on 32 "
+                    f"threads with FFTW, publication/joss/paper.md:269)",
+            "seconds": full["elapsed_s"], "pairs": nb,
+            "extrapolation_check": {"predicted_s": t_setup + nb * unit,
+                                    "ratio": full["elapsed_s"] / (t_setup + nb * unit)}}
+    else:
+        line["measured_full_call"] = {"skipped": f"estimated {est_full:.0f} s exceeds the remaining "
+                                                 f"budget {left:.0f} s (TRV_REF_BUDGET_S)"}
+    if budget - (time.perf_counter() - t_start) > 30.:
+        line["fft_calibration"] = fft_calibration(ref)
+    print(json.dumps(line), flush=True)
 
 
 def main():

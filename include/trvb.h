@@ -65,6 +65,11 @@ const char* trvb_version(void);
 /* Number of visible CUDA devices (0 when none / no driver); replaces the
  * probe of S/monitor.cpp:258-282. */
 int trvb_device_count(void);
+/* The calling thread's current CUDA device (cudaGetDevice / cudaSetDevice): used by
+ * the host layer to pick the device when no environment variable names one, and to
+ * restore the caller's device after an estimator call.  -1 / non-zero on failure. */
+int trvb_current_device(void);
+int trvb_set_current_device(int device);
 /* Number of hand-written kernels launched by this library since the last
  * reset, and (separately) the number of cuFFT executions. */
 long long trvb_launch_count(void);
@@ -99,6 +104,9 @@ size_t trvb_mesh_bytes(const trvb_ctx* ctx, int layout);
  * the reference). */
 int trvb_mem_info(trvb_ctx* ctx, size_t* free_bytes, size_t* total_bytes);
 void trvb_mem_info_invalidate(int device);
+/* Return the blocks the caching arena of `device` holds for reuse to the driver
+ * (synchronises the device). */
+void trvb_arena_release(int device);
 int trvb_malloc(trvb_ctx* ctx, void** dptr, size_t bytes);
 int trvb_free(trvb_ctx* ctx, void* dptr);
 int trvb_memset0(trvb_ctx* ctx, void* dptr, size_t bytes);

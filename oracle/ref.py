@@ -324,8 +324,65 @@ def bispec_pair(idx_row, idx_col):
     return complex(out[0], out[1]), complex(out[2], out[3]), t.value
 
 
+def bispec_pair_shells():
+    """(k_eff_a, k_eff_b), (nmodes_a, nmodes_b) of the last :func:`bispec_pair`
+    (S/threept.cpp:1912-1919)."""
+    keff = np.zeros(2)
+    nmodes = np.zeros(2, dtype=np.int32)
+    _check(lib().trvref_bispec_pair_shells(keff.ctypes.data_as(_dp), nmodes.ctypes.data_as(_ip)))
+    return keff, nmodes
+
+
+def bispec_twopt(num_bins):
+    """Binned ``pk`` and ``sn`` of ``compute_ylm_wgtd_2pt_stats_in_fourier(dn_00,
+    N_L0, Sbar, 0, 0)`` (S/threept.cpp:1988-1992); complex arrays of length num_bins."""
+    buf = np.zeros(4 * num_bins)
+    _check(lib().trvref_bispec_twopt(buf.ctypes.data_as(_dp)))
+    buf = buf.reshape(num_bins, 4)
+    return buf[:, 0] + 1j * buf[:, 1], buf[:, 2] + 1j * buf[:, 3]
+
+
+def bispec_entries(pairs, num_bins, ntotal, norm_factor=1.):
+    """Entries of the reference's B_000 box data vector for the listed (row, column)
+    bin pairs, assembled exactly as compute_bispec_in_gpp_box does for
+    (l1, l2, L) = (0, 0, 0) (coupling = 1, no mirror term, unit phase;
+    S/threept.cpp:1981-1986, 2044-2056, 2110-2122, 2126-2140, 2162-2163).
+    Needs :func:`bispec_setup` first.  Returns a dict shaped like the estimator's
+    output restricted to those pairs, plus the wall seconds of every pair unit."""
+    pk, sn = bispec_twopt(num_bins)
+    sbar = complex(float(ntotal))
+    out = {k: [] for k in ("k1_eff", "k2_eff", "nmodes_1", "nmodes_2", "bk_raw", "bk_shot",
+                           "unit_s")}
+    for a, b in pairs:
+        bk, s_ab, t = bispec_pair(a, b)
+        keff, nmodes = bispec_pair_shells()
+        shot = 0j
+        shot += sbar                      # S|{i = j = k}
+        shot += pk[a] - sn[a]             # S|{i != j = k} (row bin)
+        shot += pk[b] - sn[b]             # S|{j != i = k} (column bin)
+        shot += s_ab                      # S|{i = j != k}
+        out["k1_eff"].append(keff[0]); out["k2_eff"].append(keff[1])
+        out["nmodes_1"].append(nmodes[0]); out["nmodes_2"].append(nmodes[1])
+        out["bk_raw"].append(norm_factor * bk); out["bk_shot"].append(norm_factor * shot)
+        out["unit_s"].append(t)
+    return {k: np.asarray(v) for k, v in out.items()}
+
+
+def triu_index(a, b, num_bins):
+    """Index of pair (a, b), b >= a, in the `triu` data vector (S/threept.cpp:1908-1909)."""
+    return (2 * num_bins - a + 1) * a // 2 + (b - a)
+
+
 def bispec_teardown():
     lib().trvref_bispec_teardown()
+
+
+def fft_time(n, reps=2):
+    """Best-of-``reps`` seconds of one n^3 forward complex transform by the FFTW
+    stand-in, through the calls the reference makes (S/field.cpp:246,1552)."""
+    t = C.c_double(0.)
+    _check(lib().trvref_fft_time(C.c_int(n), C.c_int(reps), C.byref(t)))
+    return t.value
 
 
 def norm_particles(pos, nz, ws=None, wc=None, alpha=1.):

@@ -249,6 +249,8 @@ struct RefBispecState {
   trv::maths::SphericalBesselCalculator* sj_a = nullptr;
   trv::maths::SphericalBesselCalculator* sj_b = nullptr;
   std::vector< std::complex<double> > ylm_k_a, ylm_k_b, ylm_r_a, ylm_r_b;
+  double last_keff[2] = {0., 0.};
+  int last_nmodes[2] = {0, 0};
 };
 static RefBispecState* g_state = nullptr;
 
@@ -343,6 +345,75 @@ int trvref_bispec_pair(int idx_row, int idx_col, double* out, double* elapsed_s)
     *elapsed_s = std::chrono::duration<double>(t1 - t0).count();
     out[0] = bk_re * s.dn_00->vol_cell; out[1] = bk_im * s.dn_00->vol_cell;
     out[2] = S.real(); out[3] = S.imag();
+    s.last_keff[0] = k_eff_a; s.last_keff[1] = k_eff_b;
+    s.last_nmodes[0] = nmodes_a; s.last_nmodes[1] = nmodes_b;
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+
+// Shell statistics (k_eff, nmodes) of the two bins of the last trvref_bispec_pair call
+// (what S/threept.cpp:1912-1919 stores in k1eff_dv/k2eff_dv/nmodes1_dv/nmodes2_dv).
+int trvref_bispec_pair_shells(double* keff, int* nmodes) {
+  if (!g_state) { g_err = "trvref_bispec_setup not called"; return 1; }
+  keff[0] = g_state->last_keff[0]; keff[1] = g_state->last_keff[1];
+  nmodes[0] = g_state->last_nmodes[0]; nmodes[1] = g_state->last_nmodes[1];
+  return 0;
+}
+
+// The binned two-point statistics behind the S|{i != j = k} and S|{j != i = k}
+// shot-noise terms (S/threept.cpp:1988-1992, 2057-2061):
+// FieldStats::compute_ylm_wgtd_2pt_stats_in_fourier(dn_00, N_L0, Sbar, 0, 0, kbinning).
+// pk_sn holds num_bins x {Re pk, Im pk, Re sn, Im sn}.
+int trvref_bispec_twopt(double* pk_sn) {
+  try {
+    if (!g_state) { g_err = "trvref_bispec_setup not called"; return 1; }
+    RefBispecState& s = *g_state;
+    std::complex<double> Sbar = double(s.cat->ntotal);
+    s.stats->compute_ylm_wgtd_2pt_stats_in_fourier(*s.dn_00, *s.N_L0, Sbar, 0, 0, *s.bins);
+    for (int i = 0; i < s.bins->num_bins; i++) {
+      pk_sn[4*i] = s.stats->pk[i].real(); pk_sn[4*i + 1] = s.stats->pk[i].imag();
+      pk_sn[4*i + 2] = s.stats->sn[i].real(); pk_sn[4*i + 3] = s.stats->sn[i].imag();
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+
+// Calibration of the FFTW stand-in (oracle/shim/trvshim_fft.cpp): best-of-`reps`
+// wall time of one in-place forward complex transform of an n^3 array through the
+// same calls the reference makes (fftw_plan_dft_3d + fftw_execute,
+// S/field.cpp:246,1552), to be quoted beside scipy.fft.fftn(workers=cores) on the
+// same host.
+int trvref_fft_time(int n, int reps, double* seconds) {
+  try {
+    size_t nmesh = size_t(n) * n * n;
+    fftw_complex* a = fftw_alloc_complex(nmesh);
+    if (!a) { g_err = "fftw_alloc_complex failed"; return 1; }
+#if defined(TRV_USE_OMP) && defined(TRV_USE_FFTWOMP)
+    fftw_init_threads();
+    fftw_plan_with_nthreads(omp_get_max_threads());
+#endif
+    fftw_plan plan = fftw_plan_dft_3d(n, n, n, a, a, FFTW_FORWARD, FFTW_ESTIMATE);
+    double best = 1.e300;
+    for (int r = 0; r < reps; r++) {
+#pragma omp parallel for
+      for (long long i = 0; i < (long long)nmesh; i++) {
+        a[i][0] = double((i * 2654435761ULL) % 1024) / 1024. - 0.5; a[i][1] = 0.;
+      }
+      auto t0 = std::chrono::steady_clock::now();
+      fftw_execute(plan);
+      auto t1 = std::chrono::steady_clock::now();
+      double t = std::chrono::duration<double>(t1 - t0).count();
+      if (t < best) best = t;
+    }
+    fftw_destroy_plan(plan);
+    fftw_free(a);
+    *seconds = best;
     return 0;
   } catch (const std::exception& e) {
     g_err = e.what();

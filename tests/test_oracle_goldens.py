@@ -10,7 +10,7 @@ is present.
 import numpy as np
 import pytest
 
-from conftest import load_golden, twopt_case, check_twopt_against_golden, TWOPT_CASES, window_inputs
+from conftest import GOLDEN, load_golden, twopt_case, check_twopt_against_golden, TWOPT_CASES, window_inputs
 
 CASES = [((0, 0, 0), "diag", None), ((2, 0, 2), "diag", None), ((0, 0, 0), "row", 0)]
 
@@ -178,3 +178,59 @@ def test_oracle_binning_edges(oracle):
     assert np.allclose(c, 0.5 * (e[1:] + e[:-1]))
     e, c, w = oracle.binning("config", "log", 10., 1000., 4)
     assert np.allclose(e, np.logspace(1, 3, 5), rtol=1e-14)
+
+
+# ---------------------------------------------------------------------------
+# Production-shape fixtures (tests/golden/oracle_prod_*.npz)
+# ---------------------------------------------------------------------------
+
+def test_pair_unit_assembly_equals_the_full_reference_call(oracle):
+    """`oracle.ref.bispec_entries` (setup + loop body per bin pair + binned two-point
+    statistics, assembled as S/threept.cpp:1981-2140 does) is what the 512^3 fixtures
+    and bench.py's parity_check are made of: it must equal the reference's full
+    compute_bispec_in_gpp_box call entry for entry."""
+    gen = np.random.default_rng(3)
+    L, ng, nb, n = 500., 32, 5, 3000
+    pos = gen.uniform(0., L, (3, n))
+    full = oracle.threept("bispec", "sim", pos, L, ng, "pcs", (0, 0, 0), "full", (0.02, 0.3), nb, 2.5)
+    oracle.bispec_setup(pos, L, ng, "pcs", (0.02, 0.3), nb)
+    pairs = [(a, b) for a in range(nb) for b in range(a, nb)]
+    ent = oracle.bispec_entries(pairs, nb, n, 2.5)
+    oracle.bispec_teardown()
+    idx = [oracle.triu_index(a, b, nb) for a, b in pairs]
+    assert idx == list(range(len(pairs)))
+    for k in ("nmodes_1", "nmodes_2"):
+        assert np.array_equal(ent[k], full[k][idx])
+    for k in ("k1_eff", "k2_eff", "bk_raw", "bk_shot"):
+        assert np.max(np.abs(ent[k] - full[k][idx]) / np.abs(full[k][idx])) < 1.e-14, k
+
+
+@pytest.mark.parametrize("tag,keys", [
+    ("C1", ("bk_raw", "bk_shot", "nmodes_1", "k1_eff")),
+    ("C2", ("bk_raw", "bk_shot", "nmodes_1", "k1_eff", "index", "pairs")),
+    ("C5proxy", ("bk_raw", "bk_shot", "nmodes_1", "k1_eff", "index", "pairs")),
+    ("C4lo", ("zeta_raw", "zeta_shot", "npairs_1", "r1_eff")),
+    ("C4hi", ("zeta_raw", "zeta_shot", "npairs_1", "r1_eff")),
+    ("C3", ("bk_raw", "bk_shot", "nmodes_1", "k1_eff")),
+])
+def test_production_fixtures_are_committed_and_sane(tag, keys):
+    fix = np.load(GOLDEN / f"oracle_prod_{tag}.npz")
+    for k in keys:
+        assert k in fix.files, (tag, k)
+        assert np.all(np.isfinite(np.asarray(fix[k]).view(float) if np.iscomplexobj(fix[k])
+                                  else np.asarray(fix[k], dtype=float))), (tag, k)
+    assert "make_golden_production.py" in str(fix["meta"])
+
+
+def test_c1_fixture_first_four_bins_are_the_reference_golden():
+    """C1 with 10 bins on [0.005, 0.105] has bins of width 0.01; the reference's own
+    golden (4 bins of width 0.025) covers the same modes: the first shell edge and the
+    particle normalisation are common, so nmodes and the shot-noise scale tie the two."""
+    fix = np.load(GOLDEN / "oracle_prod_C1.npz")
+    ext = np.loadtxt(GOLDEN / "bk000_diag_gpp.txt", unpack=True)
+    assert fix["bk_raw"].shape == (10,)
+    # 10-bin shells nest in the 4-bin ones only at 0.005, 0.055, 0.105: modes of bins 0..4
+    # equal modes of golden bins 0..1
+    assert int(fix["nmodes_1"][:5].sum()) == int(ext[2][:2].sum())
+    assert int(fix["nmodes_1"].sum()) == int(ext[2].sum())
+    assert abs(float(fix["norm_factor"]) - 3.703703704e16) < 1.e7

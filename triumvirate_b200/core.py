@@ -301,6 +301,12 @@ def threept_box_arrays(stat, n, x_ptr, y_ptr, z_ptr, on_device, boxsize, ngrid,
     return dict(zip(names, vals))
 
 
+def release_contexts():
+    """Drop the cached device contexts (cuFFT plans, tables) and hand the arena's
+    cached blocks back to the driver."""
+    _trv().trv_release_contexts()
+
+
 def profile_enable(on=True):
     _trv().trv_profile_enable(C.c_int(1 if on else 0))
 

@@ -1494,6 +1494,25 @@ extern "C" int trvb_cat_create(trvb_ctx* ctx, trvb_cat** out, long long n,
   cat->owner = ctx; cat->n = n;
   const size_t nb = sizeof(double) * (size_t)n;
   const cudaMemcpyKind kind = src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  if (src_on_device) {
+    // Device sources must live on the context's GPU (a single-process caller may have made
+    // another device current): a pointer of another device would fault or go over peer access.
+    const double* srcs[5] = {x, y, z, w, los};
+    for (const double* p : srcs) {
+      if (!p) continue;
+      cudaPointerAttributes attr;
+      TRVB_CUDA(cudaPointerGetAttributes(&attr, p));
+      const bool ok = (attr.type == cudaMemoryTypeDevice && attr.device == ctx->device)
+        || attr.type == cudaMemoryTypeManaged;
+      if (!ok) {
+        delete cat;
+        trvb_set_error("trvb_cat_create: device array %p is not memory of GPU %d (type %d, "
+                       "device %d); create the context on the GPU that holds the catalogue",
+                       (const void*)p, ctx->device, (int)attr.type, attr.device);
+        return 2;
+      }
+    }
+  }
   if (src_on_device == 2) {
     // Borrowed: the caller keeps the coordinate arrays alive and unchanged for the
     // life of the catalogue (one estimator call); no copy, never freed here.

@@ -26,6 +26,15 @@ extern "C" int trvb_device_count(void) {
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
   return n;
 }
+extern "C" int trvb_current_device(void) {
+  int d = -1;
+  if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); return -1; }
+  return d;
+}
+extern "C" int trvb_set_current_device(int device) {
+  TRVB_CUDA(cudaSetDevice(device));
+  return 0;
+}
 extern "C" long long trvb_launch_count(void) { return g_trvb_launches; }
 extern "C" void trvb_launch_count_reset(void) { g_trvb_launches = 0; g_trvb_fft_execs = 0; }
 extern "C" long long trvb_fft_exec_count(void) { return g_trvb_fft_execs; }
@@ -133,6 +142,13 @@ void trvb_arena_trim(int device) {
 }
 
 extern "C" void trvb_mem_info_invalidate(int device);
+extern "C" void trvb_arena_release(int device) {
+  if (trvb_arena_cached_bytes(device) == 0) return;   // never touches a GPU it did not use
+  int prev = -1;
+  if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+  if (cudaSetDevice(device) == cudaSuccess) trvb_arena_trim(device); else cudaGetLastError();
+  if (prev >= 0) cudaSetDevice(prev);
+}
 
 int trvb_scratch(trvb_ctx* ctx, size_t bytes, double** out) {
   if (ctx->scratch_bytes < bytes) {
@@ -218,6 +234,12 @@ extern "C" int trvb_ctx_create(trvb_ctx** out, int device, const int ngrid[3],
   }
   TRVB_REQUIRE(device >= 0 && device < ndev, "trvb_ctx_create: device %d of %d",
                device, ndev);
+  // The caller's current device is put back on every return path.
+  struct DeviceRestore {
+    int prev = -1;
+    DeviceRestore() { if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; } }
+    ~DeviceRestore() { if (prev >= 0) cudaSetDevice(prev); }
+  } restore;
   TRVB_CUDA(cudaSetDevice(device));
   trvb_ctx* ctx = new trvb_ctx();
   ctx->device = device;

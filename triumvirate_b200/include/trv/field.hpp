@@ -39,7 +39,21 @@ void profile_reset();
 void profile_mark(trvb_ctx* ctx, const char* phase);
 std::string profile_report();
 
-/// Shared device context for one (ngrid, boxsize, assignment order).
+/// GPU used by this process's estimator calls: TRV_GPU_DEVICE, else LOCAL_RANK, else
+/// the calling thread's current CUDA device; out-of-range ids throw DeviceError.
+int select_device();
+/// Restores the calling thread's current CUDA device when it goes out of scope (the
+/// device layer makes the context's GPU current while it works).
+class DeviceScope {
+ public:
+  DeviceScope();
+  ~DeviceScope();
+  DeviceScope(const DeviceScope&) = delete;
+  DeviceScope& operator=(const DeviceScope&) = delete;
+ private:
+  int prev_;
+};
+/// Shared device context for one (device, ngrid, boxsize, assignment order).
 std::shared_ptr<trvb_ctx> acquire_context(const trv::ParameterSet& params);
 /// Most recently acquired context (null if none is alive); lets callers put
 /// CUDA events on the stream the estimators enqueue on.

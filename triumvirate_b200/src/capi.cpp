@@ -26,6 +26,7 @@ thread_local std::string g_capi_err;
 template <class F>
 int guarded(F f) {
   try {
+    trv::dev::DeviceScope restore_callers_device;
     f();
     return 0;
   } catch (const trv::sys::DeviceError& e) {

@@ -36,22 +36,39 @@ void check(int status, const char* what) {
 
 namespace {
 
-typedef std::tuple<int, int, int, double, double, double, int> CtxKey;
+typedef std::tuple<int, int, int, int, double, double, double, int> CtxKey;   // device first
 std::mutex g_ctx_mutex;
 std::map<CtxKey, std::weak_ptr<trvb_ctx> > g_ctx_cache;
 std::vector<std::shared_ptr<trvb_ctx> > g_ctx_recent;
 trvb_ctx* g_last_ctx = nullptr;
 
-int device_from_env() {
-  // One process per GPU: LOCAL_RANK (torchrun) or TRV_GPU_DEVICE selects it.
-  const char* dev = std::getenv("TRV_GPU_DEVICE");
-  if (dev == nullptr) dev = std::getenv("LOCAL_RANK");
-  int id = dev ? std::atoi(dev) : 0;
-  int n = trvb_device_count();
-  return (n > 0) ? id % n : 0;
+}  // namespace
+
+/// The GPU of this process's estimator calls: TRV_GPU_DEVICE, else LOCAL_RANK (one
+/// process per GPU under torchrun), else the calling thread's CURRENT CUDA device --
+/// so a single-process caller that selected a device (cudaSetDevice,
+/// torch.cuda.set_device) and hands over device pointers gets its context there.
+/// Ids outside [0, device count) are an error, not wrapped.
+int select_device() {
+  const int n = trvb_device_count();
+  const char* name = "TRV_GPU_DEVICE";
+  const char* dev = std::getenv(name);
+  if (dev == nullptr || dev[0] == '\0') { name = "LOCAL_RANK"; dev = std::getenv(name); }
+  if (dev != nullptr && dev[0] != '\0') {
+    char* end = nullptr;
+    const long id = std::strtol(dev, &end, 10);
+    if (end == dev || *end != '\0' || id < 0 || id >= n) {
+      throw trvs::DeviceError("%s=%s does not name one of the %d visible CUDA devices.",
+                              name, dev, n);
+    }
+    return static_cast<int>(id);
+  }
+  const int cur = trvb_current_device();
+  return (cur >= 0 && cur < n) ? cur : 0;
 }
 
-}  // namespace
+DeviceScope::DeviceScope() : prev_(trvb_current_device()) {}
+DeviceScope::~DeviceScope() { if (prev_ >= 0) trvb_set_current_device(prev_); }
 
 std::shared_ptr<trvb_ctx> acquire_context(const trv::ParameterSet& params) {
   if (!trvs::is_gpu_enabled()) {
@@ -63,7 +80,8 @@ std::shared_ptr<trvb_ctx> acquire_context(const trv::ParameterSet& params) {
     throw trvs::DeviceError(
       "No usable CUDA device: triumvirate_b200 has no CPU fallback.");
   }
-  CtxKey key(params.ngrid[0], params.ngrid[1], params.ngrid[2],
+  const int device = select_device();
+  CtxKey key(device, params.ngrid[0], params.ngrid[1], params.ngrid[2],
              params.boxsize[0], params.boxsize[1], params.boxsize[2],
              params.assignment_order);
   std::lock_guard<std::mutex> lock(g_ctx_mutex);
@@ -72,7 +90,7 @@ std::shared_ptr<trvb_ctx> acquire_context(const trv::ParameterSet& params) {
     if (auto sp = it->second.lock()) { g_last_ctx = sp.get(); return sp; }
   }
   trvb_ctx* raw = nullptr;
-  check(trvb_ctx_create(&raw, device_from_env(), params.ngrid, params.boxsize,
+  check(trvb_ctx_create(&raw, device, params.ngrid, params.boxsize,
                         params.assignment_order), "trvb_ctx_create");
   std::shared_ptr<trvb_ctx> sp(raw, [](trvb_ctx* c) { trvb_ctx_destroy(c); });
   g_ctx_cache[key] = sp;
@@ -91,6 +109,9 @@ void release_contexts() {
   std::lock_guard<std::mutex> lock(g_ctx_mutex);
   g_ctx_recent.clear();
   g_last_ctx = nullptr;
+  // With the contexts gone the arena's cached blocks serve nobody: back to the driver.
+  const int n = trvb_device_count();
+  for (int d = 0; d < n; d++) trvb_arena_release(d);
 }
 
 Catalogue::Catalogue(std::shared_ptr<trvb_ctx> ctx, ParticleCatalogue& particles,
