@@ -426,8 +426,9 @@ def run_b200(args):
                               out_det["k1_eff"], out_det["k2_eff"],
                               out_det["nmodes_1"].astype(np.float64),
                               out_det["nmodes_2"].astype(np.float64)])
-    vec = np.concatenate([out["bk_raw"].view(np.float64), out["bk_shot"].view(np.float64)])
-    dev_det = float(np.max(np.abs(vec - vec_det[:vec.size]) / np.maximum(np.abs(vec_det[:vec.size]), 1.e-300)))
+    # timed (throughput-mode) result against the deterministic one, per complex entry
+    dev_det = float(max(np.max(np.abs(out[k] - out_det[k]) / np.abs(out_det[k]))
+                        for k in ("bk_raw", "bk_shot")))
 
     result = {
         "metric": "bispectrum time-to-solution", "value": sec / args.steps, "unit": "s",

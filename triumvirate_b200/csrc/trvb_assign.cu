@@ -1086,6 +1086,8 @@ __global__ void k_sum_partials(const double* __restrict__ partial, int nblocks, 
   out[t] = s;
 }
 
+#include "trvb_assign_own.cuh"
+
 CatView view_of(const trvb_cat* cat) {
   CatView v;
   v.x = cat->x; v.y = cat->y; v.z = cat->z; v.w = cat->w;
@@ -1327,6 +1329,145 @@ k_assign_gather_warp(SortedView c, const int* __restrict__ order,
 
 // Particle-wise scatter of a sorted view: warp-cooperative for TSC/PCS, thread per
 // particle for NGP/CIC.
+// ---------------------------------------------------------------------
+// Tile-owned assignment: owner-sorted copies and launch (trvb_assign_own.cuh).
+// ---------------------------------------------------------------------
+
+void free_own_sorted(trvb_ctx* ctx, trvb_cat* cat) {
+  trvb_dev_free_raw(ctx, cat->own_rec); trvb_dev_free_raw(ctx, cat->own_pk);
+  trvb_dev_free_raw(ctx, cat->own_src); trvb_dev_free_raw(ctx, cat->own_offsets);
+  trvb_dev_free_raw(ctx, cat->own_irr);
+  cat->own_rec = nullptr; cat->own_pk = nullptr; cat->own_src = nullptr;
+  cat->own_offsets = nullptr; cat->own_irr = nullptr;
+  cat->own_total = 0; cat->own_nirr = 0; cat->own_shifted = -1; cat->own_order = 0;
+}
+
+OwnDesc own_desc(const GridDesc& g, int shifted) {
+  OwnDesc d;
+  for (int a = 0; a < 3; a++) { d.n[a] = g.n[a]; d.L[a] = g.L[a]; }
+  d.shifted = shifted;
+  d.nch[0] = (g.n[0] + OWN_PX - 1) / OWN_PX;
+  d.nch[1] = (g.n[1] + OWN_PY - 1) / OWN_PY;
+  d.nch[2] = (g.n[2] + OWN_ZS - 1) / OWN_ZS;
+  d.kpt = OWN_ZS + g.order - 1;
+  d.pk_in_w = 0;
+  return d;
+}
+
+template <int ORDER>
+int ensure_own_sorted(trvb_ctx* ctx, trvb_cat* cat, int shifted) {
+  const GridDesc& g = ctx->g;
+  const bool need_src = cat->los != nullptr || cat->cw != nullptr;
+  bool valid = cat->own_rec != nullptr && cat->own_shifted == shifted && cat->own_order == ORDER
+    && (!need_src || cat->own_src != nullptr);
+  for (int a = 0; a < 3; a++) valid = valid && cat->own_n[a] == g.n[a] && cat->own_L[a] == g.L[a];
+  if (valid) return 0;
+  free_own_sorted(ctx, cat);
+  OwnDesc d = own_desc(g, shifted);
+  d.pk_in_w = cat->w == nullptr;   // unit weights: one 32-byte sector per copy, no key array
+  const long long ntasks = (long long)d.nch[0] * d.nch[1] * d.nch[2];
+  const long long nkeys = ntasks * d.kpt;
+  TRVB_REQUIRE(nkeys < 2147483647LL, "mesh too large for int sort keys");
+  TRVB_REQUIRE(cat->n < 2147483647LL / 8, "catalogue too large for int indices");
+  int* offsets = nullptr; int* cursor = nullptr; int* chunk_sums = nullptr; int* misc = nullptr;
+  TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&offsets, sizeof(int) * (size_t)(nkeys + 1)));
+  TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cursor, sizeof(int) * (size_t)nkeys));
+  const long long nscan = nkeys + 1;
+  const int nchunks = div_up(nscan, SCAN_CHUNK);
+  TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&chunk_sums, sizeof(int) * (size_t)nchunks));
+  TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&misc, sizeof(int) * 4));
+  TRVB_CUDA(cudaMemsetAsync(offsets, 0, sizeof(int) * (size_t)nscan, ctx->stream));
+  TRVB_CUDA(cudaMemsetAsync(misc, 0, sizeof(int) * 4, ctx->stream));
+  const CatView cv = view_of(cat);
+  const int threads = 256;
+  const int blocks = (int)std::min<long long>(div_up(cat->n, threads), (long long)ctx->num_sms * 16);
+  k_own_sort<ORDER><<<blocks, threads, 0, ctx->stream>>>(cv, d, offsets, nullptr, misc, nullptr,
+                                                         nullptr, nullptr, nullptr);
+  TRVB_LAUNCH_CHECK();
+  k_scan_chunk_sums<<<nchunks, SCAN_THREADS, 0, ctx->stream>>>(offsets, nscan, chunk_sums);
+  TRVB_LAUNCH_CHECK();
+  k_scan_chunk_offsets<<<1, 1024, 0, ctx->stream>>>(chunk_sums, nchunks);
+  TRVB_LAUNCH_CHECK();
+  k_scan_apply<<<nchunks, SCAN_THREADS, 0, ctx->stream>>>(offsets, nscan, chunk_sums);
+  TRVB_LAUNCH_CHECK();
+  // The number of copies (1 to 8 per particle) sizes the lists: one small read-back.
+  int h_total = 0, h_nirr = 0;
+  TRVB_CUDA(cudaMemcpyAsync(&h_total, offsets + nkeys, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  TRVB_CUDA(cudaMemcpyAsync(&h_nirr, misc, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  TRVB_REQUIRE(h_total >= 0, "owner sort: copy count overflows int indices");
+  const size_t ncopy = (size_t)std::max(h_total, 1);
+  TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->own_rec, sizeof(double4) * ncopy));
+  if (!d.pk_in_w) TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->own_pk, sizeof(int) * ncopy));
+  if (need_src) TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->own_src, sizeof(int) * ncopy));
+  if (h_nirr > 0) TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->own_irr, sizeof(int) * (size_t)h_nirr));
+  TRVB_CUDA(cudaMemcpyAsync(cursor, offsets, sizeof(int) * (size_t)nkeys,
+                            cudaMemcpyDeviceToDevice, ctx->stream));
+  k_own_sort<ORDER><<<blocks, threads, 0, ctx->stream>>>(cv, d, offsets, cursor, misc + 1,
+                                                         cat->own_rec, cat->own_pk, cat->own_src,
+                                                         cat->own_irr);
+  TRVB_LAUNCH_CHECK();
+  TRVB_CUDA(trvb_dev_free_raw(ctx, cursor));
+  TRVB_CUDA(trvb_dev_free_raw(ctx, chunk_sums));
+  TRVB_CUDA(trvb_dev_free_raw(ctx, misc));
+  cat->own_offsets = offsets;
+  cat->own_total = h_total; cat->own_nirr = h_nirr;
+  for (int a = 0; a < 3; a++) { cat->own_n[a] = g.n[a]; cat->own_L[a] = g.L[a]; }
+  cat->own_shifted = shifted; cat->own_order = ORDER;
+  return 0;
+}
+
+template <int ORDER, bool COMPLEX, bool HEAVY>
+int launch_own_general(trvb_ctx* ctx, const OwnView& v, const GridDesc& g, const OwnDesc& d, int kind,
+                       const YlmCoef& yc, double s, int accumulate, double* mesh, unsigned nblocks,
+                       trvb_cat* cat, int L, int M, int shifted) {
+  // all of the SM's shared memory to the rings: seven one-warp CTAs per SM
+  TRVB_CUDA(cudaFuncSetAttribute(k_assign_own<ORDER, COMPLEX, HEAVY>,
+                                 cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  TRVB_CUDA(cudaFuncSetAttribute(k_assign_own<ORDER, COMPLEX, HEAVY>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)OwnGeom<ORDER>::SMEM));
+  k_assign_own<ORDER, COMPLEX, HEAVY><<<nblocks, 32, OwnGeom<ORDER>::SMEM, ctx->stream>>>(
+    v, g, d, kind, yc, s, accumulate, mesh);
+  TRVB_LAUNCH_CHECK();
+  if (cat->own_nirr > 0) {
+    const int blocks = div_up(cat->own_nirr, 128);
+    k_assign_irregular<ORDER, COMPLEX><<<blocks, 128, 0, ctx->stream>>>(
+      view_of(cat), cat->own_irr, cat->own_nirr, g, shifted, kind, L, M, s, mesh);
+    TRVB_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+template <int ORDER, bool COMPLEX>
+int launch_own_kernels(trvb_ctx* ctx, trvb_cat* cat, int kind, int L, int M, const YlmCoef& yc,
+                       double s, int accumulate, int shifted, double* mesh) {
+  const GridDesc& g = ctx->g;
+  const OwnDesc d = own_desc(g, shifted);
+  const long long ntasks = (long long)d.nch[0] * d.nch[1] * d.nch[2];
+  OwnView v;
+  v.rec = cat->own_rec; v.pk = cat->own_pk; v.src = cat->own_src; v.offsets = cat->own_offsets;
+  v.lx = cat->los; v.ly = cat->los ? cat->los + cat->n : nullptr;
+  v.lz = cat->los ? cat->los + 2 * cat->n : nullptr;
+  v.cw = cat->cw;
+  const long long nblocks = ntasks * (COMPLEX ? 2 : 1);
+  TRVB_REQUIRE(nblocks < 2147483647LL, "too many assignment tasks");
+  // weights that read the lines of sight or the custom column get their own instantiation
+  const bool heavy = kind == TRVB_W_CUSTOM
+    || ((kind == TRVB_W_YLM_W || kind == TRVB_W_CYLM_W2) && !(L == 0 && M == 0));
+  const int kind_eff = (!heavy && kind != TRVB_W_UNIT) ? (int)TRVB_W_W : kind;
+  if (kind == TRVB_W_CYLM_W2 && !heavy) {
+    // y_00 = 1: conj(y_00) w^2 is the weight squared -- evaluated by the general path
+    return launch_own_general<ORDER, COMPLEX, true>(ctx, v, g, d, kind, yc, s, accumulate, mesh,
+                                                    (unsigned)nblocks, cat, L, M, shifted);
+  }
+  return heavy
+    ? launch_own_general<ORDER, COMPLEX, true>(ctx, v, g, d, kind, yc, s, accumulate, mesh,
+                                               (unsigned)nblocks, cat, L, M, shifted)
+    : launch_own_general<ORDER, COMPLEX, false>(ctx, v, g, d, kind_eff, yc, s, accumulate, mesh,
+                                                (unsigned)nblocks, cat, L, M, shifted);
+}
+
 template <int ORDER>
 void launch_throughput_scatter(trvb_ctx* ctx, const SortedView& cv, int kind, const YlmCoef& yc,
                                double s, int shifted, bool cplx_mesh, double* mesh) {
@@ -1369,13 +1510,31 @@ int launch_assign(trvb_ctx* ctx, trvb_cat* cat, int kind, int L, int M, double s
       // the tile kernel needs global (tile, column) offsets: re-sort a chunked order
       if (env_tile_pre != nullptr && env_tile_pre[0] == '1' && cat->chunked) trvb_cat_invalidate_sort(cat);
     }
+    const double s = density_units ? scale * (1. / g.vol_cell) : scale;
+    // TRV_ASSIGN_OWN=1 selects the tile-owned, store-once assignment (trvb_assign_own.cuh):
+    // no zero-fill, no RED, 1.08x the algorithmic DRAM traffic instead of 2.65x -- but on
+    // B200 it only ties the warp-cooperative scatter below (PCS, C2: 1.48 vs 1.60 ms, and
+    // 2.35 vs 2.03 ms once its 1.7x larger counting sort is included): it saturates the SM's
+    // LSU wavefront pipe (87 %) where the scatter saturates the L2 RED units (76 %), see
+    // profiles/r02_assign_own_vs_coop.txt.  Opt-in, parity-tested.
+    {
+      const char* env_own = getenv("TRV_ASSIGN_OWN");
+      if (env_own && env_own[0] == '1' && !cat->chunked) {
+        int st = ensure_own_sorted<ORDER>(ctx, cat, shifted);
+        if (st) return st;
+        return cplx_mesh
+          ? launch_own_kernels<ORDER, true>(ctx, cat, kind, L, M, yc, s, accumulate, shifted,
+                                            (double*)mesh.data)
+          : launch_own_kernels<ORDER, false>(ctx, cat, kind, L, M, yc, s, accumulate, shifted,
+                                             (double*)mesh.data);
+      }
+    }
     int st = ensure_sorted(ctx, cat, shifted, 0);
     if (st) return st;
     SortedView cv = sorted_view_of(cat);
     if (!accumulate) {
       TRVB_CUDA(cudaMemsetAsync(mesh.data, 0, trvb_mesh_bytes(ctx, mesh.layout), ctx->stream));
     }
-    const double s = density_units ? scale * (1. / g.vol_cell) : scale;
     const int threads = 256;
     // TRV_ASSIGN_TILE=1 selects the tile-owned shared-memory kernel.  Measured on
     // B200 (profiles/r01d_assign_tile_vs_coop.txt) it only ties the cooperative
@@ -1810,11 +1969,14 @@ extern "C" void trvb_cat_destroy(trvb_cat* cat) {
   trvb_dev_free_raw(o, cat->w); trvb_dev_free_raw(o, cat->los); trvb_dev_free_raw(o, cat->cw);
   trvb_dev_free_raw(o, cat->order); trvb_dev_free_raw(o, cat->cell_start);
   trvb_dev_free_raw(o, cat->s4); trvb_dev_free_raw(o, cat->slos); trvb_dev_free_raw(o, cat->scw);
+  trvb_dev_free_raw(o, cat->own_rec); trvb_dev_free_raw(o, cat->own_pk);
+  trvb_dev_free_raw(o, cat->own_src); trvb_dev_free_raw(o, cat->own_offsets);
+  trvb_dev_free_raw(o, cat->own_irr);
   delete cat;
 }
 
 extern "C" void trvb_cat_invalidate_sort(trvb_cat* cat) {
-  if (cat) { cat->sort_kind = -1; cat->sort_shifted = -1; }
+  if (cat) { cat->sort_kind = -1; cat->sort_shifted = -1; cat->own_shifted = -1; }
 }
 
 extern "C" long long trvb_cat_size(const trvb_cat* cat) { return cat ? cat->n : 0; }

@@ -133,6 +133,19 @@ struct trvb_cat {
   int sort_shifted = -1;
   int sort_kind = -1;          // 0 tile-sorted (throughput), 1 cell-sorted
   int sort_order = 0;
+  // Owner-sorted copies for the tile-owned assignment (trvb_assign_own.cuh): one record
+  // per (particle, task it touches), counting-sorted by (task, first plane touched).
+  double4* own_rec = nullptr;  // {s_x, s_y, s_z, w}
+  int* own_pk = nullptr;       // relative bases, plane key, TSC branches
+  int* own_src = nullptr;      // catalogue index of the copy (only with los / custom weights)
+  int* own_offsets = nullptr;  // nkeys + 1
+  int* own_irr = nullptr;      // catalogue indices of the irregular particles
+  long long own_total = 0;
+  int own_nirr = 0;
+  int own_n[3] = {0, 0, 0};
+  double own_L[3] = {0., 0., 0.};
+  int own_shifted = -1;
+  int own_order = 0;
 };
 
 int trvb_scratch(trvb_ctx* ctx, size_t bytes, double** out);
