@@ -314,6 +314,10 @@ def run_b200(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
+        # The one exchange of the path -- the sum of the partial result vectors -- happens
+        # inside the estimator call (NCCL behind the C API); torch.distributed ships the id.
+        from triumvirate_b200 import dist as tdist
+        assert tdist.init_comm() == world
 
     wl = WORKLOADS[args.workload]
     n, L, ng = wl["n"], wl["L"], wl["ngrid"]
@@ -349,14 +353,6 @@ def run_b200(args):
         out = core.threept_box_arrays("bispec", n, src[0].data_ptr(), src[1].data_ptr(),
                                       src[2].data_ptr(), on_device, deterministic=deterministic,
                                       **kw)
-        if world > 1:
-            # the single small exchange of the path: sum the partial result vectors
-            buf = torch.from_numpy(np.concatenate([
-                out["bk_raw"].view(np.float64), out["bk_shot"].view(np.float64)])).to(dev)
-            dist.all_reduce(buf)
-            res = buf.cpu().numpy()
-            out["bk_raw"] = res[:2 * dim].view(np.complex128)
-            out["bk_shot"] = res[2 * dim:].view(np.complex128)
         return out
 
     def barrier():
@@ -436,7 +432,8 @@ def run_b200(args):
         "ms_per_step": 1.e3 * sec / args.steps, "higher_is_better": False,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_of(args, wl),
-        "run": {"parallelism": f"pairs/{world}gpu" if world > 1 else "1gpu",
+        "run": {"parallelism": (f"pairs/{world}gpu, all-reduce inside the C API (NCCL)"
+                                if world > 1 else "1gpu"),
                 "e2e_upload": ("1/N slice per rank from pinned host memory + NCCL all-gather"
                                if world > 1 else "pinned host -> device")},
         "clocks": clocks,
@@ -454,6 +451,14 @@ def run_b200(args):
         },
     }
 
+    # BASELINE config 5 (1024^3, 1e8 particles, 820 pairs -- the configuration north_star
+    # names for 8 GPUs) as an extra key of the default line, so that the scaling run records
+    # its curve too.  Device-resident catalogue, max over ranks; never fatal for the main line.
+    if args.workload == "C2" and not args.no_c5:
+        dpos = host = gathered = part = None
+        result["c5"] = c5_extra(torch, dist, core, dev, rank, world)
+        dpos = torch.from_numpy(pos).to(dev)
+
     if rank == 0:
         result["roofline"], result["particles_per_s"] = assignment_roofline(torch, dev, dpos, wl)
         if world == 1 and not args.no_cpu_baseline:
@@ -464,6 +469,62 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def c5_extra(torch, dist, core, dev, rank, world, steps=3, warmup=2):
+    """Time-to-solution of BASELINE config 5 on the GPUs of this run."""
+    wl = WORKLOADS["C5"]
+    try:
+        core.release_contexts()
+        torch.cuda.empty_cache()
+        free, _ = torch.cuda.mem_get_info(dev)
+        if free < 100 * 2**30:
+            return {"skipped": f"{free / 2**30:.0f} GiB free HBM, 100 needed"}
+        n = wl["n"]
+        pos = make_catalogue(wl)
+        d = torch.from_numpy(pos).to(dev)
+        del pos
+        kw = dict(boxsize=wl["L"], ngrid=wl["ngrid"], assignment=wl["assignment"],
+                  degrees=wl["degrees"], form=wl["form"], bin_range=wl["bin_range"],
+                  num_bins=wl["num_bins"], norm_factor=1., part_rank=rank, part_count=world)
+
+        def step():
+            return core.threept_box_arrays("bispec", n, d[0].data_ptr(), d[1].data_ptr(),
+                                           d[2].data_ptr(), True, **kw)
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        for _ in range(warmup):
+            out = step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out = step()
+        barrier()
+        sec = (time.perf_counter() - t0) / steps
+        if world > 1:
+            t = torch.tensor([sec], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t.item())
+        ok = bool(np.all(np.isfinite(out["bk_raw"].view(np.float64))))
+        res = {"workload": wl["name"], "ms_per_step": 1.e3 * sec, "steps": steps, "warmup": warmup,
+               "pairs": len(out["bk_raw"]), "finite": ok,
+               "bk_raw_first": float(out["bk_raw"][0].real), "nmodes_last": int(out["nmodes_2"][-1]),
+               "timing": "wall clock around the calls (each returns its result to the host), max over ranks"}
+        del d
+        core.release_contexts()
+        torch.cuda.empty_cache()
+        return res
+    except Exception as exc:   # the main line must survive
+        try:
+            core.release_contexts()
+            torch.cuda.empty_cache()
+        except Exception:
+            pass
+        return {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
 
 def assignment_roofline(torch, dev, dpos, wl):
@@ -685,6 +746,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the extra C5 (1024^3) timing")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

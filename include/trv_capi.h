@@ -137,6 +137,23 @@ int trv_threept_window(
   int* dim, double* c1_bin, double* c2_bin, double* c1_eff, double* c2_eff,
   int* n1, int* n2, double* raw, double* shot);
 
+/* One process per GPU (torchrun, mpirun, ...): attach an NCCL communicator to this
+ * process.  Rank 0 obtains the 128-byte id with trv_comm_unique_id and ships it to
+ * the other ranks (any channel: torch.distributed, MPI, a file); every rank then
+ * calls trv_comm_init(nranks, rank, id) -- collective.  From then on an estimator
+ * call with part_count == nranks ends with one all-reduce of its result vectors, so
+ * every rank returns the complete measurement.  trv_allreduce sums a host buffer of
+ * n doubles over the ranks (no-op without a communicator).  Status 4: NCCL absent.
+ * Single-process callers need none of this: with several usable GPUs (TRV_GPU_MAXNUM,
+ * S/monitor.cpp:258-324) the estimators spread over them by themselves. */
+int trv_comm_unique_id(char id[128]);
+int trv_comm_init(int nranks, int rank, const char id[128]);
+int trv_comm_size(void);
+int trv_allreduce(double* buf, long long n);
+void trv_comm_finalize(void);
+/* GPUs a single-process estimator call on this mesh would spread over. */
+int trv_multi_device_count(const int* ngrid);
+
 /* cudaStream_t of the most recently used estimator context (NULL before the
  * first call). */
 void* trv_last_stream(void);

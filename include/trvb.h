@@ -119,7 +119,9 @@ int trvb_d2d(trvb_ctx* ctx, void* dst, const void* src, size_t bytes);
  * (unit weights), `los` is n x 3 row-major unit vectors or NULL
  * (I/dataobjs.hpp:186-188).  Positions must already be aligned in the box.
  * src_on_device == 2 BORROWS the device arrays x, y, z instead of copying them:
- * the caller keeps them alive and unchanged until trvb_cat_destroy. */
+ * the caller keeps them alive and unchanged until trvb_cat_destroy.  Device arrays
+ * that live on ANOTHER GPU than the context's (single-process multi-GPU runs) are
+ * copied over with cudaMemcpyPeer instead of borrowed. */
 int trvb_cat_create(trvb_ctx* ctx, trvb_cat** cat, long long n,
                     const double* x, const double* y, const double* z,
                     const double* w, const double* los, int src_on_device);
@@ -308,6 +310,33 @@ int trvb_shot_3pcf_bin(trvb_ctx* ctx, trvb_mesh xi, int la, int ma, int lb,
 int trvb_twopt_config_bin(trvb_ctx* ctx, trvb_mesh xi, int ell, int m,
                           const double* edges, const double* centres, int nbins,
                           long long* npairs, double* r, double* xi_out);
+
+/* ---- multi-GPU exchange (`trvb_allreduce`) ---------------
+ * The mesh state is replicated on every GPU, the data-vector entries are dealt to
+ * the ranks (trv::partition_owners) and every entry is produced by exactly one of
+ * them; one all-reduce(sum) of the result vectors (<= 26 KB) over NCCL completes
+ * the call.  The reference's own multi-GPU mode is single-process cuFFT-Xt
+ * (S/field.cpp:212-235); it has no counterpart of these functions.
+ * NCCL is bound at run time (dlopen libnccl.so.2): status 4 when it is absent.
+ *   trvb_comm_unique_id  rank 0 creates the 128-byte id and ships it to the others
+ *                        (ncclGetUniqueId)
+ *   trvb_comm_create     collective over the `nranks` processes/threads, one GPU
+ *                        each (ncclCommInitRank on `device`)
+ *   trvb_allreduce       in-place sum of n doubles in HOST memory, staged through
+ *                        the device; returns when the sum is back
+ *   trvb_allreduce_device  the same for a DEVICE buffer, enqueued on the context's
+ *                        stream without host synchronisation */
+typedef struct trvb_comm trvb_comm;
+int trvb_nccl_version(void);   /* 0 when NCCL cannot be loaded */
+int trvb_comm_unique_id(char id[128]);
+int trvb_comm_create(trvb_comm** comm, int device, int nranks, int rank, const char id[128]);
+void trvb_comm_destroy(trvb_comm* comm);
+int trvb_comm_size(const trvb_comm* comm);
+int trvb_comm_rank(const trvb_comm* comm);
+int trvb_allreduce(trvb_ctx* ctx, trvb_comm* comm, double* host_buf, long long n);
+int trvb_allreduce_device(trvb_ctx* ctx, trvb_comm* comm, double* dev_buf, long long n);
+/* Device of a context. */
+int trvb_ctx_device(const trvb_ctx* ctx);
 
 #ifdef __cplusplus
 }

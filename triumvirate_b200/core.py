@@ -51,8 +51,7 @@ def partition_owners(form, degrees, num_bins, world, idx_bin=0):
     st = _trv().trv_partition_owners(form.encode(), C.c_int(degrees[0]), C.c_int(degrees[1]),
                                      C.c_int(idx_bin), C.c_int(num_bins), C.c_int(world),
                                      owner.ctypes.data_as(C.c_void_p), C.byref(dim))
-    if st != 0:
-        raise RuntimeError(_trv().trv_last_error().decode())
+    _check(st)
     return owner[:dim.value].copy()
 
 
@@ -299,6 +298,60 @@ def threept_box_arrays(stat, n, x_ptr, y_ptr, z_ptr, on_device, boxsize, ngrid,
     vals = (c1b[:n_].copy(), c2b[:n_].copy(), c1e[:n_].copy(), c2e[:n_].copy(),
             n1[:n_].copy(), n2[:n_].copy(), raw_c, shot_c)
     return dict(zip(names, vals))
+
+
+def _prefer_bundled_nccl():
+    """Point TRV_NCCL_LIB at the libnccl.so.2 that ships with PyTorch (pip package
+    nvidia-nccl), so that this process maps one NCCL only -- the one torch itself needs --
+    whichever of the two libraries asks for it first."""
+    import os
+    if os.environ.get("TRV_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for root in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(root, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["TRV_NCCL_LIB"] = cand
+                return
+    except Exception:
+        pass
+
+
+def comm_unique_id():
+    """128-byte NCCL id created by rank 0 (``trv_comm_unique_id``)."""
+    _prefer_bundled_nccl()
+    buf = C.create_string_buffer(128)
+    _check(_trv().trv_comm_unique_id(buf))
+    return buf.raw
+
+
+def comm_init(nranks, rank, ident):
+    """Attach an NCCL communicator to this process (collective, ``trv_comm_init``)."""
+    _prefer_bundled_nccl()
+    _check(_trv().trv_comm_init(C.c_int(nranks), C.c_int(rank), C.c_char_p(bytes(ident))))
+
+
+def comm_size():
+    return _trv().trv_comm_size()
+
+
+def comm_finalize():
+    _trv().trv_comm_finalize()
+
+
+def allreduce(buf):
+    """In-place sum of a float64 array over the ranks of the process communicator."""
+    buf = np.ascontiguousarray(buf, dtype=np.float64)
+    _check(_trv().trv_allreduce(buf.ctypes.data_as(_dp), C.c_longlong(buf.size)))
+    return buf
+
+
+def multi_device_count(ngrid):
+    """GPUs a single-process estimator call on this mesh spreads over."""
+    ngrid = np.broadcast_to(np.asarray(ngrid, dtype=np.int32), (3,)).copy()
+    return _trv().trv_multi_device_count(ngrid.ctypes.data_as(_ip))
 
 
 def release_contexts():

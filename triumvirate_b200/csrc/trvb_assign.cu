@@ -1653,25 +1653,48 @@ extern "C" int trvb_cat_create(trvb_ctx* ctx, trvb_cat** out, long long n,
   cat->owner = ctx; cat->n = n;
   const size_t nb = sizeof(double) * (size_t)n;
   const cudaMemcpyKind kind = src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  int peer = -1;   // >= 0: the device arrays live on that other GPU and are copied over
   if (src_on_device) {
-    // Device sources must live on the context's GPU (a single-process caller may have made
-    // another device current): a pointer of another device would fault or go over peer access.
+    // Device sources normally live on the context's GPU.  In a single-process multi-GPU run
+    // the caller's arrays belong to one GPU only: the other contexts copy them over
+    // (cudaMemcpyPeer).  Anything else (host memory passed as device memory) is an error.
     const double* srcs[5] = {x, y, z, w, los};
     for (const double* p : srcs) {
       if (!p) continue;
       cudaPointerAttributes attr;
       TRVB_CUDA(cudaPointerGetAttributes(&attr, p));
-      const bool ok = (attr.type == cudaMemoryTypeDevice && attr.device == ctx->device)
-        || attr.type == cudaMemoryTypeManaged;
-      if (!ok) {
+      if (attr.type == cudaMemoryTypeManaged) continue;
+      if (attr.type != cudaMemoryTypeDevice) {
         delete cat;
-        trvb_set_error("trvb_cat_create: device array %p is not memory of GPU %d (type %d, "
-                       "device %d); create the context on the GPU that holds the catalogue",
-                       (const void*)p, ctx->device, (int)attr.type, attr.device);
+        trvb_set_error("trvb_cat_create: array %p passed as device memory is not (type %d)",
+                       (const void*)p, (int)attr.type);
         return 2;
+      }
+      if (attr.device != ctx->device) {
+        if (peer >= 0 && peer != attr.device) {
+          delete cat;
+          trvb_set_error("trvb_cat_create: device arrays spread over GPUs %d and %d", peer, attr.device);
+          return 2;
+        }
+        peer = attr.device;
+      }
+    }
+    if (peer >= 0) {
+      src_on_device = 1;   // copy, never borrow
+      // direct NVLink copies instead of staging through the host
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, ctx->device, peer) == cudaSuccess && can) {
+        const cudaError_t pe = cudaDeviceEnablePeerAccess(peer, 0);
+        if (pe != cudaSuccess) cudaGetLastError();   // already enabled
+      } else {
+        cudaGetLastError();
       }
     }
   }
+  auto copy_in = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
+    if (peer >= 0) return cudaMemcpyPeerAsync(dst, ctx->device, src, peer, bytes, ctx->stream);
+    return cudaMemcpyAsync(dst, src, bytes, kind, ctx->stream);
+  };
   if (src_on_device == 2) {
     // Borrowed: the caller keeps the coordinate arrays alive and unchanged for the
     // life of the catalogue (one estimator call); no copy, never freed here.
@@ -1681,26 +1704,27 @@ extern "C" int trvb_cat_create(trvb_ctx* ctx, trvb_cat** out, long long n,
     TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->x, nb));
     TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->y, nb));
     TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->z, nb));
-    TRVB_CUDA(cudaMemcpyAsync(cat->x, x, nb, kind, ctx->stream));
-    TRVB_CUDA(cudaMemcpyAsync(cat->y, y, nb, kind, ctx->stream));
-    TRVB_CUDA(cudaMemcpyAsync(cat->z, z, nb, kind, ctx->stream));
+    TRVB_CUDA(copy_in(cat->x, x, nb));
+    TRVB_CUDA(copy_in(cat->y, y, nb));
+    TRVB_CUDA(copy_in(cat->z, z, nb));
   }
   if (w) {
     TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->w, nb));
-    TRVB_CUDA(cudaMemcpyAsync(cat->w, w, nb, kind, ctx->stream));
+    TRVB_CUDA(copy_in(cat->w, w, nb));
   }
   if (los) {
     double* tmp = nullptr;
     TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->los, 3 * nb));
-    if (src_on_device) {
+    const bool los_in_place = src_on_device && peer < 0;
+    if (los_in_place) {
       tmp = const_cast<double*>(los);
     } else {
       TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&tmp, 3 * nb));
-      TRVB_CUDA(cudaMemcpyAsync(tmp, los, 3 * nb, kind, ctx->stream));
+      TRVB_CUDA(copy_in(tmp, los, 3 * nb));
     }
     k_los_to_soa<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(tmp, n, cat->los);
     TRVB_LAUNCH_CHECK();
-    if (!src_on_device) {
+    if (!los_in_place) {
       TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
       TRVB_CUDA(trvb_dev_free_raw(ctx, tmp));
     }

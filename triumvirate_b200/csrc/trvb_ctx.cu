@@ -361,6 +361,7 @@ extern "C" int trvb_ctx_sync(trvb_ctx* ctx) {
 }
 
 extern "C" void* trvb_ctx_stream(trvb_ctx* ctx) { return (void*)ctx->stream; }
+extern "C" int trvb_ctx_device(const trvb_ctx* ctx) { return ctx ? ctx->device : -1; }
 extern "C" long long trvb_ctx_nmesh(const trvb_ctx* ctx) { return ctx->g.nmesh; }
 
 extern "C" size_t trvb_mesh_bytes(const trvb_ctx* ctx, int layout) {

@@ -6,10 +6,35 @@ independent entries of the data vector -- the (k1, k2) bin pairs of every
 (m1, m2, M) term, S/threept.cpp:1902-1904, 2137-2139 -- are dealt to the ranks;
 each entry is produced by exactly one rank (zeros elsewhere), so a single small
 all-reduce(sum) of ``4 * dv_dim`` doubles over NCCL/NVLink completes the result
-and is bit-identical to the single-GPU one.  ``torch.distributed`` is plumbing
-only: ``nccl`` on GPUs, ``gloo`` in the CPU tests.
+and is bit-identical to the single-GPU one.
+
+The exchange itself lives behind the C API (``trv_comm_init`` / ``trvb_allreduce``,
+NCCL bound inside ``libtrvb.so``): once :func:`init_comm` has attached the
+communicator, ``core.threept(..., part_rank=r, part_count=R)`` returns the complete
+measurement on every rank with no Python in the data path.  ``torch.distributed``
+only ships the 128-byte NCCL id at start-up (any backend) and serves the CPU tests
+(``gloo``), where :func:`allreduce_result` sums the partial vectors instead.
 """
 import numpy as np
+
+
+def init_comm(group=None):
+    """Attach an NCCL communicator spanning the ranks of ``group`` to this process's
+    estimator calls (collective).  Needs an initialised ``torch.distributed`` group of
+    any backend to ship the id; returns the communicator size."""
+    import torch
+    import torch.distributed as dist
+    from . import core
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if world == 1:
+        return 1
+    ident = [core.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ident, src=0, group=group)
+    core.comm_init(world, rank, ident[0])
+    return core.comm_size()
 
 _STAT_KEYS = {"bispec": ("bk_raw", "bk_shot"), "3pcf": ("zeta_raw", "zeta_shot")}
 
@@ -23,13 +48,13 @@ def owners(form, degrees, num_bins, world_size, idx_bin=0):
     return core.partition_owners(form, degrees, num_bins, world_size, idx_bin=idx_bin)
 
 
-def bispec_owners(form, degrees, num_bins, world_size, idx_bin=0):
-    """Shot-noise owner of every bispectrum entry: with two or more ranks the LAST rank
-    computes the shot noise of every entry (its full-grid inverse FFT does not depend on
-    the pair partition); the pairs are dealt to all ranks with the last one handicapped
-    by the cost of that branch (``bispec_share`` in src/threept.cpp -- the exact pair
-    owners depend on the mesh and sub-grid sizes).  The 3PCF keeps both on the pair
-    owner."""
+def shot_noise_owners(form, degrees, num_bins, world_size, idx_bin=0):
+    """Rank that computes the SHOT NOISE of every bispectrum entry: with two or more ranks
+    the last rank does, for every entry (its full-grid inverse FFT does not depend on the
+    pair partition).  The raw-bispectrum (pair) owners of a bispectrum call are
+    :func:`owners` with the last rank's share cut short by the cost of that branch
+    (``bispec_share`` in src/threept.cpp; the cut depends on the mesh and sub-grid sizes,
+    so :func:`owners` is exact for the 3PCF and for bispectrum runs on one rank only)."""
     own = owners(form, degrees, num_bins, max(world_size, 1), idx_bin=idx_bin)
     if world_size < 2:
         return own
@@ -71,8 +96,9 @@ def allreduce_result(out, stat, group=None, device=None):
 
 def threept(stat, *args, group=None, device=None, **kwargs):
     """``core.threept`` / ``core.threept_box_arrays`` on this rank's share of the
-    entries followed by the all-reduce.  Pass ``x_ptr=...`` style arguments
-    through ``kwargs`` exactly as for the single-GPU call."""
+    entries; the sum over ranks happens inside the call when :func:`init_comm` attached
+    the NCCL communicator, else through ``torch.distributed``.  Pass ``x_ptr=...`` style
+    arguments through ``kwargs`` exactly as for the single-GPU call."""
     import torch.distributed as dist
     from . import core
     rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -80,4 +106,6 @@ def threept(stat, *args, group=None, device=None, **kwargs):
     kwargs.update(part_rank=rank, part_count=world)
     fn = core.threept_box_arrays if kwargs.pop("_arrays", False) else core.threept
     out = fn(stat, *args, **kwargs)
+    if core.comm_size() == world:
+        return out
     return allreduce_result(out, stat, group=group, device=device)

@@ -53,6 +53,22 @@ class DeviceScope {
  private:
   int prev_;
 };
+/// Communicator of a one-process-per-GPU run (trv_comm_init / trv::dev::comm_init), or
+/// null.  When it spans `part_count` ranks the estimators finish with one all-reduce of
+/// their result vectors over NCCL, so every rank returns the complete measurement.
+trvb_comm* process_comm();
+/// Rank 0 creates the 128-byte id (ncclGetUniqueId) and ships it to the other ranks by
+/// whatever channel launched them; every rank then calls comm_init (collective).
+void comm_unique_id(char id[128]);
+void comm_init(int nranks, int rank, const char id[128]);
+void comm_finalize();
+/// In-place sum over the ranks of the process communicator (no-op without one).
+void allreduce(trvb_ctx* ctx, double* buf, long long n);
+/// Number of GPUs a SINGLE-process estimator call spreads over: every usable device
+/// (trv::sys::get_gpu_count(), i.e. capped by TRV_GPU_MAXNUM, S/monitor.cpp:258-324)
+/// unless the process is pinned to one (TRV_GPU_DEVICE, LOCAL_RANK), a process
+/// communicator exists, TRV_GPU_MULTI=0, or the mesh is small (< 256^3 cells).
+int multi_device_count(const trv::ParameterSet& params);
 /// Shared device context for one (device, ngrid, boxsize, assignment order).
 std::shared_ptr<trvb_ctx> acquire_context(const trv::ParameterSet& params);
 /// Most recently acquired context (null if none is alive); lets callers put

@@ -326,6 +326,41 @@ void* trv_last_stream() {
 
 void trv_release_contexts() { trv::dev::release_contexts(); }
 
+int trv_comm_unique_id(char id[128]) {
+  return guarded([&]() { trv::dev::comm_unique_id(id); });
+}
+
+int trv_comm_init(int nranks, int rank, const char id[128]) {
+  return guarded([&]() { trv::dev::comm_init(nranks, rank, id); });
+}
+
+int trv_comm_size(void) {
+  trvb_comm* c = trv::dev::process_comm();
+  return c ? trvb_comm_size(c) : 1;
+}
+
+int trv_allreduce(double* buf, long long n) {
+  return guarded([&]() {
+    if (trv::dev::process_comm() == nullptr) return;
+    trv::ParameterSet p;
+    for (int ax = 0; ax < 3; ax++) { p.boxsize[ax] = 1.; p.ngrid[ax] = 4; }
+    p.assignment_order = 1;
+    trvb_ctx* ctx = trv::dev::last_context();
+    std::shared_ptr<trvb_ctx> hold;
+    if (ctx == nullptr) { hold = trv::dev::acquire_context(p); ctx = hold.get(); }
+    trv::dev::allreduce(ctx, buf, n);
+  });
+}
+
+void trv_comm_finalize(void) { trv::dev::comm_finalize(); }
+
+int trv_multi_device_count(const int* ngrid) {
+  trv::ParameterSet p;
+  for (int ax = 0; ax < 3; ax++) { p.boxsize[ax] = 1.; p.ngrid[ax] = ngrid[ax]; }
+  p.nmesh = (long long)ngrid[0] * ngrid[1] * ngrid[2];
+  return trv::dev::multi_device_count(p);
+}
+
 /// Phase timer of the estimator pipeline (development / bench aid).
 void trv_profile_enable(int on) { trv::dev::profile_enable(on != 0); }
 

@@ -105,6 +105,44 @@ std::shared_ptr<trvb_ctx> acquire_context(const trv::ParameterSet& params) {
 
 trvb_ctx* last_context() { return g_last_ctx; }
 
+namespace {
+trvb_comm* g_comm = nullptr;
+bool g_prof_enabled() { return profile_enabled(); }
+}  // namespace
+
+trvb_comm* process_comm() { return g_comm; }
+
+void comm_unique_id(char id[128]) {
+  check(trvb_comm_unique_id(id), "trvb_comm_unique_id");
+}
+
+void comm_init(int nranks, int rank, const char id[128]) {
+  comm_finalize();
+  check(trvb_comm_create(&g_comm, select_device(), nranks, rank, id), "trvb_comm_create");
+}
+
+void comm_finalize() {
+  if (g_comm != nullptr) { trvb_comm_destroy(g_comm); g_comm = nullptr; }
+}
+
+void allreduce(trvb_ctx* ctx, double* buf, long long n) {
+  if (g_comm == nullptr) return;
+  check(trvb_allreduce(ctx, g_comm, buf, n), "trvb_allreduce");
+}
+
+int multi_device_count(const trv::ParameterSet& params) {
+  if (g_comm != nullptr || g_prof_enabled()) return 1;
+  for (const char* name : {"TRV_GPU_DEVICE", "LOCAL_RANK"}) {
+    const char* v = std::getenv(name);
+    if (v != nullptr && v[0] != '\0') return 1;
+  }
+  const char* multi = std::getenv("TRV_GPU_MULTI");
+  if (multi != nullptr && multi[0] == '0') return 1;
+  if (params.nmesh < (1LL << 24) && !(multi != nullptr && multi[0] == '1')) return 1;
+  const int n = trvs::get_gpu_count();
+  return n > 1 ? n : 1;
+}
+
 void release_contexts() {
   std::lock_guard<std::mutex> lock(g_ctx_mutex);
   g_ctx_recent.clear();

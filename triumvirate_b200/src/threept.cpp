@@ -21,6 +21,7 @@
 #include <map>
 #include <memory>
 #include <set>
+#include <thread>
 #include <tuple>
 
 namespace trvs = trv::sys;
@@ -1141,6 +1142,73 @@ trv::ThreePCFMeasurements threepcf_impl(
 // Public entry points
 // =====================================================================
 
+namespace {
+
+/// Runs one estimator call over the GPUs.
+///  * Caller-driven partition (params.part_count > 1, one process per GPU): the call
+///    computes this rank's share; when the process communicator spans part_count ranks the
+///    raw and shot-noise vectors are summed over NCCL, so every rank returns the complete
+///    measurement (every entry comes from exactly one rank: the sum adds zeros).
+///  * Otherwise, when the process sees several usable GPUs (dev::multi_device_count), one
+///    host thread per GPU computes a share with its own context and the shares are summed on
+///    the host in rank order -- the single-process multi-GPU mode of the reference
+///    (S/field.cpp:212-235, S/monitor.cpp:258-324) without its cuFFT-Xt slab transforms.
+/// `run(p)` builds the engine on the calling thread's current device and returns the result.
+template <class Result, class Run>
+Result run_over_gpus(trv::ParameterSet& params, Run run,
+                     std::vector<cdouble> Result::* raw, std::vector<cdouble> Result::* shot) {
+  if (params.part_count > 1) {
+    Result out = run(params);
+    trvb_comm* comm = dev::process_comm();
+    if (comm != nullptr && trvb_comm_size(comm) == params.part_count) {
+      const size_t n = (out.*raw).size();
+      std::vector<double> buf(4 * n);
+      for (size_t i = 0; i < n; i++) {
+        buf[2*i] = (out.*raw)[i].real(); buf[2*i + 1] = (out.*raw)[i].imag();
+        buf[2*n + 2*i] = (out.*shot)[i].real(); buf[2*n + 2*i + 1] = (out.*shot)[i].imag();
+      }
+      dev::allreduce(dev::last_context(), buf.data(), (long long)buf.size());
+      for (size_t i = 0; i < n; i++) {
+        (out.*raw)[i] = cdouble(buf[2*i], buf[2*i + 1]);
+        (out.*shot)[i] = cdouble(buf[2*n + 2*i], buf[2*n + 2*i + 1]);
+      }
+    }
+    return out;
+  }
+  const int ndev = dev::multi_device_count(params);
+  if (ndev <= 1) return run(params);
+
+  std::vector<Result> parts(ndev);
+  std::vector<std::string> errors(ndev);
+  std::vector<std::thread> workers;
+  for (int r = 0; r < ndev; r++) {
+    workers.emplace_back([&, r]() {
+      try {
+        dev::check(trvb_set_current_device(r), "trvb_set_current_device");
+        trv::ParameterSet p = params;
+        p.part_rank = r; p.part_count = ndev;
+        parts[r] = run(p);
+      } catch (const std::exception& e) {
+        errors[r] = e.what()[0] ? e.what() : "unknown error";
+      }
+    });
+  }
+  for (std::thread& w : workers) w.join();
+  for (int r = 0; r < ndev; r++) {
+    if (!errors[r].empty()) throw trvs::DeviceError("GPU %d: %s", r, errors[r].c_str());
+  }
+  Result out = std::move(parts[0]);
+  for (int r = 1; r < ndev; r++) {
+    for (size_t i = 0; i < (out.*raw).size(); i++) {
+      (out.*raw)[i] += (parts[r].*raw)[i];
+      (out.*shot)[i] += (parts[r].*shot)[i];
+    }
+  }
+  return out;
+}
+
+}  // namespace
+
 trv::BispecMeasurements compute_bispec(
   ParticleCatalogue& catalogue_data, ParticleCatalogue& catalogue_rand,
   LineOfSight* los_data, LineOfSight* los_rand,
@@ -1151,8 +1219,11 @@ trv::BispecMeasurements compute_bispec(
     trvs::logger.stat("Computing bispectrum from paired survey-type catalogues...");
   }
   validate_multipole_coupling(params);
-  Engine eng(params, catalogue_data, &catalogue_rand, los_data, los_rand);
-  trv::BispecMeasurements out = bispec_impl(eng, params, kbinning, norm_factor);
+  trv::BispecMeasurements out = run_over_gpus<trv::BispecMeasurements>(
+    params, [&](trv::ParameterSet& p) {
+      Engine eng(p, catalogue_data, &catalogue_rand, los_data, los_rand);
+      return bispec_impl(eng, p, kbinning, norm_factor);
+    }, &trv::BispecMeasurements::bk_raw, &trv::BispecMeasurements::bk_shot);
   if (trvs::currTask == 0) {
     trvs::logger.stat("... computed bispectrum from paired survey-type catalogues.");
   }
@@ -1170,8 +1241,11 @@ trv::BispecMeasurements compute_bispec_in_gpp_box(
       "in the global plane-parallel approximation...");
   }
   validate_multipole_coupling(params);
-  Engine eng(params, catalogue_data, nullptr, nullptr, nullptr);
-  trv::BispecMeasurements out = bispec_impl(eng, params, kbinning, norm_factor);
+  trv::BispecMeasurements out = run_over_gpus<trv::BispecMeasurements>(
+    params, [&](trv::ParameterSet& p) {
+      Engine eng(p, catalogue_data, nullptr, nullptr, nullptr);
+      return bispec_impl(eng, p, kbinning, norm_factor);
+    }, &trv::BispecMeasurements::bk_raw, &trv::BispecMeasurements::bk_shot);
   if (trvs::currTask == 0) {
     trvs::logger.stat(
       "... computed bispectrum from a periodic-box simulation-type catalogue "
@@ -1191,8 +1265,11 @@ trv::ThreePCFMeasurements compute_3pcf(
       "Computing three-point correlation function from paired survey-type catalogues...");
   }
   validate_multipole_coupling(params);
-  Engine eng(params, catalogue_data, &catalogue_rand, los_data, los_rand);
-  trv::ThreePCFMeasurements out = threepcf_impl(eng, params, rbinning, norm_factor);
+  trv::ThreePCFMeasurements out = run_over_gpus<trv::ThreePCFMeasurements>(
+    params, [&](trv::ParameterSet& p) {
+      Engine eng(p, catalogue_data, &catalogue_rand, los_data, los_rand);
+      return threepcf_impl(eng, p, rbinning, norm_factor);
+    }, &trv::ThreePCFMeasurements::zeta_raw, &trv::ThreePCFMeasurements::zeta_shot);
   if (trvs::currTask == 0) {
     trvs::logger.stat(
       "... computed three-point correlation function from paired survey-type catalogues.");
@@ -1211,8 +1288,11 @@ trv::ThreePCFMeasurements compute_3pcf_in_gpp_box(
       "simulation-type catalogue in the global plane-parallel approximation...");
   }
   validate_multipole_coupling(params);
-  Engine eng(params, catalogue_data, nullptr, nullptr, nullptr);
-  trv::ThreePCFMeasurements out = threepcf_impl(eng, params, rbinning, norm_factor);
+  trv::ThreePCFMeasurements out = run_over_gpus<trv::ThreePCFMeasurements>(
+    params, [&](trv::ParameterSet& p) {
+      Engine eng(p, catalogue_data, nullptr, nullptr, nullptr);
+      return threepcf_impl(eng, p, rbinning, norm_factor);
+    }, &trv::ThreePCFMeasurements::zeta_raw, &trv::ThreePCFMeasurements::zeta_shot);
   if (trvs::currTask == 0) {
     trvs::logger.stat(
       "... computed three-point correlation function from a periodic-box "
@@ -1233,8 +1313,11 @@ trv::ThreePCFWindowMeasurements compute_3pcf_window(
       "Computing three-point correlation function window %sfrom random catalogue...", tag);
   }
   validate_multipole_coupling(params);
-  Engine eng(params, catalogue_rand, los_rand, alpha);
-  trv::ThreePCFMeasurements res = threepcf_impl(eng, params, rbinning, norm_factor, wide_angle);
+  trv::ThreePCFMeasurements res = run_over_gpus<trv::ThreePCFMeasurements>(
+    params, [&](trv::ParameterSet& p) {
+      Engine eng(p, catalogue_rand, los_rand, alpha);
+      return threepcf_impl(eng, p, rbinning, norm_factor, wide_angle);
+    }, &trv::ThreePCFMeasurements::zeta_raw, &trv::ThreePCFMeasurements::zeta_shot);
   trv::ThreePCFWindowMeasurements out;
   out.dim = res.dim;
   out.r1_bin = std::move(res.r1_bin); out.r2_bin = std::move(res.r2_bin);
@@ -1261,8 +1344,11 @@ trv::BispecMeasurements compute_bispec_in_gpp_box(
 ) {
   trvs::logger.reset_level(params.verbose);
   validate_multipole_coupling(params);
-  Engine eng(params, nparticles, x, y, z, on_device);
-  return bispec_impl(eng, params, kbinning, norm_factor);
+  return run_over_gpus<trv::BispecMeasurements>(
+    params, [&](trv::ParameterSet& p) {
+      Engine eng(p, nparticles, x, y, z, on_device);
+      return bispec_impl(eng, p, kbinning, norm_factor);
+    }, &trv::BispecMeasurements::bk_raw, &trv::BispecMeasurements::bk_shot);
 }
 
 trv::ThreePCFMeasurements compute_3pcf_in_gpp_box(
@@ -1271,8 +1357,11 @@ trv::ThreePCFMeasurements compute_3pcf_in_gpp_box(
 ) {
   trvs::logger.reset_level(params.verbose);
   validate_multipole_coupling(params);
-  Engine eng(params, nparticles, x, y, z, on_device);
-  return threepcf_impl(eng, params, rbinning, norm_factor);
+  return run_over_gpus<trv::ThreePCFMeasurements>(
+    params, [&](trv::ParameterSet& p) {
+      Engine eng(p, nparticles, x, y, z, on_device);
+      return threepcf_impl(eng, p, rbinning, norm_factor);
+    }, &trv::ThreePCFMeasurements::zeta_raw, &trv::ThreePCFMeasurements::zeta_shot);
 }
 
 }  // namespace trv
