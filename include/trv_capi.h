@@ -181,7 +181,8 @@ int trv_norm_powspec(
 
 /* trv::MeshField pipeline for intermediate checks (S/field.cpp:569-1112,
  * 1496-1720, 1764-1785).  stage: 0 assignment, 1 + fourier_transform,
- * 2 + apply_assignment_compensation, 3 + inv_fourier_transform.  Weights:
+ * 2 + apply_assignment_compensation, 3 + inv_fourier_transform; 4 = assignment followed by
+ * apply_wide_angle_pow_law_kernel at order (i_wa, j_wa) = (1, 2) (S/field.cpp:1727-1762).  Weights:
  * complex per particle (w_re, w_im) or NULL (unit).  field_out: 2*nmesh doubles. */
 int trv_mesh(
   int stage, int subtract_mean, int interlace, int deterministic,
@@ -193,6 +194,11 @@ int trv_mesh(
 /* trv::maths (S/maths.cpp:167-375): reduced spherical harmonics at n positions
  * (pos is (n, 3); out interleaved), spline-evaluated and exact j_l, Wigner 3-j. */
 void trv_ylm(int ell, int m, const double* pos, int n, double* out);
+/* SphericalHarmonicCalculator::store_reduced_spherical_harmonic_in_fourier_space
+ * (fourier != 0) / _in_config_space (S/maths.cpp:222-302): y_lm at every mesh cell,
+ * out holds 2 * n_x n_y n_z doubles (host tables; the estimators do not use them). */
+int trv_ylm_mesh(int fourier, int ell, int m, const double* boxsize, const int* ngrid,
+                 double* out);
 void trv_sjl(int ell, const double* x, int n, double* out);
 double trv_sjl_exact(int ell, double x);
 double trv_w3j(int j1, int j2, int j3, int m1, int m2, int m3);

@@ -447,6 +447,17 @@ def ylm(ell, m, pos):
     return out.view(np.complex128)
 
 
+def ylm_mesh(space, ell, m, boxsize, ngrid):
+    """``store_reduced_spherical_harmonic_in_{fourier,config}_space`` (S/maths.cpp:222-302)."""
+    boxsize = np.broadcast_to(np.asarray(boxsize, dtype=np.float64), (3,)).copy()
+    ngrid = np.broadcast_to(np.asarray(ngrid, dtype=np.int32), (3,)).copy()
+    out = np.zeros(2 * int(np.prod(ngrid)))
+    _check(lib().trvref_ylm_mesh(C.c_int(1 if space == "fourier" else 0), C.c_int(ell), C.c_int(m),
+                                 boxsize.ctypes.data_as(_dp), ngrid.ctypes.data_as(_ip),
+                                 out.ctypes.data_as(_dp)))
+    return out.view(np.complex128).reshape(tuple(int(v) for v in ngrid))
+
+
 def sjl(ell, x):
     """``SphericalBesselCalculator(ell).eval(x)`` (S/maths.cpp:309-375)."""
     x = np.ascontiguousarray(x, dtype=np.float64).ravel()

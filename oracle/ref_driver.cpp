@@ -594,6 +594,13 @@ int trvref_mesh(
       double nbar = double(cat.ntotal) / mesh.vol;
       for (long long g = 0; g < params.nmesh; g++) mesh.field[g][0] -= nbar;
     }
+    if (stage == 4) {
+      // assignment followed by MeshField::apply_wide_angle_pow_law_kernel at order (1, 2)
+      mesh.params.i_wa = 1; mesh.params.j_wa = 2;
+      mesh.apply_wide_angle_pow_law_kernel();
+      std::memcpy(field_out, mesh.field, sizeof(fftw_complex) * params.nmesh);
+      return 0;
+    }
     if (stage >= 1) mesh.fourier_transform();
     if (stage >= 2) mesh.apply_assignment_compensation();
     if (stage >= 3) mesh.inv_fourier_transform();
@@ -612,6 +619,24 @@ void trvref_ylm(int ell, int m, const double* pos, int n, double* out) {
     std::complex<double> y = trv::maths::SphericalHarmonicCalculator::
       calc_reduced_spherical_harmonic(ell, m, p);
     out[2*i] = y.real(); out[2*i+1] = y.imag();
+  }
+}
+
+// SphericalHarmonicCalculator::store_reduced_spherical_harmonic_in_{fourier,config}_space
+// (S/maths.cpp:222-302); out holds 2 * nmesh doubles.
+int trvref_ylm_mesh(int fourier, int ell, int m, const double* boxsize, const int* ngrid,
+                    double* out) {
+  try {
+    const long long nmesh = (long long)ngrid[0] * ngrid[1] * ngrid[2];
+    std::vector< std::complex<double> > tab(nmesh);
+    typedef trv::maths::SphericalHarmonicCalculator SHC;
+    if (fourier) SHC::store_reduced_spherical_harmonic_in_fourier_space(ell, m, boxsize, ngrid, tab);
+    else SHC::store_reduced_spherical_harmonic_in_config_space(ell, m, boxsize, ngrid, tab);
+    std::memcpy(out, tab.data(), sizeof(double) * 2 * nmesh);
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
   }
 }
 

@@ -51,19 +51,25 @@ TEST_PARAMS = {
 }
 
 
-@pytest.fixture(scope="module")
-def trvcy():
+def _load_binding(name):
+    import importlib
     sys.path.insert(0, str(ROOT / "oracle"))
     import build_refcy
-    if not build_refcy.build():
-        pytest.skip("oracle/_ref/trvcy not built and /root/reference absent")
-    sys.path.insert(0, str(ROOT / "oracle" / "_ref"))
-    import trvcy._particles   # noqa: F401
-    import trvcy._threept     # noqa: F401
-    import trvcy._twopt       # noqa: F401
-    import trvcy.dataobjs     # noqa: F401
-    import trvcy.parameters   # noqa: F401
-    return trvcy
+    if not build_refcy.build(patched=(name == "trvcy_b200")):
+        pytest.skip(f"oracle/_ref/{name} not built and /root/reference absent")
+    if str(ROOT / "oracle" / "_ref") not in sys.path:
+        sys.path.insert(0, str(ROOT / "oracle" / "_ref"))
+    pkg = importlib.import_module(name)
+    for sub in ("_particles", "_threept", "_twopt", "dataobjs", "parameters"):
+        importlib.import_module(f"{name}.{sub}")
+    return pkg
+
+
+@pytest.fixture(scope="module", params=["trvcy", "trvcy_b200"])
+def trvcy(request):
+    """The reference's Cython layer built against libtrv_b200.so: unmodified (`trvcy`) and
+    with the Python-boundary fixes of bindings/patch_bindings.py applied (`trvcy_b200`)."""
+    return _load_binding(request.param)
 
 
 def _paramset(trvcy, catalogue_type, statistic_type, degrees, form, idx_bin, rng):
@@ -227,3 +233,76 @@ def test_twopt_goldens_through_reference_cython(trvcy, stat, degree, golden_data
     norm = trvcy._twopt._calc_powspec_normalisation_from_particles(cat_r, alpha=alpha)
     out = getattr(trvcy._twopt, f"_compute_{name}")(cat_d, cat_r, los_d, los_r, ps, binning, norm)
     check_twopt_against_golden(out, load_golden(f"{prefix}{degree}_lpp.txt"), stat)
+
+
+# ---- Python-boundary fixes: bindings/patch_bindings.py -----------
+
+def test_patched_binding_turns_device_errors_into_python_exceptions(monkeypatch,
+                                                                    golden_data_catalogue):
+    """`except +` on the compute_* externs (T/_threept.pyx:50-95 have none): with the GPU
+    path disabled the estimator throws trv::sys::DeviceError -- the patched binding raises
+    RuntimeError where the unmodified one would terminate the interpreter."""
+    from triumvirate_b200 import catalogue as tcat
+    mod = _load_binding("trvcy_b200")
+    monkeypatch.setenv("TRV_GPU_MODE", "off")
+    ps = _paramset(mod, "sim", "bispec", (0, 0, 0), "diag", None, (0.005, 0.105))
+    binning = mod.dataobjs.Binning.from_parameter_set(ps)
+    data = golden_data_catalogue
+    cat = _catalogue(mod, tcat.periodise(data[:3], 1000.), data[3])
+    with pytest.raises(RuntimeError, match="CUDA device"):
+        mod._threept._compute_bispec_in_gpp_box(cat, ps, binning, 1.)
+    with pytest.raises(RuntimeError, match="CUDA device"):
+        mod._twopt._compute_powspec_in_gpp_box(cat, ps, binning, 1.)
+    with pytest.raises(RuntimeError, match="CUDA device"):
+        mod._threept._calc_bispec_normalisation_from_mesh(cat, ps, 1.)
+
+
+def test_patched_binding_catalogue_upload_is_one_pass():
+    """Raw-array catalogue loader instead of six by-value std::vector conversions
+    (T/_particles.pxd:11-14): 2e6 rows in well under a second, same contents."""
+    import time
+    plain, fixed = _load_binding("trvcy"), _load_binding("trvcy_b200")
+    gen = np.random.default_rng(3)
+    n = 2 * 10**6
+    cols = [gen.uniform(0., 1000., n) for _ in range(3)] + [np.full(n, 1.e-4), np.ones(n),
+                                                              gen.uniform(0.5, 1., n)]
+    t0 = time.perf_counter()
+    a = fixed._particles._ParticleCatalogue(*cols, verbose=20)
+    t_fixed = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    b = plain._particles._ParticleCatalogue(*cols, verbose=20)
+    t_plain = time.perf_counter() - t0
+    na = fixed._threept._calc_bispec_normalisation_from_particles(a, 0.5)
+    nb = plain._threept._calc_bispec_normalisation_from_particles(b, 0.5)
+    assert abs(na - nb) <= 1.e-12 * abs(nb)
+    assert t_fixed < 0.5 and t_fixed < t_plain, (t_fixed, t_plain)
+    with pytest.raises(ValueError):
+        fixed._particles._ParticleCatalogue(cols[0][:5], *cols[1:], verbose=20)
+
+
+@pytest.mark.gpu
+def test_patched_binding_los_marshalling_is_a_memcpy(golden_data_catalogue):
+    """memcpy of the (N, 3) array instead of the per-particle Python loop
+    (T/_threept.pyx:138-152): a survey call with 2e6 randoms spends less time in the binding
+    than the unmodified loop alone, and returns the same measurement."""
+    import time
+    from triumvirate_b200 import catalogue as tcat
+    plain, fixed = _load_binding("trvcy"), _load_binding("trvcy_b200")
+    gen = np.random.default_rng(17)
+    nr = 2 * 10**6
+    rand = np.vstack([gen.uniform(-500., 500., (3, nr)), np.full((1, nr), 2.e-3)])
+    data = np.vstack([gen.uniform(-500., 500., (3, 20000)), np.full((1, 20000), 2.e-3)])
+    los_d, los_r = tcat.compute_los(data[:3]), tcat.compute_los(rand[:3])
+    pos_d, pos_r = tcat.centre(data[:3], rand[:3], 1000.)
+    res, times = {}, {}
+    for name, mod in (("fixed", fixed), ("plain", plain)):
+        ps = _paramset(mod, "survey", "bispec", (2, 0, 2), "diag", None, (0.005, 0.105))
+        binning = mod.dataobjs.Binning.from_parameter_set(ps)
+        cat_d, cat_r = _catalogue(mod, pos_d, data[3]), _catalogue(mod, pos_r, rand[3])
+        mod._threept._compute_bispec(cat_d, cat_r, los_d, los_r, ps, binning, 1.)   # warm-up
+        t0 = time.perf_counter()
+        res[name] = mod._threept._compute_bispec(cat_d, cat_r, los_d, los_r, ps, binning, 1.)
+        times[name] = time.perf_counter() - t0
+    assert np.allclose(res["fixed"]["bk_raw"], res["plain"]["bk_raw"], rtol=1.e-10, atol=0.)
+    assert np.array_equal(res["fixed"]["nmodes_1"], res["plain"]["nmodes_1"])
+    assert times["fixed"] < 0.5 * times["plain"], times

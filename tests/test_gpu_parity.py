@@ -290,6 +290,16 @@ def test_assignment_shadow_mesh_and_interlacing(core, oracle, assignment):
     assert np.max(np.abs(out - ref)) <= 1.e-12 * np.max(np.abs(ref))
 
 
+def test_meshfield_wide_angle_pow_law_kernel(core, oracle):
+    """MeshField::apply_wide_angle_pow_law_kernel (S/field.cpp:1727-1762) on an assigned mesh
+    (stage 4 of the mesh pipeline drivers: order (i_wa, j_wa) = (1, 2))."""
+    L, ng, n = (300., 250., 420.), (16, 12, 20), 3000
+    pos = _random_catalogue(21, n, 1.) * np.array(L)[:, None]
+    ref = oracle.mesh(pos, L, ng, "tsc", stage=4)
+    out = core.mesh(pos, L, ng, "tsc", stage=4, deterministic=True)
+    assert np.max(np.abs(out - ref)) <= 1.e-13 * np.max(np.abs(ref))
+
+
 @pytest.mark.parametrize("stage", [1, 2, 3])
 def test_meshfield_pipeline(core, oracle, stage):
     """MeshField compat methods: FFT, window compensation, inverse FFT

@@ -157,3 +157,16 @@ def test_catalogue_helpers_match_oracle_restatement(oracle):
     assert np.array_equal(tcat.compute_los(d), oracle.compute_los(d))
     mid = 0.5 * (a[1].min(axis=1) + a[1].max(axis=1))
     assert np.allclose(mid, 500.)
+
+
+def test_reduced_harmonic_mesh_tables_equal_the_reference(oracle):
+    """SphericalHarmonicCalculator::store_reduced_spherical_harmonic_in_{fourier,config}_space
+    (S/maths.cpp:222-302): host tables kept for callers of the reference API."""
+    from triumvirate_b200 import core
+    box, ng = (300., 210., 450.), (8, 6, 10)
+    for space in ("fourier", "config"):
+        for ell, m in ((0, 0), (1, -1), (2, 1), (4, -3)):
+            a = core.ylm_mesh(space, ell, m, box, ng)
+            b = oracle.ylm_mesh(space, ell, m, box, ng)
+            assert a.shape == b.shape == ng
+            assert np.max(np.abs(a - b)) < 1.e-14, (space, ell, m)

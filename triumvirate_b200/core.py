@@ -435,6 +435,16 @@ def ylm(ell, m, pos):
     return out.view(np.complex128)
 
 
+def ylm_mesh(space, ell, m, boxsize, ngrid):
+    """``store_reduced_spherical_harmonic_in_{fourier,config}_space`` tables (host)."""
+    boxsize, ngrid = _box(boxsize, ngrid)
+    out = np.zeros(2 * int(np.prod(ngrid)))
+    _check(_trv().trv_ylm_mesh(C.c_int(1 if space == "fourier" else 0), C.c_int(ell), C.c_int(m),
+                               boxsize.ctypes.data_as(_dp), ngrid.ctypes.data_as(_ip),
+                               out.ctypes.data_as(_dp)))
+    return out.view(np.complex128).reshape(tuple(int(v) for v in ngrid))
+
+
 def sjl(ell, x):
     x = np.ascontiguousarray(x, dtype=np.float64).ravel()
     out = np.zeros(len(x))

@@ -175,6 +175,9 @@ class MeshField {
   void inv_fourier_transform();
 
   // -- Field operations (S/field.cpp:1764-1785) --
+  /// field(x) *= |x|^(-i_wa - j_wa) where |x| >= 1e-6 (params.i_wa, params.j_wa), x the
+  /// signed cell offset vector (S/field.cpp:1727-1762).
+  void apply_wide_angle_pow_law_kernel();
   void apply_assignment_compensation();
 
   // -- One-point statistics (S/field.cpp:1792-2010); y_lm by orders --

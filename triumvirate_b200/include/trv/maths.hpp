@@ -31,6 +31,21 @@ class SphericalHarmonicCalculator {
   static std::complex<double> calc_reduced_spherical_harmonic(
     const int ell, const int m, double pos[3]
   );
+  /// y_lm at the wavevector of every mesh cell, signed FFT index order, index
+  /// (i n_y + j) n_z + k (S/maths.cpp:222-261).  The device estimators never build these
+  /// tables (y_lm is evaluated in registers); they are kept for C++ callers of the
+  /// reference API.  Throws trv::sys::InvalidDataError when `ylm_out` is not sized n_x n_y n_z.
+  static void store_reduced_spherical_harmonic_in_fourier_space(
+    const int ell, const int m,
+    const double boxsize[3], const int ngrid[3],
+    std::vector< std::complex<double> >& ylm_out
+  );
+  /// The same at the signed position vector of every cell (S/maths.cpp:263-302).
+  static void store_reduced_spherical_harmonic_in_config_space(
+    const int ell, const int m,
+    const double boxsize[3], const int ngrid[3],
+    std::vector< std::complex<double> >& ylm_out
+  );
 };
 
 /// Interpolated spherical Bessel function (I/maths.hpp:262-312; S/maths.cpp:

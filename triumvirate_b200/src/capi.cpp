@@ -445,9 +445,15 @@ int trv_mesh(
       trv::dev::check(trvb_mesh_add_const(mesh.context(), mesh.device_view(), -nbar),
                       "trvb_mesh_add_const");
     }
-    if (stage >= 1) mesh.fourier_transform();
-    if (stage >= 2) mesh.apply_assignment_compensation();
-    if (stage >= 3) mesh.inv_fourier_transform();
+    if (stage == 4) {
+      // assignment followed by MeshField::apply_wide_angle_pow_law_kernel at order (1, 2)
+      mesh.params.i_wa = 1; mesh.params.j_wa = 2;
+      mesh.apply_wide_angle_pow_law_kernel();
+    } else {
+      if (stage >= 1) mesh.fourier_transform();
+      if (stage >= 2) mesh.apply_assignment_compensation();
+      if (stage >= 3) mesh.inv_fourier_transform();
+    }
     mesh.sync_host();
     std::memcpy(field_out, mesh.field, 2 * sizeof(double) * (size_t)params.nmesh);
   });
@@ -460,6 +466,18 @@ void trv_ylm(int ell, int m, const double* pos, int n, double* out) {
       calc_reduced_spherical_harmonic(ell, m, p);
     out[2*i] = y.real(); out[2*i+1] = y.imag();
   }
+}
+
+int trv_ylm_mesh(int fourier, int ell, int m, const double* boxsize, const int* ngrid,
+                 double* out) {
+  return guarded([&]() {
+    const long long nmesh = (long long)ngrid[0] * ngrid[1] * ngrid[2];
+    std::vector< std::complex<double> > tab(nmesh);
+    typedef trv::maths::SphericalHarmonicCalculator SHC;
+    if (fourier) SHC::store_reduced_spherical_harmonic_in_fourier_space(ell, m, boxsize, ngrid, tab);
+    else SHC::store_reduced_spherical_harmonic_in_config_space(ell, m, boxsize, ngrid, tab);
+    std::memcpy(out, tab.data(), sizeof(double) * 2 * nmesh);
+  });
 }
 
 void trv_sjl(int ell, const double* x, int n, double* out) {

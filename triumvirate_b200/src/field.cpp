@@ -431,6 +431,15 @@ void MeshField::inv_fourier_transform() {
   this->host_stale_ = true;
 }
 
+void MeshField::apply_wide_angle_pow_law_kernel() {
+  if (trvs::currTask == 0) {
+    trvs::logger.debug("Applying wide-angle power-law kernel to '%s'.", this->name.c_str());
+  }
+  dev::check(trvb_mesh_pow_law(this->ctx_.get(), this->mesh_.view(),
+                               this->params.i_wa + this->params.j_wa), "trvb_mesh_pow_law");
+  this->host_stale_ = true;
+}
+
 void MeshField::apply_assignment_compensation() {
   dev::check(trvb_compensate(this->ctx_.get(), this->mesh_.view()), "trvb_compensate");
   this->host_stale_ = true;

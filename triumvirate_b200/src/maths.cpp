@@ -168,6 +168,51 @@ std::complex<double> SphericalHarmonicCalculator::calc_reduced_spherical_harmoni
   return ylm;
 }
 
+namespace {
+
+/// Fill `out` with y_lm of (signed index) x (step per axis) for every mesh cell.
+void store_ylm_on_mesh(int ell, int m, const double step[3], const int ngrid[3],
+                       std::vector< std::complex<double> >& out) {
+  const long long nmesh = (long long)ngrid[0] * ngrid[1] * ngrid[2];
+  if ((long long)out.size() < nmesh) {
+    throw trv::sys::InvalidDataError(
+      "Output vector for reduced spherical harmonics holds %zu of %lld mesh cells.",
+      out.size(), nmesh);
+  }
+#pragma omp parallel for collapse(2)
+  for (int i = 0; i < ngrid[0]; i++) {
+    for (int j = 0; j < ngrid[1]; j++) {
+      double v[3];
+      v[0] = ((i < ngrid[0] / 2) ? i : i - ngrid[0]) * step[0];
+      v[1] = ((j < ngrid[1] / 2) ? j : j - ngrid[1]) * step[1];
+      std::complex<double>* row = out.data() + ((long long)i * ngrid[1] + j) * ngrid[2];
+      for (int k = 0; k < ngrid[2]; k++) {
+        v[2] = ((k < ngrid[2] / 2) ? k : k - ngrid[2]) * step[2];
+        row[k] = SphericalHarmonicCalculator::calc_reduced_spherical_harmonic(ell, m, v);
+      }
+    }
+  }
+}
+
+}  // namespace
+
+void SphericalHarmonicCalculator::store_reduced_spherical_harmonic_in_fourier_space(
+  const int ell, const int m, const double boxsize[3], const int ngrid[3],
+  std::vector< std::complex<double> >& ylm_out
+) {
+  const double dk[3] = {2. * M_PI / boxsize[0], 2. * M_PI / boxsize[1], 2. * M_PI / boxsize[2]};
+  store_ylm_on_mesh(ell, m, dk, ngrid, ylm_out);
+}
+
+void SphericalHarmonicCalculator::store_reduced_spherical_harmonic_in_config_space(
+  const int ell, const int m, const double boxsize[3], const int ngrid[3],
+  std::vector< std::complex<double> >& ylm_out
+) {
+  const double dr[3] = {boxsize[0] / double(ngrid[0]), boxsize[1] / double(ngrid[1]),
+                        boxsize[2] / double(ngrid[2])};
+  store_ylm_on_mesh(ell, m, dr, ngrid, ylm_out);
+}
+
 // ---------------------------------------------------------------------
 // Spline-interpolated spherical Bessel calculator.
 // ---------------------------------------------------------------------
