@@ -38,6 +38,18 @@ class Binning {
   void compute_binning();
 };
 
+/// Mesh vectors falling in each bin (I/dataobjs.hpp:166-175).
+struct BinnedVectors {
+  int count = 0;
+  int num_bins = 0;
+  std::vector<int> indices;
+  std::vector<double> lower_edges;
+  std::vector<double> upper_edges;
+  std::vector<double> vecx;
+  std::vector<double> vecy;
+  std::vector<double> vecz;
+};
+
 struct LineOfSight {
   double pos[3];
 };

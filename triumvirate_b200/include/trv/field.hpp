@@ -24,6 +24,11 @@
 #include "particles.hpp"
 #include "trvb.h"
 
+// Callers of the reference API release FFTW's global state at exit (fftw_cleanup[_threads],
+// T/main/triumvirate.cpp:905-911).  The device build holds none: no-ops keep them compiling.
+inline void fftw_cleanup() {}
+inline void fftw_cleanup_threads() {}
+
 namespace trv {
 
 namespace dev {
@@ -219,6 +224,11 @@ class FieldStats {
   ~FieldStats() = default;
 
   void reset_stats();
+
+  /// Mesh vectors (wavevectors for binning.space "fourier", separation vectors for
+  /// "config") listed bin by bin, optionally written to `save_file`
+  /// (S/field.cpp:2317-2509).  Host-side; bins ascending, row-major cell order within a bin.
+  trv::BinnedVectors record_binned_vectors(trv::Binning& binning, const std::string& save_file = {});
 
   /// S/field.cpp:2511-2703.
   void compute_ylm_wgtd_2pt_stats_in_fourier(

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 namespace trv {
 namespace sys {
@@ -36,6 +37,28 @@ double size_in_gb(long long num) {
 int get_gpu_count(bool sys = false);
 bool is_gpu_available();
 bool is_gpu_enabled();
+
+// -- paths and strings (I/monitor.hpp:208-245, 830; S/monitor.cpp:38-90, 1012-1040) --
+/// Delimiter between the files of a multi-file catalogue.
+const std::string fn_delimiter = "::";
+/// True when `fname` ends in `fext`.
+bool has_extension(const std::string& fname, const std::string& fext);
+/// Pieces of `str` between occurrences of `delimiter` (no empty trailing piece).
+std::vector<std::string> split_string(const std::string& str, const std::string& delimiter);
+/// Replace every ${NAME} by the value of the environment variable NAME (kept when unset).
+void expand_envar_in_path(std::string& path_str);
+/// I/io.hpp:55-62 (declared in io.hpp by the reference; defined with the I/O code).
+bool if_filepath_is_set(const std::string& pathstr);
+void make_write_dir(std::string dirstr);
+
+// -- program display and termination (I/monitor.hpp:429, 575, 785-818) --
+bool is_colourable();
+[[noreturn]] void exit_fatal(const std::string& msg);
+void display_help();
+void display_prog_logo();
+void display_prog_licence(bool brief = false);
+void display_prog_info(bool runtime = false);
+void display_prog_logbars(int endpoint);
 
 enum LogLevel { NSET = 0, DBUG = 10, STAT = 20, INFO = 30, WARN = 40, ERRO = 50 };
 

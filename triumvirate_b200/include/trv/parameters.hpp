@@ -11,7 +11,7 @@ namespace trv {
 
 class ParameterSet {
  public:
-  // -- I/O (kept for struct compatibility; file I/O is out of scope) --
+  // -- I/O (S/parameters.cpp:94-466, 1271-1380) --
   std::string catalogue_dir;
   std::string measurement_dir;
   std::string data_catalogue_file;
@@ -77,9 +77,32 @@ class ParameterSet {
   ParameterSet() = default;
   ~ParameterSet() = default;
 
-  /// Validate and derive parameters (S/parameters.cpp:466-1270).
+  /// Read `key = value` lines of a parameter INI file ('#' starts a comment line), then
+  /// validate(true) (S/parameters.cpp:94-464).  Returns validate()'s status.
+  int read_from_file(char* parameter_filepath);
+
+  /// Validate and derive parameters (S/parameters.cpp:466-1270).  `init`: first
+  /// validation after reading a file -- directory and catalogue paths are joined.
   int validate(bool init = false);
+
+  /// Write the parameters in use as `key = value` lines (S/parameters.cpp:1271-1372);
+  /// without argument: `<measurement_dir>parameters_used<output_tag>`.
+  int print_to_file(char* out_parameter_filepath);
+  int print_to_file();
+
+  /// Catalogue file paths after splitting at trv::sys::fn_delimiter and joining with
+  /// `catalogue_dir` (filled by validate()).
+  std::vector<std::string> data_catalogue_files;
+  std::vector<std::string> rand_catalogue_files;
 };
+
+/// TRV_OVERRIDE_OUTPUT_TAG / _VERBOSE / _PROGBAR replace the corresponding parameters
+/// (S/parameters.cpp:1382-1414; the FFTW overrides have no effect in this build).
+void override_paramset_by_envvars(trv::ParameterSet& params);
+/// boxsize = expand x coordinate spans (S/parameters.cpp:1416-1432).
+void set_boxsize_from_expand(const double* spans, trv::ParameterSet& params);
+/// ngrid from the Nyquist cut-off, rounded up to even (S/parameters.cpp:1434-1470).
+void set_ngrid_from_cutoff(trv::ParameterSet& params);
 
 }  // namespace trv
 

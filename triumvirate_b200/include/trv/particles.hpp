@@ -39,6 +39,16 @@ class ParticleCatalogue {
   void reset_particles();
   ParticleData& operator[](const int pid);
 
+  /// Read a (multi-file, `::`-delimited) plain-text catalogue: whitespace-separated
+  /// numeric columns, '#' comment lines; `catalogue_columns` names the columns present,
+  /// comma-separated, among x, y, z, nz, ws, wc (missing nz: ntotal / volume; missing
+  /// weights: 1) (S/particles.cpp:94-510).  HDF5 files are not supported by this build.
+  int load_catalogue_file(
+    const std::string& catalogue_filepath,
+    const std::string& catalogue_columns,
+    const std::string& catalogue_dataset = "",
+    double volume = 0.
+  );
   int load_particle_data(
     std::vector<double> x, std::vector<double> y, std::vector<double> z,
     std::vector<double> nz, std::vector<double> ws, std::vector<double> wc

@@ -4,6 +4,7 @@
 // as calls into the C-ABI device layer (include/trvb.h).  The mesh stays in
 // HBM between calls; the host mirror `field` is refreshed on demand only.
 #include "trv/field.hpp"
+#include "trv/io.hpp"
 
 #include <chrono>
 #include <cmath>
@@ -498,6 +499,71 @@ FieldStats::FieldStats(trv::ParameterSet& params, bool plan_ini) {
   this->params = params;
   this->ctx_ = dev::acquire_context(this->params);
   this->reset_stats();
+}
+
+trv::BinnedVectors FieldStats::record_binned_vectors(
+  trv::Binning& binning, const std::string& save_file
+) {
+  if (binning.space != "config" && binning.space != "fourier") {
+    if (trvs::currTask == 0) trvs::logger.error("Invalid binning space: '%s'.", binning.space.c_str());
+    throw trvs::InvalidDataError("Invalid binning space: '%s'.", binning.space.c_str());
+  }
+  const bool fourier = binning.space == "fourier";
+  double step[3];
+  for (int ax = 0; ax < 3; ax++) {
+    step[ax] = fourier ? 2. * M_PI / this->params.boxsize[ax]
+                       : this->params.boxsize[ax] / this->params.ngrid[ax];
+  }
+  // per bin, in row-major cell order; only indices whose vector can reach bin_max are visited
+  std::vector<trv::BinnedVectors> per_bin(binning.num_bins);
+  std::vector<int> reach[3];
+  for (int ax = 0; ax < 3; ax++) {
+    const int n = this->params.ngrid[ax];
+    for (int i = 0; i < n; i++) {
+      const int s = (i < n / 2) ? i : i - n;
+      if (std::fabs(s * step[ax]) < binning.bin_max + step[ax]) reach[ax].push_back(i);
+    }
+  }
+  for (int i : reach[0]) {
+    const int n0 = this->params.ngrid[0], n1 = this->params.ngrid[1], n2 = this->params.ngrid[2];
+    const double vx = ((i < n0 / 2) ? i : i - n0) * step[0];
+    for (int j : reach[1]) {
+      const double vy = ((j < n1 / 2) ? j : j - n1) * step[1];
+      for (int k : reach[2]) {
+        const double vz = ((k < n2 / 2) ? k : k - n2) * step[2];
+        const double scale = std::sqrt(vx * vx + vy * vy + vz * vz);
+        for (int b = 0; b < binning.num_bins; b++) {
+          if (binning.bin_edges[b] <= scale && scale < binning.bin_edges[b + 1]) {
+            per_bin[b].vecx.push_back(vx); per_bin[b].vecy.push_back(vy); per_bin[b].vecz.push_back(vz);
+            break;
+          }
+        }
+      }
+    }
+  }
+  trv::BinnedVectors out;
+  out.num_bins = binning.num_bins;
+  for (int b = 0; b < binning.num_bins; b++) {
+    for (size_t t = 0; t < per_bin[b].vecx.size(); t++) {
+      out.indices.push_back(b);
+      out.lower_edges.push_back(binning.bin_edges[b]);
+      out.upper_edges.push_back(binning.bin_edges[b + 1]);
+      out.vecx.push_back(per_bin[b].vecx[t]);
+      out.vecy.push_back(per_bin[b].vecy[t]);
+      out.vecz.push_back(per_bin[b].vecz[t]);
+      out.count++;
+    }
+  }
+  if (!save_file.empty()) {
+    std::FILE* fp = std::fopen(save_file.c_str(), "w");
+    if (fp == nullptr) throw trvs::IOError("Failed to open file: %s", save_file.c_str());
+    trv::io::print_binned_vectors_to_file(fp, this->params, out);
+    std::fclose(fp);
+    if (trvs::currTask == 0) {
+      trvs::logger.info("Check binned-vectors file for reference: %s", save_file.c_str());
+    }
+  }
+  return out;
 }
 
 void FieldStats::reset_stats() {

@@ -2,8 +2,11 @@
 #include "trv/monitor.hpp"
 
 #include <chrono>
+#include <cctype>
 #include <cstdlib>
+#include <cstring>
 #include <ctime>
+#include <filesystem>
 
 #include "trvb.h"
 
@@ -57,6 +60,120 @@ bool is_gpu_enabled() {
     if (m == "false" || m == "no" || m == "off" || m == "0") return false;
   }
   return true;
+}
+
+bool has_extension(const std::string& fname, const std::string& fext) {
+  return fname.size() >= fext.size()
+    && fname.compare(fname.size() - fext.size(), fext.size(), fext) == 0;
+}
+
+std::vector<std::string> split_string(const std::string& str, const std::string& delimiter) {
+  std::vector<std::string> parts;
+  if (str.empty()) return parts;
+  if (delimiter.empty()) { parts.push_back(str); return parts; }
+  size_t from = 0;
+  for (;;) {
+    const size_t at = str.find(delimiter, from);
+    if (at == std::string::npos) break;
+    parts.push_back(str.substr(from, at - from));
+    from = at + delimiter.size();
+  }
+  if (from < str.size()) parts.push_back(str.substr(from));
+  return parts;
+}
+
+void expand_envar_in_path(std::string& path_str) {
+  size_t from = 0;
+  for (;;) {
+    const size_t open = path_str.find("${", from);
+    if (open == std::string::npos) return;
+    const size_t close = path_str.find('}', open + 2);
+    if (close == std::string::npos) return;
+    const std::string name = path_str.substr(open + 2, close - open - 2);
+    const char* value = name.empty() ? nullptr : std::getenv(name.c_str());
+    if (value != nullptr) {
+      path_str.replace(open, close - open + 1, value);
+      from = open + std::strlen(value);
+    } else {
+      from = close + 1;   // unset: left as written
+    }
+  }
+}
+
+bool if_filepath_is_set(const std::string& pathstr) {
+  // a path is "set" when it is not blank and does not name a directory (trailing '/')
+  if (pathstr.empty() || pathstr.back() == '/') return false;
+  for (char c : pathstr) if (!std::isspace(static_cast<unsigned char>(c))) return true;
+  return false;
+}
+
+void make_write_dir(std::string dirstr) {
+  if (dirstr.empty() || dirstr == "." || dirstr == "./" || dirstr == "/") return;
+  while (!dirstr.empty() && dirstr.back() == '/') dirstr.pop_back();
+  std::error_code ec;
+  const bool created = std::filesystem::create_directories(std::filesystem::path(dirstr), ec);
+  if (created) {
+    if (currTask == 0) logger.info("Directory created: %s", dirstr.c_str());
+  } else if (ec) {
+    if (currTask == 0) logger.error("Failed to create directory: %s", dirstr.c_str());
+    throw IOError("Failed to create directory: %s", dirstr.c_str());
+  }
+}
+
+bool is_colourable() {
+  // colour only on request (TRV_INTERACTIVE) and on a terminal that advertises it
+  const char* term = std::getenv("TERM");
+  const char* inter = std::getenv("TRV_INTERACTIVE");
+  if (term == nullptr || inter == nullptr || std::strstr(term, "color") == nullptr) return false;
+  const std::string v(inter);
+  return v == "true" || v == "yes" || v == "on" || v == "1";
+}
+
+void exit_fatal(const std::string& msg) {
+  std::printf(is_colourable() ? "\n\033[1;37;41mFATAL\033[0m: %s\n" : "\nFATAL: %s\n", msg.c_str());
+  std::fflush(stdout);
+  std::exit(EXIT_FAILURE);
+}
+
+void display_help() {
+  std::printf(
+    "Triumvirate (B200 build): three-point clustering measurements in LSS\n\n"
+    "Usage: triumvirate [-h] [-V] <parameter-ini-file>\n\n"
+    "Positional arguments:\n"
+    "  <parameter-ini-file>  path to the parameter INI file\n\n"
+    "Options:\n"
+    "  -h, --help     show help message and exit\n"
+    "  -V, --version  show version and licensing information and exit\n");
+}
+
+void display_prog_logo() {
+  std::printf("\n  TRIUMVIRATE  --  Three-Point Clustering Measurements in LSS (B200 device build)\n\n");
+}
+
+void display_prog_licence(bool brief) {
+  std::printf("Estimator definitions after Triumvirate (Wang & Sugiyama), GPL-3.0-or-later.\n");
+  if (!brief) {
+    std::printf(
+      "This program is free software: you can redistribute it and/or modify it under the\n"
+      "terms of the GNU General Public License, version 3 or later.  It comes WITHOUT ANY\n"
+      "WARRANTY; see the licence text for details.\n");
+  }
+  std::printf("\n");
+}
+
+void display_prog_info(bool runtime) {
+  std::printf(runtime ? "RUNTIME INFORMATION >\n\n" : "PROGRAM INFORMATION >\n\n");
+  std::printf("Device layer: %s\n", trvb_version());
+  std::printf("CUDA devices visible / usable: %d / %d\n", get_gpu_count(true), get_gpu_count());
+  std::printf("GPU mode: %s (no CPU fallback)\n\n", is_gpu_enabled() ? "enabled" : "DISABLED");
+}
+
+void display_prog_logbars(int endpoint) {
+  if (endpoint == 0) {
+    std::printf("PROGRAM LOG >\n\n");
+  } else if (endpoint != 1) {
+    throw InvalidParameterError("Invalid endpoint for log bars: %d.", endpoint);
+  }
 }
 
 Logger logger(INFO);

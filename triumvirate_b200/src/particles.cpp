@@ -4,7 +4,14 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <sstream>
 #include <vector>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 namespace trvs = trv::sys;
 
@@ -62,6 +69,139 @@ void ParticleCatalogue::reset_particles() {
 }
 
 ParticleData& ParticleCatalogue::operator[](const int pid) { return this->pdata[pid]; }
+
+namespace {
+
+/// One catalogue file in memory with the start of every data line (not empty, not '#').
+struct TextFile {
+  std::string bytes;
+  std::vector<size_t> line_start;
+};
+
+TextFile slurp_data_lines(const std::string& path) {
+  TextFile f;
+  std::FILE* fp = std::fopen(path.c_str(), "rb");
+  if (fp == nullptr) {
+    if (trvs::currTask == 0) trvs::logger.error("Failed to open file: %s", path.c_str());
+    throw trvs::IOError("Failed to open file: %s", path.c_str());
+  }
+  std::fseek(fp, 0, SEEK_END);
+  const long size = std::ftell(fp);
+  std::fseek(fp, 0, SEEK_SET);
+  f.bytes.resize(size > 0 ? (size_t)size : 0);
+  if (size > 0 && std::fread(&f.bytes[0], 1, (size_t)size, fp) != (size_t)size) {
+    std::fclose(fp);
+    throw trvs::IOError("Failed to read file: %s", path.c_str());
+  }
+  std::fclose(fp);
+  f.bytes.push_back('\n');   // sentinel: every line ends in a newline
+  size_t at = 0;
+  const size_t n = f.bytes.size();
+  while (at < n) {
+    const size_t eol = f.bytes.find('\n', at);
+    if (eol > at && f.bytes[at] != '#') f.line_start.push_back(at);
+    at = eol + 1;
+  }
+  return f;
+}
+
+}  // namespace
+
+int ParticleCatalogue::load_catalogue_file(
+  const std::string& catalogue_filepath, const std::string& catalogue_columns,
+  const std::string& catalogue_dataset, double volume
+) {
+  (void)catalogue_dataset;   // HDF5 only
+  if (!this->source.empty()) {
+    if (trvs::currTask == 0) {
+      trvs::logger.error("Catalogue already loaded from another source: %s.", this->source.c_str());
+    }
+    throw trvs::InvalidDataError(
+      "Catalogue already loaded from another source: %s.", this->source.c_str());
+  }
+  this->source = "extfile:" + catalogue_filepath;
+  if (trvs::has_extension(catalogue_filepath, ".h5")
+      || trvs::has_extension(catalogue_filepath, ".hdf5")) {
+    if (trvs::currTask == 0) {
+      trvs::logger.error("HDF5 file format is not supported in this build: %s",
+                         catalogue_filepath.c_str());
+    }
+    throw trvs::InvalidDataError("HDF5 file format is not supported in this build: %s",
+                                 catalogue_filepath.c_str());
+  }
+
+  // column of each of x, y, z, nz, ws, wc in the file (-1: absent)
+  const char* wanted[6] = {"x", "y", "z", "nz", "ws", "wc"};
+  int column[6] = {-1, -1, -1, -1, -1, -1};
+  {
+    std::istringstream names(catalogue_columns);
+    std::string name;
+    for (int col = 0; std::getline(names, name, ','); col++) {
+      for (int q = 0; q < 6; q++) if (column[q] < 0 && name == wanted[q]) column[q] = col;
+    }
+  }
+  if (column[0] < 0 || column[1] < 0 || column[2] < 0) {
+    throw trvs::InvalidDataError(
+      "Catalogue columns must name 'x', 'y' and 'z': `catalogue_columns` = '%s'.",
+      catalogue_columns.c_str());
+  }
+  const int ncol_needed = 1 + *std::max_element(column, column + 6);
+
+  std::vector<TextFile> files;
+  long long nentry = 0;
+  for (const std::string& path : trvs::split_string(catalogue_filepath, trvs::fn_delimiter)) {
+    files.push_back(slurp_data_lines(path));
+    nentry += (long long)files.back().line_start.size();
+  }
+  if (nentry > 2147483647LL) {
+    throw trvs::InvalidDataError("Catalogue holds more than 2^31 - 1 particles.");
+  }
+  this->initialise_particles(static_cast<int>(nentry));
+  if (column[3] < 0 && trvs::currTask == 0) {
+    trvs::logger.info(
+      "Catalogue 'nz' field is unavailable and will be set to the mean density in the "
+      "bounding box (source=%s).", this->source.c_str());
+  }
+  const double nz_default = (volume > 0.) ? this->ntotal / volume : 0.;
+
+  // the lines are independent: parsed in parallel (strtod on the in-memory text)
+  long long base = 0;
+  bool short_row = false;
+  for (const TextFile& f : files) {
+    const long long nline = (long long)f.line_start.size();
+#pragma omp parallel for schedule(static) reduction(||:short_row)
+    for (long long ln = 0; ln < nline; ln++) {
+      const char* p = f.bytes.data() + f.line_start[ln];
+      double row[64];
+      int nread = 0;
+      while (nread < 64) {
+        char* end = nullptr;
+        const double v = std::strtod(p, &end);
+        if (end == p) break;
+        row[nread++] = v;
+        p = end;
+        while (*p == ' ' || *p == '\t' || *p == '\r') p++;
+        if (*p == '\n') break;
+      }
+      if (nread < ncol_needed) { short_row = true; continue; }
+      ParticleData& pt = this->pdata[base + ln];
+      pt.pos[0] = row[column[0]]; pt.pos[1] = row[column[1]]; pt.pos[2] = row[column[2]];
+      pt.nz = column[3] >= 0 ? row[column[3]] : nz_default;
+      pt.ws = column[4] >= 0 ? row[column[4]] : 1.;
+      pt.wc = column[5] >= 0 ? row[column[5]] : 1.;
+      pt.w = pt.ws * pt.wc;
+    }
+    base += nline;
+  }
+  if (short_row) {
+    throw trvs::InvalidDataError(
+      "Catalogue rows hold fewer columns than `catalogue_columns` names (source=%s).",
+      this->source.c_str());
+  }
+  this->calc_total_weights();
+  this->calc_pos_extents();
+  return 0;
+}
 
 int ParticleCatalogue::load_particle_data(
   std::vector<double> x, std::vector<double> y, std::vector<double> z,
