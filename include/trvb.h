@@ -243,6 +243,19 @@ int trvb_shell_ifft_batch(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh src, int ell,
                           int m, const double* klo, const double* khi,
                           const double* amp, int nbins, void* dst, int dst_layout);
 
+/* Slab form of trvb_shell_ifft_batch for the multi-GPU pair phase: the same `nbins`
+ * REAL shell fields (src TRVB_HALF, m = 0, even l; klo[q] < 0 and khi[q] < 0 disable the
+ * shell test, as for G), but only on the x-planes [x0, x0 + nx) of `sub`'s grid, written
+ * as nbins consecutive REAL blocks [nx][ns1][ns2] at device address `dst`.  The inverse
+ * transform is pruned: a direct x-DFT of the non-zero low-|k| modes for the nx planes
+ * wanted (each mode belongs to one shell: no dense spectrum is ever built), then batched
+ * 1-D transforms along y and z on those planes only -- so R ranks that split the x-planes
+ * share the transform work of every shell instead of each transforming whole shells.
+ * `sub` must be a true sub-grid of `ctx`. */
+int trvb_shell_slab_batch(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh src, int ell, int m,
+                          const double* klo, const double* khi, const double* amp,
+                          int nbins, int x0, int nx, void* dst);
+
 /* dst(x) = IFFT[ amp * j_l(|k| r) * y_lm(khat) * src(k) / W(k) ]
  * (S/field.cpp:1908-2010, amp = 1/V), spline table from trvb_sjl_table. */
 int trvb_sjl_ifft(trvb_ctx* ctx, trvb_mesh src, int ell, int m, double r,

@@ -578,6 +578,38 @@ def test_partitioned_pairs_sum_to_full(core):
             assert np.array_equal(sum(p[key] for p in parts), full[key])
 
 
+@pytest.mark.parametrize("degrees,form,ngrid", [((0, 0, 0), "full", 64), ((2, 0, 2), "full", (72, 64, 80)),
+                                                ((0, 0, 0), "diag", 96)])
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_slab_mode_shares_sum_to_full(core, degrees, form, ngrid, world, monkeypatch):
+    """Multi-GPU pair phase in slab mode (throughput mode, real shell fields on a true
+    sub-grid): every rank builds ALL shell fields on its own x-planes of the sub-grid
+    (pruned transforms, trvb_shell_slab_batch) and reduces all pairs there; the shares sum to
+    the single-rank result up to summation order.  The pair-block split (TRV_NO_SLAB=1) and
+    the slab split must agree with it and with each other."""
+    gen = np.random.default_rng(4242)
+    L = 1000.
+    pos = gen.uniform(0., L, size=(3, 30000))
+    kw = dict(boxsize=L, ngrid=ngrid, assignment="tsc", degrees=degrees, form=form,
+              bin_range=(0.01, 0.07), num_bins=6, norm_factor=1., pos_d=pos)
+    full = core.threept("bispec", "sim", **kw)
+    scale = np.abs(full["bk_raw"]).max()
+    for no_slab in ("0", "1"):
+        monkeypatch.setenv("TRV_NO_SLAB", no_slab)
+        parts = [core.threept("bispec", "sim", part_rank=r, part_count=world, **kw)
+                 for r in range(world)]
+        raw = sum(p["bk_raw"] for p in parts)
+        shot = sum(p["bk_shot"] for p in parts)
+        assert np.max(np.abs(raw - full["bk_raw"])) <= 1.e-11 * scale, no_slab
+        assert np.max(np.abs(shot - full["bk_shot"])) <= 1.e-11 * np.abs(full["bk_shot"]).max()
+        if no_slab == "0":
+            # slab mode: every pair rank contributes to every entry (the last rank only
+            # when the shot-noise branch leaves it a slab)
+            assert np.all(parts[0]["bk_raw"] != 0.)
+        else:
+            assert np.all(sum((p["bk_raw"] != 0).astype(int) for p in parts) == 1)
+
+
 @pytest.mark.parametrize("stat,degrees,form", [("bispec", (2, 0, 2), "diag"),
                                                 ("bispec", (1, 1, 0), "full"),
                                                 ("3pcf", (1, 1, 0), "diag")])

@@ -102,6 +102,8 @@ struct trvb_ctx {
   bool has_z2z = false, has_d2z = false, has_z2d = false;
   // Batched out-of-place/in-place plans keyed by (cufftType, batch).
   std::map<std::pair<int, int>, cufftHandle> batch_plans;
+  // Batched 1-D plans of the slab transforms keyed by {type, length, batch}.
+  std::map<std::vector<long long>, cufftHandle> line_plans;
   // Spherical-Bessel spline tables keyed by ell.
   std::map<int, SjlTable> sjl;
   // Scratch for two-stage reductions.

@@ -315,6 +315,7 @@ static void destroy_ctx_now(trvb_ctx* ctx) {
   if (ctx->has_d2z) cufftDestroy(ctx->plan_d2z);
   if (ctx->has_z2d) cufftDestroy(ctx->plan_z2d);
   for (auto& kv : ctx->batch_plans) cufftDestroy(kv.second);
+  for (auto& kv : ctx->line_plans) cufftDestroy(kv.second);
   for (int ax = 0; ax < 3; ax++) {
     if (ctx->d_sinc[ax]) cudaFree(ctx->d_sinc[ax]);
     if (ctx->d_alias[ax]) cudaFree(ctx->d_alias[ax]);

@@ -525,6 +525,221 @@ extern "C" int trvb_shell_ifft_batch(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh src
   return st;
 }
 
+// ---------------------------------------------------------------------
+// Slab (x-plane) form of the batched shell transform.
+// ---------------------------------------------------------------------
+
+namespace {
+
+constexpr int SLAB_XT = 8;        // x-planes accumulated per thread
+
+// Direct x-DFT of the low-|k| modes for the planes of the slab.  Thread = one (k_y, k_z)
+// column of the low-|k| cube and SLAB_XT planes; it walks k_x, evaluates the filtered mode
+// once, and adds twiddle x mode to the accumulators of the shell that holds it.  Output
+// D[q][x][c = k_z][y-slot of k_y] (zero-filled beforehand): the rows the y-transform reads.
+__global__ void __launch_bounds__(128)
+k_shell_xdft(KView src, GridDesc gp, GridDesc gs, Tables tb, int ell, int m,
+             int lo0, int lo1, int K0, int K1, int K2, ShellBatch sb,
+             const double2* __restrict__ tw, int nx, double2* __restrict__ D) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= K1 * K2) return;
+  const int b = col % K1, c = col / K1;
+  const int xbeg = blockIdx.y * SLAB_XT;
+  const int mj = lo1 + b, mk = c;
+  const int ys = mj >= 0 ? mj : mj + gs.n[1];
+  const double ky = __dmul_rn((double)mj, gp.dk[1]);
+  const double kz = __dmul_rn((double)mk, gp.dk[2]);
+  const YlmCoef yc = ylm_coef(ell, m);
+  double2 acc[SLAB_XT];
+  int cur = -1;
+  auto flush = [&]() {
+    if (cur < 0) return;
+#pragma unroll
+    for (int t = 0; t < SLAB_XT; t++) {
+      const int x = xbeg + t;
+      if (x < nx) {
+        double2* d = D + (((long long)cur * nx + x) * K2 + c) * gs.n[1] + ys;
+        double2 v = *d; v.x += acc[t].x; v.y += acc[t].y; *d = v;
+      }
+    }
+  };
+  for (int a = 0; a < K0; a++) {
+    const int mi = lo0 + a;
+    const double kx = __dmul_rn((double)mi, gp.dk[0]);
+    const double kmag = vec3_norm_exact(kx, ky, kz);
+    bool loaded = false;
+    double2 base = make_double2(0., 0.);
+    for (int q = 0; q < sb.nbins; q++) {
+      const double lo = sb.klo[q], hi = sb.khi[q];
+      if (!((lo < 0. && hi < 0.) || (lo <= kmag && kmag < hi))) continue;
+      if (!loaded) { base = shell_mode(src, gp, tb, yc, mi, mj, mk, kx, ky, kz, 1.); loaded = true; }
+      if (q != cur) {
+        flush();
+        cur = q;
+#pragma unroll
+        for (int t = 0; t < SLAB_XT; t++) acc[t] = make_double2(0., 0.);
+      }
+      const double amp = sb.amp[q];
+      const double vr = base.x * amp, vi = base.y * amp;
+#pragma unroll
+      for (int t = 0; t < SLAB_XT; t++) {
+        const int x = min(xbeg + t, nx - 1);
+        const double2 w = __ldg(tw + (long long)x * K0 + a);
+        acc[t].x += w.x * vr - w.y * vi;
+        acc[t].y += w.x * vi + w.y * vr;
+      }
+    }
+  }
+  flush();
+}
+
+// E[r][y][kz] = (kz < K2) ? D[r][kz][y] : 0 for every (shell, plane) r: the rows the
+// z-transform reads, zero-padded to the half-spectrum length.
+__global__ void __launch_bounds__(256)
+k_slab_transpose(const double2* __restrict__ D, int K2, int n1, int nh, long long nrows,
+                 double2* __restrict__ E) {
+  __shared__ double2 tile[32][33];
+  const int tiles_y = (n1 + 31) / 32, tiles_k = (nh + 31) / 32;
+  const long long ntile = nrows * tiles_y * tiles_k;
+  for (long long t = blockIdx.x; t < ntile; t += gridDim.x) {
+    const int tk = (int)(t % tiles_k);
+    const int ty = (int)((t / tiles_k) % tiles_y);
+    const long long r = t / ((long long)tiles_k * tiles_y);
+    const double2* src = D + r * (long long)K2 * n1;
+    double2* dst = E + r * (long long)n1 * nh;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int kz = tk * 32 + i, y = ty * 32 + threadIdx.x;
+      tile[i][threadIdx.x] = (kz < K2 && y < n1) ? src[(long long)kz * n1 + y] : make_double2(0., 0.);
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int y = ty * 32 + i, kz = tk * 32 + threadIdx.x;
+      if (y < n1 && kz < nh) dst[(long long)y * nh + kz] = tile[threadIdx.x][i];
+    }
+    __syncthreads();
+  }
+}
+
+int get_line_plan(trvb_ctx* ctx, cufftType type, int n, long long batch, cufftHandle* out) {
+  const std::vector<long long> key = {(long long)type, (long long)n, batch};
+  auto it = ctx->line_plans.find(key);
+  if (it == ctx->line_plans.end()) {
+    TRVB_REQUIRE(batch < 2147483647LL, "slab transform: batch too large");
+    cufftHandle plan;
+    int len[1] = {n};
+    if (type == CUFFT_Z2Z) {
+      TRVB_CUFFT(cufftPlanMany(&plan, 1, len, nullptr, 1, n, nullptr, 1, n, CUFFT_Z2Z, (int)batch));
+    } else {
+      int inembed[1] = {n / 2 + 1}, onembed[1] = {n};
+      TRVB_CUFFT(cufftPlanMany(&plan, 1, len, inembed, 1, n / 2 + 1, onembed, 1, n, CUFFT_Z2D,
+                               (int)batch));
+    }
+    TRVB_CUFFT(cufftSetStream(plan, ctx->stream));
+    it = ctx->line_plans.emplace(key, plan).first;
+  }
+  *out = it->second;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int trvb_shell_slab_batch(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh src, int ell,
+                                     int m, const double* klo, const double* khi,
+                                     const double* amp, int nbins, int x0, int nx, void* dst) {
+  TRVB_REQUIRE(ctx && sub && src.data && dst && klo && khi && amp && nbins > 0,
+               "trvb_shell_slab_batch: bad argument");
+  TRVB_REQUIRE(ctx->parent == nullptr && sub->parent == ctx,
+               "trvb_shell_slab_batch: `sub` must be a sub-grid of `ctx`");
+  TRVB_REQUIRE(src.layout == TRVB_HALF && m == 0 && (ell % 2) == 0 && ell >= 0,
+               "trvb_shell_slab_batch: needs a HALF source, m = 0 and even l (real shell fields)");
+  const GridDesc& gp = ctx->g;
+  const GridDesc& gs = sub->g;
+  TRVB_REQUIRE(x0 >= 0 && nx > 0 && x0 + nx <= gs.n[0], "trvb_shell_slab_batch: planes [%d, %d) "
+               "outside the %d planes of the sub-grid", x0, x0 + nx, gs.n[0]);
+  // Low-|k| cube that holds every shell, strictly inside the sub-grid's Nyquist frequency.
+  double kmax = 0.;
+  bool unbounded = false;
+  for (int q = 0; q < nbins; q++) {
+    if (klo[q] < 0. && khi[q] < 0.) unbounded = true;
+    kmax = std::max(kmax, khi[q]);
+  }
+  int lo[3], cnt[3];
+  for (int a = 0; a < 3; a++) {
+    const long long smax = (long long)((gs.n[a] - 1) / 2);
+    long long mc = unbounded ? smax : (long long)std::floor(kmax / gp.dk[a]) + 1;
+    mc = std::min(mc, smax);
+    lo[a] = (int)-mc; cnt[a] = (int)(2 * mc + 1);
+  }
+  const int K0 = cnt[0], K1 = cnt[1], K2 = -lo[2] + 1;   // k_z >= 0 only (Hermitian half)
+  const int n1 = gs.n[1], n2 = gs.n[2], nh = gs.nh;
+
+  // twiddles exp(+2 pi i k_x (x0 + x) / n0), argument reduced exactly in integers
+  std::vector<double> h_tw(2 * (size_t)nx * K0);
+  for (int x = 0; x < nx; x++) {
+    for (int a = 0; a < K0; a++) {
+      long long r = ((long long)(lo[0] + a) * (x0 + x)) % gs.n[0];
+      if (r < 0) r += gs.n[0];
+      const double ang = 2. * M_PI * (double)r / (double)gs.n[0];
+      h_tw[2 * ((size_t)x * K0 + a)] = std::cos(ang);
+      h_tw[2 * ((size_t)x * K0 + a) + 1] = std::sin(ang);
+    }
+  }
+  double* d_tw = nullptr; double* d_par = nullptr;
+  TRVB_CUDA(trvb_dev_alloc_raw(sub, (void**)&d_tw, sizeof(double) * h_tw.size()));
+  TRVB_CUDA(trvb_dev_alloc_raw(sub, (void**)&d_par, sizeof(double) * 3 * (size_t)nbins));
+  std::vector<double> h_par(3 * (size_t)nbins);
+  for (int q = 0; q < nbins; q++) {
+    h_par[q] = klo[q]; h_par[nbins + q] = khi[q]; h_par[2 * nbins + q] = amp[q];
+  }
+  TRVB_CUDA(cudaMemcpyAsync(d_tw, h_tw.data(), sizeof(double) * h_tw.size(),
+                            cudaMemcpyHostToDevice, sub->stream));
+  TRVB_CUDA(cudaMemcpyAsync(d_par, h_par.data(), sizeof(double) * h_par.size(),
+                            cudaMemcpyHostToDevice, sub->stream));
+  TRVB_CUDA(cudaStreamSynchronize(sub->stream));   // the host vectors go out of scope
+
+  // Sub-batches of shells bound the two transient arrays to ~6 GiB.
+  const size_t d_bin = sizeof(double2) * (size_t)nx * K2 * n1;
+  const size_t e_bin = sizeof(double2) * (size_t)nx * n1 * nh;
+  int maxb = (int)std::max<size_t>(1, ((size_t)6 << 30) / (d_bin + e_bin));
+  maxb = std::min(maxb, nbins);
+  double2* D = nullptr; double2* E = nullptr;
+  TRVB_CUDA(trvb_dev_alloc_raw(sub, (void**)&D, d_bin * maxb));
+  TRVB_CUDA(trvb_dev_alloc_raw(sub, (void**)&E, e_bin * maxb));
+  const size_t out_bin = sizeof(double) * (size_t)nx * n1 * n2;
+  int st = 0;
+  for (int q0 = 0; q0 < nbins && st == 0; q0 += maxb) {
+    const int nq = std::min(maxb, nbins - q0);
+    TRVB_CUDA(cudaMemsetAsync(D, 0, d_bin * nq, sub->stream));
+    ShellBatch sb; sb.klo = d_par + q0; sb.khi = d_par + nbins + q0; sb.amp = d_par + 2 * nbins + q0;
+    sb.nbins = nq;
+    const dim3 grid((K1 * K2 + 127) / 128, (nx + SLAB_XT - 1) / SLAB_XT);
+    k_shell_xdft<<<grid, 128, 0, sub->stream>>>(
+      kview_of(ctx, src), gp, gs, tables_of(ctx), ell, m, lo[0], lo[1], K0, K1, K2, sb,
+      (const double2*)d_tw, nx, D);
+    TRVB_LAUNCH_CHECK();
+    cufftHandle plan_y, plan_z;
+    st = get_line_plan(sub, CUFFT_Z2Z, n1, (long long)nq * nx * K2, &plan_y);
+    if (st) break;
+    TRVB_CUFFT(cufftExecZ2Z(plan_y, (cufftDoubleComplex*)D, (cufftDoubleComplex*)D, CUFFT_INVERSE));
+    g_trvb_fft_execs++;
+    const long long nrows = (long long)nq * nx;
+    const int tblocks = (int)std::min<long long>(
+      nrows * ((n1 + 31) / 32) * ((nh + 31) / 32), (long long)ctx->num_sms * 16);
+    k_slab_transpose<<<tblocks, dim3(32, 8), 0, sub->stream>>>(D, K2, n1, nh, nrows, E);
+    TRVB_LAUNCH_CHECK();
+    st = get_line_plan(sub, CUFFT_Z2D, n2, nrows * n1, &plan_z);
+    if (st) break;
+    TRVB_CUFFT(cufftExecZ2D(plan_z, (cufftDoubleComplex*)E,
+                            (cufftDoubleReal*)((char*)dst + out_bin * (size_t)q0)));
+    g_trvb_fft_execs++;
+  }
+  trvb_dev_free_raw(sub, D);
+  trvb_dev_free_raw(sub, E);
+  trvb_dev_free_raw(sub, d_tw);
+  trvb_dev_free_raw(sub, d_par);
+  return st;
+}
+
 extern "C" int trvb_sjl_ifft_batch(trvb_ctx* ctx, trvb_mesh src, int ell, int m,
                                    const double* r, double amp, int nbins, void* dst) {
   TRVB_REQUIRE(ctx && src.data && r && dst && nbins > 0, "trvb_sjl_ifft_batch: bad argument");

@@ -747,7 +747,42 @@ trv::BispecMeasurements bispec_impl(
   choose_subgrid(params, kbinning.bin_edges.back(), nsub);
   const double shot_cost_in_fields = 1.7 * double(params.nmesh)
     / (double(nsub[0]) * double(nsub[1]) * double(nsub[2]));
-  const BispecShare share = bispec_share(params, dv, shot_cost_in_fields);
+  const std::vector<Term> terms = enumerate_terms(params, survey);
+
+  // Slab mode (two or more ranks, throughput mode, real shell fields on a true sub-grid):
+  // instead of dealing whole PAIRS -- which makes every rank transform ~2/sqrt(R) of the
+  // shells -- the ranks split the x-PLANES of the sub-grid.  Each rank builds every shell
+  // field on its own planes only (pruned transforms, trvb_shell_slab_batch), reduces ALL
+  // pairs over those cells, and the sum over ranks completes each entry.  The last rank
+  // still owns the shot-noise branch and takes a thinner slab (none when that branch
+  // outweighs a fair share).
+  bool slab_mode = params.part_count > 1 && !params.deterministic
+    && nsub[0] != params.ngrid[0] && (params.ell1 % 2 == 0) && (params.ell2 % 2 == 0)
+    && (!survey || params.ELL % 2 == 0);
+  for (const Term& t : terms) slab_mode = slab_mode && t.m1 == 0 && t.m2 == 0 && t.M == 0;
+  {
+    const char* env = std::getenv("TRV_NO_SLAB");
+    if (env != nullptr && env[0] == '1') slab_mode = false;
+  }
+  int slab_x0 = 0, slab_nx = 0;
+  if (slab_mode) {
+    const int R = params.part_count, r = params.part_rank;
+    const double W = 1.2 * nb * (params.ell1 == params.ell2 ? 1. : 2.) + 1.;   // fields + pair products
+    const double f_last = std::max(0., (W - (R - 1) * shot_cost_in_fields) / (R * W));
+    const int n_last = static_cast<int>(std::floor(f_last * nsub[0] + 0.5));
+    const int rest = nsub[0] - n_last;
+    auto first_plane = [&](int q) {   // ranks 0 .. R-2 share `rest` planes evenly
+      return static_cast<int>((long long)rest * q / (R - 1));
+    };
+    if (r < R - 1) { slab_x0 = first_plane(r); slab_nx = first_plane(r + 1) - slab_x0; }
+    else { slab_x0 = rest; slab_nx = n_last; }
+  }
+
+  BispecShare share = bispec_share(params, dv, shot_cost_in_fields);
+  if (slab_mode) {
+    share.pairs.assign(dv.dim, slab_nx > 0 ? 1 : 0);
+    share.any_pairs = slab_nx > 0;
+  }
   const std::vector<char>& active = share.pairs;
   const std::vector<char>& shot_active = share.shot;
 
@@ -791,7 +826,14 @@ trv::BispecMeasurements bispec_impl(
   std::vector<double> k1eff(dv.dim), k2eff(dv.dim);
   for (int i = 0; i < dv.dim; i++) { k1eff[i] = keff[dv.row[i]]; k2eff[i] = keff[dv.col[i]]; }
 
-  const std::vector<Term> terms = enumerate_terms(params, survey);
+  // Slab mode: a context whose "grid" is this rank's block of x-planes (allocation sizes
+  // and the cell count of the pair reduction).
+  trvb_ctx* slab_ctx = nullptr;
+  if (slab_mode && slab_nx > 0) {
+    const int dims[3] = {slab_nx, nsub[1], nsub[2]};
+    dev::check(trvb_subgrid_create(c, &slab_ctx, dims), "trvb_subgrid_create (slab)");
+  }
+  trvb_ctx* pair_grid = slab_ctx ? slab_ctx : sub;
   dev::Mesh xi;             // shot-noise mesh, reused across terms in a box
   dev::Mesh G;              // G_LM(x) on the sub-grid
   int G_M = 0; bool have_G = false, have_xi = false;
@@ -809,9 +851,15 @@ trv::BispecMeasurements bispec_impl(
       khi.push_back(kbinning.bin_edges[b + 1]);
       amp.push_back(1. / double(nmodes[b]));   // F /= nmodes, S/field.cpp:1900-1905
     }
-    dev::check(trvb_shell_ifft_batch(c, sub, src.view(), ell, m, klo.data(), khi.data(),
-                                     amp.data(), (int)bins.size(), dst.data(), layout),
-               "trvb_shell_ifft_batch");
+    if (slab_ctx) {
+      dev::check(trvb_shell_slab_batch(c, sub, src.view(), ell, m, klo.data(), khi.data(),
+                                       amp.data(), (int)bins.size(), slab_x0, slab_nx, dst.data()),
+                 "trvb_shell_slab_batch");
+    } else {
+      dev::check(trvb_shell_ifft_batch(c, sub, src.view(), ell, m, klo.data(), khi.data(),
+                                       amp.data(), (int)bins.size(), dst.data(), layout),
+                 "trvb_shell_ifft_batch");
+    }
     trvs::count_ifft += (int)bins.size();
   };
   // Shell fields depend on (ell, m, bin) only: terms that share a side (e.g.
@@ -823,9 +871,9 @@ trv::BispecMeasurements bispec_impl(
     const SlabKey key(ell, m, layout, bins);
     auto hit = slab_cache.find(key);
     if (hit != slab_cache.end()) return hit->second;
-    auto slab = std::make_shared<Slab>(eng.shared(), sub, layout, (int)bins.size());
+    auto slab = std::make_shared<Slab>(eng.shared(), pair_grid, layout, (int)bins.size());
     shell_fields(dn_00, ell, m, bins, layout, *slab);
-    const size_t bytes = trvb_mesh_bytes(sub, layout) * bins.size();
+    const size_t bytes = trvb_mesh_bytes(pair_grid, layout) * bins.size();
     if (terms.size() > 1 && eng.mesh_capacity(bytes) >= 6) slab_cache[key] = slab;
     return slab;
   };
@@ -882,9 +930,16 @@ trv::BispecMeasurements bispec_impl(
       const int layout = real_path ? TRVB_REAL : TRVB_COMPLEX;
       if (!(have_G && G_M == t.M && G.layout() == layout)) {
         // G_LM(x) = IFFT[delta n_LM(k) / W(k)] / V (S/threept.cpp:452-459).
-        G = dev::Mesh(eng.shared(), sub, layout);
-        dev::check(trvb_shell_ifft(c, sub, dn_LM_ref.view(), 0, 0, -1., -1., 1. / eng.vol(),
-                                   G.view()), "trvb_shell_ifft (G)");
+        G = dev::Mesh(eng.shared(), pair_grid, layout);
+        if (slab_ctx) {
+          const double none = -1., ampG = 1. / eng.vol();
+          dev::check(trvb_shell_slab_batch(c, sub, dn_LM_ref.view(), 0, 0, &none, &none, &ampG, 1,
+                                           slab_x0, slab_nx, G.view().data),
+                     "trvb_shell_slab_batch (G)");
+        } else {
+          dev::check(trvb_shell_ifft(c, sub, dn_LM_ref.view(), 0, 0, -1., -1., 1. / eng.vol(),
+                                     G.view()), "trvb_shell_ifft (G)");
+        }
         trvs::count_ifft += 1;
         G_M = t.M; have_G = true;
         dev::profile_mark(c, "G_field");
@@ -896,7 +951,7 @@ trv::BispecMeasurements bispec_impl(
       const int m_b = mirror ? t.m1 : t.m2;
       std::vector<cdouble> bk_comp;
       reduce_pairs(
-        eng, sub, dv, active, same_fields || mirror, G.view(),
+        eng, pair_grid, dv, active, same_fields || mirror, G.view(),
         [&](const std::vector<int>& bins) { return shell_slab(params.ell1, t.m1, bins, layout); },
         [&](const std::vector<int>& bins) { return shell_slab(params.ell2, m_b, bins, layout); },
         bk_comp, mirror);
