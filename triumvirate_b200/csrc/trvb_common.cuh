@@ -104,6 +104,7 @@ struct trvb_ctx {
   std::map<std::pair<int, int>, cufftHandle> batch_plans;
   // Batched 1-D plans of the slab transforms keyed by {type, length, batch}.
   std::map<std::vector<long long>, cufftHandle> line_plans;
+  std::map<std::vector<long long>, size_t> line_plan_work;   // their work-area sizes
   // Spherical-Bessel spline tables keyed by ell.
   std::map<int, SjlTable> sjl;
   // Scratch for two-stage reductions.

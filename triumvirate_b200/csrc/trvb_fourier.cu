@@ -531,25 +531,56 @@ extern "C" int trvb_shell_ifft_batch(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh src
 
 namespace {
 
-constexpr int SLAB_XT = 8;        // x-planes accumulated per thread
+constexpr int SLAB_XT = 16;       // x-planes accumulated per thread
+
+// The filtered modes of the low-|k| cube, evaluated ONCE per call: value y_lm src / W and
+// the shell (index into the call's bin list, -1: none) of every mode (k_x, k_z >= 0, k_y),
+// laid out [a = k_x][c = k_z][b = k_y] so that the x-DFT reads them coalesced along k_y.
+__global__ void __launch_bounds__(256)
+k_lowk_modes(KView src, GridDesc gp, Tables tb, int ell, int m, int lo0, int lo1,
+             int K0, int K1, int K2, ShellBatch sb, double2* __restrict__ val,
+             int* __restrict__ shell) {
+  const YlmCoef yc = ylm_coef(ell, m);
+  const long long total = (long long)K0 * K1 * K2;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(t % K1), c = (int)((t / K1) % K2), a = (int)(t / ((long long)K1 * K2));
+    const int mi = lo0 + a, mj = lo1 + b, mk = c;
+    const double kx = __dmul_rn((double)mi, gp.dk[0]);
+    const double ky = __dmul_rn((double)mj, gp.dk[1]);
+    const double kz = __dmul_rn((double)mk, gp.dk[2]);
+    const double kmag = vec3_norm_exact(kx, ky, kz);
+    int q = -1;
+    for (int i = 0; i < sb.nbins; i++) {
+      const double lo = sb.klo[i], hi = sb.khi[i];
+      if ((lo < 0. && hi < 0.) || (lo <= kmag && kmag < hi)) { q = i; break; }
+    }
+    shell[t] = q;
+    if (q >= 0) {
+      const double2 v = shell_mode(src, gp, tb, yc, mi, mj, mk, kx, ky, kz, 1.);
+      const double amp = sb.amp[q];
+      val[t] = make_double2(v.x * amp, v.y * amp);
+    } else {
+      val[t] = make_double2(0., 0.);
+    }
+  }
+}
 
 // Direct x-DFT of the low-|k| modes for the planes of the slab.  Thread = one (k_y, k_z)
-// column of the low-|k| cube and SLAB_XT planes; it walks k_x, evaluates the filtered mode
-// once, and adds twiddle x mode to the accumulators of the shell that holds it.  Output
-// D[q][x][c = k_z][y-slot of k_y] (zero-filled beforehand): the rows the y-transform reads.
+// column of the cube and SLAB_XT planes; it walks k_x and adds twiddle x mode to the
+// accumulators of the shell that holds the mode (shells q0 .. q0 + nq - 1 of the call).
+// Output D[q][x][c = k_z][y-slot of k_y] (zero-filled beforehand): the rows the y-transform
+// reads.  A column meets each shell in at most two runs of k_x, so the flush is rare.
 __global__ void __launch_bounds__(128)
-k_shell_xdft(KView src, GridDesc gp, GridDesc gs, Tables tb, int ell, int m,
-             int lo0, int lo1, int K0, int K1, int K2, ShellBatch sb,
+k_shell_xdft(const double2* __restrict__ val, const int* __restrict__ shell, int lo1,
+             int K0, int K1, int K2, int q0, int nq, int n1,
              const double2* __restrict__ tw, int nx, double2* __restrict__ D) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;   // c * K1 + b
   if (col >= K1 * K2) return;
   const int b = col % K1, c = col / K1;
   const int xbeg = blockIdx.y * SLAB_XT;
-  const int mj = lo1 + b, mk = c;
-  const int ys = mj >= 0 ? mj : mj + gs.n[1];
-  const double ky = __dmul_rn((double)mj, gp.dk[1]);
-  const double kz = __dmul_rn((double)mk, gp.dk[2]);
-  const YlmCoef yc = ylm_coef(ell, m);
+  const int mj = lo1 + b;
+  const int ys = mj >= 0 ? mj : mj + n1;
   double2 acc[SLAB_XT];
   int cur = -1;
   auto flush = [&]() {
@@ -558,36 +589,28 @@ k_shell_xdft(KView src, GridDesc gp, GridDesc gs, Tables tb, int ell, int m,
     for (int t = 0; t < SLAB_XT; t++) {
       const int x = xbeg + t;
       if (x < nx) {
-        double2* d = D + (((long long)cur * nx + x) * K2 + c) * gs.n[1] + ys;
+        double2* d = D + (((long long)cur * nx + x) * K2 + c) * n1 + ys;
         double2 v = *d; v.x += acc[t].x; v.y += acc[t].y; *d = v;
       }
     }
   };
+  const long long plane = (long long)K1 * K2;
   for (int a = 0; a < K0; a++) {
-    const int mi = lo0 + a;
-    const double kx = __dmul_rn((double)mi, gp.dk[0]);
-    const double kmag = vec3_norm_exact(kx, ky, kz);
-    bool loaded = false;
-    double2 base = make_double2(0., 0.);
-    for (int q = 0; q < sb.nbins; q++) {
-      const double lo = sb.klo[q], hi = sb.khi[q];
-      if (!((lo < 0. && hi < 0.) || (lo <= kmag && kmag < hi))) continue;
-      if (!loaded) { base = shell_mode(src, gp, tb, yc, mi, mj, mk, kx, ky, kz, 1.); loaded = true; }
-      if (q != cur) {
-        flush();
-        cur = q;
+    const int q = shell[a * plane + col] - q0;
+    if (q < 0 || q >= nq) continue;
+    const double2 v = val[a * plane + col];
+    if (q != cur) {
+      flush();
+      cur = q;
 #pragma unroll
-        for (int t = 0; t < SLAB_XT; t++) acc[t] = make_double2(0., 0.);
-      }
-      const double amp = sb.amp[q];
-      const double vr = base.x * amp, vi = base.y * amp;
+      for (int t = 0; t < SLAB_XT; t++) acc[t] = make_double2(0., 0.);
+    }
 #pragma unroll
-      for (int t = 0; t < SLAB_XT; t++) {
-        const int x = min(xbeg + t, nx - 1);
-        const double2 w = __ldg(tw + (long long)x * K0 + a);
-        acc[t].x += w.x * vr - w.y * vi;
-        acc[t].y += w.x * vi + w.y * vr;
-      }
+    for (int t = 0; t < SLAB_XT; t++) {
+      const int x = min(xbeg + t, nx - 1);
+      const double2 w = __ldg(tw + (long long)x * K0 + a);
+      acc[t].x += w.x * v.x - w.y * v.y;
+      acc[t].y += w.x * v.y + w.y * v.x;
     }
   }
   flush();
@@ -620,24 +643,34 @@ k_slab_transpose(const double2* __restrict__ D, int K2, int n1, int nh, long lon
   }
 }
 
-int get_line_plan(trvb_ctx* ctx, cufftType type, int n, long long batch, cufftHandle* out) {
+// Batched 1-D plans WITHOUT their own work areas (several batch sizes are alive at once and
+// cuFFT's automatic areas would add up): the area comes from the arena for the duration of
+// one execution.
+int get_line_plan(trvb_ctx* ctx, cufftType type, int n, long long batch, cufftHandle* out,
+                  size_t* work_bytes) {
   const std::vector<long long> key = {(long long)type, (long long)n, batch};
   auto it = ctx->line_plans.find(key);
   if (it == ctx->line_plans.end()) {
     TRVB_REQUIRE(batch < 2147483647LL, "slab transform: batch too large");
     cufftHandle plan;
+    TRVB_CUFFT(cufftCreate(&plan));
+    TRVB_CUFFT(cufftSetAutoAllocation(plan, 0));
     int len[1] = {n};
+    size_t ws = 0;
     if (type == CUFFT_Z2Z) {
-      TRVB_CUFFT(cufftPlanMany(&plan, 1, len, nullptr, 1, n, nullptr, 1, n, CUFFT_Z2Z, (int)batch));
+      TRVB_CUFFT(cufftMakePlanMany(plan, 1, len, nullptr, 1, n, nullptr, 1, n, CUFFT_Z2Z,
+                                   (int)batch, &ws));
     } else {
       int inembed[1] = {n / 2 + 1}, onembed[1] = {n};
-      TRVB_CUFFT(cufftPlanMany(&plan, 1, len, inembed, 1, n / 2 + 1, onembed, 1, n, CUFFT_Z2D,
-                               (int)batch));
+      TRVB_CUFFT(cufftMakePlanMany(plan, 1, len, inembed, 1, n / 2 + 1, onembed, 1, n,
+                                   CUFFT_Z2D, (int)batch, &ws));
     }
     TRVB_CUFFT(cufftSetStream(plan, ctx->stream));
     it = ctx->line_plans.emplace(key, plan).first;
+    ctx->line_plan_work[key] = ws;
   }
   *out = it->second;
+  *work_bytes = ctx->line_plan_work[key];
   return 0;
 }
 
@@ -697,6 +730,20 @@ extern "C" int trvb_shell_slab_batch(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh src
                             cudaMemcpyHostToDevice, sub->stream));
   TRVB_CUDA(cudaStreamSynchronize(sub->stream));   // the host vectors go out of scope
 
+  // The modes of the low-|k| cube, once for the whole call.
+  const long long nmodes = (long long)K0 * K1 * K2;
+  double2* d_val = nullptr; int* d_shell = nullptr;
+  TRVB_CUDA(trvb_dev_alloc_raw(sub, (void**)&d_val, sizeof(double2) * (size_t)nmodes));
+  TRVB_CUDA(trvb_dev_alloc_raw(sub, (void**)&d_shell, sizeof(int) * (size_t)nmodes));
+  {
+    ShellBatch all; all.klo = d_par; all.khi = d_par + nbins; all.amp = d_par + 2 * nbins;
+    all.nbins = nbins;
+    const int blocks = (int)std::min<long long>((nmodes + 255) / 256, (long long)ctx->num_sms * 16);
+    k_lowk_modes<<<blocks, 256, 0, sub->stream>>>(kview_of(ctx, src), gp, tables_of(ctx), ell, m,
+                                                  lo[0], lo[1], K0, K1, K2, all, d_val, d_shell);
+    TRVB_LAUNCH_CHECK();
+  }
+
   // Sub-batches of shells bound the two transient arrays to ~6 GiB.
   const size_t d_bin = sizeof(double2) * (size_t)nx * K2 * n1;
   const size_t e_bin = sizeof(double2) * (size_t)nx * n1 * nh;
@@ -707,34 +754,50 @@ extern "C" int trvb_shell_slab_batch(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh src
   TRVB_CUDA(trvb_dev_alloc_raw(sub, (void**)&E, e_bin * maxb));
   const size_t out_bin = sizeof(double) * (size_t)nx * n1 * n2;
   int st = 0;
+  auto exec_with_area = [&](cufftHandle plan, size_t ws, auto run) -> int {
+    void* area = nullptr;
+    if (ws) TRVB_CUDA(trvb_dev_alloc_raw(sub, &area, ws));
+    if (ws) TRVB_CUFFT(cufftSetWorkArea(plan, area));
+    int rc = run();
+    if (ws) trvb_dev_free_raw(sub, area);   // stream-ordered reuse
+    return rc;
+  };
   for (int q0 = 0; q0 < nbins && st == 0; q0 += maxb) {
     const int nq = std::min(maxb, nbins - q0);
     TRVB_CUDA(cudaMemsetAsync(D, 0, d_bin * nq, sub->stream));
-    ShellBatch sb; sb.klo = d_par + q0; sb.khi = d_par + nbins + q0; sb.amp = d_par + 2 * nbins + q0;
-    sb.nbins = nq;
     const dim3 grid((K1 * K2 + 127) / 128, (nx + SLAB_XT - 1) / SLAB_XT);
-    k_shell_xdft<<<grid, 128, 0, sub->stream>>>(
-      kview_of(ctx, src), gp, gs, tables_of(ctx), ell, m, lo[0], lo[1], K0, K1, K2, sb,
-      (const double2*)d_tw, nx, D);
+    k_shell_xdft<<<grid, 128, 0, sub->stream>>>(d_val, d_shell, lo[1], K0, K1, K2, q0, nq, n1,
+                                                (const double2*)d_tw, nx, D);
     TRVB_LAUNCH_CHECK();
     cufftHandle plan_y, plan_z;
-    st = get_line_plan(sub, CUFFT_Z2Z, n1, (long long)nq * nx * K2, &plan_y);
+    size_t ws_y = 0, ws_z = 0;
+    st = get_line_plan(sub, CUFFT_Z2Z, n1, (long long)nq * nx * K2, &plan_y, &ws_y);
     if (st) break;
-    TRVB_CUFFT(cufftExecZ2Z(plan_y, (cufftDoubleComplex*)D, (cufftDoubleComplex*)D, CUFFT_INVERSE));
+    st = exec_with_area(plan_y, ws_y, [&]() -> int {
+      TRVB_CUFFT(cufftExecZ2Z(plan_y, (cufftDoubleComplex*)D, (cufftDoubleComplex*)D, CUFFT_INVERSE));
+      return 0;
+    });
+    if (st) break;
     g_trvb_fft_execs++;
     const long long nrows = (long long)nq * nx;
     const int tblocks = (int)std::min<long long>(
       nrows * ((n1 + 31) / 32) * ((nh + 31) / 32), (long long)ctx->num_sms * 16);
     k_slab_transpose<<<tblocks, dim3(32, 8), 0, sub->stream>>>(D, K2, n1, nh, nrows, E);
     TRVB_LAUNCH_CHECK();
-    st = get_line_plan(sub, CUFFT_Z2D, n2, nrows * n1, &plan_z);
+    st = get_line_plan(sub, CUFFT_Z2D, n2, nrows * n1, &plan_z, &ws_z);
     if (st) break;
-    TRVB_CUFFT(cufftExecZ2D(plan_z, (cufftDoubleComplex*)E,
-                            (cufftDoubleReal*)((char*)dst + out_bin * (size_t)q0)));
+    double* out = (double*)((char*)dst + out_bin * (size_t)q0);
+    st = exec_with_area(plan_z, ws_z, [&]() -> int {
+      TRVB_CUFFT(cufftExecZ2D(plan_z, (cufftDoubleComplex*)E, (cufftDoubleReal*)out));
+      return 0;
+    });
+    if (st) break;
     g_trvb_fft_execs++;
   }
   trvb_dev_free_raw(sub, D);
   trvb_dev_free_raw(sub, E);
+  trvb_dev_free_raw(sub, d_val);
+  trvb_dev_free_raw(sub, d_shell);
   trvb_dev_free_raw(sub, d_tw);
   trvb_dev_free_raw(sub, d_par);
   return st;

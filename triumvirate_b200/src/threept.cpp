@@ -930,16 +930,12 @@ trv::BispecMeasurements bispec_impl(
       const int layout = real_path ? TRVB_REAL : TRVB_COMPLEX;
       if (!(have_G && G_M == t.M && G.layout() == layout)) {
         // G_LM(x) = IFFT[delta n_LM(k) / W(k)] / V (S/threept.cpp:452-459).
-        G = dev::Mesh(eng.shared(), pair_grid, layout);
-        if (slab_ctx) {
-          const double none = -1., ampG = 1. / eng.vol();
-          dev::check(trvb_shell_slab_batch(c, sub, dn_LM_ref.view(), 0, 0, &none, &none, &ampG, 1,
-                                           slab_x0, slab_nx, G.view().data),
-                     "trvb_shell_slab_batch (G)");
-        } else {
-          dev::check(trvb_shell_ifft(c, sub, dn_LM_ref.view(), 0, 0, -1., -1., 1. / eng.vol(),
-                                     G.view()), "trvb_shell_ifft (G)");
-        }
+        // (slab mode too: G holds every mode the sub-grid represents -- twice the shells'
+        // cut-off per axis -- so the pruned x-DFT does not pay for it; the whole G is
+        // transformed once, 2 % of the job, and the slab reads its own planes of it)
+        G = dev::Mesh(eng.shared(), sub, layout);
+        dev::check(trvb_shell_ifft(c, sub, dn_LM_ref.view(), 0, 0, -1., -1., 1. / eng.vol(),
+                                   G.view()), "trvb_shell_ifft (G)");
         trvs::count_ifft += 1;
         G_M = t.M; have_G = true;
         dev::profile_mark(c, "G_field");
@@ -950,8 +946,13 @@ trv::BispecMeasurements bispec_impl(
         && mirror_harmonics(params, t, dn_00, kbinning.bin_edges.back());
       const int m_b = mirror ? t.m1 : t.m2;
       std::vector<cdouble> bk_comp;
+      trvb_mesh G_pairs = G.view();
+      if (slab_ctx) {   // REAL layout, x slowest: the slab's planes are contiguous
+        G_pairs.data = static_cast<char*>(G_pairs.data)
+          + sizeof(double) * (size_t)slab_x0 * (size_t)nsub[1] * (size_t)nsub[2];
+      }
       reduce_pairs(
-        eng, pair_grid, dv, active, same_fields || mirror, G.view(),
+        eng, pair_grid, dv, active, same_fields || mirror, G_pairs,
         [&](const std::vector<int>& bins) { return shell_slab(params.ell1, t.m1, bins, layout); },
         [&](const std::vector<int>& bins) { return shell_slab(params.ell2, m_b, bins, layout); },
         bk_comp, mirror);
