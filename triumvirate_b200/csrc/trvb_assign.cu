@@ -1745,24 +1745,56 @@ constexpr long long STAGE_CHUNK = 1 << 20;          // particles per chunk
 constexpr int STAGE_DOUBLES = 7;                    // {x, y, z, w} + {lx, ly, lz}
 struct PinnedStage {
   double* host[2] = {nullptr, nullptr};
-  cudaEvent_t done[2];
+  cudaEvent_t done[2] = {nullptr, nullptr};
   bool ready = false;
 };
-PinnedStage g_stage;
-std::mutex g_stage_mutex;
+struct UploadLane { cudaStream_t stream = nullptr; std::vector<cudaEvent_t> done; };
+// Upload state of ONE device: events and streams belong to the device that was current
+// when they were made, and in single-process multi-GPU mode (one host thread per GPU)
+// every device uploads its own copy of the catalogue at the same time.
+struct DeviceUpload {
+  std::mutex mutex;      // one upload at a time per device
+  PinnedStage stage;
+  UploadLane lane;
+};
+std::mutex g_upload_map_mutex;
+std::map<int, DeviceUpload> g_upload;   // nodes of a std::map never move
 
-cudaError_t ensure_stage() {
-  if (g_stage.ready) return cudaSuccess;
+DeviceUpload& upload_state(int device) {
+  std::lock_guard<std::mutex> lock(g_upload_map_mutex);
+  return g_upload[device];
+}
+
+// current device = the one `st` belongs to
+cudaError_t ensure_stage(PinnedStage& st) {
+  if (st.ready) return cudaSuccess;
   for (int b = 0; b < 2; b++) {
-    cudaError_t e = cudaHostAlloc((void**)&g_stage.host[b],
-                                  sizeof(double) * STAGE_DOUBLES * STAGE_CHUNK, cudaHostAllocDefault);
-    if (e != cudaSuccess) return e;
-    e = cudaEventCreateWithFlags(&g_stage.done[b], cudaEventDisableTiming);
-    if (e != cudaSuccess) return e;
+    if (!st.host[b]) {
+      cudaError_t e = cudaHostAlloc((void**)&st.host[b],
+                                    sizeof(double) * STAGE_DOUBLES * STAGE_CHUNK,
+                                    cudaHostAllocPortable);
+      if (e != cudaSuccess) return e;
+    }
+    if (!st.done[b]) {
+      cudaError_t e = cudaEventCreateWithFlags(&st.done[b], cudaEventDisableTiming);
+      if (e != cudaSuccess) return e;
+    }
   }
-  g_stage.ready = true;
+  st.ready = true;
   return cudaSuccess;
 }
+
+// Frees a half-built catalogue and the staging blocks when an upload fails part-way.
+struct UploadGuard {
+  trvb_ctx* ctx; trvb_cat* cat; void* blocks[3] = {nullptr, nullptr, nullptr};
+  bool armed = true;
+  ~UploadGuard() {
+    if (!armed) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (void* b : blocks) if (b) trvb_dev_free_raw(ctx, b);
+    trvb_cat_destroy(cat);
+  }
+};
 
 template <class F>
 void host_parallel(long long m, F body) {
@@ -1801,11 +1833,14 @@ extern "C" int trvb_cat_create_aos(trvb_ctx* ctx, trvb_cat** out, long long n,
                                    const double* pdata, const double* los) {
   TRVB_REQUIRE(ctx && out && pdata && n > 0, "trvb_cat_create_aos: bad argument");
   TRVB_CUDA(cudaSetDevice(ctx->device));
-  std::lock_guard<std::mutex> lock(g_stage_mutex);
-  TRVB_CUDA(ensure_stage());
+  DeviceUpload& up = upload_state(ctx->device);
+  std::lock_guard<std::mutex> lock(up.mutex);
+  PinnedStage& stage = up.stage;
+  TRVB_CUDA(ensure_stage(stage));
   const size_t nb = sizeof(double) * (size_t)n;
   trvb_cat* cat = new trvb_cat();
   cat->owner = ctx; cat->n = n;
+  UploadGuard guard{ctx, cat};
   TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->x, nb));
   TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->y, nb));
   TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->z, nb));
@@ -1814,15 +1849,17 @@ extern "C" int trvb_cat_create_aos(trvb_ctx* ctx, trvb_cat** out, long long n,
   const size_t chunk_bytes = sizeof(double) * STAGE_DOUBLES * STAGE_CHUNK;
   double* d_chunk[2] = {nullptr, nullptr};
   TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&d_chunk[0], chunk_bytes));
+  guard.blocks[0] = d_chunk[0];
   TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&d_chunk[1], chunk_bytes));
+  guard.blocks[1] = d_chunk[1];
   const int width = los ? 7 : 4;
   long long c = 0;
   for (long long off = 0; off < n; off += STAGE_CHUNK, c++) {
     const long long m = std::min<long long>(STAGE_CHUNK, n - off);
     const int b = (int)(c & 1);
     // the DMA that last read this pinned buffer must have finished
-    if (c >= 2) TRVB_CUDA(cudaEventSynchronize(g_stage.done[b]));
-    double* h = g_stage.host[b];
+    if (c >= 2) TRVB_CUDA(cudaEventSynchronize(stage.done[b]));
+    double* h = stage.host[b];
     host_parallel(m, [=](long long lo, long long hi) {
       for (long long i = lo; i < hi; i++) {
         // ParticleData {pos[3], nz, ws, wc, w} (I/particles.hpp:63-69)
@@ -1834,13 +1871,14 @@ extern "C" int trvb_cat_create_aos(trvb_ctx* ctx, trvb_cat** out, long long n,
     });
     TRVB_CUDA(cudaMemcpyAsync(d_chunk[b], h, sizeof(double) * width * m, cudaMemcpyHostToDevice,
                               ctx->stream));
-    TRVB_CUDA(cudaEventRecord(g_stage.done[b], ctx->stream));
+    TRVB_CUDA(cudaEventRecord(stage.done[b], ctx->stream));
     const int blocks = (int)std::min<long long>(div_up(m, 256), (long long)ctx->num_sms * 8);
     k_unpack_chunk<<<blocks, 256, 0, ctx->stream>>>(d_chunk[b], m, off, n, cat->x, cat->y, cat->z,
                                                    cat->w, los ? cat->los : nullptr);
     TRVB_LAUNCH_CHECK();
   }
   TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  guard.armed = false;
   TRVB_CUDA(trvb_dev_free_raw(ctx, d_chunk[0]));
   TRVB_CUDA(trvb_dev_free_raw(ctx, d_chunk[1]));
   *out = cat;
@@ -1852,16 +1890,12 @@ extern "C" int trvb_cat_create_aos(trvb_ctx* ctx, trvb_cat** out, long long n,
 // ---------------------------------------------------------------------
 namespace {
 
-struct UploadLane { cudaStream_t stream = nullptr; std::vector<cudaEvent_t> done; };
-std::map<int, UploadLane> g_upload_lane;   // per device; guarded by g_stage_mutex
-
 template <int ORDER>
-int streamed_assign(trvb_ctx* ctx, trvb_cat* cat, const double* hx, const double* hy,
+int streamed_assign(trvb_ctx* ctx, trvb_cat* cat, UploadLane& lane, const double* hx, const double* hy,
                     const double* hz, double scale, trvb_mesh mesh) {
   const GridDesc& g = ctx->g;
   const long long n = cat->n;
   const bool cplx_mesh = mesh.layout == TRVB_COMPLEX;
-  UploadLane& lane = g_upload_lane[ctx->device];
   if (!lane.stream) TRVB_CUDA(cudaStreamCreateWithFlags(&lane.stream, cudaStreamNonBlocking));
   // Every chunk costs one sweep over the mesh (its REDs touch sectors all over it: the
   // four-chunk form spends 2.6 ms in the scatter kernels instead of 1.4), so chunks are
@@ -1898,6 +1932,10 @@ int streamed_assign(trvb_ctx* ctx, trvb_cat* cat, const double* hx, const double
   TRVB_REQUIRE(nkeys < 2147483647LL, "mesh too large for int sort keys");
   { int st = alloc_sorted(ctx, cat); if (st) return st; }
   int* offsets = nullptr; int* cursor = nullptr; int* chunk_sums = nullptr;
+  struct Temporaries {   // returned to the arena on every exit, error paths included
+    trvb_ctx* ctx; int** p[3];
+    ~Temporaries() { for (int** q : p) if (*q) { trvb_dev_free_raw(ctx, *q); *q = nullptr; } }
+  } temporaries{ctx, {&offsets, &cursor, &chunk_sums}};
   TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&offsets, sizeof(int) * (size_t)(nkeys + 1)));
   TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cursor, sizeof(int) * (size_t)nkeys));
   TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&chunk_sums,
@@ -1928,9 +1966,6 @@ int streamed_assign(trvb_ctx* ctx, trvb_cat* cat, const double* hx, const double
                                      (double*)mesh.data);
     TRVB_LAUNCH_CHECK();
   }
-  TRVB_CUDA(trvb_dev_free_raw(ctx, offsets));
-  TRVB_CUDA(trvb_dev_free_raw(ctx, cursor));
-  TRVB_CUDA(trvb_dev_free_raw(ctx, chunk_sums));
   for (int a = 0; a < 3; a++) { cat->sort_n[a] = g.n[a]; cat->sort_L[a] = g.L[a]; }
   cat->sort_shifted = 0; cat->sort_kind = 0;
   cat->order_valid = false; cat->chunked = true; cat->scw_valid = false;
@@ -1951,22 +1986,26 @@ extern "C" int trvb_cat_create_assign(trvb_ctx* ctx, trvb_cat** out, long long n
   TRVB_REQUIRE(ctx->parent == nullptr, "trvb_cat_create_assign: root context only");
   TRVB_REQUIRE(n < 2147483647LL, "catalogue too large for int indices");
   TRVB_CUDA(cudaSetDevice(ctx->device));
-  std::lock_guard<std::mutex> lock(g_stage_mutex);
+  DeviceUpload& up = upload_state(ctx->device);
+  std::lock_guard<std::mutex> lock(up.mutex);
+  UploadLane& lane = up.lane;
   trvb_cat* cat = new trvb_cat();
   cat->owner = ctx; cat->n = n;
+  UploadGuard guard{ctx, cat};
   const size_t nb = sizeof(double) * (size_t)n;
   TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->x, nb));
   TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->y, nb));
   TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&cat->z, nb));
   int st = 0;
   switch (ctx->g.order) {
-    case 1: st = streamed_assign<1>(ctx, cat, x, y, z, scale, mesh); break;
-    case 2: st = streamed_assign<2>(ctx, cat, x, y, z, scale, mesh); break;
-    case 3: st = streamed_assign<3>(ctx, cat, x, y, z, scale, mesh); break;
-    case 4: st = streamed_assign<4>(ctx, cat, x, y, z, scale, mesh); break;
+    case 1: st = streamed_assign<1>(ctx, cat, lane, x, y, z, scale, mesh); break;
+    case 2: st = streamed_assign<2>(ctx, cat, lane, x, y, z, scale, mesh); break;
+    case 3: st = streamed_assign<3>(ctx, cat, lane, x, y, z, scale, mesh); break;
+    case 4: st = streamed_assign<4>(ctx, cat, lane, x, y, z, scale, mesh); break;
     default: st = 2;
   }
-  if (st) { trvb_cat_destroy(cat); return st; }
+  if (st) return st;   // the guard frees the half-built catalogue
+  guard.armed = false;
   *out = cat;
   return 0;
 }

@@ -4,6 +4,8 @@
 #define TRVB_COMMON_CUH_
 
 #include <cuda_runtime.h>
+
+#include <atomic>
 #include <cufft.h>
 
 #include <cmath>
@@ -20,8 +22,8 @@
 // ---------------------------------------------------------------------
 
 void trvb_set_error(const char* fmt, ...);
-extern long long g_trvb_launches;    // hand-written kernels launched
-extern long long g_trvb_fft_execs;   // cuFFT executions (library launches)
+extern std::atomic<long long> g_trvb_launches;    // hand-written kernels launched
+extern std::atomic<long long> g_trvb_fft_execs;   // cuFFT executions (library launches)
 
 #define TRVB_CUDA(call)                                                    \
   do {                                                                     \

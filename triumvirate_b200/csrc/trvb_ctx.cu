@@ -6,9 +6,10 @@
 #include <unordered_map>
 
 static thread_local std::string g_err;
-long long g_trvb_launches = 0;
-long long g_trvb_fft_execs = 0;
-static long long g_arena_mallocs = 0;
+// relaxed atomics: several host threads launch in single-process multi-GPU mode
+std::atomic<long long> g_trvb_launches{0};
+std::atomic<long long> g_trvb_fft_execs{0};
+static std::atomic<long long> g_arena_mallocs{0};
 
 void trvb_set_error(const char* fmt, ...) {
   char buf[2048];
