@@ -17,9 +17,12 @@ def run(rank, count):
 res = {}
 full = run(0, 1); full = run(0, 1)
 core.profile_enable(True)
-for no_slab in ("0", "1"):
+quick = os.environ.get("C5_PROBE_SET") == "quick"
+combos = ((0, 1), (0, 2), (0, 8), (7, 8)) if quick else \
+    ((0, 1), (0, 2), (1, 2), (0, 4), (3, 4), (0, 8), (3, 8), (7, 8))
+for no_slab in (("0",) if quick else ("0", "1")):
     os.environ["TRV_NO_SLAB"] = no_slab
-    for rank, count in ((0, 1), (0, 2), (1, 2), (0, 4), (3, 4), (0, 8), (3, 8), (7, 8)):
+    for rank, count in combos:
         if count == 1 and no_slab == "1":
             continue
         for it in range(2):

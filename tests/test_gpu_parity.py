@@ -877,3 +877,67 @@ def test_deterministic_mode_is_bit_reproducible_for_survey_catalogues(core, stat
         for k in o:
             if k != "elapsed_s":
                 assert np.array_equal(o[k], outs[0][k]), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["triu40", "two_lists", "many_fields_row", "tail"])
+def test_gram_reduce_tensor_core_path_against_numpy(case, monkeypatch):
+    """`trvb_gram_reduce` on real meshes (the DMMA kernel: 8 x 8 blocks of pairs on the FP64
+    tensor cores, cells split over the warps) against numpy sums, and against the vector-FMA
+    kernel it replaced (TRV_GRAM_NO_DMMA=1): one list on both sides (upper triangle and
+    row-form pairs with a > b), two different lists, more than 48 fields per side (several
+    launches), and a grid whose cell count is not a multiple of the 256-cell tile."""
+    import ctypes as C
+    import torch
+    from triumvirate_b200 import _lib
+    lib = _lib.trvb()
+
+    class Mesh(C.Structure):
+        _fields_ = [("data", C.c_void_p), ("layout", C.c_int), ("k0_add", C.c_double)]
+
+    gen = np.random.default_rng(77)
+    ng = {"triu40": (48, 40, 36), "two_lists": (32, 32, 30), "many_fields_row": (24, 20, 18),
+          "tail": (10, 10, 10)}[case]
+    ncells = ng[0] * ng[1] * ng[2]
+    ctx = C.c_void_p()
+    n3 = (C.c_int * 3)(*ng); L3 = (C.c_double * 3)(100., 100., 100.)
+    assert lib.trvb_ctx_create(C.byref(ctx), 0, n3, L3, 2) == 0, lib.trvb_last_error()
+    try:
+        if case == "triu40":
+            na = nb = 40; same = True
+            pairs = [(a, b) for a in range(na) for b in range(a, nb)]
+        elif case == "two_lists":
+            na, nb, same = 13, 21, False
+            pairs = [(a, b) for a in range(na) for b in range(nb)]
+        elif case == "many_fields_row":
+            na = nb = 70; same = True
+            pairs = [(55, b) for b in range(nb)] + [(a, a) for a in range(na)] + [(3, 69), (69, 3)]
+        else:
+            na = nb = 5; same = True
+            pairs = [(a, b) for a in range(na) for b in range(a, nb)]
+        fa = gen.standard_normal((na, ncells))
+        fb = fa if same else gen.standard_normal((nb, ncells))
+        g = gen.standard_normal(ncells)
+        dA = torch.from_numpy(fa).cuda(); dB = dA if same else torch.from_numpy(fb).cuda()
+        dG = torch.from_numpy(g).cuda()
+        torch.cuda.synchronize()
+        pa = (C.c_void_p * na)(*[dA[i].data_ptr() for i in range(na)])
+        pb = (C.c_void_p * nb)(*[dB[i].data_ptr() for i in range(nb)])
+        ia = (C.c_int * len(pairs))(*[p[0] for p in pairs])
+        ib = (C.c_int * len(pairs))(*[p[1] for p in pairs])
+        G = Mesh(dG.data_ptr(), 0, 0.)
+        want = np.array([np.sum(fa[a] * fb[b] * g) for a, b in pairs])
+        scale = np.sqrt(ncells)      # |sum| of ncells products of unit normals
+        got = {}
+        for flag in ("0", "1"):
+            monkeypatch.setenv("TRV_GRAM_NO_DMMA", flag)
+            out = np.zeros(2 * len(pairs))
+            st = lib.trvb_gram_reduce(ctx, pa, na, pb, nb, G, ia, ib, len(pairs), 0,
+                                      out.ctypes.data_as(C.POINTER(C.c_double)))
+            assert st == 0, lib.trvb_last_error()
+            assert np.all(out[1::2] == 0.)
+            got[flag] = out[0::2]
+            assert np.max(np.abs(out[0::2] - want)) < 1.e-11 * scale, (case, flag)
+        assert np.max(np.abs(got["0"] - got["1"])) < 1.e-11 * scale
+    finally:
+        lib.trvb_ctx_destroy(ctx)

@@ -526,16 +526,23 @@ extern "C" int trvb_shell_ifft_batch(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh src
 }
 
 // ---------------------------------------------------------------------
-// Slab (x-plane) form of the batched shell transform.
+// Pruned (and x-slab) form of the batched shell transform.
 // ---------------------------------------------------------------------
+//
+// A shell [klo, khi) only has modes with |k_a| <= khi on every axis: on the sub-grid
+// (n_s >= 4 m_cut + 2 per axis) at most a (2 m + 1)^2 (m + 1) corner block of the
+// n_s^2 (n_s/2 + 1) half-spectrum is non-zero.  The 3-D inverse transform is taken one
+// axis at a time and every pass only touches the lines that can be non-zero:
+//   x: (2m+1)(m+1) lines  ->  y: n_x (m+1) lines  ->  z: n_x n_y lines (c2r),
+// 6 % + 24 % + 100 % of the line transforms of a dense 3-D FFT at m = n_s/4, less for the
+// inner shells (the extents follow the largest khi of each sub-batch of shells).  With
+// x-slabs [x0, x0 + nx) the y and z passes run on the slab's planes only.
 
 namespace {
 
-constexpr int SLAB_XT = 16;       // x-planes accumulated per thread
-
-// The filtered modes of the low-|k| cube, evaluated ONCE per call: value y_lm src / W and
-// the shell (index into the call's bin list, -1: none) of every mode (k_x, k_z >= 0, k_y),
-// laid out [a = k_x][c = k_z][b = k_y] so that the x-DFT reads them coalesced along k_y.
+// The filtered modes of the low-|k| cube, evaluated ONCE per call: value y_lm src / W x amp
+// and the shell (index into the call's bin list, -1: none) of every mode (k_y, k_z >= 0,
+// k_x), laid out [c = k_z][b = k_y][a = k_x]: the x-lines are contiguous.
 __global__ void __launch_bounds__(256)
 k_lowk_modes(KView src, GridDesc gp, Tables tb, int ell, int m, int lo0, int lo1,
              int K0, int K1, int K2, ShellBatch sb, double2* __restrict__ val,
@@ -544,7 +551,7 @@ k_lowk_modes(KView src, GridDesc gp, Tables tb, int ell, int m, int lo0, int lo1
   const long long total = (long long)K0 * K1 * K2;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
        t += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(t % K1), c = (int)((t / K1) % K2), a = (int)(t / ((long long)K1 * K2));
+    const int a = (int)(t % K0), b = (int)((t / K0) % K1), c = (int)(t / ((long long)K0 * K1));
     const int mi = lo0 + a, mj = lo1 + b, mk = c;
     const double kx = __dmul_rn((double)mi, gp.dk[0]);
     const double ky = __dmul_rn((double)mj, gp.dk[1]);
@@ -566,69 +573,95 @@ k_lowk_modes(KView src, GridDesc gp, Tables tb, int ell, int m, int lo0, int lo1
   }
 }
 
-// Direct x-DFT of the low-|k| modes for the planes of the slab.  Thread = one (k_y, k_z)
-// column of the cube and SLAB_XT planes; it walks k_x and adds twiddle x mode to the
-// accumulators of the shell that holds the mode (shells q0 .. q0 + nq - 1 of the call).
-// Output D[q][x][c = k_z][y-slot of k_y] (zero-filled beforehand): the rows the y-transform
-// reads.  A column meets each shell in at most two runs of k_x, so the flush is rare.
-__global__ void __launch_bounds__(128)
-k_shell_xdft(const double2* __restrict__ val, const int* __restrict__ shell, int lo1,
-             int K0, int K1, int K2, int q0, int nq, int n1,
-             const double2* __restrict__ tw, int nx, double2* __restrict__ D) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;   // c * K1 + b
-  if (col >= K1 * K2) return;
-  const int b = col % K1, c = col / K1;
-  const int xbeg = blockIdx.y * SLAB_XT;
-  const int mj = lo1 + b;
-  const int ys = mj >= 0 ? mj : mj + n1;
-  double2 acc[SLAB_XT];
-  int cur = -1;
-  auto flush = [&]() {
-    if (cur < 0) return;
-#pragma unroll
-    for (int t = 0; t < SLAB_XT; t++) {
-      const int x = xbeg + t;
-      if (x < nx) {
-        double2* d = D + (((long long)cur * nx + x) * K2 + c) * n1 + ys;
-        double2 v = *d; v.x += acc[t].x; v.y += acc[t].y; *d = v;
-      }
+// Extents of the non-zero corner block of one sub-batch of shells (signed mode indices
+// -mc[a] .. mc[a]; k_z >= 0 only) inside the call's cube (-gc[a] .. gc[a]).
+struct PruneDims {
+  int mc[3];    // sub-batch
+  int gc[3];    // whole call: the layout of val / shell
+};
+
+// Pass 1 input: zero-padded x-lines A[q][c][b][x] of the nq shells of the sub-batch,
+// c = k_z in [0, mc2], b = k_y + mc1 in [0, 2 mc1], x = the slot of k_x on the n0-line.
+__global__ void __launch_bounds__(256)
+k_shell_xlines(const double2* __restrict__ val, const int* __restrict__ shell, PruneDims pd,
+               int q0, int nq, int n0, double2* __restrict__ A) {
+  const int K1 = 2 * pd.mc[1] + 1, K2 = pd.mc[2] + 1;
+  const int G0 = 2 * pd.gc[0] + 1, G1 = 2 * pd.gc[1] + 1;
+  const long long lines = (long long)K1 * K2;
+  const long long total = lines * n0;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(t % n0);
+    const long long col = t / n0;
+    const int b = (int)(col % K1), c = (int)(col / K1);
+    int mi = 0; bool live = true;
+    if (x <= pd.mc[0]) mi = x;
+    else if (x >= n0 - pd.mc[0]) mi = x - n0;
+    else live = false;
+    int q = -1;
+    double2 v = make_double2(0., 0.);
+    if (live) {
+      const int mj = b - pd.mc[1];
+      const long long g = ((long long)c * G1 + (mj + pd.gc[1])) * G0 + (mi + pd.gc[0]);
+      q = shell[g] - q0;
+      if (q >= 0 && q < nq) v = val[g];
     }
-  };
-  const long long plane = (long long)K1 * K2;
-  for (int a = 0; a < K0; a++) {
-    const int q = shell[a * plane + col] - q0;
-    if (q < 0 || q >= nq) continue;
-    const double2 v = val[a * plane + col];
-    if (q != cur) {
-      flush();
-      cur = q;
-#pragma unroll
-      for (int t = 0; t < SLAB_XT; t++) acc[t] = make_double2(0., 0.);
-    }
-#pragma unroll
-    for (int t = 0; t < SLAB_XT; t++) {
-      const int x = min(xbeg + t, nx - 1);
-      const double2 w = __ldg(tw + (long long)x * K0 + a);
-      acc[t].x += w.x * v.x - w.y * v.y;
-      acc[t].y += w.x * v.y + w.y * v.x;
+    for (int i = 0; i < nq; i++) {
+      A[((long long)i * lines + col) * n0 + x] = (i == q) ? v : make_double2(0., 0.);
     }
   }
-  flush();
 }
 
-// E[r][y][kz] = (kz < K2) ? D[r][kz][y] : 0 for every (shell, plane) r: the rows the
-// z-transform reads, zero-padded to the half-spectrum length.
+// Pass 2 input: B[q][xi][c][y] = A[q][c][b(y)][x0 + xi], zero where y is the slot of no k_y
+// of the block.  One 32 x 32 tile (x by y) per step through shared memory.
 __global__ void __launch_bounds__(256)
-k_slab_transpose(const double2* __restrict__ D, int K2, int n1, int nh, long long nrows,
-                 double2* __restrict__ E) {
+k_shell_ylines(const double2* __restrict__ A, PruneDims pd, int nq, int n0, int n1, int x0,
+               int nx, double2* __restrict__ B) {
   __shared__ double2 tile[32][33];
-  const int tiles_y = (n1 + 31) / 32, tiles_k = (nh + 31) / 32;
+  const int K1 = 2 * pd.mc[1] + 1, K2 = pd.mc[2] + 1;
+  const int tiles_x = (nx + 31) / 32, tiles_y = (n1 + 31) / 32;
+  const long long ntile = (long long)nq * K2 * tiles_x * tiles_y;
+  for (long long t = blockIdx.x; t < ntile; t += gridDim.x) {
+    const int ty = (int)(t % tiles_y);
+    const int tx = (int)((t / tiles_y) % tiles_x);
+    const long long qc = t / ((long long)tiles_y * tiles_x);
+    const int c = (int)(qc % K2), q = (int)(qc / K2);
+    // rows of the tile: 32 y-slots; columns: 32 planes
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int y = ty * 32 + i, xi = tx * 32 + threadIdx.x;
+      int b = -1;
+      if (y < n1) {
+        if (y <= pd.mc[1]) b = y + pd.mc[1];
+        else if (y >= n1 - pd.mc[1]) b = y - n1 + pd.mc[1];
+      }
+      tile[i][threadIdx.x] = (b >= 0 && xi < nx)
+        ? A[(((long long)q * K2 + c) * K1 + b) * n0 + x0 + xi] : make_double2(0., 0.);
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int xi = tx * 32 + i, y = ty * 32 + threadIdx.x;
+      if (xi < nx && y < n1) {
+        B[((((long long)q * nx + xi) * K2) + c) * n1 + y] = tile[threadIdx.x][i];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Pass 3 input: E[r][y][kz] = B[r][kz][y] for kz < K2, zero for K2 <= kz < kw, for every
+// (shell, plane) r: the rows the c2r transform reads.  Entries kz >= kw are zero already
+// (E is cleared once per call and the blocks of the sub-batches only grow).
+__global__ void __launch_bounds__(256)
+k_shell_zlines(const double2* __restrict__ B, int K2, int kw, int n1, int nh, long long nrows,
+               double2* __restrict__ E) {
+  __shared__ double2 tile[32][33];
+  const int tiles_y = (n1 + 31) / 32, tiles_k = (kw + 31) / 32;
   const long long ntile = nrows * tiles_y * tiles_k;
   for (long long t = blockIdx.x; t < ntile; t += gridDim.x) {
     const int tk = (int)(t % tiles_k);
     const int ty = (int)((t / tiles_k) % tiles_y);
     const long long r = t / ((long long)tiles_k * tiles_y);
-    const double2* src = D + r * (long long)K2 * n1;
+    const double2* src = B + r * (long long)K2 * n1;
     double2* dst = E + r * (long long)n1 * nh;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
       const int kz = tk * 32 + i, y = ty * 32 + threadIdx.x;
@@ -637,7 +670,7 @@ k_slab_transpose(const double2* __restrict__ D, int K2, int n1, int nh, long lon
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
       const int y = ty * 32 + i, kz = tk * 32 + threadIdx.x;
-      if (y < n1 && kz < nh) dst[(long long)y * nh + kz] = tile[threadIdx.x][i];
+      if (y < n1 && kz < kw) dst[(long long)y * nh + kz] = tile[threadIdx.x][i];
     }
     __syncthreads();
   }
@@ -651,20 +684,26 @@ int get_line_plan(trvb_ctx* ctx, cufftType type, int n, long long batch, cufftHa
   const std::vector<long long> key = {(long long)type, (long long)n, batch};
   auto it = ctx->line_plans.find(key);
   if (it == ctx->line_plans.end()) {
-    TRVB_REQUIRE(batch < 2147483647LL, "slab transform: batch too large");
+    TRVB_REQUIRE(batch < 2147483647LL, "pruned transform: batch too large");
+    if (ctx->line_plans.size() >= 192) {   // binning after binning in one process: start over
+      TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
+      for (auto& kv : ctx->line_plans) cufftDestroy(kv.second);
+      ctx->line_plans.clear(); ctx->line_plan_work.clear();
+    }
     cufftHandle plan;
     TRVB_CUFFT(cufftCreate(&plan));
     TRVB_CUFFT(cufftSetAutoAllocation(plan, 0));
     int len[1] = {n};
     size_t ws = 0;
+    cufftResult rc;
     if (type == CUFFT_Z2Z) {
-      TRVB_CUFFT(cufftMakePlanMany(plan, 1, len, nullptr, 1, n, nullptr, 1, n, CUFFT_Z2Z,
-                                   (int)batch, &ws));
+      rc = cufftMakePlanMany(plan, 1, len, nullptr, 1, n, nullptr, 1, n, CUFFT_Z2Z, (int)batch, &ws);
     } else {
       int inembed[1] = {n / 2 + 1}, onembed[1] = {n};
-      TRVB_CUFFT(cufftMakePlanMany(plan, 1, len, inembed, 1, n / 2 + 1, onembed, 1, n,
-                                   CUFFT_Z2D, (int)batch, &ws));
+      rc = cufftMakePlanMany(plan, 1, len, inembed, 1, n / 2 + 1, onembed, 1, n, CUFFT_Z2D,
+                             (int)batch, &ws);
     }
+    if (rc != CUFFT_SUCCESS) { cufftDestroy(plan); TRVB_CUFFT(rc); }
     TRVB_CUFFT(cufftSetStream(plan, ctx->stream));
     it = ctx->line_plans.emplace(key, plan).first;
     ctx->line_plan_work[key] = ws;
@@ -673,6 +712,18 @@ int get_line_plan(trvb_ctx* ctx, cufftType type, int n, long long batch, cufftHa
   *work_bytes = ctx->line_plan_work[key];
   return 0;
 }
+
+// Arena blocks of one call, returned on every exit.
+struct ArenaBlocks {
+  trvb_ctx* ctx;
+  std::vector<void*> blocks;
+  cudaError_t get(void** p, size_t bytes) {
+    cudaError_t e = trvb_dev_alloc_raw(ctx, p, bytes);
+    if (e == cudaSuccess) blocks.push_back(*p);
+    return e;
+  }
+  ~ArenaBlocks() { for (void* b : blocks) trvb_dev_free_raw(ctx, b); }
+};
 
 }  // namespace
 
@@ -689,71 +740,72 @@ extern "C" int trvb_shell_slab_batch(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh src
   const GridDesc& gs = sub->g;
   TRVB_REQUIRE(x0 >= 0 && nx > 0 && x0 + nx <= gs.n[0], "trvb_shell_slab_batch: planes [%d, %d) "
                "outside the %d planes of the sub-grid", x0, x0 + nx, gs.n[0]);
-  // Low-|k| cube that holds every shell, strictly inside the sub-grid's Nyquist frequency.
-  double kmax = 0.;
-  bool unbounded = false;
-  for (int q = 0; q < nbins; q++) {
-    if (klo[q] < 0. && khi[q] < 0.) unbounded = true;
-    kmax = std::max(kmax, khi[q]);
-  }
-  int lo[3], cnt[3];
-  for (int a = 0; a < 3; a++) {
-    const long long smax = (long long)((gs.n[a] - 1) / 2);
-    long long mc = unbounded ? smax : (long long)std::floor(kmax / gp.dk[a]) + 1;
-    mc = std::min(mc, smax);
-    lo[a] = (int)-mc; cnt[a] = (int)(2 * mc + 1);
-  }
-  const int K0 = cnt[0], K1 = cnt[1], K2 = -lo[2] + 1;   // k_z >= 0 only (Hermitian half)
-  const int n1 = gs.n[1], n2 = gs.n[2], nh = gs.nh;
-
-  // twiddles exp(+2 pi i k_x (x0 + x) / n0), argument reduced exactly in integers
-  std::vector<double> h_tw(2 * (size_t)nx * K0);
-  for (int x = 0; x < nx; x++) {
-    for (int a = 0; a < K0; a++) {
-      long long r = ((long long)(lo[0] + a) * (x0 + x)) % gs.n[0];
-      if (r < 0) r += gs.n[0];
-      const double ang = 2. * M_PI * (double)r / (double)gs.n[0];
-      h_tw[2 * ((size_t)x * K0 + a)] = std::cos(ang);
-      h_tw[2 * ((size_t)x * K0 + a) + 1] = std::sin(ang);
+  const int n0 = gs.n[0], n1 = gs.n[1], n2 = gs.n[2], nh = gs.nh;
+  // Largest signed mode index per axis that a shell reaching `kmax` can hold, strictly
+  // inside the sub-grid's Nyquist frequency.
+  auto extent_of = [&](double kmax, bool unbounded, int mc[3]) {
+    for (int a = 0; a < 3; a++) {
+      const long long smax = (long long)((gs.n[a] - 1) / 2);
+      long long v = unbounded ? smax : (long long)std::floor(kmax / gp.dk[a]) + 1;
+      mc[a] = (int)std::min(v, smax);
     }
+  };
+  PruneDims pd;
+  {
+    double kmax = 0.; bool unbounded = false;
+    for (int q = 0; q < nbins; q++) {
+      if (klo[q] < 0. && khi[q] < 0.) unbounded = true;
+      kmax = std::max(kmax, khi[q]);
+    }
+    extent_of(kmax, unbounded, pd.gc);
   }
-  double* d_tw = nullptr; double* d_par = nullptr;
-  TRVB_CUDA(trvb_dev_alloc_raw(sub, (void**)&d_tw, sizeof(double) * h_tw.size()));
-  TRVB_CUDA(trvb_dev_alloc_raw(sub, (void**)&d_par, sizeof(double) * 3 * (size_t)nbins));
+  const int G0 = 2 * pd.gc[0] + 1, G1 = 2 * pd.gc[1] + 1, G2 = pd.gc[2] + 1;
+
+  ArenaBlocks arena{sub, {}};
+  double* d_par = nullptr;
+  TRVB_CUDA(arena.get((void**)&d_par, sizeof(double) * 3 * (size_t)nbins));
   std::vector<double> h_par(3 * (size_t)nbins);
   for (int q = 0; q < nbins; q++) {
     h_par[q] = klo[q]; h_par[nbins + q] = khi[q]; h_par[2 * nbins + q] = amp[q];
   }
-  TRVB_CUDA(cudaMemcpyAsync(d_tw, h_tw.data(), sizeof(double) * h_tw.size(),
-                            cudaMemcpyHostToDevice, sub->stream));
+  // Pageable source: the copy is staged before cudaMemcpyAsync returns.
   TRVB_CUDA(cudaMemcpyAsync(d_par, h_par.data(), sizeof(double) * h_par.size(),
                             cudaMemcpyHostToDevice, sub->stream));
-  TRVB_CUDA(cudaStreamSynchronize(sub->stream));   // the host vectors go out of scope
 
   // The modes of the low-|k| cube, once for the whole call.
-  const long long nmodes = (long long)K0 * K1 * K2;
+  const long long nmodes = (long long)G0 * G1 * G2;
   double2* d_val = nullptr; int* d_shell = nullptr;
-  TRVB_CUDA(trvb_dev_alloc_raw(sub, (void**)&d_val, sizeof(double2) * (size_t)nmodes));
-  TRVB_CUDA(trvb_dev_alloc_raw(sub, (void**)&d_shell, sizeof(int) * (size_t)nmodes));
+  TRVB_CUDA(arena.get((void**)&d_val, sizeof(double2) * (size_t)nmodes));
+  TRVB_CUDA(arena.get((void**)&d_shell, sizeof(int) * (size_t)nmodes));
   {
     ShellBatch all; all.klo = d_par; all.khi = d_par + nbins; all.amp = d_par + 2 * nbins;
     all.nbins = nbins;
     const int blocks = (int)std::min<long long>((nmodes + 255) / 256, (long long)ctx->num_sms * 16);
     k_lowk_modes<<<blocks, 256, 0, sub->stream>>>(kview_of(ctx, src), gp, tables_of(ctx), ell, m,
-                                                  lo[0], lo[1], K0, K1, K2, all, d_val, d_shell);
+                                                  -pd.gc[0], -pd.gc[1], G0, G1, G2, all, d_val,
+                                                  d_shell);
     TRVB_LAUNCH_CHECK();
   }
 
-  // Sub-batches of shells bound the two transient arrays to ~6 GiB.
-  const size_t d_bin = sizeof(double2) * (size_t)nx * K2 * n1;
+  // Sub-batches of consecutive shells: they bound the transient arrays to ~6 GiB, and each
+  // takes the extents of its own largest shell (TRV_SHELL_GROUPS = least number of them).
+  const size_t a_bin = sizeof(double2) * (size_t)G1 * G2 * n0;
+  const size_t b_bin = sizeof(double2) * (size_t)nx * G2 * n1;
   const size_t e_bin = sizeof(double2) * (size_t)nx * n1 * nh;
-  int maxb = (int)std::max<size_t>(1, ((size_t)6 << 30) / (d_bin + e_bin));
-  maxb = std::min(maxb, nbins);
-  double2* D = nullptr; double2* E = nullptr;
-  TRVB_CUDA(trvb_dev_alloc_raw(sub, (void**)&D, d_bin * maxb));
-  TRVB_CUDA(trvb_dev_alloc_raw(sub, (void**)&E, e_bin * maxb));
+  int maxb = (int)std::max<size_t>(1, ((size_t)6 << 30) / (a_bin + b_bin + e_bin));
+  {
+    const char* env = getenv("TRV_SHELL_GROUPS");
+    const int groups = std::max(1, env ? atoi(env) : 4);
+    maxb = std::min(maxb, (nbins + groups - 1) / groups);
+  }
+  maxb = std::max(1, std::min(maxb, nbins));
+  double2* A = nullptr; double2* B = nullptr; double2* E = nullptr;
+  TRVB_CUDA(arena.get((void**)&A, a_bin * maxb));
+  TRVB_CUDA(arena.get((void**)&B, b_bin * maxb));
+  TRVB_CUDA(arena.get((void**)&E, e_bin * maxb));
+  TRVB_CUDA(cudaMemsetAsync(E, 0, e_bin * maxb, sub->stream));
+  int e_written = 0;   // kz extent of E that may hold non-zero values
   const size_t out_bin = sizeof(double) * (size_t)nx * n1 * n2;
-  int st = 0;
   auto exec_with_area = [&](cufftHandle plan, size_t ws, auto run) -> int {
     void* area = nullptr;
     if (ws) TRVB_CUDA(trvb_dev_alloc_raw(sub, &area, ws));
@@ -762,45 +814,71 @@ extern "C" int trvb_shell_slab_batch(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh src
     if (ws) trvb_dev_free_raw(sub, area);   // stream-ordered reuse
     return rc;
   };
-  for (int q0 = 0; q0 < nbins && st == 0; q0 += maxb) {
+  const long long cap = (long long)ctx->num_sms * 16;
+  for (int q0 = 0; q0 < nbins; q0 += maxb) {
     const int nq = std::min(maxb, nbins - q0);
-    TRVB_CUDA(cudaMemsetAsync(D, 0, d_bin * nq, sub->stream));
-    const dim3 grid((K1 * K2 + 127) / 128, (nx + SLAB_XT - 1) / SLAB_XT);
-    k_shell_xdft<<<grid, 128, 0, sub->stream>>>(d_val, d_shell, lo[1], K0, K1, K2, q0, nq, n1,
-                                                (const double2*)d_tw, nx, D);
-    TRVB_LAUNCH_CHECK();
-    cufftHandle plan_y, plan_z;
-    size_t ws_y = 0, ws_z = 0;
-    st = get_line_plan(sub, CUFFT_Z2Z, n1, (long long)nq * nx * K2, &plan_y, &ws_y);
-    if (st) break;
-    st = exec_with_area(plan_y, ws_y, [&]() -> int {
-      TRVB_CUFFT(cufftExecZ2Z(plan_y, (cufftDoubleComplex*)D, (cufftDoubleComplex*)D, CUFFT_INVERSE));
+    {
+      double kmax = 0.; bool unbounded = false;
+      for (int q = q0; q < q0 + nq; q++) {
+        if (klo[q] < 0. && khi[q] < 0.) unbounded = true;
+        kmax = std::max(kmax, khi[q]);
+      }
+      extent_of(kmax, unbounded, pd.mc);
+    }
+    const int K1 = 2 * pd.mc[1] + 1, K2 = pd.mc[2] + 1;
+    const long long lines_x = (long long)nq * K1 * K2;
+    // -- x --
+    {
+      const long long work = (long long)K1 * K2 * n0;
+      k_shell_xlines<<<(int)std::min((work + 255) / 256, cap), 256, 0, sub->stream>>>(
+        d_val, d_shell, pd, q0, nq, n0, A);
+      TRVB_LAUNCH_CHECK();
+    }
+    cufftHandle plan; size_t ws = 0;
+    int st = get_line_plan(sub, CUFFT_Z2Z, n0, lines_x, &plan, &ws);
+    if (st) return st;
+    st = exec_with_area(plan, ws, [&]() -> int {
+      TRVB_CUFFT(cufftExecZ2Z(plan, (cufftDoubleComplex*)A, (cufftDoubleComplex*)A, CUFFT_INVERSE));
       return 0;
     });
-    if (st) break;
+    if (st) return st;
     g_trvb_fft_execs++;
-    const long long nrows = (long long)nq * nx;
-    const int tblocks = (int)std::min<long long>(
-      nrows * ((n1 + 31) / 32) * ((nh + 31) / 32), (long long)ctx->num_sms * 16);
-    k_slab_transpose<<<tblocks, dim3(32, 8), 0, sub->stream>>>(D, K2, n1, nh, nrows, E);
-    TRVB_LAUNCH_CHECK();
-    st = get_line_plan(sub, CUFFT_Z2D, n2, nrows * n1, &plan_z, &ws_z);
-    if (st) break;
-    double* out = (double*)((char*)dst + out_bin * (size_t)q0);
-    st = exec_with_area(plan_z, ws_z, [&]() -> int {
-      TRVB_CUFFT(cufftExecZ2D(plan_z, (cufftDoubleComplex*)E, (cufftDoubleReal*)out));
+    // -- y --
+    {
+      const long long ntile = (long long)nq * K2 * ((nx + 31) / 32) * ((n1 + 31) / 32);
+      k_shell_ylines<<<(int)std::min(ntile, cap), dim3(32, 8), 0, sub->stream>>>(
+        A, pd, nq, n0, n1, x0, nx, B);
+      TRVB_LAUNCH_CHECK();
+    }
+    st = get_line_plan(sub, CUFFT_Z2Z, n1, (long long)nq * nx * K2, &plan, &ws);
+    if (st) return st;
+    st = exec_with_area(plan, ws, [&]() -> int {
+      TRVB_CUFFT(cufftExecZ2Z(plan, (cufftDoubleComplex*)B, (cufftDoubleComplex*)B, CUFFT_INVERSE));
       return 0;
     });
-    if (st) break;
+    if (st) return st;
+    g_trvb_fft_execs++;
+    // -- z --
+    const long long nrows = (long long)nq * nx;
+    const int kw = std::min(nh, std::max(K2, e_written));
+    e_written = kw;
+    {
+      const long long ntile = nrows * ((n1 + 31) / 32) * ((kw + 31) / 32);
+      k_shell_zlines<<<(int)std::min(ntile, cap), dim3(32, 8), 0, sub->stream>>>(
+        B, K2, kw, n1, nh, nrows, E);
+      TRVB_LAUNCH_CHECK();
+    }
+    st = get_line_plan(sub, CUFFT_Z2D, n2, nrows * n1, &plan, &ws);
+    if (st) return st;
+    double* out = (double*)((char*)dst + out_bin * (size_t)q0);
+    st = exec_with_area(plan, ws, [&]() -> int {
+      TRVB_CUFFT(cufftExecZ2D(plan, (cufftDoubleComplex*)E, (cufftDoubleReal*)out));
+      return 0;
+    });
+    if (st) return st;
     g_trvb_fft_execs++;
   }
-  trvb_dev_free_raw(sub, D);
-  trvb_dev_free_raw(sub, E);
-  trvb_dev_free_raw(sub, d_val);
-  trvb_dev_free_raw(sub, d_shell);
-  trvb_dev_free_raw(sub, d_tw);
-  trvb_dev_free_raw(sub, d_par);
-  return st;
+  return 0;
 }
 
 extern "C" int trvb_sjl_ifft_batch(trvb_ctx* ctx, trvb_mesh src, int ell, int m,

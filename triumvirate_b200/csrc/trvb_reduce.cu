@@ -1037,6 +1037,321 @@ int run_binned(trvb_ctx* ctx, const std::vector<BinRule>& rules, long long nwork
 }  // namespace
 
 // =====================================================================
+// Real-field Gram product on the FP64 tensor cores (DMMA, mma.sync m8n8k4)
+// =====================================================================
+//
+// sum_x F_a(x) F_b(x) G(x) for all pairs is a skinny fp64 GEMM: C[a][b] += A[a][x] B'[x][b]
+// with B'[x][b] = F_b(x) G(x) and x running over the cells.  The vector-FMA kernels above
+// hold a private 4 x 4 pair block per lane and re-read eight operands from shared memory
+// for every sixteen FMAs -- at 4.5 B per FMA the 128 B/clk of shared-memory bandwidth, not
+// HBM, is what bounds them (C5: 29 ms for a 52 GB read).  With m8n8k4 the 8 x 8 block of C
+// is spread over the warp (two doubles per lane), a fragment of eight fields x four cells
+// is one 8-byte load per lane, and a warp that holds the fragments of all its field blocks
+// issues every (a-block, b-block) product from registers: 6 loads for 15 DMMAs (3840 FMAs)
+// on 40 fields, 0.4 B per FMA.  One warp owns ALL pair blocks; the eight warps of the CTA
+// split the cells of the staged tile, so every field is read from HBM exactly once per
+// launch and a launch covers up to 48 x 48 fields.
+//
+// Stage rows are padded by four doubles: the eight rows of a fragment then fall into
+// distinct banks (2 wavefronts per 64-bit warp load, the minimum).
+
+namespace {
+
+constexpr int DM_WARPS = 8;                      // consumer warps: they split the cells of a tile
+constexpr int DM_THREADS = (DM_WARPS + 1) * 32;  // + one producer warp feeding the TMA engine
+constexpr int DM_PAD = 4;
+constexpr int DM_MAXB = 6;        // 8-field blocks per launch, one list on both sides
+constexpr int DM_MAXB_PAIR = 4;   // ... per side with two lists (or several groups)
+constexpr int DM_MAX_STAGES = 6;
+constexpr size_t DM_SMEM_LIMIT = 220 * 1024;
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(a) : "memory");
+}
+
+// sel_a: 8 * nab field indices into A (padded by repetition), sel_b likewise into B
+// (unused when SAME: the b-blocks are the a-blocks).  mask bit (8 i + j): block (i, j)
+// wanted.  partial: [blockIdx][i * NB8 + j][64] (row-major 8 x 8 blocks).
+//
+// A ring of `nstages` tiles of T cells: the producer warp refills a stage as soon as the
+// eight consumer warps have released it (`empty` barriers) and arms its `full` barrier
+// with the byte count of the row copies; a consumer warp waits for `full`, takes its
+// T / 8 cells through the tensor cores and releases the stage -- no block-wide barrier
+// in the loop, several tiles in flight per SM.
+template <int NB8, bool SAME, int T>
+__global__ void __launch_bounds__(DM_THREADS, 1)
+k_gram_dmma(const double* const* __restrict__ A, const double* const* __restrict__ B,
+            const double* __restrict__ G, const int* __restrict__ sel_a, int nab,
+            const int* __restrict__ sel_b, int nbb, long long ncells,
+            unsigned long long mask, int nstages, double* __restrict__ partial) {
+  constexpr int PITCH = T + DM_PAD;
+  extern __shared__ __align__(128) double2 smem_raw[];
+  const int na = 8 * nab, nb = SAME ? 0 : 8 * nbb;
+  const int rows = na + nb + 1;
+  const size_t stage_doubles = (size_t)rows * PITCH;
+  double* ring = reinterpret_cast<double*>(smem_raw);
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(ring + stage_doubles * nstages);
+  unsigned long long* empty = full + DM_MAX_STAGES;
+  const double** s_ptr = reinterpret_cast<const double**>(empty + DM_MAX_STAGES);
+  for (int r = threadIdx.x; r < rows; r += DM_THREADS) {
+    s_ptr[r] = r < na ? A[sel_a[r]] : (r < na + nb ? B[sel_b[r - na]] : G);
+  }
+  if (threadIdx.x == 0) {
+    for (int st = 0; st < nstages; st++) { mbar_init(&full[st], 1); mbar_init(&empty[st], DM_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long ntiles = (ncells + T - 1) / T;
+  double acc[NB8 * NB8][2];
+#pragma unroll
+  for (int e = 0; e < NB8 * NB8; e++) { acc[e][0] = 0.; acc[e][1] = 0.; }
+
+  if (warp == DM_WARPS) {
+    // ---- producer ----
+    int n = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, n++) {
+      const int st = n % nstages, round = n / nstages;
+      if (round > 0) mbar_wait(&empty[st], (unsigned)((round - 1) & 1));
+      const long long base = tile * T;
+      const int valid = (int)min((long long)T, ncells - base);
+      const unsigned row_bytes = (unsigned)(valid * sizeof(double));
+      if (lane == 0) mbar_arrive_expect_tx(&full[st], row_bytes * (unsigned)rows);
+      __syncwarp();
+      double* dst = ring + stage_doubles * st;
+      for (int r = lane; r < rows; r += 32) {
+        tma_load_1d(dst + (size_t)r * PITCH, s_ptr[r] + base, row_bytes, &full[st]);
+      }
+    }
+  } else {
+    // ---- consumers ----
+    const int frow = lane >> 2, fcol = lane & 3;
+    constexpr int KSTEPS = T / (4 * DM_WARPS);
+    int n = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, n++) {
+      const int st = n % nstages, round = n / nstages;
+      mbar_wait(&full[st], (unsigned)(round & 1));
+      const double* cur = ring + stage_doubles * st;
+      const int valid = (int)min((long long)T, ncells - tile * T);
+      const double* sA = cur + (size_t)frow * PITCH;
+      const double* sB = cur + (size_t)(na + frow) * PITCH;
+      const double* sG = cur + (size_t)(na + nb) * PITCH;
+#pragma unroll
+      for (int ks = 0; ks < KSTEPS; ks++) {
+        const int kk = (warp * KSTEPS + ks) * 4 + fcol;
+        const bool live = kk < valid;
+        const double g = live ? sG[kk] : 0.;
+        double af[NB8], bf[NB8];
+#pragma unroll
+        for (int i = 0; i < NB8; i++) {
+          af[i] = (live && i < nab) ? sA[(size_t)(8 * i) * PITCH + kk] : 0.;
+        }
+#pragma unroll
+        for (int j = 0; j < NB8; j++) {
+          if (SAME) bf[j] = af[j] * g;
+          else bf[j] = ((live && j < nbb) ? sB[(size_t)(8 * j) * PITCH + kk] : 0.) * g;
+        }
+#pragma unroll
+        for (int i = 0; i < NB8; i++) {
+#pragma unroll
+          for (int j = SAME ? i : 0; j < NB8; j++) {
+            if ((mask >> (8 * i + j)) & 1ull) dmma884(acc[i * NB8 + j][0], acc[i * NB8 + j][1], af[i], bf[j]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[st]);   // this warp's reads of the stage are done
+    }
+  }
+  __syncthreads();
+  // Sum over the consumer warps in fixed order through the (now idle) ring.
+  double* red = reinterpret_cast<double*>(smem_raw);   // [warp][NB8 * NB8][64]
+  if (warp < DM_WARPS) {
+    const int frow = lane >> 2, fcol = lane & 3;
+#pragma unroll
+    for (int e = 0; e < NB8 * NB8; e++) {
+      double* d = red + ((size_t)warp * (NB8 * NB8) + e) * 64 + frow * 8 + 2 * fcol;
+      d[0] = acc[e][0]; d[1] = acc[e][1];
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < NB8 * NB8 * 64; t += DM_THREADS) {
+    double v = 0.;
+#pragma unroll
+    for (int w = 0; w < DM_WARPS; w++) v += red[(size_t)w * (NB8 * NB8 * 64) + t];
+    partial[(size_t)blockIdx.x * (NB8 * NB8 * 64) + t] = v;
+  }
+}
+
+template <int T>
+size_t dmma_stage_bytes(int rows) { return sizeof(double) * (size_t)rows * (T + DM_PAD); }
+inline size_t dmma_fixed_bytes(int rows) {
+  return sizeof(unsigned long long) * 2 * DM_MAX_STAGES + sizeof(void*) * (size_t)rows;
+}
+
+template <int NB8, bool SAME, int T>
+int launch_gram_dmma(trvb_ctx* ctx, const double* const* A, const double* const* B, const double* G,
+                     const int* d_sel_a, int nab, const int* d_sel_b, int nbb, long long ncells,
+                     unsigned long long mask, double* d_partial, int nblocks) {
+  const int rows = 8 * nab + (SAME ? 0 : 8 * nbb) + 1;
+  const size_t stage = dmma_stage_bytes<T>(rows), fixed = dmma_fixed_bytes(rows);
+  int nstages = (int)std::min<size_t>(DM_MAX_STAGES, (DM_SMEM_LIMIT - fixed) / stage);
+  {
+    const char* env = getenv("TRV_GRAM_STAGES");
+    if (env && atoi(env) >= 2) nstages = std::min(nstages, atoi(env));
+  }
+  TRVB_REQUIRE(nstages >= 2, "gram (dmma): %d staged rows exceed shared memory", rows);
+  const size_t red = sizeof(double) * DM_WARPS * NB8 * NB8 * 64;
+  const size_t sm = std::max(stage * nstages + fixed, red);
+  TRVB_CUDA(cudaFuncSetAttribute(k_gram_dmma<NB8, SAME, T>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  const long long nt = (ncells + T - 1) / T;
+  const int nbk = (int)std::min<long long>(nt, (long long)nblocks);
+  if (nbk < nblocks) {   // partials are laid out for `nblocks` blocks
+    TRVB_CUDA(cudaMemsetAsync(d_partial, 0, sizeof(double) * NB8 * NB8 * 64 * (size_t)nblocks, ctx->stream));
+  }
+  k_gram_dmma<NB8, SAME, T><<<nbk, DM_THREADS, sm, ctx->stream>>>(
+    A, B, G, d_sel_a, nab, d_sel_b, nbb, ncells, mask, nstages, d_partial);
+  TRVB_LAUNCH_CHECK();
+  return 0;
+}
+
+// Tile length: the longest rows (cells per bulk copy) of which two stages fit -- long rows
+// feed the TMA engine better than a deeper ring of short ones (C5, 41 rows of 157 M cells:
+// T = 320 / 256 with 2 stages 11.6 / 11.8 ms, T = 192 with 3 stages 11.9 ms, T = 128 with
+// 2 / 3 / 6 stages 14.7 / 14.0 / 14.0 ms; profiles/r02_gram_dmma.txt).
+template <int NB8, bool SAME>
+int dispatch_gram_dmma_tile(trvb_ctx* ctx, const double* const* A, const double* const* B,
+                            const double* G, const int* d_sel_a, int nab, const int* d_sel_b,
+                            int nbb, long long ncells, unsigned long long mask, double* d_partial,
+                            int nblocks) {
+  const int rows = 8 * nab + (SAME ? 0 : 8 * nbb) + 1;
+  const char* env = getenv("TRV_GRAM_TILE");
+  const int want = env ? atoi(env) : 320;
+  auto fits = [&](size_t stage) { return 2 * stage + dmma_fixed_bytes(rows) <= DM_SMEM_LIMIT; };
+#define TRVB_DMMA_TILE(TT)                                                                      \
+  if (want >= TT && fits(dmma_stage_bytes<TT>(rows)))                                           \
+    return launch_gram_dmma<NB8, SAME, TT>(ctx, A, B, G, d_sel_a, nab, d_sel_b, nbb, ncells,    \
+                                           mask, d_partial, nblocks);
+  TRVB_DMMA_TILE(320)
+  TRVB_DMMA_TILE(256)
+  TRVB_DMMA_TILE(192)
+#undef TRVB_DMMA_TILE
+  return launch_gram_dmma<NB8, SAME, 128>(ctx, A, B, G, d_sel_a, nab, d_sel_b, nbb, ncells, mask,
+                                          d_partial, nblocks);
+}
+
+template <int NB8>
+int dispatch_gram_dmma(trvb_ctx* ctx, bool same, const double* const* A, const double* const* B,
+                       const double* G, const int* d_sel_a, int nab, const int* d_sel_b, int nbb,
+                       long long ncells, unsigned long long mask, double* d_partial, int nblocks) {
+  if (same) {
+    return dispatch_gram_dmma_tile<NB8, true>(ctx, A, B, G, d_sel_a, nab, d_sel_b, nbb, ncells,
+                                              mask, d_partial, nblocks);
+  }
+  if constexpr (NB8 <= DM_MAXB_PAIR) {
+    return dispatch_gram_dmma_tile<NB8, false>(ctx, A, B, G, d_sel_a, nab, d_sel_b, nbb, ncells,
+                                               mask, d_partial, nblocks);
+  } else {
+    trvb_set_error("gram (dmma): %d blocks per side with two lists", NB8);
+    return 2;
+  }
+}
+
+// All `npairs` sums over real fields: groups of up to 48 fields per side and launch.
+// d_A / d_B: device tables of field pointers; out: 2 * npairs doubles (imaginary parts 0).
+int run_gram_dmma(trvb_ctx* ctx, const double* const* d_A, const double* const* d_B,
+                  const double* G, int na_all, int nb_all, long long ncells, const int* ia,
+                  const int* ib, int npairs, double* out, bool b_is_a) {
+  const int nba = (na_all + 7) / 8, nbb_all = (nb_all + 7) / 8;
+  // pair -> 8 x 8 block; with one list on both sides C is symmetric: upper blocks only
+  std::vector<char> need((size_t)nba * nbb_all, 0);
+  for (int p = 0; p < npairs; p++) {
+    int a = ia[p] / 8, b = ib[p] / 8;
+    if (b_is_a && a > b) std::swap(a, b);
+    need[(size_t)a * nbb_all + b] = 1;
+  }
+  // one launch holds up to 48 fields when both sides are one list that fits, else groups
+  // of 32 fields per side
+  const int GB = (b_is_a && nba <= DM_MAXB) ? DM_MAXB : DM_MAXB_PAIR;
+  const int nga = (nba + GB - 1) / GB, ngb = (nbb_all + GB - 1) / GB;
+  struct Launch { int ga, gb, nab, nbb; bool same; unsigned long long mask; size_t res_off; int nb8; };
+  std::vector<Launch> launches;
+  size_t res_doubles = 0;
+  for (int ga = 0; ga < nga; ga++) {
+    for (int gb = 0; gb < ngb; gb++) {
+      Launch L; L.ga = ga; L.gb = gb;
+      L.nab = std::min(GB, nba - ga * GB);
+      L.nbb = std::min(GB, nbb_all - gb * GB);
+      L.same = b_is_a && ga == gb;
+      L.mask = 0;
+      for (int i = 0; i < L.nab; i++)
+        for (int j = 0; j < L.nbb; j++)
+          if (need[(size_t)(ga * GB + i) * nbb_all + gb * GB + j]) L.mask |= 1ull << (8 * i + j);
+      if (!L.mask) continue;
+      L.nb8 = std::max(L.nab, L.same ? L.nab : L.nbb);
+      L.res_off = res_doubles;
+      res_doubles += (size_t)L.nb8 * L.nb8 * 64;
+      launches.push_back(L);
+    }
+  }
+  const long long ntiles = (ncells + 127) / 128;
+  const int nblocks = (int)std::min<long long>(ntiles, (long long)ctx->num_sms);
+  const size_t sel_ints = 8 * (size_t)(nba + nbb_all);
+  const size_t bytes_tab = (sizeof(int) * sel_ints + 255) / 256 * 256;
+  const size_t bytes_partial = sizeof(double) * DM_MAXB * DM_MAXB * 64 * (size_t)nblocks;
+  double* scratch;
+  int st = trvb_scratch(ctx, bytes_tab + bytes_partial + sizeof(double) * res_doubles + 512, &scratch);
+  if (st) return st;
+  int* d_tab = (int*)scratch;
+  double* d_partial = (double*)((char*)scratch + bytes_tab);
+  double* d_res = d_partial + bytes_partial / sizeof(double);
+  std::vector<int> h_tab(sel_ints);
+  for (int r = 0; r < 8 * nba; r++) h_tab[r] = std::min(r, na_all - 1);
+  for (int r = 0; r < 8 * nbb_all; r++) h_tab[8 * nba + r] = std::min(r, nb_all - 1);
+  TRVB_CUDA(cudaMemcpyAsync(d_tab, h_tab.data(), sizeof(int) * h_tab.size(), cudaMemcpyHostToDevice,
+                            ctx->stream));
+  for (const Launch& L : launches) {
+    const int* sa = d_tab + 8 * L.ga * GB;
+    const int* sb = d_tab + 8 * nba + 8 * L.gb * GB;
+#define TRVB_DMMA_CASE(N) case N: st = dispatch_gram_dmma<N>(ctx, L.same, d_A, d_B, G, sa, L.nab, sb, \
+                                       L.nbb, ncells, L.mask, d_partial, nblocks); break;
+    switch (L.nb8) {
+      TRVB_DMMA_CASE(1) TRVB_DMMA_CASE(2) TRVB_DMMA_CASE(3)
+      TRVB_DMMA_CASE(4) TRVB_DMMA_CASE(5) TRVB_DMMA_CASE(6)
+      default: st = 2;
+    }
+#undef TRVB_DMMA_CASE
+    if (st) return st;
+    const int width = L.nb8 * L.nb8 * 64;
+    k_sum_cols<<<div_up(width, 128), 128, 0, ctx->stream>>>(d_partial, nblocks, width, d_res + L.res_off);
+    TRVB_LAUNCH_CHECK();
+  }
+  std::vector<double> h_res(res_doubles);
+  TRVB_CUDA(cudaMemcpyAsync(h_res.data(), d_res, sizeof(double) * res_doubles, cudaMemcpyDeviceToHost,
+                            ctx->stream));
+  TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<int> launch_of((size_t)nga * ngb, -1);
+  for (size_t t = 0; t < launches.size(); t++) launch_of[(size_t)launches[t].ga * ngb + launches[t].gb] = (int)t;
+  for (int p = 0; p < npairs; p++) {
+    int a = ia[p], b = ib[p];
+    if (b_is_a && a / 8 > b / 8) std::swap(a, b);
+    const Launch& L = launches[launch_of[(size_t)(a / 8 / GB) * ngb + b / 8 / GB]];
+    const int i = a / 8 - L.ga * GB, j = b / 8 - L.gb * GB;
+    out[2 * p] = h_res[L.res_off + ((size_t)(i * L.nb8 + j) * 64) + (a % 8) * 8 + b % 8];
+    out[2 * p + 1] = 0.;
+  }
+  return 0;
+}
+
+}  // namespace
+
+// =====================================================================
 // C ABI
 // =====================================================================
 
@@ -1096,7 +1411,12 @@ extern "C" int trvb_gram_reduce(trvb_ctx* ctx, const void* const* A, int na,
     ld.A = (const double* const*)d_tab;
     ld.B = (const double* const*)(d_tab + na);
     ld.G = (const double*)G.data;
-    st = run_gram(ctx, ld, na, nb, ctx->g.nmesh, ia, ib, npairs, out, b_is_a);
+    const char* env_dmma = getenv("TRV_GRAM_NO_DMMA");
+    if (aligned && !(env_dmma && env_dmma[0] == '1')) {
+      st = run_gram_dmma(ctx, ld.A, ld.B, ld.G, na, nb, ctx->g.nmesh, ia, ib, npairs, out, b_is_a);
+    } else {
+      st = run_gram(ctx, ld, na, nb, ctx->g.nmesh, ia, ib, npairs, out, b_is_a);
+    }
   } else {
     FieldLoader ld;
     ld.aligned16 = aligned;

@@ -40,7 +40,7 @@ namespace {
 typedef std::tuple<int, int, int, int, double, double, double, int> CtxKey;   // device first
 std::mutex g_ctx_mutex;
 std::map<CtxKey, std::weak_ptr<trvb_ctx> > g_ctx_cache;
-std::vector<std::shared_ptr<trvb_ctx> > g_ctx_recent;
+std::map<int, std::vector<std::shared_ptr<trvb_ctx> > > g_ctx_recent;   // per device
 trvb_ctx* g_last_ctx = nullptr;
 
 }  // namespace
@@ -97,9 +97,11 @@ std::shared_ptr<trvb_ctx> acquire_context(const trv::ParameterSet& params) {
   g_ctx_cache[key] = sp;
   // Keep the most recent contexts alive between estimator calls so that cuFFT
   // plans, correction tables and the sort scratch are built once per grid
-  // (the counterpart of the reference's FFTW wisdom, S/field.cpp:90-169).
-  g_ctx_recent.push_back(sp);
-  if (g_ctx_recent.size() > 4) g_ctx_recent.erase(g_ctx_recent.begin());
+  // (the counterpart of the reference's FFTW wisdom, S/field.cpp:90-169).  Four per
+  // device: in single-process multi-GPU mode every device holds its own.
+  std::vector<std::shared_ptr<trvb_ctx> >& recent = g_ctx_recent[device];
+  recent.push_back(sp);
+  if (recent.size() > 4) recent.erase(recent.begin());
   g_last_ctx = raw;
   return sp;
 }

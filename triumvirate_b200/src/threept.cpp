@@ -834,6 +834,14 @@ trv::BispecMeasurements bispec_impl(
     dev::check(trvb_subgrid_create(c, &slab_ctx, dims), "trvb_subgrid_create (slab)");
   }
   trvb_ctx* pair_grid = slab_ctx ? slab_ctx : sub;
+  // Real shell fields on a true sub-grid take the pruned per-axis transform (throughput
+  // mode; the deterministic mode keeps the dense batched 3-D transform, whose arithmetic
+  // per shell does not depend on how the shells are grouped).  TRV_NO_PRUNE=1: dense.
+  bool pruned = coarse && !params.deterministic;
+  {
+    const char* env = std::getenv("TRV_NO_PRUNE");
+    if (env != nullptr && env[0] == '1') pruned = false;
+  }
   dev::Mesh xi;             // shot-noise mesh, reused across terms in a box
   dev::Mesh G;              // G_LM(x) on the sub-grid
   int G_M = 0; bool have_G = false, have_xi = false;
@@ -854,6 +862,11 @@ trv::BispecMeasurements bispec_impl(
     if (slab_ctx) {
       dev::check(trvb_shell_slab_batch(c, sub, src.view(), ell, m, klo.data(), khi.data(),
                                        amp.data(), (int)bins.size(), slab_x0, slab_nx, dst.data()),
+                 "trvb_shell_slab_batch");
+    } else if (pruned && layout == TRVB_REAL) {
+      // one GPU: the same pruned per-axis transform over all the planes
+      dev::check(trvb_shell_slab_batch(c, sub, src.view(), ell, m, klo.data(), khi.data(),
+                                       amp.data(), (int)bins.size(), 0, nsub[0], dst.data()),
                  "trvb_shell_slab_batch");
     } else {
       dev::check(trvb_shell_ifft_batch(c, sub, src.view(), ell, m, klo.data(), khi.data(),
