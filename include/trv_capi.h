@@ -153,6 +153,8 @@ int trv_allreduce(double* buf, long long n);
 void trv_comm_finalize(void);
 /* GPUs a single-process estimator call on this mesh would spread over. */
 int trv_multi_device_count(const int* ngrid);
+/* Estimator calls of this process that ran the distributed mesh phase (trvb_dmesh_*). */
+long long trv_dmesh_call_count(void);
 
 /* cudaStream_t of the most recently used estimator context (NULL before the
  * first call). */

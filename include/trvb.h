@@ -127,6 +127,9 @@ int trvb_cat_create(trvb_ctx* ctx, trvb_cat** cat, long long n,
                     const double* w, const double* los, int src_on_device);
 /* Same from the reference's AoS layout: 7 doubles per particle
  * {x, y, z, nz, ws, wc, w} (I/particles.hpp:63-69). */
+/* Device arrays of the positions held by a catalogue (valid until it is destroyed). */
+int trvb_cat_positions(const trvb_cat* cat, const double** x, const double** y,
+                       const double** z);
 int trvb_cat_create_aos(trvb_ctx* ctx, trvb_cat** cat, long long n,
                         const double* pdata, const double* los);
 /* Periodic-box fast path for HOST coordinate arrays (pinned memory preferred): the
@@ -350,6 +353,54 @@ int trvb_allreduce(trvb_ctx* ctx, trvb_comm* comm, double* host_buf, long long n
 int trvb_allreduce_device(trvb_ctx* ctx, trvb_comm* comm, double* dev_buf, long long n);
 /* Device of a context. */
 int trvb_ctx_device(const trvb_ctx* ctx);
+/* Exchanges on the context's stream (device buffers, no host synchronisation):
+ *   trvb_comm_alltoall        block q (`n` doubles) of `send` goes to rank q, block q of
+ *                             `recv` comes from rank q (grouped ncclSend/ncclRecv)
+ *   trvb_comm_bcast_segments  segment s of `buf` (offset[s], count[s] doubles) is sent by
+ *                             rank root[s] to all others (grouped ncclBroadcast) */
+int trvb_comm_alltoall(trvb_ctx* ctx, trvb_comm* comm, const double* send, double* recv,
+                       long long n);
+int trvb_comm_bcast_segments(trvb_ctx* ctx, trvb_comm* comm, double* buf, int nseg,
+                             const int* root, const long long* offset, const long long* count);
+
+/* ---- distributed mesh phase of the periodic-box estimators ------------------
+ * The part of a box estimator call that a replicated grid cannot shrink -- particle
+ * assignment (S/field.cpp:987-1112) and the two full-grid FFTs (S/field.cpp:1496-1720) --
+ * spread over the ranks of a communicator: x-slabs of the configuration-space mesh,
+ * k_y-slabs of the Fourier-space mesh, one all-to-all per transform.  The counterpart of
+ * the reference's cuFFT-Xt mode (S/field.cpp:212-235), across processes.  Needs
+ * n0 % R == 0 and n1 % R == 0 (trvb_dmesh_supported).  All calls below except
+ * _supported, _planes and _forget_lowk are collective over the communicator.
+ *   trvb_dmesh_density      delta n(k) of n unit-weight particles (device arrays holding
+ *                           the whole catalogue on every rank); k0_add is added at k = 0
+ *   trvb_dmesh_gather_lowk  the modes the grid of `sub` represents -> HALF mesh `dst` of
+ *                           sub's extents on every rank; from then on a trvb_mesh at that
+ *                           address is read as a spectrum of the BIG grid by every function
+ *                           that takes a Fourier-space source (shell transforms, binned
+ *                           two-point statistics), until _forget_lowk
+ *   trvb_dmesh_shot_xi      xi(r) of trvb_shot_xi on this rank's planes
+ *                           (REAL, [nx][n1][n2]) for fa = dn + add_a delta_k0,
+ *                           fb = dn + add_b delta_k0
+ *   trvb_shot_bispec_reduce_slab  trvb_shot_bispec_reduce from those planes: the radial
+ *                           histogram is summed over the ranks, every rank gets all pairs */
+typedef struct trvb_dmesh trvb_dmesh;
+int trvb_dmesh_supported(const trvb_ctx* ctx, int nranks);
+long long trvb_dmesh_call_count(void);   /* trvb_dmesh_density calls of this process */
+int trvb_dmesh_create(trvb_ctx* ctx, trvb_comm* comm, trvb_dmesh** out);
+/* The context's own distributed-mesh state for `comm` (plans and the assignment window are
+ * built once per context; destroyed with it). */
+int trvb_dmesh_get(trvb_ctx* ctx, trvb_comm* comm, trvb_dmesh** out);
+void trvb_dmesh_destroy(trvb_dmesh* dm);
+int trvb_dmesh_planes(const trvb_dmesh* dm, int* x0, int* nx);
+int trvb_dmesh_density(trvb_dmesh* dm, long long n, const double* x, const double* y,
+                       const double* z, double k0_add);
+int trvb_dmesh_gather_lowk(trvb_dmesh* dm, trvb_ctx* sub, trvb_mesh dst);
+void trvb_dmesh_forget_lowk(trvb_dmesh* dm);
+int trvb_dmesh_shot_xi(trvb_dmesh* dm, double add_a, double add_b, const double S[2],
+                       double* xi_planes);
+int trvb_shot_bispec_reduce_slab(trvb_ctx* ctx, const double* xi_planes, int x0, int nx,
+                                 trvb_comm* comm, int la, int ma, int lb, int mb,
+                                 const double* ka, const double* kb, int npairs, double* out);
 
 #ifdef __cplusplus
 }

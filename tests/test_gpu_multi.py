@@ -95,6 +95,72 @@ def test_two_processes_nccl_allreduce_inside_the_call(core):
         assert np.array_equal(nm, full["nmodes_1"])
 
 
+def _dist_case():
+    gen = np.random.default_rng(2718)
+    L, ng = 1000., 128
+    pos = gen.uniform(0., L, size=(3, 300000))
+    pos[0, :20000] = gen.uniform(0., 3. * L / ng, size=20000)      # crowd the slab boundaries
+    pos[0, 20000:40000] = gen.uniform(L / 2 - 8., L / 2 + 8., size=20000)
+    kw = dict(boxsize=L, ngrid=ng, assignment="pcs", degrees=(0, 0, 0), form="full",
+              bin_range=(0.01, 0.1), num_bins=9, norm_factor=1.)
+    return pos, kw
+
+
+def _dist_worker(rank, world, port, q):
+    os.environ["TRV_GPU_DEVICE"] = str(rank)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, str(ROOT))
+    import torch.distributed as dist
+    from triumvirate_b200 import core, dist as tdist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        assert tdist.init_comm() == world
+        pos, kw = _dist_case()
+        res = {}
+        for assignment in ("pcs", "tsc", "cic"):
+            for flag in ("1", "0"):
+                os.environ["TRV_NO_DIST_MESH"] = flag
+                before = core.dmesh_call_count()
+                out = tdist.threept("bispec", "sim", pos_d=pos, **dict(kw, assignment=assignment))
+                assert core.dmesh_call_count() - before == (1 if flag == "0" else 0)
+                res[(assignment, flag)] = (out["bk_raw"], out["bk_shot"])
+        q.put((rank, res))
+        core.comm_finalize()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_processes_distributed_mesh_phase(core):
+    """NCCL communicator attached, grid extents that split over the ranks: assignment and the
+    full-grid transforms run on x-slabs / k_y-slabs (trvb_dmesh_*: windowed assignment, 2-D
+    transforms, all-to-all, 1-D transform; low-|k| modes gathered; xi(r) by the inverse
+    route with the radial histogram summed over the ranks).  Every rank returns the complete
+    data vector, equal to the one-GPU result and to the replicated-mesh run to round-off."""
+    if core.gpu_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    pos, kw = _dist_case()
+    full = {a: core.threept("bispec", "sim", pos_d=pos, **dict(kw, assignment=a))
+            for a in ("pcs", "tsc", "cic")}
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dist_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=500) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, out in res:
+        for (assignment, flag), (raw, shot) in out.items():
+            ref = full[assignment]
+            for got, want in ((raw, ref["bk_raw"]), (shot, ref["bk_shot"])):
+                err = np.max(np.abs(got - want)) / np.max(np.abs(want))
+                assert err < 1.e-11, (rank, assignment, flag, err)
+
+
 def test_single_process_spreads_over_the_visible_gpus(core, monkeypatch):
     """No environment pin, several GPUs: trv::compute_* deals the entries to one host
     thread per GPU and sums the shares on the host -- same bits as one GPU."""

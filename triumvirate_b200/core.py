@@ -354,6 +354,13 @@ def multi_device_count(ngrid):
     return _trv().trv_multi_device_count(ngrid.ctypes.data_as(_ip))
 
 
+def dmesh_call_count():
+    """Estimator calls of this process that ran the distributed mesh phase."""
+    fn = _trv().trv_dmesh_call_count
+    fn.restype = C.c_longlong
+    return int(fn())
+
+
 def release_contexts():
     """Drop the cached device contexts (cuFFT plans, tables) and hand the arena's
     cached blocks back to the driver."""

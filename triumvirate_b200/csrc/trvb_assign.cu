@@ -2044,6 +2044,13 @@ extern "C" void trvb_cat_invalidate_sort(trvb_cat* cat) {
 
 extern "C" long long trvb_cat_size(const trvb_cat* cat) { return cat ? cat->n : 0; }
 
+extern "C" int trvb_cat_positions(const trvb_cat* cat, const double** x, const double** y,
+                                  const double** z) {
+  TRVB_REQUIRE(cat && x && y && z, "trvb_cat_positions: null argument");
+  *x = cat->x; *y = cat->y; *z = cat->z;
+  return 0;
+}
+
 extern "C" int trvb_cat_sum(trvb_ctx* ctx, trvb_cat* cat, int kind, int L, int M,
                             double out[2]) {
   TRVB_REQUIRE(ctx && cat && out, "trvb_cat_sum: null argument");

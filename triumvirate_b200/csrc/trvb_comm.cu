@@ -34,6 +34,9 @@ struct NcclApi {
   ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -72,12 +75,16 @@ int load_nccl() {
   api.CommInitAll = (decltype(api.CommInitAll))dlsym(h, "ncclCommInitAll");
   api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
   api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
+  api.Send = (decltype(api.Send))dlsym(h, "ncclSend");
+  api.Recv = (decltype(api.Recv))dlsym(h, "ncclRecv");
+  api.Broadcast = (decltype(api.Broadcast))dlsym(h, "ncclBroadcast");
   api.GroupStart = (decltype(api.GroupStart))dlsym(h, "ncclGroupStart");
   api.GroupEnd = (decltype(api.GroupEnd))dlsym(h, "ncclGroupEnd");
   api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
   api.GetVersion = (decltype(api.GetVersion))dlsym(h, "ncclGetVersion");
   if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce
-      || !api.GroupStart || !api.GroupEnd || !api.GetErrorString) {
+      || !api.GroupStart || !api.GroupEnd || !api.GetErrorString || !api.Send || !api.Recv
+      || !api.Broadcast) {
     trvb_set_error("libnccl.so.2 lacks an expected symbol");
     dlclose(h);
     return 4;
@@ -193,5 +200,58 @@ extern "C" int trvb_allreduce(trvb_ctx* ctx, trvb_comm* c, double* buf, long lon
   TRVB_CUDA(cudaMemcpyAsync(buf, c->d_buf, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost,
                             ctx->stream));
   TRVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// Personalised exchange on the context's stream (no host synchronisation): block q of
+// `send` (`n` doubles each) goes to rank q, block q of `recv` comes from rank q.  The one
+// data-path exchange of the distributed mesh phase (x-slab <-> k_y-slab transposition of
+// the 3-D FFT); over NVSwitch every pair of GPUs has its own full-bandwidth path.
+extern "C" int trvb_comm_alltoall(trvb_ctx* ctx, trvb_comm* c, const double* send, double* recv,
+                                  long long n) {
+  TRVB_REQUIRE(ctx && c && send && recv && n >= 0, "trvb_comm_alltoall: bad argument");
+  TRVB_REQUIRE(ctx->device == c->device, "trvb_comm_alltoall: context on device %d, "
+               "communicator on device %d", ctx->device, c->device);
+  if (n == 0) return 0;
+  TRVB_CUDA(cudaSetDevice(ctx->device));
+  TRVB_NCCL(g_nccl.GroupStart());
+  for (int q = 0; q < c->nranks; q++) {
+    ncclResult_t r1 = g_nccl.Send(send + (size_t)q * n, (size_t)n, ncclFloat64, q, c->comm, ctx->stream);
+    ncclResult_t r2 = g_nccl.Recv(recv + (size_t)q * n, (size_t)n, ncclFloat64, q, c->comm, ctx->stream);
+    if (r1 != ncclSuccess || r2 != ncclSuccess) {
+      g_nccl.GroupEnd();
+      trvb_set_error("trvb_comm_alltoall: ncclSend/ncclRecv with rank %d -> %s", q,
+                     g_nccl.GetErrorString(r1 != ncclSuccess ? r1 : r2));
+      return 2000 + (int)(r1 != ncclSuccess ? r1 : r2);
+    }
+  }
+  TRVB_NCCL(g_nccl.GroupEnd());
+  return 0;
+}
+
+// `nseg` broadcasts in one group on the context's stream: segment s of the device buffer
+// `buf` (offset[s], count[s] doubles) is sent by rank root[s] and received by all others.
+extern "C" int trvb_comm_bcast_segments(trvb_ctx* ctx, trvb_comm* c, double* buf, int nseg,
+                                        const int* root, const long long* offset,
+                                        const long long* count) {
+  TRVB_REQUIRE(ctx && c && buf && nseg >= 0 && (nseg == 0 || (root && offset && count)),
+               "trvb_comm_bcast_segments: bad argument");
+  TRVB_REQUIRE(ctx->device == c->device, "trvb_comm_bcast_segments: context on device %d, "
+               "communicator on device %d", ctx->device, c->device);
+  if (nseg == 0) return 0;
+  TRVB_CUDA(cudaSetDevice(ctx->device));
+  TRVB_NCCL(g_nccl.GroupStart());
+  for (int s = 0; s < nseg; s++) {
+    if (count[s] <= 0) continue;
+    ncclResult_t r = g_nccl.Broadcast(buf + offset[s], buf + offset[s], (size_t)count[s],
+                                      ncclFloat64, root[s], c->comm, ctx->stream);
+    if (r != ncclSuccess) {
+      g_nccl.GroupEnd();
+      trvb_set_error("trvb_comm_bcast_segments: ncclBroadcast(root %d) -> %s", root[s],
+                     g_nccl.GetErrorString(r));
+      return 2000 + (int)r;
+    }
+  }
+  TRVB_NCCL(g_nccl.GroupEnd());
   return 0;
 }

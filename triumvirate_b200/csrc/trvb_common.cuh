@@ -114,7 +114,14 @@ struct trvb_ctx {
   size_t scratch_bytes = 0;
   int num_sms = 148;
   int deterministic = 0;   // 1: reductions avoid atomics (bit-reproducible)
+  bool borrowed_stream = false;   // root context that runs on another context's stream
+  // Low-|k| storage registered by the distributed mesh phase (root contexts): a HALF mesh at
+  // this address holds the modes of this grid on the extents lowk_dims (KView::p0).
+  const void* lowk_ptr = nullptr;
+  int lowk_dims[3] = {0, 0, 0};
+  struct trvb_dmesh* dmesh = nullptr;   // trvb_dmesh_get: owned by the context
 };
+
 
 struct trvb_cat {
   trvb_ctx* owner = nullptr;   // context that owns the allocations (device)
@@ -210,9 +217,27 @@ __device__ __forceinline__ double vec3_norm_exact(double a, double b, double c) 
 struct KView {
   const double2* p;
   int layout;
-  int n0, n1, n2, nh;
+  int n0, n1, n2, nh;   // extents of the STORED array
   double add0;   // trvb_mesh::k0_add
+  // Low-|k| storage (multi-GPU runs with a distributed mesh): the array holds, in HALF
+  // layout on the extents above, only the modes of a (p0, p1, p2) grid that lie strictly
+  // inside the stored extents' Nyquist frequencies; callers keep indexing by the big grid.
+  int p0 = 0, p1 = 0, p2 = 0;   // 0: the stored array IS the grid
 };
+
+// Kernel-side view of a Fourier-space mesh of `ctx`'s grid.
+inline KView kview_of(const trvb_ctx* ctx, trvb_mesh m) {
+  KView v;
+  v.p = (const double2*)m.data; v.layout = m.layout;
+  v.n0 = ctx->g.n[0]; v.n1 = ctx->g.n[1]; v.n2 = ctx->g.n[2]; v.nh = ctx->g.nh;
+  v.add0 = m.k0_add;
+  if (m.data != nullptr && m.data == ctx->lowk_ptr && m.layout == TRVB_HALF) {
+    v.p0 = v.n0; v.p1 = v.n1; v.p2 = v.n2;
+    v.n0 = ctx->lowk_dims[0]; v.n1 = ctx->lowk_dims[1]; v.n2 = ctx->lowk_dims[2];
+    v.nh = v.n2 / 2 + 1;
+  }
+  return v;
+}
 
 // Configuration-space mesh read as complex values (REAL meshes have Im = 0).
 struct XView {
@@ -229,6 +254,20 @@ __device__ __forceinline__ cplx kload(const KView& v, int i, int j, int k) {
   if ((i | j | k) == 0) {
     double2 t = v.p[0];
     r.re = t.x + v.add0; r.im = t.y;
+    return r;
+  }
+  if (v.p0) {
+    // (i, j, k) index the big grid; the array holds its low-|k| modes only.
+    int mi = (i < v.p0 / 2) ? i : i - v.p0;
+    int mj = (j < v.p1 / 2) ? j : j - v.p1;
+    int mk = (k < v.p2 / 2) ? k : k - v.p2;
+    r.re = 0.; r.im = 0.;
+    if (2 * abs(mi) >= v.n0 || 2 * abs(mj) >= v.n1 || 2 * abs(mk) >= v.n2) return r;
+    const bool conj = mk < 0;
+    if (conj) { mi = -mi; mj = -mj; mk = -mk; }
+    const int is = mi >= 0 ? mi : mi + v.n0, js = mj >= 0 ? mj : mj + v.n1;
+    double2 t = v.p[((long long)is * v.n1 + js) * v.nh + mk];
+    r.re = t.x; r.im = conj ? -t.y : t.y;
     return r;
   }
   if (v.layout == TRVB_COMPLEX) {

@@ -312,6 +312,7 @@ extern "C" void trvb_ctx_destroy(trvb_ctx* ctx) {
 static void destroy_ctx_now(trvb_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->dmesh) { trvb_dmesh_destroy(ctx->dmesh); ctx->dmesh = nullptr; }
   if (ctx->has_z2z) cufftDestroy(ctx->plan_z2z);
   if (ctx->has_d2z) cufftDestroy(ctx->plan_d2z);
   if (ctx->has_z2d) cufftDestroy(ctx->plan_z2d);
@@ -327,7 +328,7 @@ static void destroy_ctx_now(trvb_ctx* ctx) {
     if (kv.second.d_c) cudaFree(kv.second.d_c);
   }
   if (ctx->d_scratch) trvb_arena_free(ctx->device, ctx->stream, ctx->d_scratch);
-  if ((!ctx->parent || ctx->own_stream) && ctx->stream) {
+  if ((!ctx->parent || ctx->own_stream) && ctx->stream && !ctx->borrowed_stream) {
     trvb_arena_retire_stream(ctx->device, ctx->stream);
     cudaStreamDestroy(ctx->stream);
     if (ctx->own_stream) cudaEventDestroy(ctx->fork_event);

@@ -287,13 +287,6 @@ Tables tables_of(const trvb_ctx* ctx) {
   return t;
 }
 
-KView kview_of(const trvb_ctx* ctx, trvb_mesh m) {
-  KView v;
-  v.p = (const double2*)m.data; v.layout = m.layout;
-  v.n0 = ctx->g.n[0]; v.n1 = ctx->g.n[1]; v.n2 = ctx->g.n[2]; v.nh = ctx->g.nh;
-  v.add0 = m.k0_add;
-  return v;
-}
 
 inline int grid_for(const trvb_ctx* ctx, long long n, int threads) {
   return (int)std::min<long long>(div_up(n, threads), (long long)ctx->num_sms * 32);

@@ -34,13 +34,6 @@ Tables tables_of(const trvb_ctx* ctx) {
   return t;
 }
 
-KView kview_of(const trvb_ctx* ctx, trvb_mesh m) {
-  KView v;
-  v.p = (const double2*)m.data; v.layout = m.layout;
-  v.n0 = ctx->g.n[0]; v.n1 = ctx->g.n[1]; v.n2 = ctx->g.n[2]; v.nh = ctx->g.nh;
-  v.add0 = m.k0_add;
-  return v;
-}
 
 __global__ void k_sum_cols(const double* __restrict__ partial, int nblocks, int width,
                            double* __restrict__ out) {
@@ -216,6 +209,38 @@ k_shot_radial_hist(XView xi, GridDesc g, int la, int ma, int lb,
     const long long q = (long long)si * si + (long long)sj * sj + (long long)sk * sk;
     atomicAdd(&hist[2 * q], re);
     if (xi.cplx || !TRIVIAL) atomicAdd(&hist[2 * q + 1], im);
+  });
+}
+
+// The same histogram from the planes [x0, x0 + nx) of xi held by one rank of a distributed
+// mesh (REAL, [nx][n1][n2]); the four cells (+-j, +-k) of a plane share q.
+template <bool TRIVIAL>
+__global__ void __launch_bounds__(256)
+k_shot_radial_hist_slab(const double* __restrict__ xi, GridDesc g, int x0, int nx, int la, int ma,
+                        int lb, int mb, double* __restrict__ hist) {
+  const int n0 = g.n[0], n1 = g.n[1], n2 = g.n[2];
+  const YlmCoef ya_c = ylm_coef(la, ma), yb_c = ylm_coef(lb, mb);
+  for_each_cell(nx, n1 / 2 + 1, n2 / 2 + 1, [&](int xl, int cj, int ck, long long) {
+    const int pj = cj ? n1 - cj : 0, pk = ck ? n2 - ck : 0;
+    const int jj[2] = {cj, pj}, kk[2] = {ck, pk};
+    const int si = signed_index(x0 + xl, n0);
+    double re = 0., im = 0.;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const int b = e >> 1, c = e & 1;
+      if ((b && pj == cj) || (c && pk == ck)) continue;   // the same cell
+      const double v = xi[((long long)xl * n1 + jj[b]) * n2 + kk[c]];
+      if (TRIVIAL) { re += v; continue; }
+      const double rx = (double)si * g.dr[0];
+      const double ry = (double)signed_index(jj[b], n1) * g.dr[1];
+      const double rz = (double)signed_index(kk[c], n2) * g.dr[2];
+      const cplx yy = cmul(ylm_eval(ya_c, rx, ry, rz), ylm_eval(yb_c, rx, ry, rz));
+      re += v * yy.re; im += v * yy.im;
+    }
+    const int sj = signed_index(cj, n1), sk = signed_index(ck, n2);
+    const long long q = (long long)si * si + (long long)sj * sj + (long long)sk * sk;
+    atomicAdd(&hist[2 * q], re);
+    if (!TRIVIAL) atomicAdd(&hist[2 * q + 1], im);
   });
 }
 
@@ -1430,9 +1455,34 @@ extern "C" int trvb_gram_reduce(trvb_ctx* ctx, const void* const* A, int na,
   return st;
 }
 
+namespace {
+int shot_bispec_reduce_impl(trvb_ctx* ctx, trvb_mesh xi, int slab_x0, int slab_nx,
+                            trvb_comm* comm, int la, int ma, int lb, int mb, const double* ka,
+                            const double* kb, int npairs, double* out);
+}
+
 extern "C" int trvb_shot_bispec_reduce(trvb_ctx* ctx, trvb_mesh xi, int la, int ma,
                                        int lb, int mb, const double* ka, const double* kb,
                                        int npairs, double* out) {
+  return shot_bispec_reduce_impl(ctx, xi, 0, 0, nullptr, la, ma, lb, mb, ka, kb, npairs, out);
+}
+
+extern "C" int trvb_shot_bispec_reduce_slab(trvb_ctx* ctx, const double* xi_planes, int x0, int nx,
+                                            trvb_comm* comm, int la, int ma, int lb, int mb,
+                                            const double* ka, const double* kb, int npairs,
+                                            double* out) {
+  TRVB_REQUIRE(ctx && comm && xi_planes && nx > 0 && x0 >= 0 && x0 + nx <= ctx->g.n[0],
+               "trvb_shot_bispec_reduce_slab: bad argument");
+  trvb_mesh xi; xi.data = const_cast<double*>(xi_planes); xi.layout = TRVB_REAL; xi.k0_add = 0.;
+  return shot_bispec_reduce_impl(ctx, xi, x0, nx, comm, la, ma, lb, mb, ka, kb, npairs, out);
+}
+
+namespace {
+// slab_nx > 0: `xi` holds the planes [slab_x0, slab_x0 + slab_nx) only (REAL) and the radial
+// histogram is summed over the ranks of `comm` before the pair reduction.
+int shot_bispec_reduce_impl(trvb_ctx* ctx, trvb_mesh xi, int slab_x0, int slab_nx,
+                            trvb_comm* comm, int la, int ma, int lb, int mb, const double* ka,
+                            const double* kb, int npairs, double* out) {
   TRVB_REQUIRE(ctx && xi.data && ka && kb && out && npairs > 0,
                "trvb_shot_bispec_reduce: bad argument");
   TRVB_REQUIRE(xi.layout == TRVB_COMPLEX || xi.layout == TRVB_REAL,
@@ -1467,6 +1517,8 @@ extern "C" int trvb_shot_bispec_reduce(trvb_ctx* ctx, trvb_mesh xi, int la, int 
   const char* env_direct = getenv("TRV_SHOT_DIRECT");
   const bool cubic = g.dr[0] == g.dr[1] && g.dr[1] == g.dr[2];
   const bool radial = cubic && !ctx->deterministic && !(env_direct && env_direct[0] == '1');
+  TRVB_REQUIRE(slab_nx == 0 || radial, "trvb_shot_bispec_reduce_slab: needs cubic cells and the "
+               "throughput mode (radial histogram)");
   int st;
   if (radial) {
     long long nq = 1;
@@ -1477,13 +1529,27 @@ extern "C" int trvb_shot_bispec_reduce(trvb_ctx* ctx, trvb_mesh xi, int la, int 
     double* d_hist = nullptr;
     TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&d_hist, 2 * sizeof(double) * (size_t)nq));
     TRVB_CUDA(cudaMemsetAsync(d_hist, 0, 2 * sizeof(double) * (size_t)nq, ctx->stream));
-    const RowLaunch rl = row_launch(ctx->num_sms, g.n[0] / 2 + 1, g.n[1] / 2 + 1, g.n[2] / 2 + 1);
-    if (la == 0 && lb == 0) {
-      k_shot_radial_hist<true><<<rl.grid, rl.block, 0, ctx->stream>>>(xv, g, la, ma, lb, mb, d_hist);
+    if (slab_nx > 0) {
+      const RowLaunch rl = row_launch(ctx->num_sms, slab_nx, g.n[1] / 2 + 1, g.n[2] / 2 + 1);
+      if (la == 0 && lb == 0) {
+        k_shot_radial_hist_slab<true><<<rl.grid, rl.block, 0, ctx->stream>>>(
+          xv.p, g, slab_x0, slab_nx, la, ma, lb, mb, d_hist);
+      } else {
+        k_shot_radial_hist_slab<false><<<rl.grid, rl.block, 0, ctx->stream>>>(
+          xv.p, g, slab_x0, slab_nx, la, ma, lb, mb, d_hist);
+      }
+      TRVB_LAUNCH_CHECK();
+      st = trvb_allreduce_device(ctx, comm, d_hist, 2 * nq);
+      if (st) return st;
     } else {
-      k_shot_radial_hist<false><<<rl.grid, rl.block, 0, ctx->stream>>>(xv, g, la, ma, lb, mb, d_hist);
+      const RowLaunch rl = row_launch(ctx->num_sms, g.n[0] / 2 + 1, g.n[1] / 2 + 1, g.n[2] / 2 + 1);
+      if (la == 0 && lb == 0) {
+        k_shot_radial_hist<true><<<rl.grid, rl.block, 0, ctx->stream>>>(xv, g, la, ma, lb, mb, d_hist);
+      } else {
+        k_shot_radial_hist<false><<<rl.grid, rl.block, 0, ctx->stream>>>(xv, g, la, ma, lb, mb, d_hist);
+      }
+      TRVB_LAUNCH_CHECK();
     }
-    TRVB_LAUNCH_CHECK();
     RadialLoader ld;
     ld.hist = (const double2*)d_hist; ld.dr = g.dr[0];
     ld.sja = sja; ld.sjb = sjb; ld.ka = d_k; ld.kb = d_k + ua.size();
@@ -1502,6 +1568,7 @@ extern "C" int trvb_shot_bispec_reduce(trvb_ctx* ctx, trvb_mesh xi, int la, int 
   for (int p = 0; p < 2 * npairs; p++) out[p] *= ctx->g.vol_cell;   // S/field.cpp:3393
   return 0;
 }
+}  // namespace
 
 extern "C" int trvb_shell_stats(trvb_ctx* ctx, const double* edges, int nbins, int fine,
                                 long long* nmodes, double* ksum) {

@@ -354,6 +354,8 @@ int trv_allreduce(double* buf, long long n) {
 
 void trv_comm_finalize(void) { trv::dev::comm_finalize(); }
 
+long long trv_dmesh_call_count(void) { return trvb_dmesh_call_count(); }
+
 int trv_multi_device_count(const int* ngrid) {
   trv::ParameterSet p;
   for (int ax = 0; ax < 3; ax++) { p.boxsize[ax] = 1.; p.ngrid[ax] = ngrid[ax]; }

@@ -316,6 +316,7 @@ class Engine {
   double vol_cell() const { return vol_cell_; }
   bool survey() const { return survey_; }
   bool window() const { return window_; }
+  long long ndata() const { return ndata_; }
 
   /// Fourier transform of the (L, M)-weighted number-density fluctuation,
   /// delta n_LM(k), including the dV factor of S/field.cpp:1503-1510:
@@ -349,6 +350,27 @@ class Engine {
     }
     return k;
   }
+
+  /// Box catalogue, multi-GPU runs with a distributed mesh phase (trvb_dmesh_*): the ranks of
+  /// `comm` assign and transform slabs of the mesh; every rank gets the modes that the grid
+  /// of `sub` represents as a HALF mesh of sub's extents, which the device layer reads as a
+  /// low-|k| view of the full-grid spectrum.  Collective.
+  dev::Mesh density_fluctuation_dist(trvb_comm* comm, trvb_ctx* sub) {
+    if (!data_) {   // pending host arrays: the whole catalogue goes up first
+      data_.reset(new dev::Catalogue(ctx_, ndata_, host_x_, host_y_, host_z_, nullptr, nullptr, false));
+    }
+    const double* x = nullptr; const double* y = nullptr; const double* z = nullptr;
+    dev::check(trvb_cat_positions(data_->get(), &x, &y, &z), "trvb_cat_positions");
+    dev::check(trvb_dmesh_get(c_, comm, &dmesh_), "trvb_dmesh_get");
+    // Mean subtraction touches the k = 0 mode only: FFT[nbar dV] = N delta_k0.
+    dev::check(trvb_dmesh_density(dmesh_, ndata_, x, y, z, -double(ndata_)), "trvb_dmesh_density");
+    trvs::count_fft += 1;
+    dev::Mesh k(ctx_, sub, TRVB_HALF);
+    dev::check(trvb_dmesh_gather_lowk(dmesh_, sub, k.view()), "trvb_dmesh_gather_lowk");
+    return k;
+  }
+  trvb_dmesh* dmesh() { return dmesh_; }
+  ~Engine() { if (dmesh_) trvb_dmesh_forget_lowk(dmesh_); }
 
   /// N_LM(k): conj(y_LM) w^2 for data plus alpha^2 x randoms
   /// (S/field.cpp:1364-1447); box: unit weights, no mean subtraction.
@@ -428,6 +450,7 @@ class Engine {
   const double* host_x_ = nullptr;   // box arrays awaiting the streamed upload
   const double* host_y_ = nullptr;
   const double* host_z_ = nullptr;
+  trvb_dmesh* dmesh_ = nullptr;      // owned by the context
 };
 
 /// `count` consecutive meshes of one grid in a single device allocation (the
@@ -455,6 +478,21 @@ class Slab {
   void* data_ = nullptr;
   size_t stride_;
   int count_;
+};
+
+/// A plain device block with RAII ownership.
+class PlaneBlock {
+ public:
+  PlaneBlock(std::shared_ptr<trvb_ctx> owner, size_t bytes) : owner_(owner) {
+    dev::check(trvb_malloc(owner_.get(), &data_, bytes), "trvb_malloc");
+  }
+  ~PlaneBlock() { if (data_) trvb_free(owner_.get(), data_); }
+  PlaneBlock(const PlaneBlock&) = delete;
+  PlaneBlock& operator=(const PlaneBlock&) = delete;
+  void* data() const { return data_; }
+ private:
+  std::shared_ptr<trvb_ctx> owner_;
+  void* data_ = nullptr;
 };
 
 /// Blocked all-pairs reduction: out[idx] = sum_x A_{row(idx)} B_{col(idx)} G
@@ -764,11 +802,28 @@ trv::BispecMeasurements bispec_impl(
     const char* env = std::getenv("TRV_NO_SLAB");
     if (env != nullptr && env[0] == '1') slab_mode = false;
   }
+  // Distributed mesh phase (box catalogues, NCCL communicator attached, grid extents that
+  // split over the ranks): assignment and the full-grid transforms are shared as well --
+  // x-slabs of the mesh, one all-to-all per transform (trvb_dmesh_*) -- every rank reads
+  // the low-|k| modes it needs from a gathered copy, and the shot-noise branch is split
+  // like the rest, so the planes of the sub-grid are dealt evenly.  TRV_NO_DIST_MESH=1:
+  // replicated mesh.
+  trvb_comm* comm = dev::process_comm();
+  bool dist_mesh = slab_mode && !survey && comm != nullptr
+    && trvb_comm_size(comm) == params.part_count && trvb_comm_rank(comm) == params.part_rank
+    && trvb_dmesh_supported(eng.ctx(), params.part_count)
+    && params.boxsize[0] * params.ngrid[1] == params.boxsize[1] * params.ngrid[0]
+    && params.boxsize[0] * params.ngrid[2] == params.boxsize[2] * params.ngrid[0];
+  {
+    const char* env = std::getenv("TRV_NO_DIST_MESH");
+    if (env != nullptr && env[0] == '1') dist_mesh = false;
+  }
   int slab_x0 = 0, slab_nx = 0;
   if (slab_mode) {
     const int R = params.part_count, r = params.part_rank;
     const double W = 1.2 * nb * (params.ell1 == params.ell2 ? 1. : 2.) + 1.;   // fields + pair products
-    const double f_last = std::max(0., (W - (R - 1) * shot_cost_in_fields) / (R * W));
+    const double f_last = dist_mesh ? 1. / R
+      : std::max(0., (W - (R - 1) * shot_cost_in_fields) / (R * W));
     const int n_last = static_cast<int>(std::floor(f_last * nsub[0] + 0.5));
     const int rest = nsub[0] - n_last;
     auto first_plane = [&](int q) {   // ranks 0 .. R-2 share `rest` planes evenly
@@ -783,13 +838,30 @@ trv::BispecMeasurements bispec_impl(
     share.pairs.assign(dv.dim, slab_nx > 0 ? 1 : 0);
     share.any_pairs = slab_nx > 0;
   }
+  if (dist_mesh) {   // every rank takes part in xi(r) and reduces its own entries from it
+    const std::vector<int> owner = partition_owners(dv.row, dv.col, params.part_count,
+                                                    params.ell1 == params.ell2, 0.);
+    for (int i = 0; i < dv.dim; i++) share.shot[i] = owner[i] == params.part_rank;
+    share.any_shot = true;
+  }
   const std::vector<char>& active = share.pairs;
   const std::vector<char>& shot_active = share.shot;
 
   trvb_ctx* c = eng.ctx();
 
+  const bool coarse = nsub[0] != params.ngrid[0];
+  std::shared_ptr<trvb_ctx> sub_holder;
+  trvb_ctx* sub = c;
+  if (coarse) {
+    trvb_ctx* raw = nullptr;
+    dev::check(trvb_subgrid_create(c, &raw, nsub), "trvb_subgrid_create");
+    sub_holder.reset(raw, [](trvb_ctx* p) { trvb_ctx_destroy(p); });
+    sub = raw;
+  }
+
   // Common fields: delta n_00(k) and N_00(k).
-  dev::Mesh dn_00 = eng.density_fluctuation(0, 0);
+  dev::Mesh dn_00 = dist_mesh ? eng.density_fluctuation_dist(comm, sub)
+                              : eng.density_fluctuation(0, 0);
   dev::Mesh N_00_own;
   if (survey && share.any_shot) N_00_own = eng.quadratic_field(0, 0);   // shot noise only
   const trvb_mesh N_00 = (survey && share.any_shot)
@@ -809,15 +881,6 @@ trv::BispecMeasurements bispec_impl(
   for (int b = 0; b < nb; b++) keff[b] = ksum[b] / double(nmodes[b]);
   dev::profile_mark(c, "shell_stats");
 
-  const bool coarse = nsub[0] != params.ngrid[0];
-  std::shared_ptr<trvb_ctx> sub_holder;
-  trvb_ctx* sub = c;
-  if (coarse) {
-    trvb_ctx* raw = nullptr;
-    dev::check(trvb_subgrid_create(c, &raw, nsub), "trvb_subgrid_create");
-    sub_holder.reset(raw, [](trvb_ctx* p) { trvb_ctx_destroy(p); });
-    sub = raw;
-  }
   const double nsub_mesh = double(nsub[0]) * nsub[1] * nsub[2];
   // vol_cell * sum over the n^3 mesh == (V / ns^3) * sum over the sub-grid.
   const double vol_cell_sub = eng.vol() / nsub_mesh;
@@ -843,6 +906,8 @@ trv::BispecMeasurements bispec_impl(
     if (env != nullptr && env[0] == '1') pruned = false;
   }
   dev::Mesh xi;             // shot-noise mesh, reused across terms in a box
+  std::unique_ptr<PlaneBlock> xi_planes;   // distributed mesh: this rank's planes of it
+  const long long params_ndata = eng.ndata();
   dev::Mesh G;              // G_LM(x) on the sub-grid
   int G_M = 0; bool have_G = false, have_xi = false;
   dev::Mesh dn_LM;          // survey: delta n_LM(k) of the current M
@@ -922,6 +987,18 @@ trv::BispecMeasurements bispec_impl(
     auto ensure_xi = [&]() {
       if (have_xi) return;
       const double S[2] = {Sbar_LM.real(), Sbar_LM.imag()};
+      if (dist_mesh) {   // this rank's planes of xi(r) only
+        int x0 = 0, nx = 0;
+        dev::check(trvb_dmesh_planes(eng.dmesh(), &x0, &nx), "trvb_dmesh_planes");
+        xi_planes.reset(new PlaneBlock(eng.shared(),
+          sizeof(double) * (size_t)nx * (size_t)params.ngrid[1] * (size_t)params.ngrid[2]));
+        dev::check(trvb_dmesh_shot_xi(eng.dmesh(), 0., double(params_ndata), S,
+                                      static_cast<double*>(xi_planes->data())), "trvb_dmesh_shot_xi");
+        trvs::count_ifft += 1;
+        have_xi = true;
+        dev::profile_mark(c, "shot_xi");
+        return;
+      }
       // Spectra of two real fields and a real amplitude: xi(x) is real.
       const bool real_xi = dn_LM_ref.layout() == TRVB_HALF && N_00.layout == TRVB_HALF
         && S[1] == 0.;
@@ -1018,11 +1095,23 @@ trv::BispecMeasurements bispec_impl(
           if (!shot_active[i]) continue;
           ka.push_back(k1eff[i]); kb.push_back(k2eff[i]); where.push_back(i);
         }
-        if (!where.empty()) {
-          std::vector<double> S(2 * where.size());
-          dev::check(trvb_shot_bispec_reduce(c, xi.view(), params.ell1, t.m1, params.ell2, t.m2,
-                                             ka.data(), kb.data(), (int)where.size(), S.data()),
-                     "trvb_shot_bispec_reduce");
+        if (dist_mesh && where.empty()) {   // the histogram sum is collective: take part
+          ka.push_back(keff[0]); kb.push_back(keff[0]);
+        }
+        if (!ka.empty()) {
+          std::vector<double> S(2 * ka.size());
+          if (dist_mesh) {
+            int x0 = 0, nx = 0;
+            dev::check(trvb_dmesh_planes(eng.dmesh(), &x0, &nx), "trvb_dmesh_planes");
+            dev::check(trvb_shot_bispec_reduce_slab(
+              c, static_cast<const double*>(xi_planes->data()), x0, nx, comm, params.ell1, t.m1,
+              params.ell2, t.m2, ka.data(), kb.data(), (int)ka.size(), S.data()),
+              "trvb_shot_bispec_reduce_slab");
+          } else {
+            dev::check(trvb_shot_bispec_reduce(c, xi.view(), params.ell1, t.m1, params.ell2, t.m2,
+                                               ka.data(), kb.data(), (int)ka.size(), S.data()),
+                       "trvb_shot_bispec_reduce");
+          }
           for (size_t p = 0; p < where.size(); p++) {
             const cdouble S_ij_k = t.coupling * cdouble(S[2*p], S[2*p+1]);
             sn_dv[where[p]] += factor_phase * (
