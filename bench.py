@@ -432,8 +432,13 @@ def run_b200(args):
         "ms_per_step": 1.e3 * sec / args.steps, "higher_is_better": False,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_of(args, wl),
-        "run": {"parallelism": (f"pairs/{world}gpu, all-reduce inside the C API (NCCL)"
-                                if world > 1 else "1gpu"),
+        "run": {"parallelism": (
+                    (f"{world}gpu: x-slabs of the mesh (assignment, FFTs: all-to-all) and of the "
+                     "sub-grid (shell fields, pair products), exchanges inside the C API (NCCL)"
+                     if core.dmesh_call_count() > 0 else
+                     f"pairs/{world}gpu, replicated mesh, all-reduce inside the C API (NCCL)")
+                    if world > 1 else "1gpu"),
+                "distributed_mesh_calls": core.dmesh_call_count(),
                 "e2e_upload": ("1/N slice per rank from pinned host memory + NCCL all-gather"
                                if world > 1 else "pinned host -> device")},
         "clocks": clocks,

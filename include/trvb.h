@@ -357,7 +357,8 @@ int trvb_ctx_device(const trvb_ctx* ctx);
  *   trvb_comm_alltoall        block q (`n` doubles) of `send` goes to rank q, block q of
  *                             `recv` comes from rank q (grouped ncclSend/ncclRecv)
  *   trvb_comm_bcast_segments  segment s of `buf` (offset[s], count[s] doubles) is sent by
- *                             rank root[s] to all others (grouped ncclBroadcast) */
+ *                             rank root[s] to all others (one group of ncclSend/ncclRecv, or of
+ *                             ncclBroadcast above 64 MB) */
 int trvb_comm_alltoall(trvb_ctx* ctx, trvb_comm* comm, const double* send, double* recv,
                        long long n);
 int trvb_comm_bcast_segments(trvb_ctx* ctx, trvb_comm* comm, double* buf, int nseg,

@@ -1,12 +1,15 @@
 """Multi-GPU execution of the three-point estimators: one process per GPU.
 
 The reference has no distributed mode (``trv::sys::currTask`` is the constant 0,
-I/monitor.hpp:249-250).  Here the mesh is replicated on every GPU and the
-independent entries of the data vector -- the (k1, k2) bin pairs of every
-(m1, m2, M) term, S/threept.cpp:1902-1904, 2137-2139 -- are dealt to the ranks;
-each entry is produced by exactly one rank (zeros elsewhere), so a single small
-all-reduce(sum) of ``4 * dv_dim`` doubles over NCCL/NVLink completes the result
-and is bit-identical to the single-GPU one.
+I/monitor.hpp:249-250).  Here every rank makes the same estimator call with
+``part_rank``/``part_count`` set.  Deterministic mode, survey catalogues, the 3PCF and
+the CPU tests: the mesh is replicated and the independent entries of the data vector --
+the (k1, k2) bin pairs of every (m1, m2, M) term, S/threept.cpp:1902-1904, 2137-2139 --
+are dealt to the ranks; each entry is produced by exactly one rank (zeros elsewhere), so
+a single small all-reduce(sum) of ``4 * dv_dim`` doubles completes the result and is
+bit-identical to the single-GPU one.  Throughput mode on a box: the ranks split the
+x-planes of the sub-grid (and, with the NCCL communicator attached, of the mesh itself:
+DESIGN.md section 6) and every entry is a sum over the ranks.
 
 The exchange itself lives behind the C API (``trv_comm_init`` / ``trvb_allreduce``,
 NCCL bound inside ``libtrvb.so``): once :func:`init_comm` has attached the
@@ -48,16 +51,20 @@ def owners(form, degrees, num_bins, world_size, idx_bin=0):
     return core.partition_owners(form, degrees, num_bins, world_size, idx_bin=idx_bin)
 
 
-def shot_noise_owners(form, degrees, num_bins, world_size, idx_bin=0):
-    """Rank that computes the SHOT NOISE of every bispectrum entry: with two or more ranks
-    the last rank does, for every entry (its full-grid inverse FFT does not depend on the
-    pair partition).  The raw-bispectrum (pair) owners of a bispectrum call are
-    :func:`owners` with the last rank's share cut short by the cost of that branch
-    (``bispec_share`` in src/threept.cpp; the cut depends on the mesh and sub-grid sizes,
-    so :func:`owners` is exact for the 3PCF and for bispectrum runs on one rank only)."""
+def shot_noise_owners(form, degrees, num_bins, world_size, idx_bin=0, distributed_mesh=False):
+    """Rank that computes the SHOT NOISE of every bispectrum entry.  Replicated mesh (CPU
+    tests, survey catalogues, deterministic mode): with two or more ranks the last rank
+    does, for every entry (its full-grid inverse FFT does not depend on the pair
+    partition).  ``distributed_mesh`` (box catalogues with the NCCL communicator attached,
+    src/threept.cpp ``dist_mesh``): every rank takes part in xi(r) and the entries are
+    dealt round robin.  The raw-bispectrum owners of a pair-block run are :func:`owners`
+    with the last rank's share cut short by the cost of that branch (``bispec_share``);
+    in x-slab mode every rank contributes to every entry."""
     own = owners(form, degrees, num_bins, max(world_size, 1), idx_bin=idx_bin)
     if world_size < 2:
         return own
+    if distributed_mesh:
+        return np.arange(len(own)) % world_size
     return np.full_like(own, world_size - 1)
 
 

@@ -81,6 +81,17 @@ std::shared_ptr<trvb_ctx> acquire_context(const trv::ParameterSet& params) {
     throw trvs::DeviceError(
       "No usable CUDA device: triumvirate_b200 has no CPU fallback.");
   }
+  // An unset box or mesh passes validate() as in the reference (the program derives them
+  // afterwards, S/parameters.cpp:1416-1470); an estimator must not be reached with one.
+  for (int ax = 0; ax < 3; ax++) {
+    if (!(params.ngrid[ax] > 0) || !(params.boxsize[ax] > 0.)) {
+      throw trvs::InvalidParameterError(
+        "Mesh is not set: `ngrid` = (%d, %d, %d), `boxsize` = (%lg, %lg, %lg); derive them "
+        "with trv::set_boxsize_from_expand / trv::set_ngrid_from_cutoff first.",
+        params.ngrid[0], params.ngrid[1], params.ngrid[2],
+        params.boxsize[0], params.boxsize[1], params.boxsize[2]);
+    }
+  }
   const int device = select_device();
   CtxKey key(device, params.ngrid[0], params.ngrid[1], params.ngrid[2],
              params.boxsize[0], params.boxsize[1], params.boxsize[2],

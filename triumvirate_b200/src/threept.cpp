@@ -19,6 +19,7 @@
 #include <cmath>
 #include <limits>
 #include <map>
+#include <mutex>
 #include <memory>
 #include <set>
 #include <thread>
@@ -612,6 +613,17 @@ std::vector<int> partition_owners(const std::vector<int>& row, const std::vector
   const int dim = static_cast<int>(row.size());
   std::vector<int> owner(dim, 0);
   if (world <= 1 || dim == 0) return owner;
+  // The search below costs milliseconds (24 orderings x 40 bisection steps over all
+  // entries) and every estimator call of a run asks for the same partition: remembered.
+  typedef std::tuple<std::vector<int>, std::vector<int>, int, bool, double> Key;
+  static std::mutex cache_mutex;
+  static std::map<Key, std::vector<int> > cache;
+  const Key key(row, col, world, same_fields, handicap_last);
+  {
+    std::lock_guard<std::mutex> lock(cache_mutex);
+    auto hit = cache.find(key);
+    if (hit != cache.end()) return hit->second;
+  }
   const std::vector<int> rows = distinct_sorted(row), cols = distinct_sorted(col);
   auto rank_in = [](const std::vector<int>& sorted, int v) {
     return static_cast<int>(std::lower_bound(sorted.begin(), sorted.end(), v) - sorted.begin());
@@ -677,6 +689,11 @@ std::vector<int> partition_owners(const std::vector<int>& row, const std::vector
     if (best_order.empty() || hi < best_cap - 1.e-9) { best_cap = hi; best_order = order; }
   }
   cut(best_order, best_cap, &owner);
+  {
+    std::lock_guard<std::mutex> lock(cache_mutex);
+    if (cache.size() >= 64) cache.clear();
+    cache[key] = owner;
+  }
   return owner;
 }
 
@@ -833,16 +850,23 @@ trv::BispecMeasurements bispec_impl(
     else { slab_x0 = rest; slab_nx = n_last; }
   }
 
-  BispecShare share = bispec_share(params, dv, shot_cost_in_fields);
+  BispecShare share;
   if (slab_mode) {
+    // planes, not pairs, are dealt: every rank reduces all pairs over its planes.  The shot
+    // noise stays with the last rank, or -- distributed mesh: every rank takes part in
+    // xi(r) -- is dealt in blocks of entries.
+    const int R = params.part_count, r = params.part_rank;
     share.pairs.assign(dv.dim, slab_nx > 0 ? 1 : 0);
+    share.shot.assign(dv.dim, 0);
+    // (compact blocks of the pair matrix: a rank evaluates j_l for the few wavenumbers of
+    // its block only; the partition is remembered per binning)
+    std::vector<int> shot_owner;
+    if (dist_mesh) shot_owner = partition_owners(dv.row, dv.col, R, params.ell1 == params.ell2, 0.);
+    for (int i = 0; i < dv.dim; i++) share.shot[i] = dist_mesh ? (shot_owner[i] == r) : (r == R - 1);
     share.any_pairs = slab_nx > 0;
-  }
-  if (dist_mesh) {   // every rank takes part in xi(r) and reduces its own entries from it
-    const std::vector<int> owner = partition_owners(dv.row, dv.col, params.part_count,
-                                                    params.ell1 == params.ell2, 0.);
-    for (int i = 0; i < dv.dim; i++) share.shot[i] = owner[i] == params.part_rank;
-    share.any_shot = true;
+    share.any_shot = dist_mesh || r == R - 1;
+  } else {
+    share = bispec_share(params, dv, shot_cost_in_fields);
   }
   const std::vector<char>& active = share.pairs;
   const std::vector<char>& shot_active = share.shot;
@@ -909,7 +933,7 @@ trv::BispecMeasurements bispec_impl(
   std::unique_ptr<PlaneBlock> xi_planes;   // distributed mesh: this rank's planes of it
   const long long params_ndata = eng.ndata();
   dev::Mesh G;              // G_LM(x) on the sub-grid
-  int G_M = 0; bool have_G = false, have_xi = false;
+  int G_M = 0; bool have_G = false, have_xi = false, G_on_slab = false;
   dev::Mesh dn_LM;          // survey: delta n_LM(k) of the current M
   dev::Mesh N_LM;
   cdouble Sbar_LM = 0.;
@@ -1023,9 +1047,21 @@ trv::BispecMeasurements bispec_impl(
         // (slab mode too: G holds every mode the sub-grid represents -- twice the shells'
         // cut-off per axis -- so the pruned x-DFT does not pay for it; the whole G is
         // transformed once, 2 % of the job, and the slab reads its own planes of it)
-        G = dev::Mesh(eng.shared(), sub, layout);
-        dev::check(trvb_shell_ifft(c, sub, dn_LM_ref.view(), 0, 0, -1., -1., 1. / eng.vol(),
-                                   G.view()), "trvb_shell_ifft (G)");
+        if (slab_ctx && layout == TRVB_REAL) {
+          // x-slabs: only this rank's planes of G, through the same per-axis transform as
+          // the shell fields (an "unbounded shell": the x pass runs on every column of the
+          // sub-grid's spectrum, the y and z passes on the slab's planes only).
+          G = dev::Mesh(eng.shared(), slab_ctx, layout);
+          const double all = -1., amp_G = 1. / eng.vol();
+          dev::check(trvb_shell_slab_batch(c, sub, dn_LM_ref.view(), 0, 0, &all, &all, &amp_G, 1,
+                                           slab_x0, slab_nx, G.data()), "trvb_shell_slab_batch (G)");
+          G_on_slab = true;
+        } else {
+          G = dev::Mesh(eng.shared(), sub, layout);
+          dev::check(trvb_shell_ifft(c, sub, dn_LM_ref.view(), 0, 0, -1., -1., 1. / eng.vol(),
+                                     G.view()), "trvb_shell_ifft (G)");
+          G_on_slab = false;
+        }
         trvs::count_ifft += 1;
         G_M = t.M; have_G = true;
         dev::profile_mark(c, "G_field");
@@ -1037,7 +1073,7 @@ trv::BispecMeasurements bispec_impl(
       const int m_b = mirror ? t.m1 : t.m2;
       std::vector<cdouble> bk_comp;
       trvb_mesh G_pairs = G.view();
-      if (slab_ctx) {   // REAL layout, x slowest: the slab's planes are contiguous
+      if (slab_ctx && !G_on_slab) {   // REAL layout, x slowest: the slab's planes are contiguous
         G_pairs.data = static_cast<char*>(G_pairs.data)
           + sizeof(double) * (size_t)slab_x0 * (size_t)nsub[1] * (size_t)nsub[2];
       }
@@ -1071,10 +1107,32 @@ trv::BispecMeasurements bispec_impl(
           std::vector<double> kk(nb);
           pk.assign(2 * nb, 0.); sn.assign(2 * nb, 0.);
           const double S[2] = {Sbar_LM.real(), Sbar_LM.imag()};
-          dev::check(trvb_twopt_fourier(c, dn_00.view(), N_LM_ref, S, ell, m, /*interlaced=*/0,
-                                        kbinning.bin_edges.data(), kbinning.bin_centres.data(),
-                                        nb, nm.data(), kk.data(), pk.data(), sn.data()),
-                     "trvb_twopt_fourier");
+          // Distributed run on a large low-|k| cube: every rank bins a contiguous range of
+          // shells and the per-bin means are summed over the ranks (zeros elsewhere).
+          double cube_modes = 0.5;
+          for (int ax = 0; ax < 3; ax++) {
+            cube_modes *= 2. * kbinning.bin_edges.back() * params.boxsize[ax] / (2. * M_PI) + 1.;
+          }
+          if (dist_mesh && cube_modes > 4.e6 && nb >= params.part_count) {
+            const int R = params.part_count, r = params.part_rank;
+            const int b0 = static_cast<int>((long long)nb * r / R);
+            const int b1 = static_cast<int>((long long)nb * (r + 1) / R);
+            dev::check(trvb_twopt_fourier(c, dn_00.view(), N_LM_ref, S, ell, m, /*interlaced=*/0,
+                                          kbinning.bin_edges.data() + b0,
+                                          kbinning.bin_centres.data() + b0, b1 - b0,
+                                          nm.data() + b0, kk.data() + b0, pk.data() + 2 * b0,
+                                          sn.data() + 2 * b0), "trvb_twopt_fourier");
+            std::vector<double> buf(pk);
+            buf.insert(buf.end(), sn.begin(), sn.end());
+            dev::allreduce(c, buf.data(), (long long)buf.size());
+            std::copy(buf.begin(), buf.begin() + 2 * nb, pk.begin());
+            std::copy(buf.begin() + 2 * nb, buf.end(), sn.begin());
+          } else {
+            dev::check(trvb_twopt_fourier(c, dn_00.view(), N_LM_ref, S, ell, m, /*interlaced=*/0,
+                                          kbinning.bin_edges.data(), kbinning.bin_centres.data(),
+                                          nb, nm.data(), kk.data(), pk.data(), sn.data()),
+                       "trvb_twopt_fourier");
+          }
           binned_ell = ell; binned_m = m;
         }
         for (int i = 0; i < dv.dim; i++) {
