@@ -941,3 +941,30 @@ def test_gram_reduce_tensor_core_path_against_numpy(case, monkeypatch):
         assert np.max(np.abs(got["0"] - got["1"])) < 1.e-11 * scale
     finally:
         lib.trvb_ctx_destroy(ctx)
+
+
+@pytest.mark.gpu
+def test_pruned_shell_transform_equals_dense(core, monkeypatch):
+    """Real shell fields on a sub-grid: the pruned per-axis transform (x on the non-zero
+    columns, y on the slab's non-zero rows, c2r along z; extents per sub-batch of shells)
+    against the sparse scatter + dense batched 3-D cuFFT it replaced, for one and many
+    sub-batches, cubic and non-cubic boxes."""
+    gen = np.random.default_rng(4242)
+    for L, ng in ((1000., 160), ((900., 1000., 1200.), (144, 160, 192))):
+        Lv = np.broadcast_to(np.asarray(L, dtype=float), (3,))
+        pos = gen.uniform(0., 1., size=(3, 150000)) * Lv[:, None]
+        kw = dict(boxsize=L, ngrid=ng, assignment="pcs", degrees=(0, 0, 0), form="full",
+                  bin_range=(0.005, 0.1), num_bins=12, norm_factor=1., pos_d=pos)
+        monkeypatch.setenv("TRV_NO_PRUNE", "1")
+        dense = core.threept("bispec", "sim", **kw)
+        monkeypatch.delenv("TRV_NO_PRUNE")
+        for groups in (None, "1", "12"):
+            if groups is None:
+                monkeypatch.delenv("TRV_SHELL_GROUPS", raising=False)
+            else:
+                monkeypatch.setenv("TRV_SHELL_GROUPS", groups)
+            pruned = core.threept("bispec", "sim", **kw)
+            err = np.max(np.abs(pruned["bk_raw"] - dense["bk_raw"])) / np.max(np.abs(dense["bk_raw"]))
+            assert err < 1.e-12, (ng, groups, err)
+            assert np.array_equal(pruned["nmodes_1"], dense["nmodes_1"])
+        monkeypatch.delenv("TRV_SHELL_GROUPS", raising=False)

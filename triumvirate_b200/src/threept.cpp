@@ -898,10 +898,32 @@ trv::BispecMeasurements bispec_impl(
 
   // Shell statistics (k_eff, nmodes) for every bin in one pass; they do not
   // depend on (l, m) (S/field.cpp:1815-1847, 1905).
+  // They depend on the grid and the bin edges only, not on the catalogue: remembered per
+  // (box, mesh, edges), which also spares every later call a kernel and a host synchronisation
+  // in the middle of its stream of launches.
   std::vector<long long> nmodes(nb);
   std::vector<double> ksum(nb), keff(nb);
-  dev::check(trvb_shell_stats(c, kbinning.bin_edges.data(), nb, 0, nmodes.data(),
-                              ksum.data()), "trvb_shell_stats");
+  {
+    typedef std::tuple<std::vector<double>, std::vector<double> > StatsKey;
+    static std::mutex stats_mutex;
+    static std::map<StatsKey, std::pair<std::vector<long long>, std::vector<double> > > stats_cache;
+    std::vector<double> grid(params.boxsize, params.boxsize + 3);
+    for (int ax = 0; ax < 3; ax++) grid.push_back(double(params.ngrid[ax]));
+    const StatsKey key(grid, kbinning.bin_edges);
+    bool hit = false;
+    {
+      std::lock_guard<std::mutex> lock(stats_mutex);
+      auto it = stats_cache.find(key);
+      if (it != stats_cache.end()) { nmodes = it->second.first; ksum = it->second.second; hit = true; }
+    }
+    if (!hit) {
+      dev::check(trvb_shell_stats(c, kbinning.bin_edges.data(), nb, 0, nmodes.data(),
+                                  ksum.data()), "trvb_shell_stats");
+      std::lock_guard<std::mutex> lock(stats_mutex);
+      if (stats_cache.size() >= 64) stats_cache.clear();
+      stats_cache[key] = std::make_pair(nmodes, ksum);
+    }
+  }
   for (int b = 0; b < nb; b++) keff[b] = ksum[b] / double(nmodes[b]);
   dev::profile_mark(c, "shell_stats");
 
