@@ -406,7 +406,18 @@ extern "C" int trvb_malloc(trvb_ctx* ctx, void** dptr, size_t bytes) {
 extern "C" int trvb_free(trvb_ctx* ctx, void* dptr) {
   if (!dptr) return 0;
   TRVB_CUDA(cudaSetDevice(ctx->device));
-  TRVB_CUDA(trvb_dev_free_raw(ctx, dptr));   // stream-ordered: no synchronisation
+  // The arena orders reuse by the stream of the freeing context.  With TRV_OVERLAP=1 a
+  // sub-grid context runs on a stream of its own while its meshes are owned (and freed) by
+  // the root context: work still queued on that stream must finish before the block can
+  // be handed to the root's stream.  (Opt-in path; by default there is one stream.)
+  trvb_ctx* root = ctx->parent ? ctx->parent : ctx;
+  for (auto& kv : root->subgrids) {
+    if (kv.second->own_stream && kv.second->stream != ctx->stream) {
+      TRVB_CUDA(cudaStreamSynchronize(kv.second->stream));
+    }
+  }
+  if (ctx->parent && ctx->own_stream) TRVB_CUDA(cudaStreamSynchronize(root->stream));
+  TRVB_CUDA(trvb_dev_free_raw(ctx, dptr));   // stream-ordered: no synchronisation otherwise
   return 0;
 }
 
