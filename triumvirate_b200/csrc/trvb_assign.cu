@@ -1244,6 +1244,7 @@ int ensure_sorted(trvb_ctx* ctx, trvb_cat* cat, int shifted, int by_cell) {
 // no divergence (the thread-per-cell kernel spent its time in 64 mostly-empty,
 // divergent list visits per cell: 740 ms for 1e7 particles on 512^3, PCS).
 constexpr int GT_X = 2, GT_Y = 4, GT_Z = 4;
+constexpr int DT_X = 4, DT_Y = 4, DT_Z = 8;     // k_assign_gather_tile (multiples of GT)
 
 template <int ORDER, bool COMPLEX>
 __global__ void __launch_bounds__(128)
@@ -1251,15 +1252,31 @@ k_assign_gather_warp(SortedView c, const int* __restrict__ order,
                      const int* __restrict__ cell_start, GridDesc g, int shifted,
                      int kind, YlmCoef yc, double scale, double pre /* 1/vol_cell or 1 */,
                      int accumulate, int nt1, int nt2, long long ntiles,
-                     double* __restrict__ mesh) {
+                     const int* __restrict__ big_tiles, const int* __restrict__ big_count,
+                     int bt1, int bt2, double* __restrict__ mesh) {
   constexpr int LO = 2, SPAN = 4;                       // homes q - 2 .. q + 1
   constexpr int UX = GT_X + SPAN - 1, UY = GT_Y + SPAN - 1, UZ = GT_Z + SPAN - 1;
   constexpr int NU = UX * UY * UZ;
   constexpr int PER = (NU + 31) / 32;
   const int lane = threadIdx.x & 31;
-  const long long tile = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (tile >= ntiles) return;                           // whole warp
-  const int tk = (int)(tile % nt2), tj = (int)((tile / nt2) % nt1), ti = (int)(tile / ((long long)nt2 * nt1));
+  // Either every tile of the mesh, or (big_tiles != null) the 2 x 1 x 2 tiles of each
+  // DT-sized tile that k_assign_gather_tile left behind (too many candidates to sort).
+  constexpr int SUB = (DT_X / GT_X) * (DT_Y / GT_Y) * (DT_Z / GT_Z);
+  const long long nwork = big_tiles ? (long long)(*big_count) * SUB : ntiles;
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long work = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+       work < nwork; work += nwarps) {
+  int ti, tj, tk;
+  if (big_tiles) {
+    const int big = big_tiles[work / SUB], sub = (int)(work % SUB);
+    const int bk = big % bt2, bj = (big / bt2) % bt1, bi = big / (bt2 * bt1);
+    ti = bi * (DT_X / GT_X) + sub / ((DT_Y / GT_Y) * (DT_Z / GT_Z));
+    tj = bj * (DT_Y / GT_Y) + (sub / (DT_Z / GT_Z)) % (DT_Y / GT_Y);
+    tk = bk * (DT_Z / GT_Z) + sub % (DT_Z / GT_Z);
+    if (ti >= (g.n[0] + GT_X - 1) / GT_X || tj >= nt1 || tk >= nt2) continue;
+  } else {
+    tk = (int)(work % nt2); tj = (int)((work / nt2) % nt1); ti = (int)(work / ((long long)nt2 * nt1));
+  }
   const int ci = ti * GT_X + (lane >> 4), cj = tj * GT_Y + ((lane >> 2) & 3), ck = tk * GT_Z + (lane & 3);
   const bool valid = ci < g.n[0] && cj < g.n[1] && ck < g.n[2];
 
@@ -1324,6 +1341,206 @@ k_assign_gather_warp(SortedView c, const int* __restrict__ order,
   if (valid) {
     if (COMPLEX) { mesh[2 * gid] = acc_re; mesh[2 * gid + 1] = acc_im; }
     else mesh[gid] = acc_re;
+  }
+  }
+}
+
+// Tile form of the ordered gather (TSC/PCS): a warp owns DT_X x DT_Y x DT_Z = 128 output
+// cells, four z-consecutive cells per lane in registers.  The particles that can reach the
+// tile -- those of the (DT + 3)^3-shaped union of home cells, ~40 on a 512^3 mesh with 1e7
+// particles -- are copied to shared memory as (id, slot) pairs and SORTED by id there
+// (bitonic, one warp), then walked once in that order: every lane evaluates each particle
+// against its own cells and adds it, so every cell accumulates in ascending particle id,
+// the reference's single-threaded order.  The merge of k_assign_gather_warp (one
+// __reduce_min_sync round trip per particle and per 32 cells) becomes one sort per 128
+// cells.  Tiles with more than DT_CAP candidates (clustered catalogues) are listed for
+// k_assign_gather_warp.
+constexpr int DT_CAP = 256;      // candidates a warp sorts in shared memory
+constexpr int DT_CHUNK = 64;     // candidates whose windows are staged at a time
+
+// Per-candidate data of the walk, evaluated once per tile by one lane each (the walk itself
+// would redo it in every lane: three fp64 window evaluations per particle and lane made the
+// fp64 pipe the bound): first stencil index and window values per axis, and the weight.
+template <int ORDER>
+struct DetStage {
+  int i0[3];
+  int pad;
+  double win[3][ORDER];
+  double w_re, w_im;
+};
+
+template <int ORDER, bool COMPLEX>
+__global__ void __launch_bounds__(128, 4)
+k_assign_gather_tile(SortedView c, const int* __restrict__ order,
+                     const int* __restrict__ cell_start, GridDesc g, int shifted,
+                     int kind, YlmCoef yc, double scale, double pre /* 1/vol_cell or 1 */,
+                     int accumulate, int nt1, int nt2, long long ntiles,
+                     int* __restrict__ big_tiles, int* __restrict__ big_count,
+                     double* __restrict__ mesh) {
+  constexpr int LO = 2, SPAN = 4;                       // homes q - 2 .. q + 1
+  constexpr int UX = DT_X + SPAN - 1, UY = DT_Y + SPAN - 1, UZ = DT_Z + SPAN - 1;
+  constexpr int ZPL = 4;                                // cells per lane, consecutive in z
+  static_assert(DT_X * DT_Y * (DT_Z / ZPL) == 32, "one lane per column segment");
+  __shared__ int s_id[4][DT_CAP];
+  __shared__ int s_slot[4][DT_CAP];
+  __shared__ DetStage<ORDER> s_stage[4][DT_CHUNK];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long tile = blockIdx.x * (long long)(blockDim.x >> 5) + warp;
+  if (tile >= ntiles) return;                           // whole warp
+  const int tk = (int)(tile % nt2), tj = (int)((tile / nt2) % nt1), ti = (int)(tile / ((long long)nt2 * nt1));
+  int* ids = s_id[warp];
+  int* slots = s_slot[warp];
+  DetStage<ORDER>* stage = s_stage[warp];
+
+  // 1. Candidates per z-row of the union (cells consecutive in z are consecutive in the
+  // cell-sorted order: a row is one slot range, two where it wraps around the box), and
+  // where this lane's go in the list.
+  constexpr int NROW = UX * UY * 2;
+  constexpr int PER_ROW = (NROW + 31) / 32;
+  int beg[PER_ROW], cnt[PER_ROW];
+  int mine = 0;
+  {
+    const int z0 = tk * DT_Z - LO;                      // first z of the union, unwrapped
+#pragma unroll
+    for (int t = 0; t < PER_ROW; t++) {
+      const int u = lane + 32 * t;
+      beg[t] = 0; cnt[t] = 0;
+      if (u < NROW) {
+        const int seg = u & 1, uy = (u >> 1) % UY, ux = (u >> 1) / UY;
+        int hx = ti * DT_X - LO + ux, hy = tj * DT_Y - LO + uy;
+        hx = (hx % g.n[0] + g.n[0]) % g.n[0];
+        hy = (hy % g.n[1] + g.n[1]) % g.n[1];
+        // segment 0: the part of [z0, z0 + UZ) inside [0, n2); segment 1: the wrapped rest
+        int za, zb;
+        if (seg == 0) { za = max(z0, 0); zb = min(z0 + UZ, g.n[2]); }
+        else if (z0 < 0) { za = g.n[2] + z0; zb = g.n[2]; }
+        else { za = 0; zb = z0 + UZ - g.n[2]; }
+        if (zb > za) {
+          const long long row = ((long long)hx * g.n[1] + hy) * g.n[2];
+          beg[t] = cell_start[row + za]; cnt[t] = cell_start[row + zb] - beg[t];
+        }
+      }
+      mine += cnt[t];
+    }
+  }
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  if (total > DT_CAP) {
+    if (lane == 0) big_tiles[atomicAdd(big_count, 1)] = (int)tile;
+    return;
+  }
+  // 2. (id, slot) pairs, padded to a power of two.
+  int npad = 32;
+  while (npad < total) npad <<= 1;
+  {
+    int at = incl - mine;
+#pragma unroll
+    for (int t = 0; t < PER_ROW; t++) {
+      for (int q = 0; q < cnt[t]; q++) { ids[at] = order[beg[t] + q]; slots[at] = beg[t] + q; at++; }
+    }
+    for (int i = total + lane; i < npad; i += 32) { ids[i] = 0x7fffffff; slots[i] = -1; }
+  }
+  __syncwarp();
+  // 3. Bitonic sort by particle id (ids are unique).
+  for (int k = 2; k <= npad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < npad; i += 32) {
+        const int l = i ^ j;
+        if (l > i) {
+          const int a = ids[i], b = ids[l];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) {
+            ids[i] = b; ids[l] = a;
+            const int sa = slots[i]; slots[i] = slots[l]; slots[l] = sa;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  // 4. Walk in id order, DT_CHUNK candidates at a time; lane = (x, y, z-quad) of the tile.
+  const int ci = ti * DT_X + (lane >> 3), cj = tj * DT_Y + ((lane >> 1) & 3);
+  const int ck0 = tk * DT_Z + (lane & 1) * ZPL;
+  const bool col_valid = ci < g.n[0] && cj < g.n[1];
+  double acc_re[ZPL], acc_im[ZPL];
+  long long gid[ZPL];
+#pragma unroll
+  for (int m = 0; m < ZPL; m++) {
+    const bool valid = col_valid && ck0 + m < g.n[2];
+    gid[m] = valid ? ((long long)ci * g.n[1] + cj) * g.n[2] + ck0 + m : -1;
+    acc_re[m] = 0.; acc_im[m] = 0.;
+    if (accumulate && valid) {
+      acc_re[m] = COMPLEX ? mesh[2 * gid[m]] : mesh[gid[m]];
+      if (COMPLEX) acc_im[m] = mesh[2 * gid[m] + 1];
+    }
+  }
+  for (int c0 = 0; c0 < total; c0 += DT_CHUNK) {
+    const int nc = min(DT_CHUNK, total - c0);
+    __syncwarp();
+    for (int i = lane; i < nc; i += 32) {               // one lane per candidate
+      const int slot = slots[c0 + i];
+      const double4 p = c.p4[slot];
+      DetStage<ORDER>& st = stage[i];
+      int ijk[ORDER]; double win[ORDER];
+      window_1d<ORDER>(shift_loc(p.x, g.n[0], shifted), g.n[0], ijk, win);
+      st.i0[0] = ijk[0];
+#pragma unroll
+      for (int a = 0; a < ORDER; a++) st.win[0][a] = win[a];
+      window_1d<ORDER>(shift_loc(p.y, g.n[1], shifted), g.n[1], ijk, win);
+      st.i0[1] = ijk[0];
+#pragma unroll
+      for (int a = 0; a < ORDER; a++) st.win[1][a] = win[a];
+      window_1d<ORDER>(shift_loc(p.z, g.n[2], shifted), g.n[2], ijk, win);
+      st.i0[2] = ijk[0];
+#pragma unroll
+      for (int a = 0; a < ORDER; a++) st.win[2][a] = win[a];
+      const cplx wt = particle_weight(c, slot, p, kind, yc);
+      // ((((inv_vol_cell * w) * Wx) * Wy) * Wz), S/field.cpp:1044-1048.
+      double bre = __dmul_rn(pre, wt.re);
+      if (scale != 1.) bre = __dmul_rn(bre, scale);
+      double bim = 0.;
+      if (COMPLEX) {
+        bim = __dmul_rn(pre, wt.im);
+        if (scale != 1.) bim = __dmul_rn(bim, scale);
+      }
+      st.w_re = bre; st.w_im = bim;
+    }
+    __syncwarp();
+    if (!col_valid) continue;
+    for (int i = 0; i < nc; i++) {
+      const DetStage<ORDER>& st = stage[i];
+      // the stencil of an axis is ORDER consecutive indices (periodic) from i0
+      int ax = ci - st.i0[0]; ax += (ax < 0) ? g.n[0] : 0;
+      if (ax >= ORDER) continue;
+      int ay = cj - st.i0[1]; ay += (ay < 0) ? g.n[1] : 0;
+      if (ay >= ORDER) continue;
+      int az = ck0 - st.i0[2]; az += (az < 0) ? g.n[2] : 0;   // of this lane's first cell
+      // cells ck0 .. ck0 + 3 -> window slots az .. az + 3 (mod n2)
+      if (az >= ORDER && az + (ZPL - 1) < g.n[2]) continue;
+      const double bxy_re = __dmul_rn(__dmul_rn(st.w_re, st.win[0][ax]), st.win[1][ay]);
+      const double bxy_im = COMPLEX ? __dmul_rn(__dmul_rn(st.w_im, st.win[0][ax]), st.win[1][ay]) : 0.;
+#pragma unroll
+      for (int m = 0; m < ZPL; m++) {
+        int a = az + m; a -= (a >= g.n[2]) ? g.n[2] : 0;
+        if (a < ORDER && gid[m] >= 0) {
+          const double wz = st.win[2][a];
+          acc_re[m] = __dadd_rn(acc_re[m], __dmul_rn(bxy_re, wz));
+          if (COMPLEX) acc_im[m] = __dadd_rn(acc_im[m], __dmul_rn(bxy_im, wz));
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < ZPL; m++) {
+    if (gid[m] >= 0) {
+      if (COMPLEX) { mesh[2 * gid[m]] = acc_re[m]; mesh[2 * gid[m] + 1] = acc_im[m]; }
+      else mesh[gid[m]] = acc_re[m];
+    }
   }
 }
 
@@ -1614,15 +1831,50 @@ int launch_assign(trvb_ctx* ctx, trvb_cat* cat, int kind, int L, int M, double s
       const int nt[3] = {(g.n[0] + GT_X - 1) / GT_X, (g.n[1] + GT_Y - 1) / GT_Y,
                          (g.n[2] + GT_Z - 1) / GT_Z};
       const long long ntiles = (long long)nt[0] * nt[1] * nt[2];
-      const int wblocks = (int)div_up(ntiles, 4);
-      if (cplx_mesh) {
-        k_assign_gather_warp<O, true><<<wblocks, 128, 0, ctx->stream>>>(
-          cv, cat->order, cat->cell_start, g, shifted, kind, yc, scale, pre, accumulate,
-          nt[1], nt[2], ntiles, (double*)mesh.data);
+      const char* env_tile = getenv("TRV_DET_NO_TILE");
+      const bool tile_form = !(env_tile && env_tile[0] == '1')
+        && g.n[0] >= 2 * DT_X + 3 && g.n[1] >= 2 * DT_Y + 3 && g.n[2] >= 2 * DT_Z + 3;
+      if (tile_form) {
+        // Sorted candidate lists per 128-cell tile; the few tiles with too many candidates
+        // go to the merge kernel afterwards.
+        const int bt[3] = {(g.n[0] + DT_X - 1) / DT_X, (g.n[1] + DT_Y - 1) / DT_Y,
+                           (g.n[2] + DT_Z - 1) / DT_Z};
+        const long long nbig = (long long)bt[0] * bt[1] * bt[2];
+        TRVB_REQUIRE(nbig < 2147483647LL, "mesh too large for int tile indices");
+        int* big = nullptr;
+        TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&big, sizeof(int) * (size_t)(nbig + 1)));
+        int* big_count = big + nbig;
+        TRVB_CUDA(cudaMemsetAsync(big_count, 0, sizeof(int), ctx->stream));
+        const int tblocks = (int)div_up(nbig, 4);
+        const int fblocks = ctx->num_sms * 8;
+        if (cplx_mesh) {
+          k_assign_gather_tile<O, true><<<tblocks, 128, 0, ctx->stream>>>(
+            cv, cat->order, cat->cell_start, g, shifted, kind, yc, scale, pre, accumulate,
+            bt[1], bt[2], nbig, big, big_count, (double*)mesh.data);
+          k_assign_gather_warp<O, true><<<fblocks, 128, 0, ctx->stream>>>(
+            cv, cat->order, cat->cell_start, g, shifted, kind, yc, scale, pre, accumulate,
+            nt[1], nt[2], ntiles, big, big_count, bt[1], bt[2], (double*)mesh.data);
+        } else {
+          k_assign_gather_tile<O, false><<<tblocks, 128, 0, ctx->stream>>>(
+            cv, cat->order, cat->cell_start, g, shifted, kind, yc, scale, pre, accumulate,
+            bt[1], bt[2], nbig, big, big_count, (double*)mesh.data);
+          k_assign_gather_warp<O, false><<<fblocks, 128, 0, ctx->stream>>>(
+            cv, cat->order, cat->cell_start, g, shifted, kind, yc, scale, pre, accumulate,
+            nt[1], nt[2], ntiles, big, big_count, bt[1], bt[2], (double*)mesh.data);
+        }
+        TRVB_LAUNCH_CHECK();
+        TRVB_CUDA(trvb_dev_free_raw(ctx, big));
       } else {
-        k_assign_gather_warp<O, false><<<wblocks, 128, 0, ctx->stream>>>(
-          cv, cat->order, cat->cell_start, g, shifted, kind, yc, scale, pre, accumulate,
-          nt[1], nt[2], ntiles, (double*)mesh.data);
+        const int wblocks = (int)std::min<long long>(div_up(ntiles, 4), 1 << 30);
+        if (cplx_mesh) {
+          k_assign_gather_warp<O, true><<<wblocks, 128, 0, ctx->stream>>>(
+            cv, cat->order, cat->cell_start, g, shifted, kind, yc, scale, pre, accumulate,
+            nt[1], nt[2], ntiles, nullptr, nullptr, 0, 0, (double*)mesh.data);
+        } else {
+          k_assign_gather_warp<O, false><<<wblocks, 128, 0, ctx->stream>>>(
+            cv, cat->order, cat->cell_start, g, shifted, kind, yc, scale, pre, accumulate,
+            nt[1], nt[2], ntiles, nullptr, nullptr, 0, 0, (double*)mesh.data);
+        }
       }
     } else if (cplx_mesh) {
       k_assign_gather<ORDER, true><<<blocks, threads, 0, ctx->stream>>>(
