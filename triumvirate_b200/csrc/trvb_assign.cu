@@ -1377,7 +1377,8 @@ k_assign_gather_tile(SortedView c, const int* __restrict__ order,
                      int accumulate, int nt1, int nt2, long long ntiles,
                      int* __restrict__ big_tiles, int* __restrict__ big_count,
                      double* __restrict__ mesh) {
-  constexpr int LO = 2, SPAN = 4;                       // homes q - 2 .. q + 1
+  // homes that reach output index q: q - 2 .. q + 1 (TSC, PCS), q - 1 .. q (NGP, CIC)
+  constexpr int LO = (ORDER >= 3) ? 2 : 1, SPAN = (ORDER >= 3) ? 4 : 2;
   constexpr int UX = DT_X + SPAN - 1, UY = DT_Y + SPAN - 1, UZ = DT_Z + SPAN - 1;
   constexpr int ZPL = 4;                                // cells per lane, consecutive in z
   static_assert(DT_X * DT_Y * (DT_Z / ZPL) == 32, "one lane per column segment");
@@ -1822,59 +1823,57 @@ int launch_assign(trvb_ctx* ctx, trvb_cat* cat, int kind, int L, int M, double s
     const double pre = density_units ? 1. / g.vol_cell : 1.;   // S/field.cpp:996
     const int threads = 128;
     const int blocks = div_up(g.nmesh, threads);
-    // Warp-cooperative merge for the wide stencils; the union of home cells of a
-    // tile (plus the overhang of a partial tile) must not wrap onto itself.
+    // Tile form (sorted candidate lists) for every scheme, warp-cooperative merge for the
+    // wide stencils on smaller meshes; the union of home cells of a tile (plus the overhang
+    // of a partial tile) must not wrap onto itself.
+    const char* env_tile = getenv("TRV_DET_NO_TILE");
+    const bool tile_form = !(env_tile && env_tile[0] == '1')
+      && g.n[0] >= 2 * DT_X + 3 && g.n[1] >= 2 * DT_Y + 3 && g.n[2] >= 2 * DT_Z + 3;
     const bool warp_form = ORDER >= 3
       && g.n[0] >= 2 * GT_X + 3 && g.n[1] >= 2 * GT_Y + 3 && g.n[2] >= 2 * GT_Z + 3;
-    if (warp_form) {
-      constexpr int O = ORDER >= 3 ? ORDER : 3;
-      const int nt[3] = {(g.n[0] + GT_X - 1) / GT_X, (g.n[1] + GT_Y - 1) / GT_Y,
-                         (g.n[2] + GT_Z - 1) / GT_Z};
-      const long long ntiles = (long long)nt[0] * nt[1] * nt[2];
-      const char* env_tile = getenv("TRV_DET_NO_TILE");
-      const bool tile_form = !(env_tile && env_tile[0] == '1')
-        && g.n[0] >= 2 * DT_X + 3 && g.n[1] >= 2 * DT_Y + 3 && g.n[2] >= 2 * DT_Z + 3;
-      if (tile_form) {
-        // Sorted candidate lists per 128-cell tile; the few tiles with too many candidates
-        // go to the merge kernel afterwards.
-        const int bt[3] = {(g.n[0] + DT_X - 1) / DT_X, (g.n[1] + DT_Y - 1) / DT_Y,
-                           (g.n[2] + DT_Z - 1) / DT_Z};
-        const long long nbig = (long long)bt[0] * bt[1] * bt[2];
-        TRVB_REQUIRE(nbig < 2147483647LL, "mesh too large for int tile indices");
-        int* big = nullptr;
-        TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&big, sizeof(int) * (size_t)(nbig + 1)));
-        int* big_count = big + nbig;
-        TRVB_CUDA(cudaMemsetAsync(big_count, 0, sizeof(int), ctx->stream));
-        const int tblocks = (int)div_up(nbig, 4);
-        const int fblocks = ctx->num_sms * 8;
-        if (cplx_mesh) {
-          k_assign_gather_tile<O, true><<<tblocks, 128, 0, ctx->stream>>>(
-            cv, cat->order, cat->cell_start, g, shifted, kind, yc, scale, pre, accumulate,
-            bt[1], bt[2], nbig, big, big_count, (double*)mesh.data);
-          k_assign_gather_warp<O, true><<<fblocks, 128, 0, ctx->stream>>>(
-            cv, cat->order, cat->cell_start, g, shifted, kind, yc, scale, pre, accumulate,
-            nt[1], nt[2], ntiles, big, big_count, bt[1], bt[2], (double*)mesh.data);
-        } else {
-          k_assign_gather_tile<O, false><<<tblocks, 128, 0, ctx->stream>>>(
-            cv, cat->order, cat->cell_start, g, shifted, kind, yc, scale, pre, accumulate,
-            bt[1], bt[2], nbig, big, big_count, (double*)mesh.data);
-          k_assign_gather_warp<O, false><<<fblocks, 128, 0, ctx->stream>>>(
-            cv, cat->order, cat->cell_start, g, shifted, kind, yc, scale, pre, accumulate,
-            nt[1], nt[2], ntiles, big, big_count, bt[1], bt[2], (double*)mesh.data);
-        }
-        TRVB_LAUNCH_CHECK();
-        TRVB_CUDA(trvb_dev_free_raw(ctx, big));
+    const int nt[3] = {(g.n[0] + GT_X - 1) / GT_X, (g.n[1] + GT_Y - 1) / GT_Y,
+                       (g.n[2] + GT_Z - 1) / GT_Z};
+    const long long ntiles = (long long)nt[0] * nt[1] * nt[2];
+    if (tile_form) {
+      // Sorted candidate lists per 128-cell tile; the few tiles with too many candidates
+      // go to the merge kernel afterwards.
+      const int bt[3] = {(g.n[0] + DT_X - 1) / DT_X, (g.n[1] + DT_Y - 1) / DT_Y,
+                         (g.n[2] + DT_Z - 1) / DT_Z};
+      const long long nbig = (long long)bt[0] * bt[1] * bt[2];
+      TRVB_REQUIRE(nbig < 2147483647LL, "mesh too large for int tile indices");
+      int* big = nullptr;
+      TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&big, sizeof(int) * (size_t)(nbig + 1)));
+      int* big_count = big + nbig;
+      TRVB_CUDA(cudaMemsetAsync(big_count, 0, sizeof(int), ctx->stream));
+      const int tblocks = (int)div_up(nbig, 4);
+      const int fblocks = ctx->num_sms * 8;
+      if (cplx_mesh) {
+        k_assign_gather_tile<ORDER, true><<<tblocks, 128, 0, ctx->stream>>>(
+          cv, cat->order, cat->cell_start, g, shifted, kind, yc, scale, pre, accumulate,
+          bt[1], bt[2], nbig, big, big_count, (double*)mesh.data);
+        k_assign_gather_warp<ORDER, true><<<fblocks, 128, 0, ctx->stream>>>(
+          cv, cat->order, cat->cell_start, g, shifted, kind, yc, scale, pre, accumulate,
+          nt[1], nt[2], ntiles, big, big_count, bt[1], bt[2], (double*)mesh.data);
       } else {
-        const int wblocks = (int)std::min<long long>(div_up(ntiles, 4), 1 << 30);
-        if (cplx_mesh) {
-          k_assign_gather_warp<O, true><<<wblocks, 128, 0, ctx->stream>>>(
-            cv, cat->order, cat->cell_start, g, shifted, kind, yc, scale, pre, accumulate,
-            nt[1], nt[2], ntiles, nullptr, nullptr, 0, 0, (double*)mesh.data);
-        } else {
-          k_assign_gather_warp<O, false><<<wblocks, 128, 0, ctx->stream>>>(
-            cv, cat->order, cat->cell_start, g, shifted, kind, yc, scale, pre, accumulate,
-            nt[1], nt[2], ntiles, nullptr, nullptr, 0, 0, (double*)mesh.data);
-        }
+        k_assign_gather_tile<ORDER, false><<<tblocks, 128, 0, ctx->stream>>>(
+          cv, cat->order, cat->cell_start, g, shifted, kind, yc, scale, pre, accumulate,
+          bt[1], bt[2], nbig, big, big_count, (double*)mesh.data);
+        k_assign_gather_warp<ORDER, false><<<fblocks, 128, 0, ctx->stream>>>(
+          cv, cat->order, cat->cell_start, g, shifted, kind, yc, scale, pre, accumulate,
+          nt[1], nt[2], ntiles, big, big_count, bt[1], bt[2], (double*)mesh.data);
+      }
+      TRVB_LAUNCH_CHECK();
+      TRVB_CUDA(trvb_dev_free_raw(ctx, big));
+    } else if (warp_form) {
+      const int wblocks = (int)std::min<long long>(div_up(ntiles, 4), 1 << 30);
+      if (cplx_mesh) {
+        k_assign_gather_warp<ORDER, true><<<wblocks, 128, 0, ctx->stream>>>(
+          cv, cat->order, cat->cell_start, g, shifted, kind, yc, scale, pre, accumulate,
+          nt[1], nt[2], ntiles, nullptr, nullptr, 0, 0, (double*)mesh.data);
+      } else {
+        k_assign_gather_warp<ORDER, false><<<wblocks, 128, 0, ctx->stream>>>(
+          cv, cat->order, cat->cell_start, g, shifted, kind, yc, scale, pre, accumulate,
+          nt[1], nt[2], ntiles, nullptr, nullptr, 0, 0, (double*)mesh.data);
       }
     } else if (cplx_mesh) {
       k_assign_gather<ORDER, true><<<blocks, threads, 0, ctx->stream>>>(
