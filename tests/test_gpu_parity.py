@@ -968,3 +968,24 @@ def test_pruned_shell_transform_equals_dense(core, monkeypatch):
             assert err < 1.e-12, (ng, groups, err)
             assert np.array_equal(pruned["nmodes_1"], dense["nmodes_1"])
         monkeypatch.delenv("TRV_SHELL_GROUPS", raising=False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("form", ["full", "row", "diag"])
+def test_radial_shot_noise_reduction_on_tensor_cores(core, monkeypatch, form):
+    """Box B_000 shot noise, throughput mode: sum_q j_0(k_a r_q) j_0(k_b r_q) H(q) for all
+    pairs as a real Gram product on k_gram_dmma (j_0 rows generated once per distinct
+    wavenumber) against the spline-in-the-loop reduction it replaced; one list on both sides
+    (full, diag) and two lists (row)."""
+    gen = np.random.default_rng(777)
+    L, ng = 1000., 128
+    pos = gen.uniform(0., L, size=(3, 200000))
+    kw = dict(boxsize=L, ngrid=ng, assignment="tsc", degrees=(0, 0, 0), form=form, idx_bin=3,
+              bin_range=(0.01, 0.1), num_bins=9, norm_factor=1., pos_d=pos)
+    monkeypatch.setenv("TRV_SHOT_NO_DMMA", "1")
+    old = core.threept("bispec", "sim", **kw)
+    monkeypatch.delenv("TRV_SHOT_NO_DMMA")
+    new = core.threept("bispec", "sim", **kw)
+    scale = np.max(np.abs(old["bk_shot"]))
+    assert np.max(np.abs(new["bk_shot"] - old["bk_shot"])) < 1.e-12 * scale
+    assert np.max(np.abs(new["bk_raw"] - old["bk_raw"])) < 1.e-12 * np.max(np.abs(old["bk_raw"]))

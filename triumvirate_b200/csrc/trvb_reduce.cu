@@ -1456,6 +1456,34 @@ extern "C" int trvb_gram_reduce(trvb_ctx* ctx, const void* const* A, int na,
 }
 
 namespace {
+
+// The radial form of the shot-noise reduction as a real Gram product: rows
+// F[f][q] = j_l(k_f r_q) for every distinct wavenumber and H[q] = Re hist[q], padded to an
+// even number of radii; sum_q F_a F_b H for all pairs then runs on k_gram_dmma.  Empty
+// radii (H = 0: most integers are not a small sum of three squares of mesh offsets ... or
+// lie outside the mesh) are skipped: their products vanish whatever j_l is.
+__global__ void __launch_bounds__(256)
+k_radial_fields(const double2* __restrict__ hist, long long nq, long long pitch, double dr,
+                SjlView sja, SjlView sjb, const double* __restrict__ ka, int na,
+                const double* __restrict__ kb, int nb /* 0: the b rows are the a rows */,
+                double* __restrict__ F /* [na + nb + 1][pitch], H last */) {
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < pitch;
+       q += (long long)gridDim.x * blockDim.x) {
+    const double h = q < nq ? hist[q].x : 0.;
+    F[(long long)(na + nb) * pitch + q] = h;
+    if (h == 0.) {
+      for (int f = 0; f < na + nb; f++) F[(long long)f * pitch + q] = 0.;
+      continue;
+    }
+    const double r = __dmul_rn(sqrt((double)q), dr);
+    for (int f = 0; f < na; f++) F[(long long)f * pitch + q] = sjl_eval(sja, ka[f] * r);
+    for (int f = 0; f < nb; f++) F[(long long)(na + f) * pitch + q] = sjl_eval(sjb, kb[f] * r);
+  }
+}
+
+}  // namespace
+
+namespace {
 int shot_bispec_reduce_impl(trvb_ctx* ctx, trvb_mesh xi, int slab_x0, int slab_nx,
                             trvb_comm* comm, int la, int ma, int lb, int mb, const double* ka,
                             const double* kb, int npairs, double* out);
@@ -1550,10 +1578,34 @@ int shot_bispec_reduce_impl(trvb_ctx* ctx, trvb_mesh xi, int slab_x0, int slab_n
       }
       TRVB_LAUNCH_CHECK();
     }
-    RadialLoader ld;
-    ld.hist = (const double2*)d_hist; ld.dr = g.dr[0];
-    ld.sja = sja; ld.sjb = sjb; ld.ka = d_k; ld.kb = d_k + ua.size();
-    st = run_gram(ctx, ld, (int)ua.size(), (int)ub.size(), nq, ia.data(), ib.data(), npairs, out);
+    const char* env_rd = getenv("TRV_SHOT_NO_DMMA");
+    if (la == 0 && lb == 0 && !xv.cplx && !(env_rd && env_rd[0] == '1')) {
+      // real histogram, real j_0: the pair sums are a real Gram product -> tensor cores
+      const int na_u = (int)ua.size();
+      const bool same = ua == ub;
+      const int nb_u = same ? 0 : (int)ub.size();
+      const long long pitch = (nq + 1) / 2 * 2;
+      double* F = nullptr; const double** d_rows = nullptr;
+      TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&F, sizeof(double) * (size_t)pitch * (na_u + nb_u + 1)));
+      TRVB_CUDA(trvb_dev_alloc_raw(ctx, (void**)&d_rows, sizeof(void*) * (size_t)(na_u + nb_u)));
+      std::vector<const double*> h_rows(na_u + nb_u);
+      for (int f = 0; f < na_u + nb_u; f++) h_rows[f] = F + (size_t)f * pitch;
+      TRVB_CUDA(cudaMemcpyAsync(d_rows, h_rows.data(), sizeof(void*) * h_rows.size(),
+                                cudaMemcpyHostToDevice, ctx->stream));
+      const int blocks = (int)std::min<long long>((pitch + 255) / 256, (long long)ctx->num_sms * 16);
+      k_radial_fields<<<blocks, 256, 0, ctx->stream>>>((const double2*)d_hist, nq, pitch, g.dr[0],
+                                                       sja, sjb, d_k, na_u, d_k + ua.size(), nb_u, F);
+      TRVB_LAUNCH_CHECK();
+      st = run_gram_dmma(ctx, d_rows, same ? d_rows : d_rows + na_u, F + (size_t)(na_u + nb_u) * pitch,
+                         na_u, (int)ub.size(), pitch, ia.data(), ib.data(), npairs, out, same);
+      trvb_dev_free_raw(ctx, F);
+      trvb_dev_free_raw(ctx, d_rows);
+    } else {
+      RadialLoader ld;
+      ld.hist = (const double2*)d_hist; ld.dr = g.dr[0];
+      ld.sja = sja; ld.sjb = sjb; ld.ka = d_k; ld.kb = d_k + ua.size();
+      st = run_gram(ctx, ld, (int)ua.size(), (int)ub.size(), nq, ia.data(), ib.data(), npairs, out);
+    }
     trvb_dev_free_raw(ctx, d_hist);
   } else {
     ShotLoader ld;
