@@ -439,6 +439,7 @@ def run_b200(args):
                      f"pairs/{world}gpu, replicated mesh, all-reduce inside the C API (NCCL)")
                     if world > 1 else "1gpu"),
                 "distributed_mesh_calls": core.dmesh_call_count(),
+                "fused_mesh_calls": core.fused_mesh_call_count(),
                 "e2e_upload": ("1/N slice per rank from pinned host memory + NCCL all-gather"
                                if world > 1 else "pinned host -> device")},
         "clocks": clocks,
@@ -466,6 +467,8 @@ def run_b200(args):
 
     if rank == 0:
         result["roofline"], result["particles_per_s"] = assignment_roofline(torch, dev, dpos, wl)
+        if world == 1 and core.fused_mesh_call_count() > 0:
+            result["roofline_xpass"] = xpass_roofline(core, step, dpos, wl)
         if world == 1 and not args.no_cpu_baseline:
             base, check = cpu_baseline(wl, pos, out, out_e2e)
             result["cpu_baseline"] = base
@@ -601,6 +604,36 @@ def assignment_roofline(torch, dev, dpos, wl):
             "with_sort": {"launch_seconds": t_sorted, "achieved": alg_bytes / t_sorted / 1.e9,
                           "frac": alg_bytes / t_sorted / 1.e9 / peak}}
     return roof, n / t_sorted
+
+
+def xpass_roofline(core, step, dpos, wl):
+    """The second hand-written full-grid kernel of the call, k_xpass_fused (forward FFT along
+    x + low-|k| modes + shot-noise spectrum + inverse FFT along x, in place on the half
+    spectrum), timed with CUDA events on the estimator's stream inside one extra estimator
+    call (TRV_XPASS_TRACE=1; outside every timed region).  Algorithmic bytes per launch = one
+    read + one write of the half spectrum, 2 x 16 B x n0 n1 (n2/2+1)."""
+    from triumvirate_b200 import _lib
+    tb = _lib.trvb()
+    ng = wl["ngrid"]
+    os.environ["TRV_XPASS_TRACE"] = "1"
+    try:
+        ms = np.zeros((5, 3))
+        for r in range(5):
+            step(dpos, True)
+            buf = (C.c_double * 3)()
+            tb.trvb_box_fields_fused_last_ms(buf)
+            ms[r] = buf[:]
+    finally:
+        del os.environ["TRV_XPASS_TRACE"]
+    d2z, kern, z2d = np.median(ms, axis=0)
+    alg_bytes = 2. * 16. * ng * ng * (ng // 2 + 1)
+    peak, how = measured_peaks()
+    achieved = alg_bytes / (kern * 1.e-3) / 1.e9
+    return {"bound": "hbm", "kernel": "k_xpass_fused<%d> (+ 24 MB low-|k| zero-fill)" % ng,
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "peak_source": how, "algorithmic_bytes_per_launch": alg_bytes,
+            "launch_seconds": kern * 1.e-3,
+            "cufft_2d_d2z_seconds": d2z * 1.e-3, "cufft_2d_z2d_seconds": z2d * 1.e-3}
 
 
 PARITY_TOL = 1.e-8   # BASELINE.json: relative tolerance against the reference's CPU code

@@ -155,6 +155,9 @@ void trv_comm_finalize(void);
 int trv_multi_device_count(const int* ngrid);
 /* Estimator calls of this process that ran the distributed mesh phase (trvb_dmesh_*). */
 long long trv_dmesh_call_count(void);
+/* Estimator calls of this process whose mesh phase ran with the fused x pass
+ * (trvb_box_fields_fused: one GPU, box bispectrum, throughput mode). */
+long long trv_fused_mesh_call_count(void);
 
 /* cudaStream_t of the most recently used estimator context (NULL before the
  * first call). */

@@ -403,6 +403,27 @@ int trvb_shot_bispec_reduce_slab(trvb_ctx* ctx, const double* xi_planes, int x0,
                                  trvb_comm* comm, int la, int ma, int lb, int mb,
                                  const double* ka, const double* kb, int npairs, double* out);
 
+/* ---- box mesh phase on one GPU, x passes fused (csrc/trvb_xpass.cu) -----------
+ * For the periodic-box bispectrum the full-grid spectrum delta n(k) is read twice and
+ * never again: for the low-|k| modes the pair phase works on (the grid of `sub`) and for
+ * xi(r) = IFFT[(fa conj(fb) / C1 - S) / V] of the shot noise (S/threept.cpp:1554-1558,
+ * S/field.cpp:1496-1655, 3273-3345).  This call does both from the REAL mesh `x`:
+ * 2-D D2Z of the x-planes (cuFFT), ONE hand-written pass over the columns along x
+ * (forward FFT, low-|k| modes stored to `lowk`, spectrum, inverse FFT, in place), 2-D Z2D
+ * of the planes into `xi`.  fa = FFT[x] + add_a delta_k0, fb = FFT[x] + add_b delta_k0;
+ * `lowk` (HALF, sub's extents) receives fa and is registered as the context's low-|k|
+ * view exactly as trvb_dmesh_gather_lowk does, until trvb_ctx_forget_lowk.  Throughput
+ * mode only (the deterministic mode keeps the 3-D cuFFT transforms); n0 must be a power
+ * of two in 32 .. 2048 (trvb_box_fields_fused_supported). */
+int trvb_box_fields_fused_supported(const trvb_ctx* ctx);
+int trvb_box_fields_fused(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh x, double add_a, double add_b,
+                          const double S[2], trvb_mesh lowk, trvb_mesh xi);
+void trvb_ctx_forget_lowk(trvb_ctx* ctx);
+long long trvb_box_fields_fused_call_count(void);   /* calls of this process */
+/* With TRV_XPASS_TRACE=1 in the environment: CUDA-event times (ms) of the last call's 2-D
+ * D2Z, x pass (k_xpass_fused) and 2-D Z2D. */
+void trvb_box_fields_fused_last_ms(double out[3]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -989,3 +989,32 @@ def test_radial_shot_noise_reduction_on_tensor_cores(core, monkeypatch, form):
     scale = np.max(np.abs(old["bk_shot"]))
     assert np.max(np.abs(new["bk_shot"] - old["bk_shot"])) < 1.e-12 * scale
     assert np.max(np.abs(new["bk_raw"] - old["bk_raw"])) < 1.e-12 * np.max(np.abs(old["bk_raw"]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ng,scheme,form", [(64, "pcs", "full"), (128, "tsc", "diag"),
+                                            (64, "cic", "full"), (256, "pcs", "row")])
+def test_fused_x_pass_mesh_phase_equals_3d_transforms(core, monkeypatch, ng, scheme, form):
+    """Box B_000 on one GPU, throughput mode: 2-D cuFFT of the planes + k_xpass_fused
+    (forward FFT along x, low-|k| modes, shot-noise spectrum, inverse FFT along x in one
+    pass; csrc/trvb_xpass.cu) against the 3-D cuFFT transforms with the separate spectrum
+    kernel they replace (S/field.cpp:1496-1655, 3273-3345).  Same catalogue, same kernels
+    downstream: equal to round-off."""
+    gen = np.random.default_rng(ng)
+    L = 1000.
+    pos = gen.uniform(0., L, size=(3, 40000))
+    kmax = 0.05
+    kw = dict(boxsize=L, ngrid=ng, assignment=scheme, degrees=(0, 0, 0), form=form, idx_bin=2,
+              bin_range=(0.005, kmax), num_bins=6, norm_factor=1., pos_d=pos)
+    monkeypatch.setenv("TRV_NO_FUSED_X", "1")
+    before = core.fused_mesh_call_count()
+    old = core.threept("bispec", "sim", **kw)
+    assert core.fused_mesh_call_count() == before
+    monkeypatch.delenv("TRV_NO_FUSED_X")
+    new = core.threept("bispec", "sim", **kw)
+    assert core.fused_mesh_call_count() == before + 1, "the fused mesh phase did not run"
+    for key in ("bk_raw", "bk_shot"):
+        scale = np.max(np.abs(old[key]))
+        assert np.max(np.abs(new[key] - old[key])) < 1.e-11 * scale, key
+    assert np.array_equal(new["nmodes_1"], old["nmodes_1"])
+    assert np.array_equal(new["k1_eff"], old["k1_eff"])

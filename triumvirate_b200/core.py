@@ -361,6 +361,13 @@ def dmesh_call_count():
     return int(fn())
 
 
+def fused_mesh_call_count():
+    """Estimator calls of this process whose mesh phase ran with the fused x pass."""
+    fn = _trv().trv_fused_mesh_call_count
+    fn.restype = C.c_longlong
+    return int(fn())
+
+
 def release_contexts():
     """Drop the cached device contexts (cuFFT plans, tables) and hand the arena's
     cached blocks back to the driver."""

@@ -355,6 +355,7 @@ int trv_allreduce(double* buf, long long n) {
 void trv_comm_finalize(void) { trv::dev::comm_finalize(); }
 
 long long trv_dmesh_call_count(void) { return trvb_dmesh_call_count(); }
+long long trv_fused_mesh_call_count(void) { return trvb_box_fields_fused_call_count(); }
 
 int trv_multi_device_count(const int* ngrid) {
   trv::ParameterSet p;

@@ -371,7 +371,40 @@ class Engine {
     return k;
   }
   trvb_dmesh* dmesh() { return dmesh_; }
-  ~Engine() { if (dmesh_) trvb_dmesh_forget_lowk(dmesh_); }
+  ~Engine() {
+    if (dmesh_) trvb_dmesh_forget_lowk(dmesh_);
+    if (fused_lowk_) trvb_ctx_forget_lowk(c_);
+  }
+
+  /// Box catalogue on one GPU, throughput mode (trvb_box_fields_fused): delta n(k) is
+  /// needed for two things only -- the modes that the grid of `sub` represents and the
+  /// shot-noise xi(r) of S/threept.cpp:1977-2110 -- so the x passes of the forward and
+  /// the inverse full-grid transform are fused around the spectrum arithmetic and the
+  /// full-grid delta n(k) is never stored.  Returns the low-|k| modes as a HALF mesh of
+  /// sub's extents (read as a view of the full-grid spectrum, like the distributed
+  /// mesh's) and fills `xi` (REAL, full grid).
+  dev::Mesh density_fluctuation_fused(trvb_ctx* sub, dev::Mesh& xi) {
+    dev::Mesh x(ctx_, c_, TRVB_REAL);
+    if (!data_) {
+      trvb_cat* cat = nullptr;
+      dev::check(trvb_cat_create_assign(c_, &cat, ndata_, host_x_, host_y_, host_z_, 1., x.view()),
+                 "trvb_cat_create_assign");
+      data_.reset(new dev::Catalogue(ctx_, cat));
+    } else {
+      assign(*data_, TRVB_W_UNIT, 0, 0, 1., false, x);
+    }
+    dev::Mesh k(ctx_, sub, TRVB_HALF);
+    xi = dev::Mesh(ctx_, c_, TRVB_REAL);
+    // fa = delta n (mean subtracted: FFT[nbar dV] = N delta_k0), fb = N_00 (not subtracted);
+    // S = N (S/threept.cpp:1977-1979)
+    const double S[2] = {double(ndata_), 0.};
+    dev::check(trvb_box_fields_fused(c_, sub, x.view(), -double(ndata_), 0., S, k.view(), xi.view()),
+               "trvb_box_fields_fused");
+    fused_lowk_ = true;
+    trvs::count_fft += 1;
+    trvs::count_ifft += 1;
+    return k;
+  }
 
   /// N_LM(k): conj(y_LM) w^2 for data plus alpha^2 x randoms
   /// (S/field.cpp:1364-1447); box: unit weights, no mean subtraction.
@@ -452,6 +485,7 @@ class Engine {
   const double* host_y_ = nullptr;
   const double* host_z_ = nullptr;
   trvb_dmesh* dmesh_ = nullptr;      // owned by the context
+  bool fused_lowk_ = false;          // the context's low-|k| view points at one of our meshes
 };
 
 /// `count` consecutive meshes of one grid in a single device allocation (the
@@ -883,9 +917,23 @@ trv::BispecMeasurements bispec_impl(
     sub = raw;
   }
 
+  // One GPU holding the whole job (box, throughput mode, real shell fields on a true
+  // sub-grid): the mesh phase with the x passes of both full-grid transforms fused around
+  // the shot-noise spectrum (trvb_box_fields_fused); xi(r) comes out of the same call.
+  // TRV_NO_FUSED_X=1: 3-D cuFFT transforms + separate spectrum kernel.
+  bool fused_x = !survey && !dist_mesh && coarse && !params.deterministic
+    && share.any_pairs && share.any_shot && params.ell1 == 0 && params.ell2 == 0
+    && params.ELL == 0 && trvb_box_fields_fused_supported(c);
+  {
+    const char* env = std::getenv("TRV_NO_FUSED_X");
+    if (env != nullptr && env[0] == '1') fused_x = false;
+  }
+  dev::Mesh xi_fused;
+
   // Common fields: delta n_00(k) and N_00(k).
   dev::Mesh dn_00 = dist_mesh ? eng.density_fluctuation_dist(comm, sub)
-                              : eng.density_fluctuation(0, 0);
+    : fused_x ? eng.density_fluctuation_fused(sub, xi_fused)
+    : eng.density_fluctuation(0, 0);
   dev::Mesh N_00_own;
   if (survey && share.any_shot) N_00_own = eng.quadratic_field(0, 0);   // shot noise only
   const trvb_mesh N_00 = (survey && share.any_shot)
@@ -956,6 +1004,7 @@ trv::BispecMeasurements bispec_impl(
   const long long params_ndata = eng.ndata();
   dev::Mesh G;              // G_LM(x) on the sub-grid
   int G_M = 0; bool have_G = false, have_xi = false, G_on_slab = false;
+  if (fused_x) { xi = std::move(xi_fused); have_xi = true; }
   dev::Mesh dn_LM;          // survey: delta n_LM(k) of the current M
   dev::Mesh N_LM;
   cdouble Sbar_LM = 0.;
