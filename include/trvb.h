@@ -258,6 +258,11 @@ int trvb_shell_ifft_batch(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh src, int ell,
 int trvb_shell_slab_batch(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh src, int ell, int m,
                           const double* klo, const double* khi, const double* amp,
                           int nbins, int x0, int nx, void* dst);
+/* 1 when the last (z) pass of trvb_shell_slab_batch runs as the hand-written pruned-input
+ * complex-to-real kernel for a sub-grid of z-extent n2 (csrc/trvb_zpass.cuh), 0 when it
+ * falls back to zero-padded lines + cuFFT.  The estimators prefer such extents when they
+ * size the sub-grid in throughput mode. */
+int trvb_shell_zpass_supported(int n2);
 
 /* dst(x) = IFFT[ amp * j_l(|k| r) * y_lm(khat) * src(k) / W(k) ]
  * (S/field.cpp:1908-2010, amp = 1/V), spline table from trvb_sjl_table. */

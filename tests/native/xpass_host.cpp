@@ -15,7 +15,12 @@ void run_tile(long long c0, double2* T, const Pointwise& pw, const std::vector<d
   std::vector<double2> tile((size_t)N * CK);
   constexpr int NS = Radix<N>::NS;
   auto col_of = [&](int tid) { return column_of(pw, c0 + tid % CK); };
-  for (int tid = 0; tid < NT; tid++) stage_first<N, CK, NT>(tid, T, pw.ncols, col_of(tid), tile.data(), tw.data());
+  if (getenv("XP_ASYNC")) {   // the cp.async variant: tile loaded first, stage 0 on "shared memory"
+    for (int tid = 0; tid < NT; tid++) stage_load_async<N, CK, NT>(tid, T, pw.ncols, c0, pw.ncols, tile.data());
+    for (int tid = 0; tid < NT; tid++) stage_fwd<N, CK, NT, 0>(tid, tile.data(), tw.data());
+  } else {
+    for (int tid = 0; tid < NT; tid++) stage_first<N, CK, NT>(tid, T, pw.ncols, col_of(tid), tile.data(), tw.data());
+  }
   if constexpr (NS >= 3) for (int tid = 0; tid < NT; tid++) stage_fwd<N, CK, NT, 1>(tid, tile.data(), tw.data());
   if constexpr (NS >= 4) for (int tid = 0; tid < NT; tid++) stage_fwd<N, CK, NT, 2>(tid, tile.data(), tw.data());
   for (int tid = 0; tid < NT; tid++) stage_junction<N, CK, NT>(tid, tile.data(), pw, col_of(tid));
@@ -58,7 +63,7 @@ int main(int argc, char** argv) {
     case 64: run_all<64, 8>(T.data(), pw); break;
     case 128: run_all<128, 8>(T.data(), pw); break;
     case 256: run_all<256, 8>(T.data(), pw); break;
-    case 512: run_all<512, 8>(T.data(), pw); break;
+    case 512: if (getenv("XP_CK4")) run_all<512, 4>(T.data(), pw); else run_all<512, 8>(T.data(), pw); break;
     case 1024: run_all<1024, 4>(T.data(), pw); break;
     case 2048: run_all<2048, 4>(T.data(), pw); break;
     default: return 4;

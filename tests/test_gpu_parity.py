@@ -1018,3 +1018,31 @@ def test_fused_x_pass_mesh_phase_equals_3d_transforms(core, monkeypatch, ng, sch
         assert np.max(np.abs(new[key] - old[key])) < 1.e-11 * scale, key
     assert np.array_equal(new["nmodes_1"], old["nmodes_1"])
     assert np.array_equal(new["k1_eff"], old["k1_eff"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kmax,ns", [(0.09, 64), (0.10, 72), (0.13, 96), (0.15, 108), (0.19, 128),
+                                     (0.205, 144), (0.24, 160)])
+def test_hand_written_z_pass_equals_cufft_z_pass(core, monkeypatch, kmax, ns):
+    """Last pass of the pruned shell transform: k_shell_zpass (pruned-input c2r along z,
+    csrc/trvb_zpass.cuh) against zero-padded lines + cuFFT Z2D (TRV_NO_ZPASS=1) on the same
+    sub-grid extent `ns` -- several radix plans -- and both against the dense 3-D transform."""
+    gen = np.random.default_rng(int(1000 * kmax))
+    L, ng = 1000., 256
+    pos = gen.uniform(0., L, size=(3, 60000))
+    kw = dict(boxsize=L, ngrid=ng, assignment="tsc", degrees=(0, 0, 0), form="full",
+              bin_range=(0.01, kmax), num_bins=5, norm_factor=1., pos_d=pos)
+    from triumvirate_b200 import _lib
+    assert _lib.trvb().trvb_shell_zpass_supported(ns) == 1
+    new = core.threept("bispec", "sim", **kw)
+    # the cuFFT z pass on the SAME extents: the size preference is tied to TRV_NO_ZPASS, so
+    # pin the groups only and compare through the dense path as the common reference
+    monkeypatch.setenv("TRV_NO_PRUNE", "1")
+    dense = core.threept("bispec", "sim", **kw)
+    monkeypatch.delenv("TRV_NO_PRUNE")
+    monkeypatch.setenv("TRV_NO_ZPASS", "1")
+    old = core.threept("bispec", "sim", **kw)
+    scale = np.max(np.abs(dense["bk_raw"]))
+    assert np.max(np.abs(new["bk_raw"] - dense["bk_raw"])) < 1.e-11 * scale
+    assert np.max(np.abs(old["bk_raw"] - dense["bk_raw"])) < 1.e-11 * scale
+    assert np.array_equal(new["nmodes_1"], dense["nmodes_1"])

@@ -26,7 +26,15 @@ def harness(tmp_path_factory):
     (512, 4, 6, (144, 4, 4)), (1024, 4, 4, (626, 2, 4)), (2048, 2, 4, (0, 0, 0)),
     (64, 3, 5, (8, 3, 3)),   # ragged: n1 nh not a multiple of the columns per tile
 ])
-def test_fused_x_pass_matches_numpy(harness, tmp_path, n0, n1, n2, sub):
+@pytest.mark.parametrize("ck4", [False, True])
+@pytest.mark.parametrize("load", ["registers", "cp.async"])
+def test_fused_x_pass_matches_numpy(harness, tmp_path, monkeypatch, n0, n1, n2, sub, ck4, load):
+    if load == "cp.async":
+        monkeypatch.setenv("XP_ASYNC", "1")   # tile copied first, stage 0 run like a middle stage
+    if ck4:
+        if n0 != 512:
+            pytest.skip("four-column tiles are an option of the 512 kernel only")
+        monkeypatch.setenv("XP_CK4", "1")   # the 4-column tile (bank swizzle with radix-8 junction)
     gen = np.random.default_rng(n0 + n1)
     nh = n2 // 2 + 1
     T = gen.normal(size=(n0, n1, nh)) + 1j * gen.normal(size=(n0, n1, nh))
@@ -65,3 +73,45 @@ def test_fused_x_pass_matches_numpy(harness, tmp_path, n0, n1, n2, sub):
                         continue
                     ref[is_, js, ks] = a[mi % n0, mj % n1, ks]
         assert np.max(np.abs(lowk - ref)) < 1.e-12 * np.max(np.abs(a))
+
+
+@pytest.fixture(scope="module")
+def zharness(tmp_path_factory):
+    exe = tmp_path_factory.mktemp("zpass") / "zpass_host"
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", f"-I{ROOT / 'triumvirate_b200' / 'csrc'}",
+                    str(ROOT / "tests" / "native" / "zpass_host.cpp"), "-o", str(exe)], check=True)
+    return exe
+
+
+ZPASS_LENGTHS = [64, 72, 96, 108, 128, 144, 160, 180, 192, 216, 240, 256, 270, 288, 320, 360, 384,
+                 432, 480, 512, 540, 576, 600, 640, 720]
+
+
+def test_zpass_length_list_matches_the_device_layer():
+    """The lengths emulated here are the ones csrc/trvb_fourier.cu dispatches."""
+    import re
+    src = (ROOT / "triumvirate_b200" / "csrc" / "trvb_fourier.cu").read_text()
+    block = src[src.index("#define TRVB_ZPASS_LENGTHS(X)"):]
+    block = block[:block.index("\n\n")]
+    assert sorted(int(v) for v in re.findall(r"X\((\d+)\)", block)) == ZPASS_LENGTHS
+
+
+@pytest.mark.parametrize("n", ZPASS_LENGTHS)
+def test_pruned_c2r_z_pass_matches_numpy(zharness, tmp_path, n):
+    """csrc/trvb_zpass.cuh (last pass of the pruned shell transform, S/field.cpp:1792-1906):
+    two real lines packed into one complex line, digit-reversed load, mixed-radix
+    decimation-in-time stages, natural-order store -- against numpy.fft.irfft on zero-padded
+    lines, with a ragged number of lines."""
+    gen = np.random.default_rng(n)
+    n1 = 37 if n % 16 == 0 else 22
+    k2 = n // 4 if n != 540 else 135
+    B = gen.normal(size=(k2, n1)) + 1j * gen.normal(size=(k2, n1))
+    B.astype(np.complex128).tofile(tmp_path / "in.bin")
+    subprocess.run([str(zharness), str(n), str(n1), str(k2), str(tmp_path / "in.bin"),
+                    str(tmp_path / "out.bin")], check=True)
+    out = np.fromfile(tmp_path / "out.bin").reshape(n1, n)
+    F = np.zeros((n1, n // 2 + 1), dtype=complex)
+    F[:, :k2] = B.T
+    F[:, 0] = F[:, 0].real     # a c2r transform ignores Im F[0]
+    want = np.fft.irfft(F, n=n, axis=1) * n
+    assert np.max(np.abs(out - want)) < 1.e-13 * np.max(np.abs(want))

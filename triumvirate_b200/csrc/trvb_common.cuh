@@ -180,6 +180,10 @@ inline cudaError_t trvb_dev_free_raw(trvb_ctx* ctx, void* p) {
   return p ? trvb_arena_free(ctx->device, ctx->stream, p) : cudaSuccess;
 }
 
+// exp(-2 pi i t / N), t < N, on ctx's device (evaluated in long double on the host; one
+// table per (device, N) for the life of the process).  csrc/trvb_xpass.cu.
+int trvb_twiddle_table(trvb_ctx* ctx, int N, const double2** out);
+
 // ---------------------------------------------------------------------
 // Device helpers
 // ---------------------------------------------------------------------

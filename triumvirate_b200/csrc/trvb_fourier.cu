@@ -7,8 +7,11 @@
 // Replaces S/field.cpp:1496-1720 (transforms), 1764-1785 (compensation),
 // 1792-1906 (band-limited y_lm-weighted IFFT), 1908-2010 (j_l-weighted IFFT).
 #include "trvb_common.cuh"
+#include "trvb_zpass.cuh"
 
 #include <algorithm>
+#include <map>
+#include <mutex>
 
 namespace {
 
@@ -669,6 +672,81 @@ k_shell_zlines(const double2* __restrict__ B, int K2, int kw, int n1, int nh, lo
   }
 }
 
+// Pass 3, hand-written: pruned-input complex-to-real transform along z straight from
+// B[r][kz][y] to the REAL slab (csrc/trvb_zpass.cuh).  One CTA = 2 LP adjacent lines of one
+// (shell, plane) r; twiddles are read through L1 (an 8.6 KB table at N = 540), which leaves
+// the shared memory to three resident tiles.
+template <int N, int LP, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+k_shell_zpass(const double2* __restrict__ B, int K2, int n1, int tiles_y,
+              const double2* __restrict__ tw, double* __restrict__ out) {
+  using namespace xpass;
+  extern __shared__ __align__(16) unsigned char zp_smem[];
+  double2* tile = reinterpret_cast<double2*>(zp_smem);
+  const int tid = threadIdx.x;
+  const long long r = blockIdx.x / tiles_y;
+  const int y0 = (int)(blockIdx.x % tiles_y) * 2 * LP;
+  constexpr int NS = Radix<N>::NS;
+  zstage_load<N, LP, NT>(tid, B + r * (long long)K2 * n1, K2, n1, y0, tile);
+  __syncthreads();
+  if constexpr (NS >= 4) { zstage<N, LP, NT, 3>(tid, tile, tw); __syncthreads(); }
+  if constexpr (NS >= 3) { zstage<N, LP, NT, 2>(tid, tile, tw); __syncthreads(); }
+  zstage<N, LP, NT, 1>(tid, tile, tw);
+  __syncthreads();
+  zstage_store<N, LP, NT>(tid, tile, tw, n1, y0, out + r * (long long)n1 * N);
+}
+
+template <int N>
+int launch_zpass(trvb_ctx* sub, const double2* B, int K2, int n1, long long nrows, double* out) {
+  constexpr int LP = N <= 288 ? 16 : 8, NT = 128;
+  constexpr size_t smem = sizeof(double2) * (size_t)LP * xpass::zp_pitch<N>();
+  constexpr int MINB = smem * 4 <= 220 * 1024 ? 4 : (smem * 3 <= 220 * 1024 ? 3 : 2);
+  const double2* tw = nullptr;
+  int st = trvb_twiddle_table(sub, N, &tw);
+  if (st) return st;
+  static std::mutex attr_mutex;
+  static std::map<int, bool> attr_done;   // per device
+  {
+    std::lock_guard<std::mutex> lock(attr_mutex);
+    if (!attr_done[sub->device]) {
+      TRVB_CUDA(cudaFuncSetAttribute(k_shell_zpass<N, LP, NT, MINB>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_done[sub->device] = true;
+    }
+  }
+  const int tiles_y = (n1 + 2 * LP - 1) / (2 * LP);
+  const long long tiles = nrows * tiles_y;
+  TRVB_REQUIRE(tiles < 2147483647LL, "pruned transform: too many z-pass tiles");
+  k_shell_zpass<N, LP, NT, MINB><<<(unsigned)tiles, NT, smem, sub->stream>>>(B, K2, n1, tiles_y, tw, out);
+  TRVB_LAUNCH_CHECK();
+  return 0;
+}
+
+#define TRVB_ZPASS_LENGTHS(X) \
+  X(64) X(72) X(96) X(108) X(128) X(144) X(160) X(180) X(192) X(216) X(240) X(256) X(270) \
+  X(288) X(320) X(360) X(384) X(432) X(480) X(512) X(540) X(576) X(600) X(640) X(720)
+
+bool zpass_supported(int n2) {
+  switch (n2) {
+#define X(n) case n:
+    TRVB_ZPASS_LENGTHS(X)
+#undef X
+      return true;
+    default: return false;
+  }
+}
+
+int run_zpass(trvb_ctx* sub, int n2, const double2* B, int K2, int n1, long long nrows,
+              double* out) {
+  switch (n2) {
+#define X(n) case n: return launch_zpass<n>(sub, B, K2, n1, nrows, out);
+    TRVB_ZPASS_LENGTHS(X)
+#undef X
+    default: break;
+  }
+  TRVB_REQUIRE(false, "pruned transform: no hand-written z pass for length %d", n2);
+}
+
 // Batched 1-D plans WITHOUT their own work areas (several batch sizes are alive at once and
 // cuFFT's automatic areas would add up): the area comes from the arena for the duration of
 // one execution.
@@ -719,6 +797,8 @@ struct ArenaBlocks {
 };
 
 }  // namespace
+
+extern "C" int trvb_shell_zpass_supported(int n2) { return zpass_supported(n2) ? 1 : 0; }
 
 extern "C" int trvb_shell_slab_batch(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh src, int ell,
                                      int m, const double* klo, const double* khi,
@@ -782,9 +862,16 @@ extern "C" int trvb_shell_slab_batch(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh src
 
   // Sub-batches of consecutive shells: they bound the transient arrays to ~6 GiB, and each
   // takes the extents of its own largest shell (TRV_SHELL_GROUPS = least number of them).
+  // The z pass: hand-written pruned c2r (k_shell_zpass) for the lengths it is built for,
+  // else zero-padded lines + cuFFT (TRV_NO_ZPASS=1 forces the latter).
+  bool own_z = zpass_supported(n2);
+  {
+    const char* env = getenv("TRV_NO_ZPASS");
+    if (env && env[0] == '1') own_z = false;
+  }
   const size_t a_bin = sizeof(double2) * (size_t)G1 * G2 * n0;
   const size_t b_bin = sizeof(double2) * (size_t)nx * G2 * n1;
-  const size_t e_bin = sizeof(double2) * (size_t)nx * n1 * nh;
+  const size_t e_bin = own_z ? 0 : sizeof(double2) * (size_t)nx * n1 * nh;
   int maxb = (int)std::max<size_t>(1, ((size_t)6 << 30) / (a_bin + b_bin + e_bin));
   {
     // (C5 shares of 8, 40 shells: 4 groups 13.0 ms, 10 groups 12.0 ms)
@@ -796,8 +883,10 @@ extern "C" int trvb_shell_slab_batch(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh src
   double2* A = nullptr; double2* B = nullptr; double2* E = nullptr;
   TRVB_CUDA(arena.get((void**)&A, a_bin * maxb));
   TRVB_CUDA(arena.get((void**)&B, b_bin * maxb));
-  TRVB_CUDA(arena.get((void**)&E, e_bin * maxb));
-  TRVB_CUDA(cudaMemsetAsync(E, 0, e_bin * maxb, sub->stream));
+  if (!own_z) {
+    TRVB_CUDA(arena.get((void**)&E, e_bin * maxb));
+    TRVB_CUDA(cudaMemsetAsync(E, 0, e_bin * maxb, sub->stream));
+  }
   int e_written = 0;   // kz extent of E that may hold non-zero values
   const size_t out_bin = sizeof(double) * (size_t)nx * n1 * n2;
   auto exec_with_area = [&](cufftHandle plan, size_t ws, auto run) -> int {
@@ -854,6 +943,12 @@ extern "C" int trvb_shell_slab_batch(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh src
     g_trvb_fft_execs++;
     // -- z --
     const long long nrows = (long long)nq * nx;
+    if (own_z) {
+      double* out = (double*)((char*)dst + out_bin * (size_t)q0);
+      st = run_zpass(sub, n2, B, K2, n1, nrows, out);
+      if (st) return st;
+      continue;
+    }
     const int kw = std::min(nh, std::max(K2, e_written));
     e_written = kw;
     {

@@ -44,12 +44,44 @@ k_xpass_fused(double2* __restrict__ T, xpass::Pointwise pw, const double2* __res
   stage_last<N, CK, NT>(tid, tile, tw, col, T, pw.ncols);
 }
 
+// The same pass with the tile brought in by cp.async: no thread waits on a global load with
+// its registers tied up, and a CTA has its whole tile in flight from its first instruction
+// (the register-staged first stage had 8 of a thread's 16 loads in flight at a time and
+// spent 40 % of its warp-cycles on the long scoreboard: profiles/r02_ncu_k_xpass_fused.txt).
+template <int N, int CK, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+k_xpass_fused_async(double2* __restrict__ T, xpass::Pointwise pw, const double2* __restrict__ tw_g) {
+  using namespace xpass;
+  extern __shared__ __align__(16) unsigned char xp_smem[];
+  double2* tile = reinterpret_cast<double2*>(xp_smem);
+  double2* tw = tile + N * CK;
+  const int tid = threadIdx.x;
+  const long long c0 = (long long)blockIdx.x * CK;
+  stage_load_async<N, CK, NT>(tid, T, pw.ncols, c0, pw.ncols, tile);
+  for (int t = tid; t < N; t += NT) tw[t] = tw_g[t];
+  const Column col = column_of(pw, c0 + tid % CK);
+  stage_load_wait();
+  __syncthreads();
+  constexpr int NS = Radix<N>::NS;
+  stage_fwd<N, CK, NT, 0>(tid, tile, tw);
+  __syncthreads();
+  if constexpr (NS >= 3) { stage_fwd<N, CK, NT, 1>(tid, tile, tw); __syncthreads(); }
+  if constexpr (NS >= 4) { stage_fwd<N, CK, NT, 2>(tid, tile, tw); __syncthreads(); }
+  stage_junction<N, CK, NT>(tid, tile, pw, col);
+  __syncthreads();
+  if constexpr (NS >= 4) { stage_inv<N, CK, NT, 2>(tid, tile, tw); __syncthreads(); }
+  if constexpr (NS >= 3) { stage_inv<N, CK, NT, 1>(tid, tile, tw); __syncthreads(); }
+  stage_last<N, CK, NT>(tid, tile, tw, col, T, pw.ncols);
+}
+
 // exp(-2 pi i t / N), t < N, evaluated in long double on the host; one table per (device, N)
 // for the life of the process (16 KB at most).
 std::mutex g_tw_mutex;
 std::map<std::pair<int, int>, double2*> g_tw_tables;
 
-int twiddles(trvb_ctx* ctx, int N, const double2** out) {
+}  // namespace
+
+int trvb_twiddle_table(trvb_ctx* ctx, int N, const double2** out) {
   std::lock_guard<std::mutex> lock(g_tw_mutex);
   const auto key = std::make_pair(ctx->device, N);
   auto it = g_tw_tables.find(key);
@@ -71,23 +103,24 @@ int twiddles(trvb_ctx* ctx, int N, const double2** out) {
   return 0;
 }
 
-template <int N, int CK, int MINB>
+namespace {
+
+template <int N, int CK, int MINB, int NT = 256, bool ASYNC = false>
 int launch_xpass(trvb_ctx* ctx, double2* T, const xpass::Pointwise& pw, const double2* tw) {
-  constexpr int NT = 256;
+  auto kernel = ASYNC ? k_xpass_fused_async<N, CK, NT, MINB> : k_xpass_fused<N, CK, NT, MINB>;
   const size_t smem = sizeof(double2) * ((size_t)N * CK + N);
   static std::mutex attr_mutex;
   static std::map<int, bool> attr_done;   // per device
   {
     std::lock_guard<std::mutex> lock(attr_mutex);
     if (!attr_done[ctx->device]) {
-      TRVB_CUDA(cudaFuncSetAttribute(k_xpass_fused<N, CK, NT, MINB>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      TRVB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_done[ctx->device] = true;
     }
   }
   const long long tiles = (pw.ncols + CK - 1) / CK;
   TRVB_REQUIRE(tiles < 2147483647LL, "trvb_box_fields_fused: too many column tiles");
-  k_xpass_fused<N, CK, NT, MINB><<<(unsigned)tiles, NT, smem, ctx->stream>>>(T, pw, tw);
+  kernel<<<(unsigned)tiles, NT, smem, ctx->stream>>>(T, pw, tw);
   TRVB_LAUNCH_CHECK();
   return 0;
 }
@@ -161,7 +194,7 @@ extern "C" int trvb_box_fields_fused(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh x, 
   TRVB_CUDA(cudaSetDevice(ctx->device));
   g_fused_calls++;
   const double2* tw = nullptr;
-  int st = twiddles(ctx, g.n[0], &tw);
+  int st = trvb_twiddle_table(ctx, g.n[0], &tw);
   if (st) return st;
   cufftHandle fwd, inv;
   size_t ws_fwd = 0, ws_inv = 0;
@@ -199,13 +232,24 @@ extern "C" int trvb_box_fields_fused(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh x, 
   pw.add_a = add_a; pw.add_b = add_b; pw.S_re = S[0]; pw.S_im = S[1]; pw.inv_vol = 1. / g.vol;
   pw.s0 = sub->g.n[0]; pw.s1 = sub->g.n[1]; pw.s2 = sub->g.n[2]; pw.sh = sub->g.nh;
   pw.lowk = (double2*)lowk.data;
+  // Launch shapes measured on B200 (scripts/xpass_bench.py, profiles/r02_xpass_variants.txt):
+  // 512: cp.async tile, 128 threads (four butterflies per thread and stage: the compiler
+  // overlaps their shared-memory loads), three CTAs per SM: 0.55 ms against 0.71 ms for the
+  // register-staged 256-thread kernel.  1024: the tile is 64 KB with FOUR columns (64-byte
+  // segments per plane) and the register-staged kernel is the best of those tried.
+  // TRV_XPASS_VARIANT=1 selects the other kernel of the pair (A/B runs).
+  const char* env_v = getenv("TRV_XPASS_VARIANT");
+  const bool other = env_v && env_v[0] == '1';
   switch (g.n[0]) {
     case 32:   st = launch_xpass<32, 8, 3>(ctx, T, pw, tw); break;
     case 64:   st = launch_xpass<64, 8, 3>(ctx, T, pw, tw); break;
     case 128:  st = launch_xpass<128, 8, 3>(ctx, T, pw, tw); break;
-    case 256:  st = launch_xpass<256, 8, 3>(ctx, T, pw, tw); break;
-    case 512:  st = launch_xpass<512, 8, 3>(ctx, T, pw, tw); break;
-    case 1024: st = launch_xpass<1024, 4, 2>(ctx, T, pw, tw); break;
+    case 256:  st = other ? launch_xpass<256, 8, 3>(ctx, T, pw, tw)
+                          : launch_xpass<256, 8, 3, 128, true>(ctx, T, pw, tw); break;
+    case 512:  st = other ? launch_xpass<512, 8, 3>(ctx, T, pw, tw)
+                          : launch_xpass<512, 8, 3, 128, true>(ctx, T, pw, tw); break;
+    case 1024: st = other ? launch_xpass<1024, 4, 2, 128, true>(ctx, T, pw, tw)
+                          : launch_xpass<1024, 4, 2>(ctx, T, pw, tw); break;
     default:   st = launch_xpass<2048, 4, 1>(ctx, T, pw, tw); break;
   }
   if (st) return st;

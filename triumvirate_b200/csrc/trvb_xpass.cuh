@@ -188,7 +188,36 @@ XP_HD void stage_first(int tid, const double2* __restrict__ T, long long plane_s
   }
 }
 
-// Forward stage t (0 < t < NS - 1), in place on the tile.
+// Asynchronous variant of the first stage's read: the whole tile goes from global to shared
+// memory with 16-byte cp.async copies (no registers, every byte of the tile in flight at
+// once), then stage_fwd<.., 0> runs on shared memory like the middle stages.  Columns beyond
+// the mesh are zero-filled.  Followed by stage_load_wait + a block barrier.
+template <int N, int CK, int NT>
+XP_HD void stage_load_async(int tid, const double2* __restrict__ T, long long plane_stride,
+                            long long c0, long long ncols, double2* tile) {
+  constexpr int RL = Radix<N>::r(Radix<N>::NS - 1);
+  const int ck = tid % CK;
+  const bool inside = c0 + ck < ncols;
+  for (int e = tid; e < N * CK; e += NT) {
+    const int row = e / CK;
+    double2* dst = tile + phys_row<CK, RL>(row) * CK + ck;
+    if (!inside) { *dst = make_double2(0., 0.); continue; }
+    const double2* src = T + (long long)row * plane_stride + c0 + ck;
+#ifdef __CUDA_ARCH__
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(src) : "memory");
+#else
+    *dst = *src;
+#endif
+  }
+}
+XP_HD void stage_load_wait() {
+#ifdef __CUDA_ARCH__
+  asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+
+// Forward stage t (0 <= t < NS - 1), in place on the tile.
 template <int N, int CK, int NT, int STAGE>
 XP_HD void stage_fwd(int tid, double2* tile, const double2* tw) {
   constexpr int R = Radix<N>::r(STAGE), L = block_len<N>(STAGE), S = L / R;

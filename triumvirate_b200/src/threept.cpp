@@ -802,12 +802,23 @@ BispecShare bispec_share(const trv::ParameterSet& params, const DataVector& dv,
 /// Sub-grid extents for shells reaching k_max (section 2 of the file header).
 void choose_subgrid(const trv::ParameterSet& params, double kmax, int nsub[3]) {
   bool coarsen = true;
+  const char* env_z = std::getenv("TRV_NO_ZPASS");
+  const bool no_zpass = env_z != nullptr && env_z[0] == '1';
   for (int ax = 0; ax < 3; ax++) {
     const double dk = 2. * M_PI / params.boxsize[ax];
     const long long mcut = static_cast<long long>(std::floor(kmax / dk)) + 1;
     const long long need = 4 * mcut + 2;
     if (need >= params.ngrid[ax]) { coarsen = false; break; }
     nsub[ax] = next_fft_size(static_cast<int>(need));
+    // Throughput mode builds real shell fields with the pruned per-axis transform, whose
+    // last pass is hand-written for a set of extents (trvb_shell_zpass_supported): the
+    // smallest of those within 25 % of the need beats the table above, which ranks dense
+    // 3-D cuFFT transforms.  The deterministic mode keeps the dense transform and the table.
+    if (!params.deterministic && !no_zpass) {
+      for (long long v = need; 4 * v <= 5 * need; v++) {
+        if (trvb_shell_zpass_supported(static_cast<int>(v))) { nsub[ax] = static_cast<int>(v); break; }
+      }
+    }
     if (nsub[ax] >= params.ngrid[ax]) { coarsen = false; break; }
   }
   const char* env = std::getenv("TRV_NO_SUBGRID");
