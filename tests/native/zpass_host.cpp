@@ -11,7 +11,7 @@ using namespace xpass;
 
 template <int N>
 int run(int n1, int K2, const std::vector<double2>& B, std::vector<double>& out) {
-  constexpr int LP = 8, NT = 128, NS = Radix<N>::NS;
+  constexpr int LP = 4, NT = 128, NS = Radix<N>::NS;
   std::vector<double2> tw(N);
   for (int t = 0; t < N; t++) {
     const long double a = -2.0L * M_PIl * t / N;

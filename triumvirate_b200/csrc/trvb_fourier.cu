@@ -245,6 +245,24 @@ k_sjl_apply(const double2* __restrict__ A, const double* __restrict__ kmag, long
   }
 }
 
+// Plans with cuFFT's own work areas allocate behind the arena's back: when that fails the
+// arena's cached blocks go back to the driver and the plan is tried once more (the arena
+// does the same for its own allocations).
+template <typename Make>
+cufftResult plan_with_retry(trvb_ctx* ctx, Make make) {
+  cufftResult rc = make();
+  if (rc == CUFFT_ALLOC_FAILED || rc == CUFFT_INTERNAL_ERROR) {
+    cudaGetLastError();
+    // batched plans of other batch sizes keep their work areas: they are rebuilt on demand
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->batch_plans) cufftDestroy(kv.second);
+    ctx->batch_plans.clear();
+    trvb_arena_trim(ctx->device);
+    rc = make();
+  }
+  return rc;
+}
+
 // Batched plan over `batch` consecutive meshes of ctx's grid.
 int get_batch_plan(trvb_ctx* ctx, cufftType type, int batch, cufftHandle* out) {
   auto key = std::make_pair((int)type, batch);
@@ -256,11 +274,13 @@ int get_batch_plan(trvb_ctx* ctx, cufftType type, int batch, cufftHandle* out) {
     TRVB_REQUIRE(nfull < 2147483647LL, "batched FFT: grid too large for a batched plan");
     cufftHandle plan;
     if (type == CUFFT_Z2Z) {
-      TRVB_CUFFT(cufftPlanMany(&plan, 3, dims, nullptr, 1, (int)nfull, nullptr, 1, (int)nfull,
-                               CUFFT_Z2Z, batch));
+      TRVB_CUFFT(plan_with_retry(ctx, [&] {
+        return cufftPlanMany(&plan, 3, dims, nullptr, 1, (int)nfull, nullptr, 1, (int)nfull,
+                             CUFFT_Z2Z, batch); }));
     } else {   // Z2D, out of place: HALF spectra -> REAL meshes
-      TRVB_CUFFT(cufftPlanMany(&plan, 3, dims, nullptr, 1, (int)nhalf, nullptr, 1, (int)nfull,
-                               CUFFT_Z2D, batch));
+      TRVB_CUFFT(plan_with_retry(ctx, [&] {
+        return cufftPlanMany(&plan, 3, dims, nullptr, 1, (int)nhalf, nullptr, 1, (int)nfull,
+                             CUFFT_Z2D, batch); }));
     }
     TRVB_CUFFT(cufftSetStream(plan, ctx->stream));
     it = ctx->batch_plans.emplace(key, plan).first;
@@ -275,7 +295,8 @@ int get_plan(trvb_ctx* ctx, cufftType type, cufftHandle* out) {
   else if (type == CUFFT_D2Z) { slot = &ctx->plan_d2z; has = &ctx->has_d2z; }
   else { slot = &ctx->plan_z2d; has = &ctx->has_z2d; }
   if (!*has) {
-    TRVB_CUFFT(cufftPlan3d(slot, ctx->g.n[0], ctx->g.n[1], ctx->g.n[2], type));
+    TRVB_CUFFT(plan_with_retry(ctx, [&] {
+      return cufftPlan3d(slot, ctx->g.n[0], ctx->g.n[1], ctx->g.n[2], type); }));
     TRVB_CUFFT(cufftSetStream(*slot, ctx->stream));
     *has = true;
   }
@@ -698,9 +719,11 @@ k_shell_zpass(const double2* __restrict__ B, int K2, int n1, int tiles_y,
 
 template <int N>
 int launch_zpass(trvb_ctx* sub, const double2* B, int K2, int n1, long long nrows, double* out) {
-  constexpr int LP = N <= 288 ? 16 : 8, NT = 128;
+  // Small tiles, many CTAs: the kernel is latency-bound at 12 warps per SM (LP = 8 at
+  // N = 540: long-scoreboard stalls, 2.1 TB/s; profiles/r02_ncu_k_shell_zpass540_lp8.txt).
+  constexpr int LP = N <= 288 ? 8 : 4, NT = 128;
   constexpr size_t smem = sizeof(double2) * (size_t)LP * xpass::zp_pitch<N>();
-  constexpr int MINB = smem * 4 <= 220 * 1024 ? 4 : (smem * 3 <= 220 * 1024 ? 3 : 2);
+  constexpr int MINB = smem * 5 <= 220 * 1024 ? 5 : 4;
   const double2* tw = nullptr;
   int st = trvb_twiddle_table(sub, N, &tw);
   if (st) return st;

@@ -160,19 +160,31 @@ XP_HD void zstage_load(int tid, const double2* __restrict__ Bq, int K2, int n1, 
     const int j = e % LP, k = K2 + e / LP;
     tile[j * P + pos_of_freq<N>(k)] = make_double2(0., 0.);
   }
-  for (int e = tid; e < K2 * LP; e += NT) {
-    const int j = e % LP, kz = e / LP;
-    const int ya = y0 + 2 * j;
-    const double2* src = Bq + (long long)kz * n1 + ya;
-    const double2 fa = ya < n1 ? src[0] : make_double2(0., 0.);
-    const double2 fb = ya + 1 < n1 ? src[1] : make_double2(0., 0.);
-    if (kz == 0) {
-      // the imaginary part of the k_z = 0 mode is dropped, as a c2r transform does
-      tile[j * P + pos_of_freq<N>(0)] = make_double2(fa.x, fb.x);
-    } else {
-      // C[k] = F_A + i F_B,  C[N - k] = conj(F_A) + i conj(F_B)
-      tile[j * P + pos_of_freq<N>(kz)] = make_double2(fa.x - fb.y, fa.y + fb.x);
-      tile[j * P + pos_of_freq<N>(N - kz)] = make_double2(fa.x + fb.y, fb.x - fa.y);
+  // UN elements per thread with all their global loads issued before the first use
+  constexpr int UN = 4;
+  for (int e0 = tid; e0 < K2 * LP; e0 += NT * UN) {
+    double2 fa[UN], fb[UN];
+#pragma unroll
+    for (int i = 0; i < UN; i++) {
+      const int e = e0 + i * NT;
+      const int j = e % LP, kz = e / LP, ya = y0 + 2 * j;
+      const double2* src = Bq + (long long)kz * n1 + ya;
+      fa[i] = (e < K2 * LP && ya < n1) ? src[0] : make_double2(0., 0.);
+      fb[i] = (e < K2 * LP && ya + 1 < n1) ? src[1] : make_double2(0., 0.);
+    }
+#pragma unroll
+    for (int i = 0; i < UN; i++) {
+      const int e = e0 + i * NT;
+      if (e >= K2 * LP) break;
+      const int j = e % LP, kz = e / LP;
+      if (kz == 0) {
+        // the imaginary part of the k_z = 0 mode is dropped, as a c2r transform does
+        tile[j * P + pos_of_freq<N>(0)] = make_double2(fa[i].x, fb[i].x);
+      } else {
+        // C[k] = F_A + i F_B,  C[N - k] = conj(F_A) + i conj(F_B)
+        tile[j * P + pos_of_freq<N>(kz)] = make_double2(fa[i].x - fb[i].y, fa[i].y + fb[i].x);
+        tile[j * P + pos_of_freq<N>(N - kz)] = make_double2(fa[i].x + fb[i].y, fb[i].x - fa[i].y);
+      }
     }
   }
 }
@@ -183,9 +195,11 @@ XP_HD void zstage(int tid, double2* tile, const double2* tw) {
   constexpr int R = Radix<N>::r(STAGE), L = block_len<N>(STAGE), S = L / R, NB = N / R;
   constexpr int P = zp_pitch<N>();
   for (int u = tid; u < NB * LP; u += NT) {
-    // unit-stride stage: lanes across the lines (distinct bank groups by the odd pitch);
-    // otherwise lanes along consecutive butterflies of one line (consecutive slots)
-    const int j = S == 1 ? u % LP : u / NB, b = S == 1 ? u / LP : u % NB;
+    // lanes across the lines: the odd pitch puts the LP rows of one slot on distinct
+    // 16-byte bank groups whatever the stride of the stage (lanes along the butterflies of
+    // one line conflict two ways wherever a group of eight straddles a block boundary and
+    // S is not a multiple of 8: a quarter of all wavefronts at N = 540, ncu)
+    const int j = u % LP, b = u / LP;
     const int base = (b / S) * L, p = b % S;
     double2* line = tile + j * P + base + p;
     double2 x[R];
