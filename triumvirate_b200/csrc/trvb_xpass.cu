@@ -48,17 +48,22 @@ k_xpass_fused(double2* __restrict__ T, xpass::Pointwise pw, const double2* __res
 // its registers tied up, and a CTA has its whole tile in flight from its first instruction
 // (the register-staged first stage had 8 of a thread's 16 loads in flight at a time and
 // spent 40 % of its warp-cycles on the long scoreboard: profiles/r02_ncu_k_xpass_fused.txt).
-template <int N, int CK, int NT, int MINB>
+// TWG: twiddles read through L1 from the global table instead of a shared-memory copy (the
+// 16 KB table of N = 1024 is what keeps a third CTA off the SM).
+template <int N, int CK, int NT, int MINB, bool TWG = false>
 __global__ void __launch_bounds__(NT, MINB)
 k_xpass_fused_async(double2* __restrict__ T, xpass::Pointwise pw, const double2* __restrict__ tw_g) {
   using namespace xpass;
   extern __shared__ __align__(16) unsigned char xp_smem[];
   double2* tile = reinterpret_cast<double2*>(xp_smem);
-  double2* tw = tile + N * CK;
+  const double2* tw = TWG ? tw_g : tile + N * CK;
   const int tid = threadIdx.x;
   const long long c0 = (long long)blockIdx.x * CK;
   stage_load_async<N, CK, NT>(tid, T, pw.ncols, c0, pw.ncols, tile);
-  for (int t = tid; t < N; t += NT) tw[t] = tw_g[t];
+  if (!TWG) {
+    double2* tws = tile + N * CK;
+    for (int t = tid; t < N; t += NT) tws[t] = tw_g[t];
+  }
   const Column col = column_of(pw, c0 + tid % CK);
   stage_load_wait();
   __syncthreads();
@@ -105,10 +110,10 @@ int trvb_twiddle_table(trvb_ctx* ctx, int N, const double2** out) {
 
 namespace {
 
-template <int N, int CK, int MINB, int NT = 256, bool ASYNC = false>
+template <int N, int CK, int MINB, int NT = 256, bool ASYNC = false, bool TWG = false>
 int launch_xpass(trvb_ctx* ctx, double2* T, const xpass::Pointwise& pw, const double2* tw) {
-  auto kernel = ASYNC ? k_xpass_fused_async<N, CK, NT, MINB> : k_xpass_fused<N, CK, NT, MINB>;
-  const size_t smem = sizeof(double2) * ((size_t)N * CK + N);
+  auto kernel = ASYNC ? k_xpass_fused_async<N, CK, NT, MINB, TWG> : k_xpass_fused<N, CK, NT, MINB>;
+  const size_t smem = sizeof(double2) * ((size_t)N * CK + (TWG ? 0 : N));
   static std::mutex attr_mutex;
   static std::map<int, bool> attr_done;   // per device
   {
@@ -236,7 +241,8 @@ extern "C" int trvb_box_fields_fused(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh x, 
   // 512: cp.async tile, 128 threads (four butterflies per thread and stage: the compiler
   // overlaps their shared-memory loads), three CTAs per SM: 0.55 ms against 0.71 ms for the
   // register-staged 256-thread kernel.  1024: the tile is 64 KB with FOUR columns (64-byte
-  // segments per plane) and the register-staged kernel is the best of those tried.
+  // segments per plane); cp.async, 128 threads and the twiddles read through L1 (no 16 KB
+  // copy in shared memory: a third CTA fits): 7.1 ms against 7.7 ms register-staged.
   // TRV_XPASS_VARIANT=1 selects the other kernel of the pair (A/B runs).
   const char* env_v = getenv("TRV_XPASS_VARIANT");
   const bool other = env_v && env_v[0] == '1';
@@ -248,8 +254,8 @@ extern "C" int trvb_box_fields_fused(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh x, 
                           : launch_xpass<256, 8, 3, 128, true>(ctx, T, pw, tw); break;
     case 512:  st = other ? launch_xpass<512, 8, 3>(ctx, T, pw, tw)
                           : launch_xpass<512, 8, 3, 128, true>(ctx, T, pw, tw); break;
-    case 1024: st = other ? launch_xpass<1024, 4, 2, 128, true>(ctx, T, pw, tw)
-                          : launch_xpass<1024, 4, 2>(ctx, T, pw, tw); break;
+    case 1024: st = other ? launch_xpass<1024, 4, 2>(ctx, T, pw, tw)
+                          : launch_xpass<1024, 4, 3, 128, true, true>(ctx, T, pw, tw); break;
     default:   st = launch_xpass<2048, 4, 1>(ctx, T, pw, tw); break;
   }
   if (st) return st;
