@@ -1024,9 +1024,10 @@ def test_fused_x_pass_mesh_phase_equals_3d_transforms(core, monkeypatch, ng, sch
 @pytest.mark.parametrize("kmax,ns", [(0.09, 64), (0.10, 72), (0.13, 96), (0.15, 108), (0.19, 128),
                                      (0.205, 144), (0.24, 160)])
 def test_hand_written_z_pass_equals_cufft_z_pass(core, monkeypatch, kmax, ns):
-    """Last pass of the pruned shell transform: k_shell_zpass (pruned-input c2r along z,
-    csrc/trvb_zpass.cuh) against zero-padded lines + cuFFT Z2D (TRV_NO_ZPASS=1) on the same
-    sub-grid extent `ns` -- several radix plans -- and both against the dense 3-D transform."""
+    """y and z passes of the pruned shell transform: k_shell_ypass (pruned-input c2c along y)
+    and k_shell_zpass (pruned-input c2r along z, csrc/trvb_zpass.cuh) against zero-padded
+    lines + cuFFT (TRV_NO_YPASS=1: cuFFT y pass only; TRV_NO_ZPASS=1: both) on the sub-grid
+    extent `ns` -- several radix plans -- and all three against the dense 3-D transform."""
     gen = np.random.default_rng(int(1000 * kmax))
     L, ng = 1000., 256
     pos = gen.uniform(0., L, size=(3, 60000))
@@ -1040,9 +1041,13 @@ def test_hand_written_z_pass_equals_cufft_z_pass(core, monkeypatch, kmax, ns):
     monkeypatch.setenv("TRV_NO_PRUNE", "1")
     dense = core.threept("bispec", "sim", **kw)
     monkeypatch.delenv("TRV_NO_PRUNE")
+    monkeypatch.setenv("TRV_NO_YPASS", "1")     # hand-written z pass after the cuFFT y pass
+    mixed = core.threept("bispec", "sim", **kw)
+    monkeypatch.delenv("TRV_NO_YPASS")
     monkeypatch.setenv("TRV_NO_ZPASS", "1")
     old = core.threept("bispec", "sim", **kw)
     scale = np.max(np.abs(dense["bk_raw"]))
     assert np.max(np.abs(new["bk_raw"] - dense["bk_raw"])) < 1.e-11 * scale
+    assert np.max(np.abs(mixed["bk_raw"] - dense["bk_raw"])) < 1.e-11 * scale
     assert np.max(np.abs(old["bk_raw"] - dense["bk_raw"])) < 1.e-11 * scale
     assert np.array_equal(new["nmodes_1"], dense["nmodes_1"])

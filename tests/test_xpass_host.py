@@ -115,3 +115,33 @@ def test_pruned_c2r_z_pass_matches_numpy(zharness, tmp_path, n):
     F[:, 0] = F[:, 0].real     # a c2r transform ignores Im F[0]
     want = np.fft.irfft(F, n=n, axis=1) * n
     assert np.max(np.abs(out - want)) < 1.e-13 * np.max(np.abs(want))
+
+
+@pytest.fixture(scope="module")
+def yharness(tmp_path_factory):
+    exe = tmp_path_factory.mktemp("ypass") / "ypass_host"
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", f"-I{ROOT / 'triumvirate_b200' / 'csrc'}",
+                    str(ROOT / "tests" / "native" / "ypass_host.cpp"), "-o", str(exe)], check=True)
+    return exe
+
+
+@pytest.mark.parametrize("n", ZPASS_LENGTHS)
+def test_pruned_c2c_y_pass_matches_numpy(yharness, tmp_path, n):
+    """csrc/trvb_zpass.cuh, y pass of the pruned shell transform: K1 = 2 mc + 1 modes per line
+    loaded along x to digit-reversed slots, decimation-in-time stages, natural-order store
+    for a window of planes [x0, x0 + nx) -- against numpy.fft.ifft on zero-padded lines.  One
+    length runs the unbounded case (every mode below the Nyquist frequency: the G field)."""
+    gen = np.random.default_rng(n + 1)
+    n0, x0, nx = 29, 3, 10
+    mc1 = (n - 1) // 2 if n == 72 else n // 4 - 1
+    k1 = 2 * mc1 + 1
+    A = gen.normal(size=(k1, n0)) + 1j * gen.normal(size=(k1, n0))
+    A.astype(np.complex128).tofile(tmp_path / "in.bin")
+    subprocess.run([str(yharness), str(n), str(n0), str(mc1), str(x0), str(nx),
+                    str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], check=True)
+    out = np.fromfile(tmp_path / "out.bin", dtype=np.complex128).reshape(nx, n)
+    F = np.zeros((nx, n), dtype=complex)
+    for b in range(k1):
+        F[:, (b - mc1) % n] = A[b, x0:x0 + nx]
+    want = np.fft.ifft(F, axis=1) * n
+    assert np.max(np.abs(out - want)) < 1.e-13 * np.max(np.abs(want))

@@ -745,6 +745,59 @@ int launch_zpass(trvb_ctx* sub, const double2* B, int K2, int n1, long long nrow
   return 0;
 }
 
+// Pass 2, hand-written: pruned-input complex-to-complex transform along y from A[q][c][b][x]
+// to B[q][xi][c][y] (csrc/trvb_zpass.cuh).  One CTA = XT adjacent planes of one (q, c).
+template <int N, int XT, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+k_shell_ypass(const double2* __restrict__ A, int K1, int K2, int mc1, int n0, int x0, int nx,
+              int tiles_x, const double2* __restrict__ tw, double2* __restrict__ B) {
+  using namespace xpass;
+  extern __shared__ __align__(16) unsigned char zp_smem[];
+  double2* tile = reinterpret_cast<double2*>(zp_smem);
+  const int tid = threadIdx.x;
+  const long long qc = blockIdx.x / tiles_x;            // q K2 + c
+  const int xi0 = (int)(blockIdx.x % tiles_x) * XT;
+  const long long q = qc / K2;
+  const int c = (int)(qc - q * K2);
+  constexpr int NS = Radix<N>::NS;
+  ystage_load<N, XT, NT>(tid, A + qc * (long long)K1 * n0, K1, mc1, n0, x0 + xi0, x0 + nx, tile);
+  __syncthreads();
+  if constexpr (NS >= 4) { zstage<N, XT, NT, 3>(tid, tile, tw); __syncthreads(); }
+  if constexpr (NS >= 3) { zstage<N, XT, NT, 2>(tid, tile, tw); __syncthreads(); }
+  zstage<N, XT, NT, 1>(tid, tile, tw);
+  __syncthreads();
+  ystage_store<N, XT, NT>(tid, tile, tw, xi0, nx, (long long)K2 * N,
+                          B + (q * nx * K2 + c) * (long long)N);
+}
+
+template <int N>
+int launch_ypass(trvb_ctx* sub, const double2* A, int nq, int K1, int K2, int mc1, int n0,
+                 int x0, int nx, double2* B) {
+  constexpr int XT = N <= 288 ? 8 : 4, NT = 128;
+  constexpr size_t smem = sizeof(double2) * (size_t)XT * xpass::zp_pitch<N>();
+  constexpr int MINB = smem * 5 <= 220 * 1024 ? 5 : 4;
+  const double2* tw = nullptr;
+  int st = trvb_twiddle_table(sub, N, &tw);
+  if (st) return st;
+  static std::mutex attr_mutex;
+  static std::map<int, bool> attr_done;   // per device
+  {
+    std::lock_guard<std::mutex> lock(attr_mutex);
+    if (!attr_done[sub->device]) {
+      TRVB_CUDA(cudaFuncSetAttribute(k_shell_ypass<N, XT, NT, MINB>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_done[sub->device] = true;
+    }
+  }
+  const int tiles_x = (nx + XT - 1) / XT;
+  const long long tiles = (long long)nq * K2 * tiles_x;
+  TRVB_REQUIRE(tiles < 2147483647LL, "pruned transform: too many y-pass tiles");
+  k_shell_ypass<N, XT, NT, MINB><<<(unsigned)tiles, NT, smem, sub->stream>>>(
+    A, K1, K2, mc1, n0, x0, nx, tiles_x, tw, B);
+  TRVB_LAUNCH_CHECK();
+  return 0;
+}
+
 #define TRVB_ZPASS_LENGTHS(X) \
   X(64) X(72) X(96) X(108) X(128) X(144) X(160) X(180) X(192) X(216) X(240) X(256) X(270) \
   X(288) X(320) X(360) X(384) X(432) X(480) X(512) X(540) X(576) X(600) X(640) X(720)
@@ -768,6 +821,17 @@ int run_zpass(trvb_ctx* sub, int n2, const double2* B, int K2, int n1, long long
     default: break;
   }
   TRVB_REQUIRE(false, "pruned transform: no hand-written z pass for length %d", n2);
+}
+
+int run_ypass(trvb_ctx* sub, int n1, const double2* A, int nq, int K1, int K2, int mc1, int n0,
+              int x0, int nx, double2* B) {
+  switch (n1) {
+#define X(n) case n: return launch_ypass<n>(sub, A, nq, K1, K2, mc1, n0, x0, nx, B);
+    TRVB_ZPASS_LENGTHS(X)
+#undef X
+    default: break;
+  }
+  TRVB_REQUIRE(false, "pruned transform: no hand-written y pass for length %d", n1);
 }
 
 // Batched 1-D plans WITHOUT their own work areas (several batch sizes are alive at once and
@@ -887,10 +951,12 @@ extern "C" int trvb_shell_slab_batch(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh src
   // takes the extents of its own largest shell (TRV_SHELL_GROUPS = least number of them).
   // The z pass: hand-written pruned c2r (k_shell_zpass) for the lengths it is built for,
   // else zero-padded lines + cuFFT (TRV_NO_ZPASS=1 forces the latter).
-  bool own_z = zpass_supported(n2);
+  bool own_z = zpass_supported(n2), own_y = zpass_supported(n1);
   {
     const char* env = getenv("TRV_NO_ZPASS");
-    if (env && env[0] == '1') own_z = false;
+    if (env && env[0] == '1') own_z = own_y = false;
+    env = getenv("TRV_NO_YPASS");
+    if (env && env[0] == '1') own_y = false;
   }
   const size_t a_bin = sizeof(double2) * (size_t)G1 * G2 * n0;
   const size_t b_bin = sizeof(double2) * (size_t)nx * G2 * n1;
@@ -950,20 +1016,25 @@ extern "C" int trvb_shell_slab_batch(trvb_ctx* ctx, trvb_ctx* sub, trvb_mesh src
     if (st) return st;
     g_trvb_fft_execs++;
     // -- y --
-    {
-      const long long ntile = (long long)nq * K2 * ((nx + 31) / 32) * ((n1 + 31) / 32);
-      k_shell_ylines<<<(int)std::min(ntile, cap), dim3(32, 8), 0, sub->stream>>>(
-        A, pd, nq, n0, n1, x0, nx, B);
-      TRVB_LAUNCH_CHECK();
+    if (own_y) {
+      st = run_ypass(sub, n1, A, nq, K1, K2, pd.mc[1], n0, x0, nx, B);
+      if (st) return st;
+    } else {
+      {
+        const long long ntile = (long long)nq * K2 * ((nx + 31) / 32) * ((n1 + 31) / 32);
+        k_shell_ylines<<<(int)std::min(ntile, cap), dim3(32, 8), 0, sub->stream>>>(
+          A, pd, nq, n0, n1, x0, nx, B);
+        TRVB_LAUNCH_CHECK();
+      }
+      st = get_line_plan(sub, CUFFT_Z2Z, n1, (long long)nq * nx * K2, &plan, &ws);
+      if (st) return st;
+      st = exec_with_area(plan, ws, [&]() -> int {
+        TRVB_CUFFT(cufftExecZ2Z(plan, (cufftDoubleComplex*)B, (cufftDoubleComplex*)B, CUFFT_INVERSE));
+        return 0;
+      });
+      if (st) return st;
+      g_trvb_fft_execs++;
     }
-    st = get_line_plan(sub, CUFFT_Z2Z, n1, (long long)nq * nx * K2, &plan, &ws);
-    if (st) return st;
-    st = exec_with_area(plan, ws, [&]() -> int {
-      TRVB_CUFFT(cufftExecZ2Z(plan, (cufftDoubleComplex*)B, (cufftDoubleComplex*)B, CUFFT_INVERSE));
-      return 0;
-    });
-    if (st) return st;
-    g_trvb_fft_execs++;
     // -- z --
     const long long nrows = (long long)nq * nx;
     if (own_z) {

@@ -244,6 +244,71 @@ XP_HD void zstage_store(int tid, const double2* tile, const double2* tw, int n1,
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// The y pass in the same scheme: complex-to-complex inverse transform of length N along y
+// with pruned input.  After the x pass a shell is A[q][c][b][x] (c = k_z, b = k_y + mc1 in
+// [0, K1), x over the whole line); the z pass wants B[q][xi][c][y] for the planes
+// xi in [0, nx) (x = x0 + xi).  A CTA takes XT adjacent x of one (q, c): loads are
+// coalesced along x, each line's K1 modes go to the digit-reversed slots of their
+// frequencies, the rest of the line is zeroed, and the last stage stores natural order with
+// lanes along y.  Replaces k_shell_ylines (zero-padded transpose) + a batched cuFFT Z2Z.
+// ---------------------------------------------------------------------------------------
+
+// Aqc = A + (q K2 + c) K1 n0: rows b = 0 .. K1-1 of n0 elements; xs = first x of the tile.
+template <int N, int XT, int NT>
+XP_HD void ystage_load(int tid, const double2* __restrict__ Aqc, int K1, int mc1, int n0, int xs,
+                       int xe /* one past the last valid x */, double2* tile) {
+  constexpr int P = zp_pitch<N>();
+  // frequencies mc1 + 1 .. N - mc1 - 1 are zero
+  const int nzero = N - K1;
+  for (int e = tid; e < nzero * XT; e += NT) {
+    const int j = e % XT, k = mc1 + 1 + e / XT;
+    tile[j * P + pos_of_freq<N>(k)] = make_double2(0., 0.);
+  }
+  constexpr int UN = 4;
+  for (int e0 = tid; e0 < K1 * XT; e0 += NT * UN) {
+    double2 v[UN];
+#pragma unroll
+    for (int i = 0; i < UN; i++) {
+      const int e = e0 + i * NT;
+      const int j = e % XT, b = e / XT;
+      v[i] = (e < K1 * XT && xs + j < xe) ? Aqc[(long long)b * n0 + xs + j] : make_double2(0., 0.);
+    }
+#pragma unroll
+    for (int i = 0; i < UN; i++) {
+      const int e = e0 + i * NT;
+      if (e >= K1 * XT) break;
+      const int j = e % XT, b = e / XT;
+      const int mj = b - mc1;
+      tile[j * P + pos_of_freq<N>(mj >= 0 ? mj : mj + N)] = v[i];
+    }
+  }
+}
+
+// Last stage: natural order in y.  Bq = B + q nx K2 n1 + c n1; line xi lives at
+// Bq + xi K2 n1 (row_stride = K2 n1).
+template <int N, int XT, int NT>
+XP_HD void ystage_store(int tid, const double2* tile, const double2* tw, int xi0, int nx,
+                        long long row_stride, double2* __restrict__ Bq) {
+  constexpr int R = Radix<N>::r(0), S = N / R;
+  constexpr int P = zp_pitch<N>();
+  for (int u = tid; u < S * XT; u += NT) {
+    const int j = u / S, p = u % S;
+    const double2* line = tile + j * P + p;
+    double2 x[R];
+#pragma unroll
+    for (int q = 0; q < R; q++) x[q] = line[q * S];
+#pragma unroll
+    for (int q = 1; q < R; q++) x[q] = cmul_conj(x[q], tw[q * p]);
+    DftT<R, +1, N>::run(x, tw);
+    if (xi0 + j < nx) {
+      double2* o = Bq + (long long)(xi0 + j) * row_stride + p;
+#pragma unroll
+      for (int m = 0; m < R; m++) o[m * S] = x[m];
+    }
+  }
+}
+
 }  // namespace xpass
 
 #endif  // TRVB_ZPASS_CUH_
