@@ -18,7 +18,7 @@ int run(int n0, int mc1, int x0, int nx, const std::vector<double2>& A, std::vec
     const long double a = -2.0L * M_PIl * t / N;
     tw[t] = make_double2((double)cosl(a), (double)sinl(a));
   }
-  std::vector<double2> tile((size_t)XT * zp_pitch<N>(), make_double2(1.e300, -1.e300));
+  std::vector<double2> tile((size_t)XT * zp_pitch<N, XT>(), make_double2(1.e300, -1.e300));
   for (int xi0 = 0; xi0 < nx; xi0 += XT) {
     for (int tid = 0; tid < NT; tid++) ystage_load<N, XT, NT>(tid, A.data(), K1, mc1, n0, x0 + xi0, x0 + nx, tile.data());
     if constexpr (NS >= 4) for (int tid = 0; tid < NT; tid++) zstage<N, XT, NT, 3>(tid, tile.data(), tw.data());

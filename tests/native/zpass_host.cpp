@@ -17,7 +17,7 @@ int run(int n1, int K2, const std::vector<double2>& B, std::vector<double>& out)
     const long double a = -2.0L * M_PIl * t / N;
     tw[t] = make_double2((double)cosl(a), (double)sinl(a));
   }
-  std::vector<double2> tile((size_t)LP * zp_pitch<N>(), make_double2(1.e300, -1.e300));
+  std::vector<double2> tile((size_t)LP * zp_pitch<N, LP>(), make_double2(1.e300, -1.e300));
   for (int y0 = 0; y0 < n1; y0 += 2 * LP) {
     for (int tid = 0; tid < NT; tid++) zstage_load<N, LP, NT>(tid, B.data(), K2, n1, y0, tile.data());
     if constexpr (NS >= 4) for (int tid = 0; tid < NT; tid++) zstage<N, LP, NT, 3>(tid, tile.data(), tw.data());

@@ -1022,14 +1022,14 @@ def test_fused_x_pass_mesh_phase_equals_3d_transforms(core, monkeypatch, ng, sch
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("kmax,ns", [(0.09, 64), (0.10, 72), (0.13, 96), (0.15, 108), (0.19, 128),
-                                     (0.205, 144), (0.24, 160)])
+                                     (0.205, 144), (0.24, 160), (0.49, 320)])
 def test_hand_written_z_pass_equals_cufft_z_pass(core, monkeypatch, kmax, ns):
     """y and z passes of the pruned shell transform: k_shell_ypass (pruned-input c2c along y)
     and k_shell_zpass (pruned-input c2r along z, csrc/trvb_zpass.cuh) against zero-padded
     lines + cuFFT (TRV_NO_YPASS=1: cuFFT y pass only; TRV_NO_ZPASS=1: both) on the sub-grid
     extent `ns` -- several radix plans -- and all three against the dense 3-D transform."""
     gen = np.random.default_rng(int(1000 * kmax))
-    L, ng = 1000., 256
+    L, ng = 1000., (256 if ns < 256 else 512)   # 320: the four-line tiles of the large extents
     pos = gen.uniform(0., L, size=(3, 60000))
     kw = dict(boxsize=L, ngrid=ng, assignment="tsc", degrees=(0, 0, 0), form="full",
               bin_range=(0.01, kmax), num_bins=5, norm_factor=1., pos_d=pos)

@@ -722,7 +722,7 @@ int launch_zpass(trvb_ctx* sub, const double2* B, int K2, int n1, long long nrow
   // Small tiles, many CTAs: the kernel is latency-bound at 12 warps per SM (LP = 8 at
   // N = 540: long-scoreboard stalls, 2.1 TB/s; profiles/r02_ncu_k_shell_zpass540_lp8.txt).
   constexpr int LP = N <= 288 ? 8 : 4, NT = 128;
-  constexpr size_t smem = sizeof(double2) * (size_t)LP * xpass::zp_pitch<N>();
+  constexpr size_t smem = sizeof(double2) * (size_t)LP * xpass::zp_pitch<N, LP>();
   constexpr int MINB = smem * 5 <= 220 * 1024 ? 5 : 4;
   const double2* tw = nullptr;
   int st = trvb_twiddle_table(sub, N, &tw);
@@ -774,7 +774,7 @@ template <int N>
 int launch_ypass(trvb_ctx* sub, const double2* A, int nq, int K1, int K2, int mc1, int n0,
                  int x0, int nx, double2* B) {
   constexpr int XT = N <= 288 ? 8 : 4, NT = 128;
-  constexpr size_t smem = sizeof(double2) * (size_t)XT * xpass::zp_pitch<N>();
+  constexpr size_t smem = sizeof(double2) * (size_t)XT * xpass::zp_pitch<N, XT>();
   constexpr int MINB = smem * 5 <= 220 * 1024 ? 5 : 4;
   const double2* tw = nullptr;
   int st = trvb_twiddle_table(sub, N, &tw);

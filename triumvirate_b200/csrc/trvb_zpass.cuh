@@ -144,16 +144,26 @@ template <int N> XP_HD int pos_of_freq(int k) {
   return pos;
 }
 
-// Row pitch of the tile [LP][pitch] in complex elements: N + 1 is odd, so the LP rows of one
-// slot fall on distinct 16-byte bank groups.
-template <int N> XP_HD constexpr int zp_pitch() { return N + 1; }
+// Row pitch of the tile [LP][pitch] in complex elements.  A 16-byte access is served eight
+// lanes at a time, one 16-byte bank group each.  With eight or more lines per tile those
+// lanes are eight lines at one slot: an odd pitch spreads them over the eight groups.  With
+// four lines they are four lines at two slots one apart (consecutive butterflies; nine
+// apart in the unit-stride stage of 540 = 6 x 10 x 9, the same modulo 8): a pitch = 2 (mod 8)
+// puts the lines on the even groups and the second slot on the odd ones (N + 1 left every
+// access two-way conflicted: 46 % of the wavefronts at N = 540, ncu).
+template <int N, int LP> XP_HD constexpr int zp_pitch() {
+  if (LP >= 8) return N + 1;
+  int p = N + 1;
+  while (p % 8 != 2) p++;
+  return p;
+}
 
 // Load: the K2 non-zero modes of 2 LP adjacent lines -> packed complex lines in the tile.
 //   Bq = B + r K2 n1 (this (shell, plane)'s block [kz][y]); lines y0 .. y0 + 2 LP - 1.
 template <int N, int LP, int NT>
 XP_HD void zstage_load(int tid, const double2* __restrict__ Bq, int K2, int n1, int y0,
                        double2* tile) {
-  constexpr int P = zp_pitch<N>();
+  constexpr int P = zp_pitch<N, LP>();
   // slots of the frequencies K2 .. N - K2 hold zeros
   const int nzero = N - 2 * K2 + 1;
   for (int e = tid; e < nzero * LP; e += NT) {
@@ -193,7 +203,7 @@ XP_HD void zstage_load(int tid, const double2* __restrict__ Bq, int K2, int n1, 
 template <int N, int LP, int NT, int STAGE>
 XP_HD void zstage(int tid, double2* tile, const double2* tw) {
   constexpr int R = Radix<N>::r(STAGE), L = block_len<N>(STAGE), S = L / R, NB = N / R;
-  constexpr int P = zp_pitch<N>();
+  constexpr int P = zp_pitch<N, LP>();
   for (int u = tid; u < NB * LP; u += NT) {
     // lanes across the lines: the odd pitch puts the LP rows of one slot on distinct
     // 16-byte bank groups whatever the stride of the stage (lanes along the butterflies of
@@ -221,7 +231,7 @@ template <int N, int LP, int NT>
 XP_HD void zstage_store(int tid, const double2* tile, const double2* tw, int n1, int y0,
                         double* __restrict__ out_r) {
   constexpr int R = Radix<N>::r(0), S = N / R;
-  constexpr int P = zp_pitch<N>();
+  constexpr int P = zp_pitch<N, LP>();
   for (int u = tid; u < S * LP; u += NT) {
     const int j = u / S, p = u % S;
     const double2* line = tile + j * P + p;
@@ -258,7 +268,7 @@ XP_HD void zstage_store(int tid, const double2* tile, const double2* tw, int n1,
 template <int N, int XT, int NT>
 XP_HD void ystage_load(int tid, const double2* __restrict__ Aqc, int K1, int mc1, int n0, int xs,
                        int xe /* one past the last valid x */, double2* tile) {
-  constexpr int P = zp_pitch<N>();
+  constexpr int P = zp_pitch<N, XT>();
   // frequencies mc1 + 1 .. N - mc1 - 1 are zero
   const int nzero = N - K1;
   for (int e = tid; e < nzero * XT; e += NT) {
@@ -291,7 +301,7 @@ template <int N, int XT, int NT>
 XP_HD void ystage_store(int tid, const double2* tile, const double2* tw, int xi0, int nx,
                         long long row_stride, double2* __restrict__ Bq) {
   constexpr int R = Radix<N>::r(0), S = N / R;
-  constexpr int P = zp_pitch<N>();
+  constexpr int P = zp_pitch<N, XT>();
   for (int u = tid; u < S * XT; u += NT) {
     const int j = u / S, p = u % S;
     const double2* line = tile + j * P + p;
