@@ -145,3 +145,12 @@ def test_pruned_c2c_y_pass_matches_numpy(yharness, tmp_path, n):
         F[:, (b - mc1) % n] = A[b, x0:x0 + nx]
     want = np.fft.ifft(F, axis=1) * n
     assert np.max(np.abs(out - want)) < 1.e-13 * np.max(np.abs(want))
+
+
+def test_library_reports_the_same_z_pass_lengths():
+    """trvb_shell_zpass_supported (a host-only query of libtrvb.so) agrees with the list the
+    emulation covers, and nothing else in 2 .. 800 is claimed."""
+    from triumvirate_b200 import _lib
+    lib = _lib.trvb()
+    got = [n for n in range(2, 801) if lib.trvb_shell_zpass_supported(n) == 1]
+    assert got == ZPASS_LENGTHS
