@@ -639,7 +639,10 @@ def xpass_roofline(core, step, dpos, wl):
     achieved = alg_bytes / (kern * 1.e-3) / 1.e9
     return {"bound": "hbm", "kernel": "k_xpass_fused<%d> (+ 24 MB low-|k| zero-fill)" % ng,
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "peak_source": how, "algorithmic_bytes_per_launch": alg_bytes,
+            "traffic": (1078631000. + 1044100000.) if ng == 512 else None,
+            "traffic_source": ("profiles/r02_ncu_full_k_xpass_fused_async.csv (dram__bytes_read + "
+                               "dram__bytes_write of one launch at 512^3)" if ng == 512 else None),
+            "peak_source": how, "algorithmic_bytes_per_launch": alg_bytes,
             "launch_seconds": kern * 1.e-3,
             "cufft_2d_d2z_seconds": d2z * 1.e-3, "cufft_2d_z2d_seconds": z2d * 1.e-3}
 
